@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- BPR SGD triplets/s (headline) and top-N ranked users/s on B200.
+
+    python bench.py [--gpus N --steps K --warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K --warmup W]    # the reference's CPU path
+
+A *step* is one SGD epoch of the hot path (recommender/cf/BPR.py:42-58) over the whole
+synthetic play log of BASELINE.json configs[1] (C2: 1 M users x 200 K tracks x 50 M plays,
+d = 64) resident in HBM; at N > 1 every rank owns its own C2-shaped user shard (weak scaling),
+Q is replicated and the ranks reconcile Q deltas with one NCCL all-reduce per step
+(SURVEY.md section 8e).  `value` times K steps on the device (CUDA events on the library's
+stream, max over ranks).  `e2e` times the same step through the host-facing C ABI with host
+buffers: upload of the log and of P/Q from pinned memory, one epoch, download of P/Q and the loss.
+`roofline` is the SGD kernel against the measured HBM copy bandwidth with the algorithmic bytes
+of SURVEY.md 8(d): 6*d*4 + 12 = 1548 B per triplet at d = 64.  `cpu_baseline` / `--impl
+reference` time the oracle's port of the reference's numpy loop (the reference ships that loop
+commented out and has nothing to compile) on the host cores.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bpr_sgd_triplets_per_sec"
+UNIT = "triplets/s"
+SEED = 20260103            # SEED_BASE + config# (C2 -> 2, +1 so that rank offsets never collide with C1)
+LR, REG_U, REG_I = 0.02, 0.01, 0.01          # config/BPR.conf
+D = 64
+BYTES_PER_TRIPLET = 6 * D * 4 + 12
+
+
+def workload(small):
+    if small:
+        return dict(name="C2-small (debug)", users=50_000, tracks=20_000, plays=2_000_000)
+    return dict(name="C2: BPR d=64, 1M users x 200K tracks x 50M plays (synthetic power-law log)",
+                users=1_000_000, tracks=200_000, plays=50_000_000)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1551.4)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's port of BPR.py:31-62 on a bounded sample
+# ------------------------------------------------------------------------------------------
+def cpu_sample(log, n_triplets, d, seed):
+    """A user-strided sample (keeps the degree mix) of about n_triplets events, as a sub-log."""
+    from yue_b200 import synth
+    deg = np.diff(log.ev_indptr)
+    stride = max(1, int(log.train_size / max(n_triplets, 1)))
+    users = np.arange(stride // 2, log.m, stride)
+    keep_ev = np.concatenate([np.arange(log.ev_indptr[u], log.ev_indptr[u + 1]) for u in users])
+    keep_uq = np.concatenate([np.arange(log.uq_indptr[u], log.uq_indptr[u + 1]) for u in users])
+    ev_indptr = np.concatenate([[0], np.cumsum(deg[users])]).astype(np.int64)
+    uq_indptr = np.concatenate([[0], np.cumsum(np.diff(log.uq_indptr)[users])]).astype(np.int64)
+    P, Q = synth.init_factors(len(users), log.n, d, seed)
+    return dict(ev_user=np.repeat(np.arange(len(users), dtype=np.int32), deg[users]),
+                ev_items=log.ev_items[keep_ev], uq_indptr=uq_indptr, uq_items=log.uq_items[keep_uq],
+                P=P, Q=Q, n=log.n, T=int(len(keep_ev)))
+
+
+def cpu_epoch(sample, epoch):
+    """One pass of the reference loop (oracle port: float32 numpy rows, Python scalars, per-triplet
+    rejection sampling) -- 1 thread, the loop is inherently serial."""
+    from oracle import bpr_ref, philox
+    t0 = time.perf_counter()
+    neg = philox.sample_negatives(SEED, epoch, sample["ev_user"], sample["n"], sample["uq_indptr"], sample["uq_items"])
+    bpr_ref.sgd_epoch(sample["P"], sample["Q"], sample["ev_user"], sample["ev_items"], neg, LR, REG_U, REG_I)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from yue_b200 import synth
+    wl = workload(args.small)
+    per_step = 60_000                      # ~1.5-2 s of CPU per step at ~4e4 triplets/s
+    log = synth.power_law_log_torch(wl["users"], wl["tracks"], wl["plays"], SEED) \
+        if not args.small else synth.power_law_log(wl["users"], wl["tracks"], wl["plays"], SEED, test_ratio=0)
+    sample = cpu_sample(log, per_step, D, SEED)
+    for w in range(args.warmup):
+        cpu_epoch(sample, w)
+    t = sum(cpu_epoch(sample, args.warmup + k) for k in range(args.steps))
+    value = sample["T"] * args.steps / t
+    desc = "%d-triplet user-strided sample of the workload per step, oracle port of BPR.py:31-62" % sample["T"]
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "d": D, "lr": LR, "reg": [REG_U, REG_I]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from yue_b200 import synth
+    from yue_b200.engine import (MODE_HOGWILD, MODE_HOGWILD_STORE, RANK_AUTO, RANK_EXACT, RANK_TC, Engine,
+                                 PinnedArray)
+    from yue_b200._lib import BUF_Q_DELTA
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = workload(args.small)
+    mode = MODE_HOGWILD_STORE if args.sgd_mode == "store" else MODE_HOGWILD
+    hbm_peak, bf16_peak, peak_kind = peaks()
+
+    eng = Engine(local)
+    log = synth.power_law_log_torch(wl["users"], wl["tracks"], wl["plays"], SEED + rank, device="cuda")
+    T = log.train_size
+    m, n = log.m, log.n
+    torch.cuda.empty_cache()
+    pP, pQ = PinnedArray((m, D), np.float32), PinnedArray((n, D), np.float32)
+    P0, Q0 = synth.init_factors(m, n, D, SEED + 1000 + rank)
+    if world > 1:                                   # Q is replicated: same init everywhere
+        Q0 = synth.init_factors(1, n, D, SEED + 999)[1]
+    pP.array[:], pQ.array[:] = P0, Q0
+    user_begin, event_base = rank * m, rank * T     # weak scaling: rank r owns users [r*m, (r+1)*m)
+
+    def upload():
+        eng.set_interactions(m, n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items,
+                             user_begin=user_begin, event_base=event_base)
+        eng.set_factors(pP.array, pQ.array)
+
+    upload()
+    delta_t = ext_stream = None
+    if world > 1:
+        eng.q_snapshot()
+        ptr, nbytes = eng.device_buffer(BUF_Q_DELTA)
+
+        class _Cai:                                 # alias the library's delta buffer as a tensor
+            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        delta_t = torch.as_tensor(_Cai(), device=torch.device("cuda", local))
+        ext_stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=torch.device("cuda", local))
+
+    def step(epoch, want_loss=False):
+        loss = eng.bpr_epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
+        if world > 1:                               # the real exchange step of the sharded path
+            eng.q_delta_pack()
+            with torch.cuda.stream(ext_stream):     # NCCL ordered on the library's stream
+                dist.all_reduce(delta_t)
+            eng.q_delta_apply()
+        return loss
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- value: K steps, inputs resident in HBM ---------------------------------------------
+    for w in range(args.warmup):
+        step(w)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count()
+    eng.timer_start()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    ms = eng.timer_stop()
+    barrier()
+    launches = eng.launch_count() - l0
+    ms_t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    value = T * world * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel alone (no collective): per-launch duration for the roofline --------
+    kms = []
+    for k in range(max(3, min(args.steps, 10))):
+        eng.sync()
+        eng.timer_start()
+        eng.bpr_epoch(LR, REG_U, REG_I, SEED, 1000 + k, mode, want_loss=False)
+        kms.append(eng.timer_stop())
+    clk = clocks.stop() if rank == 0 else None
+    k_ms = float(np.mean(kms))
+    achieved = BYTES_PER_TRIPLET * T / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("bpr_sgd_kernel_dram_bytes_per_launch")
+
+    # ---- e2e: same step through the C ABI with host buffers ---------------------------------
+    h2d = log.ev_indptr.nbytes + log.ev_items.nbytes + log.uq_indptr.nbytes + log.uq_items.nbytes + pP.nbytes + pQ.nbytes
+    d2h = pP.nbytes + pQ.nbytes + 8
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    eng.timer_start()
+    for k in range(e2e_steps):
+        upload()
+        if world > 1:
+            eng.q_snapshot()
+        loss = step(2000 + k, want_loss=True)
+        p2, q2 = eng.frob2()
+        eng.get_factors(pP.array, pQ.array)
+        loss += REG_U * p2 + REG_I * q2
+    e2e_ms = eng.timer_stop()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, e2e_wall)                  # host-side work between copies counts too
+    e_t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+    e2e_value = T * world * e2e_steps / (float(e_t.item()) * 1e-3)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "d": D, "triplets_per_step_per_gpu": T, "lr": LR,
+                       "reg": [REG_U, REG_I], "sgd_mode": "hogwild_" + ("store" if mode == MODE_HOGWILD_STORE else "atomic_delta"),
+                       "l2": "inputs exceed L2 (P 256 MB + log 400 MB per step; Q 51 MB is L2-resident by nature)",
+                       "parallelism": "user-sharded, Q replicated, 1 all-reduce of dQ per step" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "what": "set_interactions + set_factors (pinned) + bpr_epoch + frob2 + get_factors"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "kernel": "bpr_sgd_kernel", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": BYTES_PER_TRIPLET * T},
+            "final_loss": loss,
+        }
+
+    # ---- secondary metric: full-catalog masked top-10 (config C4 shape, bounded user block) --
+    if not args.no_rank and world == 1:
+        out["ranking"] = bench_ranking(eng, args, bf16_peak)
+
+    # ---- cpu_baseline (rank 0, N = 1 only) -----------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = cpu_sample(log, 400_000 if not args.small else 40_000, D, SEED)
+        t = cpu_epoch(sample, 0)
+        out["cpu_baseline"] = {"value": sample["T"] / t, "unit": UNIT, "cores": 1, "kind": "port",
+                               "host_cores": os.cpu_count(),
+                               "sample": "%d-triplet user-strided sample of the same log, one epoch of the oracle "
+                                         "port of BPR.py:31-62 (float32 numpy rows, serial)" % sample["T"]}
+    if rank == 0:
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_ranking(eng, args, bf16_peak):
+    """Top-10 of a user block against a 2M-track catalog (C4 shape), users/s on one GPU."""
+    from yue_b200 import synth
+    from yue_b200.engine import RANK_AUTO
+    n = 2_000_000 if not args.small else 100_000
+    B = args.rank_users
+    m = B
+    indptr, uq = synth.mask_csr(m, n, 50, SEED + 4)
+    P, Q = synth.init_factors(m, n, D, SEED + 4)
+    eng.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), indptr, uq)
+    eng.set_factors(P, Q)
+    users = np.arange(B, dtype=np.int32)
+    eng.rank_topn(users[:256], 10, RANK_AUTO)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        eng.rank_topn(users, 10, RANK_AUTO)
+        times.append(time.perf_counter() - t0)
+    t = min(times)
+    flops = 2.0 * B * n * D
+    return {"metric": "topn_ranked_users_per_sec", "value": B / t, "unit": "users/s",
+            "workload": "C4 shape: top-10 of %d users x %d tracks, d=64, ~50 masked tracks/user" % (B, n),
+            "seconds": t, "dense_tflops": flops / t / 1e12, "frac_of_bf16_peak": flops / t / 1e12 / bf16_peak,
+            "includes": "H2D of user ids, D2H of ids+scores"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--small", action="store_true", help="debug-size workload (not a bench number)")
+    ap.add_argument("--sgd-mode", default="atomic", choices=["atomic", "store"])
+    ap.add_argument("--no-rank", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rank-users", type=int, default=8192)
+    args = ap.parse_args()
+    if args.warmup < 3 and not args.small:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

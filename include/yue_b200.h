@@ -1,0 +1,149 @@
+/* yue_b200.h -- C ABI of the B200-native BPR hot path (libyue_b200.so).
+ *
+ * The reference (0411tony/Yue) is pure Python and has NO FFI of its own; this is the thin
+ * boundary a maintainer binds with ctypes from recommender/cf/BPR.py.
+ * Each entry point names the reference code it replaces (paths relative to the reference
+ * tree).  Conventions: every function returns 0 on success or a YUE_E_* code, with a
+ * message available from yue_last_error(); the caller owns every host buffer, the library
+ * owns every device buffer; no global mutable state; one host thread per handle, distinct
+ * handles are independent; plain pointers and sizes only.
+ *
+ * Array form of the play log (built from data/record.py's Record by the host side):
+ *   ev_indptr[m+1] int64, ev_items[T] int32   every training event, user-major in user-id
+ *        order (= first-appearance order, recommender/cf/BPR.py:42), file order inside a
+ *        user, repeat plays kept (BPR.py:44-45).  One BPR triplet per event.
+ *   uq_indptr[m+1] int64, uq_items[nnz] int32  per-user SORTED UNIQUE played tracks
+ *        (= userListen, BPR.py:32-35): the sampler's rejection set and the ranking mask
+ *        (base/IterativeRecommender.py:102-106).
+ * Factor tables are dense row-major float32, P[m,k] and Q[n,k]
+ * (base/IterativeRecommender.py:36-39).
+ */
+#ifndef YUE_B200_H
+#define YUE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct yue_handle yue_t;
+
+enum {
+    YUE_OK = 0,
+    YUE_E_ARG = 1,      /* bad argument / call order                                  */
+    YUE_E_CUDA = 2,     /* CUDA runtime error (message has the cudaError string)      */
+    YUE_E_STATE = 3,    /* interactions or factors not set                            */
+    YUE_E_NUMERIC = 4,  /* loss is NaN or infinite (IterativeRecommender.py:63-66)    */
+    YUE_E_NCCL = 5,
+    YUE_E_UNSUPPORTED = 6
+};
+
+/* update schedule of yue_bpr_epoch / yue_bpr_apply */
+enum {
+    YUE_MODE_SERIAL = 0,        /* one warp, events strictly in order: reproduces the
+                                   reference loop given the same negatives (parity mode) */
+    YUE_MODE_HOGWILD = 1,       /* throughput mode: contiguous event slices per warp, row
+                                   changes published as vector atomic deltas            */
+    YUE_MODE_HOGWILD_STORE = 2  /* as HOGWILD but plain stores (last writer wins)         */
+};
+
+/* algorithm of yue_rank_topn */
+enum {
+    YUE_RANK_EXACT = 0,   /* fp32 FMA-chain scores on CUDA cores, fused masked top-N      */
+    YUE_RANK_TC = 1,      /* tcgen05 tf32 candidate pass + exact fp32 re-score (same ids) */
+    YUE_RANK_AUTO = 2
+};
+
+/* which device buffer yue_device_buffer exposes (for torch.distributed plumbing) */
+enum { YUE_BUF_P = 0, YUE_BUF_Q = 1, YUE_BUF_Q_DELTA = 2, YUE_BUF_Q_SNAPSHOT = 3 };
+
+const char* yue_version(void);
+const char* yue_last_error(const yue_t* h);          /* h may be NULL: last create error */
+
+int yue_create(int device, yue_t** out);
+int yue_destroy(yue_t* h);
+int yue_sync(yue_t* h);
+
+/* pinned host memory, so the P/Q/ids arrays the Python class exposes can be DMA targets */
+int yue_host_alloc(size_t bytes, void** out);
+int yue_host_free(void* p);
+
+/* Replaces the userListen build and the epoch iteration order, BPR.py:32-45 (id-keyed
+ * variant BPR.py:84-91).  The shard form is for user-sharded multi-GPU runs: this handle
+ * owns users [user_begin, user_begin + m_local); event_base is the global index of its first
+ * event (the sampler stream is a function of the GLOBAL event index, so samples do not
+ * depend on the sharding).  yue_set_interactions == shard with user_begin = event_base = 0. */
+int yue_set_interactions(yue_t* h, int64_t m, int64_t n,
+                         const int64_t* ev_indptr, const int32_t* ev_items,
+                         const int64_t* uq_indptr, const int32_t* uq_items);
+int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n,
+                               int64_t user_begin, int64_t event_base,
+                               const int64_t* ev_indptr, const int32_t* ev_items,
+                               const int64_t* uq_indptr, const int32_t* uq_items);
+
+/* Replaces IterativeRecommender.initModel's tables (IterativeRecommender.py:36-39) on the
+ * device: P is [m_local,k], Q is [n,k].  get copies the current tables back (either pointer
+ * may be NULL) -- buildModel leaves self.P / self.Q on the host (BPR.py:127-128). */
+int yue_set_factors(yue_t* h, int k, const float* P, const float* Q);
+int yue_get_factors(yue_t* h, float* P, float* Q);
+
+/* Replaces `choice(itemList)` + redraw-while-played, BPR.py:46-49 (BPR.py:73-76,
+ * recommender/advanced/APR.py:104-107).  Writes the accepted negative of every local event
+ * for (seed, epoch, slot); bit-exact with oracle/philox.py.  Check hook: the epoch kernels
+ * sample in-register and never materialise this array. */
+int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot,
+                         int32_t* j_out);
+
+/* Replaces one pass of the SGD loop body, BPR.py:42-58, over every local event, negatives
+ * drawn in-kernel.  *loss_out (may be NULL: no host sync) receives sum of -log(s), BPR.py:58;
+ * the caller adds regU*|P|^2 + regI*|Q|^2 from yue_frob2 (BPR.py:59) and runs the lr
+ * schedule (IterativeRecommender.py:47-75) on the host. */
+int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI,
+                  uint64_t seed, uint32_t epoch, int mode, double* loss_out);
+
+/* Same update on a caller-supplied triplet stream (parity hook for the "same triplet
+ * stream" check of north_star; also the building block for APR-style batches). */
+int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T,
+                  double lr, double regU, double regI, int mode, double* loss_out);
+
+/* (P*P).sum(), (Q*Q).sum() of BPR.py:59, accumulated in float64. */
+int yue_frob2(yue_t* h, double* p2, double* q2);
+
+/* Replaces predict, BPR.py:131-134 / IterativeRecommender.py:58-60: scores[n] = Q.P[user]
+ * as the canonical float32 FMA chain k = 0..d-1.  `user` is a local user index. */
+int yue_predict(yue_t* h, int64_t user, float* scores_out);
+
+/* Replaces the per-user body of evalRanking, IterativeRecommender.py:93-145: score every
+ * track, drop the user's training tracks, keep the N best.  Output order is (score desc,
+ * track id asc) -- exact top-N, see DESIGN.md for why the reference's lossy selection is not
+ * reproduced.  ids_out/scores_out are [B,N]; rows with fewer than N unmasked tracks are
+ * padded with -1 / -inf.  users[] are local user indices. */
+int yue_rank_topn(yue_t* h, const int32_t* users, int64_t B, int N, int algo,
+                  int32_t* ids_out, float* scores_out);
+
+/* ---- multi-GPU: user-sharded SGD with Q replicated; once per sub-epoch
+ *      Q <- Q_snapshot + sum_over_ranks(Q_rank - Q_snapshot).  No reference counterpart
+ *      (the reference has no collective anywhere). ---- */
+int yue_q_snapshot(yue_t* h);       /* snapshot <- Q                                        */
+int yue_q_delta_pack(yue_t* h);     /* delta <- Q - snapshot                                */
+int yue_q_delta_apply(yue_t* h);    /* Q <- snapshot + delta (after the reduction); snapshot <- Q */
+int yue_device_buffer(yue_t* h, int which, void** dev_ptr, size_t* bytes);
+int yue_stream(yue_t* h, void** cuda_stream);
+/* NCCL path for non-Python hosts: id is an ncclUniqueId (128 bytes) from yue_comm_unique_id
+ * on rank 0, distributed by the caller. */
+int yue_comm_unique_id(void* id128);
+int yue_comm_init(yue_t* h, int nranks, int rank, const void* id128);
+int yue_allreduce_q_delta(yue_t* h);   /* pack + ncclAllReduce(sum, fp32) + apply            */
+
+/* ---- measurement hooks (bench.py): CUDA events on the handle's stream, launch counter ---- */
+int yue_timer_start(yue_t* h);
+int yue_timer_stop(yue_t* h, float* ms);
+int yue_launch_count(yue_t* h, int64_t* n);
+int yue_flush_l2(yue_t* h);            /* overwrite a >L2-sized scratch buffer              */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YUE_B200_H */

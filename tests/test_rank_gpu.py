@@ -1,0 +1,98 @@
+"""GPU parity of full-catalog scoring + masked top-N (K3/K5) against the oracle: ids bit-exact
+(ties broken by track id), scores bit-exact for the canonical FMA chain and within 1e-3 relative
+of numpy's dot."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import topn
+from yue_b200 import synth
+from yue_b200.engine import RANK_EXACT
+
+pytestmark = pytest.mark.gpu
+
+
+def check(engine, P, Q, users, N, uq_indptr, uq_items, algo):
+    ids, sc = engine.rank_topn(users, N, algo)
+    rid, rsc = topn.topn_exact(P, Q, users, N, uq_indptr, uq_items)
+    assert np.array_equal(ids, rid)
+    assert np.array_equal(sc, rsc)
+    return ids, sc
+
+
+def test_golden_eval_ids(engine, golden_dir):
+    e = np.load(os.path.join(golden_dir, "eval_small.npz"))
+    mj = json.load(open(os.path.join(golden_dir, "measure_small.json")))
+    m, n = e["P"].shape[0], e["Q"].shape[0]
+    z = np.zeros(m + 1, np.int64)
+    engine.set_interactions(m, n, z, np.zeros(0, np.int32), e["uq_indptr"], e["uq_items"])
+    engine.set_factors(e["P"], e["Q"])
+    ids, sc = engine.rank_topn(e["test_users"], 10, RANK_EXACT)
+    assert ids.tolist() == mj["exact_ids"]
+    blas = e["blas_scores"]
+    for b in range(40):
+        assert np.allclose(sc[b], blas[b][ids[b]], rtol=1e-3, atol=1e-7)
+    s0 = engine.predict(int(e["test_users"][0]))
+    assert np.array_equal(s0, topn.scores_fma32(e["P"][e["test_users"][:1]], e["Q"])[0])
+
+
+@pytest.mark.parametrize("d,N,n", [(10, 5, 777), (64, 10, 5000), (64, 20, 3001), (128, 32, 1500), (36, 100, 1200)])
+def test_exact_topn_shapes(engine, d, N, n):
+    m = 300
+    log = synth.power_law_log(m, n, 12000, seed=d + N)
+    P, Q = synth.init_factors(m, n, d, seed=N)
+    rng = np.random.default_rng(1)
+    P = (P - 0.05) * rng.uniform(0.5, 3.0, (m, 1)).astype(np.float32)     # mixed signs and scales
+    Q = (Q - 0.05).astype(np.float32)
+    engine.set_interactions(m, n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    engine.set_factors(P, Q)
+    users = rng.permutation(m)[:211].astype(np.int32)                      # ragged last block
+    check(engine, P, Q, users, N, log.uq_indptr, log.uq_items, RANK_EXACT)
+
+
+def test_ties_break_by_track_id_and_padding(engine):
+    m, n, d, N = 4, 40, 8, 10
+    P = np.ones((m, d), np.float32)
+    Q = np.zeros((n, d), np.float32)
+    Q[:, 0] = np.repeat(np.arange(8), 5)[::-1]          # 5-way ties, descending blocks
+    uq_rows = [np.array([], np.int32), np.arange(0, 35, dtype=np.int32), np.arange(n, dtype=np.int32)[:-3], np.array([0, 1, 2], np.int32)]
+    uq_indptr = np.concatenate([[0], np.cumsum([len(r) for r in uq_rows])]).astype(np.int64)
+    uq_items = np.concatenate(uq_rows).astype(np.int32)
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), uq_indptr, uq_items)
+    engine.set_factors(P, Q)
+    ids, sc = check(engine, P, Q, np.arange(m, dtype=np.int32), N, uq_indptr, uq_items, RANK_EXACT)
+    assert ids[0].tolist() == list(range(10))            # ties -> ascending id
+    assert ids[1].tolist() == [35, 36, 37, 38, 39, -1, -1, -1, -1, -1]
+    assert ids[2].tolist()[:3] == [37, 38, 39] and (ids[2][3:] == -1).all() and np.isneginf(sc[2][3:]).all()
+
+
+def test_adversarial_orders(engine):
+    """Ascending scores make every new tile beat the running threshold (worst case for the buffers)."""
+    m, n, d, N = 130, 4000, 16, 20
+    rng = np.random.default_rng(3)
+    P = np.abs(rng.normal(size=(m, d))).astype(np.float32)
+    base = np.abs(rng.normal(size=d)).astype(np.float32)
+    Q = (base[None, :] * (1.0 + np.arange(n)[:, None] * 1e-3)).astype(np.float32)
+    uq_indptr = np.zeros(m + 1, np.int64)
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), uq_indptr, np.zeros(0, np.int32))
+    engine.set_factors(P, Q)
+    check(engine, P, Q, np.arange(m, dtype=np.int32), N, uq_indptr, np.zeros(0, np.int32), RANK_EXACT)
+    Qd = np.ascontiguousarray(Q[::-1])
+    engine.set_factors(P, Qd)
+    check(engine, P, Qd, np.arange(m, dtype=np.int32), N, uq_indptr, np.zeros(0, np.int32), RANK_EXACT)
+
+
+def test_rank_block_sharding_concatenates(engine):
+    """Ranking shards by user block: any split of the user list gives the same rows."""
+    m, n, d, N = 500, 2500, 64, 10
+    log = synth.power_law_log(m, n, 20000, seed=9)
+    P, Q = synth.init_factors(m, n, d, seed=9)
+    engine.set_interactions(m, n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    engine.set_factors(P, Q)
+    users = np.arange(m, dtype=np.int32)
+    full, fs = engine.rank_topn(users, N, RANK_EXACT)
+    parts = [engine.rank_topn(users[a:b], N, RANK_EXACT) for a, b in [(0, 130), (130, 131), (131, 500)]]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), fs)

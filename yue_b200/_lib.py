@@ -1,0 +1,104 @@
+"""ctypes binding of libyue_b200.so (include/yue_b200.h).  There is no fallback: if the CUDA
+library is missing or does not load, importing the product path raises."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_DIR = os.path.join(HERE, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libyue_b200.so")
+SRC = os.path.join(HERE, "csrc", "yue_b200.cu")
+HEADER = os.path.join(ROOT, "include", "yue_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and \
+            os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, SRC, "-ldl"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class YueError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("yue_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+E_ARG, E_CUDA, E_STATE, E_NUMERIC, E_NCCL, E_UNSUPPORTED = 1, 2, 3, 4, 5, 6
+MODE_SERIAL, MODE_HOGWILD, MODE_HOGWILD_STORE = 0, 1, 2
+RANK_EXACT, RANK_TC, RANK_AUTO = 0, 1, 2
+BUF_P, BUF_Q, BUF_Q_DELTA, BUF_Q_SNAPSHOT = 0, 1, 2, 3
+
+_i64p, _i32p, _f32p, _f64p = (C.POINTER(t) for t in (C.c_int64, C.c_int32, C.c_float, C.c_double))
+_H = C.c_void_p
+
+# name -> (restype, argtypes); kept in step with include/yue_b200.h (tests/test_abi.py checks it)
+SIGNATURES = {
+    "yue_version": (C.c_char_p, []),
+    "yue_last_error": (C.c_char_p, [_H]),
+    "yue_create": (C.c_int, [C.c_int, C.POINTER(_H)]),
+    "yue_destroy": (C.c_int, [_H]),
+    "yue_sync": (C.c_int, [_H]),
+    "yue_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "yue_host_free": (C.c_int, [C.c_void_p]),
+    "yue_set_interactions": (C.c_int, [_H, C.c_int64, C.c_int64, _i64p, _i32p, _i64p, _i32p]),
+    "yue_set_interactions_shard": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                             _i64p, _i32p, _i64p, _i32p]),
+    "yue_set_factors": (C.c_int, [_H, C.c_int, _f32p, _f32p]),
+    "yue_get_factors": (C.c_int, [_H, _f32p, _f32p]),
+    "yue_sample_negatives": (C.c_int, [_H, C.c_uint64, C.c_uint32, C.c_uint32, _i32p]),
+    "yue_bpr_epoch": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
+                                C.c_int, _f64p]),
+    "yue_bpr_apply": (C.c_int, [_H, _i32p, _i32p, _i32p, C.c_int64, C.c_double, C.c_double,
+                                C.c_double, C.c_int, _f64p]),
+    "yue_frob2": (C.c_int, [_H, _f64p, _f64p]),
+    "yue_predict": (C.c_int, [_H, C.c_int64, _f32p]),
+    "yue_rank_topn": (C.c_int, [_H, _i32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p]),
+    "yue_q_snapshot": (C.c_int, [_H]),
+    "yue_q_delta_pack": (C.c_int, [_H]),
+    "yue_q_delta_apply": (C.c_int, [_H]),
+    "yue_device_buffer": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "yue_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "yue_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "yue_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "yue_allreduce_q_delta": (C.c_int, [_H]),
+    "yue_timer_start": (C.c_int, [_H]),
+    "yue_timer_stop": (C.c_int, [_H, _f32p]),
+    "yue_launch_count": (C.c_int, [_H, _i64p]),
+    "yue_flush_l2": (C.c_int, [_H]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it first when sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "yue_b200: %s is missing.  Build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (needs nvcc); there is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,298 @@
+// K1+K2: fused negative sampler + BPR triplet update (replaces recommender/cf/BPR.py:42-58).
+//
+// Work decomposition.  Events are stored user-major (BPR.py:42-45).  The host cuts every
+// user's event range into SEGMENTS of <= 32 consecutive events (one user per segment) and
+// gives every warp a CONTIGUOUS slice of segments holding ~T/W events.  A warp walks its
+// slice in order, so
+//   * P[u] lives in registers while the warp stays on user u and is published once when the
+//     user changes: P traffic is ~2 rows per USER instead of 2 per triplet, and a user that
+//     lies inside one slice sees exactly the serial update order of the reference;
+//   * only slice-boundary users and the shared Q rows are touched by several warps.
+// Per segment the 32 lanes first draw the negatives of 32 events in parallel (Philox +
+// rejection against the user's sorted play row), then the warp applies the 32 updates one
+// after the other with the next PF row pairs already in flight.
+//
+// Row access.  A row is ld floats (ld % 4 == 0).  The lower half-warp owns Q[i], the upper
+// half-warp owns Q[j]: ONE warp-wide 128-bit load (LDG.E.128) fetches both rows of a triplet
+// and one 128-bit store / vector atomic (REDG.E.ADD.F32x4) publishes both.  Lane l of a half
+// holds float4 chunks l, l+16, ... (NCH of them), so d = 64 is exactly one float4 per lane.
+//
+// Update order inside a triplet is the reference's: dots with the old
+// rows; P[u] += g(Qi - Qj); Q[i] += g P[u]_new; Q[j] -= g P[u]_new; then the three
+// multiplicative shrinks; loss uses the pre-update s.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "philox.cuh"
+
+namespace yue {
+
+enum : int { kSerial = 0, kAtomic = 1, kStore = 2 };
+
+struct SgdParams {
+    float* P;                      // [m_local, ld]
+    float* Q;                      // [n, ld]
+    int ld;                        // row stride in floats, multiple of 4
+    int nchunks;                   // ld / 4
+    uint32_t n_items;
+    const int64_t* seg_begin;      // [nseg] first local event of the segment
+    const int32_t* seg_user;       // [nseg] local user
+    const int32_t* seg_len;        // [nseg] 1..32
+    const int64_t* warp_seg;       // [n_warps+1] segment slice per warp
+    int n_warps;
+    const int32_t* ev_items;       // [T] positives
+    const int32_t* ev_neg;         // [T] negatives, or nullptr -> sample in-kernel
+    const int64_t* uq_indptr;      // [m_local+1]
+    const int32_t* uq_items;
+    uint64_t seed;
+    uint32_t epoch;
+    int64_t event_base;            // global index of local event 0
+    float lr, c_u, c_i;            // lr, float(lr*regU), float(lr*regI)
+    double lr_d;
+    double* loss;                  // device accumulator of sum -log(s)
+};
+
+__device__ __forceinline__ float4 ld_row(const float* p) {
+    return __ldcg(reinterpret_cast<const float4*>(p));      // L2 only: rows are shared, L1 would go stale
+}
+__device__ __forceinline__ void st_row(float* p, float4 v) {
+    __stcg(reinterpret_cast<float4*>(p), v);
+}
+__device__ __forceinline__ void red_row(float* p, float4 v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
+    v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+    v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+    v.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+    v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+    return v;
+}
+
+template <int NCH, int MODE>
+struct RowOps {
+    // p = p + g*d (serial: two roundings like numpy's `row += scalar * row`; else one FMA)
+    static __device__ __forceinline__ float axpy(float g, float d, float p) {
+        if (MODE == kSerial) return __fadd_rn(p, __fmul_rn(g, d));
+        return fmaf(g, d, p);
+    }
+    static __device__ __forceinline__ float4 axpy4(float g, float4 d, float4 p) {
+        return make_float4(axpy(g, d.x, p.x), axpy(g, d.y, p.y), axpy(g, d.z, p.z), axpy(g, d.w, p.w));
+    }
+};
+
+template <int NCH, int MODE, int PF>
+__global__ void __launch_bounds__(256) bpr_sgd_kernel(const SgdParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (warp >= p.n_warps) return;
+    const int half = lane >> 4;
+    const int l16 = lane & 15;
+    const int64_t sb = p.warp_seg[warp], se = p.warp_seg[warp + 1];
+    using R = RowOps<NCH, MODE>;
+
+    bool act[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) act[c] = (l16 + 16 * c) < p.nchunks;
+    const int lane_off = 4 * l16;
+
+    float4 pu[NCH], pu0[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) pu[c] = pu0[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur_u = -1;
+    const int32_t* row = nullptr;
+    int row_len = 0;
+    double loss = 0.0;
+
+    auto flush_user = [&]() {
+        if (cur_u < 0 || half != 0) return;
+        float* dst = p.P + (size_t)cur_u * p.ld + lane_off;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (!act[c]) continue;
+            if (MODE == kAtomic)
+                red_row(dst + 64 * c, make_float4(pu[c].x - pu0[c].x, pu[c].y - pu0[c].y,
+                                                  pu[c].z - pu0[c].z, pu[c].w - pu0[c].w));
+            else
+                st_row(dst + 64 * c, pu[c]);
+        }
+    };
+
+    for (int64_t seg = sb; seg < se; ++seg) {
+        const int u = p.seg_user[seg];
+        const int64_t begin = p.seg_begin[seg];
+        const int len = p.seg_len[seg];
+        if (u != cur_u) {
+            flush_user();
+            if (MODE == kSerial) __syncwarp();
+            cur_u = u;
+            const float* src = p.P + (size_t)u * p.ld + lane_off;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                pu[c] = act[c] ? ld_row(src + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pu0[c] = pu[c];
+            }
+            const int64_t r0 = p.uq_indptr[u];
+            row = p.uq_items + r0;
+            row_len = (int)(p.uq_indptr[u + 1] - r0);
+        }
+
+        // ---- K1: lane t draws the negative of event begin+t -------------------------------
+        int32_t my_i = 0, my_j = 0;
+        if (lane < len) {
+            const int64_t e = begin + lane;
+            my_i = p.ev_items[e];
+            my_j = p.ev_neg ? p.ev_neg[e]
+                            : sample_negative(p.seed, p.epoch, (uint64_t)(p.event_base + e), 0u,
+                                              p.n_items, row, row_len);
+        }
+        __syncwarp();
+
+        // ---- K2: the updates, one after the other, PF row pairs in flight -----------------
+        auto row_ptr = [&](int t) -> float* {
+            const int32_t it = __shfl_sync(0xffffffffu, my_i, t);
+            const int32_t jt = __shfl_sync(0xffffffffu, my_j, t);
+            return p.Q + (size_t)(half ? jt : it) * p.ld + lane_off;
+        };
+        float4 qb[PF][NCH];
+        float* qp[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            if (k < len) {
+                qp[k] = row_ptr(k);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    qb[k][c] = act[c] ? ld_row(qp[k] + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        for (int t0 = 0; t0 < len; t0 += PF) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int t = t0 + k;
+                if (t >= len) break;
+                float4 q[NCH];
+                float* dst = qp[k];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) q[c] = qb[k][c];
+                if (PF > 1 && t + PF < len) {          // refill this slot for event t+PF
+                    qp[k] = row_ptr(t + PF);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+                        qb[k][c] = act[c] ? ld_row(qp[k] + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // dots: each half reduces its own row, then x = P.Qi - P.Qj (BPR.py:50)
+                float part = 0.f;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    part = fmaf(pu[c].x, q[c].x, part);
+                    part = fmaf(pu[c].y, q[c].y, part);
+                    part = fmaf(pu[c].z, q[c].z, part);
+                    part = fmaf(pu[c].w, q[c].w, part);
+                }
+#pragma unroll
+                for (int m = 8; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+                const float other = __shfl_xor_sync(0xffffffffu, part, 16);
+                const float x = half ? (other - part) : (part - other);
+
+                float g;
+                if (MODE == kSerial) {          // tool/qmath.py:115-116 in float64, like CPython
+                    const double s = 1.0 / (1.0 + exp(-(double)x));
+                    g = (float)(p.lr_d * (1.0 - s));
+                    loss += -log(s);
+                } else {
+                    const float ex = __expf(-fabsf(x));              // e^{-|x|} in (0,1]
+                    const float s = (x >= 0.f ? 1.f : ex) / (1.f + ex);
+                    g = p.lr * (1.f - s);
+                    loss += (double)(fmaxf(-x, 0.f) + log1pf(ex));  // -log(s), stable
+                }
+                const float sg = half ? -g : g;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float4 o = shfl_xor4(q[c], 16);
+                    float4 d;                   // Q[i] - Q[j] on both halves (old rows, BPR.py:51)
+                    d.x = half ? (o.x - q[c].x) : (q[c].x - o.x);
+                    d.y = half ? (o.y - q[c].y) : (q[c].y - o.y);
+                    d.z = half ? (o.z - q[c].z) : (q[c].z - o.z);
+                    d.w = half ? (o.w - q[c].w) : (q[c].w - o.w);
+                    pu[c] = R::axpy4(g, d, pu[c]);
+                    float4 qn = R::axpy4(sg, pu[c], q[c]);          // uses the UPDATED P[u] (52-53)
+                    pu[c] = R::axpy4(-p.c_u, pu[c], pu[c]);         // shrinks (55-57)
+                    qn = R::axpy4(-p.c_i, qn, qn);
+                    if (act[c]) {
+                        if (MODE == kAtomic)
+                            red_row(dst + 64 * c, make_float4(qn.x - q[c].x, qn.y - q[c].y,
+                                                              qn.z - q[c].z, qn.w - q[c].w));
+                        else
+                            st_row(dst + 64 * c, qn);
+                    }
+                }
+                if (MODE == kSerial) __syncwarp();   // order this triplet's stores before the next loads
+            }
+        }
+    }
+    flush_user();
+    if (lane == 0 && loss != 0.0) atomicAdd(p.loss, loss);
+}
+
+// ---- check hook: materialise the negatives (yue_sample_negatives) -------------------------
+__global__ void sample_negatives_kernel(int64_t T, const int32_t* __restrict__ ev_user,
+                                        const int64_t* __restrict__ uq_indptr,
+                                        const int32_t* __restrict__ uq_items, uint64_t seed,
+                                        uint32_t epoch, uint32_t slot, int64_t event_base,
+                                        uint32_t n_items, int32_t* __restrict__ out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int u = ev_user[e];
+        const int64_t r0 = uq_indptr[u];
+        out[e] = sample_negative(seed, epoch, (uint64_t)(event_base + e), slot, n_items,
+                                 uq_items + r0, (int)(uq_indptr[u + 1] - r0));
+    }
+}
+
+// ---- sum of squares of a [rows, ld] table in float64 (BPR.py:59) --------------------------
+__global__ void frob2_kernel(const float* __restrict__ x, size_t count, double* out) {
+    double acc = 0.0;
+    const size_t n4 = count / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = x4[i];
+        acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sm[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        acc = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0.0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (lane == 0) atomicAdd(out, acc);
+    }
+}
+
+// ---- elementwise helpers of the multi-GPU Q reconciliation (K4) ---------------------------
+__global__ void q_delta_pack_kernel(const float4* __restrict__ q, const float4* __restrict__ snap,
+                                    float4* __restrict__ delta, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = q[i], b = snap[i];
+        delta[i] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    }
+}
+__global__ void q_delta_apply_kernel(float4* __restrict__ q, float4* __restrict__ snap,
+                                     const float4* __restrict__ delta, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const float4 b = snap[i], d = delta[i];
+        const float4 r = make_float4(b.x + d.x, b.y + d.y, b.z + d.z, b.w + d.w);
+        q[i] = r;
+        snap[i] = r;
+    }
+}
+
+}  // namespace yue

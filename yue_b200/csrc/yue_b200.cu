@@ -1,0 +1,608 @@
+// libyue_b200.so -- C ABI over the sm_100a kernels (include/yue_b200.h documents each entry
+// point and the reference code it replaces).  No torch types here; the Python host side binds
+// this with ctypes (yue_b200/_lib.py).
+#include "../../include/yue_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bpr_sgd.cuh"
+#include "rank_exact.cuh"
+#include "rank_tc.cuh"
+
+using namespace yue;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL, resolved at run time so the library has no link-time dependency ----------------
+struct NcclUniqueId { char internal[128]; };
+typedef void* ncclComm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+            err = "libnccl is missing a required symbol";
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t resize(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct yue_handle {
+    int device = 0;
+    int sm_count = 148;
+    int warps_per_sm = 32;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // play log (local shard)
+    int64_t m = 0, n = 0, T = 0, nnz = 0, user_begin = 0, event_base = 0;
+    bool have_log = false;
+    DevBuf<int64_t> ev_indptr, uq_indptr;
+    DevBuf<int32_t> ev_items, uq_items, ev_user;
+    bool have_ev_user = false;
+    std::vector<int64_t> h_ev_indptr;
+    // segments of the epoch kernels
+    int64_t nseg = 0;
+    int n_warps = 0;
+    DevBuf<int64_t> seg_begin, warp_seg, warp_seg_serial;
+    DevBuf<int32_t> seg_user, seg_len;
+
+    // factors
+    int k = 0, ld = 0;
+    bool have_factors = false;
+    DevBuf<float> P, Q, Qsnap, Qdelta;
+    bool have_snap = false;
+    DevBuf<double> scal;          // [0] loss, [1] |P|^2, [2] |Q|^2
+
+    // scratch
+    DevBuf<int32_t> tmp_i, tmp_j, tmp_su, tmp_sl, rk_users, rk_ids;
+    DevBuf<int64_t> tmp_sb, tmp_ws;
+    DevBuf<float> rk_scores, pred;
+    DevBuf<unsigned char> l2buf;
+    RankTcState tc;
+
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+#define CK(...)                                                                           \
+    do {                                                                                  \
+        cudaError_t e_ = (__VA_ARGS__);                                                   \
+        if (e_ != cudaSuccess) {                                                          \
+            h->err = std::string(#__VA_ARGS__) + ": " + cudaGetErrorString(e_);           \
+            return YUE_E_CUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+#define REQUIRE(cond, code, msg)            \
+    do {                                    \
+        if (!(cond)) { h->err = (msg); return (code); } \
+    } while (0)
+
+static int fail(yue_t* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+// Cut every user's event range into <=32-event segments and slice them evenly over n_warps.
+static void build_segments(const int64_t* indptr, int64_t m, std::vector<int64_t>& sb,
+                           std::vector<int32_t>& su, std::vector<int32_t>& sl) {
+    sb.clear(); su.clear(); sl.clear();
+    for (int64_t u = 0; u < m; ++u) {
+        for (int64_t b = indptr[u], e = indptr[u + 1]; b < e; b += 32) {
+            sb.push_back(b); su.push_back((int32_t)u); sl.push_back((int32_t)std::min<int64_t>(32, e - b));
+        }
+    }
+}
+static void slice_segments(const std::vector<int64_t>& sb, const std::vector<int32_t>& sl, int64_t T,
+                           int n_warps, std::vector<int64_t>& ws) {
+    ws.assign((size_t)n_warps + 1, (int64_t)sb.size());
+    ws[0] = 0;
+    const int64_t nseg = (int64_t)sb.size();
+    int64_t seg = 0;
+    for (int w = 1; w < n_warps; ++w) {
+        const int64_t target = (int64_t)((__int128)T * w / n_warps);   // first event of warp w
+        while (seg < nseg && sb[seg] + sl[seg] <= target) ++seg;       // segments ending before it stay left
+        ws[w] = seg;
+    }
+    ws[n_warps] = nseg;
+}
+
+// Every yue_* function below is declared extern "C" by include/yue_b200.h and inherits that linkage.
+
+const char* yue_version(void) { return "yue_b200 0.1 (sm_100a)"; }
+
+const char* yue_last_error(const yue_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int yue_create(int device, yue_t** out) {
+    if (!out) { g_create_error = "out is NULL"; return YUE_E_ARG; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return YUE_E_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "device index out of range"; return YUE_E_ARG; }
+    yue_t* h = new yue_handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+        (e = h->scal.resize(4)) != cudaSuccess) {
+        g_create_error = std::string("device setup failed: ") + cudaGetErrorString(e);
+        delete h;
+        return YUE_E_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = "yue_b200 needs an sm_100a device (B200); found sm_" + std::to_string(prop.major * 10 + prop.minor);
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return YUE_E_UNSUPPORTED;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->l2_bytes = (size_t)prop.l2CacheSize;
+    if (const char* s = getenv("YUE_SGD_WARPS_PER_SM")) h->warps_per_sm = std::max(1, atoi(s));
+    *out = h;
+    return YUE_OK;
+}
+
+int yue_destroy(yue_t* h) {
+    if (!h) return YUE_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    rank_tc_release(h->tc);
+    for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->seg_begin, &h->warp_seg, &h->warp_seg_serial, &h->tmp_sb, &h->tmp_ws}) b->release();
+    for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->seg_user, &h->seg_len, &h->tmp_i, &h->tmp_j,
+                    &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids}) b->release();
+    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->rk_scores, &h->pred}) b->release();
+    h->scal.release();
+    h->l2buf.release();
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return YUE_OK;
+}
+
+int yue_sync(yue_t* h) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+int yue_host_alloc(size_t bytes, void** out) {
+    if (!out) return YUE_E_ARG;
+    return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? YUE_OK : YUE_E_CUDA;
+}
+int yue_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? YUE_OK : YUE_E_CUDA; }
+
+int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t user_begin, int64_t event_base,
+                               const int64_t* ev_indptr, const int32_t* ev_items,
+                               const int64_t* uq_indptr, const int32_t* uq_items) {
+    REQUIRE(h && ev_indptr && uq_indptr, YUE_E_ARG, "null argument");
+    REQUIRE(m_local >= 0 && n > 0 && n < (int64_t)1 << 31 && m_local < (int64_t)1 << 31, YUE_E_ARG, "m/n out of range");
+    REQUIRE(ev_indptr[0] == 0 && uq_indptr[0] == 0, YUE_E_ARG, "indptr must start at 0 (rebase shards)");
+    const int64_t T = ev_indptr[m_local], nnz = uq_indptr[m_local];
+    REQUIRE((T == 0 || ev_items) && (nnz == 0 || uq_items), YUE_E_ARG, "null item array");
+    for (int64_t u = 0; u < m_local; ++u) {
+        REQUIRE(ev_indptr[u + 1] >= ev_indptr[u] && uq_indptr[u + 1] >= uq_indptr[u], YUE_E_ARG, "indptr not monotone");
+        // a user who played the whole catalog has no negative: the reference would spin forever (BPR.py:47-48)
+        REQUIRE(uq_indptr[u + 1] - uq_indptr[u] < n || ev_indptr[u + 1] == ev_indptr[u], YUE_E_ARG,
+                "user " + std::to_string(u + user_begin) + " played every track: no negative exists");
+    }
+    CK(cudaSetDevice(h->device));
+    h->m = m_local; h->n = n; h->T = T; h->nnz = nnz; h->user_begin = user_begin; h->event_base = event_base;
+    CK(h->ev_indptr.resize(m_local + 1)); CK(h->uq_indptr.resize(m_local + 1));
+    CK(h->ev_items.resize(T)); CK(h->uq_items.resize(nnz));
+    CK(cudaMemcpyAsync(h->ev_indptr.p, ev_indptr, (m_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->uq_indptr.p, uq_indptr, (m_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (T) CK(cudaMemcpyAsync(h->ev_items.p, ev_items, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (nnz) CK(cudaMemcpyAsync(h->uq_items.p, uq_items, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    h->h_ev_indptr.assign(ev_indptr, ev_indptr + m_local + 1);
+    h->have_ev_user = false;
+
+    std::vector<int64_t> sb, ws;
+    std::vector<int32_t> su, sl;
+    build_segments(ev_indptr, m_local, sb, su, sl);
+    h->nseg = (int64_t)sb.size();
+    h->n_warps = h->sm_count * h->warps_per_sm;
+    slice_segments(sb, sl, T, h->n_warps, ws);
+    const int64_t serial[2] = {0, h->nseg};
+    CK(h->seg_begin.resize(h->nseg)); CK(h->seg_user.resize(h->nseg)); CK(h->seg_len.resize(h->nseg));
+    CK(h->warp_seg.resize(ws.size())); CK(h->warp_seg_serial.resize(2));
+    if (h->nseg) {
+        CK(cudaMemcpyAsync(h->seg_begin.p, sb.data(), sb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->seg_user.p, su.data(), su.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->seg_len.p, sl.data(), sl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->warp_seg.p, ws.data(), ws.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->warp_seg_serial.p, serial, sizeof(serial), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));      // host vectors die here
+    h->have_log = true;
+    return YUE_OK;
+}
+
+int yue_set_interactions(yue_t* h, int64_t m, int64_t n, const int64_t* ev_indptr, const int32_t* ev_items,
+                         const int64_t* uq_indptr, const int32_t* uq_items) {
+    return yue_set_interactions_shard(h, m, n, 0, 0, ev_indptr, ev_items, uq_indptr, uq_items);
+}
+
+int yue_set_factors(yue_t* h, int k, const float* P, const float* Q) {
+    REQUIRE(h && P && Q, YUE_E_ARG, "null argument");
+    REQUIRE(h->have_log, YUE_E_STATE, "call yue_set_interactions first (it fixes m and n)");
+    REQUIRE(k >= 1 && k <= 256, YUE_E_UNSUPPORTED, "num.factors must be in 1..256");
+    CK(cudaSetDevice(h->device));
+    const int ld = (k + 3) & ~3;
+    h->k = k; h->ld = ld;
+    CK(h->P.resize((size_t)std::max<int64_t>(h->m, 1) * ld));
+    CK(h->Q.resize((size_t)h->n * ld));
+    if (ld != k) {   // zero the pad columns; they stay zero under every update
+        CK(cudaMemsetAsync(h->P.p, 0, (size_t)std::max<int64_t>(h->m, 1) * ld * sizeof(float), h->stream));
+        CK(cudaMemsetAsync(h->Q.p, 0, (size_t)h->n * ld * sizeof(float), h->stream));
+    }
+    if (h->m) CK(cudaMemcpy2DAsync(h->P.p, ld * sizeof(float), P, k * sizeof(float), k * sizeof(float), h->m, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(h->Q.p, ld * sizeof(float), Q, k * sizeof(float), k * sizeof(float), h->n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_factors = true;
+    h->have_snap = false;
+    h->tc.q_dirty = true;
+    return YUE_OK;
+}
+
+int yue_get_factors(yue_t* h, float* P, float* Q) {
+    REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
+    CK(cudaSetDevice(h->device));
+    const int k = h->k, ld = h->ld;
+    if (P && h->m) CK(cudaMemcpy2DAsync(P, k * sizeof(float), h->P.p, ld * sizeof(float), k * sizeof(float), h->m, cudaMemcpyDeviceToHost, h->stream));
+    if (Q) CK(cudaMemcpy2DAsync(Q, k * sizeof(float), h->Q.p, ld * sizeof(float), k * sizeof(float), h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+static int ensure_ev_user(yue_t* h) {
+    if (h->have_ev_user) return YUE_OK;
+    std::vector<int32_t> eu((size_t)h->T);
+    for (int64_t u = 0; u < h->m; ++u)
+        std::fill(eu.begin() + h->h_ev_indptr[u], eu.begin() + h->h_ev_indptr[u + 1], (int32_t)u);
+    CK(h->ev_user.resize(h->T));
+    if (h->T) CK(cudaMemcpy(h->ev_user.p, eu.data(), eu.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->have_ev_user = true;
+    return YUE_OK;
+}
+
+int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot, int32_t* j_out) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "interactions not set");
+    REQUIRE(j_out || h->T == 0, YUE_E_ARG, "null output");
+    REQUIRE(slot < 4096, YUE_E_ARG, "slot must be < 4096");
+    CK(cudaSetDevice(h->device));
+    if (h->T == 0) return YUE_OK;
+    if (int rc = ensure_ev_user(h)) return rc;
+    CK(h->tmp_j.resize(h->T));
+    const int grid = (int)std::min<int64_t>((h->T + 255) / 256, (int64_t)h->sm_count * 16);
+    sample_negatives_kernel<<<grid, 256, 0, h->stream>>>(h->T, h->ev_user.p, h->uq_indptr.p, h->uq_items.p, seed, epoch,
+                                                         slot, h->event_base, (uint32_t)h->n, h->tmp_j.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(j_out, h->tmp_j.p, h->T * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+template <int NCH>
+static void launch_sgd(const SgdParams& sp, int mode, cudaStream_t st) {
+    if (mode == YUE_MODE_SERIAL) {
+        bpr_sgd_kernel<NCH, kSerial, 1><<<1, 32, 0, st>>>(sp);
+    } else {
+        constexpr int PF = NCH <= 2 ? 4 : 2;
+        const int grid = (sp.n_warps * 32 + 255) / 256;
+        if (mode == YUE_MODE_HOGWILD) bpr_sgd_kernel<NCH, kAtomic, PF><<<grid, 256, 0, st>>>(sp);
+        else bpr_sgd_kernel<NCH, kStore, PF><<<grid, 256, 0, st>>>(sp);
+    }
+}
+
+static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
+    REQUIRE(mode >= YUE_MODE_SERIAL && mode <= YUE_MODE_HOGWILD_STORE, YUE_E_ARG, "unknown mode");
+    CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
+    sp.P = h->P.p; sp.Q = h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
+    sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
+    const int nch = (sp.nchunks + 15) / 16;
+    switch (nch) {
+        case 1: launch_sgd<1>(sp, mode, h->stream); break;
+        case 2: launch_sgd<2>(sp, mode, h->stream); break;
+        case 3: launch_sgd<3>(sp, mode, h->stream); break;
+        case 4: launch_sgd<4>(sp, mode, h->stream); break;
+        default: return fail(h, YUE_E_UNSUPPORTED, "num.factors > 256");
+    }
+    ++h->launches;
+    CK(cudaGetLastError());
+    h->tc.q_dirty = true;
+    if (loss_out) {
+        CK(cudaMemcpyAsync(loss_out, h->scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (!std::isfinite(*loss_out))
+            return fail(h, YUE_E_NUMERIC, "Loss = NaN or Infinity: current settings does not fit the recommender!");
+    }
+    return YUE_OK;
+}
+
+static void fill_rates(SgdParams& sp, double lr, double regU, double regI) {
+    sp.lr_d = lr; sp.lr = (float)lr; sp.c_u = (float)(lr * regU); sp.c_i = (float)(lr * regI);
+}
+
+int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, uint32_t epoch, int mode,
+                  double* loss_out) {
+    REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
+    CK(cudaSetDevice(h->device));
+    if (h->T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
+    SgdParams sp{};
+    fill_rates(sp, lr, regU, regI);
+    sp.seg_begin = h->seg_begin.p; sp.seg_user = h->seg_user.p; sp.seg_len = h->seg_len.p;
+    sp.warp_seg = mode == YUE_MODE_SERIAL ? h->warp_seg_serial.p : h->warp_seg.p;
+    sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
+    sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
+    sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base;
+    return run_sgd(h, sp, mode, loss_out);
+}
+
+int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T, double lr,
+                  double regU, double regI, int mode, double* loss_out) {
+    REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
+    REQUIRE(T >= 0 && (T == 0 || (u && i && j)), YUE_E_ARG, "null triplet array");
+    CK(cudaSetDevice(h->device));
+    if (T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
+    std::vector<int64_t> sb, ws;
+    std::vector<int32_t> su, sl;
+    for (int64_t t = 0; t < T;) {               // runs of one user, <= 32 long
+        REQUIRE(u[t] >= 0 && u[t] < h->m && i[t] >= 0 && i[t] < h->n && j[t] >= 0 && j[t] < h->n, YUE_E_ARG,
+                "triplet index out of range");
+        int64_t e = t + 1;
+        while (e < T && e - t < 32 && u[e] == u[t]) {
+            REQUIRE(i[e] >= 0 && i[e] < h->n && j[e] >= 0 && j[e] < h->n, YUE_E_ARG, "triplet index out of range");
+            ++e;
+        }
+        sb.push_back(t); su.push_back(u[t]); sl.push_back((int32_t)(e - t));
+        t = e;
+    }
+    const int n_warps = mode == YUE_MODE_SERIAL ? 1 : h->sm_count * h->warps_per_sm;
+    slice_segments(sb, sl, T, n_warps, ws);
+    CK(h->tmp_i.resize(T)); CK(h->tmp_j.resize(T));
+    CK(h->tmp_sb.resize(sb.size())); CK(h->tmp_su.resize(su.size())); CK(h->tmp_sl.resize(sl.size()));
+    CK(h->tmp_ws.resize(ws.size()));
+    CK(cudaMemcpyAsync(h->tmp_i.p, i, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_j.p, j, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_sb.p, sb.data(), sb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_su.p, su.data(), su.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_sl.p, sl.data(), sl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_ws.p, ws.data(), ws.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    SgdParams sp{};
+    fill_rates(sp, lr, regU, regI);
+    sp.seg_begin = h->tmp_sb.p; sp.seg_user = h->tmp_su.p; sp.seg_len = h->tmp_sl.p;
+    sp.warp_seg = h->tmp_ws.p; sp.n_warps = n_warps;
+    sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
+    int rc = run_sgd(h, sp, mode, loss_out);
+    cudaStreamSynchronize(h->stream);           // host staging vectors die here
+    return rc;
+}
+
+int yue_frob2(yue_t* h, double* p2, double* q2) {
+    REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->scal.p + 1, 0, 2 * sizeof(double), h->stream));
+    const int grid = h->sm_count * 8;
+    if (h->m) { frob2_kernel<<<grid, 256, 0, h->stream>>>(h->P.p, (size_t)h->m * h->ld, h->scal.p + 1); ++h->launches; }
+    frob2_kernel<<<grid, 256, 0, h->stream>>>(h->Q.p, (size_t)h->n * h->ld, h->scal.p + 2); ++h->launches;
+    CK(cudaGetLastError());
+    double r[2];
+    CK(cudaMemcpyAsync(r, h->scal.p + 1, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (p2) *p2 = r[0];
+    if (q2) *q2 = r[1];
+    return YUE_OK;
+}
+
+int yue_predict(yue_t* h, int64_t user, float* scores_out) {
+    REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
+    REQUIRE(user >= 0 && user < h->m && scores_out, YUE_E_ARG, "bad user or null output");
+    CK(cudaSetDevice(h->device));
+    CK(h->pred.resize(h->n));
+    predict_kernel<<<(int)std::min<int64_t>((h->n + 255) / 256, 4096), 256, 0, h->stream>>>(h->P.p, h->Q.p, h->ld, h->k, user, (int)h->n, h->pred.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(scores_out, h->pred.p, h->n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+template <int BU, int CAP>
+static cudaError_t launch_rank_exact(const RankParams& rp, cudaStream_t st) {
+    const size_t smem = sizeof(RankSmem<BU, CAP>);
+    cudaError_t e = cudaFuncSetAttribute(rank_exact_kernel<BU, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)((rp.B + BU - 1) / BU);
+    rank_exact_kernel<BU, CAP><<<grid, 256, smem, st>>>(rp);
+    return cudaGetLastError();
+}
+
+static int yue_rank_exact_device(yue_t* h, const int32_t* d_users, int64_t B, int N, int32_t* d_ids, float* d_scores) {
+    RankParams rp{};
+    rp.P = h->P.p; rp.Q = h->Q.p; rp.ld = h->ld; rp.n_items = (int)h->n; rp.users = d_users; rp.B = B; rp.N = N;
+    rp.uq_indptr = h->uq_indptr.p; rp.uq_items = h->uq_items.p; rp.ids_out = d_ids; rp.scores_out = d_scores;
+    if (N <= 32) CK(launch_rank_exact<128, 64>(rp, h->stream));
+    else CK(launch_rank_exact<64, 256>(rp, h->stream));
+    ++h->launches;
+    return YUE_OK;
+}
+
+int yue_rank_topn(yue_t* h, const int32_t* users, int64_t B, int N, int algo, int32_t* ids_out, float* scores_out) {
+    REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
+    REQUIRE(B >= 0 && (B == 0 || (users && ids_out && scores_out)), YUE_E_ARG, "null argument");
+    REQUIRE(N >= 1 && N <= 128, YUE_E_ARG, "N must be in 1..128 (the reference caps it at 100)");
+    REQUIRE(algo >= YUE_RANK_EXACT && algo <= YUE_RANK_AUTO, YUE_E_ARG, "unknown algo");
+    for (int64_t b = 0; b < B; ++b) REQUIRE(users[b] >= 0 && users[b] < h->m, YUE_E_ARG, "user index out of range");
+    CK(cudaSetDevice(h->device));
+    if (B == 0) return YUE_OK;
+    CK(h->rk_users.resize(B)); CK(h->rk_ids.resize((size_t)B * N)); CK(h->rk_scores.resize((size_t)B * N));
+    CK(cudaMemcpyAsync(h->rk_users.p, users, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int rc;
+    const bool tc_ok = rank_tc_supported(h->k, N);
+    if (algo == YUE_RANK_TC && !tc_ok) return fail(h, YUE_E_UNSUPPORTED, "tcgen05 ranking needs num.factors % 8 == 0, <= 128 and N <= 32");
+    if (algo == YUE_RANK_TC || (algo == YUE_RANK_AUTO && tc_ok && B >= 256)) {
+        rc = rank_tc_run(h->tc, h->stream, h->sm_count, h->P.p, h->Q.p, h->ld, h->k, (int)h->n, h->rk_users.p, B, N,
+                         h->uq_indptr.p, h->uq_items.p, h->rk_ids.p, h->rk_scores.p, h->err, h->launches,
+                         [&](const int32_t* du, int64_t b, int32_t* di, float* ds) {
+                             return yue_rank_exact_device(h, du, b, N, di, ds);
+                         });
+        if (rc) return rc;
+    } else {
+        rc = yue_rank_exact_device(h, h->rk_users.p, B, N, h->rk_ids.p, h->rk_scores.p);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(ids_out, h->rk_ids.p, (size_t)B * N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(scores_out, h->rk_scores.p, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+// ---- multi-GPU Q reconciliation ------------------------------------------------------------
+static int ensure_snap(yue_t* h) {
+    CK(h->Qsnap.resize((size_t)h->n * h->ld));
+    CK(h->Qdelta.resize((size_t)h->n * h->ld));
+    return YUE_OK;
+}
+int yue_q_snapshot(yue_t* h) {
+    REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_snap(h)) return rc;
+    CK(cudaMemcpyAsync(h->Qsnap.p, h->Q.p, (size_t)h->n * h->ld * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    h->have_snap = true;
+    return YUE_OK;
+}
+int yue_q_delta_pack(yue_t* h) {
+    REQUIRE(h && h->have_factors && h->have_snap, YUE_E_STATE, "call yue_q_snapshot first");
+    CK(cudaSetDevice(h->device));
+    const size_t n4 = (size_t)h->n * h->ld / 4;
+    q_delta_pack_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((const float4*)h->Q.p, (const float4*)h->Qsnap.p, (float4*)h->Qdelta.p, n4);
+    ++h->launches;
+    CK(cudaGetLastError());
+    return YUE_OK;
+}
+int yue_q_delta_apply(yue_t* h) {
+    REQUIRE(h && h->have_factors && h->have_snap, YUE_E_STATE, "call yue_q_snapshot first");
+    CK(cudaSetDevice(h->device));
+    const size_t n4 = (size_t)h->n * h->ld / 4;
+    q_delta_apply_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((float4*)h->Q.p, (float4*)h->Qsnap.p, (const float4*)h->Qdelta.p, n4);
+    ++h->launches;
+    CK(cudaGetLastError());
+    h->tc.q_dirty = true;
+    return YUE_OK;
+}
+int yue_device_buffer(yue_t* h, int which, void** dev_ptr, size_t* bytes) {
+    REQUIRE(h && dev_ptr && bytes, YUE_E_ARG, "null argument");
+    REQUIRE(h->have_factors, YUE_E_STATE, "factors not set");
+    switch (which) {
+        case YUE_BUF_P: *dev_ptr = h->P.p; *bytes = (size_t)h->m * h->ld * sizeof(float); break;
+        case YUE_BUF_Q: *dev_ptr = h->Q.p; *bytes = (size_t)h->n * h->ld * sizeof(float); break;
+        case YUE_BUF_Q_DELTA:
+        case YUE_BUF_Q_SNAPSHOT:
+            if (int rc = ensure_snap(h)) return rc;
+            *dev_ptr = which == YUE_BUF_Q_DELTA ? h->Qdelta.p : h->Qsnap.p;
+            *bytes = (size_t)h->n * h->ld * sizeof(float);
+            break;
+        default: return fail(h, YUE_E_ARG, "unknown buffer");
+    }
+    return YUE_OK;
+}
+int yue_stream(yue_t* h, void** cuda_stream) {
+    REQUIRE(h && cuda_stream, YUE_E_ARG, "null argument");
+    *cuda_stream = (void*)h->stream;
+    return YUE_OK;
+}
+
+int yue_comm_unique_id(void* id128) {
+    std::string err;
+    if (!id128 || !g_nccl.load(err)) { g_create_error = err; return YUE_E_NCCL; }
+    return g_nccl.GetUniqueId((NcclUniqueId*)id128) == 0 ? YUE_OK : YUE_E_NCCL;
+}
+int yue_comm_init(yue_t* h, int nranks, int rank, const void* id128) {
+    REQUIRE(h && id128 && nranks >= 1 && rank >= 0 && rank < nranks, YUE_E_ARG, "bad communicator arguments");
+    if (!g_nccl.load(h->err)) return YUE_E_NCCL;
+    CK(cudaSetDevice(h->device));
+    NcclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    const int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (rc != 0) return fail(h, YUE_E_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    h->nranks = nranks; h->rank = rank;
+    return YUE_OK;
+}
+int yue_allreduce_q_delta(yue_t* h) {
+    REQUIRE(h && h->comm, YUE_E_STATE, "call yue_comm_init first");
+    if (int rc = yue_q_delta_pack(h)) return rc;
+    const int rc = g_nccl.AllReduce(h->Qdelta.p, h->Qdelta.p, (size_t)h->n * h->ld, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream);
+    if (rc != 0) return fail(h, YUE_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return yue_q_delta_apply(h);
+}
+
+// ---- measurement hooks ---------------------------------------------------------------------
+int yue_timer_start(yue_t* h) { CK(cudaSetDevice(h->device)); CK(cudaEventRecord(h->ev0, h->stream)); return YUE_OK; }
+int yue_timer_stop(yue_t* h, float* ms) {
+    REQUIRE(ms, YUE_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return YUE_OK;
+}
+int yue_launch_count(yue_t* h, int64_t* n) { REQUIRE(h && n, YUE_E_ARG, "null argument"); *n = h->launches; return YUE_OK; }
+int yue_flush_l2(yue_t* h) {
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = std::max<size_t>(h->l2_bytes * 2, (size_t)256 << 20);
+    CK(h->l2buf.resize(bytes));
+    CK(cudaMemsetAsync(h->l2buf.p, 0x5a, bytes, h->stream));
+    return YUE_OK;
+}
+

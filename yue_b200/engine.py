@@ -1,0 +1,204 @@
+"""Engine: one device handle of libyue_b200.so, numpy in / numpy out.
+
+This is the layer the recommender classes (yue_b200/bpr.py) sit on; it only marshals
+arguments.  All compute happens in the CUDA library -- there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MODE_HOGWILD, MODE_HOGWILD_STORE, MODE_SERIAL, RANK_AUTO, RANK_EXACT,  # noqa: F401
+                   RANK_TC, YueError)
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class PinnedArray:
+    """numpy array over cudaHostAlloc'ed memory (DMA target for factor tables / results)."""
+
+    def __init__(self, shape, dtype):
+        lib = _lib.load()
+        self._lib = lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = lib.yue_host_alloc(self.nbytes, C.byref(p))
+        if rc:
+            raise YueError(rc, "yue_host_alloc(%d) failed" % self.nbytes)
+        self._p = p
+        buf = (C.c_byte * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._p is not None:
+            self.array = None
+            self._lib.yue_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.yue_create(int(device), C.byref(h))
+        if rc:
+            raise YueError(rc, self.lib.yue_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+        self.m = self.n = self.k = self.T = 0
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise YueError(rc, self.lib.yue_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.yue_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._ck(self.lib.yue_sync(self.h))
+
+    # -- data ------------------------------------------------------------------------------
+    def set_interactions(self, m, n, ev_indptr, ev_items, uq_indptr, uq_items,
+                         user_begin=0, event_base=0):
+        ev_indptr, uq_indptr = _as(ev_indptr, np.int64), _as(uq_indptr, np.int64)
+        ev_items, uq_items = _as(ev_items, np.int32), _as(uq_items, np.int32)
+        if len(ev_indptr) != m + 1 or len(uq_indptr) != m + 1:
+            raise ValueError("indptr arrays must have m+1 entries")
+        if len(ev_items) != ev_indptr[-1] or len(uq_items) != uq_indptr[-1]:
+            raise ValueError("item arrays do not match indptr[-1]")
+        self._ck(self.lib.yue_set_interactions_shard(
+            self.h, m, n, user_begin, event_base, _ptr(ev_indptr, C.c_int64), _ptr(ev_items, C.c_int32),
+            _ptr(uq_indptr, C.c_int64), _ptr(uq_items, C.c_int32)))
+        self.m, self.n, self.T = int(m), int(n), int(ev_indptr[-1])
+
+    def set_factors(self, P, Q):
+        P, Q = _as(P, np.float32), _as(Q, np.float32)
+        if P.shape[0] != self.m or Q.shape[0] != self.n or P.shape[1] != Q.shape[1]:
+            raise ValueError("factor shapes %s %s do not match m=%d n=%d" % (P.shape, Q.shape, self.m, self.n))
+        self.k = int(P.shape[1])
+        self._ck(self.lib.yue_set_factors(self.h, self.k, _ptr(P, C.c_float), _ptr(Q, C.c_float)))
+
+    def get_factors(self, P=None, Q=None):
+        """Copy the tables back; pass preallocated (e.g. pinned) arrays to avoid an allocation."""
+        if P is None:
+            P = np.empty((self.m, self.k), dtype=np.float32)
+        if Q is None:
+            Q = np.empty((self.n, self.k), dtype=np.float32)
+        assert P.dtype == np.float32 and Q.dtype == np.float32 and P.flags.c_contiguous and Q.flags.c_contiguous
+        self._ck(self.lib.yue_get_factors(self.h, _ptr(P, C.c_float), _ptr(Q, C.c_float)))
+        return P, Q
+
+    # -- training --------------------------------------------------------------------------
+    def sample_negatives(self, seed, epoch, slot=0):
+        out = np.empty(self.T, dtype=np.int32)
+        self._ck(self.lib.yue_sample_negatives(self.h, seed, epoch, slot, _ptr(out, C.c_int32)))
+        return out
+
+    def bpr_epoch(self, lr, regU, regI, seed, epoch, mode=MODE_HOGWILD, want_loss=True):
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_bpr_epoch(self.h, lr, regU, regI, seed, epoch, mode,
+                                        C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
+    def bpr_apply(self, u, i, j, lr, regU, regI, mode=MODE_SERIAL, want_loss=True):
+        u, i, j = _as(u, np.int32), _as(i, np.int32), _as(j, np.int32)
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_bpr_apply(self.h, _ptr(u, C.c_int32), _ptr(i, C.c_int32), _ptr(j, C.c_int32),
+                                        len(u), lr, regU, regI, mode, C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
+    def frob2(self):
+        p2, q2 = C.c_double(), C.c_double()
+        self._ck(self.lib.yue_frob2(self.h, C.byref(p2), C.byref(q2)))
+        return p2.value, q2.value
+
+    # -- scoring ---------------------------------------------------------------------------
+    def predict(self, user):
+        out = np.empty(self.n, dtype=np.float32)
+        self._ck(self.lib.yue_predict(self.h, int(user), _ptr(out, C.c_float)))
+        return out
+
+    def rank_topn(self, users, N, algo=RANK_AUTO, ids=None, scores=None):
+        users = _as(users, np.int32)
+        B = len(users)
+        if ids is None:
+            ids = np.empty((B, N), dtype=np.int32)
+        if scores is None:
+            scores = np.empty((B, N), dtype=np.float32)
+        self._ck(self.lib.yue_rank_topn(self.h, _ptr(users, C.c_int32), B, int(N), algo,
+                                        _ptr(ids, C.c_int32), _ptr(scores, C.c_float)))
+        return ids, scores
+
+    # -- multi-GPU plumbing ----------------------------------------------------------------
+    def q_snapshot(self):
+        self._ck(self.lib.yue_q_snapshot(self.h))
+
+    def q_delta_pack(self):
+        self._ck(self.lib.yue_q_delta_pack(self.h))
+
+    def q_delta_apply(self):
+        self._ck(self.lib.yue_q_delta_apply(self.h))
+
+    def device_buffer(self, which):
+        p, nbytes = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.yue_device_buffer(self.h, which, C.byref(p), C.byref(nbytes)))
+        return p.value, nbytes.value
+
+    def stream_ptr(self):
+        s = C.c_void_p()
+        self._ck(self.lib.yue_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.yue_comm_init(self.h, nranks, rank, buf))
+
+    def allreduce_q_delta(self):
+        self._ck(self.lib.yue_allreduce_q_delta(self.h))
+
+    # -- measurement -----------------------------------------------------------------------
+    def timer_start(self):
+        self._ck(self.lib.yue_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.yue_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._ck(self.lib.yue_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def flush_l2(self):
+        self._ck(self.lib.yue_flush_l2(self.h))
+
+
+def comm_unique_id():
+    lib = _lib.load()
+    buf = C.create_string_buffer(128)
+    rc = lib.yue_comm_unique_id(buf)
+    if rc:
+        raise YueError(rc, lib.yue_last_error(None).decode())
+    return buf.raw

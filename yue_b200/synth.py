@@ -128,3 +128,49 @@ CONFIGS = {
     "C4": dict(users=1_000_000, tracks=2_000_000, d=64, mask_mean=50),
     "C5": dict(users=1_000_000, tracks=200_000, plays=50_000_000, d=64),
 }
+
+
+def power_law_log_torch(m, n, plays, seed, test_ratio=0.0, device=None, alpha=0.8, beta=1.0):
+    """Same distributions as power_law_log, generated with torch ops (on the GPU when there is
+    one: ~1 s for config C2 instead of ~1 min of numpy).  Bench/data plumbing only -- the stream
+    differs from the numpy generator's, both are seeded and deterministic per device type."""
+    import torch
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    deg_np = user_degrees(m, plays, alpha)
+    deg = torch.from_numpy(deg_np).to(device)
+    T = int(deg_np.sum())
+    cdf = torch.cumsum(torch.arange(1, n + 1, device=device, dtype=torch.float64) ** (-beta), 0)
+    cdf /= cdf[-1].clone()
+    items = torch.empty(T, dtype=torch.int64, device=device)
+    step = 1 << 24                                  # bounded temporaries
+    for a in range(0, T, step):
+        b = min(T, a + step)
+        r = torch.rand(b - a, generator=g, device=device, dtype=torch.float64)
+        items[a:b] = torch.searchsorted(cdf, r, right=True).clamp_(max=n - 1)
+    users = torch.repeat_interleave(torch.arange(m, device=device, dtype=torch.int64), deg)
+    if test_ratio > 0:
+        held = torch.rand(T, generator=g, device=device) < test_ratio
+    else:
+        held = torch.zeros(T, dtype=torch.bool, device=device)
+    tr_u, tr_i = users[~held], items[~held]
+    ev_indptr = torch.zeros(m + 1, dtype=torch.int64, device=device)
+    ev_indptr[1:] = torch.cumsum(torch.bincount(tr_u, minlength=m), 0)
+    tr_key = torch.unique(tr_u * n + tr_i)           # sorted unique (user, item)
+    uq_u = tr_key // n
+    uq_indptr = torch.zeros(m + 1, dtype=torch.int64, device=device)
+    uq_indptr[1:] = torch.cumsum(torch.bincount(uq_u, minlength=m), 0)
+    uq_items = (tr_key - uq_u * n).to(torch.int32)
+    te_key = torch.unique(users[held] * n + items[held])
+    if te_key.numel():
+        pos = torch.searchsorted(tr_key, te_key).clamp_(max=max(tr_key.numel() - 1, 0))
+        te_key = te_key[tr_key[pos] != te_key] if tr_key.numel() else te_key
+    te_u = te_key // n
+    test_indptr = torch.zeros(m + 1, dtype=torch.int64, device=device)
+    test_indptr[1:] = torch.cumsum(torch.bincount(te_u, minlength=m), 0)
+    test_items = (te_key - te_u * n).to(torch.int32)
+    host = lambda t: t.cpu().numpy()                 # noqa: E731
+    return PlayLog(m, n, host(ev_indptr), host(tr_i.to(torch.int32)), host(uq_indptr), host(uq_items),
+                   host(test_indptr), host(test_items))
