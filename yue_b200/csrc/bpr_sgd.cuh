@@ -29,6 +29,7 @@
 namespace yue {
 
 enum : int { kSerial = 0, kAtomic = 1, kStore = 2 };
+constexpr int32_t kSegShared = 1 << 30;   // the segment's user is worked on by more than one warp
 
 struct SgdParams {
     float* P;                      // [m_local, ld]
@@ -38,10 +39,10 @@ struct SgdParams {
     uint32_t n_items;
     const int64_t* seg_begin;      // [nseg] first local event of the segment
     const int32_t* seg_user;       // [nseg] local user
-    const int32_t* seg_len;        // [nseg] 1..32
+    const int32_t* seg_len;        // [nseg] 1..32, | kSegShared when the user spans several warps
     const int64_t* warp_seg;       // [n_warps+1] segment slice per warp
     int n_warps;
-    const int32_t* ev_items;       // [T] positives
+    const int32_t* ev_items;       // [T] positives; a value v < 0 names hot slot -v-1 (see hot_items)
     const int32_t* ev_neg;         // [T] negatives, or nullptr -> sample in-kernel
     const int64_t* uq_indptr;      // [m_local+1]
     const int32_t* uq_items;
@@ -51,6 +52,16 @@ struct SgdParams {
     float lr, c_u, c_i;            // lr, float(lr*regU), float(lr*regI)
     double lr_d;
     double* loss;                  // device accumulator of sum -log(s)
+    // Hot rows.  On a power-law log the most played track is the positive of several percent of
+    // ALL triplets; its row lives in one L2 slice and the vector atomics to it serialise there
+    // (ncu: lts__d_atomic_input_cycles_active 86% on one slice, 5% on average -- the whole epoch
+    // waited on that slice).  The n_hot most played tracks therefore get a per-CTA copy in shared
+    // memory: a triplet whose positive is hot reads base+delta from shared memory, adds its change
+    // to delta with shared-memory atomics, and every hot_flush-th update of a slot publishes the
+    // accumulated delta with ONE vector atomic and re-reads the row.
+    const int32_t* hot_items;      // [n_hot] track id of each hot slot
+    int n_hot;
+    int hot_flush;
 };
 
 __device__ __forceinline__ float4 ld_row(const float* p) {
@@ -62,6 +73,17 @@ __device__ __forceinline__ void st_row(float* p, float4 v) {
 __device__ __forceinline__ void red_row(float* p, float4 v) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// shared-memory row access that the compiler may not cache or reorder (other warps update it)
+__device__ __forceinline__ float4 lds_row(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_row(float* p, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
     v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
@@ -83,14 +105,29 @@ struct RowOps {
     }
 };
 
+constexpr int kSgdThreads = 512;
+
 template <int NCH, int MODE, int PF>
-__global__ void __launch_bounds__(256) bpr_sgd_kernel(const SgdParams p) {
+__global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams p) {
+    extern __shared__ __align__(16) float hot_smem[];     // base[n_hot][ld] | delta[n_hot][ld] | cnt[n_hot]
+    float* hot_base = hot_smem;
+    float* hot_delta = hot_smem + (size_t)p.n_hot * p.ld;
+    int* hot_cnt = reinterpret_cast<int*>(hot_smem + 2 * (size_t)p.n_hot * p.ld);
+    if (MODE != kSerial && p.n_hot > 0) {
+        for (int x = threadIdx.x; x < p.n_hot * (p.ld / 4); x += blockDim.x) {
+            const int slot = x / (p.ld / 4), c4 = x % (p.ld / 4);
+            reinterpret_cast<float4*>(hot_base)[x] = ld_row(p.Q + (size_t)p.hot_items[slot] * p.ld + 4 * c4);
+            reinterpret_cast<float4*>(hot_delta)[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) hot_cnt[x] = 0;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    if (warp >= p.n_warps) return;
     const int half = lane >> 4;
     const int l16 = lane & 15;
-    const int64_t sb = p.warp_seg[warp], se = p.warp_seg[warp + 1];
+    const bool has_work = warp < p.n_warps;
+    const int64_t sb = has_work ? p.warp_seg[warp] : 0, se = has_work ? p.warp_seg[warp + 1] : 0;
     using R = RowOps<NCH, MODE>;
 
     bool act[NCH];
@@ -123,20 +160,32 @@ __global__ void __launch_bounds__(256) bpr_sgd_kernel(const SgdParams p) {
     for (int64_t seg = sb; seg < se; ++seg) {
         const int u = p.seg_user[seg];
         const int64_t begin = p.seg_begin[seg];
-        const int len = p.seg_len[seg];
-        if (u != cur_u) {
+        const int32_t raw_len = p.seg_len[seg];
+        const int len = raw_len & 63;
+        // A user shared between warps is re-read at every segment: otherwise each warp would run
+        // thousands of updates on a private copy and the summed deltas overshoot (Hogwild with
+        // unbounded staleness diverges on the heaviest users).
+        const bool resync = MODE != kSerial && (raw_len & kSegShared) != 0;
+        if (u != cur_u || resync) {
             flush_user();
-            if (MODE == kSerial) __syncwarp();
+            if (u != cur_u) {
+                const int64_t r0 = p.uq_indptr[u];
+                row = p.uq_items + r0;
+                row_len = (int)(p.uq_indptr[u + 1] - r0);
+            }
             cur_u = u;
+            // the lower half reads after its own publish (same thread, same address: ordered) and
+            // hands the row to the upper half, so both halves always hold the same P[u]
             const float* src = p.P + (size_t)u * p.ld + lane_off;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                pu[c] = act[c] ? ld_row(src + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                pu0[c] = pu[c];
+                float4 v = (act[c] && half == 0) ? ld_row(src + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v.x = __shfl_sync(0xffffffffu, v.x, l16);
+                v.y = __shfl_sync(0xffffffffu, v.y, l16);
+                v.z = __shfl_sync(0xffffffffu, v.z, l16);
+                v.w = __shfl_sync(0xffffffffu, v.w, l16);
+                pu[c] = pu0[c] = v;
             }
-            const int64_t r0 = p.uq_indptr[u];
-            row = p.uq_items + r0;
-            row_len = (int)(p.uq_indptr[u + 1] - r0);
         }
 
         // ---- K1: lane t draws the negative of event begin+t -------------------------------
@@ -151,20 +200,26 @@ __global__ void __launch_bounds__(256) bpr_sgd_kernel(const SgdParams p) {
         __syncwarp();
 
         // ---- K2: the updates, one after the other, PF row pairs in flight -----------------
+        // lower half -> Q[i], upper half -> Q[j]; nullptr = hot positive (served from shared memory)
         auto row_ptr = [&](int t) -> float* {
-            const int32_t it = __shfl_sync(0xffffffffu, my_i, t);
+            int32_t it = __shfl_sync(0xffffffffu, my_i, t);
             const int32_t jt = __shfl_sync(0xffffffffu, my_j, t);
-            return p.Q + (size_t)(half ? jt : it) * p.ld + lane_off;
+            if (MODE == kSerial && it < 0) it = p.hot_items[-it - 1];
+            const int32_t r = half ? jt : it;
+            return r >= 0 ? p.Q + (size_t)r * p.ld + lane_off : nullptr;
+        };
+        auto load_rows = [&](float* ptr, float4* dstv) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                dstv[c] = (act[c] && ptr) ? ld_row(ptr + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         float4 qb[PF][NCH];
         float* qp[PF];
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
-            if (k < len) {
+            if (PF > 1 && k < len) {
                 qp[k] = row_ptr(k);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-                    qb[k][c] = act[c] ? ld_row(qp[k] + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                load_rows(qp[k], qb[k]);
             }
         }
         for (int t0 = 0; t0 < len; t0 += PF) {
@@ -172,15 +227,32 @@ __global__ void __launch_bounds__(256) bpr_sgd_kernel(const SgdParams p) {
             for (int k = 0; k < PF; ++k) {
                 const int t = t0 + k;
                 if (t >= len) break;
+                if (PF == 1) {                          // serial parity mode: read when reached
+                    qp[0] = row_ptr(t);
+                    load_rows(qp[0], qb[0]);
+                }
                 float4 q[NCH];
                 float* dst = qp[k];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) q[c] = qb[k][c];
                 if (PF > 1 && t + PF < len) {          // refill this slot for event t+PF
                     qp[k] = row_ptr(t + PF);
+                    load_rows(qp[k], qb[k]);
+                }
+                // hot positive: the lower half takes base+delta of its slot from shared memory
+                const int32_t it_raw = __shfl_sync(0xffffffffu, my_i, t);
+                const bool hot = MODE != kSerial && it_raw < 0;
+                const int slot = hot ? -it_raw - 1 : 0;
+                float* sbase = hot_base + (size_t)slot * p.ld + lane_off;
+                float* sdelta = hot_delta + (size_t)slot * p.ld + lane_off;
+                if (hot && half == 0) {
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c)
-                        qb[k][c] = act[c] ? ld_row(qp[k] + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < NCH; ++c) {
+                        if (!act[c]) continue;
+                        const float4 b = lds_row(sbase + 64 * c);
+                        const float4 dl = lds_row(sdelta + 64 * c);
+                        q[c] = make_float4(b.x + dl.x, b.y + dl.y, b.z + dl.z, b.w + dl.w);
+                    }
                 }
                 // dots: each half reduces its own row, then x = P.Qi - P.Qj (BPR.py:50)
                 float part = 0.f;
@@ -221,11 +293,37 @@ __global__ void __launch_bounds__(256) bpr_sgd_kernel(const SgdParams p) {
                     pu[c] = R::axpy4(-p.c_u, pu[c], pu[c]);         // shrinks (55-57)
                     qn = R::axpy4(-p.c_i, qn, qn);
                     if (act[c]) {
-                        if (MODE == kAtomic)
+                        if (hot && half == 0) {
+                            atomicAdd(sdelta + 64 * c + 0, qn.x - q[c].x);
+                            atomicAdd(sdelta + 64 * c + 1, qn.y - q[c].y);
+                            atomicAdd(sdelta + 64 * c + 2, qn.z - q[c].z);
+                            atomicAdd(sdelta + 64 * c + 3, qn.w - q[c].w);
+                        } else if (MODE == kAtomic) {
                             red_row(dst + 64 * c, make_float4(qn.x - q[c].x, qn.y - q[c].y,
                                                               qn.z - q[c].z, qn.w - q[c].w));
-                        else
+                        } else {
                             st_row(dst + 64 * c, qn);
+                        }
+                    }
+                }
+                if (hot) {      // every hot_flush-th update of the slot publishes the CTA's delta
+                    int n_upd = 0;
+                    if (lane == 0) n_upd = atomicAdd(hot_cnt + slot, 1) + 1;
+                    n_upd = __shfl_sync(0xffffffffu, n_upd, 0);
+                    if (n_upd % p.hot_flush == 0 && half == 0) {
+                        float* grow = p.Q + (size_t)p.hot_items[slot] * p.ld + lane_off;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            if (!act[c]) continue;
+                            float4 dl;
+                            dl.x = atomicExch(sdelta + 64 * c + 0, 0.f);
+                            dl.y = atomicExch(sdelta + 64 * c + 1, 0.f);
+                            dl.z = atomicExch(sdelta + 64 * c + 2, 0.f);
+                            dl.w = atomicExch(sdelta + 64 * c + 3, 0.f);
+                            red_row(grow + 64 * c, dl);
+                            const float4 nb = ld_row(grow + 64 * c);     // after own red: ordered
+                            sts_row(sbase + 64 * c, nb);
+                        }
                     }
                 }
                 if (MODE == kSerial) __syncwarp();   // order this triplet's stores before the next loads
@@ -234,6 +332,15 @@ __global__ void __launch_bounds__(256) bpr_sgd_kernel(const SgdParams p) {
     }
     flush_user();
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss, loss);
+    if (MODE != kSerial && p.n_hot > 0) {            // publish what is left in the CTA's hot deltas
+        __syncthreads();
+        for (int x = threadIdx.x; x < p.n_hot * (p.ld / 4); x += blockDim.x) {
+            const int slot = x / (p.ld / 4), c4 = x % (p.ld / 4);
+            const float4 dl = reinterpret_cast<float4*>(hot_delta)[x];
+            if (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f)
+                red_row(p.Q + (size_t)p.hot_items[slot] * p.ld + 4 * c4, dl);
+        }
+    }
 }
 
 // ---- check hook: materialise the negatives (yue_sample_negatives) -------------------------
@@ -248,6 +355,21 @@ __global__ void sample_negatives_kernel(int64_t T, const int32_t* __restrict__ e
         const int64_t r0 = uq_indptr[u];
         out[e] = sample_negative(seed, epoch, (uint64_t)(event_base + e), slot, n_items,
                                  uq_items + r0, (int)(uq_indptr[u + 1] - r0));
+    }
+}
+
+// ---- hot-track selection support: play counts, and re-labelling of hot positives ------------
+__global__ void item_count_kernel(const int32_t* __restrict__ ev_items, int64_t T, int32_t* __restrict__ counts) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t it = ev_items[e];
+        const unsigned peers = __match_any_sync(__activemask(), it);     // one atomic per distinct id in the warp
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + it, __popc(peers));
+    }
+}
+__global__ void mark_hot_kernel(int32_t* __restrict__ ev_items, int64_t T, const int32_t* __restrict__ hot_slot) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t s = hot_slot[ev_items[e]];
+        if (s >= 0) ev_items[e] = -s - 1;
     }
 }
 

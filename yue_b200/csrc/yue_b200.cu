@@ -72,7 +72,13 @@ struct DevBuf {
 struct yue_handle {
     int device = 0;
     int sm_count = 148;
-    int warps_per_sm = 32;
+    int warps_per_sm = kSgdThreads / 32;   // one resident CTA per SM, a single wave
+    int min_events_per_warp = 2048;   // small logs get fewer warps: bounds Hogwild staleness
+    int hot_max = 64;                 // shared-memory hot-row slots per CTA
+    int hot_min_count = 16384;        // a track is hot when it is the positive of at least this many events
+    int hot_flush = 16;               // updates of a slot between publishes
+    int n_hot = 0;
+    DevBuf<int32_t> hot_items, hot_slot, item_counts;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -149,6 +155,18 @@ static void slice_segments(const std::vector<int64_t>& sb, const std::vector<int
     }
     ws[n_warps] = nseg;
 }
+// Flag every segment of a user whose segments fall into more than one warp slice.
+static void mark_shared_users(const std::vector<int32_t>& su, std::vector<int32_t>& sl,
+                              const std::vector<int64_t>& ws) {
+    const int64_t nseg = (int64_t)su.size();
+    for (size_t w = 1; w + 1 < ws.size(); ++w) {
+        const int64_t s0 = ws[w];
+        if (s0 <= 0 || s0 >= nseg || su[s0] != su[s0 - 1] || (sl[s0] & kSegShared)) continue;
+        const int32_t u = su[s0];
+        for (int64_t s = s0; s < nseg && su[s] == u; ++s) sl[s] |= kSegShared;
+        for (int64_t s = s0 - 1; s >= 0 && su[s] == u; --s) sl[s] |= kSegShared;
+    }
+}
 
 // Every yue_* function below is declared extern "C" by include/yue_b200.h and inherits that linkage.
 
@@ -185,7 +203,10 @@ int yue_create(int device, yue_t** out) {
     }
     h->sm_count = prop.multiProcessorCount;
     h->l2_bytes = (size_t)prop.l2CacheSize;
-    if (const char* s = getenv("YUE_SGD_WARPS_PER_SM")) h->warps_per_sm = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(96, atoi(s)));   // 96 slots x 256 floats x 8 B fits one CTA
+    if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_HOT_FLUSH")) h->hot_flush = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_MIN_EVENTS_PER_WARP")) h->min_events_per_warp = std::max(32, atoi(s));
     *out = h;
     return YUE_OK;
 }
@@ -198,7 +219,7 @@ int yue_destroy(yue_t* h) {
     rank_tc_release(h->tc);
     for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->seg_begin, &h->warp_seg, &h->warp_seg_serial, &h->tmp_sb, &h->tmp_ws}) b->release();
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->seg_user, &h->seg_len, &h->tmp_i, &h->tmp_j,
-                    &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids}) b->release();
+                    &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts}) b->release();
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->rk_scores, &h->pred}) b->release();
     h->scal.release();
     h->l2buf.release();
@@ -250,8 +271,9 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     std::vector<int32_t> su, sl;
     build_segments(ev_indptr, m_local, sb, su, sl);
     h->nseg = (int64_t)sb.size();
-    h->n_warps = h->sm_count * h->warps_per_sm;
+    h->n_warps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
     slice_segments(sb, sl, T, h->n_warps, ws);
+    mark_shared_users(su, sl, ws);
     const int64_t serial[2] = {0, h->nseg};
     CK(h->seg_begin.resize(h->nseg)); CK(h->seg_user.resize(h->nseg)); CK(h->seg_len.resize(h->nseg));
     CK(h->warp_seg.resize(ws.size())); CK(h->warp_seg_serial.resize(2));
@@ -262,6 +284,36 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     }
     CK(cudaMemcpyAsync(h->warp_seg.p, ws.data(), ws.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->warp_seg_serial.p, serial, sizeof(serial), cudaMemcpyHostToDevice, h->stream));
+    // hot tracks: device histogram of the positives, top hot_max by count on the host, then the hot
+    // positives of the device copy of ev_items are re-labelled -slot-1 (see SgdParams::hot_items)
+    h->n_hot = 0;
+    if (T > 0 && h->hot_max > 0) {
+        CK(h->item_counts.resize(n));
+        CK(cudaMemsetAsync(h->item_counts.p, 0, n * sizeof(int32_t), h->stream));
+        const int grid = (int)std::min<int64_t>((T + 255) / 256, (int64_t)h->sm_count * 16);
+        item_count_kernel<<<grid, 256, 0, h->stream>>>(h->ev_items.p, T, h->item_counts.p);
+        ++h->launches;
+        CK(cudaGetLastError());
+        std::vector<int32_t> counts((size_t)n);
+        CK(cudaMemcpyAsync(counts.data(), h->item_counts.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<int32_t> cand;
+        for (int64_t t = 0; t < n; ++t) if (counts[t] >= h->hot_min_count) cand.push_back((int32_t)t);
+        std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return counts[a] != counts[b] ? counts[a] > counts[b] : a < b; });
+        if ((int)cand.size() > h->hot_max) cand.resize(h->hot_max);
+        h->n_hot = (int)cand.size();
+        if (h->n_hot) {
+            std::vector<int32_t> slot((size_t)n, -1);
+            for (int s2 = 0; s2 < h->n_hot; ++s2) slot[cand[s2]] = s2;
+            CK(h->hot_items.resize(h->n_hot)); CK(h->hot_slot.resize(n));
+            CK(cudaMemcpyAsync(h->hot_items.p, cand.data(), cand.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->hot_slot.p, slot.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            mark_hot_kernel<<<grid, 256, 0, h->stream>>>(h->ev_items.p, T, h->hot_slot.p);
+            ++h->launches;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(h->stream));
+        }
+    }
     CK(cudaStreamSynchronize(h->stream));      // host vectors die here
     h->have_log = true;
     return YUE_OK;
@@ -334,15 +386,19 @@ int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot,
 }
 
 template <int NCH>
-static void launch_sgd(const SgdParams& sp, int mode, cudaStream_t st) {
+static cudaError_t launch_sgd(const SgdParams& sp, int mode, cudaStream_t st) {
     if (mode == YUE_MODE_SERIAL) {
         bpr_sgd_kernel<NCH, kSerial, 1><<<1, 32, 0, st>>>(sp);
-    } else {
-        constexpr int PF = NCH <= 2 ? 4 : 2;
-        const int grid = (sp.n_warps * 32 + 255) / 256;
-        if (mode == YUE_MODE_HOGWILD) bpr_sgd_kernel<NCH, kAtomic, PF><<<grid, 256, 0, st>>>(sp);
-        else bpr_sgd_kernel<NCH, kStore, PF><<<grid, 256, 0, st>>>(sp);
+        return cudaGetLastError();
     }
+    constexpr int PF = NCH <= 2 ? 4 : 2;
+    const int grid = (sp.n_warps * 32 + kSgdThreads - 1) / kSgdThreads;
+    const size_t smem = (size_t)sp.n_hot * sp.ld * 8 + (size_t)sp.n_hot * 4;
+    auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF> : bpr_sgd_kernel<NCH, kStore, PF>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kSgdThreads, smem, st>>>(sp);
+    return cudaGetLastError();
 }
 
 static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
@@ -352,14 +408,13 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
     const int nch = (sp.nchunks + 15) / 16;
     switch (nch) {
-        case 1: launch_sgd<1>(sp, mode, h->stream); break;
-        case 2: launch_sgd<2>(sp, mode, h->stream); break;
-        case 3: launch_sgd<3>(sp, mode, h->stream); break;
-        case 4: launch_sgd<4>(sp, mode, h->stream); break;
+        case 1: CK(launch_sgd<1>(sp, mode, h->stream)); break;
+        case 2: CK(launch_sgd<2>(sp, mode, h->stream)); break;
+        case 3: CK(launch_sgd<3>(sp, mode, h->stream)); break;
+        case 4: CK(launch_sgd<4>(sp, mode, h->stream)); break;
         default: return fail(h, YUE_E_UNSUPPORTED, "num.factors > 256");
     }
     ++h->launches;
-    CK(cudaGetLastError());
     h->tc.q_dirty = true;
     if (loss_out) {
         CK(cudaMemcpyAsync(loss_out, h->scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -385,6 +440,7 @@ int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, 
     sp.warp_seg = mode == YUE_MODE_SERIAL ? h->warp_seg_serial.p : h->warp_seg.p;
     sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
+    sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot; sp.hot_flush = h->hot_flush;
     sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base;
     return run_sgd(h, sp, mode, loss_out);
 }
@@ -408,8 +464,10 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
         sb.push_back(t); su.push_back(u[t]); sl.push_back((int32_t)(e - t));
         t = e;
     }
-    const int n_warps = mode == YUE_MODE_SERIAL ? 1 : h->sm_count * h->warps_per_sm;
+    const int n_warps = mode == YUE_MODE_SERIAL ? 1
+        : (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
     slice_segments(sb, sl, T, n_warps, ws);
+    if (mode != YUE_MODE_SERIAL) mark_shared_users(su, sl, ws);
     CK(h->tmp_i.resize(T)); CK(h->tmp_j.resize(T));
     CK(h->tmp_sb.resize(sb.size())); CK(h->tmp_su.resize(su.size())); CK(h->tmp_sl.resize(sl.size()));
     CK(h->tmp_ws.resize(ws.size()));
@@ -424,6 +482,7 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
     sp.seg_begin = h->tmp_sb.p; sp.seg_user = h->tmp_su.p; sp.seg_len = h->tmp_sl.p;
     sp.warp_seg = h->tmp_ws.p; sp.n_warps = n_warps;
     sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
+    sp.n_hot = 0; sp.hot_flush = 1;              // explicit triplets take the direct path
     int rc = run_sgd(h, sp, mode, loss_out);
     cudaStreamSynchronize(h->stream);           // host staging vectors die here
     return rc;
