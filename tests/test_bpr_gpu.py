@@ -203,30 +203,35 @@ def _train_and_eval(eng, log, P, Q, mode, epochs, lr, seed):
 def test_quality_gate_hogwild_vs_serial(monkeypatch):
     """north_star: end-to-end Recall@10 and NDCG@10 within 0.5% absolute of the reference order on
     the same synthetic log.  The serial-order mode (proven equal to the reference loop above) is
-    the reference trainer; the throughput mode runs with the shared-memory hot-row path forced on."""
+    the reference trainer.  The throughput mode runs with MORE concurrency per event than config C2
+    gets (C2: 50 M events over 2368 warps = 21 K events per warp; here 1 K per warp) and with the
+    shared-memory hot-row path forced on.  A second serial run with another sampler seed gives the
+    seed-to-seed noise floor the 0.5% is to be read against."""
     from yue_b200.engine import Engine
-    monkeypatch.setenv("YUE_SGD_HOT_MIN_COUNT", "256")
-    monkeypatch.setenv("YUE_SGD_MIN_EVENTS_PER_WARP", "512")
+    monkeypatch.setenv("YUE_SGD_HOT_MIN_COUNT", "2048")
+    monkeypatch.setenv("YUE_SGD_MIN_EVENTS_PER_WARP", "1024")
     eng = Engine(0)
     try:
-        log = synth.power_law_log(3000, 1500, 200000, seed=33)
+        log = synth.power_law_log(12000, 3000, 900000, seed=33)
         P, Q = synth.init_factors(log.m, log.n, 32, seed=5)
-        rs, ns = _train_and_eval(eng, log, P, Q, MODE_SERIAL, 12, 0.05, 99)
-        rh, nh = _train_and_eval(eng, log, P, Q, MODE_HOGWILD, 12, 0.05, 99)
-        rt, nt = _train_and_eval(eng, log, P, Q, MODE_HOGWILD_STORE, 12, 0.05, 99)
+        rs, ns = _train_and_eval(eng, log, P, Q, MODE_SERIAL, 10, 0.05, 99)
+        r2, n2 = _train_and_eval(eng, log, P, Q, MODE_SERIAL, 10, 0.05, 100)
+        rh, nh = _train_and_eval(eng, log, P, Q, MODE_HOGWILD, 10, 0.05, 99)
     finally:
         eng.close()
-    print("recall@10 serial %.4f hogwild %.4f store %.4f | ndcg@10 %.4f %.4f %.4f" % (rs, rh, rt, ns, nh, nt))
+    print("\nrecall@10 serial %.4f serial(seed2) %.4f hogwild %.4f | ndcg@10 %.4f %.4f %.4f"
+          % (rs, r2, rh, ns, n2, nh))
     assert rs > 0.05                       # the model actually learned something
     assert abs(rh - rs) < 0.005 and abs(nh - ns) < 0.005
 
 
 def test_hot_row_path_conserves_updates(monkeypatch):
-    """With lr-free bookkeeping the hot path must not lose or duplicate deltas: regI = 0 and a
-    frozen P (regU = 0, huge user count of one event each is not needed) -- compare the column sums
-    of Q's movement between the direct and the shared-memory path on a conflict-heavy log."""
+    """The shared-memory hot path must neither lose nor duplicate deltas.  With a tiny learning
+    rate the epoch is in the linear regime (row movement independent of update order), so the
+    movement of P and Q must agree between the direct path and the hot path on a conflict-heavy
+    log where the 64 hottest tracks carry most plays."""
     from yue_b200.engine import Engine
-    log = synth.power_law_log(1500, 64, 150000, seed=4)          # 64 tracks: every row is hot
+    log = synth.power_law_log(1500, 400, 150000, seed=4)         # few tracks: the 64 hottest carry most plays
     P, Q = synth.init_factors(log.m, log.n, 64, seed=6)
     out = {}
     for name, min_count in (("direct", "1000000000"), ("hot", "1")):
@@ -236,7 +241,7 @@ def test_hot_row_path_conserves_updates(monkeypatch):
         try:
             eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
             eng.set_factors(P, Q)
-            loss = eng.bpr_epoch(1e-4, 0.0, 0.0, 3, 0, MODE_HOGWILD)     # tiny lr: updates ~ linear, order-free
+            loss = eng.bpr_epoch(1e-5, 0.0, 0.0, 3, 0, MODE_HOGWILD)     # tiny lr: updates ~ linear, order-free
             out[name] = (loss, eng.get_factors())
         finally:
             eng.close()

@@ -1,13 +1,17 @@
 // K1+K2: fused negative sampler + BPR triplet update (replaces recommender/cf/BPR.py:42-58).
 //
 // Work decomposition.  Events are stored user-major (BPR.py:42-45).  The host cuts every
-// user's event range into SEGMENTS of <= 32 consecutive events (one user per segment) and
-// gives every warp a CONTIGUOUS slice of segments holding ~T/W events.  A warp walks its
-// slice in order, so
-//   * P[u] lives in registers while the warp stays on user u and is published once when the
-//     user changes: P traffic is ~2 rows per USER instead of 2 per triplet, and a user that
-//     lies inside one slice sees exactly the serial update order of the reference;
-//   * only slice-boundary users and the shared Q rows are touched by several warps.
+// user's event range into SEGMENTS of <= 32 consecutive events and groups them into WORK ITEMS:
+// one item per user, except that a heavy user is split into items of <= kItemSegs segments.
+// Warps pull items from a global cursor IN STREAM ORDER, so the work in flight is always a
+// sliding window of W adjacent users -- the closest a parallel schedule gets to the reference's
+// user-major serial order (the model BPR-SGD reaches depends on that order: with exact arithmetic
+// and no staleness at all, walking W distant user ranges at once already changes |Q[hot]| by 20 %
+// while a window of adjacent users reproduces the serial result; tools/quality_study.py).
+//   * P[u] lives in registers for the whole item and is published once at its end: ~2 rows of
+//     P traffic per USER instead of per triplet, and a single-item user sees exactly the serial
+//     update order of the reference;
+//   * only multi-item (heavy) users and the shared Q rows are touched by several warps.
 // Per segment the 32 lanes first draw the negatives of 32 events in parallel (Philox +
 // rejection against the user's sorted play row), then the warp applies the 32 updates one
 // after the other with the next PF row pairs already in flight.
@@ -39,8 +43,10 @@ struct SgdParams {
     uint32_t n_items;
     const int64_t* seg_begin;      // [nseg] first local event of the segment
     const int32_t* seg_user;       // [nseg] local user
-    const int32_t* seg_len;        // [nseg] 1..32, | kSegShared when the user spans several warps
-    const int64_t* warp_seg;       // [n_warps+1] segment slice per warp
+    const int32_t* seg_len;        // [nseg] 1..32, | kSegShared when the user spans several items
+    const int64_t* item_ptr;       // [n_items+1] segment range of each work item (stream order)
+    int64_t n_work;
+    unsigned long long* cursor;    // next item to hand out (zeroed before the launch)
     int n_warps;
     const int32_t* ev_items;       // [T] positives; a value v < 0 names hot slot -v-1 (see hot_items)
     const int32_t* ev_neg;         // [T] negatives, or nullptr -> sample in-kernel
@@ -127,7 +133,6 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
     const int half = lane >> 4;
     const int l16 = lane & 15;
     const bool has_work = warp < p.n_warps;
-    const int64_t sb = has_work ? p.warp_seg[warp] : 0, se = has_work ? p.warp_seg[warp + 1] : 0;
     using R = RowOps<NCH, MODE>;
 
     bool act[NCH];
@@ -157,6 +162,15 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
         }
     };
 
+    auto take_item = [&]() -> int64_t {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(p.cursor, 1ull);
+        return (int64_t)__shfl_sync(0xffffffffu, it, 0);
+    };
+    int64_t item = has_work ? take_item() : p.n_work;
+    while (item < p.n_work) {
+    const int64_t next_item = take_item();          // fetched early: its latency hides behind the item
+    const int64_t sb = p.item_ptr[item], se = p.item_ptr[item + 1];
     for (int64_t seg = sb; seg < se; ++seg) {
         const int u = p.seg_user[seg];
         const int64_t begin = p.seg_begin[seg];
@@ -330,6 +344,8 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
             }
         }
     }
+    item = next_item;
+    }   // while items
     flush_user();
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss, loss);
     if (MODE != kSerial && p.n_hot > 0) {            // publish what is left in the CTA's hot deltas

@@ -73,10 +73,14 @@ struct yue_handle {
     int device = 0;
     int sm_count = 148;
     int warps_per_sm = kSgdThreads / 32;   // one resident CTA per SM, a single wave
-    int min_events_per_warp = 2048;   // small logs get fewer warps: bounds Hogwild staleness
+    // Small logs get fewer warps.  tools/quality_study.py: at >= 16 K events per warp (what config
+    // C2 has on a full B200) the sliding-window schedule reproduces the serial model's Recall/NDCG to
+    // 1e-4; at <= 4 K events per warp heavy-user items become stragglers, light users finish long
+    // before the heavy ones (the opposite of the serial order) and Recall@10 drops by 2-8 points.
+    int min_events_per_warp = 16384;
     int hot_max = 64;                 // shared-memory hot-row slots per CTA
     int hot_min_count = 16384;        // a track is hot when it is the positive of at least this many events
-    int hot_flush = 16;               // updates of a slot between publishes
+    int hot_flush = 4;                // updates of a slot (per CTA) between publishes; 64 diverges, 4 and 16 run equally fast
     int n_hot = 0;
     DevBuf<int32_t> hot_items, hot_slot, item_counts;
     size_t l2_bytes = 0;
@@ -95,7 +99,9 @@ struct yue_handle {
     // segments of the epoch kernels
     int64_t nseg = 0;
     int n_warps = 0;
-    DevBuf<int64_t> seg_begin, warp_seg, warp_seg_serial;
+    DevBuf<int64_t> seg_begin, item_ptr;
+    int64_t n_items = 0;
+    DevBuf<unsigned long long> cursor;
     DevBuf<int32_t> seg_user, seg_len;
 
     // factors
@@ -132,39 +138,28 @@ struct yue_handle {
 
 static int fail(yue_t* h, int code, const std::string& msg) { h->err = msg; return code; }
 
-// Cut every user's event range into <=32-event segments and slice them evenly over n_warps.
-static void build_segments(const int64_t* indptr, int64_t m, std::vector<int64_t>& sb,
-                           std::vector<int32_t>& su, std::vector<int32_t>& sl) {
-    sb.clear(); su.clear(); sl.clear();
-    for (int64_t u = 0; u < m; ++u) {
-        for (int64_t b = indptr[u], e = indptr[u + 1]; b < e; b += 32) {
-            sb.push_back(b); su.push_back((int32_t)u); sl.push_back((int32_t)std::min<int64_t>(32, e - b));
+// Cut every user's event range into <=32-event segments and group them into work items: one item
+// per user, heavy users split into items of <= kItemSegs segments (all their segments are then
+// flagged kSegShared: several warps work on that user and re-read P[u] at every segment).
+static void build_items_from_runs(const std::vector<int64_t>& run_begin, const std::vector<int64_t>& run_end,
+                                  const std::vector<int32_t>& run_user, bool allow_shared, int64_t kItemSegs,
+                                  std::vector<int64_t>& sb, std::vector<int32_t>& su, std::vector<int32_t>& sl,
+                                  std::vector<int64_t>& item_ptr) {
+    sb.clear(); su.clear(); sl.clear(); item_ptr.clear();
+    item_ptr.push_back(0);
+    for (size_t r = 0; r < run_begin.size(); ++r) {
+        const int64_t first = (int64_t)sb.size();
+        for (int64_t b = run_begin[r], e = run_end[r]; b < e; b += 32) {
+            sb.push_back(b); su.push_back(run_user[r]); sl.push_back((int32_t)std::min<int64_t>(32, e - b));
         }
-    }
-}
-static void slice_segments(const std::vector<int64_t>& sb, const std::vector<int32_t>& sl, int64_t T,
-                           int n_warps, std::vector<int64_t>& ws) {
-    ws.assign((size_t)n_warps + 1, (int64_t)sb.size());
-    ws[0] = 0;
-    const int64_t nseg = (int64_t)sb.size();
-    int64_t seg = 0;
-    for (int w = 1; w < n_warps; ++w) {
-        const int64_t target = (int64_t)((__int128)T * w / n_warps);   // first event of warp w
-        while (seg < nseg && sb[seg] + sl[seg] <= target) ++seg;       // segments ending before it stay left
-        ws[w] = seg;
-    }
-    ws[n_warps] = nseg;
-}
-// Flag every segment of a user whose segments fall into more than one warp slice.
-static void mark_shared_users(const std::vector<int32_t>& su, std::vector<int32_t>& sl,
-                              const std::vector<int64_t>& ws) {
-    const int64_t nseg = (int64_t)su.size();
-    for (size_t w = 1; w + 1 < ws.size(); ++w) {
-        const int64_t s0 = ws[w];
-        if (s0 <= 0 || s0 >= nseg || su[s0] != su[s0 - 1] || (sl[s0] & kSegShared)) continue;
-        const int32_t u = su[s0];
-        for (int64_t s = s0; s < nseg && su[s] == u; ++s) sl[s] |= kSegShared;
-        for (int64_t s = s0 - 1; s >= 0 && su[s] == u; --s) sl[s] |= kSegShared;
+        const int64_t nsegs = (int64_t)sb.size() - first;
+        if (nsegs == 0) continue;
+        if (nsegs > kItemSegs && allow_shared)
+            for (int64_t s = first; s < first + nsegs; ++s) sl[s] |= kSegShared;
+        if (allow_shared)
+            for (int64_t s = first; s < first + nsegs; s += kItemSegs) item_ptr.push_back(std::min(first + nsegs, s + kItemSegs));
+        else
+            item_ptr.push_back(first + nsegs);
     }
 }
 
@@ -217,7 +212,8 @@ int yue_destroy(yue_t* h) {
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     rank_tc_release(h->tc);
-    for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->seg_begin, &h->warp_seg, &h->warp_seg_serial, &h->tmp_sb, &h->tmp_ws}) b->release();
+    for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->seg_begin, &h->item_ptr, &h->tmp_sb, &h->tmp_ws}) b->release();
+    h->cursor.release();
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->seg_user, &h->seg_len, &h->tmp_i, &h->tmp_j,
                     &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts}) b->release();
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->rk_scores, &h->pred}) b->release();
@@ -267,23 +263,25 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     h->h_ev_indptr.assign(ev_indptr, ev_indptr + m_local + 1);
     h->have_ev_user = false;
 
-    std::vector<int64_t> sb, ws;
-    std::vector<int32_t> su, sl;
-    build_segments(ev_indptr, m_local, sb, su, sl);
-    h->nseg = (int64_t)sb.size();
+    std::vector<int64_t> sb, ip, rb((size_t)m_local), re((size_t)m_local);
+    std::vector<int32_t> su, sl, ru((size_t)m_local);
+    for (int64_t u = 0; u < m_local; ++u) { rb[u] = ev_indptr[u]; re[u] = ev_indptr[u + 1]; ru[u] = (int32_t)u; }
+    // concurrency: at most one resident wave, fewer warps on small logs (bounds Hogwild staleness
+    // and keeps the in-flight window a small fraction of the users)
     h->n_warps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
-    slice_segments(sb, sl, T, h->n_warps, ws);
-    mark_shared_users(su, sl, ws);
-    const int64_t serial[2] = {0, h->nseg};
+    // a heavy user's item is at most a quarter of a warp's fair share, so no item is a straggler
+    const int64_t item_segs = std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)h->n_warps * 4 * 32)));
+    build_items_from_runs(rb, re, ru, true, item_segs, sb, su, sl, ip);
+    h->nseg = (int64_t)sb.size();
+    h->n_items = (int64_t)ip.size() - 1;
     CK(h->seg_begin.resize(h->nseg)); CK(h->seg_user.resize(h->nseg)); CK(h->seg_len.resize(h->nseg));
-    CK(h->warp_seg.resize(ws.size())); CK(h->warp_seg_serial.resize(2));
+    CK(h->item_ptr.resize(ip.size())); CK(h->cursor.resize(1));
     if (h->nseg) {
         CK(cudaMemcpyAsync(h->seg_begin.p, sb.data(), sb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->seg_user.p, su.data(), su.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->seg_len.p, sl.data(), sl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     }
-    CK(cudaMemcpyAsync(h->warp_seg.p, ws.data(), ws.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->warp_seg_serial.p, serial, sizeof(serial), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->item_ptr.p, ip.data(), ip.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     // hot tracks: device histogram of the positives, top hot_max by count on the host, then the hot
     // positives of the device copy of ev_items are re-labelled -slot-1 (see SgdParams::hot_items)
     h->n_hot = 0;
@@ -404,6 +402,8 @@ static cudaError_t launch_sgd(const SgdParams& sp, int mode, cudaStream_t st) {
 static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
     REQUIRE(mode >= YUE_MODE_SERIAL && mode <= YUE_MODE_HOGWILD_STORE, YUE_E_ARG, "unknown mode");
     CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
+    sp.cursor = h->cursor.p;
     sp.P = h->P.p; sp.Q = h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
     const int nch = (sp.nchunks + 15) / 16;
@@ -437,7 +437,7 @@ int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, 
     SgdParams sp{};
     fill_rates(sp, lr, regU, regI);
     sp.seg_begin = h->seg_begin.p; sp.seg_user = h->seg_user.p; sp.seg_len = h->seg_len.p;
-    sp.warp_seg = mode == YUE_MODE_SERIAL ? h->warp_seg_serial.p : h->warp_seg.p;
+    sp.item_ptr = h->item_ptr.p; sp.n_work = h->n_items;
     sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
     sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot; sp.hot_flush = h->hot_flush;
@@ -451,36 +451,35 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
     REQUIRE(T >= 0 && (T == 0 || (u && i && j)), YUE_E_ARG, "null triplet array");
     CK(cudaSetDevice(h->device));
     if (T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
-    std::vector<int64_t> sb, ws;
-    std::vector<int32_t> su, sl;
-    for (int64_t t = 0; t < T;) {               // runs of one user, <= 32 long
-        REQUIRE(u[t] >= 0 && u[t] < h->m && i[t] >= 0 && i[t] < h->n && j[t] >= 0 && j[t] < h->n, YUE_E_ARG,
-                "triplet index out of range");
-        int64_t e = t + 1;
-        while (e < T && e - t < 32 && u[e] == u[t]) {
-            REQUIRE(i[e] >= 0 && i[e] < h->n && j[e] >= 0 && j[e] < h->n, YUE_E_ARG, "triplet index out of range");
+    std::vector<int64_t> sb, ip, rb, re;
+    std::vector<int32_t> su, sl, ru;
+    for (int64_t t = 0; t < T;) {               // runs of one user
+        REQUIRE(u[t] >= 0 && u[t] < h->m, YUE_E_ARG, "triplet user out of range");
+        int64_t e = t;
+        while (e < T && u[e] == u[t]) {
+            REQUIRE(i[e] >= 0 && i[e] < h->n && j[e] >= 0 && j[e] < h->n, YUE_E_ARG, "triplet item out of range");
             ++e;
         }
-        sb.push_back(t); su.push_back(u[t]); sl.push_back((int32_t)(e - t));
+        rb.push_back(t); re.push_back(e); ru.push_back(u[t]);
         t = e;
     }
     const int n_warps = mode == YUE_MODE_SERIAL ? 1
         : (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
-    slice_segments(sb, sl, T, n_warps, ws);
-    if (mode != YUE_MODE_SERIAL) mark_shared_users(su, sl, ws);
+    build_items_from_runs(rb, re, ru, mode != YUE_MODE_SERIAL,
+                          std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)n_warps * 4 * 32))), sb, su, sl, ip);
     CK(h->tmp_i.resize(T)); CK(h->tmp_j.resize(T));
     CK(h->tmp_sb.resize(sb.size())); CK(h->tmp_su.resize(su.size())); CK(h->tmp_sl.resize(sl.size()));
-    CK(h->tmp_ws.resize(ws.size()));
+    CK(h->tmp_ws.resize(ip.size())); CK(h->cursor.resize(1));
     CK(cudaMemcpyAsync(h->tmp_i.p, i, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tmp_j.p, j, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tmp_sb.p, sb.data(), sb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tmp_su.p, su.data(), su.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tmp_sl.p, sl.data(), sl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->tmp_ws.p, ws.data(), ws.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_ws.p, ip.data(), ip.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     SgdParams sp{};
     fill_rates(sp, lr, regU, regI);
     sp.seg_begin = h->tmp_sb.p; sp.seg_user = h->tmp_su.p; sp.seg_len = h->tmp_sl.p;
-    sp.warp_seg = h->tmp_ws.p; sp.n_warps = n_warps;
+    sp.item_ptr = h->tmp_ws.p; sp.n_work = (int64_t)ip.size() - 1; sp.n_warps = n_warps;
     sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
     sp.n_hot = 0; sp.hot_flush = 1;              // explicit triplets take the direct path
     int rc = run_sgd(h, sp, mode, loss_out);
