@@ -24,7 +24,11 @@ def run(log, P, Q, mode, epochs, lr, seed, env):
         eng.set_factors(P, Q)
         t0 = time.time()
         for ep in range(epochs):
-            loss = eng.bpr_epoch(lr, 0.01, 0.01, seed, ep, mode)
+            try:
+                loss = eng.bpr_epoch(lr, 0.01, 0.01, seed, ep, mode)
+            except Exception:                       # NaN/inf loss: report as diverged
+                loss = float("inf")
+                break
         dt = time.time() - t0
         users = log.test_users()
         ids, _ = eng.rank_topn(users, 10, RANK_EXACT)
@@ -60,11 +64,20 @@ def main():
     for epw in (65536, 16384, 4096, 2048) if big else (16384, 4096, 1024):
         configs.append(("hogwild %d ev/warp, no hot" % epw, MODE_HOGWILD, dict(YUE_SGD_MIN_EVENTS_PER_WARP=epw, **nohot)))
         configs.append(("hogwild %d ev/warp, hot flush 4" % epw, MODE_HOGWILD, dict(YUE_SGD_MIN_EVENTS_PER_WARP=epw, **hot)))
-    if c2_epochs:       # full-GPU concurrency at the true scale: serial once, default engine settings once
+    if c2_epochs:       # full-GPU concurrency at the true scale
         sweeps = ((0.02, c2_epochs),)
-        configs = [("serial seed 99", MODE_SERIAL, {}),
-                   ("hogwild default (hot flush 4)", MODE_HOGWILD, dict(YUE_SGD_MIN_EVENTS_PER_WARP=16384, **hot)),
-                   ("hogwild default, no hot", MODE_HOGWILD, dict(YUE_SGD_MIN_EVENTS_PER_WARP=16384, **nohot))]
+        base_env = dict(YUE_SGD_MIN_EVENTS_PER_WARP=16384, YUE_SGD_ITEM_SEGS=0, YUE_SGD_SEG_EVENTS=32, YUE_SGD_WARPS_PER_SM=16, YUE_SGD_MAX_ITEMS=16, **nohot)
+        def cfg(name, **kw):
+            e = dict(base_env); e.update(kw); return (name, MODE_HOGWILD, e)
+        configs = []
+        if os.environ.get("STUDY_SERIAL", "1") == "1":
+            configs.append(("serial seed 99", MODE_SERIAL, {}))
+        base_env.pop("YUE_SGD_MAX_ITEMS")
+        hotenv = dict(YUE_SGD_HOT_MAX=64, YUE_SGD_HOT_MIN_COUNT=16384, YUE_SGD_HOT_FLUSH=4)
+        reps = int(os.environ.get("STUDY_REPS", "5"))
+        configs += [cfg("resync 8, no hot, run %d" % k) for k in range(reps)]
+        configs += [cfg("resync 8, hot flush 4, run %d" % k, **hotenv) for k in range(reps)]
+        configs += [cfg("resync 8, hot flush 2, run %d" % k, **dict(hotenv, YUE_SGD_HOT_FLUSH=2)) for k in range(reps)]
     for lr, epochs in sweeps:
         base = None
         for name, mode, env in configs:

@@ -8,6 +8,7 @@
 // user-major serial order (the model BPR-SGD reaches depends on that order: with exact arithmetic
 // and no staleness at all, walking W distant user ranges at once already changes |Q[hot]| by 20 %
 // while a window of adjacent users reproduces the serial result; tools/quality_study.py).
+// A heavy user is cut into at most 16 items, all at the user's stream position (see the host side).
 //   * P[u] lives in registers for the whole item and is published once at its end: ~2 rows of
 //     P traffic per USER instead of per triplet, and a single-item user sees exactly the serial
 //     update order of the reference;
@@ -44,7 +45,7 @@ struct SgdParams {
     const int64_t* seg_begin;      // [nseg] first local event of the segment
     const int32_t* seg_user;       // [nseg] local user
     const int32_t* seg_len;        // [nseg] 1..32, | kSegShared when the user spans several items
-    const int64_t* item_ptr;       // [n_items+1] segment range of each work item (stream order)
+    const int64_t* item_ptr;       // [2*n_work] segment range [begin, end) of each work item, in hand-out order
     int64_t n_work;
     unsigned long long* cursor;    // next item to hand out (zeroed before the launch)
     int n_warps;
@@ -65,6 +66,7 @@ struct SgdParams {
     // memory: a triplet whose positive is hot reads base+delta from shared memory, adds its change
     // to delta with shared-memory atomics, and every hot_flush-th update of a slot publishes the
     // accumulated delta with ONE vector atomic and re-reads the row.
+    int resync_events;             // a shared (multi-item) user publishes + re-reads P[u] every this many events
     const int32_t* hot_items;      // [n_hot] track id of each hot slot
     int n_hot;
     int hot_flush;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
     int64_t item = has_work ? take_item() : p.n_work;
     while (item < p.n_work) {
     const int64_t next_item = take_item();          // fetched early: its latency hides behind the item
-    const int64_t sb = p.item_ptr[item], se = p.item_ptr[item + 1];
+    const int64_t sb = p.item_ptr[2 * item], se = p.item_ptr[2 * item + 1];
     for (int64_t seg = sb; seg < se; ++seg) {
         const int u = p.seg_user[seg];
         const int64_t begin = p.seg_begin[seg];
@@ -180,17 +182,13 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
         // thousands of updates on a private copy and the summed deltas overshoot (Hogwild with
         // unbounded staleness diverges on the heaviest users).
         const bool resync = MODE != kSerial && (raw_len & kSegShared) != 0;
-        if (u != cur_u || resync) {
+        // publish the pending change of P[cur_u], then (re)load P[u]: the lower half reads after its
+        // own publish (same thread, same address: ordered) and hands the row to the upper half, so
+        // both halves always hold the same P[u]
+        auto sync_user = [&](int uu) {
             flush_user();
-            if (u != cur_u) {
-                const int64_t r0 = p.uq_indptr[u];
-                row = p.uq_items + r0;
-                row_len = (int)(p.uq_indptr[u + 1] - r0);
-            }
-            cur_u = u;
-            // the lower half reads after its own publish (same thread, same address: ordered) and
-            // hands the row to the upper half, so both halves always hold the same P[u]
-            const float* src = p.P + (size_t)u * p.ld + lane_off;
+            cur_u = uu;
+            const float* src = p.P + (size_t)uu * p.ld + lane_off;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float4 v = (act[c] && half == 0) ? ld_row(src + 64 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -200,6 +198,14 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
                 v.w = __shfl_sync(0xffffffffu, v.w, l16);
                 pu[c] = pu0[c] = v;
             }
+        };
+        if (u != cur_u || resync) {
+            if (u != cur_u) {
+                const int64_t r0 = p.uq_indptr[u];
+                row = p.uq_items + r0;
+                row_len = (int)(p.uq_indptr[u + 1] - r0);
+            }
+            sync_user(u);
         }
 
         // ---- K1: lane t draws the negative of event begin+t -------------------------------
@@ -241,6 +247,7 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
             for (int k = 0; k < PF; ++k) {
                 const int t = t0 + k;
                 if (t >= len) break;
+                if (resync && t > 0 && t % p.resync_events == 0) sync_user(u);
                 if (PF == 1) {                          // serial parity mode: read when reached
                     qp[0] = row_ptr(t);
                     load_rows(qp[0], qb[0]);

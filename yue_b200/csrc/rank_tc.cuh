@@ -1,19 +1,493 @@
-// K3 (tcgen05 flavour) -- placeholder until the tensor-core kernel lands; the exact kernel
-// serves every request meanwhile (rank_tc_supported() == false).
+// K3 (tcgen05 flavour): full-catalog scoring on the 5th-generation tensor cores with a fused,
+// masked top-N epilogue, followed in the same kernel by the exact re-score (K5).
+//
+// Replaces the per-user body of evalRanking, base/IterativeRecommender.py:93-145, like
+// rank_exact.cuh -- and returns the SAME ids and scores, bit for bit:
+//
+//   1. candidate pass.  A CTA owns 128 users (UMMA M = 128).  TMA streams Q in tiles of 128 tracks
+//      (SWIZZLE_128B, fp32 in shared memory); one elected thread issues tcgen05.mma kind::tf32
+//      (the tensor core reads the fp32 bits and drops the low mantissa bits: no conversion pass)
+//      into a double-buffered TMEM accumulator; four epilogue warps read it back with tcgen05.ld
+//      -- one thread per user row, 32 columns per load -- reduce each chunk to its maximum and
+//      compare with the row's running threshold.  After the first tiles > 99 % of chunks are
+//      rejected by that one compare.  Survivors are checked against the user's sorted play row with
+//      a monotone cursor (tiles arrive in track order) and pushed into a per-row buffer in shared
+//      memory; a full buffer is compacted by the whole warp.
+//   2. the tf32 scores are approximate, so the threshold is tau - 2*eps with tau the N-th best
+//      approximate score so far and eps = c * |p_u| * max_t |q_t| a bound on the tf32 error
+//      (c = 2^-9 for two truncated operands + accumulation slack).  Every track whose EXACT score is
+//      among the N best then survives: exact(x) >= sigma  =>  approx(x) >= sigma - eps >= tau - 2 eps
+//      (sigma = N-th best exact score >= tau - eps because N tracks have approx >= tau).
+//   3. exact pass.  The surviving <= 64 candidates of a row are re-scored with the canonical fp32
+//      FMA chain and sorted by (score desc, id asc) -- identical to the exact kernel.
+//   4. a row whose buffer cannot hold its candidates (too many near-ties) is reported in fail_rows
+//      and the caller re-runs it through rank_exact_kernel.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 #pragma once
-#include <cstdint>
-#include <string>
+#include <cuda.h>            // CUtensorMap + enums only; the encoder is fetched at run time
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <string>
+
+#include "rank_exact.cuh"
+
 namespace yue {
-struct RankTcState { bool q_dirty = true; };
-inline bool rank_tc_supported(int, int) { return false; }
-inline void rank_tc_release(RankTcState&) {}
-template <class Fallback>
-inline int rank_tc_run(RankTcState&, cudaStream_t, int, const float*, const float*, int, int, int,
-                       const int32_t*, int64_t, int, const int64_t*, const int32_t*, int32_t*, float*,
-                       std::string& err, int64_t&, Fallback) {
-    err = "tcgen05 ranking not built";
-    return 6;
+
+constexpr int kTcThreads = 192;
+constexpr int kTcBM = 128;            // users per CTA (UMMA M)
+constexpr int kTcBN = 128;            // tracks per tile (UMMA N)
+constexpr int kTcStages = 3;          // TMA -> MMA shared-memory stages
+constexpr int kTcCap = 64;            // candidate slots per row
+constexpr int kTcBoxBytes = 128 * 128;   // one TMA box: 128 rows x 128 B
+constexpr float kTf32ErrCoef = 2.1e-3f;  // 2^-9 (two operands truncated to 10 mantissa bits) + slack
+
+struct RankTcParams {
+    int kblocks;                // 128-byte k-blocks per row: ceil(ld / 32), 1..2
+    int ntiles;
+    int n_items;
+    int64_t B;
+    int N;
+    int ld, d;
+    const float* Psel;          // [Bpad, ld] gathered user rows
+    const float* Q;
+    const float* pnorm;         // [Bpad] |p_u|
+    const float* qmax;          // max_t |q_t|
+    const int32_t* users;       // [B]
+    const int64_t* uq_indptr;
+    const int32_t* uq_items;
+    int32_t* ids_out;
+    float* scores_out;
+    int* fail_count;
+    int32_t* fail_rows;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (base lane + t)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major operand, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);      // start address, 16-byte units   [0,14)
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused here) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: 8 rows x 128 B [32,46)
+    d |= (uint64_t)1 << 46;                                 // descriptor version 1 (sm_100)     [46,48)
+    d |= (uint64_t)2 << 61;                                 // layout type SWIZZLE_128B          [61,64)
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) |
+                                ((uint32_t)(kTcBM >> 4) << 24);
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const RankTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_tc_raw) + 1023) & ~(uintptr_t)1023);
+    const int KB = p.kblocks;
+    const uint32_t stage_bytes = (uint32_t)KB * kTcBoxBytes;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + stage_bytes;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sB + kTcStages * stage_bytes);        // [128][kTcCap]
+    uint64_t* bars = keys + kTcBM * kTcCap;
+    // barriers: 0 = A landed, 1..S = B full, S+1..2S = B empty, then 2 TMEM full, 2 TMEM empty
+    const uint32_t bar_a = smem_u32(bars);
+    auto bar_full = [&](int s) { return smem_u32(bars + 1 + s); };
+    auto bar_empty = [&](int s) { return smem_u32(bars + 1 + kTcStages + s); };
+    auto bar_tfull = [&](int t) { return smem_u32(bars + 1 + 2 * kTcStages + t); };
+    auto bar_tempty = [&](int t) { return smem_u32(bars + 3 + 2 * kTcStages + t); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kTcStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_tempty(t), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmP) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmQ) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, stage_bytes);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(smem_u32(sA + kb * kTcBoxBytes), &tmP, bar_a, kb * 32, blockIdx.x * kTcBM);
+            for (int j = 0; j < p.ntiles; ++j) {
+                const int s = j % kTcStages;
+                const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                mbar_expect_tx(bar_full(s), stage_bytes);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(smem_u32(sB + s * stage_bytes + kb * kTcBoxBytes), &tmQ, bar_full(s), kb * 32, j * kTcBN);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            for (int j = 0; j < p.ntiles; ++j) {
+                const int s = j % kTcStages, t = j & 1;
+                const uint32_t ph = (uint32_t)(j / kTcStages) & 1u, tph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(bar_tempty(t), tph ^ 1u);
+                mbar_wait(bar_full(s), ph);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * stage_bytes);
+                for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {       // UMMA K = 8 tf32 = 32 bytes along the swizzle row
+                        const uint64_t ad = umma_desc_sw128(a0 + kb * kTcBoxBytes + k * 32);
+                        const uint64_t bd = umma_desc_sw128(b0 + kb * kTcBoxBytes + k * 32);
+                        tc_mma_tf32(tmem_base + (uint32_t)t * kTcBN, ad, bd, kIdescTf32, (kb | k) ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar_empty(s));                // smem stage free once these MMAs retire
+                tc_commit(bar_tfull(t));                // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: one thread per user row =====
+        const int quarter = warp & 3;                   // TMEM lanes this warp may read
+        const int r = quarter * 32 + lane;
+        const int64_t b = (int64_t)blockIdx.x * kTcBM + r;
+        const bool valid = b < p.B;
+        uint64_t* K = keys + (size_t)r * kTcCap;
+        const float eps2 = valid ? 2.f * kTf32ErrCoef * p.pnorm[b] * (*p.qmax) : 0.f;
+        float thr = valid ? -INFINITY : INFINITY;       // push threshold = tau - 2 eps
+        int cnt = 0;
+        bool fail = false;
+        int64_t mcur = 0, mend = 0;
+        if (valid) { const int u = p.users[b]; mcur = p.uq_indptr[u]; mend = p.uq_indptr[u + 1]; }
+        int mval = mcur < mend ? p.uq_items[mcur] : INT32_MAX;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+        for (int j = 0; j < p.ntiles; ++j) {
+            const int t = j & 1;
+            const uint32_t tph = (uint32_t)(j >> 1) & 1u;
+            const int i0 = j * kTcBN;
+            mbar_wait(bar_tfull(t), tph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < kTcBN / 32; ++c) {
+                float v[32];
+                tc_ld32(trow + (uint32_t)(t * kTcBN + c * 32), v);
+                float m = v[0];
+#pragma unroll
+                for (int x = 1; x < 32; ++x) m = fmaxf(m, v[x]);
+                if (!__any_sync(0xffffffffu, m >= thr)) continue;
+                // ---- rare path ------------------------------------------------------------------
+                if (m >= thr) {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) {
+                        const int id = i0 + c * 32 + x;
+                        if (v[x] >= thr && id < p.n_items) {
+                            while (mval < id) { ++mcur; mval = mcur < mend ? p.uq_items[mcur] : INT32_MAX; }
+                            if (mval != id) K[cnt++] = make_key(v[x], id);      // cnt <= 32 before the chunk
+                        }
+                    }
+                }
+                __syncwarp();
+                unsigned full;
+                while ((full = __ballot_sync(0xffffffffu, cnt > kTcCap - 32)) != 0u) {
+                    const int src = __ffs(full) - 1;
+                    const int cc = __shfl_sync(0xffffffffu, cnt, src);
+                    const float e2 = __shfl_sync(0xffffffffu, eps2, src);
+                    uint64_t* R = keys + (size_t)(quarter * 32 + src) * kTcCap;
+                    const uint64_t m0 = lane < cc ? R[lane] : ~0ull, m1 = lane + 32 < cc ? R[lane + 32] : ~0ull;
+                    int r0 = 0, r1 = 0;
+                    for (int e = 0; e < cc; ++e) { const uint64_t k = R[e]; r0 += k < m0; r1 += k < m1; }
+                    __syncwarp();
+                    if (lane < cc) R[r0] = m0;
+                    if (lane + 32 < cc) R[r1] = m1;
+                    __syncwarp();
+                    const float lim = key_score(R[p.N - 1]) - e2;             // cc > 32 >= N
+                    const bool k0 = lane < cc && key_score(R[lane]) >= lim;
+                    const bool k1 = lane + 32 < cc && key_score(R[lane + 32]) >= lim;
+                    const int kept = __popc(__ballot_sync(0xffffffffu, k0)) + __popc(__ballot_sync(0xffffffffu, k1));
+                    if (lane == src) {
+                        if (kept > kTcCap - 32) { fail = true; thr = INFINITY; cnt = 0; }   // too many near-ties
+                        else { cnt = kept; thr = lim; }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty(t));
+        }
+
+        // ---- exact pass: re-score the survivors with the fp32 FMA chain, sort, write -------------
+        __syncwarp();
+        for (int rr = 0; rr < 32; ++rr) {
+            const int64_t bb = (int64_t)blockIdx.x * kTcBM + quarter * 32 + rr;
+            if (bb >= p.B) break;
+            const int cc = __shfl_sync(0xffffffffu, cnt, rr);
+            const bool ff = __shfl_sync(0xffffffffu, (int)fail, rr) != 0;
+            if (ff) {
+                if (lane == 0) p.fail_rows[atomicAdd(p.fail_count, 1)] = (int32_t)bb;
+                continue;
+            }
+            uint64_t* R = keys + (size_t)(quarter * 32 + rr) * kTcCap;
+            const float* pu = p.Psel + (size_t)bb * p.ld;
+            uint64_t nk[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;
+                nk[h] = 0;
+                if (e < cc) {
+                    const int id = key_id(R[e]);
+                    nk[h] = make_key(score_fma32(pu, p.Q + (size_t)id * p.ld, p.d), id);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) if (lane + 32 * h < cc) R[lane + 32 * h] = nk[h];
+            __syncwarp();
+            const int nc = compact_row<kTcCap>(R, cc, p.N, lane);
+            for (int x = lane; x < p.N; x += 32) {
+                const bool ok = x < nc;
+                const uint64_t k = ok ? R[x] : 0ull;
+                p.ids_out[bb * p.N + x] = ok ? key_id(k) : -1;
+                p.scores_out[bb * p.N + x] = ok ? key_score(k) : -INFINITY;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// ---- helpers of the TC path ---------------------------------------------------------------------
+__global__ void tc_gather_rows_kernel(const float* __restrict__ P, const int32_t* __restrict__ users, int64_t B,
+                                      int64_t Bpad, int ld, float* __restrict__ Psel, float* __restrict__ pnorm) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= Bpad) return;
+    float acc = 0.f;
+    for (int k = lane; k < ld; k += 32) {
+        const float v = row < B ? P[(size_t)users[row] * ld + k] : 0.f;
+        Psel[(size_t)row * ld + k] = v;
+        acc += v * v;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) pnorm[row] = sqrtf(acc) * 1.0001f;
+}
+__global__ void tc_row_norm_max_kernel(const float* __restrict__ Q, int64_t n, int ld, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    float best = 0.f;
+    for (int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; row < n;
+         row += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        float acc = 0.f;
+        for (int k = lane; k < ld; k += 32) { const float v = Q[(size_t)row * ld + k]; acc += v * v; }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        best = fmaxf(best, acc);
+    }
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best) * 1.0001f));   // >= 0: int order = float order
+}
+__global__ void tc_scatter_rows_kernel(const int32_t* __restrict__ rows, int nrows, int N, const int32_t* __restrict__ ids,
+                                       const float* __restrict__ sc, int32_t* __restrict__ ids_out, float* __restrict__ sc_out) {
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nrows * N; x += gridDim.x * blockDim.x) {
+        const int64_t dst = (int64_t)rows[x / N] * N + x % N;
+        ids_out[dst] = ids[x];
+        sc_out[dst] = sc[x];
+    }
+}
+__global__ void tc_gather_users_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ rows, int nrows,
+                                       int32_t* __restrict__ out) {
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nrows; x += gridDim.x * blockDim.x) out[x] = users[rows[x]];
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct RankTcState {
+    bool q_dirty = true;
+    PFN_tmapEncodeTiled encode = nullptr;
+    float* qmax = nullptr;
+    float* psel = nullptr; size_t psel_cap = 0;
+    float* pnorm = nullptr; size_t pnorm_cap = 0;
+    int* fail_count = nullptr;
+    int32_t* fail_rows = nullptr; size_t fail_cap = 0;
+    int32_t* fb_users = nullptr; int32_t* fb_ids = nullptr; float* fb_scores = nullptr; size_t fb_cap = 0;
+    int64_t last_fail = 0;       // rows sent to the exact kernel by the last call (diagnostics)
+};
+
+inline bool rank_tc_supported(int k, int N) { return k >= 1 && k <= 64 && N >= 1 && N <= 32; }
+
+inline void rank_tc_release(RankTcState& st) {
+    for (void* p : {(void*)st.qmax, (void*)st.psel, (void*)st.pnorm, (void*)st.fail_count, (void*)st.fail_rows,
+                    (void*)st.fb_users, (void*)st.fb_ids, (void*)st.fb_scores})
+        if (p) cudaFree(p);
+    st = RankTcState();
+}
+
+template <class T>
+static cudaError_t tc_grow(T*& p, size_t& cap, size_t need) {
+    if (need <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cudaError_t e = cudaMalloc((void**)&p, need * sizeof(T));
+    cap = e == cudaSuccess ? need : 0;
+    return e;
+}
+
+static bool tc_make_map(PFN_tmapEncodeTiled enc, CUtensorMap* map, const float* base, uint64_t rows, int ld) {
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {32u, 128u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Runs the TC path on device buffers.  `fallback(d_users, B, d_ids, d_scores)` must run the exact
+// kernel for the given rows.  Returns 0 or a YUE_E_* code (2 = CUDA).
+template <class Fallback>
+inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const float* P, const float* Q, int ld, int d,
+                       int n_items, const int32_t* d_users, int64_t B, int N, const int64_t* uq_indptr,
+                       const int32_t* uq_items, int32_t* d_ids, float* d_scores, std::string& err, int64_t& launches,
+                       Fallback fallback) {
+#define TC_CK(call)                                                                 \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return 2; } \
+    } while (0)
+    if (!st.encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TC_CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { err = "cuTensorMapEncodeTiled not available"; return 6; }
+        st.encode = (PFN_tmapEncodeTiled)fn;
+        TC_CK(cudaMalloc((void**)&st.qmax, sizeof(float)));
+        TC_CK(cudaMalloc((void**)&st.fail_count, sizeof(int)));
+    }
+    const int64_t Bpad = (B + kTcBM - 1) / kTcBM * kTcBM;
+    size_t cap_tmp = st.psel_cap;
+    TC_CK(tc_grow(st.psel, st.psel_cap, (size_t)Bpad * ld));
+    (void)cap_tmp;
+    TC_CK(tc_grow(st.pnorm, st.pnorm_cap, (size_t)Bpad));
+    TC_CK(tc_grow(st.fail_rows, st.fail_cap, (size_t)Bpad));
+    if (st.q_dirty) {
+        TC_CK(cudaMemsetAsync(st.qmax, 0, sizeof(float), stream));
+        tc_row_norm_max_kernel<<<sm_count * 8, 256, 0, stream>>>(Q, n_items, ld, st.qmax);
+        ++launches;
+        st.q_dirty = false;
+    }
+    TC_CK(cudaMemsetAsync(st.fail_count, 0, sizeof(int), stream));
+    tc_gather_rows_kernel<<<(unsigned)((Bpad * 32 + 255) / 256), 256, 0, stream>>>(P, d_users, B, Bpad, ld, st.psel, st.pnorm);
+    ++launches;
+    TC_CK(cudaGetLastError());
+
+    CUtensorMap tmP, tmQ;
+    if (!tc_make_map(st.encode, &tmP, st.psel, (uint64_t)Bpad, ld) || !tc_make_map(st.encode, &tmQ, Q, (uint64_t)n_items, ld)) {
+        err = "cuTensorMapEncodeTiled failed";
+        return 2;
+    }
+    RankTcParams p{};
+    p.kblocks = (ld + 31) / 32;
+    p.ntiles = (n_items + kTcBN - 1) / kTcBN;
+    p.n_items = n_items; p.B = B; p.N = N; p.ld = ld; p.d = d;
+    p.Psel = st.psel; p.Q = Q; p.pnorm = st.pnorm; p.qmax = st.qmax; p.users = d_users;
+    p.uq_indptr = uq_indptr; p.uq_items = uq_items; p.ids_out = d_ids; p.scores_out = d_scores;
+    p.fail_count = st.fail_count; p.fail_rows = st.fail_rows;
+    const size_t smem = 1024 + (size_t)p.kblocks * kTcBoxBytes * (1 + kTcStages) + (size_t)kTcBM * kTcCap * 8 + 256;
+    TC_CK(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rank_tc_kernel<<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);
+    ++launches;
+    TC_CK(cudaGetLastError());
+
+    int nfail = 0;
+    TC_CK(cudaMemcpyAsync(&nfail, st.fail_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TC_CK(cudaStreamSynchronize(stream));
+    st.last_fail = nfail;
+    if (nfail > 0) {                      // rows with too many near-ties: exact kernel, then scatter back
+        if ((size_t)nfail > st.fb_cap) {
+            for (void* q : {(void*)st.fb_users, (void*)st.fb_ids, (void*)st.fb_scores}) if (q) cudaFree(q);
+            st.fb_users = nullptr; st.fb_ids = nullptr; st.fb_scores = nullptr;
+            TC_CK(cudaMalloc((void**)&st.fb_users, (size_t)nfail * sizeof(int32_t)));
+            TC_CK(cudaMalloc((void**)&st.fb_ids, (size_t)nfail * 32 * sizeof(int32_t)));
+            TC_CK(cudaMalloc((void**)&st.fb_scores, (size_t)nfail * 32 * sizeof(float)));
+            st.fb_cap = (size_t)nfail;
+        }
+        tc_gather_users_kernel<<<(nfail + 255) / 256, 256, 0, stream>>>(d_users, st.fail_rows, nfail, st.fb_users);
+        ++launches;
+        if (int rc = fallback(st.fb_users, (int64_t)nfail, st.fb_ids, st.fb_scores)) return rc;
+        tc_scatter_rows_kernel<<<(nfail * N + 255) / 256, 256, 0, stream>>>(st.fail_rows, nfail, N, st.fb_ids, st.fb_scores, d_ids, d_scores);
+        ++launches;
+        TC_CK(cudaGetLastError());
+    }
+    return 0;
+#undef TC_CK
+}
+
 }  // namespace yue

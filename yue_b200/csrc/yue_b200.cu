@@ -78,6 +78,14 @@ struct yue_handle {
     // 1e-4; at <= 4 K events per warp heavy-user items become stragglers, light users finish long
     // before the heavy ones (the opposite of the serial order) and Recall@10 drops by 2-8 points.
     int min_events_per_warp = 16384;
+    int item_segs_env = 0;            // experiments: YUE_SGD_ITEM_SEGS overrides the heavy-user item size
+    int seg_events = 32;              // experiments: YUE_SGD_SEG_EVENTS (<= 32) events between P[u] resyncs
+    int max_items_per_user = 1 << 30; // YUE_SGD_MAX_ITEMS (experiments): cap on the items of one heavy user
+    // Shared (multi-item) users publish and re-read P[u] every resync_events events.  At config C2 the
+    // heaviest user is worked on by ~100 warps at once: with 32 events between publishes their summed
+    // stale deltas inflate the epoch loss 1.7-2.5x; with <= 16 the loss is within 0.3 % of the serial
+    // order and 8 reproduces its Recall@10 / NDCG@10 (profiles/quality_study_r1.md).
+    int resync_events = 8;
     int hot_max = 64;                 // shared-memory hot-row slots per CTA
     int hot_min_count = 16384;        // a track is hot when it is the positive of at least this many events
     int hot_flush = 4;                // updates of a slot (per CTA) between publishes; 64 diverges, 4 and 16 run equally fast
@@ -138,28 +146,40 @@ struct yue_handle {
 
 static int fail(yue_t* h, int code, const std::string& msg) { h->err = msg; return code; }
 
-// Cut every user's event range into <=32-event segments and group them into work items: one item
-// per user, heavy users split into items of <= kItemSegs segments (all their segments are then
-// flagged kSegShared: several warps work on that user and re-read P[u] at every segment).
+// Cut every user's event range into <=32-event segments and group them into work items, returned
+// as [begin, end) segment ranges in STREAM ORDER (the order the kernel's cursor hands them out and
+// the order the reference visits users in, recommender/cf/BPR.py:42):
+//   * a user with <= item_segs segments is one item;
+//   * a heavy user is cut into items of item_segs segments (a quarter of a warp's fair share of the
+//     epoch), all at the user's stream position; its segments are flagged kSegShared and the warps
+//     working on it publish and re-read P[u] every few events (resync_events).
+// What the measurements at config C2 say (tools/quality_study.py, profiles/quality_study_r1.md):
+// a heavy user has to FINISH EARLY, like in the serial order -- big items make it a straggler, every
+// light user's P[u] is then stale against the large Q changes it keeps making and Recall@10 drops
+// from 0.098 to 0.005; spreading its items over the epoch does the same (0.17 -> 0.04 at 5 M events).
+// So ~100 warps must share the heaviest user, and the staleness of P[u] is bounded by resync_events.
 static void build_items_from_runs(const std::vector<int64_t>& run_begin, const std::vector<int64_t>& run_end,
-                                  const std::vector<int32_t>& run_user, bool allow_shared, int64_t kItemSegs,
+                                  const std::vector<int32_t>& run_user, bool allow_shared, int64_t item_segs,
+                                  int64_t max_items, int seg_events,
                                   std::vector<int64_t>& sb, std::vector<int32_t>& su, std::vector<int32_t>& sl,
-                                  std::vector<int64_t>& item_ptr) {
-    sb.clear(); su.clear(); sl.clear(); item_ptr.clear();
-    item_ptr.push_back(0);
+                                  std::vector<int64_t>& item_rng) {
+    sb.clear(); su.clear(); sl.clear(); item_rng.clear();
     for (size_t r = 0; r < run_begin.size(); ++r) {
         const int64_t first = (int64_t)sb.size();
-        for (int64_t b = run_begin[r], e = run_end[r]; b < e; b += 32) {
-            sb.push_back(b); su.push_back(run_user[r]); sl.push_back((int32_t)std::min<int64_t>(32, e - b));
+        for (int64_t b = run_begin[r], e = run_end[r]; b < e; b += seg_events) {
+            sb.push_back(b); su.push_back(run_user[r]); sl.push_back((int32_t)std::min<int64_t>(seg_events, e - b));
         }
         const int64_t nsegs = (int64_t)sb.size() - first;
         if (nsegs == 0) continue;
-        if (nsegs > kItemSegs && allow_shared)
+        if (nsegs > item_segs && allow_shared) {
+            const int64_t per = std::max(item_segs, (nsegs + max_items - 1) / max_items);
             for (int64_t s = first; s < first + nsegs; ++s) sl[s] |= kSegShared;
-        if (allow_shared)
-            for (int64_t s = first; s < first + nsegs; s += kItemSegs) item_ptr.push_back(std::min(first + nsegs, s + kItemSegs));
-        else
-            item_ptr.push_back(first + nsegs);
+            for (int64_t s = first; s < first + nsegs; s += per) {
+                item_rng.push_back(s); item_rng.push_back(std::min(first + nsegs, s + per));
+            }
+        } else {
+            item_rng.push_back(first); item_rng.push_back(first + nsegs);
+        }
     }
 }
 
@@ -201,6 +221,11 @@ int yue_create(int device, yue_t** out) {
     if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(96, atoi(s)));   // 96 slots x 256 floats x 8 B fits one CTA
     if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_HOT_FLUSH")) h->hot_flush = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
+    if (const char* s = getenv("YUE_SGD_MAX_ITEMS")) h->max_items_per_user = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_RESYNC_EVENTS")) h->resync_events = std::max(1, std::min(32, atoi(s)));
+    if (const char* s = getenv("YUE_SGD_SEG_EVENTS")) h->seg_events = std::max(1, std::min(32, atoi(s)));
+    if (const char* s = getenv("YUE_SGD_WARPS_PER_SM")) h->warps_per_sm = std::max(1, std::min(kSgdThreads / 32, atoi(s)));
     if (const char* s = getenv("YUE_SGD_MIN_EVENTS_PER_WARP")) h->min_events_per_warp = std::max(32, atoi(s));
     *out = h;
     return YUE_OK;
@@ -270,10 +295,11 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     // and keeps the in-flight window a small fraction of the users)
     h->n_warps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
     // a heavy user's item is at most a quarter of a warp's fair share, so no item is a straggler
-    const int64_t item_segs = std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)h->n_warps * 4 * 32)));
-    build_items_from_runs(rb, re, ru, true, item_segs, sb, su, sl, ip);
+    int64_t item_segs = std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)h->n_warps * 4 * 32)));
+    if (h->item_segs_env > 0) item_segs = h->item_segs_env;
+    build_items_from_runs(rb, re, ru, true, item_segs, h->max_items_per_user, h->seg_events, sb, su, sl, ip);
     h->nseg = (int64_t)sb.size();
-    h->n_items = (int64_t)ip.size() - 1;
+    h->n_items = (int64_t)ip.size() / 2;
     CK(h->seg_begin.resize(h->nseg)); CK(h->seg_user.resize(h->nseg)); CK(h->seg_len.resize(h->nseg));
     CK(h->item_ptr.resize(ip.size())); CK(h->cursor.resize(1));
     if (h->nseg) {
@@ -441,6 +467,7 @@ int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, 
     sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
     sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot; sp.hot_flush = h->hot_flush;
+    sp.resync_events = h->resync_events;
     sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base;
     return run_sgd(h, sp, mode, loss_out);
 }
@@ -466,7 +493,8 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
     const int n_warps = mode == YUE_MODE_SERIAL ? 1
         : (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
     build_items_from_runs(rb, re, ru, mode != YUE_MODE_SERIAL,
-                          std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)n_warps * 4 * 32))), sb, su, sl, ip);
+                          std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)n_warps * 4 * 32))),
+                          h->max_items_per_user, 32, sb, su, sl, ip);
     CK(h->tmp_i.resize(T)); CK(h->tmp_j.resize(T));
     CK(h->tmp_sb.resize(sb.size())); CK(h->tmp_su.resize(su.size())); CK(h->tmp_sl.resize(sl.size()));
     CK(h->tmp_ws.resize(ip.size())); CK(h->cursor.resize(1));
@@ -479,9 +507,10 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
     SgdParams sp{};
     fill_rates(sp, lr, regU, regI);
     sp.seg_begin = h->tmp_sb.p; sp.seg_user = h->tmp_su.p; sp.seg_len = h->tmp_sl.p;
-    sp.item_ptr = h->tmp_ws.p; sp.n_work = (int64_t)ip.size() - 1; sp.n_warps = n_warps;
+    sp.item_ptr = h->tmp_ws.p; sp.n_work = (int64_t)ip.size() / 2; sp.n_warps = n_warps;
     sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
     sp.n_hot = 0; sp.hot_flush = 1;              // explicit triplets take the direct path
+    sp.resync_events = h->resync_events;
     int rc = run_sgd(h, sp, mode, loss_out);
     cudaStreamSynchronize(h->stream);           // host staging vectors die here
     return rc;
