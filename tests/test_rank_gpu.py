@@ -96,3 +96,55 @@ def test_rank_block_sharding_concatenates(engine):
     parts = [engine.rank_topn(users[a:b], N, RANK_EXACT) for a, b in [(0, 130), (130, 131), (131, 500)]]
     assert np.array_equal(np.concatenate([p[0] for p in parts]), full)
     assert np.array_equal(np.concatenate([p[1] for p in parts]), fs)
+
+
+# ---- tcgen05 flavour: must return exactly what the exact kernel / the oracle return -----------
+from yue_b200.engine import RANK_TC  # noqa: E402
+
+
+@pytest.mark.parametrize("d,N,n,B", [(64, 10, 5000, 300), (64, 20, 20011, 257), (32, 5, 3000, 128),
+                                     (10, 10, 777, 50), (48, 32, 9000, 130)])
+def test_tc_topn_matches_oracle(engine, d, N, n, B):
+    m = max(B, 300)
+    log = synth.power_law_log(m, n, 15000, seed=d + N)
+    P, Q = synth.init_factors(m, n, d, seed=N)
+    rng = np.random.default_rng(2)
+    P = ((P - 0.03) * rng.uniform(0.5, 4.0, (m, 1))).astype(np.float32)       # mixed signs and scales
+    Q = ((Q - 0.04) * rng.uniform(0.2, 3.0, (n, 1))).astype(np.float32)
+    engine.set_interactions(m, n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    engine.set_factors(P, Q)
+    users = rng.permutation(m)[:B].astype(np.int32)
+    check(engine, P, Q, users, N, log.uq_indptr, log.uq_items, RANK_TC)
+
+
+def test_tc_equals_exact_kernel_at_scale(engine):
+    """Bigger than the oracle likes: the tensor-core flavour against the exact kernel, trained-like
+    factors (heavy-tailed norms), 100 K tracks."""
+    m, n, d, N = 3000, 100_000, 64, 10
+    rng = np.random.default_rng(5)
+    P = (rng.normal(size=(m, d)) * rng.lognormal(0, 0.5, (m, 1))).astype(np.float32)
+    Q = (rng.normal(size=(n, d)) * rng.lognormal(0, 0.7, (n, 1)) * 0.3).astype(np.float32)
+    indptr, uq = synth.mask_csr(m, n, 50, seed=3)
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), indptr, uq)
+    engine.set_factors(P, Q)
+    users = np.arange(m, dtype=np.int32)
+    ie, se = engine.rank_topn(users, N, RANK_EXACT)
+    it, st = engine.rank_topn(users, N, RANK_TC)
+    assert np.array_equal(ie, it) and np.array_equal(se, st)
+    for b in (0, 1, m - 1):                     # and never a masked track
+        assert not np.isin(it[b], uq[indptr[b]:indptr[b + 1]]).any()
+
+
+def test_tc_tie_flood_falls_back_exactly(engine):
+    """Thousands of identical rows: more near-ties than a candidate buffer holds -> those users are
+    re-run through the exact kernel and the answer is still (score desc, id asc)."""
+    m, n, d, N = 140, 6000, 64, 10
+    rng = np.random.default_rng(9)
+    P = np.abs(rng.normal(size=(m, d))).astype(np.float32)
+    Q = np.tile(np.abs(rng.normal(size=(1, d))).astype(np.float32), (n, 1))    # every track identical
+    Q[::7] *= 0.5
+    uq_indptr = np.zeros(m + 1, np.int64)
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), uq_indptr, np.zeros(0, np.int32))
+    engine.set_factors(P, Q)
+    ids, sc = check(engine, P, Q, np.arange(m, dtype=np.int32), N, uq_indptr, np.zeros(0, np.int32), RANK_TC)
+    assert ids[0].tolist() == [1, 2, 3, 4, 5, 6, 8, 9, 10, 11]

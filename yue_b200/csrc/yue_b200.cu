@@ -86,7 +86,9 @@ struct yue_handle {
     // stale deltas inflate the epoch loss 1.7-2.5x; with <= 16 the loss is within 0.3 % of the serial
     // order and 8 reproduces its Recall@10 / NDCG@10 (profiles/quality_study_r1.md).
     int resync_events = 8;
-    int hot_max = 64;                 // shared-memory hot-row slots per CTA
+    // Off by default: per-CTA copies of the hot rows cost 1.5-2.4 points of Recall@10 at config C2
+    // (profiles/quality_study_r1.md); YUE_SGD_HOT_MAX=64 turns the path on.
+    int hot_max = 0;                  // shared-memory hot-row slots per CTA
     int hot_min_count = 16384;        // a track is hot when it is the positive of at least this many events
     int hot_flush = 4;                // updates of a slot (per CTA) between publishes; 64 diverges, 4 and 16 run equally fast
     int n_hot = 0;
@@ -116,6 +118,9 @@ struct yue_handle {
     int k = 0, ld = 0;
     bool have_factors = false;
     DevBuf<float> P, Q, Qsnap, Qdelta;
+    // interleaved working copy of Q for the SGD kernels (d = 64); exactly one of the two is current
+    DevBuf<float> Qilv;
+    bool use_ilv = true, ilv_current = false, rowmajor_current = true;
     bool have_snap = false;
     DevBuf<double> scal;          // [0] loss, [1] |P|^2, [2] |Q|^2
 
@@ -145,6 +150,8 @@ struct yue_handle {
     } while (0)
 
 static int fail(yue_t* h, int code, const std::string& msg) { h->err = msg; return code; }
+static int q_rowmajor(yue_t* h);
+static int q_interleaved(yue_t* h);
 
 // Cut every user's event range into <=32-event segments and group them into work items, returned
 // as [begin, end) segment ranges in STREAM ORDER (the order the kernel's cursor hands them out and
@@ -223,6 +230,7 @@ int yue_create(int device, yue_t** out) {
     if (const char* s = getenv("YUE_SGD_HOT_FLUSH")) h->hot_flush = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
     if (const char* s = getenv("YUE_SGD_MAX_ITEMS")) h->max_items_per_user = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_Q_INTERLEAVE")) h->use_ilv = atoi(s) != 0;
     if (const char* s = getenv("YUE_SGD_RESYNC_EVENTS")) h->resync_events = std::max(1, std::min(32, atoi(s)));
     if (const char* s = getenv("YUE_SGD_SEG_EVENTS")) h->seg_events = std::max(1, std::min(32, atoi(s)));
     if (const char* s = getenv("YUE_SGD_WARPS_PER_SM")) h->warps_per_sm = std::max(1, std::min(kSgdThreads / 32, atoi(s)));
@@ -241,7 +249,7 @@ int yue_destroy(yue_t* h) {
     h->cursor.release();
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->seg_user, &h->seg_len, &h->tmp_i, &h->tmp_j,
                     &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts}) b->release();
-    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->rk_scores, &h->pred}) b->release();
+    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred}) b->release();
     h->scal.release();
     h->l2buf.release();
     cudaEventDestroy(h->ev0);
@@ -367,16 +375,39 @@ int yue_set_factors(yue_t* h, int k, const float* P, const float* Q) {
     h->have_factors = true;
     h->have_snap = false;
     h->tc.q_dirty = true;
+    h->rowmajor_current = true;
+    h->ilv_current = false;
     return YUE_OK;
 }
 
 int yue_get_factors(yue_t* h, float* P, float* Q) {
     REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
     CK(cudaSetDevice(h->device));
+    if (Q) { if (int rc = q_rowmajor(h)) return rc; }
     const int k = h->k, ld = h->ld;
     if (P && h->m) CK(cudaMemcpy2DAsync(P, k * sizeof(float), h->P.p, ld * sizeof(float), k * sizeof(float), h->m, cudaMemcpyDeviceToHost, h->stream));
     if (Q) CK(cudaMemcpy2DAsync(Q, k * sizeof(float), h->Q.p, ld * sizeof(float), k * sizeof(float), h->n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+// Q lives in two layouts (see q_ilv_float_offset); these make one of them current.
+static int q_rowmajor(yue_t* h) {
+    if (h->rowmajor_current) return YUE_OK;
+    q_from_ilv_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((float4*)h->Q.p, h->Qilv.p, h->n);
+    ++h->launches;
+    CK(cudaGetLastError());
+    h->rowmajor_current = true;
+    return YUE_OK;
+}
+static int q_interleaved(yue_t* h) {
+    if (h->ilv_current) return YUE_OK;
+    const size_t floats = (size_t)((h->n + 15) / 16) * 1024;
+    CK(h->Qilv.resize(floats));
+    q_to_ilv_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((const float4*)h->Q.p, h->Qilv.p, h->n);
+    ++h->launches;
+    CK(cudaGetLastError());
+    h->ilv_current = true;
     return YUE_OK;
 }
 
@@ -409,16 +440,16 @@ int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot,
     return YUE_OK;
 }
 
-template <int NCH>
+template <int NCH, bool ILV>
 static cudaError_t launch_sgd(const SgdParams& sp, int mode, cudaStream_t st) {
     if (mode == YUE_MODE_SERIAL) {
-        bpr_sgd_kernel<NCH, kSerial, 1><<<1, 32, 0, st>>>(sp);
+        bpr_sgd_kernel<NCH, kSerial, 1, ILV><<<1, 32, 0, st>>>(sp);
         return cudaGetLastError();
     }
     constexpr int PF = NCH <= 2 ? 4 : 2;
     const int grid = (sp.n_warps * 32 + kSgdThreads - 1) / kSgdThreads;
     const size_t smem = (size_t)sp.n_hot * sp.ld * 8 + (size_t)sp.n_hot * 4;
-    auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF> : bpr_sgd_kernel<NCH, kStore, PF>;
+    auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF, ILV> : bpr_sgd_kernel<NCH, kStore, PF, ILV>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
     if (e != cudaSuccess) return e;
     kern<<<grid, kSgdThreads, smem, st>>>(sp);
@@ -430,17 +461,20 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
     CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
     sp.cursor = h->cursor.p;
-    sp.P = h->P.p; sp.Q = h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
+    const bool ilv = h->use_ilv && h->ld == 64 && mode != YUE_MODE_SERIAL;
+    if (ilv) { if (int rc = q_interleaved(h)) return rc; } else { if (int rc = q_rowmajor(h)) return rc; }
+    sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
     const int nch = (sp.nchunks + 15) / 16;
     switch (nch) {
-        case 1: CK(launch_sgd<1>(sp, mode, h->stream)); break;
-        case 2: CK(launch_sgd<2>(sp, mode, h->stream)); break;
-        case 3: CK(launch_sgd<3>(sp, mode, h->stream)); break;
-        case 4: CK(launch_sgd<4>(sp, mode, h->stream)); break;
+        case 1: if (ilv) CK(launch_sgd<1, true>(sp, mode, h->stream)); else CK(launch_sgd<1, false>(sp, mode, h->stream)); break;
+        case 2: CK(launch_sgd<2, false>(sp, mode, h->stream)); break;
+        case 3: CK(launch_sgd<3, false>(sp, mode, h->stream)); break;
+        case 4: CK(launch_sgd<4, false>(sp, mode, h->stream)); break;
         default: return fail(h, YUE_E_UNSUPPORTED, "num.factors > 256");
     }
     ++h->launches;
+    if (ilv) h->rowmajor_current = false; else h->ilv_current = false;   // the other copy is stale now
     h->tc.q_dirty = true;
     if (loss_out) {
         CK(cudaMemcpyAsync(loss_out, h->scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -519,6 +553,7 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
 int yue_frob2(yue_t* h, double* p2, double* q2) {
     REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
     CK(cudaSetDevice(h->device));
+    if (int rc = q_rowmajor(h)) return rc;
     CK(cudaMemsetAsync(h->scal.p + 1, 0, 2 * sizeof(double), h->stream));
     const int grid = h->sm_count * 8;
     if (h->m) { frob2_kernel<<<grid, 256, 0, h->stream>>>(h->P.p, (size_t)h->m * h->ld, h->scal.p + 1); ++h->launches; }
@@ -536,6 +571,7 @@ int yue_predict(yue_t* h, int64_t user, float* scores_out) {
     REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
     REQUIRE(user >= 0 && user < h->m && scores_out, YUE_E_ARG, "bad user or null output");
     CK(cudaSetDevice(h->device));
+    if (int rc = q_rowmajor(h)) return rc;
     CK(h->pred.resize(h->n));
     predict_kernel<<<(int)std::min<int64_t>((h->n + 255) / 256, 4096), 256, 0, h->stream>>>(h->P.p, h->Q.p, h->ld, h->k, user, (int)h->n, h->pred.p);
     ++h->launches;
@@ -573,6 +609,7 @@ int yue_rank_topn(yue_t* h, const int32_t* users, int64_t B, int N, int algo, in
     for (int64_t b = 0; b < B; ++b) REQUIRE(users[b] >= 0 && users[b] < h->m, YUE_E_ARG, "user index out of range");
     CK(cudaSetDevice(h->device));
     if (B == 0) return YUE_OK;
+    if (int rc = q_rowmajor(h)) return rc;
     CK(h->rk_users.resize(B)); CK(h->rk_ids.resize((size_t)B * N)); CK(h->rk_scores.resize((size_t)B * N));
     CK(cudaMemcpyAsync(h->rk_users.p, users, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     int rc;
@@ -605,6 +642,7 @@ int yue_q_snapshot(yue_t* h) {
     REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
     CK(cudaSetDevice(h->device));
     if (int rc = ensure_snap(h)) return rc;
+    if (int rc = q_rowmajor(h)) return rc;
     CK(cudaMemcpyAsync(h->Qsnap.p, h->Q.p, (size_t)h->n * h->ld * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     h->have_snap = true;
     return YUE_OK;
@@ -612,6 +650,7 @@ int yue_q_snapshot(yue_t* h) {
 int yue_q_delta_pack(yue_t* h) {
     REQUIRE(h && h->have_factors && h->have_snap, YUE_E_STATE, "call yue_q_snapshot first");
     CK(cudaSetDevice(h->device));
+    if (int rc = q_rowmajor(h)) return rc;
     const size_t n4 = (size_t)h->n * h->ld / 4;
     q_delta_pack_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((const float4*)h->Q.p, (const float4*)h->Qsnap.p, (float4*)h->Qdelta.p, n4);
     ++h->launches;
@@ -626,6 +665,8 @@ int yue_q_delta_apply(yue_t* h) {
     ++h->launches;
     CK(cudaGetLastError());
     h->tc.q_dirty = true;
+    h->rowmajor_current = true;
+    h->ilv_current = false;
     return YUE_OK;
 }
 int yue_device_buffer(yue_t* h, int which, void** dev_ptr, size_t* bytes) {
@@ -633,7 +674,7 @@ int yue_device_buffer(yue_t* h, int which, void** dev_ptr, size_t* bytes) {
     REQUIRE(h->have_factors, YUE_E_STATE, "factors not set");
     switch (which) {
         case YUE_BUF_P: *dev_ptr = h->P.p; *bytes = (size_t)h->m * h->ld * sizeof(float); break;
-        case YUE_BUF_Q: *dev_ptr = h->Q.p; *bytes = (size_t)h->n * h->ld * sizeof(float); break;
+        case YUE_BUF_Q: if (int rc = q_rowmajor(h)) return rc; *dev_ptr = h->Q.p; *bytes = (size_t)h->n * h->ld * sizeof(float); break;
         case YUE_BUF_Q_DELTA:
         case YUE_BUF_Q_SNAPSHOT:
             if (int rc = ensure_snap(h)) return rc;
