@@ -73,11 +73,16 @@ def main():
         if os.environ.get("STUDY_SERIAL", "1") == "1":
             configs.append(("serial seed 99", MODE_SERIAL, {}))
         base_env.pop("YUE_SGD_MAX_ITEMS")
-        hotenv = dict(YUE_SGD_HOT_MAX=64, YUE_SGD_HOT_MIN_COUNT=16384, YUE_SGD_HOT_FLUSH=4)
+        hotenv = dict(YUE_SGD_HOT_MAX=64, YUE_SGD_HOT_MIN_COUNT=16384)
         reps = int(os.environ.get("STUDY_REPS", "5"))
-        configs += [cfg("resync 8, no hot, run %d" % k) for k in range(reps)]
-        configs += [cfg("resync 8, hot flush 4, run %d" % k, **hotenv) for k in range(reps)]
-        configs += [cfg("resync 8, hot flush 2, run %d" % k, **dict(hotenv, YUE_SGD_HOT_FLUSH=2)) for k in range(reps)]
+        which = os.environ.get("STUDY_SET", "base")
+        if which == "base":
+            configs += [cfg("direct (no hot rows), run %d" % k) for k in range(reps)]
+            configs += [cfg("sharded hot rows (default), run %d" % k, **hotenv) for k in range(reps)]
+        else:
+            configs += [cfg("sharded, items 2.6K events, run %d" % k, YUE_SGD_ITEM_SEGS=82, **hotenv) for k in range(reps)]
+            configs += [cfg("sharded, items 1.3K events, run %d" % k, YUE_SGD_ITEM_SEGS=41, **hotenv) for k in range(reps)]
+            configs += [cfg("sharded, 8 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=8, **hotenv) for k in range(reps)]
     for lr, epochs in sweeps:
         base = None
         for name, mode, env in configs:

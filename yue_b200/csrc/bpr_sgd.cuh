@@ -76,16 +76,18 @@ struct SgdParams {
     double lr_d;
     double* loss;                  // device accumulator of sum -log(s)
     // Hot rows.  On a power-law log the most played track is the positive of several percent of
-    // ALL triplets; its row lives in one L2 slice and the vector atomics to it serialise there
-    // (ncu: lts__d_atomic_input_cycles_active 86% on one slice, 5% on average -- the whole epoch
-    // waited on that slice).  The n_hot most played tracks therefore get a per-CTA copy in shared
-    // memory: a triplet whose positive is hot reads base+delta from shared memory, adds its change
-    // to delta with shared-memory atomics, and every hot_flush-th update of a slot publishes the
-    // accumulated delta with ONE vector atomic and re-reads the row.
+    // ALL triplets.  Every update is a read-modify-write of the same sectors in L2, and dependent
+    // atomics on one address retire about one per 22 cycles: 3.9 M updates of track 0 at config C2
+    // are a 45 ms chain however many SMs feed it (ncu: one L2 slice's atomic unit 86 % busy, the rest
+    // 5 %).  Per-CTA copies of the hot rows in shared memory removed the chain but cost 1.5-2.4 points
+    // of Recall@10 (stale replicas; profiles/quality_study_r1.md), so the hot rows are instead kept
+    // as SHARDED ACCUMULATORS: the logical row is  Q[t] + sum_r shard[r][t];  a warp adds its change
+    // to shard (warp % R) and every reader sums all R rows.  One logical copy, nothing goes stale,
+    // the chain per address is R times shorter.  hot_fold_kernel folds the shards back into Q.
     int resync_events;             // a shared (multi-item) user publishes + re-reads P[u] every this many events
     const int32_t* hot_items;      // [n_hot] track id of each hot slot
     int n_hot;
-    int hot_flush;
+    float* hot_shards;             // [(kHotShards-1), n_hot, ld] extra accumulators (shard 0 is Q itself)
 };
 
 __device__ __forceinline__ float4 ld_row(const float* p) {
@@ -130,6 +132,7 @@ struct RowOps {
 };
 
 constexpr int kSgdThreads = 512;
+constexpr int kHotShards = 8;
 
 template <int NCH, int MODE, int PF, bool ILV>
 __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams p) {
@@ -138,17 +141,9 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
     auto q_lane_ptr = [&](int64_t r, int l16_) -> float* {
         return ILV ? p.Q + q_ilv_float_offset(r, l16_) : p.Q + (size_t)r * p.ld + 4 * l16_;
     };
-    extern __shared__ __align__(16) float hot_smem[];     // base[n_hot][ld] | delta[n_hot][ld] | cnt[n_hot]
-    float* hot_base = hot_smem;
-    float* hot_delta = hot_smem + (size_t)p.n_hot * p.ld;
-    int* hot_cnt = reinterpret_cast<int*>(hot_smem + 2 * (size_t)p.n_hot * p.ld);
+    extern __shared__ __align__(16) int hot_ids[];        // [n_hot] track id per hot slot
     if (MODE != kSerial && p.n_hot > 0) {
-        for (int x = threadIdx.x; x < p.n_hot * (p.ld / 4); x += blockDim.x) {
-            const int slot = x / (p.ld / 4), c4 = x % (p.ld / 4);
-            reinterpret_cast<float4*>(hot_base)[x] = ld_row(ILV ? q_lane_ptr(p.hot_items[slot], c4) : p.Q + (size_t)p.hot_items[slot] * p.ld + 4 * c4);
-            reinterpret_cast<float4*>(hot_delta)[x] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) hot_cnt[x] = 0;
+        for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) hot_ids[x] = p.hot_items[x];
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -241,13 +236,12 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
         __syncwarp();
 
         // ---- K2: the updates, one after the other, PF row pairs in flight -----------------
-        // lower half -> Q[i], upper half -> Q[j]; nullptr = hot positive (served from shared memory)
+        // lower half -> Q[i], upper half -> Q[j]; a hot positive (-slot-1) decodes to its main row
         auto row_ptr = [&](int t) -> float* {
             int32_t it = __shfl_sync(0xffffffffu, my_i, t);
             const int32_t jt = __shfl_sync(0xffffffffu, my_j, t);
-            if (MODE == kSerial && it < 0) it = p.hot_items[-it - 1];
-            const int32_t r = half ? jt : it;
-            return r >= 0 ? q_lane_ptr(r, l16) : nullptr;
+            if (it < 0) it = MODE == kSerial ? p.hot_items[-it - 1] : hot_ids[-it - 1];
+            return q_lane_ptr(half ? jt : it, l16);
         };
         auto load_rows = [&](float* ptr, float4* dstv) {
 #pragma unroll
@@ -281,20 +275,32 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
                     qp[k] = row_ptr(t + PF);
                     load_rows(qp[k], qb[k]);
                 }
-                // hot positive: the lower half takes base+delta of its slot from shared memory
+                // hot positive: the logical row is the main row plus the extra shards; this warp's
+                // change goes to shard (warp % kHotShards) (shard 0 = the main row)
                 const int32_t it_raw = __shfl_sync(0xffffffffu, my_i, t);
                 const bool hot = MODE != kSerial && it_raw < 0;
-                const int slot = hot ? -it_raw - 1 : 0;
-                float* sbase = hot_base + (size_t)slot * p.ld + lane_off;
-                float* sdelta = hot_delta + (size_t)slot * p.ld + lane_off;
                 if (hot && half == 0) {
+                    const int slot = -it_raw - 1;
+                    const float* sh = p.hot_shards + (size_t)slot * p.ld + lane_off;
+                    const size_t stride = (size_t)p.n_hot * p.ld;
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        if (!act[c]) continue;
-                        const float4 b = lds_row(sbase + 64 * c);
-                        const float4 dl = lds_row(sdelta + 64 * c);
-                        q[c] = make_float4(b.x + dl.x, b.y + dl.y, b.z + dl.z, b.w + dl.w);
+                    for (int r0 = 0; r0 < kHotShards - 1; r0 += 4) {      // 4 independent loads in flight
+                        float4 ex[4][NCH];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c)
+                                ex[r][c] = (act[c] && r0 + r < kHotShards - 1) ? ld_row(sh + (r0 + r) * stride + 64 * c)
+                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) {
+                                q[c].x += ex[r][c].x; q[c].y += ex[r][c].y; q[c].z += ex[r][c].z; q[c].w += ex[r][c].w;
+                            }
                     }
+                    const int myshard = warp % kHotShards;
+                    if (myshard > 0) dst = const_cast<float*>(sh) + (size_t)(myshard - 1) * stride;
                 }
                 // dots: each half reduces its own row, then x = P.Qi - P.Qj (BPR.py:50)
                 float part = 0.f;
@@ -335,36 +341,11 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
                     pu[c] = R::axpy4(-p.c_u, pu[c], pu[c]);         // shrinks (55-57)
                     qn = R::axpy4(-p.c_i, qn, qn);
                     if (act[c]) {
-                        if (hot && half == 0) {
-                            atomicAdd(sdelta + 64 * c + 0, qn.x - q[c].x);
-                            atomicAdd(sdelta + 64 * c + 1, qn.y - q[c].y);
-                            atomicAdd(sdelta + 64 * c + 2, qn.z - q[c].z);
-                            atomicAdd(sdelta + 64 * c + 3, qn.w - q[c].w);
-                        } else if (MODE == kAtomic) {
+                        if (MODE == kAtomic || (hot && half == 0)) {   // hot rows are always additive
                             red_row(dst + 64 * c, make_float4(qn.x - q[c].x, qn.y - q[c].y,
                                                               qn.z - q[c].z, qn.w - q[c].w));
                         } else {
                             st_row(dst + 64 * c, qn);
-                        }
-                    }
-                }
-                if (hot) {      // every hot_flush-th update of the slot publishes the CTA's delta
-                    int n_upd = 0;
-                    if (lane == 0) n_upd = atomicAdd(hot_cnt + slot, 1) + 1;
-                    n_upd = __shfl_sync(0xffffffffu, n_upd, 0);
-                    if (n_upd % p.hot_flush == 0 && half == 0) {
-                        float* grow = q_lane_ptr(p.hot_items[slot], l16);
-#pragma unroll
-                        for (int c = 0; c < NCH; ++c) {
-                            if (!act[c]) continue;
-                            float4 dl;
-                            dl.x = atomicExch(sdelta + 64 * c + 0, 0.f);
-                            dl.y = atomicExch(sdelta + 64 * c + 1, 0.f);
-                            dl.z = atomicExch(sdelta + 64 * c + 2, 0.f);
-                            dl.w = atomicExch(sdelta + 64 * c + 3, 0.f);
-                            red_row(grow + 64 * c, dl);
-                            const float4 nb = ld_row(grow + 64 * c);     // after own red: ordered
-                            sts_row(sbase + 64 * c, nb);
                         }
                     }
                 }
@@ -376,15 +357,6 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
     }   // while items
     flush_user();
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss, loss);
-    if (MODE != kSerial && p.n_hot > 0) {            // publish what is left in the CTA's hot deltas
-        __syncthreads();
-        for (int x = threadIdx.x; x < p.n_hot * (p.ld / 4); x += blockDim.x) {
-            const int slot = x / (p.ld / 4), c4 = x % (p.ld / 4);
-            const float4 dl = reinterpret_cast<float4*>(hot_delta)[x];
-            if (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f)
-                red_row(ILV ? q_lane_ptr(p.hot_items[slot], c4) : p.Q + (size_t)p.hot_items[slot] * p.ld + 4 * c4, dl);
-        }
-    }
 }
 
 // ---- check hook: materialise the negatives (yue_sample_negatives) -------------------------
@@ -410,6 +382,25 @@ __global__ void q_to_ilv_kernel(const float4* __restrict__ q, float* __restrict_
 __global__ void q_from_ilv_kernel(float4* __restrict__ q, const float* __restrict__ qi, int64_t n) {
     for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n * 16; x += (int64_t)gridDim.x * blockDim.x)
         q[x] = *reinterpret_cast<const float4*>(qi + q_ilv_float_offset(x >> 4, (int)(x & 15)));
+}
+
+// ---- fold the hot-row shards back into Q (after every Hogwild launch) ----------------------------
+template <bool ILV>
+__global__ void hot_fold_kernel(float* __restrict__ Q, float* __restrict__ shards, const int32_t* __restrict__ hot_items,
+                                int n_hot, int ld) {
+    const int per = ld / 4;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n_hot * per; x += gridDim.x * blockDim.x) {
+        const int slot = x / per, c4 = x % per;
+        float* dst = ILV ? Q + q_ilv_float_offset(hot_items[slot], c4) : Q + (size_t)hot_items[slot] * ld + 4 * c4;
+        float4 acc = *reinterpret_cast<float4*>(dst);
+        for (int r = 0; r < kHotShards - 1; ++r) {
+            float4* sp = reinterpret_cast<float4*>(shards + ((size_t)r * n_hot + slot) * ld + 4 * c4);
+            const float4 v = *sp;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<float4*>(dst) = acc;
+    }
 }
 
 // ---- hot-track selection support: play counts, and re-labelling of hot positives ------------

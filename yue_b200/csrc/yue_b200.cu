@@ -86,13 +86,12 @@ struct yue_handle {
     // stale deltas inflate the epoch loss 1.7-2.5x; with <= 16 the loss is within 0.3 % of the serial
     // order and 8 reproduces its Recall@10 / NDCG@10 (profiles/quality_study_r1.md).
     int resync_events = 8;
-    // Off by default: per-CTA copies of the hot rows cost 1.5-2.4 points of Recall@10 at config C2
-    // (profiles/quality_study_r1.md); YUE_SGD_HOT_MAX=64 turns the path on.
-    int hot_max = 0;                  // shared-memory hot-row slots per CTA
+    int hot_max = 64;                 // tracks kept as sharded accumulators (see SgdParams)
     int hot_min_count = 16384;        // a track is hot when it is the positive of at least this many events
-    int hot_flush = 4;                // updates of a slot (per CTA) between publishes; 64 diverges, 4 and 16 run equally fast
     int n_hot = 0;
     DevBuf<int32_t> hot_items, hot_slot, item_counts;
+    DevBuf<float> hot_shards;
+    bool shards_clean = false;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -120,7 +119,7 @@ struct yue_handle {
     DevBuf<float> P, Q, Qsnap, Qdelta;
     // interleaved working copy of Q for the SGD kernels (d = 64); exactly one of the two is current
     DevBuf<float> Qilv;
-    bool use_ilv = true, ilv_current = false, rowmajor_current = true;
+    bool use_ilv = false, ilv_current = false, rowmajor_current = true;   // measured: no gain (the limit is per address, not per slice)
     bool have_snap = false;
     DevBuf<double> scal;          // [0] loss, [1] |P|^2, [2] |Q|^2
 
@@ -227,7 +226,6 @@ int yue_create(int device, yue_t** out) {
     h->l2_bytes = (size_t)prop.l2CacheSize;
     if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(96, atoi(s)));   // 96 slots x 256 floats x 8 B fits one CTA
     if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
-    if (const char* s = getenv("YUE_SGD_HOT_FLUSH")) h->hot_flush = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
     if (const char* s = getenv("YUE_SGD_MAX_ITEMS")) h->max_items_per_user = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_Q_INTERLEAVE")) h->use_ilv = atoi(s) != 0;
@@ -249,7 +247,7 @@ int yue_destroy(yue_t* h) {
     h->cursor.release();
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->seg_user, &h->seg_len, &h->tmp_i, &h->tmp_j,
                     &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts}) b->release();
-    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred}) b->release();
+    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->hot_shards}) b->release();
     h->scal.release();
     h->l2buf.release();
     cudaEventDestroy(h->ev0);
@@ -448,7 +446,7 @@ static cudaError_t launch_sgd(const SgdParams& sp, int mode, cudaStream_t st) {
     }
     constexpr int PF = NCH <= 2 ? 4 : 2;
     const int grid = (sp.n_warps * 32 + kSgdThreads - 1) / kSgdThreads;
-    const size_t smem = (size_t)sp.n_hot * sp.ld * 8 + (size_t)sp.n_hot * 4;
+    const size_t smem = (size_t)sp.n_hot * 4;
     auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF, ILV> : bpr_sgd_kernel<NCH, kStore, PF, ILV>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
     if (e != cudaSuccess) return e;
@@ -474,6 +472,13 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
         default: return fail(h, YUE_E_UNSUPPORTED, "num.factors > 256");
     }
     ++h->launches;
+    if (mode != YUE_MODE_SERIAL && sp.n_hot > 0) {     // fold the hot-row shards back into Q
+        const int fgrid = (sp.n_hot * (h->ld / 4) + 255) / 256;
+        if (ilv) hot_fold_kernel<true><<<fgrid, 256, 0, h->stream>>>(sp.Q, sp.hot_shards, sp.hot_items, sp.n_hot, h->ld);
+        else hot_fold_kernel<false><<<fgrid, 256, 0, h->stream>>>(sp.Q, sp.hot_shards, sp.hot_items, sp.n_hot, h->ld);
+        ++h->launches;
+        CK(cudaGetLastError());
+    }
     if (ilv) h->rowmajor_current = false; else h->ilv_current = false;   // the other copy is stale now
     h->tc.q_dirty = true;
     if (loss_out) {
@@ -500,7 +505,16 @@ int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, 
     sp.item_ptr = h->item_ptr.p; sp.n_work = h->n_items;
     sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
-    sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot; sp.hot_flush = h->hot_flush;
+    sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot;
+    if (h->n_hot > 0) {
+        const size_t need = (size_t)(kHotShards - 1) * h->n_hot * h->ld;
+        if (h->hot_shards.n < need || !h->shards_clean) {
+            CK(h->hot_shards.resize(need));
+            CK(cudaMemsetAsync(h->hot_shards.p, 0, need * sizeof(float), h->stream));
+            h->shards_clean = true;
+        }
+        sp.hot_shards = h->hot_shards.p;
+    }
     sp.resync_events = h->resync_events;
     sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base;
     return run_sgd(h, sp, mode, loss_out);
@@ -543,7 +557,7 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
     sp.seg_begin = h->tmp_sb.p; sp.seg_user = h->tmp_su.p; sp.seg_len = h->tmp_sl.p;
     sp.item_ptr = h->tmp_ws.p; sp.n_work = (int64_t)ip.size() / 2; sp.n_warps = n_warps;
     sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
-    sp.n_hot = 0; sp.hot_flush = 1;              // explicit triplets take the direct path
+    sp.n_hot = 0;                                // explicit triplets take the direct path
     sp.resync_events = h->resync_events;
     int rc = run_sgd(h, sp, mode, loss_out);
     cudaStreamSynchronize(h->stream);           // host staging vectors die here
