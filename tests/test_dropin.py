@@ -1,0 +1,148 @@
+"""The recommender class layer (yue_b200/bpr.py): CPU checks of the host logic with the engine
+replaced by the oracle, and a GPU end-to-end run of config C1 through the reference-shaped API."""
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from oracle import bpr_ref, philox, record_ref, topn
+from yue_b200.host.config import Config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def conf_values(out_dir, eval_setup="-target track -ap 0.2", extra=None):
+    v = {"record": "./dataset/log.txt", "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,",
+         "recommender": "BPR", "evaluation.setup": eval_setup, "item.ranking": "-topN 5,10",
+         "num.factors": "10", "num.max.iter": "3", "learnRate": "-init 0.02 -max 1",
+         "reg.lambda": "-u 0.01 -i 0.01 -b 0.2 -s 0.2", "output.setup": "on -dir %s/" % out_dir}
+    v.update(extra or {})
+    return v
+
+
+class OracleEngine:
+    """Stands in for yue_b200.engine.Engine on a CPU-only box (tests only)."""
+
+    def __init__(self, model):
+        self.m = model
+        self.arr = model.data.interaction_arrays(model.recType) if hasattr(model.data, "interaction_arrays") else None
+
+    def rank_topn(self, users, N, algo):
+        ev_indptr, ev_items, uq_indptr, uq_items = self.arr
+        return topn.topn_exact(self.m.P, self.m.Q, users, N, uq_indptr, uq_items)
+
+
+def golden_split(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    train = [e for e, h in zip(g["events"], g["held"]) if not h]
+    test = [e for e, h in zip(g["events"], g["held"]) if h]
+    return g, train, test
+
+
+def test_evalranking_host_logic_matches_reference_measure(golden_dir, tmp_path):
+    """Same P, Q as the golden run -> the class's evalRanking (ids -> names -> result lines ->
+    Measure) reproduces the reference's Measure output on exact top-N lists, and writes the two
+    result files the reference writes (IterativeRecommender.py:156-173)."""
+    from yue_b200.bpr import BPR
+    g, train, test = golden_split(golden_dir)
+    e = np.load(os.path.join(golden_dir, "eval_small.npz"))
+    mj = json.load(open(os.path.join(golden_dir, "measure_small.json")))
+    with redirect_stdout(io.StringIO()):
+        model = BPR(Config(values=conf_values(tmp_path)), train, test)
+        model.readConfiguration()
+        model.initModel()
+        assert model.P.dtype == np.float32 and model.P.shape == (model.m, 10) and model.Q.shape == (model.n, 10)
+        assert model.P.min() >= 0 and model.P.max() < 0.1
+        model.P, model.Q = e["P"], e["Q"]
+        oe = OracleEngine(model)
+        model._push_factors = lambda: oe
+        model.evalRanking()
+    assert model.measure == mj["measure_exact"]
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and "-measure[1].txt" in files[0] and "-top-5,10items[1].txt" in files[1]
+    lines = open(os.path.join(tmp_path, files[1])).read().splitlines()
+    assert lines[0].startswith("userId: recommendations in (itemId, ranking score) pairs")
+    assert len(lines) == 1 + len(model.data.testSet) and "*" in "".join(lines)
+    assert set(model.ndcg) == {5, 10} and 0 < model.ndcg[10] < 1
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_dropin_shim_on_top_of_the_reference_tree(golden_dir, tmp_path):
+    """dropin/recommender/cf/BPR.py imports against the REFERENCE's own base classes, Record and
+    Measure, and produces the reference's measure strings."""
+    import subprocess
+    code = r'''
+import io, json, os, sys
+import numpy as np
+from contextlib import redirect_stdout
+sys.path[:0] = [%(dropin)r, %(ref)r, %(root)r]
+from tool.config import Config
+from recommender.cf.BPR import BPR
+import base.IterativeRecommender as ref_base
+assert BPR.__mro__[2] is ref_base.IterativeRecommender
+from oracle import topn
+g = json.load(open(%(gold)r + "/record_small.json"))
+train = [e for e, h in zip(g["events"], g["held"]) if not h]
+test = [e for e, h in zip(g["events"], g["held"]) if h]
+open(%(tmp)r + "/c.conf", "w").write("\n".join(k + "=" + v for k, v in %(conf)r.items()))
+e = np.load(%(gold)r + "/eval_small.npz")
+mj = json.load(open(%(gold)r + "/measure_small.json"))
+with redirect_stdout(io.StringIO()):
+    m = BPR(Config(%(tmp)r + "/c.conf"), train, test)
+    m.readConfiguration(); m.initModel()
+    m.P, m.Q = e["P"], e["Q"]
+    from yue_b200.host.record import interaction_arrays
+    arr = interaction_arrays(m.data.name2id, m.data.userRecord, m.recType)
+    class E:
+        def rank_topn(self, users, N, algo): return topn.topn_exact(m.P, m.Q, users, N, arr[2], arr[3])
+    m._push_factors = lambda: E()
+    m.evalRanking()
+assert m.measure == mj["measure_exact"], m.measure[:3]
+print("OK")
+''' % dict(dropin=os.path.join(ROOT, "dropin"), ref=REF, root=ROOT, gold=golden_dir, tmp=str(tmp_path),
+           conf=conf_values(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_c1_end_to_end_through_the_class_api(tmp_path):
+    """Config C1 (Xiami-100K-shaped log, d = 10, config/BPR.conf hyper-parameters, -ap 0.2) from a
+    CSV file through Yue -> BPR.execute() on the GPU; the serial-order run is compared with the
+    oracle trained from the same initial factors, the default (Hogwild) run with the serial one."""
+    from yue_b200 import synth
+    from yue_b200.host.driver import Yue
+    import random
+    log_path = tmp_path / "log.txt"
+    synth.write_csv_log(str(log_path), 4000, 50000, 100000, seed=20260101)
+    results = {}
+    for mode in ("serial", "hogwild"):
+        vals = conf_values(tmp_path / mode, extra={"record": str(log_path), "yue.sgd": mode, "yue.seed": "77",
+                                                   "num.max.iter": "2"})
+        random.seed(5)                       # DataSplit uses the global stream (tool/dataSplit.py:15)
+        np.random.seed(11)                   # initModel uses the global numpy stream
+        with redirect_stdout(io.StringIO()):
+            y = Yue(Config(values=vals))
+            from yue_b200.bpr import BPR
+            model = BPR(y.config, y.trainingData, y.testData)
+            measure = model.execute()
+        results[mode] = (model, measure)
+    ms, meas = results["serial"]
+    # oracle: same split (same seed), same init stream, same sampler seed
+    ev_indptr, ev_items, uq_indptr, uq_items = ms.data.interaction_arrays()
+    np.random.seed(11)
+    P = np.random.rand(ms.m, 10).astype(np.float32) / 10
+    Q = np.random.rand(ms.n, 10).astype(np.float32) / 10
+    hist = bpr_ref.train(P, Q, record_ref.ev_users(ev_indptr), ev_items, ms.n, uq_indptr, uq_items, 2, 0.02, 1.0,
+                         0.01, 0.01, 77)
+    assert np.allclose(ms.P, P, rtol=1e-5, atol=1e-7) and np.allclose(ms.Q, Q, rtol=1e-5, atol=1e-7)
+    assert ms.loss == pytest.approx(hist[-1][0], rel=1e-5)
+    assert meas[0] == "Top 5\n" and meas[6] == "Top 10\n" and meas[1].startswith("Precision:")
+    mh, _ = results["hogwild"]
+    rec = lambda m: float(m.measure[8].split(":")[1])       # Recall@10
+    assert abs(rec(mh) - rec(ms)) < 0.005

@@ -1,0 +1,90 @@
+"""Host-side logic of the user-sharded multi-GPU path on CPU: the event-balanced user split, the
+shard-independent sampler, and the Q reconciliation over a real 2-process gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import bpr_ref, philox, record_ref
+from yue_b200 import sharding, synth
+
+
+def test_shard_users_by_events_balances_power_law():
+    log = synth.power_law_log(5000, 800, 200000, seed=2)
+    for world in (2, 4, 8):
+        b = sharding.shard_users_by_events(log.ev_indptr, world)
+        assert b[0] == 0 and b[-1] == log.m and (np.diff(b) >= 0).all()
+        ev = np.diff(log.ev_indptr[b])
+        assert ev.sum() == log.train_size
+        assert ev.max() <= log.train_size / world + np.diff(log.ev_indptr).max()
+    # degenerate: more ranks than users with events
+    b = sharding.shard_users_by_events(np.array([0, 5, 5, 5]), 4)
+    assert b[0] == 0 and b[-1] == 3 and (np.diff(b) >= 0).all()
+
+
+def test_local_shard_is_consistent_and_sampler_is_shard_independent():
+    log = synth.power_law_log(600, 300, 30000, seed=3)
+    b = sharding.shard_users_by_events(log.ev_indptr, 3)
+    ev_user = record_ref.ev_users(log.ev_indptr)
+    full = philox.sample_negatives(9, 1, ev_user, log.n, log.uq_indptr, log.uq_items)
+    got = []
+    for r in range(3):
+        s = sharding.local_shard(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, b, r)
+        assert s["ev_indptr"][0] == 0 and s["uq_indptr"][0] == 0 and len(s["ev_items"]) == s["ev_indptr"][-1]
+        got.append(philox.sample_negatives(9, 1, record_ref.ev_users(s["ev_indptr"]), log.n, s["uq_indptr"],
+                                           s["uq_items"], event_base=s["event_base"]))
+    assert np.array_equal(np.concatenate(got), full)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    log = synth.power_law_log(400, 200, 20000, seed=5)
+    P, Q = synth.init_factors(log.m, log.n, 16, seed=6)
+    b = sharding.shard_users_by_events(log.ev_indptr, world)
+    s = sharding.local_shard(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, b, rank)
+    u0 = s["user_begin"]
+    Pl, Ql = P[u0:u0 + s["m_local"]].copy(), Q.copy()
+    ev_user = record_ref.ev_users(s["ev_indptr"])
+    for ep in range(2):                                   # local serial epoch (the oracle plays the kernel), then exchange
+        snap = torch.from_numpy(Ql.copy())
+        neg = philox.sample_negatives(7, ep, ev_user, log.n, s["uq_indptr"], s["uq_items"], event_base=s["event_base"])
+        bpr_ref.sgd_epoch(Pl, Ql, ev_user, s["ev_items"], neg, 0.02, 0.01, 0.01)
+        Ql = sharding.reconcile_q(torch.from_numpy(Ql), snap, lambda t: dist.all_reduce(t)).numpy().copy()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (u0, Pl, Ql))
+    if rank == 0:
+        ret["out"] = gathered
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_reconciliation_equals_sum_of_deltas():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    (u0a, Pa, Qa), (u0b, Pb, Qb) = ret["out"]
+    assert np.array_equal(Qa, Qb)                          # replicas agree bit for bit after the exchange
+    # single-process emulation of the same schedule: both shards from the same snapshot, deltas summed
+    log = synth.power_law_log(400, 200, 20000, seed=5)
+    P, Q = synth.init_factors(log.m, log.n, 16, seed=6)
+    b = sharding.shard_users_by_events(log.ev_indptr, 2)
+    shards = [sharding.local_shard(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, b, r) for r in range(2)]
+    Pl = [P[s["user_begin"]:s["user_begin"] + s["m_local"]].copy() for s in shards]
+    for ep in range(2):
+        qs = []
+        for r, s in enumerate(shards):
+            ql = Q.copy()
+            eu = record_ref.ev_users(s["ev_indptr"])
+            neg = philox.sample_negatives(7, ep, eu, log.n, s["uq_indptr"], s["uq_items"], event_base=s["event_base"])
+            bpr_ref.sgd_epoch(Pl[r], ql, eu, s["ev_items"], neg, 0.02, 0.01, 0.01)
+            qs.append(ql)
+        Q = Q + ((qs[0] - Q) + (qs[1] - Q))
+    assert np.array_equal(Qa, Q)
+    assert np.array_equal(Pa, Pl[0]) and np.array_equal(Pb, Pl[1])

@@ -80,9 +80,9 @@ def main():
             configs += [cfg("direct (no hot rows), run %d" % k) for k in range(reps)]
             configs += [cfg("sharded hot rows (default), run %d" % k, **hotenv) for k in range(reps)]
         else:
-            configs += [cfg("sharded, items 2.6K events, run %d" % k, YUE_SGD_ITEM_SEGS=82, **hotenv) for k in range(reps)]
-            configs += [cfg("sharded, items 1.3K events, run %d" % k, YUE_SGD_ITEM_SEGS=41, **hotenv) for k in range(reps)]
-            configs += [cfg("sharded, 8 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=8, **hotenv) for k in range(reps)]
+            configs += [cfg("sharded, 12 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=12, **hotenv) for k in range(reps)]
+            configs += [cfg("sharded, 10 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=10, **hotenv) for k in range(reps)]
+            configs += [cfg("direct, 12 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=12) for k in range(reps)]
     for lr, epochs in sweeps:
         base = None
         for name, mode, env in configs:

@@ -1,0 +1,73 @@
+"""User-sharded multi-GPU BPR: one process per GPU, each rank owns a
+contiguous range of users (its rows of P and all their events), Q is replicated, and once per
+sub-epoch the ranks reconcile it:  Q <- Q_snapshot + sum_ranks (Q_rank - Q_snapshot).
+
+The reference has no counterpart (no collective anywhere).  Plumbing is
+torch.distributed; the packing / applying of the deltas and the epoch are CUDA kernels of
+libyue_b200.so.  The arithmetic of the exchange is backend-agnostic and is what the CPU tests
+(gloo, world_size 2) cover with `reconcile_q`.
+"""
+import numpy as np
+
+
+def shard_users_by_events(ev_indptr, world):
+    """Contiguous user ranges with (nearly) equal event counts: returns world+1 user boundaries.
+    Power-law aware -- a prefix sum over events, not over users."""
+    ev_indptr = np.asarray(ev_indptr, dtype=np.int64)
+    m, T = len(ev_indptr) - 1, int(ev_indptr[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = T * r // world
+        u = int(np.searchsorted(ev_indptr, target, side="left"))
+        bounds.append(min(max(u, bounds[-1]), m))
+    bounds.append(m)
+    return np.asarray(bounds, dtype=np.int64)
+
+
+def local_shard(ev_indptr, ev_items, uq_indptr, uq_items, bounds, rank):
+    """Rebased CSR slices of rank's users + (user_begin, event_base) for yue_set_interactions_shard."""
+    u0, u1 = int(bounds[rank]), int(bounds[rank + 1])
+    e0, e1 = int(ev_indptr[u0]), int(ev_indptr[u1])
+    q0, q1 = int(uq_indptr[u0]), int(uq_indptr[u1])
+    return dict(m_local=u1 - u0, user_begin=u0, event_base=e0,
+                ev_indptr=np.ascontiguousarray(ev_indptr[u0:u1 + 1] - e0), ev_items=np.ascontiguousarray(ev_items[e0:e1]),
+                uq_indptr=np.ascontiguousarray(uq_indptr[u0:u1 + 1] - q0), uq_items=np.ascontiguousarray(uq_items[q0:q1]))
+
+
+def reconcile_q(q_local, q_snapshot, all_reduce_sum):
+    """Q <- snapshot + sum over ranks of (Q_rank - snapshot).  `all_reduce_sum(t)` sums a tensor over
+    the ranks in place.  Works on any torch tensors (CPU for the gloo tests, the library's device
+    buffers on the GPU path, where the two elementwise steps are the q_delta_* kernels instead)."""
+    delta = q_local - q_snapshot
+    all_reduce_sum(delta)
+    q_new = q_snapshot + delta
+    return q_new
+
+
+class _DevAlias:
+    """Expose a device buffer of the library as a torch tensor (no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class ShardedTrainer:
+    """One rank of the user-sharded trainer.  `engine` already holds this rank's shard
+    (Engine.set_interactions(..., user_begin, event_base)) and factors (local P rows, full Q)."""
+
+    def __init__(self, engine, dist, device):
+        import torch
+        from ._lib import BUF_Q_DELTA
+        self.eng, self.dist, self.torch = engine, dist, torch
+        engine.q_snapshot()
+        ptr, nbytes = engine.device_buffer(BUF_Q_DELTA)
+        self.delta = torch.as_tensor(_DevAlias(ptr, nbytes), device=device)
+        self.stream = torch.cuda.ExternalStream(engine.stream_ptr(), device=device)
+
+    def epoch(self, lr, regU, regI, seed, epoch, mode, want_loss=False):
+        loss = self.eng.bpr_epoch(lr, regU, regI, seed, epoch, mode, want_loss=want_loss)
+        self.eng.q_delta_pack()
+        with self.torch.cuda.stream(self.stream):        # NCCL ordered on the library's stream
+            self.dist.all_reduce(self.delta)
+        self.eng.q_delta_apply()
+        return loss
