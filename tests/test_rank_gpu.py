@@ -148,3 +148,21 @@ def test_tc_tie_flood_falls_back_exactly(engine):
     engine.set_factors(P, Q)
     ids, sc = check(engine, P, Q, np.arange(m, dtype=np.int32), N, uq_indptr, np.zeros(0, np.int32), RANK_TC)
     assert ids[0].tolist() == [1, 2, 3, 4, 5, 6, 8, 9, 10, 11]
+
+
+def test_tc_overflow_pool_keeps_exactness(engine):
+    """~150 tracks share the top score of every user: more near-ties than the 32 a shared-memory row
+    buffer keeps, few enough for the global overflow pool -- no exact-kernel fallback needed and the
+    ids are still (score desc, id asc)."""
+    m, n, d, N = 200, 20000, 64, 10
+    rng = np.random.default_rng(11)
+    P = np.abs(rng.normal(size=(m, d))).astype(np.float32)
+    Q = (np.abs(rng.normal(size=(n, d))) * 0.1).astype(np.float32)
+    top = np.abs(rng.normal(size=(1, d))).astype(np.float32) * 2.0
+    dup = rng.choice(n, 150, replace=False)
+    Q[dup] = top                                          # identical rows -> identical exact scores
+    uq_indptr = np.zeros(m + 1, np.int64)
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), uq_indptr, np.zeros(0, np.int32))
+    engine.set_factors(P, Q)
+    ids, sc = check(engine, P, Q, np.arange(m, dtype=np.int32), N, uq_indptr, np.zeros(0, np.int32), RANK_TC)
+    assert ids[0].tolist() == sorted(dup.tolist())[:10]

@@ -41,6 +41,9 @@ constexpr int kTcBM = 128;            // users per CTA (UMMA M)
 constexpr int kTcBN = 128;            // tracks per tile (UMMA N)
 constexpr int kTcStages = 3;          // TMA -> MMA shared-memory stages
 constexpr int kTcCap = 64;            // candidate slots per row
+constexpr int kTcAcc = 4;             // TMEM accumulator stages (4 x 128 columns = all of TMEM)
+constexpr int kTcOvfCap = 1024;       // candidate slots of a row that overflowed into the global pool
+constexpr int kTcOvfRows = 512;       // rows the pool can take per launch
 constexpr int kTcBoxBytes = 128 * 128;   // one TMA box: 128 rows x 128 B
 constexpr float kTf32ErrCoef = 2.1e-3f;  // 2^-9 (two operands truncated to 10 mantissa bits) + slack
 
@@ -62,6 +65,8 @@ struct RankTcParams {
     float* scores_out;
     int* fail_count;
     int32_t* fail_rows;
+    uint64_t* ovf_pool;         // [kTcOvfRows, kTcOvfCap] spill space for rows with too many near-ties
+    int* ovf_next;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -120,6 +125,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue only (no wait): 64 consecutive columns
+__device__ __forceinline__ void tc_ld64_issue(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major operand, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);      // start address, 16-byte units   [0,14)
@@ -143,26 +167,26 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     uint8_t* sB = sA + stage_bytes;
     uint64_t* keys = reinterpret_cast<uint64_t*>(sB + kTcStages * stage_bytes);        // [128][kTcCap]
     uint64_t* bars = keys + kTcBM * kTcCap;
-    // barriers: 0 = A landed, 1..S = B full, S+1..2S = B empty, then 2 TMEM full, 2 TMEM empty
+    // barriers: 0 = A landed, 1..S = B full, S+1..2S = B empty, then kTcAcc TMEM full, kTcAcc TMEM empty
     const uint32_t bar_a = smem_u32(bars);
     auto bar_full = [&](int s) { return smem_u32(bars + 1 + s); };
     auto bar_empty = [&](int s) { return smem_u32(bars + 1 + kTcStages + s); };
     auto bar_tfull = [&](int t) { return smem_u32(bars + 1 + 2 * kTcStages + t); };
-    auto bar_tempty = [&](int t) { return smem_u32(bars + 3 + 2 * kTcStages + t); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kTcStages);
+    auto bar_tempty = [&](int t) { return smem_u32(bars + 1 + 2 * kTcStages + kTcAcc + t); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kTcStages + 2 * kTcAcc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(bar_a, 1);
         for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_tempty(t), 128); }
+        for (int t = 0; t < kTcAcc; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_tempty(t), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmP) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmQ) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+                     :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -190,8 +214,8 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         if (lane == 0) {
             mbar_wait(bar_a, 0);
             for (int j = 0; j < p.ntiles; ++j) {
-                const int s = j % kTcStages, t = j & 1;
-                const uint32_t ph = (uint32_t)(j / kTcStages) & 1u, tph = (uint32_t)(j >> 1) & 1u;
+                const int s = j % kTcStages, t = j % kTcAcc;
+                const uint32_t ph = (uint32_t)(j / kTcStages) & 1u, tph = (uint32_t)(j / kTcAcc) & 1u;
                 mbar_wait(bar_tempty(t), tph ^ 1u);
                 mbar_wait(bar_full(s), ph);
                 tc_fence_after();
@@ -224,58 +248,84 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         int mval = mcur < mend ? p.uq_items[mcur] : INT32_MAX;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-        for (int j = 0; j < p.ntiles; ++j) {
-            const int t = j & 1;
-            const uint32_t tph = (uint32_t)(j >> 1) & 1u;
-            const int i0 = j * kTcBN;
-            mbar_wait(bar_tfull(t), tph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < kTcBN / 32; ++c) {
-                float v[32];
-                tc_ld32(trow + (uint32_t)(t * kTcBN + c * 32), v);
-                float m = v[0];
+        int ovf_slot = -1, ovf_cnt = 0;                 // >= 0: this row spills into the global pool
+        // examine 32 scores of columns [col0, col0+32): push survivors, then compact crowded rows
+        auto rare_path = [&](const uint32_t* v, int col0, float m) {
+            if (m >= thr) {
 #pragma unroll
-                for (int x = 1; x < 32; ++x) m = fmaxf(m, v[x]);
-                if (!__any_sync(0xffffffffu, m >= thr)) continue;
-                // ---- rare path ------------------------------------------------------------------
-                if (m >= thr) {
-#pragma unroll
-                    for (int x = 0; x < 32; ++x) {
-                        const int id = i0 + c * 32 + x;
-                        if (v[x] >= thr && id < p.n_items) {
-                            while (mval < id) { ++mcur; mval = mcur < mend ? p.uq_items[mcur] : INT32_MAX; }
-                            if (mval != id) K[cnt++] = make_key(v[x], id);      // cnt <= 32 before the chunk
+                for (int x = 0; x < 32; ++x) {
+                    const float sc = __uint_as_float(v[x]);
+                    const int id = col0 + x;
+                    if (sc >= thr && id < p.n_items) {
+                        while (mval < id) { ++mcur; mval = mcur < mend ? p.uq_items[mcur] : INT32_MAX; }
+                        if (mval != id) {
+                            if (ovf_slot < 0) K[cnt++] = make_key(sc, id);          // cnt <= 32 before the chunk
+                            else if (ovf_cnt < kTcOvfCap) p.ovf_pool[(size_t)ovf_slot * kTcOvfCap + ovf_cnt++] = make_key(sc, id);
+                            else { fail = true; thr = INFINITY; }
                         }
                     }
                 }
-                __syncwarp();
-                unsigned full;
-                while ((full = __ballot_sync(0xffffffffu, cnt > kTcCap - 32)) != 0u) {
-                    const int src = __ffs(full) - 1;
-                    const int cc = __shfl_sync(0xffffffffu, cnt, src);
-                    const float e2 = __shfl_sync(0xffffffffu, eps2, src);
-                    uint64_t* R = keys + (size_t)(quarter * 32 + src) * kTcCap;
-                    const uint64_t m0 = lane < cc ? R[lane] : ~0ull, m1 = lane + 32 < cc ? R[lane + 32] : ~0ull;
-                    int r0 = 0, r1 = 0;
-                    for (int e = 0; e < cc; ++e) { const uint64_t k = R[e]; r0 += k < m0; r1 += k < m1; }
-                    __syncwarp();
-                    if (lane < cc) R[r0] = m0;
-                    if (lane + 32 < cc) R[r1] = m1;
-                    __syncwarp();
-                    const float lim = key_score(R[p.N - 1]) - e2;             // cc > 32 >= N
-                    const bool k0 = lane < cc && key_score(R[lane]) >= lim;
-                    const bool k1 = lane + 32 < cc && key_score(R[lane + 32]) >= lim;
-                    const int kept = __popc(__ballot_sync(0xffffffffu, k0)) + __popc(__ballot_sync(0xffffffffu, k1));
-                    if (lane == src) {
-                        if (kept > kTcCap - 32) { fail = true; thr = INFINITY; cnt = 0; }   // too many near-ties
-                        else { cnt = kept; thr = lim; }
-                    }
-                    __syncwarp();
-                }
             }
+            __syncwarp();
+            unsigned full;
+            while ((full = __ballot_sync(0xffffffffu, cnt > kTcCap - 32)) != 0u) {
+                const int src = __ffs(full) - 1;
+                const int cc = __shfl_sync(0xffffffffu, cnt, src);
+                const float e2 = __shfl_sync(0xffffffffu, eps2, src);
+                uint64_t* R = keys + (size_t)(quarter * 32 + src) * kTcCap;
+                const uint64_t m0 = lane < cc ? R[lane] : ~0ull, m1 = lane + 32 < cc ? R[lane + 32] : ~0ull;
+                int r0 = 0, r1 = 0;
+                for (int e = 0; e < cc; ++e) { const uint64_t k = R[e]; r0 += k < m0; r1 += k < m1; }
+                __syncwarp();
+                if (lane < cc) R[r0] = m0;
+                if (lane + 32 < cc) R[r1] = m1;
+                __syncwarp();
+                const float lim = key_score(R[p.N - 1]) - e2;             // cc > 32 >= N
+                const bool k0 = lane < cc && key_score(R[lane]) >= lim;
+                const bool k1 = lane + 32 < cc && key_score(R[lane + 32]) >= lim;
+                const int kept = __popc(__ballot_sync(0xffffffffu, k0)) + __popc(__ballot_sync(0xffffffffu, k1));
+                int slot = -1;
+                if (kept > kTcCap - 32) {          // too many near-ties for shared memory: spill the row
+                    if (lane == 0) slot = atomicAdd(p.ovf_next, 1);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (slot < kTcOvfRows) {
+                        uint64_t* G = p.ovf_pool + (size_t)slot * kTcOvfCap;
+                        if (lane < kept) G[lane] = R[lane];
+                        if (lane + 32 < kept) G[lane + 32] = R[lane + 32];
+                    }
+                }
+                if (lane == src) {
+                    thr = lim;
+                    if (kept <= kTcCap - 32) cnt = kept;
+                    else if (slot < kTcOvfRows) { ovf_slot = slot; ovf_cnt = kept; cnt = 0; }   // threshold frozen from here on
+                    else { fail = true; thr = INFINITY; cnt = 0; }
+                }
+                __syncwarp();
+            }
+        };
+        for (int j = 0; j < p.ntiles; ++j) {
+            const int t = j % kTcAcc;
+            const uint32_t tph = (uint32_t)(j / kTcAcc) & 1u;
+            const int i0 = j * kTcBN;
+            mbar_wait(bar_tfull(t), tph);
+            tc_fence_after();
+            uint32_t va[64], vb[64];
+            tc_ld64_issue(trow + (uint32_t)(t * kTcBN), va);
+            tc_ld_wait();
+            tc_ld64_issue(trow + (uint32_t)(t * kTcBN + 64), vb);      // in flight while the first half is reduced
+            float m0 = __uint_as_float(va[0]), m1 = __uint_as_float(va[32]);
+#pragma unroll
+            for (int x = 1; x < 32; ++x) { m0 = fmaxf(m0, __uint_as_float(va[x])); m1 = fmaxf(m1, __uint_as_float(va[32 + x])); }
+            if (__any_sync(0xffffffffu, m0 >= thr)) rare_path(va, i0, m0);
+            if (__any_sync(0xffffffffu, m1 >= thr)) rare_path(va + 32, i0 + 32, m1);
+            tc_ld_wait();
             tc_fence_before();
-            mbar_arrive(bar_tempty(t));
+            mbar_arrive(bar_tempty(t));                                 // TMEM stage free: the rest works on registers
+            float m2 = __uint_as_float(vb[0]), m3 = __uint_as_float(vb[32]);
+#pragma unroll
+            for (int x = 1; x < 32; ++x) { m2 = fmaxf(m2, __uint_as_float(vb[x])); m3 = fmaxf(m3, __uint_as_float(vb[32 + x])); }
+            if (__any_sync(0xffffffffu, m2 >= thr)) rare_path(vb, i0 + 64, m2);
+            if (__any_sync(0xffffffffu, m3 >= thr)) rare_path(vb + 32, i0 + 96, m3);
         }
 
         // ---- exact pass: re-score the survivors with the fp32 FMA chain, sort, write -------------
@@ -283,14 +333,42 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         for (int rr = 0; rr < 32; ++rr) {
             const int64_t bb = (int64_t)blockIdx.x * kTcBM + quarter * 32 + rr;
             if (bb >= p.B) break;
-            const int cc = __shfl_sync(0xffffffffu, cnt, rr);
+            int cc = __shfl_sync(0xffffffffu, cnt, rr);
             const bool ff = __shfl_sync(0xffffffffu, (int)fail, rr) != 0;
+            const int oslot = __shfl_sync(0xffffffffu, ovf_slot, rr), ocnt = __shfl_sync(0xffffffffu, ovf_cnt, rr);
             if (ff) {
                 if (lane == 0) p.fail_rows[atomicAdd(p.fail_count, 1)] = (int32_t)bb;
                 continue;
             }
             uint64_t* R = keys + (size_t)(quarter * 32 + rr) * kTcCap;
             const float* pu = p.Psel + (size_t)bb * p.ld;
+            if (oslot >= 0) {
+                // spilled row: stream the pool entries through the 64-slot buffer, 32 at a time, keeping
+                // the N best EXACT scores in R[0..N)
+                const uint64_t* G = p.ovf_pool + (size_t)oslot * kTcOvfCap;
+                int have = 0;
+                for (int base = 0; base < ocnt; base += 32) {
+                    const int e = base + lane;
+                    uint64_t nk = ~0ull;
+                    if (e < ocnt) {
+                        const int id = key_id(G[e]);
+                        nk = make_key(score_fma32(pu, p.Q + (size_t)id * p.ld, p.d), id);
+                    }
+                    const int take = min(32, ocnt - base);
+                    __syncwarp();
+                    if (lane < take) R[have + lane] = nk;
+                    __syncwarp();
+                    have = compact_row<kTcCap>(R, have + take, p.N, lane);
+                    __syncwarp();
+                }
+                for (int x = lane; x < p.N; x += 32) {
+                    const bool ok = x < have;
+                    const uint64_t k = ok ? R[x] : 0ull;
+                    p.ids_out[bb * p.N + x] = ok ? key_id(k) : -1;
+                    p.scores_out[bb * p.N + x] = ok ? key_score(k) : -INFINITY;
+                }
+                continue;
+            }
             uint64_t nk[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -319,7 +397,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -378,6 +456,8 @@ struct RankTcState {
     int* fail_count = nullptr;
     int32_t* fail_rows = nullptr; size_t fail_cap = 0;
     int32_t* fb_users = nullptr; int32_t* fb_ids = nullptr; float* fb_scores = nullptr; size_t fb_cap = 0;
+    uint64_t* ovf_pool = nullptr;
+    int* ovf_next = nullptr;
     int64_t last_fail = 0;       // rows sent to the exact kernel by the last call (diagnostics)
 };
 
@@ -385,7 +465,7 @@ inline bool rank_tc_supported(int k, int N) { return k >= 1 && k <= 64 && N >= 1
 
 inline void rank_tc_release(RankTcState& st) {
     for (void* p : {(void*)st.qmax, (void*)st.psel, (void*)st.pnorm, (void*)st.fail_count, (void*)st.fail_rows,
-                    (void*)st.fb_users, (void*)st.fb_ids, (void*)st.fb_scores})
+                    (void*)st.fb_users, (void*)st.fb_ids, (void*)st.fb_scores, (void*)st.ovf_pool, (void*)st.ovf_next})
         if (p) cudaFree(p);
     st = RankTcState();
 }
@@ -430,6 +510,8 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
         st.encode = (PFN_tmapEncodeTiled)fn;
         TC_CK(cudaMalloc((void**)&st.qmax, sizeof(float)));
         TC_CK(cudaMalloc((void**)&st.fail_count, sizeof(int)));
+        TC_CK(cudaMalloc((void**)&st.ovf_next, sizeof(int)));
+        TC_CK(cudaMalloc((void**)&st.ovf_pool, (size_t)kTcOvfRows * kTcOvfCap * sizeof(uint64_t)));
     }
     const int64_t Bpad = (B + kTcBM - 1) / kTcBM * kTcBM;
     size_t cap_tmp = st.psel_cap;
@@ -444,6 +526,7 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
         st.q_dirty = false;
     }
     TC_CK(cudaMemsetAsync(st.fail_count, 0, sizeof(int), stream));
+    TC_CK(cudaMemsetAsync(st.ovf_next, 0, sizeof(int), stream));
     tc_gather_rows_kernel<<<(unsigned)((Bpad * 32 + 255) / 256), 256, 0, stream>>>(P, d_users, B, Bpad, ld, st.psel, st.pnorm);
     ++launches;
     TC_CK(cudaGetLastError());
@@ -460,6 +543,7 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
     p.Psel = st.psel; p.Q = Q; p.pnorm = st.pnorm; p.qmax = st.qmax; p.users = d_users;
     p.uq_indptr = uq_indptr; p.uq_items = uq_items; p.ids_out = d_ids; p.scores_out = d_scores;
     p.fail_count = st.fail_count; p.fail_rows = st.fail_rows;
+    p.ovf_pool = st.ovf_pool; p.ovf_next = st.ovf_next;
     const size_t smem = 1024 + (size_t)p.kblocks * kTcBoxBytes * (1 + kTcStages) + (size_t)kTcBM * kTcCap * 8 + 256;
     TC_CK(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rank_tc_kernel<<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);

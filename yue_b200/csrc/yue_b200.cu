@@ -442,18 +442,20 @@ int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot,
 }
 
 template <int NCH, bool ILV>
-static cudaError_t launch_sgd(const SgdParams& sp, int mode, cudaStream_t st) {
+static cudaError_t launch_sgd(const SgdParams& sp, int mode, int warps_per_cta, cudaStream_t st) {
     if (mode == YUE_MODE_SERIAL) {
         bpr_sgd_kernel<NCH, kSerial, 1, ILV><<<1, 32, 0, st>>>(sp);
         return cudaGetLastError();
     }
     constexpr int PF = NCH <= 2 ? 4 : 2;
-    const int grid = (sp.n_warps * 32 + kSgdThreads - 1) / kSgdThreads;
+    // one CTA per SM with warps_per_cta warps each (not n_warps packed into full CTAs: that would
+    // leave SMs idle when fewer than 16 warps per SM are wanted)
+    const int grid = (sp.n_warps + warps_per_cta - 1) / warps_per_cta;
     const size_t smem = (size_t)sp.n_hot * 4;
     auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF, ILV> : bpr_sgd_kernel<NCH, kStore, PF, ILV>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
     if (e != cudaSuccess) return e;
-    kern<<<grid, kSgdThreads, smem, st>>>(sp);
+    kern<<<grid, warps_per_cta * 32, smem, st>>>(sp);
     return cudaGetLastError();
 }
 
@@ -467,11 +469,12 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
     sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
     const int nch = (sp.nchunks + 15) / 16;
+    const int wpc = std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm));
     switch (nch) {
-        case 1: if (ilv) CK(launch_sgd<1, true>(sp, mode, h->stream)); else CK(launch_sgd<1, false>(sp, mode, h->stream)); break;
-        case 2: CK(launch_sgd<2, false>(sp, mode, h->stream)); break;
-        case 3: CK(launch_sgd<3, false>(sp, mode, h->stream)); break;
-        case 4: CK(launch_sgd<4, false>(sp, mode, h->stream)); break;
+        case 1: if (ilv) CK(launch_sgd<1, true>(sp, mode, wpc, h->stream)); else CK(launch_sgd<1, false>(sp, mode, wpc, h->stream)); break;
+        case 2: CK(launch_sgd<2, false>(sp, mode, wpc, h->stream)); break;
+        case 3: CK(launch_sgd<3, false>(sp, mode, wpc, h->stream)); break;
+        case 4: CK(launch_sgd<4, false>(sp, mode, wpc, h->stream)); break;
         default: return fail(h, YUE_E_UNSUPPORTED, "num.factors > 256");
     }
     ++h->launches;
