@@ -159,7 +159,6 @@ def run_native(args):
     from yue_b200 import synth
     from yue_b200.engine import (MODE_HOGWILD, MODE_HOGWILD_STORE, RANK_AUTO, RANK_EXACT, RANK_TC, Engine,
                                  PinnedArray)
-    from yue_b200._lib import BUF_Q_DELTA
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,24 +191,15 @@ def run_native(args):
         eng.set_factors(pP.array, pQ.array)
 
     upload()
-    delta_t = ext_stream = None
-    if world > 1:
-        eng.q_snapshot()
-        ptr, nbytes = eng.device_buffer(BUF_Q_DELTA)
-
-        class _Cai:                                 # alias the library's delta buffer as a tensor
-            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-        delta_t = torch.as_tensor(_Cai(), device=torch.device("cuda", local))
-        ext_stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=torch.device("cuda", local))
+    trainer = None
+    if world > 1:                                   # user-sharded: dQ all-reduced once per step (yue_b200/sharding.py)
+        from yue_b200.sharding import ShardedTrainer
+        trainer = ShardedTrainer(eng, dist, torch.device("cuda", local))
 
     def step(epoch, want_loss=False):
-        loss = eng.bpr_epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
-        if world > 1:                               # the real exchange step of the sharded path
-            eng.q_delta_pack()
-            with torch.cuda.stream(ext_stream):     # NCCL ordered on the library's stream
-                dist.all_reduce(delta_t)
-            eng.q_delta_apply()
-        return loss
+        if trainer is not None:
+            return trainer.epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
+        return eng.bpr_epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
 
     def barrier():
         eng.sync()
@@ -264,6 +254,10 @@ def run_native(args):
         if world > 1:
             eng.q_snapshot()
         loss = step(2000 + k, want_loss=True)
+        if world > 1:                               # the epoch loss is a sum over all ranks' events
+            lt = torch.tensor([loss], device="cuda", dtype=torch.float64)
+            dist.all_reduce(lt)
+            loss = float(lt.item())
         p2, q2 = eng.frob2()
         eng.get_factors(pP.array, pQ.array)
         loss += REG_U * p2 + REG_I * q2
