@@ -108,6 +108,18 @@ int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI,
 int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T,
                   double lr, double regU, double regI, int mode, double* loss_out);
 
+/* APR (adversarial BPR, recommender/advanced/APR.py:25-76, config C5): the same pass with the
+ * adversarial perturbation fused per triplet -- loss softplus(-y) + regA softplus(-y_adv),
+ * delta = eps * normalised gradient, held constant in the step (oracle/apr_ref.py states the
+ * closed forms).  `slot` numbers the negative of each positive (the reference draws 3 per
+ * positive, APR.py:95-111: call with slot = 0, 1, 2).  Replaces the body of APR.buildModel's
+ * adversarial phase (APR.py:129-137); the first phase (APR.py:120-127) is yue_bpr_epoch. */
+int yue_apr_epoch(yue_t* h, double lr, double regU, double regI, double eps, double regA,
+                  uint64_t seed, uint32_t epoch, uint32_t slot, int mode, double* loss_out);
+int yue_apr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T,
+                  double lr, double regU, double regI, double eps, double regA, int mode,
+                  double* loss_out);
+
 /* (P*P).sum(), (Q*Q).sum() of BPR.py:59, accumulated in float64. */
 int yue_frob2(yue_t* h, double* p2, double* q2);
 

@@ -84,6 +84,8 @@ struct SgdParams {
     // as SHARDED ACCUMULATORS: the logical row is  Q[t] + sum_r shard[r][t];  a warp adds its change
     // to shard (warp % R) and every reader sums all R rows.  One logical copy, nothing goes stale,
     // the chain per address is R times shorter.  hot_fold_kernel folds the shards back into Q.
+    uint32_t slot;                 // which negative of the positive (0 for BPR; APR draws 3, slots 0..2)
+    float eps, regA;               // APR only: perturbation size and adversarial weight (APR.conf -eps -regA)
     int resync_events;             // a shared (multi-item) user publishes + re-reads P[u] every this many events
     const int32_t* hot_items;      // [n_hot] track id of each hot slot
     int n_hot;
@@ -134,7 +136,11 @@ struct RowOps {
 constexpr int kSgdThreads = 512;
 constexpr int kHotShards = 8;
 
-template <int NCH, int MODE, int PF, bool ILV>
+// APR = true: K2a, adversarial BPR with the perturbation fused per triplet (oracle/apr_ref.py has the
+// derivation): y_adv = y - 2 eps |P| - eps |d| + 2 eps^2 y / (|P||d|), a = lr (s0 + regA s1),
+// b = lr regA s1 eps;  P += a d - 2 b P^,  Q[i] += a P - b d^,  Q[j] -= a P - b d^  (old rows), then
+// the same multiplicative shrinks.  Two more half-warp reductions (|P|^2, |d|^2) per triplet.
+template <int NCH, int MODE, int PF, bool ILV, bool APR>
 __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams p) {
     static_assert(!ILV || NCH == 1, "the interleaved Q layout is defined for 64-float rows");
     // address of this lane's first chunk of Q row r
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
             const int64_t e = begin + lane;
             my_i = p.ev_items[e];
             my_j = p.ev_neg ? p.ev_neg[e]
-                            : sample_negative(p.seed, p.epoch, (uint64_t)(p.event_base + e), 0u,
+                            : sample_negative(p.seed, p.epoch, (uint64_t)(p.event_base + e), p.slot,
                                               p.n_items, row, row_len);
         }
         __syncwarp();
@@ -316,6 +322,62 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
                 const float other = __shfl_xor_sync(0xffffffffu, part, 16);
                 const float x = half ? (other - part) : (part - other);
 
+                if (APR) {
+                    // d = Q[i] - Q[j] on both halves, |P|^2 and |d|^2 reduced inside each half
+                    float4 d[NCH];
+                    float pp = 0.f, dd = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float4 o = shfl_xor4(q[c], 16);
+                        d[c].x = half ? (o.x - q[c].x) : (q[c].x - o.x);
+                        d[c].y = half ? (o.y - q[c].y) : (q[c].y - o.y);
+                        d[c].z = half ? (o.z - q[c].z) : (q[c].z - o.z);
+                        d[c].w = half ? (o.w - q[c].w) : (q[c].w - o.w);
+                        pp += pu[c].x * pu[c].x + pu[c].y * pu[c].y + pu[c].z * pu[c].z + pu[c].w * pu[c].w;
+                        dd += d[c].x * d[c].x + d[c].y * d[c].y + d[c].z * d[c].z + d[c].w * d[c].w;
+                    }
+#pragma unroll
+                    for (int m = 8; m >= 1; m >>= 1) {
+                        pp += __shfl_xor_sync(0xffffffffu, pp, m);
+                        dd += __shfl_xor_sync(0xffffffffu, dd, m);
+                    }
+                    const float np_ = sqrtf(pp), nd = sqrtf(dd);
+                    const float inp = np_ > 0.f ? 1.f / np_ : 0.f, ind = nd > 0.f ? 1.f / nd : 0.f;
+                    const float xa = x - 2.f * p.eps * np_ - p.eps * nd + 2.f * p.eps * p.eps * x * inp * ind;
+                    float s0, s1;
+                    if (MODE == kSerial) {
+                        s0 = (float)(1.0 / (1.0 + exp((double)x)));
+                        s1 = (float)(1.0 / (1.0 + exp((double)xa)));
+                        loss += fmax(-(double)x, 0.0) + log1p(exp(-fabs((double)x))) +
+                                (double)p.regA * (fmax(-(double)xa, 0.0) + log1p(exp(-fabs((double)xa))));
+                    } else {
+                        const float e0 = __expf(-fabsf(x)), e1 = __expf(-fabsf(xa));
+                        s0 = (x >= 0.f ? e0 : 1.f) / (1.f + e0);           // sigmoid(-x)
+                        s1 = (xa >= 0.f ? e1 : 1.f) / (1.f + e1);
+                        loss += (double)(fmaxf(-x, 0.f) + log1pf(e0) + p.regA * (fmaxf(-xa, 0.f) + log1pf(e1)));
+                    }
+                    const float a = p.lr * (s0 + p.regA * s1), b = p.lr * p.regA * s1 * p.eps;
+                    const float sa = half ? -a : a, sb = (half ? b : -b) * ind;       // Q[i]: +aP - b d^ ; Q[j]: -aP + b d^
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float4 po = pu[c];
+                        const float k2 = -2.f * b * inp;
+                        pu[c] = make_float4(fmaf(a, d[c].x, fmaf(k2, po.x, po.x)), fmaf(a, d[c].y, fmaf(k2, po.y, po.y)),
+                                            fmaf(a, d[c].z, fmaf(k2, po.z, po.z)), fmaf(a, d[c].w, fmaf(k2, po.w, po.w)));
+                        float4 qn = make_float4(fmaf(sa, po.x, fmaf(sb, d[c].x, q[c].x)), fmaf(sa, po.y, fmaf(sb, d[c].y, q[c].y)),
+                                                fmaf(sa, po.z, fmaf(sb, d[c].z, q[c].z)), fmaf(sa, po.w, fmaf(sb, d[c].w, q[c].w)));
+                        pu[c] = R::axpy4(-p.c_u, pu[c], pu[c]);
+                        qn = R::axpy4(-p.c_i, qn, qn);
+                        if (act[c]) {
+                            if (MODE == kAtomic || (hot && half == 0))
+                                red_row(dst + 64 * c, make_float4(qn.x - q[c].x, qn.y - q[c].y, qn.z - q[c].z, qn.w - q[c].w));
+                            else
+                                st_row(dst + 64 * c, qn);
+                        }
+                    }
+                    if (MODE == kSerial) __syncwarp();
+                    continue;
+                }
                 float g;
                 if (MODE == kSerial) {          // tool/qmath.py:115-116 in float64, like CPython
                     const double s = 1.0 / (1.0 + exp(-(double)x));

@@ -441,10 +441,10 @@ int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot,
     return YUE_OK;
 }
 
-template <int NCH, bool ILV>
+template <int NCH, bool ILV, bool APR>
 static cudaError_t launch_sgd(const SgdParams& sp, int mode, int warps_per_cta, cudaStream_t st) {
     if (mode == YUE_MODE_SERIAL) {
-        bpr_sgd_kernel<NCH, kSerial, 1, ILV><<<1, 32, 0, st>>>(sp);
+        bpr_sgd_kernel<NCH, kSerial, 1, ILV, APR><<<1, 32, 0, st>>>(sp);
         return cudaGetLastError();
     }
     constexpr int PF = NCH <= 2 ? 4 : 2;
@@ -452,29 +452,32 @@ static cudaError_t launch_sgd(const SgdParams& sp, int mode, int warps_per_cta, 
     // leave SMs idle when fewer than 16 warps per SM are wanted)
     const int grid = (sp.n_warps + warps_per_cta - 1) / warps_per_cta;
     const size_t smem = (size_t)sp.n_hot * 4;
-    auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF, ILV> : bpr_sgd_kernel<NCH, kStore, PF, ILV>;
+    auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF, ILV, APR> : bpr_sgd_kernel<NCH, kStore, PF, ILV, APR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
     if (e != cudaSuccess) return e;
     kern<<<grid, warps_per_cta * 32, smem, st>>>(sp);
     return cudaGetLastError();
 }
 
-static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out) {
+static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr = false) {
     REQUIRE(mode >= YUE_MODE_SERIAL && mode <= YUE_MODE_HOGWILD_STORE, YUE_E_ARG, "unknown mode");
     CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
     sp.cursor = h->cursor.p;
-    const bool ilv = h->use_ilv && h->ld == 64 && mode != YUE_MODE_SERIAL;
+    const bool ilv = h->use_ilv && h->ld == 64 && mode != YUE_MODE_SERIAL && !apr;
     if (ilv) { if (int rc = q_interleaved(h)) return rc; } else { if (int rc = q_rowmajor(h)) return rc; }
     sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
     const int nch = (sp.nchunks + 15) / 16;
     const int wpc = std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm));
     switch (nch) {
-        case 1: if (ilv) CK(launch_sgd<1, true>(sp, mode, wpc, h->stream)); else CK(launch_sgd<1, false>(sp, mode, wpc, h->stream)); break;
-        case 2: CK(launch_sgd<2, false>(sp, mode, wpc, h->stream)); break;
-        case 3: CK(launch_sgd<3, false>(sp, mode, wpc, h->stream)); break;
-        case 4: CK(launch_sgd<4, false>(sp, mode, wpc, h->stream)); break;
+        case 1: if (apr) CK(launch_sgd<1, false, true>(sp, mode, wpc, h->stream));
+                else if (ilv) CK(launch_sgd<1, true, false>(sp, mode, wpc, h->stream));
+                else CK(launch_sgd<1, false, false>(sp, mode, wpc, h->stream));
+                break;
+        case 2: if (apr) CK(launch_sgd<2, false, true>(sp, mode, wpc, h->stream)); else CK(launch_sgd<2, false, false>(sp, mode, wpc, h->stream)); break;
+        case 3: if (apr) CK(launch_sgd<3, false, true>(sp, mode, wpc, h->stream)); else CK(launch_sgd<3, false, false>(sp, mode, wpc, h->stream)); break;
+        case 4: if (apr) CK(launch_sgd<4, false, true>(sp, mode, wpc, h->stream)); else CK(launch_sgd<4, false, false>(sp, mode, wpc, h->stream)); break;
         default: return fail(h, YUE_E_UNSUPPORTED, "num.factors > 256");
     }
     ++h->launches;
@@ -500,9 +503,10 @@ static void fill_rates(SgdParams& sp, double lr, double regU, double regI) {
     sp.lr_d = lr; sp.lr = (float)lr; sp.c_u = (float)(lr * regU); sp.c_i = (float)(lr * regI);
 }
 
-int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, uint32_t epoch, int mode,
-                  double* loss_out) {
+static int sgd_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, uint32_t epoch, uint32_t slot,
+                     int mode, double* loss_out, bool apr, double eps, double regA) {
     REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
+    REQUIRE(slot < 4096, YUE_E_ARG, "slot must be < 4096");
     CK(cudaSetDevice(h->device));
     if (h->T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     SgdParams sp{};
@@ -522,12 +526,21 @@ int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, 
         sp.hot_shards = h->hot_shards.p;
     }
     sp.resync_events = h->resync_events;
-    sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base;
-    return run_sgd(h, sp, mode, loss_out);
+    sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base; sp.slot = slot;
+    sp.eps = (float)eps; sp.regA = (float)regA;
+    return run_sgd(h, sp, mode, loss_out, apr);
+}
+int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, uint32_t epoch, int mode,
+                  double* loss_out) {
+    return sgd_epoch(h, lr, regU, regI, seed, epoch, 0u, mode, loss_out, false, 0.0, 0.0);
+}
+int yue_apr_epoch(yue_t* h, double lr, double regU, double regI, double eps, double regA, uint64_t seed,
+                  uint32_t epoch, uint32_t slot, int mode, double* loss_out) {
+    return sgd_epoch(h, lr, regU, regI, seed, epoch, slot, mode, loss_out, true, eps, regA);
 }
 
-int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T, double lr,
-                  double regU, double regI, int mode, double* loss_out) {
+static int sgd_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T, double lr,
+                     double regU, double regI, int mode, double* loss_out, bool apr, double eps, double regA) {
     REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
     REQUIRE(T >= 0 && (T == 0 || (u && i && j)), YUE_E_ARG, "null triplet array");
     CK(cudaSetDevice(h->device));
@@ -565,9 +578,18 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
     sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
     sp.n_hot = 0;                                // explicit triplets take the direct path
     sp.resync_events = h->resync_events;
-    int rc = run_sgd(h, sp, mode, loss_out);
+    sp.eps = (float)eps; sp.regA = (float)regA;
+    int rc = run_sgd(h, sp, mode, loss_out, apr);
     cudaStreamSynchronize(h->stream);           // host staging vectors die here
     return rc;
+}
+int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T, double lr,
+                  double regU, double regI, int mode, double* loss_out) {
+    return sgd_apply(h, u, i, j, T, lr, regU, regI, mode, loss_out, false, 0.0, 0.0);
+}
+int yue_apr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T, double lr,
+                  double regU, double regI, double eps, double regA, int mode, double* loss_out) {
+    return sgd_apply(h, u, i, j, T, lr, regU, regI, mode, loss_out, true, eps, regA);
 }
 
 int yue_frob2(yue_t* h, double* p2, double* q2) {

@@ -128,6 +128,19 @@ class Engine:
                                         len(u), lr, regU, regI, mode, C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
 
+    def apr_epoch(self, lr, regU, regI, eps, regA, seed, epoch, slot=0, mode=MODE_HOGWILD, want_loss=True):
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_apr_epoch(self.h, lr, regU, regI, eps, regA, seed, epoch, slot, mode,
+                                        C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
+    def apr_apply(self, u, i, j, lr, regU, regI, eps, regA, mode=MODE_SERIAL, want_loss=True):
+        u, i, j = _as(u, np.int32), _as(i, np.int32), _as(j, np.int32)
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_apr_apply(self.h, _ptr(u, C.c_int32), _ptr(i, C.c_int32), _ptr(j, C.c_int32),
+                                        len(u), lr, regU, regI, eps, regA, mode, C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
     def frob2(self):
         p2, q2 = C.c_double(), C.c_double()
         self._ck(self.lib.yue_frob2(self.h, C.byref(p2), C.byref(q2)))
