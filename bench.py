@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--sgd-mode", default="atomic", choices=["atomic", "store"])
     ap.add_argument("--no-rank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--rank-users", type=int, default=8192)
+    ap.add_argument("--rank-users", type=int, default=18944)   # one full wave: 148 CTAs x 128 users
     args = ap.parse_args()
     if args.warmup < 3 and not args.small:
         args.warmup = 3

@@ -157,6 +157,69 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) |
                                 ((uint32_t)(kTcBM >> 4) << 24);
 
+// ---- the rare path of the epilogue, kept OUT of line ------------------------------------------
+// ncu on the first version: 73 % of the epilogue's stall samples were `no_inst` -- the 32-way
+// unrolled push code, inlined at four sites, made a 218 KB kernel that thrashed the instruction
+// cache.  Now an unrolled slot is a compare and a predicated call.
+struct TcRow {                 // per-thread (= per user row) state the rare path works on
+    int64_t mcur, mend;        // cursor into the user's sorted play row (tiles arrive in track order)
+    int mval;                  // uq_items[mcur] or INT32_MAX
+    int cnt;                   // entries in the row's shared-memory buffer
+    int ovf_slot, ovf_cnt;     // >= 0: the row spills into the global pool
+    int fail;                  // row must be redone by the exact kernel
+};
+// push one surviving score; returns true when the row has to give up (pool row full)
+__device__ __noinline__ bool tc_push(TcRow* st, uint64_t* K, const int32_t* __restrict__ uq_items,
+                                     uint64_t* __restrict__ ovf_pool, float sc, int id) {
+    while (st->mval < id) { ++st->mcur; st->mval = st->mcur < st->mend ? uq_items[st->mcur] : INT32_MAX; }
+    if (st->mval == id) return false;                               // a training track of this user
+    if (st->ovf_slot < 0) { K[st->cnt++] = make_key(sc, id); return false; }   // cnt <= 32 before the chunk
+    if (st->ovf_cnt < kTcOvfCap) { ovf_pool[(size_t)st->ovf_slot * kTcOvfCap + st->ovf_cnt++] = make_key(sc, id); return false; }
+    st->fail = 1;
+    return true;
+}
+// whole warp: compact every row of this warp whose buffer is more than half full; returns the
+// (possibly raised) push threshold of the calling lane's row
+__device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int lane, int N, float eps2, float thr,
+                                         uint64_t* __restrict__ ovf_pool, int* __restrict__ ovf_next) {
+    unsigned full;
+    while ((full = __ballot_sync(0xffffffffu, st->cnt > kTcCap - 32)) != 0u) {
+        const int src = __ffs(full) - 1;
+        const int cc = __shfl_sync(0xffffffffu, st->cnt, src);
+        const float e2 = __shfl_sync(0xffffffffu, eps2, src);
+        uint64_t* R = keys_quarter + (size_t)src * kTcCap;
+        const uint64_t m0 = lane < cc ? R[lane] : ~0ull, m1 = lane + 32 < cc ? R[lane + 32] : ~0ull;
+        int r0 = 0, r1 = 0;
+        for (int e = 0; e < cc; ++e) { const uint64_t k = R[e]; r0 += k < m0; r1 += k < m1; }
+        __syncwarp();
+        if (lane < cc) R[r0] = m0;
+        if (lane + 32 < cc) R[r1] = m1;
+        __syncwarp();
+        const float lim = key_score(R[N - 1]) - e2;                 // cc > 32 >= N
+        const bool k0 = lane < cc && key_score(R[lane]) >= lim;
+        const bool k1 = lane + 32 < cc && key_score(R[lane + 32]) >= lim;
+        const int kept = __popc(__ballot_sync(0xffffffffu, k0)) + __popc(__ballot_sync(0xffffffffu, k1));
+        int slot = -1;
+        if (kept > kTcCap - 32) {              // too many near-ties for shared memory: spill the row
+            if (lane == 0) slot = atomicAdd(ovf_next, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < kTcOvfRows) {
+                uint64_t* G = ovf_pool + (size_t)slot * kTcOvfCap;
+                if (lane < kept) G[lane] = R[lane];
+                if (lane + 32 < kept) G[lane + 32] = R[lane + 32];
+            }
+        }
+        if (lane == src) {
+            thr = lim;
+            if (kept <= kTcCap - 32) st->cnt = kept;
+            else if (slot < kTcOvfRows) { st->ovf_slot = slot; st->ovf_cnt = kept; st->cnt = 0; }   // threshold frozen from here on
+            else { st->fail = 1; thr = INFINITY; st->cnt = 0; }
+        }
+        __syncwarp();
+    }
+    return thr;
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const RankTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
@@ -241,68 +304,28 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         uint64_t* K = keys + (size_t)r * kTcCap;
         const float eps2 = valid ? 2.f * kTf32ErrCoef * p.pnorm[b] * (*p.qmax) : 0.f;
         float thr = valid ? -INFINITY : INFINITY;       // push threshold = tau - 2 eps
-        int cnt = 0;
-        bool fail = false;
-        int64_t mcur = 0, mend = 0;
-        if (valid) { const int u = p.users[b]; mcur = p.uq_indptr[u]; mend = p.uq_indptr[u + 1]; }
-        int mval = mcur < mend ? p.uq_items[mcur] : INT32_MAX;
+        TcRow st;
+        st.mcur = 0; st.mend = 0; st.cnt = 0; st.ovf_slot = -1; st.ovf_cnt = 0; st.fail = 0;
+        if (valid) { const int u = p.users[b]; st.mcur = p.uq_indptr[u]; st.mend = p.uq_indptr[u + 1]; }
+        st.mval = st.mcur < st.mend ? p.uq_items[st.mcur] : INT32_MAX;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint64_t* keys_quarter = keys + (size_t)(quarter * 32) * kTcCap;
 
-        int ovf_slot = -1, ovf_cnt = 0;                 // >= 0: this row spills into the global pool
         // examine 32 scores of columns [col0, col0+32): push survivors, then compact crowded rows
-        auto rare_path = [&](const uint32_t* v, int col0, float m) {
-            if (m >= thr) {
-#pragma unroll
-                for (int x = 0; x < 32; ++x) {
-                    const float sc = __uint_as_float(v[x]);
-                    const int id = col0 + x;
-                    if (sc >= thr && id < p.n_items) {
-                        while (mval < id) { ++mcur; mval = mcur < mend ? p.uq_items[mcur] : INT32_MAX; }
-                        if (mval != id) {
-                            if (ovf_slot < 0) K[cnt++] = make_key(sc, id);          // cnt <= 32 before the chunk
-                            else if (ovf_cnt < kTcOvfCap) p.ovf_pool[(size_t)ovf_slot * kTcOvfCap + ovf_cnt++] = make_key(sc, id);
-                            else { fail = true; thr = INFINITY; }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            unsigned full;
-            while ((full = __ballot_sync(0xffffffffu, cnt > kTcCap - 32)) != 0u) {
-                const int src = __ffs(full) - 1;
-                const int cc = __shfl_sync(0xffffffffu, cnt, src);
-                const float e2 = __shfl_sync(0xffffffffu, eps2, src);
-                uint64_t* R = keys + (size_t)(quarter * 32 + src) * kTcCap;
-                const uint64_t m0 = lane < cc ? R[lane] : ~0ull, m1 = lane + 32 < cc ? R[lane + 32] : ~0ull;
-                int r0 = 0, r1 = 0;
-                for (int e = 0; e < cc; ++e) { const uint64_t k = R[e]; r0 += k < m0; r1 += k < m1; }
-                __syncwarp();
-                if (lane < cc) R[r0] = m0;
-                if (lane + 32 < cc) R[r1] = m1;
-                __syncwarp();
-                const float lim = key_score(R[p.N - 1]) - e2;             // cc > 32 >= N
-                const bool k0 = lane < cc && key_score(R[lane]) >= lim;
-                const bool k1 = lane + 32 < cc && key_score(R[lane + 32]) >= lim;
-                const int kept = __popc(__ballot_sync(0xffffffffu, k0)) + __popc(__ballot_sync(0xffffffffu, k1));
-                int slot = -1;
-                if (kept > kTcCap - 32) {          // too many near-ties for shared memory: spill the row
-                    if (lane == 0) slot = atomicAdd(p.ovf_next, 1);
-                    slot = __shfl_sync(0xffffffffu, slot, 0);
-                    if (slot < kTcOvfRows) {
-                        uint64_t* G = p.ovf_pool + (size_t)slot * kTcOvfCap;
-                        if (lane < kept) G[lane] = R[lane];
-                        if (lane + 32 < kept) G[lane + 32] = R[lane + 32];
-                    }
-                }
-                if (lane == src) {
-                    thr = lim;
-                    if (kept <= kTcCap - 32) cnt = kept;
-                    else if (slot < kTcOvfRows) { ovf_slot = slot; ovf_cnt = kept; cnt = 0; }   // threshold frozen from here on
-                    else { fail = true; thr = INFINITY; cnt = 0; }
-                }
-                __syncwarp();
-            }
-        };
+#define TC_RARE(v, col0, m)                                                                          \
+        do {                                                                                         \
+            if ((m) >= thr) {                                                                        \
+                _Pragma("unroll")                                                                    \
+                for (int x = 0; x < 32; ++x) {                                                       \
+                    const float sc = __uint_as_float((v)[x]);                                        \
+                    if (sc >= thr && (col0) + x < p.n_items)                                         \
+                        if (tc_push(&st, K, p.uq_items, p.ovf_pool, sc, (col0) + x)) thr = INFINITY; \
+                }                                                                                    \
+            }                                                                                        \
+            __syncwarp();                                                                            \
+            thr = tc_compact(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next);       \
+        } while (0)
+
         for (int j = 0; j < p.ntiles; ++j) {
             const int t = j % kTcAcc;
             const uint32_t tph = (uint32_t)(j / kTcAcc) & 1u;
@@ -316,17 +339,20 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             float m0 = __uint_as_float(va[0]), m1 = __uint_as_float(va[32]);
 #pragma unroll
             for (int x = 1; x < 32; ++x) { m0 = fmaxf(m0, __uint_as_float(va[x])); m1 = fmaxf(m1, __uint_as_float(va[32 + x])); }
-            if (__any_sync(0xffffffffu, m0 >= thr)) rare_path(va, i0, m0);
-            if (__any_sync(0xffffffffu, m1 >= thr)) rare_path(va + 32, i0 + 32, m1);
+            if (__any_sync(0xffffffffu, m0 >= thr)) TC_RARE(va, i0, m0);
+            if (__any_sync(0xffffffffu, m1 >= thr)) TC_RARE(va + 32, i0 + 32, m1);
             tc_ld_wait();
             tc_fence_before();
             mbar_arrive(bar_tempty(t));                                 // TMEM stage free: the rest works on registers
             float m2 = __uint_as_float(vb[0]), m3 = __uint_as_float(vb[32]);
 #pragma unroll
             for (int x = 1; x < 32; ++x) { m2 = fmaxf(m2, __uint_as_float(vb[x])); m3 = fmaxf(m3, __uint_as_float(vb[32 + x])); }
-            if (__any_sync(0xffffffffu, m2 >= thr)) rare_path(vb, i0 + 64, m2);
-            if (__any_sync(0xffffffffu, m3 >= thr)) rare_path(vb + 32, i0 + 96, m3);
+            if (__any_sync(0xffffffffu, m2 >= thr)) TC_RARE(vb, i0 + 64, m2);
+            if (__any_sync(0xffffffffu, m3 >= thr)) TC_RARE(vb + 32, i0 + 96, m3);
         }
+#undef TC_RARE
+        const int cnt = st.cnt, ovf_slot = st.ovf_slot, ovf_cnt = st.ovf_cnt;
+        const bool fail = st.fail != 0;
 
         // ---- exact pass: re-score the survivors with the fp32 FMA chain, sort, write -------------
         __syncwarp();
