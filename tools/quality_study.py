@@ -19,6 +19,8 @@ def run(log, P, Q, mode, epochs, lr, seed, env):
     for k, v in env.items():
         os.environ[k] = str(v)
     eng = Engine(0)
+    for k in env:
+        os.environ.pop(k, None)
     try:
         eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
         eng.set_factors(P, Q)
@@ -65,26 +67,19 @@ def main():
         configs.append(("hogwild %d ev/warp, no hot" % epw, MODE_HOGWILD, dict(YUE_SGD_MIN_EVENTS_PER_WARP=epw, **nohot)))
         configs.append(("hogwild %d ev/warp, hot flush 4" % epw, MODE_HOGWILD, dict(YUE_SGD_MIN_EVENTS_PER_WARP=epw, **hot)))
     if c2_epochs:       # full-GPU concurrency at the true scale
+        # STUDY_CONFIGS="name:K=V,K=V;name2:K=V" (env of each configuration), STUDY_REPS runs of each;
+        # STUDY_SERIAL=1 trains the serial-order reference first (minutes at C2)
         sweeps = ((0.02, c2_epochs),)
-        base_env = dict(YUE_SGD_MIN_EVENTS_PER_WARP=16384, YUE_SGD_ITEM_SEGS=0, YUE_SGD_SEG_EVENTS=32, YUE_SGD_WARPS_PER_SM=16, YUE_SGD_MAX_ITEMS=16, **nohot)
-        def cfg(name, **kw):
-            e = dict(base_env); e.update(kw); return (name, MODE_HOGWILD, e)
         configs = []
         if os.environ.get("STUDY_SERIAL", "1") == "1":
             configs.append(("serial seed 99", MODE_SERIAL, {}))
-        base_env.pop("YUE_SGD_MAX_ITEMS")
-        hotenv = dict(YUE_SGD_HOT_MAX=64, YUE_SGD_HOT_MIN_COUNT=16384)
-        reps = int(os.environ.get("STUDY_REPS", "5"))
-        which = os.environ.get("STUDY_SET", "base")
-        if which == "base":
-            configs += [cfg("direct (no hot rows), run %d" % k) for k in range(reps)]
-            configs += [cfg("sharded hot rows (default), run %d" % k, **hotenv) for k in range(reps)]
-        else:
-            configs += [cfg("sharded, 12 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=12, **hotenv) for k in range(reps)]
-            configs += [cfg("sharded, 10 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=10, **hotenv) for k in range(reps)]
-            configs += [cfg("direct, 12 warps/SM, run %d" % k, YUE_SGD_WARPS_PER_SM=12) for k in range(reps)]
+        reps = int(os.environ.get("STUDY_REPS", "3"))
+        for spec in os.environ.get("STUDY_CONFIGS", "default:").split(";"):
+            name, _, kvs = spec.partition(":")
+            env = dict(kv.split("=") for kv in kvs.split(",") if kv)
+            configs += [("%s, run %d" % (name, k), MODE_HOGWILD, env) for k in range(reps)]
     for lr, epochs in sweeps:
-        base = None
+        base = tuple(float(x) for x in os.environ["STUDY_BASE"].split(",")) if os.environ.get("STUDY_BASE") else None
         for name, mode, env in configs:
             seed = 100 if name.endswith("100") else 99
             r, n, loss, dt, qn = run(log, P, Q, mode, epochs, lr, seed, env)

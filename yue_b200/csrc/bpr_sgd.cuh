@@ -89,7 +89,12 @@ struct SgdParams {
     int resync_events;             // a shared (multi-item) user publishes + re-reads P[u] every this many events
     const int32_t* hot_items;      // [n_hot] track id of each hot slot
     int n_hot;
-    float* hot_shards;             // [(kHotShards-1), n_hot, ld] extra accumulators (shard 0 is Q itself)
+    const int32_t* hot_meta;       // [n_hot] (first extra row << 4) | shards; shards is a power of two <= 8
+    float* hot_shards;             // [extra rows, ld] extra accumulators of the hot tracks (shard 0 is Q itself)
+    // blocked kernel (bpr_sgd_blk.cuh): the hot rows live in a table with a slice-friendly layout
+    float* hotQ;
+    const int32_t* hot_sorted;     // [n_hot] hot track ids ascending, and the slot of each
+    const int32_t* hot_sorted_slot;
 };
 
 __device__ __forceinline__ float4 ld_row(const float* p) {
@@ -147,9 +152,10 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
     auto q_lane_ptr = [&](int64_t r, int l16_) -> float* {
         return ILV ? p.Q + q_ilv_float_offset(r, l16_) : p.Q + (size_t)r * p.ld + 4 * l16_;
     };
-    extern __shared__ __align__(16) int hot_ids[];        // [n_hot] track id per hot slot
+    extern __shared__ __align__(16) int hot_ids[];        // [n_hot] track id per hot slot, then [n_hot] meta
+    int* hot_meta = hot_ids + p.n_hot;
     if (MODE != kSerial && p.n_hot > 0) {
-        for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) hot_ids[x] = p.hot_items[x];
+        for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) { hot_ids[x] = p.hot_items[x]; hot_meta[x] = p.hot_meta[x]; }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -286,18 +292,19 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
                 const int32_t it_raw = __shfl_sync(0xffffffffu, my_i, t);
                 const bool hot = MODE != kSerial && it_raw < 0;
                 if (hot && half == 0) {
-                    const int slot = -it_raw - 1;
-                    const float* sh = p.hot_shards + (size_t)slot * p.ld + lane_off;
-                    const size_t stride = (size_t)p.n_hot * p.ld;
+                    const int meta = hot_meta[-it_raw - 1];
+                    const int nex = (meta & 15) - 1;                      // extra shard rows of this track
+                    const float* sh = p.hot_shards + (size_t)(meta >> 4) * p.ld + lane_off;
 #pragma unroll
                     for (int r0 = 0; r0 < kHotShards - 1; r0 += 4) {      // 4 independent loads in flight
+                        if (r0 >= nex) break;
                         float4 ex[4][NCH];
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
 #pragma unroll
                             for (int c = 0; c < NCH; ++c)
-                                ex[r][c] = (act[c] && r0 + r < kHotShards - 1) ? ld_row(sh + (r0 + r) * stride + 64 * c)
-                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                                ex[r][c] = (act[c] && r0 + r < nex) ? ld_row(sh + (size_t)(r0 + r) * p.ld + 64 * c)
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -305,8 +312,8 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
                                 q[c].x += ex[r][c].x; q[c].y += ex[r][c].y; q[c].z += ex[r][c].z; q[c].w += ex[r][c].w;
                             }
                     }
-                    const int myshard = warp % kHotShards;
-                    if (myshard > 0) dst = const_cast<float*>(sh) + (size_t)(myshard - 1) * stride;
+                    const int myshard = warp & ((meta & 15) - 1);          // shard counts are powers of two
+                    if (myshard > 0) dst = const_cast<float*>(sh) + (size_t)(myshard - 1) * p.ld;
                 }
                 // dots: each half reduces its own row, then x = P.Qi - P.Qj (BPR.py:50)
                 float part = 0.f;
@@ -449,14 +456,16 @@ __global__ void q_from_ilv_kernel(float4* __restrict__ q, const float* __restric
 // ---- fold the hot-row shards back into Q (after every Hogwild launch) ----------------------------
 template <bool ILV>
 __global__ void hot_fold_kernel(float* __restrict__ Q, float* __restrict__ shards, const int32_t* __restrict__ hot_items,
-                                int n_hot, int ld) {
+                                const int32_t* __restrict__ hot_meta, int n_hot, int ld) {
     const int per = ld / 4;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n_hot * per; x += gridDim.x * blockDim.x) {
         const int slot = x / per, c4 = x % per;
+        const int meta = hot_meta[slot], nex = (meta & 15) - 1;
+        if (nex <= 0) continue;
         float* dst = ILV ? Q + q_ilv_float_offset(hot_items[slot], c4) : Q + (size_t)hot_items[slot] * ld + 4 * c4;
         float4 acc = *reinterpret_cast<float4*>(dst);
-        for (int r = 0; r < kHotShards - 1; ++r) {
-            float4* sp = reinterpret_cast<float4*>(shards + ((size_t)r * n_hot + slot) * ld + 4 * c4);
+        for (int r = 0; r < nex; ++r) {
+            float4* sp = reinterpret_cast<float4*>(shards + ((size_t)(meta >> 4) + r) * ld + 4 * c4);
             const float4 v = *sp;
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             *sp = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "bpr_sgd.cuh"
+#include "bpr_sgd_blk.cuh"
 #include "rank_exact.cuh"
 #include "rank_tc.cuh"
 
@@ -89,12 +90,19 @@ struct yue_handle {
     // stale deltas inflate the epoch loss 1.7-2.5x; with <= 16 the loss is within 0.3 % of the serial
     // order and 8 reproduces its Recall@10 / NDCG@10 (profiles/quality_study_r1.md).
     int resync_events = 8;
-    int hot_max = 64;                 // tracks kept as sharded accumulators (see SgdParams)
-    int hot_min_count = 16384;        // a track is hot when it is the positive of at least this many events
+    // Hot tracks (see SgdParams): a track is hot when it is the positive of >= hot_min_count events AND of
+    // more than 1/hot_div of all events; it gets min(cap, pow2ceil(share * hot_div)) accumulator shards, so
+    // the chain of dependent atomics on one address stays below ~T/hot_div updates (~11 ns each).
+    int hot_max = kHotSlots;
+    int hot_min_count = 16384;
+    int hot_div = 128;
     int n_hot = 0;
-    DevBuf<int32_t> hot_items, hot_slot, item_counts;
-    DevBuf<float> hot_shards;
-    bool shards_clean = false;
+    std::vector<int32_t> h_hot_counts;   // per hot slot
+    int hot_meta_cap = 0, hot_meta_ld = 0;   // what the current hot_meta / hot_shards were built for
+    int64_t hot_extra_rows = 0;
+    int sgd_kernel = 2;               // YUE_SGD_KERNEL: 1 = per-triplet kernel, 2 = blocked kernel where it applies
+    DevBuf<int32_t> hot_items, hot_slot, item_counts, hot_meta, hot_sorted, hot_sorted_slot;
+    DevBuf<float> hot_shards, hotQ;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -227,8 +235,10 @@ int yue_create(int device, yue_t** out) {
     }
     h->sm_count = prop.multiProcessorCount;
     h->l2_bytes = (size_t)prop.l2CacheSize;
-    if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(96, atoi(s)));   // 96 slots x 256 floats x 8 B fits one CTA
+    if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(kHotSlots, atoi(s)));
     if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_HOT_DIV")) h->hot_div = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_KERNEL")) h->sgd_kernel = atoi(s) == 1 ? 1 : 2;
     if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
     if (const char* s = getenv("YUE_SGD_MAX_ITEMS")) h->max_items_per_user = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_Q_INTERLEAVE")) h->use_ilv = atoi(s) != 0;
@@ -249,8 +259,8 @@ int yue_destroy(yue_t* h) {
     for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->seg_begin, &h->item_ptr, &h->tmp_sb, &h->tmp_ws}) b->release();
     h->cursor.release();
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->seg_user, &h->seg_len, &h->tmp_i, &h->tmp_j,
-                    &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts}) b->release();
-    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->hot_shards}) b->release();
+                    &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot}) b->release();
+    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
     h->l2buf.release();
     cudaEventDestroy(h->ev0);
@@ -331,13 +341,24 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
         CK(cudaMemcpyAsync(counts.data(), h->item_counts.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         std::vector<int32_t> cand;
-        for (int64_t t = 0; t < n; ++t) if (counts[t] >= h->hot_min_count) cand.push_back((int32_t)t);
+        for (int64_t t = 0; t < n; ++t)
+            if (counts[t] >= h->hot_min_count && (int64_t)counts[t] * h->hot_div > T) cand.push_back((int32_t)t);
         std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return counts[a] != counts[b] ? counts[a] > counts[b] : a < b; });
         if ((int)cand.size() > h->hot_max) cand.resize(h->hot_max);
         h->n_hot = (int)cand.size();
+        h->h_hot_counts.clear();
+        for (int32_t t : cand) h->h_hot_counts.push_back(counts[t]);
+        h->hot_meta_cap = 0;
         if (h->n_hot) {
             std::vector<int32_t> slot((size_t)n, -1);
             for (int s2 = 0; s2 < h->n_hot; ++s2) slot[cand[s2]] = s2;
+            std::vector<int32_t> order((size_t)h->n_hot), sorted_ids, sorted_slots;      // ascending track id, for the kernel's lookup of negatives
+            for (int s2 = 0; s2 < h->n_hot; ++s2) order[s2] = s2;
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cand[a] < cand[b]; });
+            for (int32_t s2 : order) { sorted_ids.push_back(cand[s2]); sorted_slots.push_back(s2); }
+            CK(h->hot_sorted.resize(h->n_hot)); CK(h->hot_sorted_slot.resize(h->n_hot)); CK(h->hotQ.resize(kHotTableFloats));
+            CK(cudaMemcpyAsync(h->hot_sorted.p, sorted_ids.data(), sorted_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->hot_sorted_slot.p, sorted_slots.data(), sorted_slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
             CK(h->hot_items.resize(h->n_hot)); CK(h->hot_slot.resize(n));
             CK(cudaMemcpyAsync(h->hot_items.p, cand.data(), cand.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(h->hot_slot.p, slot.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -451,7 +472,7 @@ static cudaError_t launch_sgd(const SgdParams& sp, int mode, int warps_per_cta, 
     // one CTA per SM with warps_per_cta warps each (not n_warps packed into full CTAs: that would
     // leave SMs idle when fewer than 16 warps per SM are wanted)
     const int grid = (sp.n_warps + warps_per_cta - 1) / warps_per_cta;
-    const size_t smem = (size_t)sp.n_hot * 4;
+    const size_t smem = (size_t)sp.n_hot * 8;
     auto kern = mode == YUE_MODE_HOGWILD ? bpr_sgd_kernel<NCH, kAtomic, PF, ILV, APR> : bpr_sgd_kernel<NCH, kStore, PF, ILV, APR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
     if (e != cudaSuccess) return e;
@@ -459,17 +480,69 @@ static cudaError_t launch_sgd(const SgdParams& sp, int mode, int warps_per_cta, 
     return cudaGetLastError();
 }
 
+// blocked kernel: hot rows move into the slice-friendly table for the launch and back after it
+template <int V>
+static cudaError_t launch_sgd_blk(const SgdParams& sp, int warps_per_cta, cudaStream_t st, int64_t& launches) {
+    warps_per_cta = std::min(warps_per_cta, kBlkThreads / 32);
+    const int grid = (sp.n_warps + warps_per_cta - 1) / warps_per_cta;
+    if (sp.n_hot > 0) { hot_gather_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.n_hot, sp.ld); ++launches; }
+    bpr_sgd_blk_kernel<V><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 8, st>>>(sp);
+    if (sp.n_hot > 0) { hot_scatter_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.n_hot, sp.ld); ++launches; }
+    return cudaGetLastError();
+}
+
+// does the blocked kernel (bpr_sgd_blk.cuh) take this launch?
+static bool use_blk_kernel(const yue_t* h, int mode, bool apr) {
+    return h->sgd_kernel == 2 && mode == YUE_MODE_HOGWILD && !apr && (h->ld == 32 || h->ld == 64 || h->ld == 128);
+}
+
+// (re)build the shard table of the hot tracks for the kernel about to run
+static int ensure_hot_meta(yue_t* h, int cap) {
+    if (h->n_hot == 0 || (h->hot_meta_cap == cap && h->hot_meta_ld == h->ld)) return YUE_OK;
+    std::vector<int32_t> meta((size_t)h->n_hot);
+    int64_t rows = 0;
+    for (int s = 0; s < h->n_hot; ++s) {
+        const int64_t want = ((int64_t)h->h_hot_counts[s] * h->hot_div + h->T - 1) / std::max<int64_t>(h->T, 1);
+        int R = 1;
+        while (R < want && R < cap) R *= 2;
+        meta[s] = (int32_t)((rows << 4) | R);
+        rows += R - 1;
+    }
+    CK(h->hot_meta.resize(h->n_hot));
+    CK(cudaMemcpyAsync(h->hot_meta.p, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(h->hot_shards.resize((size_t)std::max<int64_t>(rows, 1) * h->ld));
+    CK(cudaMemsetAsync(h->hot_shards.p, 0, (size_t)std::max<int64_t>(rows, 1) * h->ld * sizeof(float), h->stream));
+    CK(cudaStreamSynchronize(h->stream));       // meta dies here
+    h->hot_extra_rows = rows; h->hot_meta_cap = cap; h->hot_meta_ld = h->ld;
+    return YUE_OK;
+}
+
 static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr = false) {
     REQUIRE(mode >= YUE_MODE_SERIAL && mode <= YUE_MODE_HOGWILD_STORE, YUE_E_ARG, "unknown mode");
     CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
     sp.cursor = h->cursor.p;
-    const bool ilv = h->use_ilv && h->ld == 64 && mode != YUE_MODE_SERIAL && !apr;
+    const bool blk = use_blk_kernel(h, mode, apr);
+    const bool ilv = h->use_ilv && h->ld == 64 && mode != YUE_MODE_SERIAL && !apr && !blk;
     if (ilv) { if (int rc = q_interleaved(h)) return rc; } else { if (int rc = q_rowmajor(h)) return rc; }
     sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
+    if (sp.n_hot > 0) {
+        if (blk) { sp.hotQ = h->hotQ.p; sp.hot_sorted = h->hot_sorted.p; sp.hot_sorted_slot = h->hot_sorted_slot.p; }
+        else {
+            if (int rc = ensure_hot_meta(h, kHotShards)) return rc;
+            sp.hot_meta = h->hot_meta.p; sp.hot_shards = h->hot_shards.p;
+        }
+    }
     const int nch = (sp.nchunks + 15) / 16;
     const int wpc = std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm));
+    if (blk) {
+        switch (h->ld) {
+            case 32: CK(launch_sgd_blk<1>(sp, wpc, h->stream, h->launches)); break;
+            case 64: CK(launch_sgd_blk<2>(sp, wpc, h->stream, h->launches)); break;
+            default: CK(launch_sgd_blk<4>(sp, wpc, h->stream, h->launches)); break;
+        }
+    } else
     switch (nch) {
         case 1: if (apr) CK(launch_sgd<1, false, true>(sp, mode, wpc, h->stream));
                 else if (ilv) CK(launch_sgd<1, true, false>(sp, mode, wpc, h->stream));
@@ -481,10 +554,10 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr 
         default: return fail(h, YUE_E_UNSUPPORTED, "num.factors > 256");
     }
     ++h->launches;
-    if (mode != YUE_MODE_SERIAL && sp.n_hot > 0) {     // fold the hot-row shards back into Q
+    if (mode != YUE_MODE_SERIAL && !blk && sp.n_hot > 0 && h->hot_extra_rows > 0) {     // fold the hot-row shards back into Q
         const int fgrid = (sp.n_hot * (h->ld / 4) + 255) / 256;
-        if (ilv) hot_fold_kernel<true><<<fgrid, 256, 0, h->stream>>>(sp.Q, sp.hot_shards, sp.hot_items, sp.n_hot, h->ld);
-        else hot_fold_kernel<false><<<fgrid, 256, 0, h->stream>>>(sp.Q, sp.hot_shards, sp.hot_items, sp.n_hot, h->ld);
+        if (ilv) hot_fold_kernel<true><<<fgrid, 256, 0, h->stream>>>(sp.Q, sp.hot_shards, sp.hot_items, sp.hot_meta, sp.n_hot, h->ld);
+        else hot_fold_kernel<false><<<fgrid, 256, 0, h->stream>>>(sp.Q, sp.hot_shards, sp.hot_items, sp.hot_meta, sp.n_hot, h->ld);
         ++h->launches;
         CK(cudaGetLastError());
     }
@@ -516,15 +589,6 @@ static int sgd_epoch(yue_t* h, double lr, double regU, double regI, uint64_t see
     sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
     sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot;
-    if (h->n_hot > 0) {
-        const size_t need = (size_t)(kHotShards - 1) * h->n_hot * h->ld;
-        if (h->hot_shards.n < need || !h->shards_clean) {
-            CK(h->hot_shards.resize(need));
-            CK(cudaMemsetAsync(h->hot_shards.p, 0, need * sizeof(float), h->stream));
-            h->shards_clean = true;
-        }
-        sp.hot_shards = h->hot_shards.p;
-    }
     sp.resync_events = h->resync_events;
     sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base; sp.slot = slot;
     sp.eps = (float)eps; sp.regA = (float)regA;
