@@ -12,7 +12,7 @@ SRC = os.path.join(HERE, "csrc", "yue_b200.cu")
 HEADER = os.path.join(ROOT, "include", "yue_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
 def build(force=False, verbose=False):

@@ -52,15 +52,26 @@ __host__ __device__ __forceinline__ size_t q_ilv_float_offset(int64_t row, int c
 }
 constexpr int32_t kSegShared = 1 << 30;   // the segment's user is worked on by more than one warp
 
+// One record per segment (<= 32 consecutive events of one user), 32 bytes, read by the whole warp with
+// two broadcast 128-bit loads: everything the segment's prologue needs, so that a record fetched one
+// segment ahead lets the warp PREFETCH the next segment's positives, play row and P[u] while it works.
+struct __align__(16) SegRec {
+    int32_t user;
+    int32_t len_flags;               // 1..32 events, | kSegShared when several warps work on the user
+    int64_t begin;                   // first local event
+    int64_t row_begin;               // the user's sorted-unique play row: uq_items[row_begin, +row_len)
+    int32_t row_len;
+    int32_t pad;
+};
+static_assert(sizeof(SegRec) == 32, "SegRec must be 32 bytes");
+
 struct SgdParams {
     float* P;                      // [m_local, ld]
     float* Q;                      // [n, ld], or the interleaved working copy when the kernel is ILV
     int ld;                        // row stride in floats, multiple of 4
     int nchunks;                   // ld / 4
     uint32_t n_items;
-    const int64_t* seg_begin;      // [nseg] first local event of the segment
-    const int32_t* seg_user;       // [nseg] local user
-    const int32_t* seg_len;        // [nseg] 1..32, | kSegShared when the user spans several items
+    const SegRec* seg_rec;         // [nseg] one 32-byte record per segment
     const int64_t* item_ptr;       // [2*n_work] segment range [begin, end) of each work item, in hand-out order
     int64_t n_work;
     unsigned long long* cursor;    // next item to hand out (zeroed before the launch)
@@ -95,6 +106,7 @@ struct SgdParams {
     float* hotQ;
     const int32_t* hot_sorted;     // [n_hot] hot track ids ascending, and the slot of each
     const int32_t* hot_sorted_slot;
+    int resync_mask;               // resync when (block & resync_mask) == 0: resync_events / 4 - 1, a power of two - 1
 };
 
 __device__ __forceinline__ float4 ld_row(const float* p) {
@@ -202,9 +214,9 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
     const int64_t next_item = take_item();          // fetched early: its latency hides behind the item
     const int64_t sb = p.item_ptr[2 * item], se = p.item_ptr[2 * item + 1];
     for (int64_t seg = sb; seg < se; ++seg) {
-        const int u = p.seg_user[seg];
-        const int64_t begin = p.seg_begin[seg];
-        const int32_t raw_len = p.seg_len[seg];
+        const int u = p.seg_rec[seg].user;
+        const int64_t begin = p.seg_rec[seg].begin;
+        const int32_t raw_len = p.seg_rec[seg].len_flags;
         const int len = raw_len & 63;
         // A user shared between warps is re-read at every segment: otherwise each warp would run
         // thousands of updates on a private copy and the summed deltas overshoot (Hogwild with

@@ -97,8 +97,11 @@ __device__ __forceinline__ float bpr_grad(float x, float lr, float& loss) {
 template <int V>
 struct BlkRows {
     float qi[kBlkK][V], qj[kBlkK][V];
-    int ri[kBlkK], rj[kBlkK];        // positive / negative track of each triplet; hot: -slot-1
+    float* pi[kBlkK];                // this lane's part of the positive / negative row of each triplet
+    float* pj[kBlkK];                // (in Q, or in the hot-row table)
 };
+
+
 
 // ---- hot-row table ---------------------------------------------------------------------------
 // Measured on B200 (tools/red_probe*.cu, profiles/red_probe_r1.md): an L2 slice serves about one
@@ -143,6 +146,14 @@ __global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restric
             Q[(size_t)hot_items[s] * ld + V * lane + v] = hotQ[hot_slot_offset(s) + hot_lane_offset<V>(lane) + v];
 }
 
+// Control flow.  A warp's work is a stream of segments (items from the global cursor, segments of an
+// item consecutive).  Per segment there is ONE loop over its blocks of 4 triplets; the pass over the
+// last block first prepares the NEXT segment -- draws its 32 negatives (K1) and issues the loads of its
+// first block -- so those loads fly while the last block is computed, and at the same point the
+// segment after that is prefetched (record, positives, play row, P[u]).  An item starts with a
+// virtual empty segment, so all of this exists once in the code (the first version, with the block
+// loop unrolled by two and the prologue inlined three times, was 12 K instructions and spent 57 % of
+// its stall samples waiting for the instruction cache).
 template <int V>
 __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdParams p) {
     extern __shared__ __align__(16) int hot_sm[];           // [n_hot] hot track ids, ascending; [n_hot] their slots
@@ -155,20 +166,23 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (warp >= p.n_warps) return;
     const int lane_off = V * lane;
-    const size_t lane_hot = hot_lane_offset<V>(lane);
     const float cu1 = 1.f - p.c_u;
+    // per-lane base addresses; a row is then base + (32-bit byte offset), see q_ptr
+    char* const q_lane = reinterpret_cast<char*>(p.Q + lane_off);
+    char* const hot_lane = reinterpret_cast<char*>(p.hotQ + hot_lane_offset<V>(lane));
+    const uint32_t row_bytes = (uint32_t)p.ld * 4u;          // n * ld * 4 < 4 GB is checked by the host
 
-    float pu[V], pu0[V];
+    float pu[V], pu0[V], pun[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) pu[v] = pu0[v] = 0.f;
+    for (int v = 0; v < V; ++v) pu[v] = pu0[v] = pun[v] = 0.f;
     int cur_u = -1;
-    const int32_t* row = nullptr;
-    int row_len = 0;
     double loss = 0.0;
 
     // address of this lane's part of track row `t` (t < 0: hot slot -t-1)
     auto q_ptr = [&](int32_t t) -> float* {
-        return t < 0 ? p.hotQ + hot_slot_offset(-t - 1) + lane_hot : p.Q + (size_t)t * p.ld + lane_off;
+        const int s = -t - 1;
+        const uint32_t off = t < 0 ? (uint32_t)(((s >> 1) << 2) | (s & 1)) * 256u : (uint32_t)t * row_bytes;
+        return reinterpret_cast<float*>((t < 0 ? hot_lane : q_lane) + off);
     };
     auto flush_user = [&]() {
         if (cur_u < 0) return;
@@ -189,130 +203,168 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
         if (lane == 0) it = atomicAdd(p.cursor, 1ull);
         return (int64_t)__shfl_sync(full, it, 0);
     };
+    auto load_rec = [&](int64_t seg, int4& a, int4& b) {
+        const int4* r = reinterpret_cast<const int4*>(p.seg_rec + seg);
+        a = __ldg(r); b = __ldg(r + 1);
+    };
+    auto rec_begin = [](const int4& a) { return (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z); };
+    auto rec_row = [](const int4& b) { return (int64_t)(((uint64_t)(uint32_t)b.y << 32) | (uint32_t)b.x); };
+    // pull what the prologue of a segment will read into L1/L2 (no register results, nothing to wait for)
+    auto prefetch_seg = [&](const int4& a, const int4& b) {
+        const int64_t begin = rec_begin(a);
+        if (lane == 0) {
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(p.ev_items + begin));
+            if (p.ev_neg) asm volatile("prefetch.global.L1 [%0];" :: "l"(p.ev_neg + begin));
+        }
+        if (lane == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(p.ev_items + begin + ((a.y & 63) - 1)));
+        if (8 * lane < b.z) asm volatile("prefetch.global.L1 [%0];" :: "l"(p.uq_items + rec_row(b) + 8 * lane));
+        if (lane < (int)(row_bytes / 32u)) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.P + (size_t)a.x * p.ld + 8 * lane));
+    };
 
     int64_t item = take_item();
     while (item < p.n_work) {
-        const int64_t next_item = take_item();      // fetched early: its latency hides behind the item
+        const int64_t next_item = take_item();
         const int64_t sb = p.item_ptr[2 * item], se = p.item_ptr[2 * item + 1];
+        // record queue: (na, nb) = segment seg+1, (fa, fb) = segment seg+2
+        int4 na, nb, fa = make_int4(0, 0, 0, 0), fb = fa;
+        load_rec(sb, na, nb);
+        if (sb + 1 < se) load_rec(sb + 1, fa, fb);
+        // current segment: starts as a virtual empty one in front of segment sb
+        int u = cur_u, len = 0;
+        bool resync = false;
+        int32_t my_i = 0, my_j = 0;
+        BlkRows<V> cur, nxt;
+#pragma unroll
+        for (int a = 0; a < kBlkK; ++a) {
+            cur.pi[a] = cur.pj[a] = nullptr;
+#pragma unroll
+            for (int v = 0; v < V; ++v) cur.qi[a][v] = cur.qj[a][v] = 0.f;
+        }
+        for (int64_t seg = sb - 1; seg < se; ++seg) {
+            const int nblk = (len + kBlkK - 1) / kBlkK;
+            const bool has_next = seg + 1 < se;
+            int32_t n_i = 0, n_j = 0;
+            int n_u = 0, n_len = 0;
+            bool n_resync = false;
 #pragma unroll 1
-        for (int64_t seg = sb; seg < se; ++seg) {
-            const int u = p.seg_user[seg];
-            const int64_t begin = p.seg_begin[seg];
-            const int32_t raw_len = p.seg_len[seg];
-            const int len = raw_len & 63;
-            const bool resync = (raw_len & kSegShared) != 0;    // user shared between warps
-            if (u != cur_u || resync) {
-                if (u != cur_u) {
-                    const int64_t r0 = p.uq_indptr[u];
-                    row = p.uq_items + r0;
-                    row_len = (int)(p.uq_indptr[u + 1] - r0);
-                }
-                sync_user(u);
-            }
-            // ---- K1: lane t draws the negative of event begin+t ---------------------------
-            int32_t my_i = 0, my_j = 0;
-            if (lane < len) {
-                const int64_t e = begin + lane;
-                my_i = p.ev_items[e];                // hot positives arrive re-labelled -slot-1
-                my_j = p.ev_neg ? p.ev_neg[e]
-                                : sample_negative(p.seed, p.epoch, (uint64_t)(p.event_base + e), p.slot,
-                                                  p.n_items, row, row_len);
-                if (p.n_hot > 0) {                   // a negative that happens to be a hot track lives in the table too
-                    int lo = 0, hi = p.n_hot;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (hot_sorted[mid] < my_j) lo = mid + 1; else hi = mid; }
-                    if (lo < p.n_hot && hot_sorted[lo] == my_j) my_j = -hot_sorted_slot[lo] - 1;
-                }
-            }
-            __syncwarp();
-
-            // ---- K2 in blocks of 4 triplets, the next block's rows in flight --------------
-            auto load_block = [&](BlkRows<V>& B, int b) {
-#pragma unroll
-                for (int a = 0; a < kBlkK; ++a) {
-                    const int t = kBlkK * b + a;                    // <= 31
-                    const int32_t it = __shfl_sync(full, my_i, t), jt = __shfl_sync(full, my_j, t);
-                    B.ri[a] = it; B.rj[a] = jt;
-                    if (t < len) {
-                        ldv<V>(q_ptr(it), B.qi[a]);
-                        ldv<V>(q_ptr(jt), B.qj[a]);
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < V; ++v) B.qi[a][v] = B.qj[a][v] = 0.f;
-                    }
-                }
-            };
-            auto compute_block = [&](const BlkRows<V>& B, int b) {
-                const int nb = len - kBlkK * b;                     // >= 1 triplets in this block
-                if (resync && b > 0 && (kBlkK * b) % p.resync_events < kBlkK) sync_user(u);
-                float d[kBlkK][V];
-                float x[10];
-#pragma unroll
-                for (int a = 0; a < kBlkK; ++a) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        d[a][v] = B.qi[a][v] - B.qj[a][v];          // Q[i] - Q[j], old rows (BPR.py:51)
-                        s = fmaf(pu[v], d[a][v], s);
-                    }
-                    x[a] = s;
-                }
-                {
-                    int g = 4;
-#pragma unroll
-                    for (int a = 0; a < kBlkK; ++a)
-#pragma unroll
-                        for (int c = a + 1; c < kBlkK; ++c) {
-                            float s = 0.f;
-#pragma unroll
-                            for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
-                            x[g++] = s;                              // order: 01 02 03 12 13 23
+            for (int b = 0; b == 0 || b < nblk; ++b) {
+                const bool last = b + 1 >= nblk;
+                if (last && has_next) {
+                    // ---- prepare segment seg+1 (record na/nb arrived; its data was prefetched) ----
+                    n_u = na.x; n_len = na.y & 63; n_resync = (na.y & kSegShared) != 0;
+                    if (lane < n_len) {
+                        const int64_t e = rec_begin(na) + lane;
+                        n_i = p.ev_items[e];             // hot positives arrive re-labelled -slot-1
+                        n_j = p.ev_neg ? p.ev_neg[e]    // K1: lane t draws the negative of event begin+t
+                                       : sample_negative(p.seed, p.epoch, (uint64_t)(p.event_base + e), p.slot,
+                                                         p.n_items, p.uq_items + rec_row(nb), nb.z);
+                        if (p.n_hot > 0) {               // a negative that happens to be a hot track lives in the table too
+                            int lo = 0, hi = p.n_hot;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (hot_sorted[mid] < n_j) lo = mid + 1; else hi = mid; }
+                            if (lo < p.n_hot && hot_sorted[lo] == n_j) n_j = -hot_sorted_slot[lo] - 1;
                         }
+                    }
+                    __syncwarp();
+                    if (n_u != cur_u) ldv<V>(p.P + (size_t)n_u * p.ld + lane_off, pun);
+                    // the segment after: its record arrived a segment ago -> prefetch its data, fetch the next record
+                    if (seg + 2 < se) prefetch_seg(fa, fb);
+                    na = fa; nb = fb;
+                    if (seg + 3 < se) load_rec(seg + 3, fa, fb);
                 }
-                warp_allreduce10(x, lane);
-                // scalar recurrence: w_c = P_a . d_c for the current a
-                float g[kBlkK];
-                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                g[0] = bpr_grad(x[0], p.lr, l0);
-                float w1 = cu1 * fmaf(g[0], x[4], x[1]);
-                float w2 = cu1 * fmaf(g[0], x[5], x[2]);
-                float w3 = cu1 * fmaf(g[0], x[6], x[3]);
-                g[1] = bpr_grad(w1, p.lr, l1);
-                w2 = cu1 * fmaf(g[1], x[7], w2);
-                w3 = cu1 * fmaf(g[1], x[8], w3);
-                g[2] = bpr_grad(w2, p.lr, l2);
-                w3 = cu1 * fmaf(g[2], x[9], w3);
-                g[3] = bpr_grad(w3, p.lr, l3);
-                loss += (double)(l0 + (nb > 1 ? l1 : 0.f) + (nb > 2 ? l2 : 0.f) + (nb > 3 ? l3 : 0.f));
-                // row updates in the reference's order (BPR.py:51-57): P first, Q with the updated P,
-                // then the three multiplicative shrinks; Q changes leave as deltas (vector atomics)
+                // ---- loads of the next block: block b+1 of this segment, or block 0 of the next one ----
+                if (!last || has_next) {
+                    const int32_t src_i = last ? n_i : my_i, src_j = last ? n_j : my_j;
+                    const int src_len = last ? n_len : len, t0 = last ? 0 : kBlkK * (b + 1);
 #pragma unroll
-                for (int a = 0; a < kBlkK; ++a) {
-                    if (a < nb) {
-                        const float ga = g[a];
-                        float di[V], dj[V];
+                    for (int a = 0; a < kBlkK; ++a) {
+                        const int t = t0 + a;                               // <= 31
+                        const int32_t it = __shfl_sync(full, src_i, t), jt = __shfl_sync(full, src_j, t);
+                        if (t < src_len) {
+                            nxt.pi[a] = q_ptr(it); nxt.pj[a] = q_ptr(jt);
+                            ldv<V>(nxt.pi[a], nxt.qi[a]);
+                            ldv<V>(nxt.pj[a], nxt.qj[a]);
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) nxt.qi[a][v] = nxt.qj[a][v] = 0.f;
+                        }
+                    }
+                }
+                if (b < nblk) {
+                    // ---- K2: block b of the current segment ----------------------------------------
+                    const int nbk = len - kBlkK * b;                        // >= 1 triplets in this block
+                    if (resync && b > 0 && (b & p.resync_mask) == 0) sync_user(u);
+                    float d[kBlkK][V];
+                    float x[10];
+#pragma unroll
+                    for (int a = 0; a < kBlkK; ++a) {
+                        float s = 0.f;
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
-                            const float pn = fmaf(ga, d[a][v], pu[v]);
-                            const float gp = ga * pn;
-                            di[v] = fmaf(-p.c_i, B.qi[a][v] + gp, gp);      // (q + g p)(1 - c) - q
-                            dj[v] = fmaf(-p.c_i, B.qj[a][v] - gp, -gp);
-                            pu[v] = fmaf(-p.c_u, pn, pn);
+                            d[a][v] = cur.qi[a][v] - cur.qj[a][v];          // Q[i] - Q[j], old rows (BPR.py:51)
+                            s = fmaf(pu[v], d[a][v], s);
                         }
-                        redv<V>(q_ptr(B.ri[a]), di);
-                        redv<V>(q_ptr(B.rj[a]), dj);
+                        x[a] = s;
+                    }
+                    {
+                        int g = 4;
+#pragma unroll
+                        for (int a = 0; a < kBlkK; ++a)
+#pragma unroll
+                            for (int c = a + 1; c < kBlkK; ++c) {
+                                float s = 0.f;
+#pragma unroll
+                                for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
+                                x[g++] = s;                                  // order: 01 02 03 12 13 23
+                            }
+                    }
+                    warp_allreduce10(x, lane);
+                    // scalar recurrence: w_c = P_a . d_c for the current a
+                    float g[kBlkK];
+                    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                    g[0] = bpr_grad(x[0], p.lr, l0);
+                    float w1 = cu1 * fmaf(g[0], x[4], x[1]);
+                    float w2 = cu1 * fmaf(g[0], x[5], x[2]);
+                    float w3 = cu1 * fmaf(g[0], x[6], x[3]);
+                    g[1] = bpr_grad(w1, p.lr, l1);
+                    w2 = cu1 * fmaf(g[1], x[7], w2);
+                    w3 = cu1 * fmaf(g[1], x[8], w3);
+                    g[2] = bpr_grad(w2, p.lr, l2);
+                    w3 = cu1 * fmaf(g[2], x[9], w3);
+                    g[3] = bpr_grad(w3, p.lr, l3);
+                    loss += (double)(l0 + (nbk > 1 ? l1 : 0.f) + (nbk > 2 ? l2 : 0.f) + (nbk > 3 ? l3 : 0.f));
+                    // row updates in the reference's order (BPR.py:51-57): P first, Q with the updated P,
+                    // then the three multiplicative shrinks; Q changes leave as deltas (vector atomics)
+#pragma unroll
+                    for (int a = 0; a < kBlkK; ++a) {
+                        if (a < nbk) {
+                            const float ga = g[a];
+                            float di[V], dj[V];
+#pragma unroll
+                            for (int v = 0; v < V; ++v) {
+                                const float pn = fmaf(ga, d[a][v], pu[v]);
+                                const float gp = ga * pn;
+                                di[v] = fmaf(-p.c_i, cur.qi[a][v] + gp, gp);    // (q + g p)(1 - c) - q
+                                dj[v] = fmaf(-p.c_i, cur.qj[a][v] - gp, -gp);
+                                pu[v] = fmaf(-p.c_u, pn, pn);
+                            }
+                            redv<V>(cur.pi[a], di);
+                            redv<V>(cur.pj[a], dj);
+                        }
                     }
                 }
-            };
-
-            const int nblk = (len + kBlkK - 1) / kBlkK;
-            BlkRows<V> cur, nxt;
-            load_block(cur, 0);
-#pragma unroll 1
-            for (int b = 0; b < nblk; ++b) {
-                if (b + 1 < nblk) load_block(nxt, b + 1);
-                compute_block(cur, b);
                 cur = nxt;
             }
+            if (!has_next) break;
+            // ---- switch to segment seg+1: its first block is already in flight ------------------
+            if (n_u != cur_u) {
+                flush_user();
+                cur_u = n_u;
+#pragma unroll
+                for (int v = 0; v < V; ++v) pu[v] = pu0[v] = pun[v];
+            } else if (n_resync) {
+                sync_user(n_u);       // a user shared between warps is re-read at every segment
+            }
+            u = n_u; len = n_len; resync = n_resync; my_i = n_i; my_j = n_j;
         }
         item = next_item;
     }

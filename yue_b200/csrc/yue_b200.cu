@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bpr_sgd.cuh"
@@ -68,6 +69,21 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// pinned host staging that lives as long as the handle: no page faults and full-speed DMA on reuse
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= cap && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = count; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 }  // namespace
 
 struct yue_handle {
@@ -95,7 +111,7 @@ struct yue_handle {
     // the chain of dependent atomics on one address stays below ~T/hot_div updates (~11 ns each).
     int hot_max = kHotSlots;
     int hot_min_count = 16384;
-    int hot_div = 128;
+    int hot_div = 32;
     int n_hot = 0;
     std::vector<int32_t> h_hot_counts;   // per hot slot
     int hot_meta_cap = 0, hot_meta_ld = 0;   // what the current hot_meta / hot_shards were built for
@@ -119,10 +135,13 @@ struct yue_handle {
     // segments of the epoch kernels
     int64_t nseg = 0;
     int n_warps = 0;
-    DevBuf<int64_t> seg_begin, item_ptr;
+    DevBuf<int64_t> item_ptr;
     int64_t n_items = 0;
     DevBuf<unsigned long long> cursor;
-    DevBuf<int32_t> seg_user, seg_len;
+    DevBuf<SegRec> seg_rec, tmp_rec;
+    PinBuf<SegRec> pin_rec;          // host staging of the segment records
+    std::vector<int64_t> h_uq_indptr;
+    int item_group_segs = 8;         // light users per work item: consecutive users until this many segments (YUE_SGD_GROUP_SEGS)
 
     // factors
     int k = 0, ld = 0;
@@ -135,8 +154,8 @@ struct yue_handle {
     DevBuf<double> scal;          // [0] loss, [1] |P|^2, [2] |Q|^2
 
     // scratch
-    DevBuf<int32_t> tmp_i, tmp_j, tmp_su, tmp_sl, rk_users, rk_ids;
-    DevBuf<int64_t> tmp_sb, tmp_ws;
+    DevBuf<int32_t> tmp_i, tmp_j, rk_users, rk_ids;
+    DevBuf<int64_t> tmp_ws;
     DevBuf<float> rk_scores, pred;
     DevBuf<unsigned char> l2buf;
     RankTcState tc;
@@ -163,41 +182,85 @@ static int fail(yue_t* h, int code, const std::string& msg) { h->err = msg; retu
 static int q_rowmajor(yue_t* h);
 static int q_interleaved(yue_t* h);
 
-// Cut every user's event range into <=32-event segments and group them into work items, returned
-// as [begin, end) segment ranges in STREAM ORDER (the order the kernel's cursor hands them out and
-// the order the reference visits users in, recommender/cf/BPR.py:42):
-//   * a user with <= item_segs segments is one item;
-//   * a heavy user is cut into items of item_segs segments (a quarter of a warp's fair share of the
-//     epoch), all at the user's stream position; its segments are flagged kSegShared and the warps
-//     working on it publish and re-read P[u] every few events (resync_events).
+// Cut every user's event range into <=32-event segments (one SegRec each) and group them into work
+// items, returned as [begin, end) segment ranges in STREAM ORDER (the order the kernel's cursor hands
+// them out and the order the reference visits users in, recommender/cf/BPR.py:42):
+//   * consecutive light users share an item until it holds group_segs segments: the cursor atomic,
+//     the item lookup and the cold start of the kernel's prefetch pipeline are paid once per item;
+//   * a heavy user (more than item_segs segments) is cut into items of item_segs segments (a quarter
+//     of a warp's fair share of the epoch), all at the user's stream position; its segments are flagged
+//     kSegShared and the warps working on it publish and re-read P[u] every few events.
 // What the measurements at config C2 say (tools/quality_study.py, profiles/quality_study_r1.md):
 // a heavy user has to FINISH EARLY, like in the serial order -- big items make it a straggler, every
 // light user's P[u] is then stale against the large Q changes it keeps making and Recall@10 drops
 // from 0.098 to 0.005; spreading its items over the epoch does the same (0.17 -> 0.04 at 5 M events).
 // So ~100 warps must share the heaviest user, and the staleness of P[u] is bounded by resync_events.
-static void build_items_from_runs(const std::vector<int64_t>& run_begin, const std::vector<int64_t>& run_end,
-                                  const std::vector<int32_t>& run_user, bool allow_shared, int64_t item_segs,
-                                  int64_t max_items, int seg_events,
-                                  std::vector<int64_t>& sb, std::vector<int32_t>& su, std::vector<int32_t>& sl,
-                                  std::vector<int64_t>& item_rng) {
-    sb.clear(); su.clear(); sl.clear(); item_rng.clear();
-    for (size_t r = 0; r < run_begin.size(); ++r) {
-        const int64_t first = (int64_t)sb.size();
-        for (int64_t b = run_begin[r], e = run_end[r]; b < e; b += seg_events) {
-            sb.push_back(b); su.push_back(run_user[r]); sl.push_back((int32_t)std::min<int64_t>(seg_events, e - b));
-        }
-        const int64_t nsegs = (int64_t)sb.size() - first;
+// A run r is the event range [begin(r), end(r)) of user(r); runs are independent, so the host cores
+// split them (an item never spans two threads' shares).
+struct ItemPlanArgs {
+    bool allow_shared; int64_t item_segs, max_items, group_segs; int seg_events; const int64_t* uq_indptr;
+};
+template <class RunFn>
+static int64_t count_run_segments(size_t r0, size_t r1, RunFn run, int seg_events) {
+    int64_t n = 0;
+    for (size_t r = r0; r < r1; ++r) { int64_t b, e; int32_t u; run(r, b, e, u); n += (e - b + seg_events - 1) / seg_events; }
+    return n;
+}
+template <class RunFn>
+static void plan_runs(size_t r0, size_t r1, RunFn run, const ItemPlanArgs& a, SegRec* rec, int64_t seg0,
+                      std::vector<int64_t>& item_rng) {
+    int64_t s = seg0, open_first = -1;
+    auto close_open = [&]() { if (open_first >= 0) { item_rng.push_back(open_first); item_rng.push_back(s); open_first = -1; } };
+    for (size_t r = r0; r < r1; ++r) {
+        int64_t b, e; int32_t u;
+        run(r, b, e, u);
+        const int64_t nsegs = (e - b + a.seg_events - 1) / a.seg_events;
         if (nsegs == 0) continue;
-        if (nsegs > item_segs && allow_shared) {
-            const int64_t per = std::max(item_segs, (nsegs + max_items - 1) / max_items);
-            for (int64_t s = first; s < first + nsegs; ++s) sl[s] |= kSegShared;
-            for (int64_t s = first; s < first + nsegs; s += per) {
-                item_rng.push_back(s); item_rng.push_back(std::min(first + nsegs, s + per));
-            }
+        const bool heavy = nsegs > a.item_segs && a.allow_shared;
+        if (heavy) close_open();
+        const int64_t first = s, row0 = a.uq_indptr[u];
+        const int32_t row_len = (int32_t)(a.uq_indptr[u + 1] - row0), flag = heavy ? kSegShared : 0;
+        for (; b < e; b += a.seg_events, ++s) {
+            SegRec& x = rec[s];
+            x.user = u; x.len_flags = (int32_t)std::min<int64_t>(a.seg_events, e - b) | flag; x.begin = b;
+            x.row_begin = row0; x.row_len = row_len; x.pad = 0;
+        }
+        if (heavy) {
+            const int64_t per = std::max(a.item_segs, (nsegs + a.max_items - 1) / a.max_items);
+            for (int64_t i = first; i < s; i += per) { item_rng.push_back(i); item_rng.push_back(std::min(s, i + per)); }
         } else {
-            item_rng.push_back(first); item_rng.push_back(first + nsegs);
+            if (open_first < 0) open_first = first;
+            if (s - open_first >= a.group_segs) close_open();
         }
     }
+    close_open();
+}
+// returns the number of segments; rec_buf is (re)allocated to hold them
+template <class RunFn>
+static cudaError_t plan_items(size_t nruns, RunFn run, const ItemPlanArgs& a, PinBuf<SegRec>& rec_buf, int64_t& nseg,
+                              std::vector<int64_t>& item_rng) {
+    const size_t nthreads = nruns < 65536 ? 1 : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<int64_t> seg_count(nthreads), seg_first(nthreads + 1, 0);
+    std::vector<std::vector<int64_t>> items(nthreads);
+    auto share = [&](size_t t) { return nruns * t / nthreads; };
+    auto parallel = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nthreads; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto& x : th) x.join();
+    };
+    parallel([&](size_t t) { seg_count[t] = count_run_segments(share(t), share(t + 1), run, a.seg_events); });
+    for (size_t t = 0; t < nthreads; ++t) seg_first[t + 1] = seg_first[t] + seg_count[t];
+    nseg = seg_first[nthreads];
+    cudaError_t e = rec_buf.ensure((size_t)nseg);
+    if (e != cudaSuccess) return e;
+    parallel([&](size_t t) {
+        items[t].reserve(2 * (size_t)(seg_count[t] / std::max<int64_t>(a.group_segs, 1) + 64));
+        plan_runs(share(t), share(t + 1), run, a, rec_buf.p, seg_first[t], items[t]);
+    });
+    item_rng.clear();
+    for (auto& v : items) item_rng.insert(item_rng.end(), v.begin(), v.end());
+    return cudaSuccess;
 }
 
 // Every yue_* function below is declared extern "C" by include/yue_b200.h and inherits that linkage.
@@ -238,6 +301,7 @@ int yue_create(int device, yue_t** out) {
     if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(kHotSlots, atoi(s)));
     if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_HOT_DIV")) h->hot_div = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_GROUP_SEGS")) h->item_group_segs = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_KERNEL")) h->sgd_kernel = atoi(s) == 1 ? 1 : 2;
     if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
     if (const char* s = getenv("YUE_SGD_MAX_ITEMS")) h->max_items_per_user = std::max(1, atoi(s));
@@ -256,10 +320,10 @@ int yue_destroy(yue_t* h) {
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     rank_tc_release(h->tc);
-    for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->seg_begin, &h->item_ptr, &h->tmp_sb, &h->tmp_ws}) b->release();
+    for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->item_ptr, &h->tmp_ws}) b->release();
+    h->seg_rec.release(); h->tmp_rec.release(); h->pin_rec.release();
     h->cursor.release();
-    for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->seg_user, &h->seg_len, &h->tmp_i, &h->tmp_j,
-                    &h->tmp_su, &h->tmp_sl, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot}) b->release();
+    for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->tmp_i, &h->tmp_j, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot}) b->release();
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
     h->l2buf.release();
@@ -305,27 +369,22 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     if (T) CK(cudaMemcpyAsync(h->ev_items.p, ev_items, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     if (nnz) CK(cudaMemcpyAsync(h->uq_items.p, uq_items, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     h->h_ev_indptr.assign(ev_indptr, ev_indptr + m_local + 1);
+    h->h_uq_indptr.assign(uq_indptr, uq_indptr + m_local + 1);
     h->have_ev_user = false;
 
-    std::vector<int64_t> sb, ip, rb((size_t)m_local), re((size_t)m_local);
-    std::vector<int32_t> su, sl, ru((size_t)m_local);
-    for (int64_t u = 0; u < m_local; ++u) { rb[u] = ev_indptr[u]; re[u] = ev_indptr[u + 1]; ru[u] = (int32_t)u; }
     // concurrency: at most one resident wave, fewer warps on small logs (bounds Hogwild staleness
     // and keeps the in-flight window a small fraction of the users)
     h->n_warps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
     // a heavy user's item is at most a quarter of a warp's fair share, so no item is a straggler
     int64_t item_segs = std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)h->n_warps * 4 * 32)));
     if (h->item_segs_env > 0) item_segs = h->item_segs_env;
-    build_items_from_runs(rb, re, ru, true, item_segs, h->max_items_per_user, h->seg_events, sb, su, sl, ip);
-    h->nseg = (int64_t)sb.size();
+    std::vector<int64_t> ip;
+    const ItemPlanArgs plan{true, item_segs, h->max_items_per_user, h->item_group_segs, h->seg_events, uq_indptr};
+    CK(plan_items((size_t)m_local, [=](size_t r, int64_t& b, int64_t& e, int32_t& u) { b = ev_indptr[r]; e = ev_indptr[r + 1]; u = (int32_t)r; },
+                  plan, h->pin_rec, h->nseg, ip));
     h->n_items = (int64_t)ip.size() / 2;
-    CK(h->seg_begin.resize(h->nseg)); CK(h->seg_user.resize(h->nseg)); CK(h->seg_len.resize(h->nseg));
-    CK(h->item_ptr.resize(ip.size())); CK(h->cursor.resize(1));
-    if (h->nseg) {
-        CK(cudaMemcpyAsync(h->seg_begin.p, sb.data(), sb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->seg_user.p, su.data(), su.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->seg_len.p, sl.data(), sl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    }
+    CK(h->seg_rec.resize(h->nseg)); CK(h->item_ptr.resize(ip.size())); CK(h->cursor.resize(1));
+    if (h->nseg) CK(cudaMemcpyAsync(h->seg_rec.p, h->pin_rec.p, h->nseg * sizeof(SegRec), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->item_ptr.p, ip.data(), ip.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     // hot tracks: device histogram of the positives, top hot_max by count on the host, then the hot
     // positives of the device copy of ev_items are re-labelled -slot-1 (see SgdParams::hot_items)
@@ -493,7 +552,8 @@ static cudaError_t launch_sgd_blk(const SgdParams& sp, int warps_per_cta, cudaSt
 
 // does the blocked kernel (bpr_sgd_blk.cuh) take this launch?
 static bool use_blk_kernel(const yue_t* h, int mode, bool apr) {
-    return h->sgd_kernel == 2 && mode == YUE_MODE_HOGWILD && !apr && (h->ld == 32 || h->ld == 64 || h->ld == 128);
+    return h->sgd_kernel == 2 && mode == YUE_MODE_HOGWILD && !apr && (h->ld == 32 || h->ld == 64 || h->ld == 128) &&
+           (uint64_t)h->n * h->ld * 4 < ((uint64_t)1 << 32);      // 32-bit byte offsets inside Q
 }
 
 // (re)build the shard table of the hot tracks for the kernel about to run
@@ -523,6 +583,7 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr 
     CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
     sp.cursor = h->cursor.p;
     const bool blk = use_blk_kernel(h, mode, apr);
+    { int rb = 1; while (rb * 2 * kBlkK <= sp.resync_events) rb *= 2; sp.resync_mask = rb - 1; }
     const bool ilv = h->use_ilv && h->ld == 64 && mode != YUE_MODE_SERIAL && !apr && !blk;
     if (ilv) { if (int rc = q_interleaved(h)) return rc; } else { if (int rc = q_rowmajor(h)) return rc; }
     sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
@@ -584,7 +645,7 @@ static int sgd_epoch(yue_t* h, double lr, double regU, double regI, uint64_t see
     if (h->T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     SgdParams sp{};
     fill_rates(sp, lr, regU, regI);
-    sp.seg_begin = h->seg_begin.p; sp.seg_user = h->seg_user.p; sp.seg_len = h->seg_len.p;
+    sp.seg_rec = h->seg_rec.p;
     sp.item_ptr = h->item_ptr.p; sp.n_work = h->n_items;
     sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
@@ -609,8 +670,8 @@ static int sgd_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t
     REQUIRE(T >= 0 && (T == 0 || (u && i && j)), YUE_E_ARG, "null triplet array");
     CK(cudaSetDevice(h->device));
     if (T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
-    std::vector<int64_t> sb, ip, rb, re;
-    std::vector<int32_t> su, sl, ru;
+    std::vector<int64_t> ip, rb, re;
+    std::vector<int32_t> ru;
     for (int64_t t = 0; t < T;) {               // runs of one user
         REQUIRE(u[t] >= 0 && u[t] < h->m, YUE_E_ARG, "triplet user out of range");
         int64_t e = t;
@@ -623,21 +684,24 @@ static int sgd_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t
     }
     const int n_warps = mode == YUE_MODE_SERIAL ? 1
         : (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
-    build_items_from_runs(rb, re, ru, mode != YUE_MODE_SERIAL,
-                          std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)n_warps * 4 * 32))),
-                          h->max_items_per_user, 32, sb, su, sl, ip);
+    const ItemPlanArgs plan{mode != YUE_MODE_SERIAL, std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)n_warps * 4 * 32))),
+                            h->max_items_per_user, mode == YUE_MODE_SERIAL ? 1 : h->item_group_segs, 32, h->h_uq_indptr.data()};
+    int64_t nseg = 0;
+    PinBuf<SegRec> recs;
+    cudaError_t pe = plan_items(rb.size(), [&](size_t r, int64_t& b, int64_t& e, int32_t& uu) { b = rb[r]; e = re[r]; uu = ru[r]; },
+                                plan, recs, nseg, ip);
+    if (pe != cudaSuccess) { recs.release(); return fail(h, YUE_E_CUDA, std::string("plan_items: ") + cudaGetErrorString(pe)); }
+    struct Guard { PinBuf<SegRec>& b; cudaStream_t st; ~Guard() { cudaStreamSynchronize(st); b.release(); } } guard{recs, h->stream};
+    CK(h->tmp_rec.resize((size_t)nseg));
+    CK(cudaMemcpyAsync(h->tmp_rec.p, recs.p, (size_t)nseg * sizeof(SegRec), cudaMemcpyHostToDevice, h->stream));
     CK(h->tmp_i.resize(T)); CK(h->tmp_j.resize(T));
-    CK(h->tmp_sb.resize(sb.size())); CK(h->tmp_su.resize(su.size())); CK(h->tmp_sl.resize(sl.size()));
     CK(h->tmp_ws.resize(ip.size())); CK(h->cursor.resize(1));
     CK(cudaMemcpyAsync(h->tmp_i.p, i, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tmp_j.p, j, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->tmp_sb.p, sb.data(), sb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->tmp_su.p, su.data(), su.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->tmp_sl.p, sl.data(), sl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tmp_ws.p, ip.data(), ip.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     SgdParams sp{};
     fill_rates(sp, lr, regU, regI);
-    sp.seg_begin = h->tmp_sb.p; sp.seg_user = h->tmp_su.p; sp.seg_len = h->tmp_sl.p;
+    sp.seg_rec = h->tmp_rec.p;
     sp.item_ptr = h->tmp_ws.p; sp.n_work = (int64_t)ip.size() / 2; sp.n_warps = n_warps;
     sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
     sp.n_hot = 0;                                // explicit triplets take the direct path

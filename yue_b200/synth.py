@@ -101,6 +101,25 @@ def mask_csr(m, n, mean_items, seed):
     return indptr, uq
 
 
+def mask_csr_torch(m, n, mean_items, seed, device=None):
+    """mask_csr with torch ops (GPU when present): config C4 at full size is 50 M (user, track) pairs."""
+    import torch
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    deg = torch.poisson(torch.full((m,), float(mean_items), device=device), generator=g).clamp_(min=1).to(torch.int64)
+    users = torch.repeat_interleave(torch.arange(m, device=device, dtype=torch.int64), deg)
+    items = torch.randint(0, n, (int(deg.sum().item()),), generator=g, device=device, dtype=torch.int64)
+    key = torch.unique(users * n + items)
+    del users, items
+    u = key // n
+    indptr = torch.zeros(m + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(u, minlength=m), 0)
+    uq = (key - u * n).to(torch.int32)
+    return indptr.cpu().numpy(), uq.cpu().numpy()
+
+
 def write_csv_log(path, n_users, n_tracks, plays, seed, n_artists=500):
     """Config C1 as text: ``time,user,track,artist`` lines in shuffled (time) order so ids
     assigned by first appearance are NOT the generator's ids, like a real log."""
