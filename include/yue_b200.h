@@ -153,6 +153,9 @@ int yue_allreduce_q_delta(yue_t* h);   /* pack + ncclAllReduce(sum, fp32) + appl
 int yue_timer_start(yue_t* h);
 int yue_timer_stop(yue_t* h, float* ms);
 int yue_launch_count(yue_t* h, int64_t* n);
+/* diagnostics of the last yue_rank_topn that took the tcgen05 path: rows whose candidate buffer
+ * spilled into the global pool, and rows that had to be redone by the exact kernel */
+int yue_rank_stats(yue_t* h, int64_t* fallback_rows, int64_t* spilled_rows);
 int yue_flush_l2(yue_t* h);            /* overwrite a >L2-sized scratch buffer              */
 
 #ifdef __cplusplus

@@ -84,6 +84,7 @@ SIGNATURES = {
     "yue_timer_start": (C.c_int, [_H]),
     "yue_timer_stop": (C.c_int, [_H, _f32p]),
     "yue_launch_count": (C.c_int, [_H, _i64p]),
+    "yue_rank_stats": (C.c_int, [_H, _i64p, _i64p]),
     "yue_flush_l2": (C.c_int, [_H]),
 }
 

@@ -61,7 +61,9 @@ struct __align__(16) SegRec {
     int64_t begin;                   // first local event
     int64_t row_begin;               // the user's sorted-unique play row: uq_items[row_begin, +row_len)
     int32_t row_len;
-    int32_t pad;
+    int32_t shared;                  // != 0 when several warps work on the user (same as the kSegShared bit; every
+                                     // word of the record is consumed: a dead word of an in-flight 128-bit load
+                                     // gets reused as a temporary by ptxas, and that write waits for the load)
 };
 static_assert(sizeof(SegRec) == 32, "SegRec must be 32 bytes");
 
@@ -106,6 +108,7 @@ struct SgdParams {
     float* hotQ;
     const int32_t* hot_sorted;     // [n_hot] hot track ids ascending, and the slot of each
     const int32_t* hot_sorted_slot;
+    const int32_t* hot_dx;         // [n_hot] byte distance from a slot's row to its second accumulator row, 0 = none
     int resync_mask;               // resync when (block & resync_mask) == 0: resync_events / 4 - 1, a power of two - 1
 };
 

@@ -99,6 +99,8 @@ struct BlkRows {
     float qi[kBlkK][V], qj[kBlkK][V];
     float* pi[kBlkK];                // this lane's part of the positive / negative row of each triplet
     float* pj[kBlkK];                // (in Q, or in the hot-row table)
+    float ex[kBlkK][V];              // second accumulator row of a sharded hot positive (valid when dx != 0)
+    int dx[kBlkK];                   // byte distance from pi to that row, 0 = the positive is not sharded
 };
 
 
@@ -116,10 +118,15 @@ struct BlkRows {
 // so a touch of the row costs each of 8 slices one load sector and one atomic sector: 2.2 ns per touch
 // of a single row, 0.9-1.2 ns per touch over a zipf mix of rows.  hot_gather/hot_scatter kernels copy
 // the rows in from Q before the launch and back after it.
-constexpr int kHotSlots = 32;
-constexpr int kHotPlaneFloats = (2 * kHotSlots + 1) * 64;     // 65 granules of 256 B (measured: tools/red_probe3.cu)
-__host__ __device__ __forceinline__ size_t hot_slot_offset(int slot) {      // floats
-    return (size_t)(((slot >> 1) << 2) | (slot & 1)) * 64;
+// The most played tracks of all additionally get a SECOND accumulator row in the table (the logical
+// row is the sum of both; a warp adds to row warp % 2, readers fetch both): one 32-byte address takes
+// a dependent load + atomic every ~2.2 ns, which for the top track of C2 is still 8.6 ms per epoch.
+constexpr int kHotSlots = 24;                                 // hot tracks
+constexpr int kHotExtra = 8;                                  // of which so many may have a second row
+constexpr int kHotRows = kHotSlots + kHotExtra;
+constexpr int kHotPlaneFloats = (2 * kHotRows + 1) * 64;      // 65 granules of 256 B (measured: tools/red_probe3.cu)
+__host__ __device__ __forceinline__ size_t hot_slot_offset(int row) {       // floats; row = slot, or n_hot + k for an extra row
+    return (size_t)(((row >> 1) << 2) | (row & 1)) * 64;
 }
 // float offset, inside a slot's row, of the V floats lane `lane` owns
 template <int V> __host__ __device__ __forceinline__ size_t hot_lane_offset(int lane) {
@@ -128,22 +135,28 @@ template <int V> __host__ __device__ __forceinline__ size_t hot_lane_offset(int 
 constexpr size_t kHotTableFloats = (size_t)16 * kHotPlaneFloats;           // up to 16 sectors (ld = 128)
 
 template <int V>
-__global__ void hot_gather_kernel(const float* __restrict__ Q, float* __restrict__ hotQ,
-                                  const int32_t* __restrict__ hot_items, int n_hot, int ld) {
+__global__ void hot_gather_kernel(const float* __restrict__ Q, float* __restrict__ hotQ, const int32_t* __restrict__ hot_items,
+                                  const int32_t* __restrict__ hot_dx, int n_hot, int ld) {
     const int lane = threadIdx.x & 31;
-    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5)
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
+        float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane);
 #pragma unroll
-        for (int v = 0; v < V; ++v)
-            hotQ[hot_slot_offset(s) + hot_lane_offset<V>(lane) + v] = Q[(size_t)hot_items[s] * ld + V * lane + v];
+        for (int v = 0; v < V; ++v) {
+            row[v] = Q[(size_t)hot_items[s] * ld + V * lane + v];
+            if (hot_dx[s]) row[hot_dx[s] / 4 + v] = 0.f;
+        }
+    }
 }
 template <int V>
-__global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restrict__ hotQ,
-                                   const int32_t* __restrict__ hot_items, int n_hot, int ld) {
+__global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restrict__ hotQ, const int32_t* __restrict__ hot_items,
+                                   const int32_t* __restrict__ hot_dx, int n_hot, int ld) {
     const int lane = threadIdx.x & 31;
-    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5)
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
+        const float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane);
 #pragma unroll
         for (int v = 0; v < V; ++v)
-            Q[(size_t)hot_items[s] * ld + V * lane + v] = hotQ[hot_slot_offset(s) + hot_lane_offset<V>(lane) + v];
+            Q[(size_t)hot_items[s] * ld + V * lane + v] = row[v] + (hot_dx[s] ? row[hot_dx[s] / 4 + v] : 0.f);
+    }
 }
 
 // Control flow.  A warp's work is a stream of segments (items from the global cursor, segments of an
@@ -156,10 +169,13 @@ __global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restric
 // its stall samples waiting for the instruction cache).
 template <int V>
 __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdParams p) {
-    extern __shared__ __align__(16) int hot_sm[];           // [n_hot] hot track ids, ascending; [n_hot] their slots
+    extern __shared__ __align__(16) int hot_sm[];           // [n_hot] hot track ids, ascending; [n_hot] their slots; [n_hot] dx
     int* hot_sorted = hot_sm;
     int* hot_sorted_slot = hot_sm + p.n_hot;
-    for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) { hot_sorted[x] = p.hot_sorted[x]; hot_sorted_slot[x] = p.hot_sorted_slot[x]; }
+    int* hot_dx = hot_sm + 2 * p.n_hot;                     // per slot: byte distance to its second row, or 0
+    for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) {
+        hot_sorted[x] = p.hot_sorted[x]; hot_sorted_slot[x] = p.hot_sorted_slot[x]; hot_dx[x] = p.hot_dx[x];
+    }
     __syncthreads();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -237,8 +253,9 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
 #pragma unroll
         for (int a = 0; a < kBlkK; ++a) {
             cur.pi[a] = cur.pj[a] = nullptr;
+            cur.dx[a] = 0;
 #pragma unroll
-            for (int v = 0; v < V; ++v) cur.qi[a][v] = cur.qj[a][v] = 0.f;
+            for (int v = 0; v < V; ++v) cur.qi[a][v] = cur.qj[a][v] = cur.ex[a][v] = 0.f;
         }
         for (int64_t seg = sb - 1; seg < se; ++seg) {
             const int nblk = (len + kBlkK - 1) / kBlkK;
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                 const bool last = b + 1 >= nblk;
                 if (last && has_next) {
                     // ---- prepare segment seg+1 (record na/nb arrived; its data was prefetched) ----
-                    n_u = na.x; n_len = na.y & 63; n_resync = (na.y & kSegShared) != 0;
+                    n_u = na.x; n_len = na.y & 63; n_resync = nb.w != 0;
                     if (lane < n_len) {
                         const int64_t e = rec_begin(na) + lane;
                         n_i = p.ev_items[e];             // hot positives arrive re-labelled -slot-1
@@ -279,10 +296,15 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                     for (int a = 0; a < kBlkK; ++a) {
                         const int t = t0 + a;                               // <= 31
                         const int32_t it = __shfl_sync(full, src_i, t), jt = __shfl_sync(full, src_j, t);
+                        nxt.dx[a] = 0;
                         if (t < src_len) {
                             nxt.pi[a] = q_ptr(it); nxt.pj[a] = q_ptr(jt);
                             ldv<V>(nxt.pi[a], nxt.qi[a]);
                             ldv<V>(nxt.pj[a], nxt.qj[a]);
+                            if (it < 0) {                                   // a sharded hot positive: fetch its second row too
+                                nxt.dx[a] = hot_dx[-it - 1];
+                                if (nxt.dx[a]) ldv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(nxt.pi[a]) + nxt.dx[a]), nxt.ex[a]);
+                            }
                         } else {
 #pragma unroll
                             for (int v = 0; v < V; ++v) nxt.qi[a][v] = nxt.qj[a][v] = 0.f;
@@ -297,6 +319,10 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                     float x[10];
 #pragma unroll
                     for (int a = 0; a < kBlkK; ++a) {
+                        if (cur.dx[a]) {                                    // logical row of a sharded positive = sum of its rows
+#pragma unroll
+                            for (int v = 0; v < V; ++v) cur.qi[a][v] += cur.ex[a][v];
+                        }
                         float s = 0.f;
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
@@ -347,7 +373,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                                 dj[v] = fmaf(-p.c_i, cur.qj[a][v] - gp, -gp);
                                 pu[v] = fmaf(-p.c_u, pn, pn);
                             }
-                            redv<V>(cur.pi[a], di);
+                            redv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
                             redv<V>(cur.pj[a], dj);
                         }
                     }

@@ -32,8 +32,8 @@ struct RankParams {
     int N;
     const int64_t* uq_indptr;   // mask rows
     const int32_t* uq_items;
-    int32_t* ids_out;           // [B, N]
-    float* scores_out;          // [B, N]
+    int32_t* ids_out;           // [B, N]; with gridDim.y = S catalog splits: [B, S, N] partial lists
+    float* scores_out;          // (rank_merge_kernel folds them into [B, N])
 };
 
 // order-preserving float <-> uint32 (ascending), and the 64-bit sort key (score desc, id asc)
@@ -109,7 +109,11 @@ __global__ void __launch_bounds__(256) rank_exact_kernel(const RankParams p) {
     const int64_t row0 = (int64_t)blockIdx.x * BU;
     const int ld = p.ld;
     const int nkc = (ld + kRankKC - 1) / kRankKC;
-    const int ntiles = (p.n_items + BI - 1) / BI;
+    // gridDim.y > 1: this CTA scans only its share of the catalog tiles and writes a partial list
+    const int ntiles_all = (p.n_items + BI - 1) / BI;
+    const int tiles_per_split = (ntiles_all + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int tile_first = (int)blockIdx.y * tiles_per_split;
+    const int ntiles = max(0, min(ntiles_all, tile_first + tiles_per_split) - tile_first);
 
     for (int r = tid; r < BU; r += 256) {
         const int64_t b = row0 + r;
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(256) rank_exact_kernel(const RankParams p) {
     constexpr int B_LD = BI * (kRankKC / 4) / 256;
     float4 ra[A_LD], rb[B_LD];
     auto load_chunk = [&](int it) {
-        const int tile = it / nkc, k0 = (it % nkc) * kRankKC;
+        const int tile = tile_first + it / nkc, k0 = (it % nkc) * kRankKC;
 #pragma unroll
         for (int x = 0; x < A_LD; ++x) {
             const int idx = tid + x * 256, r = idx % BU, k = k0 + (idx / BU) * 4;
@@ -162,9 +166,9 @@ __global__ void __launch_bounds__(256) rank_exact_kernel(const RankParams p) {
 
     float acc[8][8];
     const int total = ntiles * nkc;
-    load_chunk(0);
+    if (total > 0) load_chunk(0);
     for (int it = 0; it < total; ++it) {
-        const int tile = it / nkc, kc = it % nkc;
+        const int tile = tile_first + it / nkc, kc = it % nkc;
         if (kc == 0) {
 #pragma unroll
             for (int m = 0; m < 8; ++m)
@@ -260,12 +264,47 @@ __global__ void __launch_bounds__(256) rank_exact_kernel(const RankParams p) {
         if (b >= p.B) continue;
         const int c = s.cnt[r] < CAP ? s.cnt[r] : CAP;
         const int nc = compact_row<CAP>(s.keys[r], c, p.N, lane);
+        const int64_t orow = b * gridDim.y + blockIdx.y;
         for (int x = lane; x < p.N; x += 32) {
             const bool ok = x < nc;
             const uint64_t k = ok ? s.keys[r][x] : 0ull;
-            p.ids_out[b * p.N + x] = ok ? key_id(k) : -1;
-            p.scores_out[b * p.N + x] = ok ? key_score(k) : -INFINITY;
+            p.ids_out[orow * p.N + x] = ok ? key_id(k) : -1;
+            p.scores_out[orow * p.N + x] = ok ? key_score(k) : -INFINITY;
         }
+    }
+}
+
+// Fold the S partial lists of every row (exact scores, each the top N of its catalog slice) into the
+// row's top N by (score desc, id asc).  One warp per row.
+__global__ void __launch_bounds__(256) rank_merge_kernel(const int32_t* __restrict__ ids_part, const float* __restrict__ sc_part,
+                                                         int64_t B, int S, int N, int32_t* __restrict__ ids_out,
+                                                         float* __restrict__ sc_out) {
+    __shared__ uint64_t keys[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    uint64_t* R = keys[warp];
+    int have = 0;
+    for (int s0 = 0; s0 < S; ++s0) {
+        if (have + N > 256) { have = compact_row<256>(R, have, N, lane); __syncwarp(); }
+        const int64_t base = (b * S + s0) * N;
+        int cntv = 0;                                   // append the valid entries of this partial list
+        for (int x = 0; x < N; x += 32) {
+            const bool ok = x + lane < N && ids_part[base + x + lane] >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) R[have + cntv + __popc(m & ((1u << lane) - 1))] = make_key(sc_part[base + x + lane], ids_part[base + x + lane]);
+            cntv += __popc(m);
+        }
+        have += cntv;
+        __syncwarp();
+    }
+    const int nc = compact_row<256>(R, have, N, lane);
+    __syncwarp();
+    for (int x = lane; x < N; x += 32) {
+        const bool ok = x < nc;
+        const uint64_t k = ok ? R[x] : 0ull;
+        ids_out[b * N + x] = ok ? key_id(k) : -1;
+        sc_out[b * N + x] = ok ? key_score(k) : -INFINITY;
     }
 }
 

@@ -43,7 +43,7 @@ constexpr int kTcStages = 3;          // TMA -> MMA shared-memory stages
 constexpr int kTcCap = 64;            // candidate slots per row
 constexpr int kTcAcc = 4;             // TMEM accumulator stages (4 x 128 columns = all of TMEM)
 constexpr int kTcOvfCap = 1024;       // candidate slots of a row that overflowed into the global pool
-constexpr int kTcOvfRows = 512;       // rows the pool can take per launch
+constexpr int kTcOvfRowsMin = 512;    // rows the spill pool can take per launch: at least this, else B / 16
 constexpr int kTcBoxBytes = 128 * 128;   // one TMA box: 128 rows x 128 B
 constexpr float kTf32ErrCoef = 2.1e-3f;  // 2^-9 (two operands truncated to 10 mantissa bits) + slack
 
@@ -65,8 +65,9 @@ struct RankTcParams {
     float* scores_out;
     int* fail_count;
     int32_t* fail_rows;
-    uint64_t* ovf_pool;         // [kTcOvfRows, kTcOvfCap] spill space for rows with too many near-ties
+    uint64_t* ovf_pool;         // [ovf_rows, kTcOvfCap] spill space for rows with too many near-ties
     int* ovf_next;
+    int ovf_rows;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -181,7 +182,7 @@ __device__ __noinline__ bool tc_push(TcRow* st, uint64_t* K, const int32_t* __re
 // whole warp: compact every row of this warp whose buffer is more than half full; returns the
 // (possibly raised) push threshold of the calling lane's row
 __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int lane, int N, float eps2, float thr,
-                                         uint64_t* __restrict__ ovf_pool, int* __restrict__ ovf_next) {
+                                         uint64_t* __restrict__ ovf_pool, int* __restrict__ ovf_next, int ovf_rows) {
     unsigned full;
     while ((full = __ballot_sync(0xffffffffu, st->cnt > kTcCap - 32)) != 0u) {
         const int src = __ffs(full) - 1;
@@ -203,7 +204,7 @@ __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int 
         if (kept > kTcCap - 32) {              // too many near-ties for shared memory: spill the row
             if (lane == 0) slot = atomicAdd(ovf_next, 1);
             slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (slot < kTcOvfRows) {
+            if (slot < ovf_rows) {
                 uint64_t* G = ovf_pool + (size_t)slot * kTcOvfCap;
                 if (lane < kept) G[lane] = R[lane];
                 if (lane + 32 < kept) G[lane + 32] = R[lane + 32];
@@ -212,7 +213,7 @@ __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int 
         if (lane == src) {
             thr = lim;
             if (kept <= kTcCap - 32) st->cnt = kept;
-            else if (slot < kTcOvfRows) { st->ovf_slot = slot; st->ovf_cnt = kept; st->cnt = 0; }   // threshold frozen from here on
+            else if (slot < ovf_rows) { st->ovf_slot = slot; st->ovf_cnt = kept; st->cnt = 0; }   // threshold frozen from here on
             else { st->fail = 1; thr = INFINITY; st->cnt = 0; }
         }
         __syncwarp();
@@ -323,7 +324,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                 }                                                                                    \
             }                                                                                        \
             __syncwarp();                                                                            \
-            thr = tc_compact(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next);       \
+            thr = tc_compact(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next, p.ovf_rows);       \
         } while (0)
 
         for (int j = 0; j < p.ntiles; ++j) {
@@ -485,6 +486,8 @@ struct RankTcState {
     uint64_t* ovf_pool = nullptr;
     int* ovf_next = nullptr;
     int64_t last_fail = 0;       // rows sent to the exact kernel by the last call (diagnostics)
+    int64_t last_spill = 0;      // rows that spilled into the pool during the last call
+    size_t ovf_rows = 0;
 };
 
 inline bool rank_tc_supported(int k, int N) { return k >= 1 && k <= 64 && N >= 1 && N <= 32; }
@@ -537,9 +540,9 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
         TC_CK(cudaMalloc((void**)&st.qmax, sizeof(float)));
         TC_CK(cudaMalloc((void**)&st.fail_count, sizeof(int)));
         TC_CK(cudaMalloc((void**)&st.ovf_next, sizeof(int)));
-        TC_CK(cudaMalloc((void**)&st.ovf_pool, (size_t)kTcOvfRows * kTcOvfCap * sizeof(uint64_t)));
     }
     const int64_t Bpad = (B + kTcBM - 1) / kTcBM * kTcBM;
+    TC_CK(tc_grow(st.ovf_pool, st.ovf_rows, (size_t)std::max<int64_t>(kTcOvfRowsMin, B / 16) * kTcOvfCap));
     size_t cap_tmp = st.psel_cap;
     TC_CK(tc_grow(st.psel, st.psel_cap, (size_t)Bpad * ld));
     (void)cap_tmp;
@@ -569,17 +572,19 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
     p.Psel = st.psel; p.Q = Q; p.pnorm = st.pnorm; p.qmax = st.qmax; p.users = d_users;
     p.uq_indptr = uq_indptr; p.uq_items = uq_items; p.ids_out = d_ids; p.scores_out = d_scores;
     p.fail_count = st.fail_count; p.fail_rows = st.fail_rows;
-    p.ovf_pool = st.ovf_pool; p.ovf_next = st.ovf_next;
+    p.ovf_pool = st.ovf_pool; p.ovf_next = st.ovf_next; p.ovf_rows = (int)(st.ovf_rows / kTcOvfCap);
     const size_t smem = 1024 + (size_t)p.kblocks * kTcBoxBytes * (1 + kTcStages) + (size_t)kTcBM * kTcCap * 8 + 256;
     TC_CK(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rank_tc_kernel<<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);
     ++launches;
     TC_CK(cudaGetLastError());
 
-    int nfail = 0;
+    int nfail = 0, nspill = 0;
     TC_CK(cudaMemcpyAsync(&nfail, st.fail_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TC_CK(cudaMemcpyAsync(&nspill, st.ovf_next, sizeof(int), cudaMemcpyDeviceToHost, stream));
     TC_CK(cudaStreamSynchronize(stream));
     st.last_fail = nfail;
+    st.last_spill = nspill;
     if (nfail > 0) {                      // rows with too many near-ties: exact kernel, then scatter back
         if ((size_t)nfail > st.fb_cap) {
             for (void* q : {(void*)st.fb_users, (void*)st.fb_ids, (void*)st.fb_scores}) if (q) cudaFree(q);

@@ -111,13 +111,14 @@ struct yue_handle {
     // the chain of dependent atomics on one address stays below ~T/hot_div updates (~11 ns each).
     int hot_max = kHotSlots;
     int hot_min_count = 16384;
-    int hot_div = 32;
+    int hot_div = 128;
+    int hot_shard_div = 40;           // blocked kernel: a track played by more than 1/hot_shard_div of the events gets two rows
     int n_hot = 0;
     std::vector<int32_t> h_hot_counts;   // per hot slot
     int hot_meta_cap = 0, hot_meta_ld = 0;   // what the current hot_meta / hot_shards were built for
     int64_t hot_extra_rows = 0;
     int sgd_kernel = 2;               // YUE_SGD_KERNEL: 1 = per-triplet kernel, 2 = blocked kernel where it applies
-    DevBuf<int32_t> hot_items, hot_slot, item_counts, hot_meta, hot_sorted, hot_sorted_slot;
+    DevBuf<int32_t> hot_items, hot_slot, item_counts, hot_meta, hot_sorted, hot_sorted_slot, hot_dx;
     DevBuf<float> hot_shards, hotQ;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -139,9 +140,13 @@ struct yue_handle {
     int64_t n_items = 0;
     DevBuf<unsigned long long> cursor;
     DevBuf<SegRec> seg_rec, tmp_rec;
-    PinBuf<SegRec> pin_rec;          // host staging of the segment records
+    PinBuf<SegRec> pin_rec;          // host staging of the segment records and item ranges
+    PinBuf<int64_t> pin_items;
     std::vector<int64_t> h_uq_indptr;
-    int item_group_segs = 8;         // light users per work item: consecutive users until this many segments (YUE_SGD_GROUP_SEGS)
+    // Light users per work item: consecutive users until this many segments (YUE_SGD_GROUP_SEGS).  Measured at C2
+    // (profiles/quality_raw/quality_study_r1t.txt): 8 is 2 % faster but Recall@10 scatters 0.094-0.099 between runs;
+    // one user per item reproduces the serial order (0.0978-0.0981 in every run).
+    int item_group_segs = 1;
 
     // factors
     int k = 0, ld = 0;
@@ -154,9 +159,9 @@ struct yue_handle {
     DevBuf<double> scal;          // [0] loss, [1] |P|^2, [2] |Q|^2
 
     // scratch
-    DevBuf<int32_t> tmp_i, tmp_j, rk_users, rk_ids;
+    DevBuf<int32_t> tmp_i, tmp_j, rk_users, rk_ids, rk_part_ids;
     DevBuf<int64_t> tmp_ws;
-    DevBuf<float> rk_scores, pred;
+    DevBuf<float> rk_scores, pred, rk_part_scores;
     DevBuf<unsigned char> l2buf;
     RankTcState tc;
 
@@ -200,17 +205,14 @@ static int q_interleaved(yue_t* h);
 struct ItemPlanArgs {
     bool allow_shared; int64_t item_segs, max_items, group_segs; int seg_events; const int64_t* uq_indptr;
 };
-template <class RunFn>
-static int64_t count_run_segments(size_t r0, size_t r1, RunFn run, int seg_events) {
-    int64_t n = 0;
-    for (size_t r = r0; r < r1; ++r) { int64_t b, e; int32_t u; run(r, b, e, u); n += (e - b + seg_events - 1) / seg_events; }
-    return n;
-}
-template <class RunFn>
-static void plan_runs(size_t r0, size_t r1, RunFn run, const ItemPlanArgs& a, SegRec* rec, int64_t seg0,
-                      std::vector<int64_t>& item_rng) {
-    int64_t s = seg0, open_first = -1;
-    auto close_open = [&]() { if (open_first >= 0) { item_rng.push_back(open_first); item_rng.push_back(s); open_first = -1; } };
+// one pass over runs [r0, r1): WRITE = false only counts segments and items, WRITE = true fills
+// rec[seg0...] and item_rng[2 * item0 ...]
+template <bool WRITE, class RunFn>
+static void plan_runs(size_t r0, size_t r1, RunFn run, const ItemPlanArgs& a, SegRec* rec, int64_t* item_rng,
+                      int64_t seg0, int64_t item0, int64_t& nseg_out, int64_t& nitem_out) {
+    int64_t s = seg0, it = item0, open_first = -1;
+    auto emit = [&](int64_t b, int64_t e) { if (WRITE) { item_rng[2 * it] = b; item_rng[2 * it + 1] = e; } ++it; };
+    auto close_open = [&]() { if (open_first >= 0) { emit(open_first, s); open_first = -1; } };
     for (size_t r = r0; r < r1; ++r) {
         int64_t b, e; int32_t u;
         run(r, b, e, u);
@@ -218,30 +220,35 @@ static void plan_runs(size_t r0, size_t r1, RunFn run, const ItemPlanArgs& a, Se
         if (nsegs == 0) continue;
         const bool heavy = nsegs > a.item_segs && a.allow_shared;
         if (heavy) close_open();
-        const int64_t first = s, row0 = a.uq_indptr[u];
-        const int32_t row_len = (int32_t)(a.uq_indptr[u + 1] - row0), flag = heavy ? kSegShared : 0;
-        for (; b < e; b += a.seg_events, ++s) {
-            SegRec& x = rec[s];
-            x.user = u; x.len_flags = (int32_t)std::min<int64_t>(a.seg_events, e - b) | flag; x.begin = b;
-            x.row_begin = row0; x.row_len = row_len; x.pad = 0;
+        const int64_t first = s;
+        if (WRITE) {
+            const int64_t row0 = a.uq_indptr[u];
+            const int32_t row_len = (int32_t)(a.uq_indptr[u + 1] - row0), flag = heavy ? kSegShared : 0;
+            for (; b < e; b += a.seg_events, ++s) {
+                SegRec& x = rec[s];
+                x.user = u; x.len_flags = (int32_t)std::min<int64_t>(a.seg_events, e - b) | flag; x.begin = b;
+                x.row_begin = row0; x.row_len = row_len; x.shared = flag;
+            }
+        } else {
+            s += nsegs;
         }
         if (heavy) {
             const int64_t per = std::max(a.item_segs, (nsegs + a.max_items - 1) / a.max_items);
-            for (int64_t i = first; i < s; i += per) { item_rng.push_back(i); item_rng.push_back(std::min(s, i + per)); }
+            for (int64_t i = first; i < s; i += per) emit(i, std::min(s, i + per));
         } else {
             if (open_first < 0) open_first = first;
             if (s - open_first >= a.group_segs) close_open();
         }
     }
     close_open();
+    nseg_out = s - seg0; nitem_out = it - item0;
 }
-// returns the number of segments; rec_buf is (re)allocated to hold them
+// plans all runs on the host cores (an item never spans two threads' shares); the buffers are (re)allocated
 template <class RunFn>
-static cudaError_t plan_items(size_t nruns, RunFn run, const ItemPlanArgs& a, PinBuf<SegRec>& rec_buf, int64_t& nseg,
-                              std::vector<int64_t>& item_rng) {
+static cudaError_t plan_items(size_t nruns, RunFn run, const ItemPlanArgs& a, PinBuf<SegRec>& rec_buf, PinBuf<int64_t>& item_buf,
+                              int64_t& nseg, int64_t& nitems) {
     const size_t nthreads = nruns < 65536 ? 1 : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
-    std::vector<int64_t> seg_count(nthreads), seg_first(nthreads + 1, 0);
-    std::vector<std::vector<int64_t>> items(nthreads);
+    std::vector<int64_t> segs(nthreads), its(nthreads), seg_first(nthreads + 1, 0), item_first(nthreads + 1, 0);
     auto share = [&](size_t t) { return nruns * t / nthreads; };
     auto parallel = [&](auto fn) {
         std::vector<std::thread> th;
@@ -249,17 +256,16 @@ static cudaError_t plan_items(size_t nruns, RunFn run, const ItemPlanArgs& a, Pi
         fn(0);
         for (auto& x : th) x.join();
     };
-    parallel([&](size_t t) { seg_count[t] = count_run_segments(share(t), share(t + 1), run, a.seg_events); });
-    for (size_t t = 0; t < nthreads; ++t) seg_first[t + 1] = seg_first[t] + seg_count[t];
-    nseg = seg_first[nthreads];
+    parallel([&](size_t t) { plan_runs<false>(share(t), share(t + 1), run, a, nullptr, nullptr, 0, 0, segs[t], its[t]); });
+    for (size_t t = 0; t < nthreads; ++t) { seg_first[t + 1] = seg_first[t] + segs[t]; item_first[t + 1] = item_first[t] + its[t]; }
+    nseg = seg_first[nthreads]; nitems = item_first[nthreads];
     cudaError_t e = rec_buf.ensure((size_t)nseg);
+    if (e == cudaSuccess) e = item_buf.ensure((size_t)nitems * 2);
     if (e != cudaSuccess) return e;
     parallel([&](size_t t) {
-        items[t].reserve(2 * (size_t)(seg_count[t] / std::max<int64_t>(a.group_segs, 1) + 64));
-        plan_runs(share(t), share(t + 1), run, a, rec_buf.p, seg_first[t], items[t]);
+        int64_t x, y;
+        plan_runs<true>(share(t), share(t + 1), run, a, rec_buf.p, item_buf.p, seg_first[t], item_first[t], x, y);
     });
-    item_rng.clear();
-    for (auto& v : items) item_rng.insert(item_rng.end(), v.begin(), v.end());
     return cudaSuccess;
 }
 
@@ -301,6 +307,7 @@ int yue_create(int device, yue_t** out) {
     if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(kHotSlots, atoi(s)));
     if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_HOT_DIV")) h->hot_div = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_SGD_HOT_SHARD_DIV")) h->hot_shard_div = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_GROUP_SEGS")) h->item_group_segs = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_KERNEL")) h->sgd_kernel = atoi(s) == 1 ? 1 : 2;
     if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
@@ -321,10 +328,10 @@ int yue_destroy(yue_t* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     rank_tc_release(h->tc);
     for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->item_ptr, &h->tmp_ws}) b->release();
-    h->seg_rec.release(); h->tmp_rec.release(); h->pin_rec.release();
+    h->seg_rec.release(); h->tmp_rec.release(); h->pin_rec.release(); h->pin_items.release();
     h->cursor.release();
-    for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->tmp_i, &h->tmp_j, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot}) b->release();
-    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->hot_shards, &h->hotQ}) b->release();
+    for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->tmp_i, &h->tmp_j, &h->rk_part_ids, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot, &h->hot_dx}) b->release();
+    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
     h->l2buf.release();
     cudaEventDestroy(h->ev0);
@@ -378,14 +385,12 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     // a heavy user's item is at most a quarter of a warp's fair share, so no item is a straggler
     int64_t item_segs = std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)h->n_warps * 4 * 32)));
     if (h->item_segs_env > 0) item_segs = h->item_segs_env;
-    std::vector<int64_t> ip;
     const ItemPlanArgs plan{true, item_segs, h->max_items_per_user, h->item_group_segs, h->seg_events, uq_indptr};
     CK(plan_items((size_t)m_local, [=](size_t r, int64_t& b, int64_t& e, int32_t& u) { b = ev_indptr[r]; e = ev_indptr[r + 1]; u = (int32_t)r; },
-                  plan, h->pin_rec, h->nseg, ip));
-    h->n_items = (int64_t)ip.size() / 2;
-    CK(h->seg_rec.resize(h->nseg)); CK(h->item_ptr.resize(ip.size())); CK(h->cursor.resize(1));
+                  plan, h->pin_rec, h->pin_items, h->nseg, h->n_items));
+    CK(h->seg_rec.resize(h->nseg)); CK(h->item_ptr.resize(2 * h->n_items)); CK(h->cursor.resize(1));
     if (h->nseg) CK(cudaMemcpyAsync(h->seg_rec.p, h->pin_rec.p, h->nseg * sizeof(SegRec), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->item_ptr.p, ip.data(), ip.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (h->n_items) CK(cudaMemcpyAsync(h->item_ptr.p, h->pin_items.p, 2 * h->n_items * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     // hot tracks: device histogram of the positives, top hot_max by count on the host, then the hot
     // positives of the device copy of ev_items are re-labelled -slot-1 (see SgdParams::hot_items)
     h->n_hot = 0;
@@ -415,6 +420,14 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
             for (int s2 = 0; s2 < h->n_hot; ++s2) order[s2] = s2;
             std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cand[a] < cand[b]; });
             for (int32_t s2 : order) { sorted_ids.push_back(cand[s2]); sorted_slots.push_back(s2); }
+            std::vector<int32_t> dx((size_t)h->n_hot, 0);       // second rows for the most played tracks (blocked kernel)
+            for (int s2 = 0, extra = 0; s2 < h->n_hot && extra < kHotExtra; ++s2)
+                if ((int64_t)counts[cand[s2]] * h->hot_shard_div > T) {
+                    dx[s2] = (int32_t)((hot_slot_offset(h->n_hot + extra) - hot_slot_offset(s2)) * sizeof(float));
+                    ++extra;
+                }
+            CK(h->hot_dx.resize(h->n_hot));
+            CK(cudaMemcpyAsync(h->hot_dx.p, dx.data(), dx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
             CK(h->hot_sorted.resize(h->n_hot)); CK(h->hot_sorted_slot.resize(h->n_hot)); CK(h->hotQ.resize(kHotTableFloats));
             CK(cudaMemcpyAsync(h->hot_sorted.p, sorted_ids.data(), sorted_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(h->hot_sorted_slot.p, sorted_slots.data(), sorted_slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -544,9 +557,9 @@ template <int V>
 static cudaError_t launch_sgd_blk(const SgdParams& sp, int warps_per_cta, cudaStream_t st, int64_t& launches) {
     warps_per_cta = std::min(warps_per_cta, kBlkThreads / 32);
     const int grid = (sp.n_warps + warps_per_cta - 1) / warps_per_cta;
-    if (sp.n_hot > 0) { hot_gather_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.n_hot, sp.ld); ++launches; }
-    bpr_sgd_blk_kernel<V><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 8, st>>>(sp);
-    if (sp.n_hot > 0) { hot_scatter_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.n_hot, sp.ld); ++launches; }
+    if (sp.n_hot > 0) { hot_gather_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
+    bpr_sgd_blk_kernel<V><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
+    if (sp.n_hot > 0) { hot_scatter_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
     return cudaGetLastError();
 }
 
@@ -589,7 +602,7 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr 
     sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
     if (sp.n_hot > 0) {
-        if (blk) { sp.hotQ = h->hotQ.p; sp.hot_sorted = h->hot_sorted.p; sp.hot_sorted_slot = h->hot_sorted_slot.p; }
+        if (blk) { sp.hotQ = h->hotQ.p; sp.hot_sorted = h->hot_sorted.p; sp.hot_sorted_slot = h->hot_sorted_slot.p; sp.hot_dx = h->hot_dx.p; }
         else {
             if (int rc = ensure_hot_meta(h, kHotShards)) return rc;
             sp.hot_meta = h->hot_meta.p; sp.hot_shards = h->hot_shards.p;
@@ -670,7 +683,7 @@ static int sgd_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t
     REQUIRE(T >= 0 && (T == 0 || (u && i && j)), YUE_E_ARG, "null triplet array");
     CK(cudaSetDevice(h->device));
     if (T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
-    std::vector<int64_t> ip, rb, re;
+    std::vector<int64_t> rb, re;
     std::vector<int32_t> ru;
     for (int64_t t = 0; t < T;) {               // runs of one user
         REQUIRE(u[t] >= 0 && u[t] < h->m, YUE_E_ARG, "triplet user out of range");
@@ -686,23 +699,24 @@ static int sgd_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t
         : (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
     const ItemPlanArgs plan{mode != YUE_MODE_SERIAL, std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)n_warps * 4 * 32))),
                             h->max_items_per_user, mode == YUE_MODE_SERIAL ? 1 : h->item_group_segs, 32, h->h_uq_indptr.data()};
-    int64_t nseg = 0;
+    int64_t nseg = 0, nitems = 0;
     PinBuf<SegRec> recs;
+    PinBuf<int64_t> ip;
     cudaError_t pe = plan_items(rb.size(), [&](size_t r, int64_t& b, int64_t& e, int32_t& uu) { b = rb[r]; e = re[r]; uu = ru[r]; },
-                                plan, recs, nseg, ip);
-    if (pe != cudaSuccess) { recs.release(); return fail(h, YUE_E_CUDA, std::string("plan_items: ") + cudaGetErrorString(pe)); }
-    struct Guard { PinBuf<SegRec>& b; cudaStream_t st; ~Guard() { cudaStreamSynchronize(st); b.release(); } } guard{recs, h->stream};
+                                plan, recs, ip, nseg, nitems);
+    struct Guard { PinBuf<SegRec>& a; PinBuf<int64_t>& b; cudaStream_t st; ~Guard() { cudaStreamSynchronize(st); a.release(); b.release(); } } guard{recs, ip, h->stream};
+    if (pe != cudaSuccess) return fail(h, YUE_E_CUDA, std::string("plan_items: ") + cudaGetErrorString(pe));
     CK(h->tmp_rec.resize((size_t)nseg));
     CK(cudaMemcpyAsync(h->tmp_rec.p, recs.p, (size_t)nseg * sizeof(SegRec), cudaMemcpyHostToDevice, h->stream));
     CK(h->tmp_i.resize(T)); CK(h->tmp_j.resize(T));
-    CK(h->tmp_ws.resize(ip.size())); CK(h->cursor.resize(1));
+    CK(h->tmp_ws.resize((size_t)nitems * 2)); CK(h->cursor.resize(1));
     CK(cudaMemcpyAsync(h->tmp_i.p, i, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tmp_j.p, j, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->tmp_ws.p, ip.data(), ip.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_ws.p, ip.p, (size_t)nitems * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     SgdParams sp{};
     fill_rates(sp, lr, regU, regI);
     sp.seg_rec = h->tmp_rec.p;
-    sp.item_ptr = h->tmp_ws.p; sp.n_work = (int64_t)ip.size() / 2; sp.n_warps = n_warps;
+    sp.item_ptr = h->tmp_ws.p; sp.n_work = nitems; sp.n_warps = n_warps;
     sp.ev_items = h->tmp_i.p; sp.ev_neg = h->tmp_j.p;
     sp.n_hot = 0;                                // explicit triplets take the direct path
     sp.resync_events = h->resync_events;
@@ -752,22 +766,38 @@ int yue_predict(yue_t* h, int64_t user, float* scores_out) {
 }
 
 template <int BU, int CAP>
-static cudaError_t launch_rank_exact(const RankParams& rp, cudaStream_t st) {
+static cudaError_t launch_rank_exact(const RankParams& rp, int splits, cudaStream_t st) {
     const size_t smem = sizeof(RankSmem<BU, CAP>);
     cudaError_t e = cudaFuncSetAttribute(rank_exact_kernel<BU, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = (int)((rp.B + BU - 1) / BU);
+    const dim3 grid((unsigned)((rp.B + BU - 1) / BU), (unsigned)splits);
     rank_exact_kernel<BU, CAP><<<grid, 256, smem, st>>>(rp);
     return cudaGetLastError();
 }
 
+// A CTA of the exact kernel scans the whole catalog for its 64/128 users, so a handful of users would
+// leave the GPU idle (0.17 s for ONE row block at 2 M tracks).  Few rows: split the catalog over
+// gridDim.y CTAs per row block, each writes a partial top-N, rank_merge_kernel folds them.
 static int yue_rank_exact_device(yue_t* h, const int32_t* d_users, int64_t B, int N, int32_t* d_ids, float* d_scores) {
     RankParams rp{};
     rp.P = h->P.p; rp.Q = h->Q.p; rp.ld = h->ld; rp.n_items = (int)h->n; rp.users = d_users; rp.B = B; rp.N = N;
     rp.uq_indptr = h->uq_indptr.p; rp.uq_items = h->uq_items.p; rp.ids_out = d_ids; rp.scores_out = d_scores;
-    if (N <= 32) CK(launch_rank_exact<128, 64>(rp, h->stream));
-    else CK(launch_rank_exact<64, 256>(rp, h->stream));
+    const int BU = N <= 32 ? 128 : 64, BI = 16384 / BU;
+    const int64_t row_blocks = (B + BU - 1) / BU, ntiles = (h->n + BI - 1) / BI;
+    int splits = 1;
+    if (row_blocks < h->sm_count) splits = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles / 8, 2 * h->sm_count / row_blocks));
+    if (splits > 1) {
+        CK(h->rk_part_ids.resize((size_t)B * splits * N)); CK(h->rk_part_scores.resize((size_t)B * splits * N));
+        rp.ids_out = h->rk_part_ids.p; rp.scores_out = h->rk_part_scores.p;
+    }
+    if (N <= 32) CK(launch_rank_exact<128, 64>(rp, splits, h->stream));
+    else CK(launch_rank_exact<64, 256>(rp, splits, h->stream));
     ++h->launches;
+    if (splits > 1) {
+        rank_merge_kernel<<<(unsigned)((B + 7) / 8), 256, 0, h->stream>>>(h->rk_part_ids.p, h->rk_part_scores.p, B, splits, N, d_ids, d_scores);
+        ++h->launches;
+        CK(cudaGetLastError());
+    }
     return YUE_OK;
 }
 
@@ -893,6 +923,12 @@ int yue_timer_stop(yue_t* h, float* ms) {
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaEventSynchronize(h->ev1));
     CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return YUE_OK;
+}
+int yue_rank_stats(yue_t* h, int64_t* fallback_rows, int64_t* spilled_rows) {
+    REQUIRE(h, YUE_E_ARG, "null argument");
+    if (fallback_rows) *fallback_rows = h->tc.last_fail;
+    if (spilled_rows) *spilled_rows = h->tc.last_spill;
     return YUE_OK;
 }
 int yue_launch_count(yue_t* h, int64_t* n) { REQUIRE(h && n, YUE_E_ARG, "null argument"); *n = h->launches; return YUE_OK; }

@@ -204,6 +204,12 @@ class Engine:
         self._ck(self.lib.yue_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def rank_stats(self):
+        """(rows redone by the exact kernel, rows spilled into the pool) of the last tcgen05 ranking call"""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.yue_rank_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def flush_l2(self):
         self._ck(self.lib.yue_flush_l2(self.h))
 
