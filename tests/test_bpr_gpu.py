@@ -248,3 +248,67 @@ def test_hot_row_path_conserves_updates(monkeypatch):
     assert np.abs((Q1 - Q) - (Q0 - Q)).max() < 2e-3 * np.abs(Q0 - Q).max()
     assert np.abs((P1 - P) - (P0 - P)).max() < 5e-2 * np.abs(P0 - P).max()
     assert np.linalg.norm(Q1 - Q) == pytest.approx(np.linalg.norm(Q0 - Q), rel=1e-3)
+
+
+# ---- the blocked kernel (bpr_sgd_blk.cuh): all three row widths, hot-row table, second rows ----------
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_blocked_kernel_conflict_free_all_widths(engine, d):
+    """Disjoint rows per triplet: the blocked kernel (4 triplets per block, scores from the Gram
+    recurrence) must give the serial loop's factors -- several triplets per user so that the
+    recurrence, partial last blocks and segment boundaries are all exercised."""
+    m, n = 300, 300 * 2 * 37
+    log = synth.power_law_log(m, n, 9000, seed=3)
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    P, Q = synth.init_factors(m, n, d, seed=1)
+    per = 1 + np.arange(m) % 37                      # 1..37 triplets per user: blocks of 1-4, up to 2 segments
+    u = np.repeat(np.arange(m, dtype=np.int32), per)
+    T = len(u)
+    i = (2 * np.arange(T)).astype(np.int32)
+    j = (2 * np.arange(T) + 1).astype(np.int32)
+    Pr, Qr = P.copy(), Q.copy()
+    ref_loss = bpr_ref.sgd_epoch(Pr, Qr, u, i, j, 0.05, 0.01, 0.02)
+    engine.set_factors(P, Q)
+    loss = engine.bpr_apply(u, i, j, 0.05, 0.01, 0.02, MODE_HOGWILD)
+    Pg, Qg = engine.get_factors()
+    assert rel_err(Pg, Pr) < REL and rel_err(Qg, Qr) < REL
+    assert loss == pytest.approx(ref_loss, rel=1e-5)
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_blocked_kernel_hot_table_lr0_and_conservation(monkeypatch, d):
+    """Hot-row table with second rows, every track of a small catalog hot.  (1) lr = 0: the epoch must
+    leave P and Q bit-identical (rows travel Q -> table -> Q) and the loss is the sum of softplus;
+    (2) tiny lr (linear regime, order-free): row movements agree with the per-triplet kernel's direct
+    path, i.e. the table neither loses nor duplicates an update, negatives that hit hot tracks included."""
+    from yue_b200.engine import Engine
+    log = synth.power_law_log(1500, 400, 150000, seed=4)
+    P, Q = synth.init_factors(log.m, log.n, d, seed=6)
+    ev_user = record_ref.ev_users(log.ev_indptr)
+    out = {}
+    for name, env in (("direct", dict(YUE_SGD_KERNEL="1", YUE_SGD_HOT_MAX="0")),
+                      ("table", dict(YUE_SGD_KERNEL="2", YUE_SGD_HOT_MIN_COUNT="1", YUE_SGD_HOT_DIV="1000000", YUE_SGD_HOT_SHARD_DIV="50"))):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = Engine(0)
+        try:
+            eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+            if name == "table":
+                eng.set_factors(P, Q)
+                loss0 = eng.bpr_epoch(0.0, 0.0, 0.0, 3, 0, MODE_HOGWILD)
+                P0, Q0 = eng.get_factors()
+                assert np.array_equal(P0, P) and np.array_equal(Q0, Q)
+                neg = eng.sample_negatives(3, 0)
+                x = np.einsum("ij,ij->i", P[ev_user].astype(np.float64), (Q[log.ev_items] - Q[neg]).astype(np.float64))
+                assert loss0 == pytest.approx(float(np.logaddexp(0.0, -x).sum()), rel=1e-5)
+            eng.set_factors(P, Q)
+            loss = eng.bpr_epoch(1e-5, 0.0, 0.0, 3, 0, MODE_HOGWILD)
+            out[name] = (loss, eng.get_factors())
+        finally:
+            eng.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    (l0, (Pd, Qd)), (l1, (Pt, Qt)) = out["direct"], out["table"]
+    assert l1 == pytest.approx(l0, rel=1e-4)
+    assert np.abs((Qt - Q) - (Qd - Q)).max() < 2e-3 * np.abs(Qd - Q).max()
+    assert np.abs((Pt - P) - (Pd - P)).max() < 5e-2 * np.abs(Pd - P).max()
+    assert np.linalg.norm(Qt - Q) == pytest.approx(np.linalg.norm(Qd - Q), rel=1e-3)

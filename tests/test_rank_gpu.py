@@ -166,3 +166,24 @@ def test_tc_overflow_pool_keeps_exactness(engine):
     engine.set_factors(P, Q)
     ids, sc = check(engine, P, Q, np.arange(m, dtype=np.int32), N, uq_indptr, np.zeros(0, np.int32), RANK_TC)
     assert ids[0].tolist() == sorted(dup.tolist())[:10]
+
+
+def test_exact_kernel_catalog_split_and_stats(engine):
+    """Few rows against a big catalog: the exact kernel splits the catalog over CTAs and merges the
+    partial lists -- ids and scores must still be the oracle's, bit for bit; rank_stats is callable."""
+    from oracle import topn
+    from yue_b200.engine import RANK_EXACT, RANK_TC
+    m, n, d = 40, 70000, 64
+    indptr, uq = synth.mask_csr(m, n, 30, seed=5)
+    P, Q = synth.init_factors(m, n, d, seed=9)
+    Q[1000:1040] = Q[999]                           # exact ties across a run of ids: order must be id ascending
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), indptr, uq)
+    engine.set_factors(P, Q)
+    users = np.arange(m, dtype=np.int32)
+    for N in (10, 50):
+        ids, sc = engine.rank_topn(users, N, RANK_EXACT)
+        rid, rsc = topn.topn_exact(P, Q, users, N, indptr, uq)
+        assert np.array_equal(ids, rid) and np.array_equal(sc, rsc)
+    engine.rank_topn(np.arange(m, dtype=np.int32).repeat(8), 10, RANK_TC)
+    fb, spilled = engine.rank_stats()
+    assert fb >= 0 and spilled >= 0
