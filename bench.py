@@ -345,6 +345,12 @@ def bench_ranking(eng, args, bf16_peak):
         flops = 2.0 * B * n * D
         out[key] = {"users": B, "tracks": n, "seconds": t, "users_per_sec": B / t, "dense_tflops": flops / t / 1e12,
                     "frac_of_bf16_peak": flops / t / 1e12 / bf16_peak}
+    # K6: the metrics of those lists against a synthetic held-out set (5 tracks per user), on the device
+    te_indptr, te_items = synth.mask_csr_torch(m, n, 5, SEED + 5)
+    eng.set_test_set(te_indptr, te_items)
+    t0 = time.perf_counter()
+    sums, distinct = eng.rank_metrics([5, 10])
+    out["metrics_seconds"] = time.perf_counter() - t0
     out["value"] = out["c4_full"]["users_per_sec"]
     out["workload"] = "C4: top-10 of %d users x %d tracks, d=64, ~50 masked tracks/user, one GPU" % (m, n)
     return out

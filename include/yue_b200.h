@@ -135,6 +135,17 @@ int yue_predict(yue_t* h, int64_t user, float* scores_out);
 int yue_rank_topn(yue_t* h, const int32_t* users, int64_t B, int N, int algo,
                   int32_t* ids_out, float* scores_out);
 
+/* Replaces Measure.rankingMeasure, evaluation/measure.py:16-41 (hits 7-13, precision 51-53,
+ * recall 91-94, MAP 56-66, coverage 43-48) plus the binary-relevance NDCG@n the reference lacks,
+ * for the lists the last yue_rank_topn left on the device.  yue_set_test_set uploads Record.testSet
+ * (data/record.py:195-202) as a CSR over the local users: test_indptr[m+1], test_items sorted unique
+ * per user.  yue_rank_metrics: for each cut-off n = cuts[k] (the -topN list) sums_out[k*4 + {0,1,2,3}]
+ * = sum over the ranked rows of {hits, hits/|test(u)|, AP, NDCG} and distinct_out[k] = number of
+ * distinct tracks in the first n columns; the caller divides (precision = hits/(rows*n), recall =
+ * sum/rows, MAP = sum/rows, coverage = distinct/itemCount).  Sums are reduced in a fixed order. */
+int yue_set_test_set(yue_t* h, const int64_t* test_indptr, const int32_t* test_items);
+int yue_rank_metrics(yue_t* h, int n_cuts, const int32_t* cuts, double* sums_out, int64_t* distinct_out);
+
 /* ---- multi-GPU: user-sharded SGD with Q replicated; once per sub-epoch
  *      Q <- Q_snapshot + sum_over_ranks(Q_rank - Q_snapshot).  No reference counterpart
  *      (the reference has no collective anywhere). ---- */

@@ -121,9 +121,10 @@ def test_c1_end_to_end_through_the_class_api(tmp_path):
     log_path = tmp_path / "log.txt"
     synth.write_csv_log(str(log_path), 4000, 50000, 100000, seed=20260101)
     results = {}
-    for mode in ("serial", "hogwild"):
-        vals = conf_values(tmp_path / mode, extra={"record": str(log_path), "yue.sgd": mode, "yue.seed": "77",
-                                                   "num.max.iter": "2"})
+    for mode in ("serial", "hogwild", "serial-device-metrics"):
+        vals = conf_values(tmp_path / mode, extra={"record": str(log_path), "yue.sgd": mode.split("-")[0], "yue.seed": "77",
+                                                   "num.max.iter": "2",
+                                                   "yue.metrics": "device" if mode.endswith("metrics") else "host"})
         random.seed(5)                       # DataSplit uses the global stream (tool/dataSplit.py:15)
         np.random.seed(11)                   # initModel uses the global numpy stream
         with redirect_stdout(io.StringIO()):
@@ -143,6 +144,17 @@ def test_c1_end_to_end_through_the_class_api(tmp_path):
     assert np.allclose(ms.P, P, rtol=1e-5, atol=1e-7) and np.allclose(ms.Q, Q, rtol=1e-5, atol=1e-7)
     assert ms.loss == pytest.approx(hist[-1][0], rel=1e-5)
     assert meas[0] == "Top 5\n" and meas[6] == "Top 10\n" and meas[1].startswith("Precision:")
+    # metrics computed on the device (K6): same numbers as the reference's Measure on the same lists
+    md, meas_d = results["serial-device-metrics"]
+    assert len(meas_d) == len(meas)
+    for a, b in zip(meas, meas_d):
+        if ":" in a:
+            assert a.split(":")[0] == b.split(":")[0]
+            assert float(b.split(":")[1]) == pytest.approx(float(a.split(":")[1]), rel=1e-12, abs=1e-15)
+        else:
+            assert a == b
+    assert meas_d[1] == meas[1] and meas_d[5] == meas[5]          # Precision and Coverage: integer sums, same strings
+    assert md.ndcg[10] == pytest.approx(ms.ndcg[10], rel=1e-12)
     mh, _ = results["hogwild"]
     rec = lambda m: float(m.measure[8].split(":")[1])       # Recall@10
     assert abs(rec(mh) - rec(ms)) < 0.005

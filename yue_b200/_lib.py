@@ -85,6 +85,8 @@ SIGNATURES = {
     "yue_timer_stop": (C.c_int, [_H, _f32p]),
     "yue_launch_count": (C.c_int, [_H, _i64p]),
     "yue_rank_stats": (C.c_int, [_H, _i64p, _i64p]),
+    "yue_set_test_set": (C.c_int, [_H, _i64p, _i32p]),
+    "yue_rank_metrics": (C.c_int, [_H, C.c_int, _i32p, _f64p, _i64p]),
     "yue_flush_l2": (C.c_int, [_H]),
 }
 

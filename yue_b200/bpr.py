@@ -37,6 +37,9 @@ class GpuBPRMixin(object):
     #:   yue.device=<int>      CUDA device (default $YUE_DEVICE or 0)
     #:   yue.sgd=hogwild|serial  update schedule (default hogwild; serial = reference order)
     #:   yue.seed=<int>        sampler seed (default: drawn from `random`, unseeded like the reference)
+    #:   yue.metrics=host|device  where evalRanking computes Precision/Recall/F1/MAP/Coverage (default host:
+    #:                         the reference's own summation order; device = one kernel over the lists that are
+    #:                         already on the GPU, for test sets where the Python set operations dominate)
     _engine = None
 
     # ---- plumbing --------------------------------------------------------------------------
@@ -131,10 +134,41 @@ class GpuBPRMixin(object):
             print('The result has been output to ', abspath(outDir), '.')
         fileName = self.config['recommender'] + '@' + currentTime + '-measure' + self.foldInfo + '.txt'
         self.recList = recList
-        self.measure = Measure.rankingMeasure(self.data.testSet, recList, top, self.data.getSize(self.recType))
-        self.ndcg = {n: Measure.NDCG(self.data.testSet, recList, n) for n in top}
+        if self._opt('yue.metrics', 'host') == 'device':
+            self.measure, self.ndcg = self._device_measure(users, top)
+        else:
+            self.measure = Measure.rankingMeasure(self.data.testSet, recList, top, self.data.getSize(self.recType))
+            self.ndcg = {n: Measure.NDCG(self.data.testSet, recList, n) for n in top}
         FileIO.writeFile(outDir, fileName, self.measure)
         print('The result of %s %s:\n%s' % (self.algorName, self.foldInfo, ''.join(self.measure)))
+
+    def _device_measure(self, users, top):
+        """Measure.rankingMeasure's list of strings (evaluation/measure.py:16-41) from the device-side sums
+        over the lists the last rank_topn call left on the GPU."""
+        eng = self._engine
+        getId = self.data.getId
+        rows = [sorted(set(getId(t, self.recType) for t in self.data.testSet[u])) for u in self.data.name2id['user']
+                if u in self.data.testSet]
+        by_user = dict(zip((u for u in self.data.name2id['user'] if u in self.data.testSet), rows))
+        indptr = np.zeros(self.m + 1, dtype=np.int64)
+        for u, r in by_user.items():
+            indptr[getId(u, 'user') + 1] = len(r)
+        np.cumsum(indptr, out=indptr)
+        items = np.zeros(int(indptr[-1]), dtype=np.int32)
+        for u, r in by_user.items():
+            items[indptr[getId(u, 'user')]:indptr[getId(u, 'user') + 1]] = r
+        eng.set_test_set(indptr, items)
+        sums, distinct = eng.rank_metrics(top)
+        B, itemCount = len(users), self.data.getSize(self.recType)
+        print('rank measure...')
+        measure, ndcg = [], {}
+        for k, n in enumerate(top):
+            prec, recall = float(sums[k, 0]) / (B * n), float(sums[k, 1]) / B
+            measure += ['Top ' + str(n) + '\n', 'Precision:' + str(prec) + '\n', 'Recall:' + str(recall) + '\n',
+                        'F1:' + str(Measure.F1(prec, recall)) + '\n', 'MAP:' + str(float(sums[k, 2]) / B) + '\n',
+                        'Coverage:' + str(int(distinct[k]) / float(itemCount)) + '\n']
+            ndcg[n] = float(sums[k, 3]) / B
+        return measure, ndcg
 
     def ranking_performance(self):
         """Top-10 on the first 300 test users (IterativeRecommender.py:175-235), masking the

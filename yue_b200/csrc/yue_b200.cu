@@ -18,6 +18,7 @@
 #include "bpr_sgd.cuh"
 #include "bpr_sgd_blk.cuh"
 #include "rank_exact.cuh"
+#include "rank_metrics.cuh"
 #include "rank_tc.cuh"
 
 using namespace yue;
@@ -164,6 +165,14 @@ struct yue_handle {
     DevBuf<float> rk_scores, pred, rk_part_scores;
     DevBuf<unsigned char> l2buf;
     RankTcState tc;
+    // ranking metrics (K6)
+    int64_t last_rank_B = 0; int last_rank_N = 0;
+    bool have_test = false;
+    DevBuf<int64_t> test_indptr;
+    DevBuf<int32_t> test_items;
+    DevBuf<double> met_terms, met_sums;
+    DevBuf<uint32_t> met_seen;
+    DevBuf<unsigned long long> met_distinct;
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -334,6 +343,7 @@ int yue_destroy(yue_t* h) {
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
     h->l2buf.release();
+    h->test_indptr.release(); h->test_items.release(); h->met_terms.release(); h->met_sums.release(); h->met_seen.release(); h->met_distinct.release();
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -826,9 +836,59 @@ int yue_rank_topn(yue_t* h, const int32_t* users, int64_t B, int N, int algo, in
         rc = yue_rank_exact_device(h, h->rk_users.p, B, N, h->rk_ids.p, h->rk_scores.p);
         if (rc) return rc;
     }
+    h->last_rank_B = B; h->last_rank_N = N;
     CK(cudaMemcpyAsync(ids_out, h->rk_ids.p, (size_t)B * N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(scores_out, h->rk_scores.p, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+// ---- ranking metrics on the device (K6) ------------------------------------------------------
+int yue_set_test_set(yue_t* h, const int64_t* test_indptr, const int32_t* test_items) {
+    REQUIRE(h && test_indptr, YUE_E_ARG, "null argument");
+    REQUIRE(h->have_log, YUE_E_STATE, "call yue_set_interactions first (it fixes m and n)");
+    REQUIRE(test_indptr[0] == 0, YUE_E_ARG, "indptr must start at 0");
+    const int64_t nnz = test_indptr[h->m];
+    REQUIRE(nnz == 0 || test_items, YUE_E_ARG, "null item array");
+    for (int64_t u = 0; u < h->m; ++u) REQUIRE(test_indptr[u + 1] >= test_indptr[u], YUE_E_ARG, "indptr not monotone");
+    CK(cudaSetDevice(h->device));
+    CK(h->test_indptr.resize(h->m + 1)); CK(h->test_items.resize(nnz));
+    CK(cudaMemcpyAsync(h->test_indptr.p, test_indptr, (h->m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (nnz) CK(cudaMemcpyAsync(h->test_items.p, test_items, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_test = true;
+    return YUE_OK;
+}
+
+int yue_rank_metrics(yue_t* h, int n_cuts, const int32_t* cuts, double* sums_out, int64_t* distinct_out) {
+    REQUIRE(h && cuts && sums_out && distinct_out, YUE_E_ARG, "null argument");
+    REQUIRE(h->have_test, YUE_E_STATE, "call yue_set_test_set first");
+    REQUIRE(h->last_rank_B > 0, YUE_E_STATE, "no ranking lists on the device: call yue_rank_topn first");
+    REQUIRE(n_cuts >= 1 && n_cuts <= kMaxCuts, YUE_E_ARG, "1..8 cut-offs");
+    CK(cudaSetDevice(h->device));
+    MetricsParams mp{};
+    mp.ids = h->rk_ids.p; mp.users = h->rk_users.p; mp.B = h->last_rank_B; mp.N = h->last_rank_N;
+    mp.test_indptr = h->test_indptr.p; mp.test_items = h->test_items.p; mp.n_cuts = n_cuts;
+    for (int k = 0; k < n_cuts; ++k) {
+        REQUIRE(cuts[k] >= 1 && cuts[k] <= mp.N, YUE_E_ARG, "a cut-off must be in 1..N of the last yue_rank_topn");
+        mp.cuts[k] = cuts[k];
+    }
+    mp.seen_words = (h->n + 31) / 32;
+    CK(h->met_terms.resize((size_t)n_cuts * 4 * mp.B)); CK(h->met_sums.resize((size_t)n_cuts * 4));
+    CK(h->met_seen.resize((size_t)n_cuts * mp.seen_words)); CK(h->met_distinct.resize(n_cuts));
+    CK(cudaMemsetAsync(h->met_seen.p, 0, (size_t)n_cuts * mp.seen_words * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->met_distinct.p, 0, n_cuts * sizeof(unsigned long long), h->stream));
+    mp.terms = h->met_terms.p; mp.seen = h->met_seen.p;
+    rank_metrics_kernel<<<(unsigned)((mp.B * 32 + 255) / 256), 256, 0, h->stream>>>(mp);
+    metrics_reduce_kernel<<<n_cuts * 4, 1024, 0, h->stream>>>(h->met_terms.p, mp.B, h->met_sums.p);
+    popcount_kernel<<<dim3((unsigned)std::min<int64_t>((mp.seen_words + 255) / 256, 1024), (unsigned)n_cuts), 256, 0, h->stream>>>(h->met_seen.p, mp.seen_words, h->met_distinct.p);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    unsigned long long dist[kMaxCuts];
+    CK(cudaMemcpyAsync(sums_out, h->met_sums.p, (size_t)n_cuts * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(dist, h->met_distinct.p, n_cuts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < n_cuts; ++k) distinct_out[k] = (int64_t)dist[k];
     return YUE_OK;
 }
 

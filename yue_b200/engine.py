@@ -163,6 +163,22 @@ class Engine:
                                         _ptr(ids, C.c_int32), _ptr(scores, C.c_float)))
         return ids, scores
 
+    def set_test_set(self, test_indptr, test_items):
+        """Held-out tracks per local user (sorted unique CSR), for rank_metrics."""
+        test_indptr, test_items = _as(test_indptr, np.int64), _as(test_items, np.int32)
+        if len(test_indptr) != self.m + 1 or len(test_items) != test_indptr[-1]:
+            raise ValueError("test CSR does not match m=%d" % self.m)
+        self._ck(self.lib.yue_set_test_set(self.h, _ptr(test_indptr, C.c_int64), _ptr(test_items, C.c_int32)))
+
+    def rank_metrics(self, cuts):
+        """Metrics of the lists of the last rank_topn call, per cut-off n: dict with hits (int), precision,
+        recall, F1, MAP, NDCG, distinct (coverage numerator) -- evaluation/measure.py semantics."""
+        cuts = _as(cuts, np.int32)
+        sums = np.zeros((len(cuts), 4), dtype=np.float64)
+        distinct = np.zeros(len(cuts), dtype=np.int64)
+        self._ck(self.lib.yue_rank_metrics(self.h, len(cuts), _ptr(cuts, C.c_int32), _ptr(sums, C.c_double), _ptr(distinct, C.c_int64)))
+        return sums, distinct
+
     # -- multi-GPU plumbing ----------------------------------------------------------------
     def q_snapshot(self):
         self._ck(self.lib.yue_q_snapshot(self.h))
