@@ -83,6 +83,19 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n,
                                const int64_t* ev_indptr, const int32_t* ev_items,
                                const int64_t* uq_indptr, const int32_t* uq_items);
 
+/* Builds the same arrays ON THE DEVICE from the events in file order: replaces the
+ * array-building half of Record.preprocess (data/record.py:138-202: userRecord grouping 147-165,
+ * testSet with the training pairs removed 182-202) and BPR.py:32-45 for logs whose users and tracks are
+ * already numbered (ids by first appearance stay with the host, record.py:138-146).  ev_user[E],
+ * ev_item[E] in file order, is_test[E] != 0 marks held-out events (NULL: none).  Afterwards the handle is
+ * in the state yue_set_interactions + yue_set_test_set would leave it in; the getters return the arrays
+ * (sizes from yue_interaction_sizes; any pointer may be NULL). */
+int yue_ingest_events(yue_t* h, int64_t m, int64_t n, int64_t E, const int32_t* ev_user,
+                      const int32_t* ev_item, const uint8_t* is_test);
+int yue_interaction_sizes(yue_t* h, int64_t* m, int64_t* n, int64_t* T, int64_t* nnz, int64_t* n_test);
+int yue_get_interactions(yue_t* h, int64_t* ev_indptr, int32_t* ev_items, int64_t* uq_indptr, int32_t* uq_items);
+int yue_get_test_set(yue_t* h, int64_t* test_indptr, int32_t* test_items);
+
 /* Replaces IterativeRecommender.initModel's tables (IterativeRecommender.py:36-39) on the
  * device: P is [m_local,k], Q is [n,k].  get copies the current tables back (either pointer
  * may be NULL) -- buildModel leaves self.P / self.Q on the host (BPR.py:127-128). */

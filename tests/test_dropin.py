@@ -124,7 +124,8 @@ def test_c1_end_to_end_through_the_class_api(tmp_path):
     for mode in ("serial", "hogwild", "serial-device-metrics"):
         vals = conf_values(tmp_path / mode, extra={"record": str(log_path), "yue.sgd": mode.split("-")[0], "yue.seed": "77",
                                                    "num.max.iter": "2",
-                                                   "yue.metrics": "device" if mode.endswith("metrics") else "host"})
+                                                   "yue.metrics": "device" if mode.endswith("metrics") else "host",
+                                                   "yue.ingest": "device" if mode.endswith("metrics") else "host"})
         random.seed(5)                       # DataSplit uses the global stream (tool/dataSplit.py:15)
         np.random.seed(11)                   # initModel uses the global numpy stream
         with redirect_stdout(io.StringIO()):

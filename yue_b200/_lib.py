@@ -86,6 +86,10 @@ SIGNATURES = {
     "yue_launch_count": (C.c_int, [_H, _i64p]),
     "yue_rank_stats": (C.c_int, [_H, _i64p, _i64p]),
     "yue_set_test_set": (C.c_int, [_H, _i64p, _i32p]),
+    "yue_ingest_events": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, C.POINTER(C.c_uint8)]),
+    "yue_interaction_sizes": (C.c_int, [_H, _i64p, _i64p, _i64p, _i64p, _i64p]),
+    "yue_get_interactions": (C.c_int, [_H, _i64p, _i32p, _i64p, _i32p]),
+    "yue_get_test_set": (C.c_int, [_H, _i64p, _i32p]),
     "yue_rank_metrics": (C.c_int, [_H, C.c_int, _i32p, _f64p, _i64p]),
     "yue_flush_l2": (C.c_int, [_H]),
 }

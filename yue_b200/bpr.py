@@ -37,6 +37,8 @@ class GpuBPRMixin(object):
     #:   yue.device=<int>      CUDA device (default $YUE_DEVICE or 0)
     #:   yue.sgd=hogwild|serial  update schedule (default hogwild; serial = reference order)
     #:   yue.seed=<int>        sampler seed (default: drawn from `random`, unseeded like the reference)
+    #:   yue.ingest=host|device   where the array form of the log (event CSR, play sets, test sets) is built: host =
+    #:                         numpy on Record's dicts; device = yue_ingest_events on the numbered events (K0)
     #:   yue.metrics=host|device  where evalRanking computes Precision/Recall/F1/MAP/Coverage (default host:
     #:                         the reference's own summation order; device = one kernel over the lists that are
     #:                         already on the GPU, for test sets where the Python set operations dominate)
@@ -51,6 +53,23 @@ class GpuBPRMixin(object):
             dev = int(self._opt('yue.device', os.environ.get('YUE_DEVICE', '0')))
             self._engine = Engine(dev)
             arrays = getattr(self.data, 'interaction_arrays', None)
+            self._test_on_device = False
+            if self._opt('yue.ingest', 'host') == 'device':
+                # Record's containers as numbered events: every training event per user in file order
+                # (userRecord, data/record.py:147-150), then the held-out pairs (testSet, 182-192)
+                uid, tid = self.data.name2id['user'], self.data.name2id[self.recType]
+                tr_u = [uid[u] for u, evs in self.data.userRecord.items() for _ in evs]
+                tr_i = [tid[e[self.recType]] for evs in self.data.userRecord.values() for e in evs]
+                te_u = [uid[u] for u, held in self.data.testSet.items() for _ in held]
+                te_i = [tid[t] for held in self.data.testSet.values() for t in held]
+                ev_user = np.array(tr_u + te_u, dtype=np.int32)
+                ev_item = np.array(tr_i + te_i, dtype=np.int32)
+                flag = np.zeros(len(ev_user), dtype=np.uint8)
+                flag[len(tr_u):] = 1
+                self._engine.ingest_events(self.m, self.n, ev_user, ev_item, flag)
+                self._test_on_device = True
+                self._synced = (None, None)
+                return self._engine
             if arrays is not None:
                 ev_indptr, ev_items, uq_indptr, uq_items = arrays(self.recType)
             else:                       # the reference's Record: build the arrays from its dicts
@@ -146,6 +165,8 @@ class GpuBPRMixin(object):
         """Measure.rankingMeasure's list of strings (evaluation/measure.py:16-41) from the device-side sums
         over the lists the last rank_topn call left on the GPU."""
         eng = self._engine
+        if getattr(self, '_test_on_device', False):
+            return self._format_device_measure(users, top)
         getId = self.data.getId
         rows = [sorted(set(getId(t, self.recType) for t in self.data.testSet[u])) for u in self.data.name2id['user']
                 if u in self.data.testSet]
@@ -158,6 +179,10 @@ class GpuBPRMixin(object):
         for u, r in by_user.items():
             items[indptr[getId(u, 'user')]:indptr[getId(u, 'user') + 1]] = r
         eng.set_test_set(indptr, items)
+        return self._format_device_measure(users, top)
+
+    def _format_device_measure(self, users, top):
+        eng = self._engine
         sums, distinct = eng.rank_metrics(top)
         B, itemCount = len(users), self.data.getSize(self.recType)
         print('rank measure...')

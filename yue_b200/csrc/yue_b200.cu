@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <functional>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -17,6 +19,7 @@
 
 #include "bpr_sgd.cuh"
 #include "bpr_sgd_blk.cuh"
+#include "ingest.cuh"
 #include "rank_exact.cuh"
 #include "rank_metrics.cuh"
 #include "rank_tc.cuh"
@@ -115,7 +118,7 @@ struct yue_handle {
     int hot_div = 128;
     int hot_shard_div = 40;           // blocked kernel: a track played by more than 1/hot_shard_div of the events gets two rows
     int n_hot = 0;
-    std::vector<int32_t> h_hot_counts;   // per hot slot
+    std::vector<int32_t> h_hot_counts, h_hot_items;   // per hot slot
     int hot_meta_cap = 0, hot_meta_ld = 0;   // what the current hot_meta / hot_shards were built for
     int64_t hot_extra_rows = 0;
     int sgd_kernel = 2;               // YUE_SGD_KERNEL: 1 = per-triplet kernel, 2 = blocked kernel where it applies
@@ -168,6 +171,7 @@ struct yue_handle {
     // ranking metrics (K6)
     int64_t last_rank_B = 0; int last_rank_N = 0;
     bool have_test = false;
+    int64_t n_test = 0;
     DevBuf<int64_t> test_indptr;
     DevBuf<int32_t> test_items;
     DevBuf<double> met_terms, met_sums;
@@ -363,31 +367,21 @@ int yue_host_alloc(size_t bytes, void** out) {
 }
 int yue_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? YUE_OK : YUE_E_CUDA; }
 
-int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t user_begin, int64_t event_base,
-                               const int64_t* ev_indptr, const int32_t* ev_items,
-                               const int64_t* uq_indptr, const int32_t* uq_items) {
-    REQUIRE(h && ev_indptr && uq_indptr, YUE_E_ARG, "null argument");
-    REQUIRE(m_local >= 0 && n > 0 && n < (int64_t)1 << 31 && m_local < (int64_t)1 << 31, YUE_E_ARG, "m/n out of range");
-    REQUIRE(ev_indptr[0] == 0 && uq_indptr[0] == 0, YUE_E_ARG, "indptr must start at 0 (rebase shards)");
-    const int64_t T = ev_indptr[m_local], nnz = uq_indptr[m_local];
-    REQUIRE((T == 0 || ev_items) && (nnz == 0 || uq_items), YUE_E_ARG, "null item array");
+// second half of yue_set_interactions / yue_ingest_events: the four arrays are on the device (h->m, n, T, nnz set),
+// ev_indptr / uq_indptr are their host copies.  Validates, plans segments and work items, selects the hot tracks.
+static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t* uq_indptr) {
+    const int64_t m_local = h->m, n = h->n, T = h->T;
     for (int64_t u = 0; u < m_local; ++u) {
         REQUIRE(ev_indptr[u + 1] >= ev_indptr[u] && uq_indptr[u + 1] >= uq_indptr[u], YUE_E_ARG, "indptr not monotone");
         // a user who played the whole catalog has no negative: the reference would spin forever (BPR.py:47-48)
         REQUIRE(uq_indptr[u + 1] - uq_indptr[u] < n || ev_indptr[u + 1] == ev_indptr[u], YUE_E_ARG,
-                "user " + std::to_string(u + user_begin) + " played every track: no negative exists");
+                "user " + std::to_string(u + h->user_begin) + " played every track: no negative exists");
     }
-    CK(cudaSetDevice(h->device));
-    h->m = m_local; h->n = n; h->T = T; h->nnz = nnz; h->user_begin = user_begin; h->event_base = event_base;
-    CK(h->ev_indptr.resize(m_local + 1)); CK(h->uq_indptr.resize(m_local + 1));
-    CK(h->ev_items.resize(T)); CK(h->uq_items.resize(nnz));
-    CK(cudaMemcpyAsync(h->ev_indptr.p, ev_indptr, (m_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->uq_indptr.p, uq_indptr, (m_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    if (T) CK(cudaMemcpyAsync(h->ev_items.p, ev_items, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    if (nnz) CK(cudaMemcpyAsync(h->uq_items.p, uq_items, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     h->h_ev_indptr.assign(ev_indptr, ev_indptr + m_local + 1);
     h->h_uq_indptr.assign(uq_indptr, uq_indptr + m_local + 1);
     h->have_ev_user = false;
+    h->have_log = false;
+    h->last_rank_B = 0;
 
     // concurrency: at most one resident wave, fewer warps on small logs (bounds Hogwild staleness
     // and keeps the in-flight window a small fraction of the users)
@@ -404,6 +398,7 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     // hot tracks: device histogram of the positives, top hot_max by count on the host, then the hot
     // positives of the device copy of ev_items are re-labelled -slot-1 (see SgdParams::hot_items)
     h->n_hot = 0;
+    h->h_hot_items.clear();
     if (T > 0 && h->hot_max > 0) {
         CK(h->item_counts.resize(n));
         CK(cudaMemsetAsync(h->item_counts.p, 0, n * sizeof(int32_t), h->stream));
@@ -422,6 +417,7 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
         h->n_hot = (int)cand.size();
         h->h_hot_counts.clear();
         for (int32_t t : cand) h->h_hot_counts.push_back(counts[t]);
+        h->h_hot_items = cand;
         h->hot_meta_cap = 0;
         if (h->n_hot) {
             std::vector<int32_t> slot((size_t)n, -1);
@@ -455,9 +451,173 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     return YUE_OK;
 }
 
+int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t user_begin, int64_t event_base,
+                               const int64_t* ev_indptr, const int32_t* ev_items,
+                               const int64_t* uq_indptr, const int32_t* uq_items) {
+    REQUIRE(h && ev_indptr && uq_indptr, YUE_E_ARG, "null argument");
+    REQUIRE(m_local >= 0 && n > 0 && n < (int64_t)1 << 31 && m_local < (int64_t)1 << 31, YUE_E_ARG, "m/n out of range");
+    REQUIRE(ev_indptr[0] == 0 && uq_indptr[0] == 0, YUE_E_ARG, "indptr must start at 0 (rebase shards)");
+    const int64_t T = ev_indptr[m_local], nnz = uq_indptr[m_local];
+    REQUIRE((T == 0 || ev_items) && (nnz == 0 || uq_items), YUE_E_ARG, "null item array");
+    REQUIRE(T >= 0 && nnz >= 0, YUE_E_ARG, "indptr not monotone");
+    CK(cudaSetDevice(h->device));
+    h->m = m_local; h->n = n; h->T = T; h->nnz = nnz; h->user_begin = user_begin; h->event_base = event_base;
+    h->have_test = false;              // a new log: the held-out set of the old one no longer applies
+    CK(h->ev_indptr.resize(m_local + 1)); CK(h->uq_indptr.resize(m_local + 1));
+    CK(h->ev_items.resize(T)); CK(h->uq_items.resize(nnz));
+    CK(cudaMemcpyAsync(h->ev_indptr.p, ev_indptr, (m_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->uq_indptr.p, uq_indptr, (m_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (T) CK(cudaMemcpyAsync(h->ev_items.p, ev_items, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (nnz) CK(cudaMemcpyAsync(h->uq_items.p, uq_items, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    return finish_interactions(h, ev_indptr, uq_indptr);
+}
+
 int yue_set_interactions(yue_t* h, int64_t m, int64_t n, const int64_t* ev_indptr, const int32_t* ev_items,
                          const int64_t* uq_indptr, const int32_t* uq_items) {
     return yue_set_interactions_shard(h, m, n, 0, 0, ev_indptr, ev_items, uq_indptr, uq_items);
+}
+
+
+// ---- K0: array form of the play log built on the device (ingest.cuh) --------------------------------
+namespace {
+struct CubTemp {
+    DevBuf<unsigned char> buf;
+    cudaError_t ensure(size_t bytes) { return buf.resize(bytes + 256); }
+};
+}  // namespace
+
+int yue_ingest_events(yue_t* h, int64_t m, int64_t n, int64_t E, const int32_t* ev_user, const int32_t* ev_item,
+                      const uint8_t* is_test) {
+    REQUIRE(h && (E == 0 || (ev_user && ev_item)), YUE_E_ARG, "null argument");
+    REQUIRE(m >= 0 && n > 0 && n < (int64_t)1 << 31 && m < (int64_t)1 << 31 && E >= 0 && E < (int64_t)1 << 31, YUE_E_ARG, "m/n/E out of range");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t Ez = (size_t)std::max<int64_t>(E, 1);
+    DevBuf<int32_t> du, di, tu, ti, su, xu, xi;
+    DevBuf<uint8_t> dt, f_train, f_test, f_keep;
+    DevBuf<uint64_t> k0, k1, k2;
+    DevBuf<int> counts;        // [0] train events, [1] unique train pairs, [2] test events, [3] unique test pairs, [4] kept test pairs, [5] bad
+    CubTemp tmp;
+    struct Free { std::vector<std::function<void()>> fs; ~Free() { for (auto& f : fs) f(); } } guard;
+    guard.fs = {[&] { du.release(); di.release(); tu.release(); ti.release(); su.release(); xu.release(); xi.release(); },
+                [&] { dt.release(); f_train.release(); f_test.release(); f_keep.release(); },
+                [&] { k0.release(); k1.release(); k2.release(); counts.release(); tmp.buf.release(); }};
+    CK(du.resize(Ez)); CK(di.resize(Ez)); CK(tu.resize(Ez)); CK(ti.resize(Ez)); CK(su.resize(Ez)); CK(xu.resize(Ez)); CK(xi.resize(Ez));
+    CK(dt.resize(Ez)); CK(f_train.resize(Ez)); CK(f_test.resize(Ez)); CK(f_keep.resize(Ez));
+    CK(k0.resize(Ez)); CK(k1.resize(Ez)); CK(k2.resize(Ez)); CK(counts.resize(8));
+    CK(cudaMemsetAsync(counts.p, 0, 8 * sizeof(int), st));
+    const int grid = (int)std::min<int64_t>((E + 255) / 256 + 1, (int64_t)h->sm_count * 16);
+    int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (E) {
+        CK(cudaMemcpyAsync(du.p, ev_user, E * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(di.p, ev_item, E * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (is_test) CK(cudaMemcpyAsync(dt.p, is_test, E * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
+        ingest_range_check_kernel<<<grid, 256, 0, st>>>(du.p, di.p, E, m, n, counts.p + 5);
+        ingest_flags_kernel<<<grid, 256, 0, st>>>(is_test ? dt.p : nullptr, E, f_train.p, f_test.p);
+        h->launches += 2;
+        // temp storage: the largest request of the primitives used below
+        size_t need = 0, b = 0;
+        cub::DeviceSelect::Flagged(nullptr, b, du.p, f_train.p, tu.p, counts.p, (int)E, st); need = std::max(need, b);
+        cub::DeviceRadixSort::SortPairs(nullptr, b, tu.p, su.p, ti.p, xi.p, (int)E, 0, 32, st); need = std::max(need, b);
+        cub::DeviceRadixSort::SortKeys(nullptr, b, k0.p, k1.p, (int)E, 0, 64, st); need = std::max(need, b);
+        cub::DeviceSelect::Unique(nullptr, b, k1.p, k2.p, counts.p, (int)E, st); need = std::max(need, b);
+        cub::DeviceSelect::Flagged(nullptr, b, k1.p, f_keep.p, k2.p, counts.p, (int)E, st); need = std::max(need, b);
+        CK(tmp.ensure(need));
+        size_t tb = tmp.buf.n;
+        // training events in file order
+        CK(cub::DeviceSelect::Flagged(tmp.buf.p, tb, du.p, f_train.p, tu.p, counts.p + 0, (int)E, st));
+        CK(cub::DeviceSelect::Flagged(tmp.buf.p, tb, di.p, f_train.p, ti.p, counts.p + 0, (int)E, st));
+        CK(cub::DeviceSelect::Flagged(tmp.buf.p, tb, du.p, f_test.p, xu.p, counts.p + 2, (int)E, st));
+        CK(cub::DeviceSelect::Flagged(tmp.buf.p, tb, di.p, f_test.p, xi.p, counts.p + 2, (int)E, st));
+        h->launches += 8;
+        CK(cudaMemcpyAsync(hc, counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        REQUIRE(hc[5] == 0, YUE_E_ARG, "an event names a user or track outside [0, m) x [0, n)");
+    }
+    const int64_t T = hc[0], Et = hc[2];
+    h->m = m; h->n = n; h->T = T; h->user_begin = 0; h->event_base = 0;
+    CK(h->ev_indptr.resize(m + 1)); CK(h->uq_indptr.resize(m + 1)); CK(h->test_indptr.resize(m + 1));
+    CK(h->ev_items.resize(T));
+    size_t tb = tmp.buf.n;
+    if (T) {
+        // ev: stable sort by user keeps the file order inside a user (BPR.py:42-45)
+        CK(cub::DeviceRadixSort::SortPairs(tmp.buf.p, tb, tu.p, su.p, ti.p, h->ev_items.p, (int)T, 0, 32, st));
+        // uq: sorted unique (user, track) pairs
+        ingest_keys_kernel<<<grid, 256, 0, st>>>(tu.p, ti.p, T, k0.p);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.buf.p, tb, k0.p, k1.p, (int)T, 0, 64, st));
+        CK(cub::DeviceSelect::Unique(tmp.buf.p, tb, k1.p, k2.p, counts.p + 1, (int)T, st));
+        h->launches += 6;
+    }
+    ingest_indptr_from_users_kernel<<<(unsigned)((m + 256) / 256), 256, 0, st>>>(su.p, T, m, h->ev_indptr.p);
+    ++h->launches;
+    CK(cudaMemcpyAsync(hc + 1, counts.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t nnz = hc[1];
+    h->nnz = nnz;
+    CK(h->uq_items.resize(nnz));
+    if (nnz) { ingest_low_words_kernel<<<grid, 256, 0, st>>>(k2.p, nnz, h->uq_items.p); ++h->launches; }
+    ingest_indptr_from_keys_kernel<<<(unsigned)((m + 256) / 256), 256, 0, st>>>(k2.p, nnz, m, h->uq_indptr.p);
+    ++h->launches;
+    // test set: unique held-out pairs that are not training pairs (record.py:182-202); k2 = training pairs stays live
+    int64_t n_test = 0;
+    if (Et) {
+        ingest_keys_kernel<<<grid, 256, 0, st>>>(xu.p, xi.p, Et, k0.p);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.buf.p, tb, k0.p, k1.p, (int)Et, 0, 64, st));
+        CK(cub::DeviceSelect::Unique(tmp.buf.p, tb, k1.p, k0.p, counts.p + 3, (int)Et, st));
+        CK(cudaMemcpyAsync(hc + 3, counts.p + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int64_t nt = hc[3];
+        ingest_antijoin_kernel<<<grid, 256, 0, st>>>(k0.p, nt, k2.p, nnz, f_keep.p);
+        CK(cub::DeviceSelect::Flagged(tmp.buf.p, tb, k0.p, f_keep.p, k1.p, counts.p + 4, (int)nt, st));
+        CK(cudaMemcpyAsync(hc + 4, counts.p + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_test = hc[4];
+        h->launches += 7;
+    }
+    CK(h->test_items.resize(n_test));
+    if (n_test) { ingest_low_words_kernel<<<grid, 256, 0, st>>>(k1.p, n_test, h->test_items.p); ++h->launches; }
+    ingest_indptr_from_keys_kernel<<<(unsigned)((m + 256) / 256), 256, 0, st>>>(k1.p, n_test, m, h->test_indptr.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    h->have_test = true;
+    h->n_test = n_test;
+    std::vector<int64_t> hev((size_t)m + 1), huq((size_t)m + 1);
+    CK(cudaMemcpyAsync(hev.data(), h->ev_indptr.p, (m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(huq.data(), h->uq_indptr.p, (m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return finish_interactions(h, hev.data(), huq.data());
+}
+
+int yue_interaction_sizes(yue_t* h, int64_t* m, int64_t* n, int64_t* T, int64_t* nnz, int64_t* n_test) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "interactions not set");
+    if (m) *m = h->m;
+    if (n) *n = h->n;
+    if (T) *T = h->T;
+    if (nnz) *nnz = h->nnz;
+    if (n_test) *n_test = h->have_test ? h->n_test : 0;
+    return YUE_OK;
+}
+
+int yue_get_interactions(yue_t* h, int64_t* ev_indptr, int32_t* ev_items, int64_t* uq_indptr, int32_t* uq_items) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "interactions not set");
+    CK(cudaSetDevice(h->device));
+    if (ev_indptr) CK(cudaMemcpyAsync(ev_indptr, h->ev_indptr.p, (h->m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (uq_indptr) CK(cudaMemcpyAsync(uq_indptr, h->uq_indptr.p, (h->m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (ev_items && h->T) CK(cudaMemcpyAsync(ev_items, h->ev_items.p, h->T * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (uq_items && h->nnz) CK(cudaMemcpyAsync(uq_items, h->uq_items.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ev_items)                       // hot positives are stored re-labelled -slot-1 on the device
+        for (int64_t e = 0; e < h->T; ++e) if (ev_items[e] < 0) ev_items[e] = h->h_hot_items[(size_t)(-ev_items[e] - 1)];
+    return YUE_OK;
+}
+
+int yue_get_test_set(yue_t* h, int64_t* test_indptr, int32_t* test_items) {
+    REQUIRE(h && h->have_log && h->have_test, YUE_E_STATE, "no test set on the device");
+    CK(cudaSetDevice(h->device));
+    if (test_indptr) CK(cudaMemcpyAsync(test_indptr, h->test_indptr.p, (h->m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (test_items && h->n_test) CK(cudaMemcpyAsync(test_items, h->test_items.p, h->n_test * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
 }
 
 int yue_set_factors(yue_t* h, int k, const float* P, const float* Q) {
@@ -857,6 +1017,7 @@ int yue_set_test_set(yue_t* h, const int64_t* test_indptr, const int32_t* test_i
     if (nnz) CK(cudaMemcpyAsync(h->test_items.p, test_items, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->have_test = true;
+    h->n_test = nnz;
     return YUE_OK;
 }
 

@@ -92,6 +92,40 @@ class Engine:
             _ptr(uq_indptr, C.c_int64), _ptr(uq_items, C.c_int32)))
         self.m, self.n, self.T = int(m), int(n), int(ev_indptr[-1])
 
+    def ingest_events(self, m, n, ev_user, ev_item, is_test=None):
+        """Array form of the log built on the device from events in file order (yue_ingest_events)."""
+        ev_user, ev_item = _as(ev_user, np.int32), _as(ev_item, np.int32)
+        if len(ev_user) != len(ev_item):
+            raise ValueError("ev_user and ev_item differ in length")
+        flag = None
+        if is_test is not None:
+            is_test = _as(is_test, np.uint8)
+            if len(is_test) != len(ev_user):
+                raise ValueError("is_test length")
+            flag = _ptr(is_test, C.c_uint8)
+        self._ck(self.lib.yue_ingest_events(self.h, m, n, len(ev_user), _ptr(ev_user, C.c_int32), _ptr(ev_item, C.c_int32), flag))
+        self.m, self.n = int(m), int(n)
+        self.T = self.interaction_sizes()[2]
+
+    def interaction_sizes(self):
+        v = [C.c_int64() for _ in range(5)]
+        self._ck(self.lib.yue_interaction_sizes(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)          # m, n, T, nnz, n_test
+
+    def get_interactions(self):
+        m, n, T, nnz, _ = self.interaction_sizes()
+        ev_indptr, uq_indptr = np.empty(m + 1, np.int64), np.empty(m + 1, np.int64)
+        ev_items, uq_items = np.empty(T, np.int32), np.empty(nnz, np.int32)
+        self._ck(self.lib.yue_get_interactions(self.h, _ptr(ev_indptr, C.c_int64), _ptr(ev_items, C.c_int32),
+                                               _ptr(uq_indptr, C.c_int64), _ptr(uq_items, C.c_int32)))
+        return ev_indptr, ev_items, uq_indptr, uq_items
+
+    def get_test_set(self):
+        m, _, _, _, nt = self.interaction_sizes()
+        indptr, items = np.empty(m + 1, np.int64), np.empty(nt, np.int32)
+        self._ck(self.lib.yue_get_test_set(self.h, _ptr(indptr, C.c_int64), _ptr(items, C.c_int32)))
+        return indptr, items
+
     def set_factors(self, P, Q):
         P, Q = _as(P, np.float32), _as(Q, np.float32)
         if P.shape[0] != self.m or Q.shape[0] != self.n or P.shape[1] != Q.shape[1]:
