@@ -202,7 +202,7 @@ def run_native(args):
     trainer = None
     if world > 1:                                   # user-sharded: dQ all-reduced once per step (yue_b200/sharding.py)
         from yue_b200.sharding import ShardedTrainer
-        trainer = ShardedTrainer(eng, dist, torch.device("cuda", local))
+        trainer = ShardedTrainer(eng, dist, torch.device("cuda", local), sub_epochs=args.sub_epochs)
 
     def step(epoch, want_loss=False):
         if trainer is not None:
@@ -250,6 +250,18 @@ def run_native(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("bpr_sgd_kernel_dram_bytes_per_launch")
 
+    # ---- config C5: APR epoch (adversarial BPR, fused per-triplet perturbation), APR.conf hyper-parameters ----
+    apr = None
+    if world == 1 and not args.no_apr:
+        ams = []
+        for k in range(4):
+            eng.sync()
+            eng.timer_start()
+            eng.apr_epoch(0.003, 0.002, 0.01, 0.5, 2.0, SEED, 3000 + k, 0, mode, want_loss=False)
+            ams.append(eng.timer_stop())
+        apr = {"metric": "apr_triplets_per_sec", "value": T / (min(ams[1:]) * 1e-3), "ms_per_epoch": min(ams[1:]),
+               "workload": "C5: APR d=64 on the C2 log, eps 0.5, regA 2, lr 0.003 (config/APR.conf)", "kernel": "bpr_sgd_kernel<APR>"}
+
     # ---- e2e: same step through the C ABI with host buffers ---------------------------------
     h2d = log.ev_indptr.nbytes + log.ev_items.nbytes + log.uq_indptr.nbytes + log.uq_items.nbytes + pP.nbytes + pQ.nbytes
     d2h = pP.nbytes + pQ.nbytes + 8
@@ -286,7 +298,7 @@ def run_native(args):
             "config": {"workload": wl["name"], "d": D, "triplets_per_step_per_gpu": T, "lr": LR,
                        "reg": [REG_U, REG_I], "sgd_mode": "hogwild_" + ("store" if mode == MODE_HOGWILD_STORE else "atomic_delta"),
                        "l2": "inputs exceed L2 (P 256 MB + log 400 MB per step; Q 51 MB is L2-resident by nature)",
-                       "parallelism": "user-sharded, Q replicated, 1 all-reduce of dQ per step" if world > 1 else "single GPU"},
+                       "parallelism": ("user-sharded, Q replicated, %d all-reduce(s) of dQ per step" % args.sub_epochs) if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "what": "set_interactions + set_factors (pinned) + bpr_epoch + frob2 + get_factors"},
             "gpu_launches": int(launches),
@@ -297,10 +309,14 @@ def run_native(args):
                          "algorithmic_bytes_per_launch": BYTES_PER_TRIPLET * T},
             "final_loss": loss,
         }
+        if apr:
+            out["apr"] = apr
 
     # ---- secondary metric: full-catalog masked top-10 (config C4 shape, bounded user block) --
-    if not args.no_rank and world == 1:
-        out["ranking"] = bench_ranking(eng, args, bf16_peak)
+    if not args.no_rank:
+        rk = bench_ranking(eng, args, bf16_peak, rank, world, dist if world > 1 else None)
+        if rank == 0:
+            out["ranking"] = rk
 
     # ---- cpu_baseline (rank 0, N = 1 only) -----------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -317,16 +333,20 @@ def run_native(args):
         dist.destroy_process_group()
 
 
-def bench_ranking(eng, args, bf16_peak):
-    """Masked top-10 against a 2M-track catalog (config C4), users/s on one GPU: one full wave of
-    148 CTAs x 128 users, then all of C4's 1 M users in one call.  Host ids in, host ids+scores out."""
+def bench_ranking(eng, args, bf16_peak, rank=0, world=1, dist=None):
+    """Masked top-10 against a 2M-track catalog (config C4), users/s: one full wave of 148 CTAs x 128
+    users, then all of C4's 1 M users.  Host ids in, host ids+scores out.  With N ranks the users are
+    sharded by contiguous block, Q is replicated, no collective on the data path; the time
+    is the max over ranks."""
     import torch
     from yue_b200 import synth
     from yue_b200.engine import RANK_AUTO, PinnedArray
     n = 2_000_000 if not args.small else 100_000
-    m = args.rank_users
-    indptr, uq = synth.mask_csr_torch(m, n, 50, SEED + 4)
-    P, Q = synth.init_factors(m, n, D, SEED + 4)
+    m_total = args.rank_users
+    m = m_total * (rank + 1) // world - m_total * rank // world          # this rank's block of users
+    indptr, uq = synth.mask_csr_torch(m, n, 50, SEED + 4 + 100 * rank)
+    P, _ = synth.init_factors(m, 1, D, SEED + 4 + 100 * rank)
+    _, Q = synth.init_factors(1, n, D, SEED + 4)
     eng.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), indptr, uq)
     eng.set_factors(P, Q)
     torch.cuda.empty_cache()
@@ -338,13 +358,21 @@ def bench_ranking(eng, args, bf16_peak):
     for key, B, reps in (("one_wave", min(m, 18944), 3), ("c4_full", m, 2)):
         times = []
         for _ in range(reps):
+            if dist is not None:
+                dist.barrier()
             t0 = time.perf_counter()
             eng.rank_topn(users[:B], 10, RANK_AUTO, ids.array[:B], sc.array[:B])
-            times.append(time.perf_counter() - t0)
+            dt = time.perf_counter() - t0
+            if dist is not None:                       # max over ranks
+                tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            times.append(dt)
         t = min(times)
-        flops = 2.0 * B * n * D
-        out[key] = {"users": B, "tracks": n, "seconds": t, "users_per_sec": B / t, "dense_tflops": flops / t / 1e12,
-                    "frac_of_bf16_peak": flops / t / 1e12 / bf16_peak}
+        Ball = B * world if key == "one_wave" else m_total
+        flops = 2.0 * Ball * n * D
+        out[key] = {"users": Ball, "tracks": n, "seconds": t, "users_per_sec": Ball / t, "dense_tflops": flops / t / 1e12,
+                    "frac_of_bf16_peak": flops / t / 1e12 / (bf16_peak * world), "fallback_and_spilled_rows_rank0": list(eng.rank_stats())}
     # K6: the metrics of those lists against a synthetic held-out set (5 tracks per user), on the device
     te_indptr, te_items = synth.mask_csr_torch(m, n, 5, SEED + 5)
     eng.set_test_set(te_indptr, te_items)
@@ -352,7 +380,7 @@ def bench_ranking(eng, args, bf16_peak):
     sums, distinct = eng.rank_metrics([5, 10])
     out["metrics_seconds"] = time.perf_counter() - t0
     out["value"] = out["c4_full"]["users_per_sec"]
-    out["workload"] = "C4: top-10 of %d users x %d tracks, d=64, ~50 masked tracks/user, one GPU" % (m, n)
+    out["workload"] = "C4: top-10 of %d users x %d tracks, d=64, ~50 masked tracks/user, %d GPU(s), users sharded by block" % (m_total, n, world)
     return out
 
 
@@ -364,8 +392,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--small", action="store_true", help="debug-size workload (not a bench number)")
     ap.add_argument("--sgd-mode", default="atomic", choices=["atomic", "store"])
+    ap.add_argument("--sub-epochs", type=int, default=1, help="multi-GPU: Q-delta all-reduces per epoch")
     ap.add_argument("--no-rank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-apr", action="store_true")
     ap.add_argument("--rank-users", type=int, default=1_000_000)   # config C4: 1 M users
     args = ap.parse_args()
     if args.warmup < 3 and not args.small:

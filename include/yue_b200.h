@@ -116,6 +116,12 @@ int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot,
 int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI,
                   uint64_t seed, uint32_t epoch, int mode, double* loss_out);
 
+/* One SUB-EPOCH: the part-th of n_parts consecutive ranges of the epoch's work (users in stream order).
+ * Running part = 0..n_parts-1 in turn is the epoch; the multi-GPU trainer reconciles Q between parts
+ * (one all-reduce of the Q deltas per sub-epoch).  *loss_out is the part's share. */
+int yue_bpr_epoch_part(yue_t* h, double lr, double regU, double regI,
+                       uint64_t seed, uint32_t epoch, int mode, int part, int n_parts, double* loss_out);
+
 /* Same update on a caller-supplied triplet stream (parity hook for the "same triplet
  * stream" check of north_star; also the building block for APR-style batches). */
 int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T,

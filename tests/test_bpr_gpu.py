@@ -312,3 +312,26 @@ def test_blocked_kernel_hot_table_lr0_and_conservation(monkeypatch, d):
     assert np.abs((Qt - Q) - (Qd - Q)).max() < 2e-3 * np.abs(Qd - Q).max()
     assert np.abs((Pt - P) - (Pd - P)).max() < 5e-2 * np.abs(Pd - P).max()
     assert np.linalg.norm(Qt - Q) == pytest.approx(np.linalg.norm(Qd - Q), rel=1e-3)
+
+
+def test_sub_epochs_compose_to_the_epoch(engine):
+    """yue_bpr_epoch_part: parts 0..S-1 in turn are the epoch -- bit-identical in the serial order, and
+    in the throughput mode every event is applied exactly once (lr = 0 loss is the full sum)."""
+    log = synth.power_law_log(900, 700, 30000, seed=9)
+    P, Q = synth.init_factors(log.m, log.n, 64, seed=4)
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    engine.set_factors(P, Q)
+    full = engine.bpr_epoch(0.05, 0.01, 0.01, 3, 0, MODE_SERIAL)
+    Pf, Qf = engine.get_factors()
+    for S in (2, 7):
+        engine.set_factors(P, Q)
+        parts = [engine.bpr_epoch_part(0.05, 0.01, 0.01, 3, 0, k, S, MODE_SERIAL) for k in range(S)]
+        Pp, Qp = engine.get_factors()
+        assert np.array_equal(Pp, Pf) and np.array_equal(Qp, Qf)
+        assert sum(parts) == pytest.approx(full, rel=1e-12)
+    engine.set_factors(P, Q)
+    l0 = engine.bpr_epoch(0.0, 0.0, 0.0, 3, 0, MODE_HOGWILD)
+    lp = sum(engine.bpr_epoch_part(0.0, 0.0, 0.0, 3, 0, k, 5, MODE_HOGWILD) for k in range(5))
+    assert lp == pytest.approx(l0, rel=1e-6)
+    with pytest.raises(YueError):
+        engine.bpr_epoch_part(0.05, 0.01, 0.01, 3, 0, 2, 2, MODE_SERIAL)

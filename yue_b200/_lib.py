@@ -64,6 +64,8 @@ SIGNATURES = {
     "yue_sample_negatives": (C.c_int, [_H, C.c_uint64, C.c_uint32, C.c_uint32, _i32p]),
     "yue_bpr_epoch": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
                                 C.c_int, _f64p]),
+    "yue_bpr_epoch_part": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
+                                     C.c_int, C.c_int, C.c_int, _f64p]),
     "yue_bpr_apply": (C.c_int, [_H, _i32p, _i32p, _i32p, C.c_int64, C.c_double, C.c_double,
                                 C.c_double, C.c_int, _f64p]),
     "yue_apr_epoch": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,

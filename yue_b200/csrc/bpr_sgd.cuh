@@ -75,7 +75,8 @@ struct SgdParams {
     uint32_t n_items;
     const SegRec* seg_rec;         // [nseg] one 32-byte record per segment
     const int64_t* item_ptr;       // [2*n_work] segment range [begin, end) of each work item, in hand-out order
-    int64_t n_work;
+    int64_t n_work;                // items [item_first, n_work) are handed out (item_first = 0 for a whole epoch)
+    int64_t item_first;
     unsigned long long* cursor;    // next item to hand out (zeroed before the launch)
     int n_warps;
     const int32_t* ev_items;       // [T] positives; a value v < 0 names hot slot -v-1 (see hot_items)

@@ -763,7 +763,8 @@ static int ensure_hot_meta(yue_t* h, int cap) {
 static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr = false) {
     REQUIRE(mode >= YUE_MODE_SERIAL && mode <= YUE_MODE_HOGWILD_STORE, YUE_E_ARG, "unknown mode");
     CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
+    if (sp.item_first == 0) CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
+    else { const unsigned long long c0 = (unsigned long long)sp.item_first; CK(cudaMemcpyAsync(h->cursor.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
     sp.cursor = h->cursor.p;
     const bool blk = use_blk_kernel(h, mode, apr);
     { int rb = 1; while (rb * 2 * kBlkK <= sp.resync_events) rb *= 2; sp.resync_mask = rb - 1; }
@@ -821,7 +822,8 @@ static void fill_rates(SgdParams& sp, double lr, double regU, double regI) {
 }
 
 static int sgd_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, uint32_t epoch, uint32_t slot,
-                     int mode, double* loss_out, bool apr, double eps, double regA) {
+                     int mode, double* loss_out, bool apr, double eps, double regA, int part = 0, int n_parts = 1) {
+    REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, YUE_E_ARG, "part must be in [0, n_parts)");
     REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
     REQUIRE(slot < 4096, YUE_E_ARG, "slot must be < 4096");
     CK(cudaSetDevice(h->device));
@@ -829,7 +831,10 @@ static int sgd_epoch(yue_t* h, double lr, double regU, double regI, uint64_t see
     SgdParams sp{};
     fill_rates(sp, lr, regU, regI);
     sp.seg_rec = h->seg_rec.p;
-    sp.item_ptr = h->item_ptr.p; sp.n_work = h->n_items;
+    sp.item_ptr = h->item_ptr.p;
+    // sub-epoch: the part-th of n_parts consecutive ranges of the work items (stream order)
+    sp.item_first = h->n_items * part / n_parts; sp.n_work = h->n_items * (part + 1) / n_parts;
+    if (sp.item_first == sp.n_work) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     sp.n_warps = mode == YUE_MODE_SERIAL ? 1 : h->n_warps;
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
     sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot;
@@ -841,6 +846,10 @@ static int sgd_epoch(yue_t* h, double lr, double regU, double regI, uint64_t see
 int yue_bpr_epoch(yue_t* h, double lr, double regU, double regI, uint64_t seed, uint32_t epoch, int mode,
                   double* loss_out) {
     return sgd_epoch(h, lr, regU, regI, seed, epoch, 0u, mode, loss_out, false, 0.0, 0.0);
+}
+int yue_bpr_epoch_part(yue_t* h, double lr, double regU, double regI, uint64_t seed, uint32_t epoch, int mode,
+                       int part, int n_parts, double* loss_out) {
+    return sgd_epoch(h, lr, regU, regI, seed, epoch, 0u, mode, loss_out, false, 0.0, 0.0, part, n_parts);
 }
 int yue_apr_epoch(yue_t* h, double lr, double regU, double regI, double eps, double regA, uint64_t seed,
                   uint32_t epoch, uint32_t slot, int mode, double* loss_out) {

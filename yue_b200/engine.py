@@ -155,6 +155,13 @@ class Engine:
                                         C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
 
+    def bpr_epoch_part(self, lr, regU, regI, seed, epoch, part, n_parts, mode=MODE_HOGWILD, want_loss=True):
+        """The part-th of n_parts consecutive sub-epochs (users in stream order)."""
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_bpr_epoch_part(self.h, lr, regU, regI, seed, epoch, mode, part, n_parts,
+                                             C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
     def bpr_apply(self, u, i, j, lr, regU, regI, mode=MODE_SERIAL, want_loss=True):
         u, i, j = _as(u, np.int32), _as(i, np.int32), _as(j, np.int32)
         loss = C.c_double(0.0)
