@@ -260,7 +260,7 @@ def run_native(args):
             eng.apr_epoch(0.003, 0.002, 0.01, 0.5, 2.0, SEED, 3000 + k, 0, mode, want_loss=False)
             ams.append(eng.timer_stop())
         apr = {"metric": "apr_triplets_per_sec", "value": T / (min(ams[1:]) * 1e-3), "ms_per_epoch": min(ams[1:]),
-               "workload": "C5: APR d=64 on the C2 log, eps 0.5, regA 2, lr 0.003 (config/APR.conf)", "kernel": "bpr_sgd_kernel<APR>"}
+               "workload": "C5: APR d=64 on the C2 log, eps 0.5, regA 2, lr 0.003 (config/APR.conf)", "kernel": "bpr_sgd_blk_kernel<2, APR>"}
 
     # ---- e2e: same step through the C ABI with host buffers ---------------------------------
     h2d = log.ev_indptr.nbytes + log.ev_items.nbytes + log.uq_indptr.nbytes + log.uq_items.nbytes + pP.nbytes + pQ.nbytes

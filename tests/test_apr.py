@@ -128,3 +128,29 @@ def test_apr_class_trains_and_ranks(tmp_path):
     with redirect_stdout(io.StringIO()):
         measure = Yue(Config(values=vals)).execute()
     assert measure[6] == "Top 10\n" and float(measure[8].split(":")[1]) > 0.05       # Recall@10 of a trained model
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_apr_blocked_kernel_recurrence_all_widths(engine, d):
+    """The blocked APR kernel (16 dots per block of 4 triplets, |P|^2 and the scores from the scalar
+    recurrence) against the per-triplet oracle: several triplets per user on disjoint rows, so blocks
+    of 1-4 triplets, the |P| recurrence over a block and segment boundaries are all exercised."""
+    from yue_b200 import synth
+    from yue_b200.engine import MODE_HOGWILD
+    m = 200
+    per = 1 + np.arange(m) % 37
+    u = np.repeat(np.arange(m, dtype=np.int32), per)
+    T = len(u)
+    n = 2 * T + 10
+    log = synth.power_law_log(m, n, 6000, seed=3)
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    P, Q = synth.init_factors(m, n, d, seed=1)
+    i, j = (2 * np.arange(T)).astype(np.int32), (2 * np.arange(T) + 1).astype(np.int32)
+    Pr, Qr = P.astype(np.float64), Q.astype(np.float64)
+    ref = apr_ref.apr_epoch(Pr, Qr, u, i, j, 0.01, 0.002, 0.01, 0.5, 2.0)
+    engine.set_factors(P, Q)
+    loss = engine.apr_apply(u, i, j, 0.01, 0.002, 0.01, 0.5, 2.0, MODE_HOGWILD)
+    Pg, Qg = engine.get_factors()
+    assert np.allclose(Pg, Pr, rtol=2e-5, atol=2e-7) and np.allclose(Qg, Qr, rtol=2e-5, atol=2e-7)
+    assert loss == pytest.approx(ref, rel=1e-5)

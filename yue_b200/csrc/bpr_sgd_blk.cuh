@@ -87,6 +87,36 @@ __device__ __forceinline__ void warp_allreduce10(float (&x)[10], int lane) {
     x[8] = y8; x[9] = y9;
 }
 
+// The same for 16 values: reduce-scatter over all five lane bits, all-gather (32 shuffles instead of 80).
+__device__ __forceinline__ void warp_allreduce16(float (&x)[16], int lane) {
+    const unsigned full = 0xffffffffu;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float k0[8], k1[4], k2[2], k3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = b4 ? x[i] : x[i + 8], keep = b4 ? x[i + 8] : x[i];
+        k0[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b3 ? k0[i] : k0[i + 4], keep = b3 ? k0[i + 4] : k0[i];
+        k1[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b2 ? k1[i] : k1[i + 2], keep = b2 ? k1[i + 2] : k1[i];
+        k2[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    {
+        const float send = b1 ? k2[0] : k2[1], keep = b1 ? k2[1] : k2[0];
+        k3 = keep + __shfl_xor_sync(full, send, 2);
+    }
+    k3 += __shfl_xor_sync(full, k3, 1);
+    // lane l now holds the total of value (l >> 1)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = __shfl_sync(full, k3, 2 * i);
+}
+
 // g = lr * sigmoid(-x) (= lr (1 - s), BPR.py:50-51) and loss += -log(sigmoid(x)) (BPR.py:58)
 __device__ __forceinline__ float bpr_grad(float x, float lr, float& loss) {
     const float ex = __expf(-fabsf(x));                     // e^{-|x|} in (0, 1]
@@ -167,7 +197,7 @@ __global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restric
 // virtual empty segment, so all of this exists once in the code (the first version, with the block
 // loop unrolled by two and the prologue inlined three times, was 12 K instructions and spent 57 % of
 // its stall samples waiting for the instruction cache).
-template <int V>
+template <int V, bool APR>
 __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdParams p) {
     extern __shared__ __align__(16) int hot_sm[];           // [n_hot] hot track ids, ascending; [n_hot] their slots; [n_hot] dx
     int* hot_sorted = hot_sm;
@@ -316,65 +346,139 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                     const int nbk = len - kBlkK * b;                        // >= 1 triplets in this block
                     if (resync && b > 0 && (b & p.resync_mask) == 0) sync_user(u);
                     float d[kBlkK][V];
-                    float x[10];
 #pragma unroll
                     for (int a = 0; a < kBlkK; ++a) {
                         if (cur.dx[a]) {                                    // logical row of a sharded positive = sum of its rows
 #pragma unroll
                             for (int v = 0; v < V; ++v) cur.qi[a][v] += cur.ex[a][v];
                         }
-                        float s = 0.f;
 #pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            d[a][v] = cur.qi[a][v] - cur.qj[a][v];          // Q[i] - Q[j], old rows (BPR.py:51)
-                            s = fmaf(pu[v], d[a][v], s);
+                        for (int v = 0; v < V; ++v) d[a][v] = cur.qi[a][v] - cur.qj[a][v];   // Q[i] - Q[j], old rows (BPR.py:51)
+                    }
+                    if constexpr (!APR) {
+                        float x[10];
+#pragma unroll
+                        for (int a = 0; a < kBlkK; ++a) {
+                            float s = 0.f;
+#pragma unroll
+                            for (int v = 0; v < V; ++v) s = fmaf(pu[v], d[a][v], s);
+                            x[a] = s;
                         }
-                        x[a] = s;
-                    }
-                    {
-                        int g = 4;
+                        {
+                            int g = 4;
 #pragma unroll
-                        for (int a = 0; a < kBlkK; ++a)
+                            for (int a = 0; a < kBlkK; ++a)
 #pragma unroll
-                            for (int c = a + 1; c < kBlkK; ++c) {
-                                float s = 0.f;
+                                for (int c = a + 1; c < kBlkK; ++c) {
+                                    float s = 0.f;
 #pragma unroll
-                                for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
-                                x[g++] = s;                                  // order: 01 02 03 12 13 23
+                                    for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
+                                    x[g++] = s;                              // order: 01 02 03 12 13 23
+                                }
+                        }
+                        warp_allreduce10(x, lane);
+                        // scalar recurrence: w_c = P_a . d_c for the current a
+                        float g[kBlkK];
+                        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                        g[0] = bpr_grad(x[0], p.lr, l0);
+                        float w1 = cu1 * fmaf(g[0], x[4], x[1]);
+                        float w2 = cu1 * fmaf(g[0], x[5], x[2]);
+                        float w3 = cu1 * fmaf(g[0], x[6], x[3]);
+                        g[1] = bpr_grad(w1, p.lr, l1);
+                        w2 = cu1 * fmaf(g[1], x[7], w2);
+                        w3 = cu1 * fmaf(g[1], x[8], w3);
+                        g[2] = bpr_grad(w2, p.lr, l2);
+                        w3 = cu1 * fmaf(g[2], x[9], w3);
+                        g[3] = bpr_grad(w3, p.lr, l3);
+                        loss += (double)(l0 + (nbk > 1 ? l1 : 0.f) + (nbk > 2 ? l2 : 0.f) + (nbk > 3 ? l3 : 0.f));
+                        // row updates in the reference's order (BPR.py:51-57): P first, Q with the updated P,
+                        // then the three multiplicative shrinks; Q changes leave as deltas (vector atomics)
+#pragma unroll
+                        for (int a = 0; a < kBlkK; ++a) {
+                            if (a < nbk) {
+                                const float ga = g[a];
+                                float di[V], dj[V];
+#pragma unroll
+                                for (int v = 0; v < V; ++v) {
+                                    const float pn = fmaf(ga, d[a][v], pu[v]);
+                                    const float gp = ga * pn;
+                                    di[v] = fmaf(-p.c_i, cur.qi[a][v] + gp, gp);    // (q + g p)(1 - c) - q
+                                    dj[v] = fmaf(-p.c_i, cur.qj[a][v] - gp, -gp);
+                                    pu[v] = fmaf(-p.c_u, pn, pn);
+                                }
+                                redv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
+                                redv<V>(cur.pj[a], dj);
                             }
-                    }
-                    warp_allreduce10(x, lane);
-                    // scalar recurrence: w_c = P_a . d_c for the current a
-                    float g[kBlkK];
-                    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                    g[0] = bpr_grad(x[0], p.lr, l0);
-                    float w1 = cu1 * fmaf(g[0], x[4], x[1]);
-                    float w2 = cu1 * fmaf(g[0], x[5], x[2]);
-                    float w3 = cu1 * fmaf(g[0], x[6], x[3]);
-                    g[1] = bpr_grad(w1, p.lr, l1);
-                    w2 = cu1 * fmaf(g[1], x[7], w2);
-                    w3 = cu1 * fmaf(g[1], x[8], w3);
-                    g[2] = bpr_grad(w2, p.lr, l2);
-                    w3 = cu1 * fmaf(g[2], x[9], w3);
-                    g[3] = bpr_grad(w3, p.lr, l3);
-                    loss += (double)(l0 + (nbk > 1 ? l1 : 0.f) + (nbk > 2 ? l2 : 0.f) + (nbk > 3 ? l3 : 0.f));
-                    // row updates in the reference's order (BPR.py:51-57): P first, Q with the updated P,
-                    // then the three multiplicative shrinks; Q changes leave as deltas (vector atomics)
+                        }
+                    } else {
+                        // K2a, APR (recommender/advanced/APR.py:25-76, oracle/apr_ref.py): per triplet, from the OLD rows,
+                        //   y_adv = y - 2 eps |P| - eps |d| + 2 eps^2 y / (|P||d|),  a = lr (s0 + regA s1),  b = lr regA s1 eps,
+                        //   P <- c (alpha P + a d),  alpha = 1 - 2 b / |P|;   Q[i] += a P - (b/|d|) d,  Q[j] -= the same
+                        // The block needs |d_a|^2 and |P_0|^2 besides the 10 dots of BPR (16 reduced values); then
+                        //   P_{a+1}.d_c = c (alpha w_c + a G_ac),   |P_{a+1}|^2 = c^2 (alpha^2 |P_a|^2 + 2 alpha a w_a + a^2 G_aa).
+                        float x[16];
+                        float pp = 0.f;
 #pragma unroll
-                    for (int a = 0; a < kBlkK; ++a) {
-                        if (a < nbk) {
-                            const float ga = g[a];
-                            float di[V], dj[V];
+                        for (int v = 0; v < V; ++v) pp = fmaf(pu[v], pu[v], pp);
 #pragma unroll
-                            for (int v = 0; v < V; ++v) {
-                                const float pn = fmaf(ga, d[a][v], pu[v]);
-                                const float gp = ga * pn;
-                                di[v] = fmaf(-p.c_i, cur.qi[a][v] + gp, gp);    // (q + g p)(1 - c) - q
-                                dj[v] = fmaf(-p.c_i, cur.qj[a][v] - gp, -gp);
-                                pu[v] = fmaf(-p.c_u, pn, pn);
+                        for (int a = 0; a < kBlkK; ++a) {
+                            float s = 0.f, q = 0.f;
+#pragma unroll
+                            for (int v = 0; v < V; ++v) { s = fmaf(pu[v], d[a][v], s); q = fmaf(d[a][v], d[a][v], q); }
+                            x[a] = s; x[10 + a] = q;
+                        }
+                        {
+                            int g = 4;
+#pragma unroll
+                            for (int a = 0; a < kBlkK; ++a)
+#pragma unroll
+                                for (int c = a + 1; c < kBlkK; ++c) {
+                                    float s = 0.f;
+#pragma unroll
+                                    for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
+                                    x[g++] = s;
+                                }
+                        }
+                        x[14] = pp; x[15] = 0.f;
+                        warp_allreduce16(x, lane);
+                        float w[kBlkK] = {x[0], x[1], x[2], x[3]};
+                        const float G[kBlkK][kBlkK] = {{x[10], x[4], x[5], x[6]}, {x[4], x[11], x[7], x[8]},
+                                                       {x[5], x[7], x[12], x[9]}, {x[6], x[8], x[9], x[13]}};
+                        float np2 = x[14], lsum = 0.f;
+                        float ca[kBlkK], calpha[kBlkK], cbd[kBlkK];           // a, alpha, b/|d| of each triplet
+#pragma unroll
+                        for (int a = 0; a < kBlkK; ++a) {
+                            const float y = w[a];
+                            const float inp = np2 > 0.f ? rsqrtf(np2) : 0.f, ind = G[a][a] > 0.f ? rsqrtf(G[a][a]) : 0.f;
+                            const float n_p = np2 * inp, n_d = G[a][a] * ind;
+                            const float ya = y - 2.f * p.eps * n_p - p.eps * n_d + 2.f * p.eps * p.eps * y * inp * ind;
+                            const float e0 = __expf(-fabsf(y)), e1 = __expf(-fabsf(ya));
+                            const float s0 = __fdividef(y >= 0.f ? e0 : 1.f, 1.f + e0);      // sigmoid(-y)
+                            const float s1 = __fdividef(ya >= 0.f ? e1 : 1.f, 1.f + e1);
+                            if (a < nbk) lsum += fmaxf(-y, 0.f) + __logf(1.f + e0) + p.regA * (fmaxf(-ya, 0.f) + __logf(1.f + e1));
+                            const float aa = p.lr * (s0 + p.regA * s1), bb = p.lr * p.regA * s1 * p.eps;
+                            const float alpha = 1.f - 2.f * bb * inp;
+                            ca[a] = aa; calpha[a] = alpha; cbd[a] = bb * ind;
+                            np2 = cu1 * cu1 * (alpha * alpha * np2 + 2.f * alpha * aa * w[a] + aa * aa * G[a][a]);
+#pragma unroll
+                            for (int c = a + 1; c < kBlkK; ++c) w[c] = cu1 * (alpha * w[c] + aa * G[a][c]);
+                        }
+                        loss += (double)lsum;
+#pragma unroll
+                        for (int a = 0; a < kBlkK; ++a) {
+                            if (a < nbk) {
+                                float di[V], dj[V];
+#pragma unroll
+                                for (int v = 0; v < V; ++v) {
+                                    const float step = fmaf(ca[a], pu[v], -cbd[a] * d[a][v]);      // a P - (b/|d|) d, old P
+                                    const float pn = fmaf(calpha[a], pu[v], ca[a] * d[a][v]);
+                                    di[v] = fmaf(-p.c_i, cur.qi[a][v] + step, step);
+                                    dj[v] = fmaf(-p.c_i, cur.qj[a][v] - step, -step);
+                                    pu[v] = fmaf(-p.c_u, pn, pn);
+                                }
+                                redv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
+                                redv<V>(cur.pj[a], dj);
                             }
-                            redv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
-                            redv<V>(cur.pj[a], dj);
                         }
                     }
                 }

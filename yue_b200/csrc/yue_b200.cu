@@ -723,19 +723,20 @@ static cudaError_t launch_sgd(const SgdParams& sp, int mode, int warps_per_cta, 
 }
 
 // blocked kernel: hot rows move into the slice-friendly table for the launch and back after it
-template <int V>
+template <int V, bool APR>
 static cudaError_t launch_sgd_blk(const SgdParams& sp, int warps_per_cta, cudaStream_t st, int64_t& launches) {
     warps_per_cta = std::min(warps_per_cta, kBlkThreads / 32);
     const int grid = (sp.n_warps + warps_per_cta - 1) / warps_per_cta;
     if (sp.n_hot > 0) { hot_gather_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
-    bpr_sgd_blk_kernel<V><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
+    bpr_sgd_blk_kernel<V, APR><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
     if (sp.n_hot > 0) { hot_scatter_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
     return cudaGetLastError();
 }
 
 // does the blocked kernel (bpr_sgd_blk.cuh) take this launch?
 static bool use_blk_kernel(const yue_t* h, int mode, bool apr) {
-    return h->sgd_kernel == 2 && mode == YUE_MODE_HOGWILD && !apr && (h->ld == 32 || h->ld == 64 || h->ld == 128) &&
+    (void)apr;
+    return h->sgd_kernel == 2 && mode == YUE_MODE_HOGWILD && (h->ld == 32 || h->ld == 64 || h->ld == 128) &&
            (uint64_t)h->n * h->ld * 4 < ((uint64_t)1 << 32);      // 32-bit byte offsets inside Q
 }
 
@@ -783,9 +784,9 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr 
     const int wpc = std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm));
     if (blk) {
         switch (h->ld) {
-            case 32: CK(launch_sgd_blk<1>(sp, wpc, h->stream, h->launches)); break;
-            case 64: CK(launch_sgd_blk<2>(sp, wpc, h->stream, h->launches)); break;
-            default: CK(launch_sgd_blk<4>(sp, wpc, h->stream, h->launches)); break;
+            case 32: CK(apr ? launch_sgd_blk<1, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<1, false>(sp, wpc, h->stream, h->launches)); break;
+            case 64: CK(apr ? launch_sgd_blk<2, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<2, false>(sp, wpc, h->stream, h->launches)); break;
+            default: CK(apr ? launch_sgd_blk<4, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<4, false>(sp, wpc, h->stream, h->launches)); break;
         }
     } else
     switch (nch) {
