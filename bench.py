@@ -139,11 +139,12 @@ def run_reference(args):
     t = sum(cpu_epoch(sample, args.warmup + k) for k in range(args.steps))
     value = sample["T"] * args.steps / t
     desc = "%d-triplet user-strided sample of the workload per step, oracle port of BPR.py:31-62" % sample["T"]
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "d": D, "lr": LR, "reg": [REG_U, REG_I]},
+        "config": {"workload": wl["name"], "d": D, "triplets_per_step_per_gpu": wl["plays"], "lr": LR, "reg": [REG_U, REG_I],
+                   "sgd_mode": "serial (the reference's loop order)", "parallelism": "1 host core (the loop is inherently serial)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -327,7 +328,7 @@ def run_native(args):
                                "sample": "%d-triplet user-strided sample of the same log, one epoch of the oracle "
                                          "port of BPR.py:31-62 (float32 numpy rows, serial)" % sample["T"]}
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -384,6 +385,24 @@ def bench_ranking(eng, args, bf16_peak, rank=0, world=1, dist=None):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Native libraries write to fd 1 (NCCL prints its version there): keep stdout for the one JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(line, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -400,6 +419,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and not args.small:
         args.warmup = 3
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
