@@ -187,3 +187,20 @@ def test_exact_kernel_catalog_split_and_stats(engine):
     engine.rank_topn(np.arange(m, dtype=np.int32).repeat(8), 10, RANK_TC)
     fb, spilled = engine.rank_stats()
     assert fb >= 0 and spilled >= 0
+
+
+def test_tc_refuses_what_it_cannot_hold(engine):
+    """N > 32 does not fit the tcgen05 kernel's per-row buffer: RANK_TC says so, RANK_AUTO takes the exact kernel."""
+    from oracle import topn
+    from yue_b200.engine import RANK_AUTO, YueError
+    m, n = 300, 4000
+    indptr, uq = synth.mask_csr(m, n, 20, seed=1)
+    P, Q = synth.init_factors(m, n, 64, seed=2)
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), indptr, uq)
+    engine.set_factors(P, Q)
+    users = np.arange(m, dtype=np.int32)
+    with pytest.raises(YueError):
+        engine.rank_topn(users, 40, RANK_TC)
+    ids, sc = engine.rank_topn(users, 40, RANK_AUTO)
+    rid, rsc = topn.topn_exact(P, Q, users, 40, indptr, uq)
+    assert np.array_equal(ids, rid) and np.array_equal(sc, rsc)

@@ -40,7 +40,9 @@ constexpr int kTcThreads = 192;
 constexpr int kTcBM = 128;            // users per CTA (UMMA M)
 constexpr int kTcBN = 128;            // tracks per tile (UMMA N)
 constexpr int kTcStages = 3;          // TMA -> MMA shared-memory stages
-constexpr int kTcCap = 64;            // candidate slots per row
+// candidate slots per row (template parameter CAP of the kernel): CAP - 32 kept + 32 new per chunk.  64 for N <= 12
+// (fastest: 10.8 ms per wave at N = 10); 96 for larger N (at N = 20 a row keeps ~27-45 near-ties: with 64 slots
+// nearly every row spilled and fell back to the exact kernel, 202 ms instead of 12.8 ms).
 constexpr int kTcAcc = 4;             // TMEM accumulator stages (4 x 128 columns = all of TMEM)
 constexpr int kTcOvfCap = 1024;       // candidate slots of a row that overflowed into the global pool
 constexpr int kTcOvfRowsMin = 512;    // rows the spill pool can take per launch: at least this, else B / 16
@@ -181,38 +183,47 @@ __device__ __noinline__ bool tc_push(TcRow* st, uint64_t* K, const int32_t* __re
 }
 // whole warp: compact every row of this warp whose buffer is more than half full; returns the
 // (possibly raised) push threshold of the calling lane's row
+template <int CAP>
 __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int lane, int N, float eps2, float thr,
                                          uint64_t* __restrict__ ovf_pool, int* __restrict__ ovf_next, int ovf_rows) {
     unsigned full;
-    while ((full = __ballot_sync(0xffffffffu, st->cnt > kTcCap - 32)) != 0u) {
+    constexpr int kTcPer = CAP / 32;
+    while ((full = __ballot_sync(0xffffffffu, st->cnt > CAP - 32)) != 0u) {
         const int src = __ffs(full) - 1;
         const int cc = __shfl_sync(0xffffffffu, st->cnt, src);
         const float e2 = __shfl_sync(0xffffffffu, eps2, src);
-        uint64_t* R = keys_quarter + (size_t)src * kTcCap;
-        const uint64_t m0 = lane < cc ? R[lane] : ~0ull, m1 = lane + 32 < cc ? R[lane + 32] : ~0ull;
-        int r0 = 0, r1 = 0;
-        for (int e = 0; e < cc; ++e) { const uint64_t k = R[e]; r0 += k < m0; r1 += k < m1; }
+        uint64_t* R = keys_quarter + (size_t)src * CAP;
+        uint64_t mine[kTcPer];
+        int rk[kTcPer];
+#pragma unroll
+        for (int q = 0; q < kTcPer; ++q) { mine[q] = lane + 32 * q < cc ? R[lane + 32 * q] : ~0ull; rk[q] = 0; }
+        for (int e = 0; e < cc; ++e) {
+            const uint64_t k = R[e];
+#pragma unroll
+            for (int q = 0; q < kTcPer; ++q) rk[q] += k < mine[q];
+        }
         __syncwarp();
-        if (lane < cc) R[r0] = m0;
-        if (lane + 32 < cc) R[r1] = m1;
+#pragma unroll
+        for (int q = 0; q < kTcPer; ++q) if (lane + 32 * q < cc) R[rk[q]] = mine[q];
         __syncwarp();
-        const float lim = key_score(R[N - 1]) - e2;                 // cc > 32 >= N
-        const bool k0 = lane < cc && key_score(R[lane]) >= lim;
-        const bool k1 = lane + 32 < cc && key_score(R[lane + 32]) >= lim;
-        const int kept = __popc(__ballot_sync(0xffffffffu, k0)) + __popc(__ballot_sync(0xffffffffu, k1));
+        const float lim = key_score(R[N - 1]) - e2;                 // cc > CAP - 32 >= N
+        int kept = 0;
+#pragma unroll
+        for (int q = 0; q < kTcPer; ++q)
+            kept += __popc(__ballot_sync(0xffffffffu, lane + 32 * q < cc && key_score(R[lane + 32 * q]) >= lim));
         int slot = -1;
-        if (kept > kTcCap - 32) {              // too many near-ties for shared memory: spill the row
+        if (kept > CAP - 32) {                 // too many near-ties for shared memory: spill the row
             if (lane == 0) slot = atomicAdd(ovf_next, 1);
             slot = __shfl_sync(0xffffffffu, slot, 0);
             if (slot < ovf_rows) {
                 uint64_t* G = ovf_pool + (size_t)slot * kTcOvfCap;
-                if (lane < kept) G[lane] = R[lane];
-                if (lane + 32 < kept) G[lane + 32] = R[lane + 32];
+#pragma unroll
+                for (int q = 0; q < kTcPer; ++q) if (lane + 32 * q < kept) G[lane + 32 * q] = R[lane + 32 * q];
             }
         }
         if (lane == src) {
             thr = lim;
-            if (kept <= kTcCap - 32) st->cnt = kept;
+            if (kept <= CAP - 32) st->cnt = kept;
             else if (slot < ovf_rows) { st->ovf_slot = slot; st->ovf_cnt = kept; st->cnt = 0; }   // threshold frozen from here on
             else { st->fail = 1; thr = INFINITY; st->cnt = 0; }
         }
@@ -221,6 +232,7 @@ __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int 
     return thr;
 }
 
+template <int CAP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const RankTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
@@ -229,8 +241,9 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     const uint32_t stage_bytes = (uint32_t)KB * kTcBoxBytes;
     uint8_t* sA = smem;
     uint8_t* sB = sA + stage_bytes;
-    uint64_t* keys = reinterpret_cast<uint64_t*>(sB + kTcStages * stage_bytes);        // [128][kTcCap]
-    uint64_t* bars = keys + kTcBM * kTcCap;
+    constexpr int kTcPer = CAP / 32;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sB + kTcStages * stage_bytes);        // [128][CAP]
+    uint64_t* bars = keys + kTcBM * CAP;
     // barriers: 0 = A landed, 1..S = B full, S+1..2S = B empty, then kTcAcc TMEM full, kTcAcc TMEM empty
     const uint32_t bar_a = smem_u32(bars);
     auto bar_full = [&](int s) { return smem_u32(bars + 1 + s); };
@@ -302,7 +315,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         const int r = quarter * 32 + lane;
         const int64_t b = (int64_t)blockIdx.x * kTcBM + r;
         const bool valid = b < p.B;
-        uint64_t* K = keys + (size_t)r * kTcCap;
+        uint64_t* K = keys + (size_t)r * CAP;
         const float eps2 = valid ? 2.f * kTf32ErrCoef * p.pnorm[b] * (*p.qmax) : 0.f;
         float thr = valid ? -INFINITY : INFINITY;       // push threshold = tau - 2 eps
         TcRow st;
@@ -310,7 +323,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         if (valid) { const int u = p.users[b]; st.mcur = p.uq_indptr[u]; st.mend = p.uq_indptr[u + 1]; }
         st.mval = st.mcur < st.mend ? p.uq_items[st.mcur] : INT32_MAX;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        uint64_t* keys_quarter = keys + (size_t)(quarter * 32) * kTcCap;
+        uint64_t* keys_quarter = keys + (size_t)(quarter * 32) * CAP;
 
         // examine 32 scores of columns [col0, col0+32): push survivors, then compact crowded rows
 #define TC_RARE(v, col0, m)                                                                          \
@@ -324,7 +337,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                 }                                                                                    \
             }                                                                                        \
             __syncwarp();                                                                            \
-            thr = tc_compact(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next, p.ovf_rows);       \
+            thr = tc_compact<CAP>(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next, p.ovf_rows);       \
         } while (0)
 
         for (int j = 0; j < p.ntiles; ++j) {
@@ -367,7 +380,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                 if (lane == 0) p.fail_rows[atomicAdd(p.fail_count, 1)] = (int32_t)bb;
                 continue;
             }
-            uint64_t* R = keys + (size_t)(quarter * 32 + rr) * kTcCap;
+            uint64_t* R = keys + (size_t)(quarter * 32 + rr) * CAP;
             const float* pu = p.Psel + (size_t)bb * p.ld;
             if (oslot >= 0) {
                 // spilled row: stream the pool entries through the 64-slot buffer, 32 at a time, keeping
@@ -385,7 +398,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                     __syncwarp();
                     if (lane < take) R[have + lane] = nk;
                     __syncwarp();
-                    have = compact_row<kTcCap>(R, have + take, p.N, lane);
+                    have = compact_row<CAP>(R, have + take, p.N, lane);
                     __syncwarp();
                 }
                 for (int x = lane; x < p.N; x += 32) {
@@ -396,9 +409,9 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                 }
                 continue;
             }
-            uint64_t nk[2];
+            uint64_t nk[kTcPer];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < kTcPer; ++h) {
                 const int e = lane + 32 * h;
                 nk[h] = 0;
                 if (e < cc) {
@@ -408,9 +421,9 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             }
             __syncwarp();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) if (lane + 32 * h < cc) R[lane + 32 * h] = nk[h];
+            for (int h = 0; h < kTcPer; ++h) if (lane + 32 * h < cc) R[lane + 32 * h] = nk[h];
             __syncwarp();
-            const int nc = compact_row<kTcCap>(R, cc, p.N, lane);
+            const int nc = compact_row<CAP>(R, cc, p.N, lane);
             for (int x = lane; x < p.N; x += 32) {
                 const bool ok = x < nc;
                 const uint64_t k = ok ? R[x] : 0ull;
@@ -490,6 +503,7 @@ struct RankTcState {
     size_t ovf_rows = 0;
 };
 
+// a row keeps its N best plus the near-ties (within 2 eps of the N-th) in kTcCap - 32 = 64 slots
 inline bool rank_tc_supported(int k, int N) { return k >= 1 && k <= 64 && N >= 1 && N <= 32; }
 
 inline void rank_tc_release(RankTcState& st) {
@@ -573,9 +587,15 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
     p.uq_indptr = uq_indptr; p.uq_items = uq_items; p.ids_out = d_ids; p.scores_out = d_scores;
     p.fail_count = st.fail_count; p.fail_rows = st.fail_rows;
     p.ovf_pool = st.ovf_pool; p.ovf_next = st.ovf_next; p.ovf_rows = (int)(st.ovf_rows / kTcOvfCap);
-    const size_t smem = 1024 + (size_t)p.kblocks * kTcBoxBytes * (1 + kTcStages) + (size_t)kTcBM * kTcCap * 8 + 256;
-    TC_CK(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rank_tc_kernel<<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);
+    const int cap = N <= 12 ? 64 : 96;
+    const size_t smem = 1024 + (size_t)p.kblocks * kTcBoxBytes * (1 + kTcStages) + (size_t)kTcBM * cap * 8 + 256;
+    if (cap == 64) {
+        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rank_tc_kernel<64><<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);
+    } else {
+        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rank_tc_kernel<96><<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);
+    }
     ++launches;
     TC_CK(cudaGetLastError());
 
