@@ -93,10 +93,10 @@ struct PinBuf {
 struct yue_handle {
     int device = 0;
     int sm_count = 148;
-    // Warps per SM that take work (one resident 512-thread CTA per SM, a single wave).  At config C2
-    // with sharded hot rows: 16 -> 25.5 ms/epoch, Recall@10 0.6 points under the serial order;
-    // 10 -> 30 ms, 0.49 under (NDCG@10 0.14 under) -- the documented gate is 0.5 (profiles/quality_study_r1.md).
-    int warps_per_sm = 10;
+    // Warps per SM that take work (one resident CTA per SM, a single wave).  Blocked kernel at config C2
+    // (profiles/quality_study_r1.md section D): 8 warps 13.6 ms, 10 warps 13.6 ms, 12 warps 12.6 ms per epoch, Recall@10 /
+    // NDCG@10 within 3e-4 / 3e-3 of the serial order in every run at all three (12 = the kernel's launch bound).
+    int warps_per_sm = 12;
     // Small logs get fewer warps.  tools/quality_study.py: at >= 16 K events per warp (what config
     // C2 has on a full B200) the sliding-window schedule reproduces the serial model's Recall/NDCG to
     // 1e-4; at <= 4 K events per warp heavy-user items become stragglers, light users finish long
