@@ -491,9 +491,9 @@ __global__ void hot_fold_kernel(float* __restrict__ Q, float* __restrict__ shard
 }
 
 // ---- hot-track selection support: play counts, and re-labelling of hot positives ------------
-__global__ void item_count_kernel(const int32_t* __restrict__ ev_items, int64_t T, int32_t* __restrict__ counts) {
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T; e += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t it = ev_items[e];
+__global__ void item_count_kernel(const int32_t* __restrict__ ev_items, int64_t T, int64_t stride, int32_t* __restrict__ counts) {
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x * stride < T; x += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t it = ev_items[x * stride];
         const unsigned peers = __match_any_sync(__activemask(), it);     // one atomic per distinct id in the warp
         if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + it, __popc(peers));
     }

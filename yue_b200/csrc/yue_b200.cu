@@ -9,6 +9,7 @@
 #include <functional>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -197,6 +198,18 @@ struct yue_handle {
     } while (0)
 
 static int fail(yue_t* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+// YUE_TIMING=1: wall-clock of the phases of yue_set_interactions on stderr (diagnostics)
+struct PhaseTimer {
+    bool on; std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(getenv("YUE_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[yue timing] %-28s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 static int q_rowmajor(yue_t* h);
 static int q_interleaved(yue_t* h);
 
@@ -371,17 +384,31 @@ int yue_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? YUE_OK : YU
 // ev_indptr / uq_indptr are their host copies.  Validates, plans segments and work items, selects the hot tracks.
 static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t* uq_indptr) {
     const int64_t m_local = h->m, n = h->n, T = h->T;
-    for (int64_t u = 0; u < m_local; ++u) {
-        REQUIRE(ev_indptr[u + 1] >= ev_indptr[u] && uq_indptr[u + 1] >= uq_indptr[u], YUE_E_ARG, "indptr not monotone");
-        // a user who played the whole catalog has no negative: the reference would spin forever (BPR.py:47-48)
-        REQUIRE(uq_indptr[u + 1] - uq_indptr[u] < n || ev_indptr[u + 1] == ev_indptr[u], YUE_E_ARG,
-                "user " + std::to_string(u + h->user_begin) + " played every track: no negative exists");
+    PhaseTimer pt;
+    {   // validation on the host cores: monotone indptr; a user who played the whole catalog has no negative
+        // (the reference would spin forever, BPR.py:47-48)
+        const size_t nth = m_local < 65536 ? 1 : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<int64_t> bad_mono(nth, -1), bad_full(nth, -1);
+        auto check = [&](size_t t) {
+            for (int64_t u = m_local * (int64_t)t / (int64_t)nth, e = m_local * (int64_t)(t + 1) / (int64_t)nth; u < e; ++u) {
+                if (!(ev_indptr[u + 1] >= ev_indptr[u] && uq_indptr[u + 1] >= uq_indptr[u])) { bad_mono[t] = u; return; }
+                if (!(uq_indptr[u + 1] - uq_indptr[u] < n || ev_indptr[u + 1] == ev_indptr[u])) { bad_full[t] = u; return; }
+            }
+        };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nth; ++t) th.emplace_back(check, t);
+        check(0);
+        for (auto& x : th) x.join();
+        for (size_t t = 0; t < nth; ++t) {
+            REQUIRE(bad_mono[t] < 0, YUE_E_ARG, "indptr not monotone");
+            REQUIRE(bad_full[t] < 0, YUE_E_ARG, "user " + std::to_string(bad_full[t] + h->user_begin) + " played every track: no negative exists");
+        }
     }
-    h->h_ev_indptr.assign(ev_indptr, ev_indptr + m_local + 1);
-    h->h_uq_indptr.assign(uq_indptr, uq_indptr + m_local + 1);
+    h->h_ev_indptr.clear(); h->h_uq_indptr.clear();       // host copies are fetched back on demand (host_indptrs)
     h->have_ev_user = false;
     h->have_log = false;
     h->last_rank_B = 0;
+    pt.lap("validate + host copies");
 
     // concurrency: at most one resident wave, fewer warps on small logs (bounds Hogwild staleness
     // and keeps the in-flight window a small fraction of the users)
@@ -392,6 +419,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     const ItemPlanArgs plan{true, item_segs, h->max_items_per_user, h->item_group_segs, h->seg_events, uq_indptr};
     CK(plan_items((size_t)m_local, [=](size_t r, int64_t& b, int64_t& e, int32_t& u) { b = ev_indptr[r]; e = ev_indptr[r + 1]; u = (int32_t)r; },
                   plan, h->pin_rec, h->pin_items, h->nseg, h->n_items));
+    pt.lap("plan segments/items");
     CK(h->seg_rec.resize(h->nseg)); CK(h->item_ptr.resize(2 * h->n_items)); CK(h->cursor.resize(1));
     if (h->nseg) CK(cudaMemcpyAsync(h->seg_rec.p, h->pin_rec.p, h->nseg * sizeof(SegRec), cudaMemcpyHostToDevice, h->stream));
     if (h->n_items) CK(cudaMemcpyAsync(h->item_ptr.p, h->pin_items.p, 2 * h->n_items * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
@@ -403,20 +431,24 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
         CK(h->item_counts.resize(n));
         CK(cudaMemsetAsync(h->item_counts.p, 0, n * sizeof(int32_t), h->stream));
         const int grid = (int)std::min<int64_t>((T + 255) / 256, (int64_t)h->sm_count * 16);
-        item_count_kernel<<<grid, 256, 0, h->stream>>>(h->ev_items.p, T, h->item_counts.p);
+        // every stride-th event is enough to find tracks with > 1/hot_div of the plays, and keeps the atomics on the
+        // counters of those very tracks short (all 50 M events of C2: 5 ms, 3.9 M of them on one address)
+        const int64_t stride = std::max<int64_t>(1, std::min<int64_t>(64, T >> 20));
+        item_count_kernel<<<grid, 256, 0, h->stream>>>(h->ev_items.p, T, stride, h->item_counts.p);
         ++h->launches;
         CK(cudaGetLastError());
         std::vector<int32_t> counts((size_t)n);
         CK(cudaMemcpyAsync(counts.data(), h->item_counts.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        pt.lap("wait: uploads + histogram");
         std::vector<int32_t> cand;
         for (int64_t t = 0; t < n; ++t)
-            if (counts[t] >= h->hot_min_count && (int64_t)counts[t] * h->hot_div > T) cand.push_back((int32_t)t);
+            if ((int64_t)counts[t] * stride >= h->hot_min_count && (int64_t)counts[t] * stride * h->hot_div > T) cand.push_back((int32_t)t);
         std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return counts[a] != counts[b] ? counts[a] > counts[b] : a < b; });
         if ((int)cand.size() > h->hot_max) cand.resize(h->hot_max);
         h->n_hot = (int)cand.size();
         h->h_hot_counts.clear();
-        for (int32_t t : cand) h->h_hot_counts.push_back(counts[t]);
+        for (int32_t t : cand) h->h_hot_counts.push_back((int32_t)std::min<int64_t>(counts[t] * stride, INT32_MAX));
         h->h_hot_items = cand;
         h->hot_meta_cap = 0;
         if (h->n_hot) {
@@ -428,7 +460,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
             for (int32_t s2 : order) { sorted_ids.push_back(cand[s2]); sorted_slots.push_back(s2); }
             std::vector<int32_t> dx((size_t)h->n_hot, 0);       // second rows for the most played tracks (blocked kernel)
             for (int s2 = 0, extra = 0; s2 < h->n_hot && extra < kHotExtra; ++s2)
-                if ((int64_t)counts[cand[s2]] * h->hot_shard_div > T) {
+                if ((int64_t)counts[cand[s2]] * stride * h->hot_shard_div > T) {
                     dx[s2] = (int32_t)((hot_slot_offset(h->n_hot + extra) - hot_slot_offset(s2)) * sizeof(float));
                     ++extra;
                 }
@@ -447,6 +479,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
         }
     }
     CK(cudaStreamSynchronize(h->stream));      // host vectors die here
+    pt.lap("hot tracks");
     h->have_log = true;
     return YUE_OK;
 }
@@ -675,8 +708,19 @@ static int q_interleaved(yue_t* h) {
     return YUE_OK;
 }
 
+// host copies of the two indptr arrays, for the rarely used paths that need them (check hooks)
+static int host_indptrs(yue_t* h) {
+    if ((int64_t)h->h_ev_indptr.size() == h->m + 1) return YUE_OK;
+    h->h_ev_indptr.resize((size_t)h->m + 1); h->h_uq_indptr.resize((size_t)h->m + 1);
+    CK(cudaMemcpyAsync(h->h_ev_indptr.data(), h->ev_indptr.p, (h->m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_uq_indptr.data(), h->uq_indptr.p, (h->m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
 static int ensure_ev_user(yue_t* h) {
     if (h->have_ev_user) return YUE_OK;
+    if (int rc = host_indptrs(h)) return rc;
     std::vector<int32_t> eu((size_t)h->T);
     for (int64_t u = 0; u < h->m; ++u)
         std::fill(eu.begin() + h->h_ev_indptr[u], eu.begin() + h->h_ev_indptr[u + 1], (int32_t)u);
@@ -877,6 +921,7 @@ static int sgd_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t
     }
     const int n_warps = mode == YUE_MODE_SERIAL ? 1
         : (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * h->warps_per_sm, T / h->min_events_per_warp));
+    if (int rc = host_indptrs(h)) return rc;
     const ItemPlanArgs plan{mode != YUE_MODE_SERIAL, std::max<int64_t>(32, std::min<int64_t>(256, T / ((int64_t)n_warps * 4 * 32))),
                             h->max_items_per_user, mode == YUE_MODE_SERIAL ? 1 : h->item_group_segs, 32, h->h_uq_indptr.data()};
     int64_t nseg = 0, nitems = 0;
