@@ -63,9 +63,11 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if os.environ.get("YUE_BENCH_NO_CLOCKS"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("YUE_BENCH_CLOCKS_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -174,11 +176,11 @@ def run_native(args):
     mode = MODE_HOGWILD_STORE if args.sgd_mode == "store" else MODE_HOGWILD
     hbm_peak, bf16_peak, peak_kind = peaks()
 
-    eng = Engine(local)
     log = synth.power_law_log_torch(wl["users"], wl["tracks"], wl["plays"], SEED + rank, device="cuda")
     T = log.train_size
     m, n = log.m, log.n
     torch.cuda.empty_cache()
+    eng = Engine(local)
     # the host copy of the play log lives in pinned memory (DMA source of the e2e step)
     pins = []
     for name in ("ev_indptr", "ev_items", "uq_indptr", "uq_items"):

@@ -163,6 +163,8 @@ template <int V> __host__ __device__ __forceinline__ size_t hot_lane_offset(int 
     return (size_t)((V * lane) >> 3) * kHotPlaneFloats + ((V * lane) & 7);
 }
 constexpr size_t kHotTableFloats = (size_t)16 * kHotPlaneFloats;           // up to 16 sectors (ld = 128)
+constexpr int kHotCandidates = 8;        // placements of the table the first launch on a log times (yue_b200.cu)
+constexpr int kHotCandidateStep = 11;    // granules between them
 
 template <int V>
 __global__ void hot_gather_kernel(const float* __restrict__ Q, float* __restrict__ hotQ, const int32_t* __restrict__ hot_items,

@@ -116,6 +116,16 @@ struct yue_handle {
     // the chain of dependent atomics on one address stays below ~T/hot_div updates (~11 ns each).
     int hot_max = kHotSlots;
     int hot_min_count = 16384;
+    // Where the hot-row table starts inside its allocation, in 256-byte granules.  Which L2 slices the table's
+    // sectors share with each other and with the rest of the working set depends on physical addresses the
+    // library cannot see: the same epoch measured 12.6 to 15.5 ms at config C2 depending on nothing but where
+    // the buffers happened to land (profiles/microbench/README.md).  So the placement is MEASURED: the first
+    // Hogwild launch on a log times 1/32 of the epoch with lr = 0 (state untouched) for kHotCandidates offsets
+    // and keeps the fastest; the choice is remembered while the table and the hot set stay the same.
+    int hot_offset_granules = 0;
+    int hot_offset_forced = -1;       // YUE_HOT_OFFSET_GRANULES (experiments): >= 0 disables the calibration
+    uint64_t hot_calibrated_key = 0;
+    std::vector<float> hot_calibration_ms;   // per candidate, of the last calibration (diagnostics)
     int hot_div = 128;
     int hot_shard_div = 40;           // blocked kernel: a track played by more than 1/hot_shard_div of the events gets two rows
     int n_hot = 0;
@@ -330,6 +340,8 @@ int yue_create(int device, yue_t** out) {
     }
     h->sm_count = prop.multiProcessorCount;
     h->l2_bytes = (size_t)prop.l2CacheSize;
+    if (const char* s = getenv("YUE_PAD_MB")) { void* pad = nullptr; cudaMalloc(&pad, (size_t)atoi(s) << 20); }   // experiments: shift the placement of later buffers
+    if (const char* s = getenv("YUE_HOT_OFFSET_GRANULES")) h->hot_offset_forced = std::max(0, std::min(kHotCandidates * kHotCandidateStep, atoi(s)));
     if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(kHotSlots, atoi(s)));
     if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_HOT_DIV")) h->hot_div = std::max(1, atoi(s));
@@ -466,7 +478,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
                 }
             CK(h->hot_dx.resize(h->n_hot));
             CK(cudaMemcpyAsync(h->hot_dx.p, dx.data(), dx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            CK(h->hot_sorted.resize(h->n_hot)); CK(h->hot_sorted_slot.resize(h->n_hot)); CK(h->hotQ.resize(kHotTableFloats));
+            CK(h->hot_sorted.resize(h->n_hot)); CK(h->hot_sorted_slot.resize(h->n_hot)); CK(h->hotQ.resize(kHotTableFloats + (size_t)(kHotCandidates + 1) * kHotCandidateStep * 64));
             CK(cudaMemcpyAsync(h->hot_sorted.p, sorted_ids.data(), sorted_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(h->hot_sorted_slot.p, sorted_slots.data(), sorted_slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
             CK(h->hot_items.resize(h->n_hot)); CK(h->hot_slot.resize(n));
@@ -805,11 +817,45 @@ static int ensure_hot_meta(yue_t* h, int cap) {
     return YUE_OK;
 }
 
+// see yue_handle::hot_offset_granules
+static int calibrate_hot_offset(yue_t* h, SgdParams sp, int wpc) {
+    uint64_t key = (uint64_t)(uintptr_t)h->hotQ.p * 1000003ull + (uint64_t)h->n_hot * 7919ull + (uint64_t)h->ld * 31ull + (uint64_t)h->T;
+    for (int32_t t : h->h_hot_items) key = key * 6364136223846793005ull + (uint64_t)t + 1442695040888963407ull;
+    if (key == 0) key = 1;
+    if (h->hot_calibrated_key == key) return YUE_OK;
+    h->hot_calibrated_key = key;
+    if (h->hot_offset_forced >= 0) { h->hot_offset_granules = h->hot_offset_forced; return YUE_OK; }
+    h->hot_offset_granules = 0;
+    const int64_t n_items = sp.n_work;
+    if (h->T < ((int64_t)1 << 22) || n_items < 4096) return YUE_OK;      // small logs: not worth 8 probes
+    sp.lr = 0.f; sp.c_u = 0.f; sp.c_i = 0.f; sp.lr_d = 0.0; sp.loss = h->scal.p + 3; sp.ev_neg = nullptr;
+    sp.item_first = n_items / 3; sp.n_work = sp.item_first + std::max<int64_t>(1024, n_items / 32);
+    sp.n_work = std::min(sp.n_work, n_items);
+    h->hot_calibration_ms.assign(kHotCandidates, 0.f);
+    float best = 1e30f;
+    for (int c = 0; c < kHotCandidates; ++c) {
+        sp.hotQ = h->hotQ.p + (size_t)c * kHotCandidateStep * 64;
+        const unsigned long long c0 = (unsigned long long)sp.item_first;
+        CK(cudaMemcpyAsync(h->cursor.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(h->ev0, h->stream));
+        switch (h->ld) {
+            case 32: CK(launch_sgd_blk<1, false>(sp, wpc, h->stream, h->launches)); break;
+            case 64: CK(launch_sgd_blk<2, false>(sp, wpc, h->stream, h->launches)); break;
+            default: CK(launch_sgd_blk<4, false>(sp, wpc, h->stream, h->launches)); break;
+        }
+        ++h->launches;
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->hot_calibration_ms[c] = ms;
+        if (ms < best) { best = ms; h->hot_offset_granules = c * kHotCandidateStep; }
+    }
+    return YUE_OK;
+}
+
 static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr = false) {
     REQUIRE(mode >= YUE_MODE_SERIAL && mode <= YUE_MODE_HOGWILD_STORE, YUE_E_ARG, "unknown mode");
-    CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
-    if (sp.item_first == 0) CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
-    else { const unsigned long long c0 = (unsigned long long)sp.item_first; CK(cudaMemcpyAsync(h->cursor.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
     sp.cursor = h->cursor.p;
     const bool blk = use_blk_kernel(h, mode, apr);
     { int rb = 1; while (rb * 2 * kBlkK <= sp.resync_events) rb *= 2; sp.resync_mask = rb - 1; }
@@ -818,12 +864,19 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr 
     sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
     if (sp.n_hot > 0) {
-        if (blk) { sp.hotQ = h->hotQ.p; sp.hot_sorted = h->hot_sorted.p; sp.hot_sorted_slot = h->hot_sorted_slot.p; sp.hot_dx = h->hot_dx.p; }
+        if (blk) {
+            sp.hot_sorted = h->hot_sorted.p; sp.hot_sorted_slot = h->hot_sorted_slot.p; sp.hot_dx = h->hot_dx.p;
+            if (int rc = calibrate_hot_offset(h, sp, std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm)))) return rc;
+            sp.hotQ = h->hotQ.p + (size_t)h->hot_offset_granules * 64;
+        }
         else {
             if (int rc = ensure_hot_meta(h, kHotShards)) return rc;
             sp.hot_meta = h->hot_meta.p; sp.hot_shards = h->hot_shards.p;
         }
     }
+    CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), h->stream));
+    if (sp.item_first == 0) CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
+    else { const unsigned long long c0 = (unsigned long long)sp.item_first; CK(cudaMemcpyAsync(h->cursor.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
     const int nch = (sp.nchunks + 15) / 16;
     const int wpc = std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm));
     if (blk) {
