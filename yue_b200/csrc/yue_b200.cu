@@ -340,7 +340,6 @@ int yue_create(int device, yue_t** out) {
     }
     h->sm_count = prop.multiProcessorCount;
     h->l2_bytes = (size_t)prop.l2CacheSize;
-    if (const char* s = getenv("YUE_PAD_MB")) { void* pad = nullptr; cudaMalloc(&pad, (size_t)atoi(s) << 20); }   // experiments: shift the placement of later buffers
     if (const char* s = getenv("YUE_HOT_OFFSET_GRANULES")) h->hot_offset_forced = std::max(0, std::min(kHotCandidates * kHotCandidateStep, atoi(s)));
     if (const char* s = getenv("YUE_SGD_HOT_MAX")) h->hot_max = std::max(0, std::min(kHotSlots, atoi(s)));
     if (const char* s = getenv("YUE_SGD_HOT_MIN_COUNT")) h->hot_min_count = std::max(1, atoi(s));
