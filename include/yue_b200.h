@@ -83,6 +83,12 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n,
                                const int64_t* ev_indptr, const int32_t* ev_items,
                                const int64_t* uq_indptr, const int32_t* uq_items);
 
+/* For shards that are not a contiguous range of users (yue_b200/sharding.py: interleaved_users): per local user,
+ * the offset that turns a local event index into the global one (global = local + delta[user]); replaces the
+ * single event_base of yue_set_interactions_shard so that the sampler stream stays that of the unsharded log.
+ * NULL switches back to event_base.  Reset by the next yue_set_interactions. */
+int yue_set_event_offsets(yue_t* h, const int64_t* delta);
+
 /* Builds the same arrays ON THE DEVICE from the events in file order: replaces the
  * array-building half of Record.preprocess (data/record.py:138-202: userRecord grouping 147-165,
  * testSet with the training pairs removed 182-202) and BPR.py:32-45 for logs whose users and tracks are

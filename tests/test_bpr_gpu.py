@@ -335,3 +335,35 @@ def test_sub_epochs_compose_to_the_epoch(engine):
     assert lp == pytest.approx(l0, rel=1e-6)
     with pytest.raises(YueError):
         engine.bpr_epoch_part(0.05, 0.01, 0.01, 3, 0, 2, 2, MODE_SERIAL)
+
+
+def test_sampler_invariant_under_interleaved_sharding(engine):
+    """Users r, r+G, r+2G, ... on rank r with per-user event offsets: every rank draws, for its events, exactly the
+    negatives the unsharded log gets (the sampler is a function of the GLOBAL event index)."""
+    from yue_b200 import sharding
+    log = synth.power_law_log(700, 500, 30000, seed=5)
+    ev_user = record_ref.ev_users(log.ev_indptr)
+    ref = philox.sample_negatives(11, 2, ev_user, log.n, log.uq_indptr, log.uq_items)
+    for world in (2, 3):
+        for rank in range(world):
+            users = sharding.interleaved_users(log.m, world, rank)
+            sh = sharding.local_shard_of_users(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, users)
+            engine.set_interactions(sh["m_local"], log.n, sh["ev_indptr"], sh["ev_items"], sh["uq_indptr"], sh["uq_items"])
+            engine.set_event_offsets(sh["event_offsets"])
+            got = engine.sample_negatives(11, 2)
+            want = np.concatenate([ref[log.ev_indptr[u]:log.ev_indptr[u + 1]] for u in users])
+            assert np.array_equal(got, want)
+    # and the epoch kernels use the same stream: a serial epoch on rank 0's shard with explicit negatives == in-kernel sampling
+    users = sharding.interleaved_users(log.m, 2, 0)
+    sh = sharding.local_shard_of_users(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, users)
+    P, Q = synth.init_factors(sh["m_local"], log.n, 64, seed=2)
+    engine.set_interactions(sh["m_local"], log.n, sh["ev_indptr"], sh["ev_items"], sh["uq_indptr"], sh["uq_items"])
+    engine.set_event_offsets(sh["event_offsets"])
+    engine.set_factors(P, Q)
+    la = engine.bpr_epoch(0.05, 0.01, 0.01, 11, 2, MODE_SERIAL)
+    Pa, Qa = engine.get_factors()
+    engine.set_factors(P, Q)
+    neg = engine.sample_negatives(11, 2)
+    lb = engine.bpr_apply(record_ref.ev_users(sh["ev_indptr"]), sh["ev_items"], neg, 0.05, 0.01, 0.01, MODE_SERIAL)
+    Pb, Qb = engine.get_factors()
+    assert np.array_equal(Pa, Pb) and np.array_equal(Qa, Qb) and la == pytest.approx(lb, rel=1e-12)

@@ -87,6 +87,7 @@ SIGNATURES = {
     "yue_timer_stop": (C.c_int, [_H, _f32p]),
     "yue_launch_count": (C.c_int, [_H, _i64p]),
     "yue_rank_stats": (C.c_int, [_H, _i64p, _i64p]),
+    "yue_set_event_offsets": (C.c_int, [_H, _i64p]),
     "yue_set_test_set": (C.c_int, [_H, _i64p, _i32p]),
     "yue_ingest_events": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, C.POINTER(C.c_uint8)]),
     "yue_interaction_sizes": (C.c_int, [_H, _i64p, _i64p, _i64p, _i64p, _i64p]),

@@ -85,7 +85,8 @@ struct SgdParams {
     const int32_t* uq_items;
     uint64_t seed;
     uint32_t epoch;
-    int64_t event_base;            // global index of local event 0
+    int64_t event_base;            // global index of local event 0 ...
+    const int64_t* ev_delta;       // ... or, when not null, per local user: global index = local index + ev_delta[user]
     float lr, c_u, c_i;            // lr, float(lr*regU), float(lr*regI)
     double lr_d;
     double* loss;                  // device accumulator of sum -log(s)
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
             const int64_t e = begin + lane;
             my_i = p.ev_items[e];
             my_j = p.ev_neg ? p.ev_neg[e]
-                            : sample_negative(p.seed, p.epoch, (uint64_t)(p.event_base + e), p.slot,
+                            : sample_negative(p.seed, p.epoch, (uint64_t)((p.ev_delta ? p.ev_delta[u] : p.event_base) + e), p.slot,
                                               p.n_items, row, row_len);
         }
         __syncwarp();
@@ -448,13 +449,13 @@ __global__ void __launch_bounds__(kSgdThreads, 1) bpr_sgd_kernel(const SgdParams
 __global__ void sample_negatives_kernel(int64_t T, const int32_t* __restrict__ ev_user,
                                         const int64_t* __restrict__ uq_indptr,
                                         const int32_t* __restrict__ uq_items, uint64_t seed,
-                                        uint32_t epoch, uint32_t slot, int64_t event_base,
+                                        uint32_t epoch, uint32_t slot, int64_t event_base, const int64_t* __restrict__ ev_delta,
                                         uint32_t n_items, int32_t* __restrict__ out) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int u = ev_user[e];
         const int64_t r0 = uq_indptr[u];
-        out[e] = sample_negative(seed, epoch, (uint64_t)(event_base + e), slot, n_items,
+        out[e] = sample_negative(seed, epoch, (uint64_t)((ev_delta ? ev_delta[u] : event_base) + e), slot, n_items,
                                  uq_items + r0, (int)(uq_indptr[u + 1] - r0));
     }
 }

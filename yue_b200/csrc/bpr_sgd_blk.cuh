@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                         const int64_t e = rec_begin(na) + lane;
                         n_i = p.ev_items[e];             // hot positives arrive re-labelled -slot-1
                         n_j = p.ev_neg ? p.ev_neg[e]    // K1: lane t draws the negative of event begin+t
-                                       : sample_negative(p.seed, p.epoch, (uint64_t)(p.event_base + e), p.slot,
+                                       : sample_negative(p.seed, p.epoch, (uint64_t)((p.ev_delta ? p.ev_delta[n_u] : p.event_base) + e), p.slot,
                                                          p.n_items, p.uq_items + rec_row(nb), nb.z);
                         if (p.n_hot > 0) {               // a negative that happens to be a hot track lives in the table too
                             int lo = 0, hi = p.n_hot;

@@ -144,7 +144,8 @@ struct yue_handle {
     // play log (local shard)
     int64_t m = 0, n = 0, T = 0, nnz = 0, user_begin = 0, event_base = 0;
     bool have_log = false;
-    DevBuf<int64_t> ev_indptr, uq_indptr;
+    DevBuf<int64_t> ev_indptr, uq_indptr, ev_delta;
+    bool have_ev_delta = false;
     DevBuf<int32_t> ev_items, uq_items, ev_user;
     bool have_ev_user = false;
     std::vector<int64_t> h_ev_indptr;
@@ -364,7 +365,7 @@ int yue_destroy(yue_t* h) {
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     rank_tc_release(h->tc);
-    for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->item_ptr, &h->tmp_ws}) b->release();
+    for (auto* b : {&h->ev_indptr, &h->uq_indptr, &h->ev_delta, &h->item_ptr, &h->tmp_ws}) b->release();
     h->seg_rec.release(); h->tmp_rec.release(); h->pin_rec.release(); h->pin_items.release();
     h->cursor.release();
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->tmp_i, &h->tmp_j, &h->rk_part_ids, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot, &h->hot_dx}) b->release();
@@ -418,6 +419,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     h->h_ev_indptr.clear(); h->h_uq_indptr.clear();       // host copies are fetched back on demand (host_indptrs)
     h->have_ev_user = false;
     h->have_log = false;
+    h->have_ev_delta = false;
     h->last_rank_B = 0;
     pt.lap("validate + host copies");
 
@@ -664,6 +666,17 @@ int yue_get_test_set(yue_t* h, int64_t* test_indptr, int32_t* test_items) {
     return YUE_OK;
 }
 
+int yue_set_event_offsets(yue_t* h, const int64_t* delta) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "call yue_set_interactions first");
+    CK(cudaSetDevice(h->device));
+    if (!delta) { h->have_ev_delta = false; return YUE_OK; }
+    CK(h->ev_delta.resize(std::max<int64_t>(h->m, 1)));
+    if (h->m) CK(cudaMemcpyAsync(h->ev_delta.p, delta, h->m * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_ev_delta = true;
+    return YUE_OK;
+}
+
 int yue_set_factors(yue_t* h, int k, const float* P, const float* Q) {
     REQUIRE(h && P && Q, YUE_E_ARG, "null argument");
     REQUIRE(h->have_log, YUE_E_STATE, "call yue_set_interactions first (it fixes m and n)");
@@ -751,7 +764,7 @@ int yue_sample_negatives(yue_t* h, uint64_t seed, uint32_t epoch, uint32_t slot,
     CK(h->tmp_j.resize(h->T));
     const int grid = (int)std::min<int64_t>((h->T + 255) / 256, (int64_t)h->sm_count * 16);
     sample_negatives_kernel<<<grid, 256, 0, h->stream>>>(h->T, h->ev_user.p, h->uq_indptr.p, h->uq_items.p, seed, epoch,
-                                                         slot, h->event_base, (uint32_t)h->n, h->tmp_j.p);
+                                                         slot, h->event_base, h->have_ev_delta ? h->ev_delta.p : nullptr, (uint32_t)h->n, h->tmp_j.p);
     ++h->launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(j_out, h->tmp_j.p, h->T * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -936,7 +949,7 @@ static int sgd_epoch(yue_t* h, double lr, double regU, double regI, uint64_t see
     sp.ev_items = h->ev_items.p; sp.ev_neg = nullptr;
     sp.hot_items = h->hot_items.p; sp.n_hot = h->n_hot;
     sp.resync_events = h->resync_events;
-    sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base; sp.slot = slot;
+    sp.seed = seed; sp.epoch = epoch; sp.event_base = h->event_base; sp.ev_delta = h->have_ev_delta ? h->ev_delta.p : nullptr; sp.slot = slot;
     sp.eps = (float)eps; sp.regA = (float)regA;
     return run_sgd(h, sp, mode, loss_out, apr);
 }

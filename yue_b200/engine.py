@@ -126,6 +126,13 @@ class Engine:
         self._ck(self.lib.yue_get_test_set(self.h, _ptr(indptr, C.c_int64), _ptr(items, C.c_int32)))
         return indptr, items
 
+    def set_event_offsets(self, delta):
+        """Per local user: global event index = local index + delta[user] (non-contiguous shards)."""
+        delta = _as(delta, np.int64)
+        if len(delta) != self.m:
+            raise ValueError("one offset per local user")
+        self._ck(self.lib.yue_set_event_offsets(self.h, _ptr(delta, C.c_int64)))
+
     def set_factors(self, P, Q):
         P, Q = _as(P, np.float32), _as(Q, np.float32)
         if P.shape[0] != self.m or Q.shape[0] != self.n or P.shape[1] != Q.shape[1]:

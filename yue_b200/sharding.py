@@ -34,6 +34,35 @@ def local_shard(ev_indptr, ev_items, uq_indptr, uq_items, bounds, rank):
                 uq_indptr=np.ascontiguousarray(uq_indptr[u0:u1 + 1] - q0), uq_items=np.ascontiguousarray(uq_items[q0:q1]))
 
 
+def interleaved_users(m, world, rank):
+    """Users rank, rank + world, rank + 2*world, ... -- the sharding that keeps every rank at the SAME position of
+    the reference's user stream (recommender/cf/BPR.py:42) at the same time.  Contiguous ranges do not: with the
+    heavy users of a power-law log on one rank and the light ones on another, the light users train for a whole
+    epoch against a Q that has not seen the heavy users' updates, which the serial order applies FIRST
+    (measured at config C2 on 2 GPUs, profiles/quality_study_r1.md section E: Recall@10 0.0004 instead of 0.098)."""
+    return np.arange(rank, m, world, dtype=np.int64)
+
+
+def local_shard_of_users(ev_indptr, ev_items, uq_indptr, uq_items, users):
+    """Rebased CSR of an arbitrary increasing list of users (their events in the original order) and, per local
+    user, the offset that turns a local event index into the global one (for yue_set_event_offsets: the sampler
+    stream is a function of the GLOBAL event index, so the negatives do not depend on the sharding)."""
+    ev_indptr, uq_indptr = np.asarray(ev_indptr, dtype=np.int64), np.asarray(uq_indptr, dtype=np.int64)
+    users = np.asarray(users, dtype=np.int64)
+
+    def take(indptr, items):
+        deg = indptr[users + 1] - indptr[users]
+        loc = np.zeros(len(users) + 1, dtype=np.int64)
+        np.cumsum(deg, out=loc[1:])
+        delta = indptr[users] - loc[:-1]
+        idx = np.repeat(delta, deg) + np.arange(int(loc[-1]), dtype=np.int64)
+        return loc, np.ascontiguousarray(np.asarray(items)[idx]), delta
+    ev_loc, ev_it, ev_delta = take(ev_indptr, ev_items)
+    uq_loc, uq_it, _ = take(uq_indptr, uq_items)
+    return dict(m_local=len(users), users=users, ev_indptr=ev_loc, ev_items=ev_it, uq_indptr=uq_loc, uq_items=uq_it,
+                event_offsets=np.ascontiguousarray(ev_delta))
+
+
 def reconcile_q(q_local, q_snapshot, all_reduce_sum):
     """Q <- snapshot + sum over ranks of (Q_rank - snapshot).  `all_reduce_sum(t)` sums a tensor over
     the ranks in place.  Works on any torch tensors (CPU for the gloo tests, the library's device
@@ -42,6 +71,22 @@ def reconcile_q(q_local, q_snapshot, all_reduce_sum):
     all_reduce_sum(delta)
     q_new = q_snapshot + delta
     return q_new
+
+
+def saturation_weights(global_counts, world, sub_epochs, kappa):
+    """Per-track factor for the summed Q deltas.  A row touched c times between two exchanges on every one of G
+    ranks moves, on each rank, towards the same equilibrium: with a per-touch contraction exp(-kappa) the ranks'
+    deltas are each (1 - a)(q* - q), a = exp(-kappa c), while the serial order would have moved the row by
+    (1 - a^G)(q* - q).  The sum of the deltas is therefore scaled by (1 - a^G) / (G (1 - a)): 1 for rarely played
+    tracks (the deltas are independent and add up), 1/G for the most played ones (every rank has already done
+    the whole move; summing would overshoot G times -- measured, profiles/quality_study_r1.md section E)."""
+    c = np.asarray(global_counts, dtype=np.float64) / float(world * sub_epochs)
+    a = np.exp(-kappa * c)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        w = (1.0 - a ** world) / (world * (1.0 - a))
+    w[~np.isfinite(w)] = 1.0
+    w[c * kappa < 1e-6] = 1.0
+    return w.astype(np.float32)
 
 
 class _DevAlias:
@@ -55,9 +100,10 @@ class ShardedTrainer:
     """One rank of the user-sharded trainer.  `engine` already holds this rank's shard
     (Engine.set_interactions(..., user_begin, event_base)) and factors (local P rows, full Q)."""
 
-    def __init__(self, engine, dist, device, sub_epochs=1):
+    def __init__(self, engine, dist, device, sub_epochs=1, row_weights=None):
         import torch
         self.sub_epochs = int(sub_epochs)
+        self.w = None if row_weights is None else torch.as_tensor(row_weights, dtype=torch.float32, device=device)
         from ._lib import BUF_Q_DELTA
         self.eng, self.dist, self.torch = engine, dist, torch
         engine.q_snapshot()
@@ -70,6 +116,8 @@ class ShardedTrainer:
         self.eng.q_delta_pack()
         with self.torch.cuda.stream(self.stream):        # NCCL ordered on the library's stream
             self.dist.all_reduce(self.delta)
+            if self.w is not None:                       # saturation-aware combination, see saturation_weights
+                self.delta.view(self.w.numel(), -1).mul_(self.w[:, None])
         self.eng.q_delta_apply()
 
     def epoch(self, lr, regU, regI, seed, epoch, mode, want_loss=False):
