@@ -204,8 +204,12 @@ def run_native(args):
     upload()
     trainer = None
     if world > 1:                                   # user-sharded: dQ all-reduced once per step (yue_b200/sharding.py)
-        from yue_b200.sharding import ShardedTrainer
-        trainer = ShardedTrainer(eng, dist, torch.device("cuda", local), sub_epochs=args.sub_epochs)
+        from yue_b200.sharding import ShardedTrainer, saturation_weights
+        # plays per track over all ranks -> per-track factor for the summed deltas (profiles/quality_study_r1.md section E)
+        cnt = torch.from_numpy(np.bincount(log.ev_items, minlength=n)).to("cuda")
+        dist.all_reduce(cnt)
+        w = saturation_weights(cnt.cpu().numpy(), world, args.sub_epochs, 0.05 * LR)
+        trainer = ShardedTrainer(eng, dist, torch.device("cuda", local), sub_epochs=args.sub_epochs, row_weights=w)
 
     def step(epoch, want_loss=False):
         if trainer is not None:
@@ -301,7 +305,7 @@ def run_native(args):
             "config": {"workload": wl["name"], "d": D, "triplets_per_step_per_gpu": T, "lr": LR,
                        "reg": [REG_U, REG_I], "sgd_mode": "hogwild_" + ("store" if mode == MODE_HOGWILD_STORE else "atomic_delta"),
                        "l2": "inputs exceed L2 (P 256 MB + log 400 MB per step; Q 51 MB is L2-resident by nature)",
-                       "parallelism": ("user-sharded, Q replicated, %d all-reduce(s) of dQ per step" % args.sub_epochs) if world > 1 else "single GPU"},
+                       "parallelism": ("user-sharded, Q replicated, %d all-reduce(s) of dQ per step, saturation-weighted sum" % args.sub_epochs) if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "what": "set_interactions + set_factors (pinned) + bpr_epoch + frob2 + get_factors"},
             "gpu_launches": int(launches),
