@@ -44,8 +44,9 @@ enum {
 enum {
     YUE_MODE_SERIAL = 0,        /* one warp, events strictly in order: reproduces the
                                    reference loop given the same negatives (parity mode) */
-    YUE_MODE_HOGWILD = 1,       /* throughput mode: contiguous event slices per warp, row
-                                   changes published as vector atomic deltas            */
+    YUE_MODE_HOGWILD = 1,       /* throughput mode: warps pull users from a cursor in stream
+                                   order, a user's triplets stay in order inside a warp, row
+                                   changes are published as vector atomic deltas          */
     YUE_MODE_HOGWILD_STORE = 2  /* as HOGWILD but plain stores (last writer wins)         */
 };
 

@@ -1,4 +1,7 @@
-// K1+K2: fused negative sampler + BPR triplet update (replaces recommender/cf/BPR.py:42-58).
+// K1+K2, general form: fused negative sampler + BPR triplet update (replaces recommender/cf/BPR.py:42-58).
+// This kernel is the serial-order parity anchor and the Hogwild path for row widths other than 32/64/128 floats
+// and for the plain-store mode; the throughput path for the benchmark shapes is bpr_sgd_blk.cuh (same work
+// decomposition and sampler, four triplets per block).  SgdParams, SegRec and the small helper kernels live here.
 //
 // Work decomposition.  Events are stored user-major (BPR.py:42-45).  The host cuts every
 // user's event range into SEGMENTS of <= 32 consecutive events and groups them into WORK ITEMS:
