@@ -88,3 +88,41 @@ def test_two_rank_gloo_reconciliation_equals_sum_of_deltas():
         Q = Q + ((qs[0] - Q) + (qs[1] - Q))
     assert np.array_equal(Qa, Q)
     assert np.array_equal(Pa, Pl[0]) and np.array_equal(Pb, Pl[1])
+
+
+def test_interleaved_shards_partition_the_log():
+    """interleaved_users + local_shard_of_users: every user on exactly one rank, events and play rows intact and in
+    order, event offsets map local event indices back to the unsharded log's."""
+    from yue_b200 import synth
+    log = synth.power_law_log(101, 60, 5000, seed=2)
+    seen = []
+    for world in (1, 2, 4):
+        total_events = 0
+        for rank in range(world):
+            users = sharding.interleaved_users(log.m, world, rank)
+            sh = sharding.local_shard_of_users(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, users)
+            assert sh["m_local"] == len(users) and sh["ev_indptr"][0] == 0 and sh["uq_indptr"][0] == 0
+            for k, u in enumerate(users):
+                a, b = sh["ev_indptr"][k], sh["ev_indptr"][k + 1]
+                assert np.array_equal(sh["ev_items"][a:b], log.ev_items[log.ev_indptr[u]:log.ev_indptr[u + 1]])
+                assert a + sh["event_offsets"][k] == log.ev_indptr[u]
+                a, b = sh["uq_indptr"][k], sh["uq_indptr"][k + 1]
+                assert np.array_equal(sh["uq_items"][a:b], log.uq_items[log.uq_indptr[u]:log.uq_indptr[u + 1]])
+            total_events += int(sh["ev_indptr"][-1])
+            seen.append(users)
+        assert total_events == log.train_size
+    assert np.array_equal(np.sort(np.concatenate(seen[-4:])), np.arange(log.m))
+
+
+def test_saturation_weights_limits():
+    """1 for tracks that are (almost) never played between two exchanges, 1/G for the most played ones, monotone."""
+    counts = np.array([0, 1, 100, 10_000, 1_000_000, 100_000_000])
+    for world in (2, 4, 8):
+        w = sharding.saturation_weights(counts, world, sub_epochs=8, kappa=1e-3)
+        assert w[0] == 1.0 and abs(w[1] - 1.0) < 1e-3
+        assert abs(w[-1] - 1.0 / world) < 1e-6
+        assert np.all(np.diff(w) <= 1e-7)
+    # the closed form: G ranks each contracting by a reproduce one stream contracting by a^G
+    a, G = 0.7, 4
+    w = sharding.saturation_weights(np.array([-np.log(a) / 1e-3 * G * 8]), G, 8, 1e-3)[0]
+    assert abs(w * G * (1 - a) - (1 - a ** G)) < 1e-6
