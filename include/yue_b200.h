@@ -177,7 +177,12 @@ int yue_rank_metrics(yue_t* h, int n_cuts, const int32_t* cuts, double* sums_out
  *      (the reference has no collective anywhere). ---- */
 int yue_q_snapshot(yue_t* h);       /* snapshot <- Q                                        */
 int yue_q_delta_pack(yue_t* h);     /* delta <- Q - snapshot                                */
-int yue_q_delta_apply(yue_t* h);    /* Q <- snapshot + delta (after the reduction); snapshot <- Q */
+int yue_q_delta_apply(yue_t* h);    /* Q <- snapshot + w * delta (after the reduction); snapshot <- Q */
+/* Per-track factor w[n] applied to the summed deltas by yue_q_delta_apply / yue_allreduce_q_delta (NULL: 1).
+ * The sum of the ranks' deltas overshoots for tracks played thousands of times between two exchanges (every
+ * rank has already moved the row to its equilibrium); yue_b200/sharding.py: saturation_weights computes
+ * (1 - a^G) / (G (1 - a)), a = exp(-kappa * plays per rank and exchange).  DESIGN.md section 6. */
+int yue_set_delta_weights(yue_t* h, const float* w);
 int yue_device_buffer(yue_t* h, int which, void** dev_ptr, size_t* bytes);
 int yue_stream(yue_t* h, void** cuda_stream);
 /* NCCL path for non-Python hosts: id is an ncclUniqueId (128 bytes) from yue_comm_unique_id

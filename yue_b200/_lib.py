@@ -78,6 +78,7 @@ SIGNATURES = {
     "yue_q_snapshot": (C.c_int, [_H]),
     "yue_q_delta_pack": (C.c_int, [_H]),
     "yue_q_delta_apply": (C.c_int, [_H]),
+    "yue_set_delta_weights": (C.c_int, [_H, _f32p]),
     "yue_device_buffer": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "yue_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "yue_comm_unique_id": (C.c_int, [C.c_void_p]),

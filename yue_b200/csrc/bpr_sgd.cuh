@@ -542,11 +542,15 @@ __global__ void q_delta_pack_kernel(const float4* __restrict__ q, const float4* 
         delta[i] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
     }
 }
+// Q = snapshot + w[row] * (sum of the ranks' deltas); w = nullptr: plain sum.  w is the per-track factor of
+// yue_b200/sharding.py: saturation_weights (1 for rarely played tracks, 1/G for the most played ones).
 __global__ void q_delta_apply_kernel(float4* __restrict__ q, float4* __restrict__ snap,
-                                     const float4* __restrict__ delta, size_t n4) {
+                                     const float4* __restrict__ delta, const float* __restrict__ w, int per_row4, size_t n4) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
          i += (size_t)gridDim.x * blockDim.x) {
-        const float4 b = snap[i], d = delta[i];
+        const float4 b = snap[i];
+        float4 d = delta[i];
+        if (w) { const float f = w[i / per_row4]; d.x *= f; d.y *= f; d.z *= f; d.w *= f; }
         const float4 r = make_float4(b.x + d.x, b.y + d.y, b.z + d.z, b.w + d.w);
         q[i] = r;
         snap[i] = r;

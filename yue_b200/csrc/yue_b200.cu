@@ -167,7 +167,8 @@ struct yue_handle {
     // factors
     int k = 0, ld = 0;
     bool have_factors = false;
-    DevBuf<float> P, Q, Qsnap, Qdelta;
+    DevBuf<float> P, Q, Qsnap, Qdelta, delta_w;
+    bool have_delta_w = false;
     // interleaved working copy of Q for the SGD kernels (d = 64); exactly one of the two is current
     DevBuf<float> Qilv;
     bool use_ilv = false, ilv_current = false, rowmajor_current = true;   // measured: no gain (the limit is per address, not per slice)
@@ -242,6 +243,14 @@ static int q_interleaved(yue_t* h);
 struct ItemPlanArgs {
     bool allow_shared; int64_t item_segs, max_items, group_segs; int seg_events; const int64_t* uq_indptr;
 };
+// host threads a handle may use for planning: the cores divided by the processes that share the box
+// (LOCAL_WORLD_SIZE is set by torchrun: one process per GPU), at most 16
+static size_t host_threads() {
+    size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* s = getenv("LOCAL_WORLD_SIZE")) hw = std::max<size_t>(1, hw / (size_t)std::max(1, atoi(s)));
+    return std::min<size_t>(16, hw);
+}
+
 // one pass over runs [r0, r1): WRITE = false only counts segments and items, WRITE = true fills
 // rec[seg0...] and item_rng[2 * item0 ...]
 template <bool WRITE, class RunFn>
@@ -284,7 +293,7 @@ static void plan_runs(size_t r0, size_t r1, RunFn run, const ItemPlanArgs& a, Se
 template <class RunFn>
 static cudaError_t plan_items(size_t nruns, RunFn run, const ItemPlanArgs& a, PinBuf<SegRec>& rec_buf, PinBuf<int64_t>& item_buf,
                               int64_t& nseg, int64_t& nitems) {
-    const size_t nthreads = nruns < 65536 ? 1 : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+    const size_t nthreads = nruns < 65536 ? 1 : host_threads();
     std::vector<int64_t> segs(nthreads), its(nthreads), seg_first(nthreads + 1, 0), item_first(nthreads + 1, 0);
     auto share = [&](size_t t) { return nruns * t / nthreads; };
     auto parallel = [&](auto fn) {
@@ -369,7 +378,7 @@ int yue_destroy(yue_t* h) {
     h->seg_rec.release(); h->tmp_rec.release(); h->pin_rec.release(); h->pin_items.release();
     h->cursor.release();
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->tmp_i, &h->tmp_j, &h->rk_part_ids, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot, &h->hot_dx}) b->release();
-    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
+    for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->delta_w, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
     h->l2buf.release();
     h->test_indptr.release(); h->test_items.release(); h->met_terms.release(); h->met_sums.release(); h->met_seen.release(); h->met_distinct.release();
@@ -399,7 +408,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     PhaseTimer pt;
     {   // validation on the host cores: monotone indptr; a user who played the whole catalog has no negative
         // (the reference would spin forever, BPR.py:47-48)
-        const size_t nth = m_local < 65536 ? 1 : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+        const size_t nth = m_local < 65536 ? 1 : host_threads();
         std::vector<int64_t> bad_mono(nth, -1), bad_full(nth, -1);
         auto check = [&](size_t t) {
             for (int64_t u = m_local * (int64_t)t / (int64_t)nth, e = m_local * (int64_t)(t + 1) / (int64_t)nth; u < e; ++u) {
@@ -507,6 +516,7 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     REQUIRE((T == 0 || ev_items) && (nnz == 0 || uq_items), YUE_E_ARG, "null item array");
     REQUIRE(T >= 0 && nnz >= 0, YUE_E_ARG, "indptr not monotone");
     CK(cudaSetDevice(h->device));
+    if (n != h->n) h->have_delta_w = false;   // per-track weights belong to a catalog
     h->m = m_local; h->n = n; h->T = T; h->nnz = nnz; h->user_begin = user_begin; h->event_base = event_base;
     h->have_test = false;              // a new log: the held-out set of the old one no longer applies
     CK(h->ev_indptr.resize(m_local + 1)); CK(h->uq_indptr.resize(m_local + 1));
@@ -581,6 +591,7 @@ int yue_ingest_events(yue_t* h, int64_t m, int64_t n, int64_t E, const int32_t* 
         REQUIRE(hc[5] == 0, YUE_E_ARG, "an event names a user or track outside [0, m) x [0, n)");
     }
     const int64_t T = hc[0], Et = hc[2];
+    if (n != h->n) h->have_delta_w = false;
     h->m = m; h->n = n; h->T = T; h->user_begin = 0; h->event_base = 0;
     CK(h->ev_indptr.resize(m + 1)); CK(h->uq_indptr.resize(m + 1)); CK(h->test_indptr.resize(m + 1));
     CK(h->ev_items.resize(T));
@@ -1198,11 +1209,22 @@ int yue_q_delta_pack(yue_t* h) {
     CK(cudaGetLastError());
     return YUE_OK;
 }
+int yue_set_delta_weights(yue_t* h, const float* w) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "call yue_set_interactions first (it fixes n)");
+    CK(cudaSetDevice(h->device));
+    if (!w) { h->have_delta_w = false; return YUE_OK; }
+    CK(h->delta_w.resize(h->n));
+    CK(cudaMemcpyAsync(h->delta_w.p, w, h->n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_delta_w = true;
+    return YUE_OK;
+}
 int yue_q_delta_apply(yue_t* h) {
     REQUIRE(h && h->have_factors && h->have_snap, YUE_E_STATE, "call yue_q_snapshot first");
     CK(cudaSetDevice(h->device));
     const size_t n4 = (size_t)h->n * h->ld / 4;
-    q_delta_apply_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((float4*)h->Q.p, (float4*)h->Qsnap.p, (const float4*)h->Qdelta.p, n4);
+    q_delta_apply_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((float4*)h->Q.p, (float4*)h->Qsnap.p, (const float4*)h->Qdelta.p,
+                                                                 h->have_delta_w ? h->delta_w.p : nullptr, h->ld / 4, n4);
     ++h->launches;
     CK(cudaGetLastError());
     h->tc.q_dirty = true;

@@ -234,6 +234,16 @@ class Engine:
     def q_delta_pack(self):
         self._ck(self.lib.yue_q_delta_pack(self.h))
 
+    def set_delta_weights(self, w):
+        """Per-track factor for the summed Q deltas (sharding.saturation_weights); None = plain sum."""
+        if w is None:
+            self._ck(self.lib.yue_set_delta_weights(self.h, None))
+            return
+        w = _as(w, np.float32)
+        if len(w) != self.n:
+            raise ValueError("one weight per track")
+        self._ck(self.lib.yue_set_delta_weights(self.h, _ptr(w, C.c_float)))
+
     def q_delta_apply(self):
         self._ck(self.lib.yue_q_delta_apply(self.h))
 

@@ -103,7 +103,7 @@ class ShardedTrainer:
     def __init__(self, engine, dist, device, sub_epochs=1, row_weights=None):
         import torch
         self.sub_epochs = int(sub_epochs)
-        self.w = None if row_weights is None else torch.as_tensor(row_weights, dtype=torch.float32, device=device)
+        engine.set_delta_weights(row_weights)            # applied by the library's q_delta_apply kernel
         from ._lib import BUF_Q_DELTA
         self.eng, self.dist, self.torch = engine, dist, torch
         engine.q_snapshot()
@@ -116,9 +116,7 @@ class ShardedTrainer:
         self.eng.q_delta_pack()
         with self.torch.cuda.stream(self.stream):        # NCCL ordered on the library's stream
             self.dist.all_reduce(self.delta)
-            if self.w is not None:                       # saturation-aware combination, see saturation_weights
-                self.delta.view(self.w.numel(), -1).mul_(self.w[:, None])
-        self.eng.q_delta_apply()
+        self.eng.q_delta_apply()                         # Q = snapshot + w * sum of deltas (w: saturation_weights)
 
     def epoch(self, lr, regU, regI, seed, epoch, mode, want_loss=False):
         """One epoch = sub_epochs parts of the local users' work, the ranks reconciling Q after each part
