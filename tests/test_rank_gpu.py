@@ -103,7 +103,7 @@ from yue_b200.engine import RANK_TC  # noqa: E402
 
 
 @pytest.mark.parametrize("d,N,n,B", [(64, 10, 5000, 300), (64, 20, 20011, 257), (32, 5, 3000, 128),
-                                     (10, 10, 777, 50), (48, 32, 9000, 130)])
+                                     (10, 10, 777, 50), (48, 32, 9000, 130), (128, 10, 6000, 200), (96, 20, 5003, 129), (72, 5, 900, 40)])
 def test_tc_topn_matches_oracle(engine, d, N, n, B):
     m = max(B, 300)
     log = synth.power_law_log(m, n, 15000, seed=d + N)

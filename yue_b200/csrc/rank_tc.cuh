@@ -38,8 +38,8 @@ namespace yue {
 
 constexpr int kTcThreads = 192;
 constexpr int kTcBM = 128;            // users per CTA (UMMA M)
-constexpr int kTcBN = 128;            // tracks per tile (UMMA N)
-constexpr int kTcStages = 3;          // TMA -> MMA shared-memory stages
+// tracks per tile (UMMA N) and TMA -> MMA shared-memory stages are template parameters of the kernel:
+//   d <= 64:  BN = 128, 3 stages of 32 KB;   64 < d <= 128:  BN = 64, 2 stages of 32 KB (A alone is 64 KB)
 // candidate slots per row (template parameter CAP of the kernel): CAP - 32 kept + 32 new per chunk.  64 for N <= 12
 // (fastest: 10.8 ms per wave at N = 10); 96 for larger N (at N = 20 a row keeps ~27-45 near-ties: with 64 slots
 // nearly every row spilled and fell back to the exact kernel, 202 ms instead of 12.8 ms).
@@ -157,8 +157,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) |
-                                ((uint32_t)(kTcBM >> 4) << 24);
+template <int BN> __host__ __device__ constexpr uint32_t idesc_tf32() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
 
 // ---- the rare path of the epilogue, kept OUT of line ------------------------------------------
 // ncu on the first version: 73 % of the epilogue's stall samples were `no_inst` -- the 32-way
@@ -232,15 +233,16 @@ __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int 
     return thr;
 }
 
-template <int CAP>
+template <int CAP, int BN, int kTcStages>
 __global__ void __launch_bounds__(kTcThreads, 1)
 rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const RankTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_tc_raw) + 1023) & ~(uintptr_t)1023);
     const int KB = p.kblocks;
-    const uint32_t stage_bytes = (uint32_t)KB * kTcBoxBytes;
+    constexpr uint32_t kBBox = BN * 128;                     // one TMA box of Q: BN rows x 128 B
+    const uint32_t a_bytes = (uint32_t)KB * kTcBoxBytes, stage_bytes = (uint32_t)KB * kBBox;
     uint8_t* sA = smem;
-    uint8_t* sB = sA + stage_bytes;
+    uint8_t* sB = sA + a_bytes;
     constexpr int kTcPer = CAP / 32;
     uint64_t* keys = reinterpret_cast<uint64_t*>(sB + kTcStages * stage_bytes);        // [128][CAP]
     uint64_t* bars = keys + kTcBM * CAP;
@@ -274,7 +276,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(bar_a, stage_bytes);
+            mbar_expect_tx(bar_a, a_bytes);
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_2d(smem_u32(sA + kb * kTcBoxBytes), &tmP, bar_a, kb * 32, blockIdx.x * kTcBM);
             for (int j = 0; j < p.ntiles; ++j) {
@@ -283,7 +285,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                 mbar_wait(bar_empty(s), ph ^ 1u);
                 mbar_expect_tx(bar_full(s), stage_bytes);
                 for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(smem_u32(sB + s * stage_bytes + kb * kTcBoxBytes), &tmQ, bar_full(s), kb * 32, j * kTcBN);
+                    tma_load_2d(smem_u32(sB + s * stage_bytes + kb * kBBox), &tmQ, bar_full(s), kb * 32, j * BN);
             }
         }
     } else if (warp == 1) {
@@ -301,8 +303,8 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {       // UMMA K = 8 tf32 = 32 bytes along the swizzle row
                         const uint64_t ad = umma_desc_sw128(a0 + kb * kTcBoxBytes + k * 32);
-                        const uint64_t bd = umma_desc_sw128(b0 + kb * kTcBoxBytes + k * 32);
-                        tc_mma_tf32(tmem_base + (uint32_t)t * kTcBN, ad, bd, kIdescTf32, (kb | k) ? 1u : 0u);
+                        const uint64_t bd = umma_desc_sw128(b0 + kb * kBBox + k * 32);
+                        tc_mma_tf32(tmem_base + (uint32_t)t * BN, ad, bd, idesc_tf32<BN>(), (kb | k) ? 1u : 0u);
                     }
                 }
                 tc_commit(bar_empty(s));                // smem stage free once these MMAs retire
@@ -343,13 +345,13 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         for (int j = 0; j < p.ntiles; ++j) {
             const int t = j % kTcAcc;
             const uint32_t tph = (uint32_t)(j / kTcAcc) & 1u;
-            const int i0 = j * kTcBN;
+            const int i0 = j * BN;
             mbar_wait(bar_tfull(t), tph);
             tc_fence_after();
             uint32_t va[64], vb[64];
-            tc_ld64_issue(trow + (uint32_t)(t * kTcBN), va);
+            tc_ld64_issue(trow + (uint32_t)(t * BN), va);
             tc_ld_wait();
-            tc_ld64_issue(trow + (uint32_t)(t * kTcBN + 64), vb);      // in flight while the first half is reduced
+            if (BN == 128) tc_ld64_issue(trow + (uint32_t)(t * BN + 64), vb);   // in flight while the first half is reduced
             float m0 = __uint_as_float(va[0]), m1 = __uint_as_float(va[32]);
 #pragma unroll
             for (int x = 1; x < 32; ++x) { m0 = fmaxf(m0, __uint_as_float(va[x])); m1 = fmaxf(m1, __uint_as_float(va[32 + x])); }
@@ -358,6 +360,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             tc_ld_wait();
             tc_fence_before();
             mbar_arrive(bar_tempty(t));                                 // TMEM stage free: the rest works on registers
+            if (BN != 128) continue;
             float m2 = __uint_as_float(vb[0]), m3 = __uint_as_float(vb[32]);
 #pragma unroll
             for (int x = 1; x < 32; ++x) { m2 = fmaxf(m2, __uint_as_float(vb[x])); m3 = fmaxf(m3, __uint_as_float(vb[32 + x])); }
@@ -504,7 +507,7 @@ struct RankTcState {
 };
 
 // a row keeps its N best plus the near-ties (within 2 eps of the N-th) in kTcCap - 32 = 64 slots
-inline bool rank_tc_supported(int k, int N) { return k >= 1 && k <= 64 && N >= 1 && N <= 32; }
+inline bool rank_tc_supported(int k, int N) { return k >= 1 && k <= 128 && N >= 1 && N <= 32; }
 
 inline void rank_tc_release(RankTcState& st) {
     for (void* p : {(void*)st.qmax, (void*)st.psel, (void*)st.pnorm, (void*)st.fail_count, (void*)st.fail_rows,
@@ -523,10 +526,10 @@ static cudaError_t tc_grow(T*& p, size_t& cap, size_t need) {
     return e;
 }
 
-static bool tc_make_map(PFN_tmapEncodeTiled enc, CUtensorMap* map, const float* base, uint64_t rows, int ld) {
+static bool tc_make_map(PFN_tmapEncodeTiled enc, CUtensorMap* map, const float* base, uint64_t rows, int ld, unsigned box_rows = 128u) {
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {32u, 128u};
+    const cuuint32_t box[2] = {32u, box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -575,27 +578,30 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
     TC_CK(cudaGetLastError());
 
     CUtensorMap tmP, tmQ;
-    if (!tc_make_map(st.encode, &tmP, st.psel, (uint64_t)Bpad, ld) || !tc_make_map(st.encode, &tmQ, Q, (uint64_t)n_items, ld)) {
+    const int bn = ld <= 64 ? 128 : 64, stages = ld <= 64 ? 3 : 2;
+    if (!tc_make_map(st.encode, &tmP, st.psel, (uint64_t)Bpad, ld) || !tc_make_map(st.encode, &tmQ, Q, (uint64_t)n_items, ld, (unsigned)bn)) {
         err = "cuTensorMapEncodeTiled failed";
         return 2;
     }
     RankTcParams p{};
     p.kblocks = (ld + 31) / 32;
-    p.ntiles = (n_items + kTcBN - 1) / kTcBN;
+    p.ntiles = (n_items + bn - 1) / bn;
     p.n_items = n_items; p.B = B; p.N = N; p.ld = ld; p.d = d;
     p.Psel = st.psel; p.Q = Q; p.pnorm = st.pnorm; p.qmax = st.qmax; p.users = d_users;
     p.uq_indptr = uq_indptr; p.uq_items = uq_items; p.ids_out = d_ids; p.scores_out = d_scores;
     p.fail_count = st.fail_count; p.fail_rows = st.fail_rows;
     p.ovf_pool = st.ovf_pool; p.ovf_next = st.ovf_next; p.ovf_rows = (int)(st.ovf_rows / kTcOvfCap);
     const int cap = N <= 12 ? 64 : 96;
-    const size_t smem = 1024 + (size_t)p.kblocks * kTcBoxBytes * (1 + kTcStages) + (size_t)kTcBM * cap * 8 + 256;
-    if (cap == 64) {
-        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rank_tc_kernel<64><<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);
-    } else {
-        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rank_tc_kernel<96><<<(unsigned)(Bpad / kTcBM), kTcThreads, smem, stream>>>(tmP, tmQ, p);
-    }
+    const size_t smem = 1024 + (size_t)p.kblocks * (kTcBoxBytes + (size_t)stages * bn * 128) + (size_t)kTcBM * cap * 8 + 256;
+    const unsigned grid = (unsigned)(Bpad / kTcBM);
+#define TC_LAUNCH(CAP_, BN_, ST_)                                                                                          \
+    do {                                                                                                                   \
+        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<CAP_, BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rank_tc_kernel<CAP_, BN_, ST_><<<grid, kTcThreads, smem, stream>>>(tmP, tmQ, p);                                   \
+    } while (0)
+    if (bn == 128) { if (cap == 64) TC_LAUNCH(64, 128, 3); else TC_LAUNCH(96, 128, 3); }
+    else { if (cap == 64) TC_LAUNCH(64, 64, 2); else TC_LAUNCH(96, 64, 2); }
+#undef TC_LAUNCH
     ++launches;
     TC_CK(cudaGetLastError());
 

@@ -1115,7 +1115,7 @@ int yue_rank_topn(yue_t* h, const int32_t* users, int64_t B, int N, int algo, in
     CK(cudaMemcpyAsync(h->rk_users.p, users, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     int rc;
     const bool tc_ok = rank_tc_supported(h->k, N);
-    if (algo == YUE_RANK_TC && !tc_ok) return fail(h, YUE_E_UNSUPPORTED, "tcgen05 ranking needs num.factors <= 64 and N <= 32");
+    if (algo == YUE_RANK_TC && !tc_ok) return fail(h, YUE_E_UNSUPPORTED, "tcgen05 ranking needs num.factors <= 128 and N <= 32");
     if (algo == YUE_RANK_TC || (algo == YUE_RANK_AUTO && tc_ok && B >= 256)) {
         rc = rank_tc_run(h->tc, h->stream, h->sm_count, h->P.p, h->Q.p, h->ld, h->k, (int)h->n, h->rk_users.p, B, N,
                          h->uq_indptr.p, h->uq_items.p, h->rk_ids.p, h->rk_scores.p, h->err, h->launches,
