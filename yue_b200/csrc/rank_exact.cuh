@@ -9,7 +9,7 @@
 //
 // Scores are the canonical float32 FMA chain acc = fmaf(P[u,k], Q[t,k], acc), k = 0..d-1
 // (SURVEY.md 8c): every output accumulates over k in order, so ids and scores are bit-exact
-// with oracle/topn.py and oracle/csrc/oracle.c.  Order: score desc, then track id asc.
+// with oracle/topn.py.  Order: score desc, then track id asc.
 //
 // This kernel is the exactness anchor: the tcgen05 flavour (rank_tc.cuh) generates candidates
 // in tf32 and re-scores them with score_fma32() below, and falls back to this kernel for rows
