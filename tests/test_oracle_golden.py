@@ -111,3 +111,25 @@ def test_ndcg_definition():
     d0 = (1 / math.log2(2) + 1 / math.log2(4)) / (1 / math.log2(2) + 1 / math.log2(3) + 1 / math.log2(4))
     d1 = (1 / math.log2(3)) / 1.0
     assert metrics.ndcg(origin, rec, 4) == pytest.approx((d0 + d1) / 2)
+
+
+def test_c_oracle_agrees_with_numpy_emulation():
+    """oracle/csrc/oracle.c scores with a true fmaf(); oracle/topn.py emulates the chain in float64.  They must give the
+    same scores and the same masked top-N (ids and order, ties by id) -- including on factors with exact ties."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    from oracle import c_oracle, topn
+    from yue_b200 import synth
+    rng = np.random.default_rng(4)
+    for d, n, m in ((64, 3000, 40), (10, 500, 25), (37, 1200, 16)):
+        P = (rng.normal(size=(m, d)) * rng.lognormal(0, 0.5, (m, 1))).astype(np.float32)
+        Q = (rng.normal(size=(n, d)) * 0.3).astype(np.float32)
+        Q[100:130] = Q[99]                       # a run of identical tracks: equal scores, order by id
+        indptr, uq = synth.mask_csr(m, n, 20, seed=d)
+        users = np.arange(m, dtype=np.int32)
+        assert np.array_equal(c_oracle.scores_fma32(P, Q), topn.scores_fma32(P, Q))
+        for N in (1, 10, 50):
+            ci, cs = c_oracle.topn_exact(P, Q, users, N, indptr, uq)
+            ni, ns = topn.topn_exact(P, Q, users, N, indptr, uq)
+            assert np.array_equal(ci, ni) and np.array_equal(cs, ns)
