@@ -269,6 +269,43 @@ def run_native(args):
         apr = {"metric": "apr_triplets_per_sec", "value": T / (min(ams[1:]) * 1e-3), "ms_per_epoch": min(ams[1:]),
                "workload": "C5: APR d=64 on the C2 log, eps 0.5, regA 2, lr 0.003 (config/APR.conf)", "kernel": "bpr_sgd_blk_kernel<2, APR>"}
 
+    # ---- WRMF (implicit ALS, recommender/cf/WRMF.py) on the same log and tables, d = 64 ----
+    wrmf = None
+    if world == 1 and not args.no_wrmf:
+        eng.sync()
+        t0 = time.perf_counter()
+        nnz = int(len(log.uq_items))
+        eng.wrmf_pair_counts()                      # one-off: play counts per pair + the track-major copy of the pairs
+        prep_s = time.perf_counter() - t0
+        wms = {0: [], 1: []}
+        for k in range(3):
+            for side in (0, 1):
+                eng.sync()
+                eng.timer_start()
+                eng.wrmf_sweep(side, 1.0, 10.0, want_loss=False)
+                wms[side].append(eng.timer_stop())
+        u_ms, t_ms = min(wms[0][1:]), min(wms[1][1:])
+        flops = lambda rows: nnz * D * (D + 1) + rows * (D ** 3 / 3.0 + 2 * D * D)      # rank-1 terms (lower triangle) + LDL^T + substitutions
+        wrmf = {"metric": "wrmf_iterations_per_sec", "value": 1e3 / (u_ms + t_ms), "ms_user_sweep": u_ms, "ms_track_sweep": t_ms,
+                "unique_pairs": nnz, "pairs_per_sec": 2 * nnz / ((u_ms + t_ms) * 1e-3), "prepare_seconds": prep_s,
+                "fp64_tflops_user_sweep": flops(m) / (u_ms * 1e-3) / 1e12, "fp64_tflops_track_sweep": flops(n) / (t_ms * 1e-3) / 1e12,
+                "dtype": "f64 arithmetic on f32 tables (as the reference)", "kernel": "wrmf_solve_kernel<4> (+ gram, chunk)",
+                "workload": "WRMF d=64, reg 1, alpha 10 on the C2 log (%d users x %d tracks, %d unique pairs)" % (m, n, nnz)}
+        if not args.no_cpu:                         # the reference's per-row solve (oracle port of WRMF.py:36-57), one core
+            from oracle import wrmf_ref
+            Pn, Qn = eng.get_factors()
+            rows = np.linspace(0, m - 1, 200).astype(np.int64)
+            sub_ptr = np.zeros(len(rows) + 1, np.int64)
+            np.cumsum(log.uq_indptr[rows + 1] - log.uq_indptr[rows], out=sub_ptr[1:])
+            sub_idx = np.concatenate([log.uq_items[log.uq_indptr[r]:log.uq_indptr[r + 1]] for r in rows])
+            out_rows = np.zeros((len(rows), D), np.float32)
+            t0 = time.perf_counter()
+            wrmf_ref.half_sweep(out_rows, Qn, sub_ptr, sub_idx, np.ones(len(sub_idx), np.int32), 1.0, gram="f32")
+            dt = time.perf_counter() - t0
+            wrmf["cpu_baseline"] = {"value": len(rows) / dt, "unit": "user rows/s", "cores": 1, "kind": "port",
+                                    "sample": "200 evenly spaced users of the same log, oracle port of WRMF.py:36-57 incl. one YtY",
+                                    "gpu_user_rows_per_sec": m / (u_ms * 1e-3)}
+
     # ---- e2e: same step through the C ABI with host buffers ---------------------------------
     h2d = log.ev_indptr.nbytes + log.ev_items.nbytes + log.uq_indptr.nbytes + log.uq_items.nbytes + pP.nbytes + pQ.nbytes
     d2h = pP.nbytes + pQ.nbytes + 8
@@ -318,6 +355,8 @@ def run_native(args):
         }
         if apr:
             out["apr"] = apr
+        if wrmf:
+            out["wrmf"] = wrmf
 
     # ---- secondary metric: full-catalog masked top-10 (config C4 shape, bounded user block) --
     if not args.no_rank:
@@ -423,6 +462,7 @@ def main():
     ap.add_argument("--no-rank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-apr", action="store_true")
+    ap.add_argument("--no-wrmf", action="store_true")
     ap.add_argument("--rank-users", type=int, default=1_000_000)   # config C4: 1 M users
     args = ap.parse_args()
     if args.warmup < 3 and not args.small:

@@ -63,6 +63,9 @@ enum { YUE_BUF_P = 0, YUE_BUF_Q = 1, YUE_BUF_Q_DELTA = 2, YUE_BUF_Q_SNAPSHOT = 3
 const char* yue_version(void);
 const char* yue_last_error(const yue_t* h);          /* h may be NULL: last create error */
 
+/* Number of CUDA devices (0 without a driver).  The host driver maps `-cv k -p` folds onto devices with it, where
+ * the reference runs the folds as processes and divides MKL threads among them (yue.py:72-105). */
+int yue_device_count(int* count);
 int yue_create(int device, yue_t** out);
 int yue_destroy(yue_t* h);
 int yue_sync(yue_t* h);
@@ -171,6 +174,23 @@ int yue_rank_topn(yue_t* h, const int32_t* users, int64_t B, int N, int algo,
  * sum/rows, MAP = sum/rows, coverage = distinct/itemCount).  Sums are reduced in a fixed order. */
 int yue_set_test_set(yue_t* h, const int64_t* test_indptr, const int32_t* test_items);
 int yue_rank_metrics(yue_t* h, int n_cuts, const int32_t* cuts, double* sums_out, int64_t* distinct_out);
+
+/* ---- WRMF (the next model on the same tables and the same ranking path) ----
+ * One half-sweep of the implicit-feedback ALS of recommender/cf/WRMF.py (X = P table, Y = Q table of the handle):
+ *   side 0  replaces the user loop, WRMF.py:34-57:  for every user  A = YtY + Y^T diag(alpha r_ui) Y + reg I,
+ *           b = sum over played tracks of (1 + alpha r_ui) Y[i],  X[u] = inv(A) b   (float64, stored as float32);
+ *           *loss_out (may be NULL) = sum over played pairs of (1 - X[u].Y[i])^2 with the X[u] from BEFORE the
+ *           update, WRMF.py:49-50.
+ *   side 1  replaces the track loop, WRMF.py:60-80, from the X just computed and listened[track][user].
+ * r_ui = plays of track i by user u in the training log (WRMF.py:28-33), counted on the device from the event CSR;
+ * alpha = 10 and reg = reg.lambda -u on BOTH sides in the reference (WRMF.py:55,79).  Users/tracks without training
+ * plays get a zero row, as in the reference (b = 0).  num.factors <= 128.  The Gram matrix is accumulated in
+ * float64 (the reference's YtY is a float32 sgemm): factors agree with the reference class to ~5e-6 per row.
+ * Ranking afterwards is yue_rank_topn (predict = Y.dot(X[u]), WRMF.py:86-88). */
+int yue_wrmf_sweep(yue_t* h, int side, double reg, double alpha, double* loss_out);
+/* Check hook: the pair counts (aligned with uq_items) and the track-major form of the play sets the sweeps use
+ * (it_indptr[n+1], it_users[nnz] sorted inside a track, it_counts[nnz]); any pointer may be NULL. */
+int yue_wrmf_pair_counts(yue_t* h, int32_t* uq_counts, int64_t* it_indptr, int32_t* it_users, int32_t* it_counts);
 
 /* ---- multi-GPU: user-sharded SGD with Q replicated; once per sub-epoch
  *      Q <- Q_snapshot + sum_over_ranks(Q_rank - Q_snapshot).  No reference counterpart

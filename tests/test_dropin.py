@@ -159,3 +159,60 @@ def test_c1_end_to_end_through_the_class_api(tmp_path):
     mh, _ = results["hogwild"]
     rec = lambda m: float(m.measure[8].split(":")[1])       # Recall@10
     assert abs(rec(mh) - rec(ms)) < 0.005
+
+
+@pytest.mark.gpu
+def test_cv_folds_and_progress_hook(tmp_path):
+    """SURVEY 8f row 3.  `-cv 3` through the driver (yue.py:72-123): every fold trains and ranks in its own process
+    (serially, and under `-p` on device fold % device_count), the fold measures are averaged label by label and the
+    k-fold file is written.  `ranking_performance` (IterativeRecommender.py:175-235): top-10 of the first 300 test
+    users, with the TRAINING tracks masked, equals Measure on the exact lists of the oracle."""
+    from yue_b200 import synth
+    from yue_b200.host.driver import Yue
+    from yue_b200.host.measure import Measure
+    import random
+    log_path = tmp_path / "log.txt"
+    synth.write_csv_log(str(log_path), 800, 3000, 20000, seed=3)
+    out = {}
+    for flag in ("", " -p"):
+        vals = conf_values(tmp_path / ("cv" + flag.strip()), eval_setup="-target track -cv 3" + flag,
+                           extra={"record": str(log_path), "yue.sgd": "serial", "yue.seed": "5", "num.max.iter": "2"})
+        random.seed(9)
+        with redirect_stdout(io.StringIO()):
+            res = Yue(Config(values=vals)).execute()
+        assert [r.split(":")[0] for r in res[:6]] == ["Top 5\n", "Precision", "Recall", "F1", "MAP", "Coverage"]
+        files = os.listdir(tmp_path / ("cv" + flag.strip()))
+        assert sum("-3-fold-cv" in f for f in files) == 1
+        assert sum("-measure[%d]" % i in f for f in files for i in (1, 2, 3)) == 3
+        out[flag] = res
+    # same folds (same `random` seed), same sampler seed, serial order: the two schedules give the same averages up to
+    # the unseeded factor init in the child processes -- so only the structure and the ranges are compared
+    for a, b in zip(out[""], out[" -p"]):
+        assert a.split(":")[0] == b.split(":")[0]
+        if ":" in a:
+            assert 0.0 <= float(a.split(":")[1]) <= 1.0 and 0.0 <= float(b.split(":")[1]) <= 1.0
+
+    # the progress hook
+    vals = conf_values(tmp_path / "hook", extra={"record": str(log_path), "yue.seed": "5", "num.max.iter": "1"})
+    random.seed(9)
+    np.random.seed(3)
+    with redirect_stdout(io.StringIO()):
+        y = Yue(Config(values=vals))
+        from yue_b200.bpr import BPR
+        model = BPR(y.config, y.trainingData, y.testData)
+        model.readConfiguration()
+        model.initModel()
+        model.buildModel()
+        got = model.ranking_performance()
+    sample = dict(list(model.data.testSet.items())[:300])
+    ev_indptr, ev_items, uq_indptr, uq_items = model.data.interaction_arrays()
+    uid = np.array([model.data.getId(u, "user") for u in sample], dtype=np.int32)
+    ids, _ = topn.topn_exact(model.P, model.Q, uid, 10, uq_indptr, uq_items)
+    id2name = model.data.id2name[model.recType]
+    rec = {u: [id2name[int(t)] for t in row if t >= 0] for u, row in zip(sample, ids)}
+    itemcount = 0
+    for k, u in enumerate(model.data.testSet):           # the reference counts one user past the sample (176-181)
+        itemcount += len(model.data.testSet[u])
+        if k == 300:
+            break
+    assert got == Measure.rankingMeasure(sample, rec, [10], itemcount)

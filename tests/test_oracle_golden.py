@@ -133,3 +133,26 @@ def test_c_oracle_agrees_with_numpy_emulation():
             ci, cs = c_oracle.topn_exact(P, Q, users, N, indptr, uq)
             ni, ns = topn.topn_exact(P, Q, users, N, indptr, uq)
             assert np.array_equal(ci, ni) and np.array_equal(cs, ns)
+
+
+def test_wrmf_oracle_reproduces_the_reference_class(golden_dir):
+    """tests/golden/wrmf_small.npz is the output of recommender/cf/WRMF.py itself (oracle/make_golden_wrmf.py).  With the
+    float32 Gram matrix the restatement gives the same float32 factors bit for bit; with the float64 Gram matrix (what
+    the CUDA kernel computes) it stays within 1e-5 per row."""
+    from oracle import wrmf_ref
+    g = np.load(os.path.join(golden_dir, "wrmf_small.npz"))
+    m, n = g["X0"].shape[0], g["Y0"].shape[0]
+    cnt = wrmf_ref.pair_counts(g["ev_indptr"], g["ev_items"], g["uq_indptr"], g["uq_items"])
+    assert np.array_equal(cnt, g["counts"]) and cnt.sum() == len(g["ev_items"])
+    itp, itu, itc = wrmf_ref.transpose(m, n, g["uq_indptr"], g["uq_items"], cnt)
+    assert itp[-1] == len(cnt) and all(np.all(np.diff(itu[itp[t]:itp[t + 1]]) > 0) for t in range(n))
+    X, Y = g["X0"].copy(), g["Y0"].copy()
+    X64, Y64 = g["X0"].copy(), g["Y0"].copy()
+    for it in range(len(g["loss"])):
+        loss = wrmf_ref.iteration(X, Y, g["uq_indptr"], g["uq_items"], cnt, itp, itu, itc, float(g["reg"]), gram="f32")
+        assert np.array_equal(X, g["X"][it]) and np.array_equal(Y, g["Y"][it])
+        assert loss == pytest.approx(float(g["loss"][it]), rel=1e-7)
+        wrmf_ref.iteration(X64, Y64, g["uq_indptr"], g["uq_items"], cnt, itp, itu, itc, float(g["reg"]), gram="f64")
+        for a, b in ((X64, X), (Y64, Y)):
+            d = np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-12)
+            assert d.max() < 1e-5

@@ -51,6 +51,7 @@ _H = C.c_void_p
 SIGNATURES = {
     "yue_version": (C.c_char_p, []),
     "yue_last_error": (C.c_char_p, [_H]),
+    "yue_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "yue_create": (C.c_int, [C.c_int, C.POINTER(_H)]),
     "yue_destroy": (C.c_int, [_H]),
     "yue_sync": (C.c_int, [_H]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "yue_get_test_set": (C.c_int, [_H, _i64p, _i32p]),
     "yue_rank_metrics": (C.c_int, [_H, C.c_int, _i32p, _f64p, _i64p]),
     "yue_flush_l2": (C.c_int, [_H]),
+    "yue_wrmf_sweep": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, _f64p]),
+    "yue_wrmf_pair_counts": (C.c_int, [_H, _i32p, _i64p, _i32p, _i32p]),
 }
 
 _lib = None

@@ -80,19 +80,27 @@ class GpuBPRMixin(object):
             self._synced = (None, None)
         return self._engine
 
+    #: names of the attributes that hold the user / track factor tables (WRMF calls them X / Y, WRMF.py:19-20)
+    _user_table, _item_table = 'P', 'Q'
+
     def _push_factors(self):
-        """Upload self.P / self.Q when the host arrays are not the ones last synchronised."""
+        """Upload the host tables when they are not the arrays last synchronised."""
         eng = self._get_engine()
-        if self._synced[0] is not self.P or self._synced[1] is not self.Q:
-            self.P = np.ascontiguousarray(self.P, dtype=np.float32)
-            self.Q = np.ascontiguousarray(self.Q, dtype=np.float32)
-            eng.set_factors(self.P, self.Q)
-            self._synced = (self.P, self.Q)
+        P, Q = getattr(self, self._user_table), getattr(self, self._item_table)
+        if self._synced[0] is not P or self._synced[1] is not Q:
+            P = np.ascontiguousarray(P, dtype=np.float32)
+            Q = np.ascontiguousarray(Q, dtype=np.float32)
+            setattr(self, self._user_table, P)
+            setattr(self, self._item_table, Q)
+            eng.set_factors(P, Q)
+            self._synced = (P, Q)
         return eng
 
     def _pull_factors(self):
-        self.P, self.Q = self._engine.get_factors()
-        self._synced = (self.P, self.Q)
+        P, Q = self._engine.get_factors()
+        setattr(self, self._user_table, P)
+        setattr(self, self._item_table, Q)
+        self._synced = (P, Q)
 
     # ---- the hot path ----------------------------------------------------------------------
     def initModel(self):

@@ -1,0 +1,389 @@
+// K7: WRMF half-sweep (replaces the two loops of recommender/cf/WRMF.py:34-80).
+//
+// The reference solves, for every user u (and then, roles swapped, for every track),
+//     A = YtY + Y^T diag(10 r_ui) Y + reg I,   b = sum_i (1 + 10 r_ui) Y[i],   X[u] = inv(A) b
+// with an n-long dense H vector, an n x n scipy COO matrix and a dense inverse per row.  Rows of a sweep are
+// independent (a solve reads only the OTHER table), so a sweep here is:
+//   wrmf_gram_kernel     G = F^T F of the other table, float64 accumulation of the float32 rows, per-CTA partials
+//                        summed in a fixed order (wrmf_gram_reduce_kernel) -- same bits on every call;
+//   wrmf_chunk_kernel    rows with more than kWrmfChunk entries (the heaviest users, the most played tracks: one
+//                        track of config C2 has ~6e5 listeners) are cut into chunks whose weighted Gram + rhs partials
+//                        go to scratch, so that no single CTA is a straggler;
+//   wrmf_solve_kernel    one CTA per row, rows from a global cursor: A = G + reg I + sum of the row's rank-1 terms
+//                        (or of its chunk partials), LDL^T in registers, forward substitution carried as an extra
+//                        row of the factorisation, backward substitution by row blocks, X[row] stored as float32.
+//
+// Tile layout.  k is padded to KP = 16 TD (TD = 1, 2, 4, 8 for k <= 16, 32, 64, 128).  A is symmetric: only the 136
+// lower-triangular TD x TD blocks of the 16 x 16 block grid exist, one per thread (160 threads, 24 of them only help
+// with loads), each block in REGISTERS from the first rank-1 term to the last substitution step.  The only matrix data
+// that ever passes through shared memory is the current column of the factorisation (double-buffered: one
+// __syncthreads per column).  All arithmetic is float64 like the reference's (the sparse int64 weights promote its
+// products to float64, WRMF.py:52-54); float64 FMA runs at half the float32 rate on sm_100, and the kernel's floor is
+// the rank-1 accumulation: nnz * KP^2 / 2 FMAs per sweep.
+//
+// Loss (WRMF.py:49-50): sum (1 - X[u].Y[i])^2 over the played pairs with the X[u] from before its update, computed by
+// the warps on the staged rows while they are in shared memory.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace yue {
+
+constexpr int kWrmfThreads = 160;        // 5 warps; threads 0..135 own a block of A
+constexpr int kWrmfBlocks = 136;         // 16 * 17 / 2 lower-triangular blocks
+constexpr int kWrmfBatch = 16;           // rows of the other table staged per step
+constexpr int kWrmfChunk = 4096;         // entries one CTA accumulates for a row at most
+
+struct WrmfSide {
+    float* out;                 // table being solved [rows, ld]
+    const float* other;         // the fixed table [*, ld]
+    const int64_t* indptr;      // [rows + 1]
+    const int32_t* idx;         // rows of `other` per entry
+    const int32_t* cnt;         // plays per entry (r_ui)
+    int64_t rows;
+    int ld, k;
+    double reg, alpha;
+    const double* G;            // Gram matrix of `other`, thread layout [TD*TD][kWrmfThreads]
+    // heavy rows
+    const int32_t* heavy_rows;  // sorted row ids with more than kWrmfChunk entries
+    const int32_t* heavy_first; // [n_heavy + 1] first chunk of each
+    int n_heavy;
+    const int64_t* chunk_begin; // [n_chunks] entry range of every chunk
+    const int64_t* chunk_end;
+    const int32_t* chunk_row;
+    double* partA;              // [n_chunks][TD*TD][kWrmfThreads]
+    double* partb;              // [n_chunks][KP]
+    unsigned long long* cursor;
+    double* loss;               // += sum of squared errors, or nullptr
+};
+
+template <int TD>
+struct WrmfTile {
+    double acc[TD][TD];         // rows ty*TD + i, columns tx*TD + j
+    double bb[TD];              // rhs of columns tx*TD + j (diagonal threads only)
+};
+
+__device__ __forceinline__ void wrmf_block_of_thread(int t, int& ty, int& tx) {
+    int r = 0;
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    ty = r; tx = t - r * (r + 1) / 2;
+}
+
+// acc += sum_e w_e y_e y_e^T, bb += sum_e (1 + w_e) y_e over entries [e0, e1) (rows idx[e] of `other`, or rows e
+// themselves when idx == nullptr, then w = 1 and bb is not touched).  ys: smem [kWrmfBatch][KP] doubles, ws: smem
+// [kWrmfBatch], xs: smem [KP] (the row's current solution, LOSS only).
+template <int TD, bool LOSS>
+__device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, const float* __restrict__ other, int ld, int k,
+                                                const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int64_t e0,
+                                                int64_t e1, double alpha, double* ys, double* ws, const double* xs, double& loss,
+                                                int ty, int tx, bool active) {
+    constexpr int KP = 16 * TD;
+    constexpr int Q4 = KP / 4;                                   // float4 per staged row
+    constexpr int NLOAD = (kWrmfBatch * Q4 + kWrmfThreads - 1) / kWrmfThreads;
+    const int tid = threadIdx.x;
+    float4 pre[NLOAD];
+    double prew = 0.0;
+    auto fetch = [&](int64_t eb) {
+#pragma unroll
+        for (int q = 0; q < NLOAD; ++q) {
+            const int s = tid + q * kWrmfThreads;
+            const int r = s / Q4, c4 = s % Q4;
+            pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < kWrmfBatch && eb + r < e1 && c4 * 4 < ld) {
+                const int64_t row = idx ? (int64_t)idx[eb + r] : eb + r;
+                pre[q] = __ldg(reinterpret_cast<const float4*>(other + row * ld) + c4);
+            }
+        }
+        if (tid < kWrmfBatch) prew = (eb + tid < e1) ? (cnt ? alpha * (double)cnt[eb + tid] : 1.0) : 0.0;
+    };
+    if (e0 < e1) fetch(e0);
+    for (int64_t eb = e0; eb < e1; eb += kWrmfBatch) {
+#pragma unroll
+        for (int q = 0; q < NLOAD; ++q) {
+            const int s = tid + q * kWrmfThreads;
+            const int r = s / Q4, c4 = s % Q4;
+            if (r < kWrmfBatch) {
+                double* d = ys + r * KP + c4 * 4;
+                // columns >= k of a padded table row are zero by construction (yue_set_factors)
+                d[0] = pre[q].x; d[1] = pre[q].y; d[2] = pre[q].z; d[3] = pre[q].w;
+            }
+        }
+        if (tid < kWrmfBatch) ws[tid] = prew;
+        __syncthreads();
+        if (eb + kWrmfBatch < e1) fetch(eb + kWrmfBatch);        // in flight under the FMAs below
+        const int nb = (int)((e1 - eb) < (int64_t)kWrmfBatch ? (e1 - eb) : (int64_t)kWrmfBatch);
+        if (active) {
+            for (int e = 0; e < nb; ++e) {
+                const double* y = ys + e * KP;
+                const double w = ws[e];
+                double a[TD], b[TD];
+#pragma unroll
+                for (int i = 0; i < TD; ++i) { a[i] = y[ty * TD + i] * w; b[i] = y[tx * TD + i]; }
+#pragma unroll
+                for (int i = 0; i < TD; ++i)
+#pragma unroll
+                    for (int j = 0; j < TD; ++j) tl.acc[i][j] = fma(a[i], b[j], tl.acc[i][j]);
+                if (cnt != nullptr && ty == tx) {
+#pragma unroll
+                    for (int j = 0; j < TD; ++j) tl.bb[j] = fma(1.0 + w, b[j], tl.bb[j]);
+                }
+            }
+        }
+        if (LOSS) {
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int e = warp; e < nb; e += kWrmfThreads / 32) {
+                double p = 0.0;
+                for (int c = lane; c < KP; c += 32) p = fma(xs[c], ys[e * KP + c], p);
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
+                if (lane == 0) { const double err = 1.0 - p; loss = fma(err, err, loss); }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// G partial of rows [row0, row1) of F (unit weights), thread layout
+template <int TD>
+__global__ void __launch_bounds__(kWrmfThreads) wrmf_gram_kernel(const float* __restrict__ F, int64_t n, int ld, int k,
+                                                                 double* __restrict__ partial) {
+    constexpr int KP = 16 * TD;
+    extern __shared__ double wrmf_smem[];
+    double* ys = wrmf_smem;
+    double* ws = ys + kWrmfBatch * KP;
+    const int tid = threadIdx.x;
+    int ty = 0, tx = 0;
+    bool active = tid < kWrmfBlocks;
+    if (active) wrmf_block_of_thread(tid, ty, tx);
+    active = active && ty < (k + TD - 1) / TD;           // blocks of padded unknowns only: nothing to do
+    WrmfTile<TD> tl;
+#pragma unroll
+    for (int i = 0; i < TD; ++i) { tl.bb[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < TD; ++j) tl.acc[i][j] = 0.0; }
+    const int64_t r0 = n * (int64_t)blockIdx.x / gridDim.x, r1 = n * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    double dummy = 0.0;
+    wrmf_accumulate<TD, false>(tl, F, ld, k, nullptr, nullptr, r0, r1, 1.0, ys, ws, nullptr, dummy, ty, tx, active);
+    double* out = partial + (size_t)blockIdx.x * TD * TD * kWrmfThreads;
+#pragma unroll
+    for (int i = 0; i < TD; ++i)
+#pragma unroll
+        for (int j = 0; j < TD; ++j) out[(i * TD + j) * kWrmfThreads + tid] = active ? tl.acc[i][j] : 0.0;
+}
+
+// G[e] = sum over the partials in index order
+__global__ void wrmf_gram_reduce_kernel(const double* __restrict__ partial, int n_part, int elems, double* __restrict__ G) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= elems) return;
+    double s = 0.0;
+    for (int p = 0; p < n_part; ++p) s += partial[(size_t)p * elems + e];
+    G[e] = s;
+}
+
+template <int TD, bool LOSS>
+__global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
+    constexpr int KP = 16 * TD;
+    extern __shared__ double wrmf_smem[];
+    double* ys = wrmf_smem;
+    double* ws = ys + kWrmfBatch * KP;
+    double* xs = ws + kWrmfBatch;
+    const int tid = threadIdx.x;
+    int ty = 0, tx = 0;
+    bool active = tid < kWrmfBlocks;
+    if (active) wrmf_block_of_thread(tid, ty, tx);
+    active = active && ty < (sd.k + TD - 1) / TD;
+    const int ch = blockIdx.x;
+    const int64_t row = sd.chunk_row[ch];
+    if (LOSS) for (int c = tid; c < KP; c += kWrmfThreads) xs[c] = c < sd.k ? (double)sd.out[row * sd.ld + c] : 0.0;
+    WrmfTile<TD> tl;
+#pragma unroll
+    for (int i = 0; i < TD; ++i) { tl.bb[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < TD; ++j) tl.acc[i][j] = 0.0; }
+    double loss = 0.0;
+    wrmf_accumulate<TD, LOSS>(tl, sd.other, sd.ld, sd.k, sd.idx, sd.cnt, sd.chunk_begin[ch], sd.chunk_end[ch], sd.alpha, ys, ws, xs,
+                              loss, ty, tx, active);
+    double* pa = sd.partA + (size_t)ch * TD * TD * kWrmfThreads;
+#pragma unroll
+    for (int i = 0; i < TD; ++i)
+#pragma unroll
+        for (int j = 0; j < TD; ++j) pa[(i * TD + j) * kWrmfThreads + tid] = active ? tl.acc[i][j] : 0.0;
+    if (active && ty == tx) {
+#pragma unroll
+        for (int j = 0; j < TD; ++j) sd.partb[(size_t)ch * KP + tx * TD + j] = tl.bb[j];
+    }
+    if (LOSS) {
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, s);
+        if ((tid & 31) == 0 && loss != 0.0) atomicAdd(sd.loss, loss);
+    }
+}
+
+template <int TD, bool LOSS>
+__global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
+    constexpr int KP = 16 * TD;
+    extern __shared__ double wrmf_smem[];
+    double* ys = wrmf_smem;                              // [kWrmfBatch][KP]
+    double* ws = ys + kWrmfBatch * KP;                   // [kWrmfBatch]
+    double* xs = ws + kWrmfBatch;                        // [KP]  solution before the update (loss)
+    double* col = xs + KP;                               // [2][KP + 1]  current column of the factorisation (+ the rhs row)
+    double* dv = col + 2 * (KP + 1);                     // [KP]  pivots
+    double* yv = dv + KP;                                // [KP]  D^-1 L^-1 b, then consumed by the back substitution
+    double* xv = yv + KP;                                // [KP]  the solution
+    double* gs = xv + KP;                                // [TD*TD][kWrmfThreads]  G + reg I
+    __shared__ long long s_row;
+    const int tid = threadIdx.x;
+    int ty = 0, tx = 0;
+    const int k = sd.k, ld = sd.ld;
+    const int nblk = (k + TD - 1) / TD;                  // block rows / columns that hold real unknowns
+    bool active = tid < kWrmfBlocks;
+    if (active) wrmf_block_of_thread(tid, ty, tx);
+    active = active && ty < nblk;                        // blocks of padded unknowns only: nothing to do
+    const bool diag = active && ty == tx;
+#pragma unroll
+    for (int i = 0; i < TD; ++i)
+#pragma unroll
+        for (int j = 0; j < TD; ++j) {
+            double g = sd.G[(i * TD + j) * kWrmfThreads + tid];
+            if (diag && i == j) g = (ty * TD + i < k) ? g + sd.reg : 1.0;      // padded unknowns: identity
+            gs[(i * TD + j) * kWrmfThreads + tid] = g;
+        }
+    double loss = 0.0;
+    for (;;) {
+        __syncthreads();                                  // smem of the previous row is free
+        if (tid == 0) s_row = (long long)atomicAdd(sd.cursor, 1ull);
+        __syncthreads();
+        const int64_t row = s_row;
+        if (row >= sd.rows) break;
+        const int64_t e0 = sd.indptr[row], e1 = sd.indptr[row + 1];
+        if (e1 == e0) {                                   // nobody played it / played nothing: b = 0 -> the row is 0
+            for (int c = tid; c < ld; c += kWrmfThreads) sd.out[row * ld + c] = 0.f;
+            continue;
+        }
+        if (LOSS) for (int c = tid; c < KP; c += kWrmfThreads) xs[c] = c < k ? (double)sd.out[row * ld + c] : 0.0;
+        WrmfTile<TD> tl;
+#pragma unroll
+        for (int i = 0; i < TD; ++i) { tl.bb[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < TD; ++j) tl.acc[i][j] = gs[(i * TD + j) * kWrmfThreads + tid]; }
+        if (e1 - e0 <= kWrmfChunk) {
+            wrmf_accumulate<TD, LOSS>(tl, sd.other, ld, k, sd.idx, sd.cnt, e0, e1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
+        } else {                                          // chunk partials, in chunk order
+            int lo = 0, hi = sd.n_heavy;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sd.heavy_rows[mid] < row) lo = mid + 1; else hi = mid; }
+            for (int ch = sd.heavy_first[lo]; ch < sd.heavy_first[lo + 1]; ++ch) {
+                const double* pa = sd.partA + (size_t)ch * TD * TD * kWrmfThreads;
+#pragma unroll
+                for (int i = 0; i < TD; ++i)
+#pragma unroll
+                    for (int j = 0; j < TD; ++j) tl.acc[i][j] += pa[(i * TD + j) * kWrmfThreads + tid];
+                if (diag) {
+#pragma unroll
+                    for (int j = 0; j < TD; ++j) tl.bb[j] += sd.partb[(size_t)ch * KP + tx * TD + j];
+                }
+            }
+        }
+        // ---- LDL^T, one column per step; the rhs rides along as row KP of the matrix ----
+        for (int jb = 0; jb < nblk; ++jb) {
+#pragma unroll
+            for (int jj = 0; jj < TD; ++jj) {
+                const int j = jb * TD + jj;
+                double* cb = col + (j & 1) * (KP + 1);
+                if (active && tx == jb) {
+#pragma unroll
+                    for (int i = 0; i < TD; ++i) cb[ty * TD + i] = tl.acc[i][jj];
+                    if (ty == jb) { cb[KP] = tl.bb[jj]; dv[j] = tl.acc[jj][jj]; }
+                }
+                __syncthreads();
+                if (active && tx >= jb) {
+                    const double inv = 1.0 / cb[j];
+                    double rv[TD];
+#pragma unroll
+                    for (int i = 0; i < TD; ++i) rv[i] = cb[ty * TD + i];
+                    const double rb = cb[KP];
+#pragma unroll
+                    for (int jc = 0; jc < TD; ++jc) {
+                        if (tx > jb || jc > jj) {
+                            const double cv = cb[tx * TD + jc] * inv;
+#pragma unroll
+                            for (int i = 0; i < TD; ++i) tl.acc[i][jc] = fma(-rv[i], cv, tl.acc[i][jc]);
+                            if (ty == tx) tl.bb[jc] = fma(-rb, cv, tl.bb[jc]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- y = D^-1 z (z = the forward-substituted rhs now in bb), then x = L^-T y by row blocks, last block first ----
+        if (diag) {
+#pragma unroll
+            for (int j = 0; j < TD; ++j) yv[tx * TD + j] = tl.bb[j] / tl.acc[j][j];
+        }
+        __syncthreads();
+        for (int rbk = nblk - 1; rbk >= 0; --rbk) {
+            if (diag && ty == rbk) {
+                double xl[TD];
+#pragma unroll
+                for (int i = TD - 1; i >= 0; --i) {
+                    double s = yv[rbk * TD + i];
+#pragma unroll
+                    for (int i2 = TD - 1; i2 > i; --i2) s = fma(-(tl.acc[i2][i] / tl.acc[i][i]), xl[i2], s);
+                    xl[i] = s;
+                    xv[rbk * TD + i] = s;
+                }
+            }
+            __syncthreads();
+            if (active && ty == rbk && tx < rbk) {
+#pragma unroll
+                for (int jc = 0; jc < TD; ++jc) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < TD; ++i) s = fma(tl.acc[i][jc], xv[rbk * TD + i], s);
+                    yv[tx * TD + jc] -= s / dv[tx * TD + jc];
+                }
+            }
+            __syncthreads();
+        }
+        for (int c = tid; c < k; c += kWrmfThreads) sd.out[row * ld + c] = (float)xv[c];
+    }
+    if (LOSS) {
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, s);
+        if ((tid & 31) == 0 && loss != 0.0) atomicAdd(sd.loss, loss);
+    }
+}
+
+template <int TD>
+constexpr size_t wrmf_solve_smem() {
+    constexpr int KP = 16 * TD;
+    return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP + 2 * (KP + 1) + 3 * KP + TD * TD * kWrmfThreads);
+}
+template <int TD>
+constexpr size_t wrmf_accum_smem() {
+    constexpr int KP = 16 * TD;
+    return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP);
+}
+
+// ---- pair counts and the track-major form of the play sets (WRMF.py:28-33, data/record.py:160-163) ----
+__global__ void wrmf_count_kernel(const int64_t* __restrict__ ev_indptr, const int32_t* __restrict__ ev_items,
+                                  const int64_t* __restrict__ uq_indptr, const int32_t* __restrict__ uq_items, int64_t m, int64_t T,
+                                  int32_t* __restrict__ cnt) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = m;                           // last u with ev_indptr[u] <= e
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (ev_indptr[mid] <= e) lo = mid; else hi = mid; }
+        const int64_t u = lo;
+        const int32_t it = ev_items[e];
+        int64_t a = uq_indptr[u], b = uq_indptr[u + 1];
+        while (a < b) { const int64_t mid = (a + b) >> 1; if (uq_items[mid] < it) a = mid + 1; else b = mid; }
+        atomicAdd(cnt + a, 1);
+    }
+}
+__global__ void wrmf_keys_kernel(const int64_t* __restrict__ uq_indptr, const int32_t* __restrict__ uq_items, int64_t m, int64_t nnz,
+                                 uint64_t* __restrict__ keys) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = m;
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (uq_indptr[mid] <= p) lo = mid; else hi = mid; }
+        keys[p] = ((uint64_t)(uint32_t)uq_items[p] << 32) | (uint32_t)lo;
+    }
+}
+
+}  // namespace yue

@@ -24,6 +24,7 @@
 #include "rank_exact.cuh"
 #include "rank_metrics.cuh"
 #include "rank_tc.cuh"
+#include "wrmf_als.cuh"
 
 using namespace yue;
 
@@ -190,6 +191,18 @@ struct yue_handle {
     DevBuf<double> met_terms, met_sums;
     DevBuf<uint32_t> met_seen;
     DevBuf<unsigned long long> met_distinct;
+
+    // WRMF (K7): plays per unique pair, the track-major form of the play sets, heavy-row chunk plans per side
+    bool wrmf_ready = false;
+    DevBuf<int32_t> uq_cnt, it_users, it_cnt;
+    DevBuf<int64_t> it_indptr;
+    struct WrmfPlan {
+        DevBuf<int32_t> heavy_rows, heavy_first, chunk_row;
+        DevBuf<int64_t> chunk_begin, chunk_end;
+        int n_heavy = 0, n_chunks = 0;
+    } wrmf_plan[2];
+    DevBuf<double> wrmf_G, wrmf_part, wrmf_partA, wrmf_partb;
+    DevBuf<unsigned long long> wrmf_cursor;
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -381,11 +394,23 @@ int yue_destroy(yue_t* h) {
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->delta_w, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
     h->l2buf.release();
+    h->uq_cnt.release(); h->it_users.release(); h->it_cnt.release(); h->it_indptr.release(); h->wrmf_cursor.release();
+    for (auto* b : {&h->wrmf_G, &h->wrmf_part, &h->wrmf_partA, &h->wrmf_partb}) b->release();
+    for (auto& pl : h->wrmf_plan) { pl.heavy_rows.release(); pl.heavy_first.release(); pl.chunk_row.release(); pl.chunk_begin.release(); pl.chunk_end.release(); }
     h->test_indptr.release(); h->test_items.release(); h->met_terms.release(); h->met_sums.release(); h->met_seen.release(); h->met_distinct.release();
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
     delete h;
+    return YUE_OK;
+}
+
+int yue_device_count(int* count) {
+    if (!count) return YUE_E_ARG;
+    *count = 0;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return YUE_OK; }   // no driver / no device: 0
+    *count = n;
     return YUE_OK;
 }
 
@@ -503,6 +528,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     CK(cudaStreamSynchronize(h->stream));      // host vectors die here
     pt.lap("hot tracks");
     h->have_log = true;
+    h->wrmf_ready = false;
     return YUE_OK;
 }
 
@@ -1181,6 +1207,171 @@ int yue_rank_metrics(yue_t* h, int n_cuts, const int32_t* cuts, double* sums_out
     CK(cudaMemcpyAsync(dist, h->met_distinct.p, n_cuts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int k = 0; k < n_cuts; ++k) distinct_out[k] = (int64_t)dist[k];
+    return YUE_OK;
+}
+
+// ---- K7: WRMF half-sweeps (wrmf_als.cuh) -------------------------------------------------------------
+static int wrmf_plan_side(yue_t* h, int side, const int64_t* indptr, int64_t rows) {
+    std::vector<int32_t> heavy, first, crow;
+    std::vector<int64_t> cb, ce;
+    for (int64_t r = 0; r < rows; ++r) {
+        const int64_t e0 = indptr[r], deg = indptr[r + 1] - e0;
+        if (deg <= kWrmfChunk) continue;
+        heavy.push_back((int32_t)r);
+        first.push_back((int32_t)crow.size());
+        const int64_t nch = (deg + kWrmfChunk - 1) / kWrmfChunk;
+        for (int64_t c = 0; c < nch; ++c) {
+            cb.push_back(e0 + deg * c / nch);
+            ce.push_back(e0 + deg * (c + 1) / nch);
+            crow.push_back((int32_t)r);
+        }
+    }
+    first.push_back((int32_t)crow.size());
+    auto& pl = h->wrmf_plan[side];
+    pl.n_heavy = (int)heavy.size();
+    pl.n_chunks = (int)crow.size();
+    CK(pl.heavy_rows.resize(heavy.size())); CK(pl.heavy_first.resize(first.size())); CK(pl.chunk_row.resize(crow.size()));
+    CK(pl.chunk_begin.resize(cb.size())); CK(pl.chunk_end.resize(ce.size()));
+    cudaStream_t st = h->stream;
+    if (!heavy.empty()) CK(cudaMemcpyAsync(pl.heavy_rows.p, heavy.data(), heavy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pl.heavy_first.p, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (!crow.empty()) {
+        CK(cudaMemcpyAsync(pl.chunk_row.p, crow.data(), crow.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pl.chunk_begin.p, cb.data(), cb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pl.chunk_end.p, ce.data(), ce.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));            // host vectors die here
+    return YUE_OK;
+}
+
+// plays per unique (user, track) pair (WRMF.py:28-33) and the track-major copy of the pairs (record.py:160-163)
+static int wrmf_prepare(yue_t* h) {
+    if (h->wrmf_ready) return YUE_OK;
+    REQUIRE(h->user_begin == 0 && h->event_base == 0 && !h->have_ev_delta, YUE_E_UNSUPPORTED,
+            "WRMF needs the whole log on one handle (the track sweep reads every user)");
+    REQUIRE(h->nnz < ((int64_t)1 << 31), YUE_E_UNSUPPORTED, "more than 2^31 unique pairs");
+    cudaStream_t st = h->stream;
+    const int64_t m = h->m, n = h->n, T = h->T, nnz = h->nnz;
+    const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+    CK(h->uq_cnt.resize(nz)); CK(h->it_users.resize(nz)); CK(h->it_cnt.resize(nz)); CK(h->it_indptr.resize(n + 1));
+    CK(cudaMemsetAsync(h->uq_cnt.p, 0, nz * sizeof(int32_t), st));
+    const int grid = h->sm_count * 16;
+    DevBuf<uint64_t> k0, k1;
+    CubTemp tmp;
+    struct Free { std::function<void()> f; ~Free() { f(); } } guard{[&] { k0.release(); k1.release(); tmp.buf.release(); }};
+    CK(k0.resize(nz)); CK(k1.resize(nz));
+    if (T && m) {
+        wrmf_count_kernel<<<grid, 256, 0, st>>>(h->ev_indptr.p, h->ev_items.p, h->uq_indptr.p, h->uq_items.p, m, T, h->uq_cnt.p);
+        ++h->launches;
+    }
+    if (nnz) {
+        wrmf_keys_kernel<<<grid, 256, 0, st>>>(h->uq_indptr.p, h->uq_items.p, m, nnz, k0.p);
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, k0.p, k1.p, h->uq_cnt.p, h->it_cnt.p, (int)nnz, 0, 64, st);
+        CK(tmp.ensure(need));
+        size_t tb = tmp.buf.n;
+        CK(cub::DeviceRadixSort::SortPairs(tmp.buf.p, tb, k0.p, k1.p, h->uq_cnt.p, h->it_cnt.p, (int)nnz, 0, 64, st));
+        ingest_low_words_kernel<<<grid, 256, 0, st>>>(k1.p, nnz, h->it_users.p);
+        h->launches += 3;
+    }
+    ingest_indptr_from_keys_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(k1.p, nnz, n, h->it_indptr.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    std::vector<int64_t> hit((size_t)n + 1);
+    CK(cudaMemcpyAsync(hit.data(), h->it_indptr.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (int rc = host_indptrs(h)) return rc;
+    if (int rc = wrmf_plan_side(h, 0, h->h_uq_indptr.data(), m)) return rc;
+    if (int rc = wrmf_plan_side(h, 1, hit.data(), n)) return rc;
+    CK(h->wrmf_cursor.resize(1));
+    h->wrmf_ready = true;
+    return YUE_OK;
+}
+
+template <int TD>
+static int wrmf_sweep_impl(yue_t* h, int side, double reg, double alpha, double* loss_out) {
+    constexpr int KP = 16 * TD;
+    constexpr size_t elems = (size_t)TD * TD * kWrmfThreads;
+    cudaStream_t st = h->stream;
+    const int64_t rows = side == 0 ? h->m : h->n, other_rows = side == 0 ? h->n : h->m;
+    if (rows == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
+    const bool want_loss = loss_out != nullptr;
+    auto& pl = h->wrmf_plan[side];
+    const int n_part = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 4, other_rows / 64));
+    CK(h->wrmf_part.resize((size_t)n_part * elems)); CK(h->wrmf_G.resize(elems));
+    CK(h->wrmf_partA.resize((size_t)pl.n_chunks * elems)); CK(h->wrmf_partb.resize((size_t)pl.n_chunks * KP));
+    const size_t sm_acc = wrmf_accum_smem<TD>(), sm_solve = wrmf_solve_smem<TD>();
+    CK(cudaFuncSetAttribute(wrmf_gram_kernel<TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
+    CK(cudaFuncSetAttribute(wrmf_chunk_kernel<TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
+    CK(cudaFuncSetAttribute(wrmf_chunk_kernel<TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
+    CK(cudaFuncSetAttribute(wrmf_solve_kernel<TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_solve));
+    CK(cudaFuncSetAttribute(wrmf_solve_kernel<TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_solve));
+    WrmfSide sd{};
+    sd.out = side == 0 ? h->P.p : h->Q.p;
+    sd.other = side == 0 ? h->Q.p : h->P.p;
+    sd.indptr = side == 0 ? h->uq_indptr.p : h->it_indptr.p;
+    sd.idx = side == 0 ? h->uq_items.p : h->it_users.p;
+    sd.cnt = side == 0 ? h->uq_cnt.p : h->it_cnt.p;
+    sd.rows = rows; sd.ld = h->ld; sd.k = h->k; sd.reg = reg; sd.alpha = alpha; sd.G = h->wrmf_G.p;
+    sd.heavy_rows = pl.heavy_rows.p; sd.heavy_first = pl.heavy_first.p; sd.n_heavy = pl.n_heavy;
+    sd.chunk_begin = pl.chunk_begin.p; sd.chunk_end = pl.chunk_end.p; sd.chunk_row = pl.chunk_row.p;
+    sd.partA = h->wrmf_partA.p; sd.partb = h->wrmf_partb.p; sd.cursor = h->wrmf_cursor.p; sd.loss = h->scal.p;
+    CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), st));
+    CK(cudaMemsetAsync(h->wrmf_cursor.p, 0, sizeof(unsigned long long), st));
+    if (other_rows) {
+        wrmf_gram_kernel<TD><<<n_part, kWrmfThreads, sm_acc, st>>>(sd.other, other_rows, h->ld, h->k, h->wrmf_part.p);
+        wrmf_gram_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(h->wrmf_part.p, n_part, (int)elems, h->wrmf_G.p);
+        h->launches += 2;
+    } else {
+        CK(cudaMemsetAsync(h->wrmf_G.p, 0, elems * sizeof(double), st));
+    }
+    if (pl.n_chunks) {
+        if (want_loss) wrmf_chunk_kernel<TD, true><<<pl.n_chunks, kWrmfThreads, sm_acc, st>>>(sd);
+        else wrmf_chunk_kernel<TD, false><<<pl.n_chunks, kWrmfThreads, sm_acc, st>>>(sd);
+        ++h->launches;
+    }
+    int per_sm = 1;
+    if (want_loss) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, true>, kWrmfThreads, sm_solve));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, false>, kWrmfThreads, sm_solve));
+    const int grid = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * std::max(per_sm, 1));
+    if (want_loss) wrmf_solve_kernel<TD, true><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
+    else wrmf_solve_kernel<TD, false><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
+    ++h->launches;
+    CK(cudaGetLastError());
+    if (side == 1) { h->tc.q_dirty = true; h->ilv_current = false; }
+    if (want_loss) {
+        CK(cudaMemcpyAsync(loss_out, h->scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!std::isfinite(*loss_out)) return fail(h, YUE_E_NUMERIC, "WRMF loss is not finite");
+    }
+    return YUE_OK;
+}
+
+int yue_wrmf_sweep(yue_t* h, int side, double reg, double alpha, double* loss_out) {
+    REQUIRE(h, YUE_E_ARG, "null handle");
+    REQUIRE(h->have_log && h->have_factors, YUE_E_STATE, "interactions or factors not set");
+    REQUIRE(side == 0 || side == 1, YUE_E_ARG, "side must be 0 (users) or 1 (tracks)");
+    REQUIRE(reg >= 0.0 && alpha >= 0.0, YUE_E_ARG, "reg and alpha must be non-negative");
+    REQUIRE(h->k <= 128, YUE_E_UNSUPPORTED, "WRMF: num.factors must be <= 128");
+    CK(cudaSetDevice(h->device));
+    if (int rc = q_rowmajor(h)) return rc;
+    if (int rc = wrmf_prepare(h)) return rc;
+    if (h->k <= 16) return wrmf_sweep_impl<1>(h, side, reg, alpha, loss_out);
+    if (h->k <= 32) return wrmf_sweep_impl<2>(h, side, reg, alpha, loss_out);
+    if (h->k <= 64) return wrmf_sweep_impl<4>(h, side, reg, alpha, loss_out);
+    return wrmf_sweep_impl<8>(h, side, reg, alpha, loss_out);
+}
+
+int yue_wrmf_pair_counts(yue_t* h, int32_t* uq_counts, int64_t* it_indptr, int32_t* it_users, int32_t* it_counts) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "interactions not set");
+    CK(cudaSetDevice(h->device));
+    if (int rc = wrmf_prepare(h)) return rc;
+    cudaStream_t st = h->stream;
+    if (uq_counts && h->nnz) CK(cudaMemcpyAsync(uq_counts, h->uq_cnt.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (it_indptr) CK(cudaMemcpyAsync(it_indptr, h->it_indptr.p, (h->n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (it_users && h->nnz) CK(cudaMemcpyAsync(it_users, h->it_users.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (it_counts && h->nnz) CK(cudaMemcpyAsync(it_counts, h->it_cnt.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return YUE_OK;
 }
 

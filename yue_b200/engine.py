@@ -189,6 +189,21 @@ class Engine:
                                         len(u), lr, regU, regI, eps, regA, mode, C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
 
+    def wrmf_sweep(self, side, reg, alpha=10.0, want_loss=False):
+        """One WRMF half-sweep (0: every user row from the track table, 1: every track row from the user table)."""
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_wrmf_sweep(self.h, int(side), float(reg), float(alpha), C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
+    def wrmf_pair_counts(self):
+        """(uq_counts[nnz], it_indptr[n+1], it_users[nnz], it_counts[nnz]): plays per unique pair and the track-major pairs."""
+        nnz = self.interaction_sizes()[3]
+        cnt, itp = np.empty(nnz, np.int32), np.empty(self.n + 1, np.int64)
+        itu, itc = np.empty(nnz, np.int32), np.empty(nnz, np.int32)
+        self._ck(self.lib.yue_wrmf_pair_counts(self.h, _ptr(cnt, C.c_int32), _ptr(itp, C.c_int64), _ptr(itu, C.c_int32),
+                                               _ptr(itc, C.c_int32)))
+        return cnt, itp, itu, itc
+
     def frob2(self):
         p2, q2 = C.c_double(), C.c_double()
         self._ck(self.lib.yue_frob2(self.h, C.byref(p2), C.byref(q2)))
@@ -286,6 +301,12 @@ class Engine:
 
     def flush_l2(self):
         self._ck(self.lib.yue_flush_l2(self.h))
+
+
+def device_count():
+    n = C.c_int(0)
+    _lib.load().yue_device_count(C.byref(n))
+    return n.value
 
 
 def comm_unique_id():

@@ -5,7 +5,7 @@ yue.py:10-135, for running the GPU recommenders without the reference tree.
     from yue_b200.host.driver import Yue
     Yue(Config('config/BPR.conf')).execute()
 
-`recommender=<Name>` is resolved in yue_b200's registry (BPR, APR) instead of by importing
+`recommender=<Name>` is resolved in yue_b200's registry (BPR, APR, WRMF) instead of by importing
 recommender.{baseline,cf,advanced}.<Name>; `-cv k` folds run one after the other on the same GPU
 unless `-p` is given, in which case fold i uses CUDA device i % device_count (the reference runs
 them as processes and divides MKL threads, yue.py:72-105).
@@ -26,6 +26,8 @@ def _registry():
         reg['APR'] = APR
     except ImportError:
         pass
+    from ..wrmf import WRMF
+    reg['WRMF'] = WRMF
     return reg
 
 
@@ -76,11 +78,8 @@ class Yue(object):
         parallel = self.evaluation.contains('-p')
         ctx = get_context('spawn')                 # CUDA contexts do not survive fork
         queue = ctx.Queue()
-        try:
-            import torch
-            ndev = max(1, torch.cuda.device_count())
-        except Exception:
-            ndev = 1
+        from ..engine import device_count
+        ndev = max(1, device_count())
         procs = []
         for i, (train, test) in enumerate(DataSplit.crossValidation(self.trainingData, k), 1):
             p = ctx.Process(target=_run_fold, args=(queue, name, self.config, train, test, '[' + str(i) + ']', i,
