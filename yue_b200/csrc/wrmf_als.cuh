@@ -9,7 +9,7 @@
 //   wrmf_chunk_kernel    rows with more than kWrmfChunk entries (the heaviest users, the most played tracks: one
 //                        track of config C2 has ~6e5 listeners) are cut into chunks whose weighted Gram + rhs partials
 //                        go to scratch, so that no single CTA is a straggler;
-//   wrmf_solve_kernel    one CTA per row, rows from a global cursor: A = G + reg I + sum of the row's rank-1 terms
+//   wrmf_solve_kernel    one CTA per row (rows strided over the grid, the next row's data prefetched): A = G + reg I + sum of the row's rank-1 terms
 //                        (or of its chunk partials), LDL^T in registers, forward substitution carried as an extra
 //                        row of the factorisation, backward substitution by row blocks, X[row] stored as float32.
 //
@@ -53,7 +53,6 @@ struct WrmfSide {
     const int32_t* chunk_row;
     double* partA;              // [n_chunks][TD*TD][kWrmfThreads]
     double* partb;              // [n_chunks][KP]
-    unsigned long long* cursor;
     double* loss;               // += sum of squared errors, or nullptr
 };
 
@@ -63,62 +62,105 @@ struct WrmfTile {
     double bb[TD];              // rhs of columns tx*TD + j (diagonal threads only)
 };
 
-__device__ __forceinline__ void wrmf_block_of_thread(int t, int& ty, int& tx) {
-    int r = 0;
-    while ((r + 1) * (r + 2) / 2 <= t) ++r;
-    ty = r; tx = t - r * (r + 1) / 2;
+// 1/d for a positive, normal d: float32 reciprocal as the seed, two Newton steps in float64 (relative error ~2^-46
+// after the first, below 2^-52 after the second).  ~4 dependent FMAs instead of the ~25-instruction IEEE division;
+// the pivots of G + reg I + (rank-1 terms) are positive and far from the float32 range limits.
+__device__ __forceinline__ double wrmf_rcp(double d) {
+    double x = (double)__frcp_rn((float)d);
+    x = fma(x, fma(-d, x, 1.0), x);
+    x = fma(x, fma(-d, x, 1.0), x);
+    return x;
 }
 
-// acc += sum_e w_e y_e y_e^T, bb += sum_e (1 + w_e) y_e over entries [e0, e1) (rows idx[e] of `other`, or rows e
-// themselves when idx == nullptr, then w = 1 and bb is not touched).  ys: smem [kWrmfBatch][KP] doubles, ws: smem
-// [kWrmfBatch], xs: smem [KP] (the row's current solution, LOSS only).
+// Thread -> block of A, column by column: threads 0..15 own block column 0 (block rows 0..15), threads 16..30 column 1
+// (rows 1..15), ...  A warp then shares (almost) one block column: its reads of the column's entries are broadcasts,
+// its reads of the row entries are contiguous, and once the factorisation has passed a warp's columns the whole warp
+// skips the update -- the shared-memory wavefronts and the float64 issue slots of a step shrink with the trailing matrix.
+__device__ __forceinline__ void wrmf_block_of_thread(int t, int& ty, int& tx) {
+    int c = 0, start = 0;
+    while (start + (16 - c) <= t) { start += 16 - c; ++c; }
+    tx = c; ty = c + (t - start);
+}
+
+// TD consecutive doubles from 16-byte aligned shared memory (LDS.128 for TD >= 2)
+template <int TD>
+__device__ __forceinline__ void wrmf_lds(const double* p, double (&v)[TD]) {
+    if constexpr (TD == 1) {
+        v[0] = p[0];
+    } else {
+#pragma unroll
+        for (int i = 0; i < TD; i += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + i);
+            v[i] = t.x; v[i + 1] = t.y;
+        }
+    }
+}
+
+// One staged batch in flight: kWrmfBatch rows of the other table (this thread's float4 slots) and one weight.
+template <int TD>
+struct WrmfPre {
+    static constexpr int Q4 = 16 * TD / 4;                       // float4 per staged row
+    static constexpr int NLOAD = (kWrmfBatch * Q4 + kWrmfThreads - 1) / kWrmfThreads;
+    float4 v[NLOAD];
+    double w;
+};
+
+// issue the loads of entries [eb, min(eb + kWrmfBatch, e1)): rows idx[e] of `other` (rows e themselves when idx ==
+// nullptr) and their weights alpha * cnt[e] (1 when cnt == nullptr)
+template <int TD>
+__device__ __forceinline__ void wrmf_fetch(WrmfPre<TD>& pre, const float* __restrict__ other, int ld, const int32_t* __restrict__ idx,
+                                           const int32_t* __restrict__ cnt, double alpha, int64_t eb, int64_t e1) {
+    constexpr int Q4 = WrmfPre<TD>::Q4;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < WrmfPre<TD>::NLOAD; ++q) {
+        const int s = tid + q * kWrmfThreads;
+        const int r = s / Q4, c4 = s % Q4;
+        pre.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < kWrmfBatch && eb + r < e1 && c4 * 4 < ld) {
+            const int64_t row = idx ? (int64_t)idx[eb + r] : eb + r;
+            pre.v[q] = __ldg(reinterpret_cast<const float4*>(other + row * ld) + c4);
+        }
+    }
+    pre.w = 0.0;
+    if (tid < kWrmfBatch && eb + tid < e1) pre.w = cnt ? alpha * (double)cnt[eb + tid] : 1.0;
+}
+
+// acc += sum_e w_e y_e y_e^T, bb += sum_e (1 + w_e) y_e over entries [e0, e1) (bb only when cnt != nullptr).  `pre` holds
+// the first batch already (wrmf_fetch(pre, ..., e0, e1) issued by the caller, possibly long ago).  ys: smem
+// [kWrmfBatch][KP] doubles, ws: smem [kWrmfBatch], xs: smem [KP] (the row's current solution, LOSS only).
 template <int TD, bool LOSS>
-__device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, const float* __restrict__ other, int ld, int k,
+__device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, WrmfPre<TD>& pre, const float* __restrict__ other, int ld,
                                                 const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int64_t e0,
                                                 int64_t e1, double alpha, double* ys, double* ws, const double* xs, double& loss,
                                                 int ty, int tx, bool active) {
     constexpr int KP = 16 * TD;
-    constexpr int Q4 = KP / 4;                                   // float4 per staged row
-    constexpr int NLOAD = (kWrmfBatch * Q4 + kWrmfThreads - 1) / kWrmfThreads;
+    constexpr int Q4 = WrmfPre<TD>::Q4;
     const int tid = threadIdx.x;
-    float4 pre[NLOAD];
-    double prew = 0.0;
-    auto fetch = [&](int64_t eb) {
-#pragma unroll
-        for (int q = 0; q < NLOAD; ++q) {
-            const int s = tid + q * kWrmfThreads;
-            const int r = s / Q4, c4 = s % Q4;
-            pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < kWrmfBatch && eb + r < e1 && c4 * 4 < ld) {
-                const int64_t row = idx ? (int64_t)idx[eb + r] : eb + r;
-                pre[q] = __ldg(reinterpret_cast<const float4*>(other + row * ld) + c4);
-            }
-        }
-        if (tid < kWrmfBatch) prew = (eb + tid < e1) ? (cnt ? alpha * (double)cnt[eb + tid] : 1.0) : 0.0;
-    };
-    if (e0 < e1) fetch(e0);
     for (int64_t eb = e0; eb < e1; eb += kWrmfBatch) {
 #pragma unroll
-        for (int q = 0; q < NLOAD; ++q) {
+        for (int q = 0; q < WrmfPre<TD>::NLOAD; ++q) {
             const int s = tid + q * kWrmfThreads;
             const int r = s / Q4, c4 = s % Q4;
             if (r < kWrmfBatch) {
                 double* d = ys + r * KP + c4 * 4;
                 // columns >= k of a padded table row are zero by construction (yue_set_factors)
-                d[0] = pre[q].x; d[1] = pre[q].y; d[2] = pre[q].z; d[3] = pre[q].w;
+                d[0] = pre.v[q].x; d[1] = pre.v[q].y; d[2] = pre.v[q].z; d[3] = pre.v[q].w;
             }
         }
-        if (tid < kWrmfBatch) ws[tid] = prew;
+        if (tid < kWrmfBatch) ws[tid] = pre.w;
         __syncthreads();
-        if (eb + kWrmfBatch < e1) fetch(eb + kWrmfBatch);        // in flight under the FMAs below
+        if (eb + kWrmfBatch < e1) wrmf_fetch<TD>(pre, other, ld, idx, cnt, alpha, eb + kWrmfBatch, e1);   // in flight under the FMAs
         const int nb = (int)((e1 - eb) < (int64_t)kWrmfBatch ? (e1 - eb) : (int64_t)kWrmfBatch);
         if (active) {
             for (int e = 0; e < nb; ++e) {
                 const double* y = ys + e * KP;
                 const double w = ws[e];
                 double a[TD], b[TD];
+                wrmf_lds<TD>(y + ty * TD, a);
+                wrmf_lds<TD>(y + tx * TD, b);
 #pragma unroll
-                for (int i = 0; i < TD; ++i) { a[i] = y[ty * TD + i] * w; b[i] = y[tx * TD + i]; }
+                for (int i = 0; i < TD; ++i) a[i] *= w;
 #pragma unroll
                 for (int i = 0; i < TD; ++i)
 #pragma unroll
@@ -148,7 +190,7 @@ template <int TD>
 __global__ void __launch_bounds__(kWrmfThreads) wrmf_gram_kernel(const float* __restrict__ F, int64_t n, int ld, int k,
                                                                  double* __restrict__ partial) {
     constexpr int KP = 16 * TD;
-    extern __shared__ double wrmf_smem[];
+    extern __shared__ __align__(16) double wrmf_smem[];
     double* ys = wrmf_smem;
     double* ws = ys + kWrmfBatch * KP;
     const int tid = threadIdx.x;
@@ -163,7 +205,9 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_gram_kernel(const float* __
         for (int j = 0; j < TD; ++j) tl.acc[i][j] = 0.0; }
     const int64_t r0 = n * (int64_t)blockIdx.x / gridDim.x, r1 = n * (int64_t)(blockIdx.x + 1) / gridDim.x;
     double dummy = 0.0;
-    wrmf_accumulate<TD, false>(tl, F, ld, k, nullptr, nullptr, r0, r1, 1.0, ys, ws, nullptr, dummy, ty, tx, active);
+    WrmfPre<TD> pre;
+    wrmf_fetch<TD>(pre, F, ld, nullptr, nullptr, 1.0, r0, r1);
+    wrmf_accumulate<TD, false>(tl, pre, F, ld, nullptr, nullptr, r0, r1, 1.0, ys, ws, nullptr, dummy, ty, tx, active);
     double* out = partial + (size_t)blockIdx.x * TD * TD * kWrmfThreads;
 #pragma unroll
     for (int i = 0; i < TD; ++i)
@@ -183,7 +227,7 @@ __global__ void wrmf_gram_reduce_kernel(const double* __restrict__ partial, int 
 template <int TD, bool LOSS>
 __global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
     constexpr int KP = 16 * TD;
-    extern __shared__ double wrmf_smem[];
+    extern __shared__ __align__(16) double wrmf_smem[];
     double* ys = wrmf_smem;
     double* ws = ys + kWrmfBatch * KP;
     double* xs = ws + kWrmfBatch;
@@ -201,8 +245,10 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
 #pragma unroll
         for (int j = 0; j < TD; ++j) tl.acc[i][j] = 0.0; }
     double loss = 0.0;
-    wrmf_accumulate<TD, LOSS>(tl, sd.other, sd.ld, sd.k, sd.idx, sd.cnt, sd.chunk_begin[ch], sd.chunk_end[ch], sd.alpha, ys, ws, xs,
-                              loss, ty, tx, active);
+    const int64_t c0 = sd.chunk_begin[ch], c1 = sd.chunk_end[ch];
+    WrmfPre<TD> pre;
+    wrmf_fetch<TD>(pre, sd.other, sd.ld, sd.idx, sd.cnt, sd.alpha, c0, c1);
+    wrmf_accumulate<TD, LOSS>(tl, pre, sd.other, sd.ld, sd.idx, sd.cnt, c0, c1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
     double* pa = sd.partA + (size_t)ch * TD * TD * kWrmfThreads;
 #pragma unroll
     for (int i = 0; i < TD; ++i)
@@ -220,18 +266,17 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
 }
 
 template <int TD, bool LOSS>
-__global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
+__global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_kernel(WrmfSide sd) {
     constexpr int KP = 16 * TD;
-    extern __shared__ double wrmf_smem[];
+    extern __shared__ __align__(16) double wrmf_smem[];
     double* ys = wrmf_smem;                              // [kWrmfBatch][KP]
     double* ws = ys + kWrmfBatch * KP;                   // [kWrmfBatch]
     double* xs = ws + kWrmfBatch;                        // [KP]  solution before the update (loss)
-    double* col = xs + KP;                               // [2][KP + 1]  current column of the factorisation (+ the rhs row)
-    double* dv = col + 2 * (KP + 1);                     // [KP]  pivots
+    double* col = xs + KP;                               // [2][KP + 2]  current column of the factorisation, the rhs row, 1/pivot
+    double* dv = col + 2 * (KP + 2);                     // [KP]  reciprocal pivots
     double* yv = dv + KP;                                // [KP]  D^-1 L^-1 b, then consumed by the back substitution
     double* xv = yv + KP;                                // [KP]  the solution
     double* gs = xv + KP;                                // [TD*TD][kWrmfThreads]  G + reg I
-    __shared__ long long s_row;
     const int tid = threadIdx.x;
     int ty = 0, tx = 0;
     const int k = sd.k, ld = sd.ld;
@@ -249,15 +294,25 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
             gs[(i * TD + j) * kWrmfThreads + tid] = g;
         }
     double loss = 0.0;
-    for (;;) {
+    // Rows blockIdx.x, blockIdx.x + gridDim.x, ...  While a row is being factorised (~64 dependent steps) the first batch
+    // of the NEXT row -- entry range, row ids, rows of the other table: three dependent global loads -- is already in
+    // flight into registers, so a row starts with its data on chip.
+    int64_t row = blockIdx.x;
+    int64_t e0 = 0, e1 = 0;
+    WrmfPre<TD> pre;
+    if (row < sd.rows) {
+        e0 = sd.indptr[row]; e1 = sd.indptr[row + 1];
+        if (e1 - e0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
+    }
+    for (; row < sd.rows; ) {
         __syncthreads();                                  // smem of the previous row is free
-        if (tid == 0) s_row = (long long)atomicAdd(sd.cursor, 1ull);
-        __syncthreads();
-        const int64_t row = s_row;
-        if (row >= sd.rows) break;
-        const int64_t e0 = sd.indptr[row], e1 = sd.indptr[row + 1];
+        const int64_t nrow = row + gridDim.x;
+        int64_t ne0 = 0, ne1 = 0;
+        if (nrow < sd.rows) { ne0 = sd.indptr[nrow]; ne1 = sd.indptr[nrow + 1]; }
         if (e1 == e0) {                                   // nobody played it / played nothing: b = 0 -> the row is 0
             for (int c = tid; c < ld; c += kWrmfThreads) sd.out[row * ld + c] = 0.f;
+            row = nrow; e0 = ne0; e1 = ne1;
+            if (row < sd.rows && e1 - e0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
             continue;
         }
         if (LOSS) for (int c = tid; c < KP; c += kWrmfThreads) xs[c] = c < k ? (double)sd.out[row * ld + c] : 0.0;
@@ -267,7 +322,7 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
 #pragma unroll
             for (int j = 0; j < TD; ++j) tl.acc[i][j] = gs[(i * TD + j) * kWrmfThreads + tid]; }
         if (e1 - e0 <= kWrmfChunk) {
-            wrmf_accumulate<TD, LOSS>(tl, sd.other, ld, k, sd.idx, sd.cnt, e0, e1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
+            wrmf_accumulate<TD, LOSS>(tl, pre, sd.other, ld, sd.idx, sd.cnt, e0, e1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
         } else {                                          // chunk partials, in chunk order
             int lo = 0, hi = sd.n_heavy;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (sd.heavy_rows[mid] < row) lo = mid + 1; else hi = mid; }
@@ -283,23 +338,30 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
                 }
             }
         }
-        // ---- LDL^T, one column per step; the rhs rides along as row KP of the matrix ----
+        if (nrow < sd.rows && ne1 - ne0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, ne0, ne1);
+        // ---- LDL^T, one column per step; the rhs rides along as row KP of the matrix.  The pivot's reciprocal is
+        //      computed once, by the thread that owns the pivot, and published with the column (slot KP + 1).
+        //      (A variant that works by block columns of TD unknowns -- two barriers per TD columns, TD^3 FMAs per
+        //      2 TD^2 shared-memory words -- was measured SLOWER, 76 vs 65 ms per user sweep at config C2: the serial
+        //      factorisation of the diagonal block by one thread stretches the chain the barriers wait on.) ----
         for (int jb = 0; jb < nblk; ++jb) {
 #pragma unroll
             for (int jj = 0; jj < TD; ++jj) {
                 const int j = jb * TD + jj;
-                double* cb = col + (j & 1) * (KP + 1);
+                double* cb = col + (j & 1) * (KP + 2);
                 if (active && tx == jb) {
 #pragma unroll
                     for (int i = 0; i < TD; ++i) cb[ty * TD + i] = tl.acc[i][jj];
-                    if (ty == jb) { cb[KP] = tl.bb[jj]; dv[j] = tl.acc[jj][jj]; }
+                    if (ty == jb) {
+                        const double inv = wrmf_rcp(tl.acc[jj][jj]);
+                        cb[KP] = tl.bb[jj]; cb[KP + 1] = inv; dv[j] = inv;
+                    }
                 }
                 __syncthreads();
                 if (active && tx >= jb) {
-                    const double inv = 1.0 / cb[j];
+                    const double inv = cb[KP + 1];
                     double rv[TD];
-#pragma unroll
-                    for (int i = 0; i < TD; ++i) rv[i] = cb[ty * TD + i];
+                    wrmf_lds<TD>(cb + ty * TD, rv);
                     const double rb = cb[KP];
 #pragma unroll
                     for (int jc = 0; jc < TD; ++jc) {
@@ -313,10 +375,11 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
                 }
             }
         }
-        // ---- y = D^-1 z (z = the forward-substituted rhs now in bb), then x = L^-T y by row blocks, last block first ----
+        // ---- y = D^-1 z (z = the forward-substituted rhs now in bb), then x = L^-T y by row blocks, last block first;
+        //      dv holds the reciprocal pivots, so no division is left ----
         if (diag) {
 #pragma unroll
-            for (int j = 0; j < TD; ++j) yv[tx * TD + j] = tl.bb[j] / tl.acc[j][j];
+            for (int j = 0; j < TD; ++j) yv[tx * TD + j] = tl.bb[j] * dv[tx * TD + j];
         }
         __syncthreads();
         for (int rbk = nblk - 1; rbk >= 0; --rbk) {
@@ -324,11 +387,11 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
                 double xl[TD];
 #pragma unroll
                 for (int i = TD - 1; i >= 0; --i) {
-                    double s = yv[rbk * TD + i];
+                    double s = 0.0;
 #pragma unroll
-                    for (int i2 = TD - 1; i2 > i; --i2) s = fma(-(tl.acc[i2][i] / tl.acc[i][i]), xl[i2], s);
-                    xl[i] = s;
-                    xv[rbk * TD + i] = s;
+                    for (int i2 = TD - 1; i2 > i; --i2) s = fma(tl.acc[i2][i], xl[i2], s);
+                    xl[i] = fma(-s, dv[rbk * TD + i], yv[rbk * TD + i]);
+                    xv[rbk * TD + i] = xl[i];
                 }
             }
             __syncthreads();
@@ -338,12 +401,13 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
                     double s = 0.0;
 #pragma unroll
                     for (int i = 0; i < TD; ++i) s = fma(tl.acc[i][jc], xv[rbk * TD + i], s);
-                    yv[tx * TD + jc] -= s / dv[tx * TD + jc];
+                    yv[tx * TD + jc] = fma(-s, dv[tx * TD + jc], yv[tx * TD + jc]);
                 }
             }
             __syncthreads();
         }
         for (int c = tid; c < k; c += kWrmfThreads) sd.out[row * ld + c] = (float)xv[c];
+        row = nrow; e0 = ne0; e1 = ne1;
     }
     if (LOSS) {
 #pragma unroll
@@ -355,7 +419,7 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_solve_kernel(WrmfSide sd) {
 template <int TD>
 constexpr size_t wrmf_solve_smem() {
     constexpr int KP = 16 * TD;
-    return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP + 2 * (KP + 1) + 3 * KP + TD * TD * kWrmfThreads);
+    return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP + 2 * (KP + 2) + 3 * KP + TD * TD * kWrmfThreads);
 }
 template <int TD>
 constexpr size_t wrmf_accum_smem() {

@@ -202,7 +202,6 @@ struct yue_handle {
         int n_heavy = 0, n_chunks = 0;
     } wrmf_plan[2];
     DevBuf<double> wrmf_G, wrmf_part, wrmf_partA, wrmf_partb;
-    DevBuf<unsigned long long> wrmf_cursor;
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -394,7 +393,7 @@ int yue_destroy(yue_t* h) {
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->delta_w, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
     h->l2buf.release();
-    h->uq_cnt.release(); h->it_users.release(); h->it_cnt.release(); h->it_indptr.release(); h->wrmf_cursor.release();
+    h->uq_cnt.release(); h->it_users.release(); h->it_cnt.release(); h->it_indptr.release();
     for (auto* b : {&h->wrmf_G, &h->wrmf_part, &h->wrmf_partA, &h->wrmf_partb}) b->release();
     for (auto& pl : h->wrmf_plan) { pl.heavy_rows.release(); pl.heavy_first.release(); pl.chunk_row.release(); pl.chunk_begin.release(); pl.chunk_end.release(); }
     h->test_indptr.release(); h->test_items.release(); h->met_terms.release(); h->met_sums.release(); h->met_seen.release(); h->met_distinct.release();
@@ -1283,7 +1282,6 @@ static int wrmf_prepare(yue_t* h) {
     if (int rc = host_indptrs(h)) return rc;
     if (int rc = wrmf_plan_side(h, 0, h->h_uq_indptr.data(), m)) return rc;
     if (int rc = wrmf_plan_side(h, 1, hit.data(), n)) return rc;
-    CK(h->wrmf_cursor.resize(1));
     h->wrmf_ready = true;
     return YUE_OK;
 }
@@ -1315,9 +1313,8 @@ static int wrmf_sweep_impl(yue_t* h, int side, double reg, double alpha, double*
     sd.rows = rows; sd.ld = h->ld; sd.k = h->k; sd.reg = reg; sd.alpha = alpha; sd.G = h->wrmf_G.p;
     sd.heavy_rows = pl.heavy_rows.p; sd.heavy_first = pl.heavy_first.p; sd.n_heavy = pl.n_heavy;
     sd.chunk_begin = pl.chunk_begin.p; sd.chunk_end = pl.chunk_end.p; sd.chunk_row = pl.chunk_row.p;
-    sd.partA = h->wrmf_partA.p; sd.partb = h->wrmf_partb.p; sd.cursor = h->wrmf_cursor.p; sd.loss = h->scal.p;
+    sd.partA = h->wrmf_partA.p; sd.partb = h->wrmf_partb.p; sd.loss = h->scal.p;
     CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), st));
-    CK(cudaMemsetAsync(h->wrmf_cursor.p, 0, sizeof(unsigned long long), st));
     if (other_rows) {
         wrmf_gram_kernel<TD><<<n_part, kWrmfThreads, sm_acc, st>>>(sd.other, other_rows, h->ld, h->k, h->wrmf_part.p);
         wrmf_gram_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(h->wrmf_part.p, n_part, (int)elems, h->wrmf_G.p);
