@@ -188,6 +188,10 @@ int yue_rank_metrics(yue_t* h, int n_cuts, const int32_t* cuts, double* sums_out
  * float64 (the reference's YtY is a float32 sgemm): factors agree with the reference class to ~5e-6 per row.
  * Ranking afterwards is yue_rank_topn (predict = Y.dot(X[u]), WRMF.py:86-88). */
 int yue_wrmf_sweep(yue_t* h, int side, double reg, double alpha, double* loss_out);
+/* The same for rows [row_begin, row_end) only (*loss_out = their share).  Rows of a sweep are independent, so N
+ * GPUs that hold the same log and tables each solve a range and exchange the solved rows (yue_b200/sharding.py:
+ * WrmfShardedTrainer) -- the result is bit-identical to one GPU's. */
+int yue_wrmf_sweep_rows(yue_t* h, int side, int64_t row_begin, int64_t row_end, double reg, double alpha, double* loss_out);
 /* Check hook: the pair counts (aligned with uq_items) and the track-major form of the play sets the sweeps use
  * (it_indptr[n+1], it_users[nnz] sorted inside a track, it_counts[nnz]); any pointer may be NULL. */
 int yue_wrmf_pair_counts(yue_t* h, int32_t* uq_counts, int64_t* it_indptr, int32_t* it_users, int32_t* it_counts);

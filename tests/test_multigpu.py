@@ -120,3 +120,55 @@ def test_two_gpu_nccl_matches_two_handle_emulation():
         eng.close()
     assert np.allclose(Q0, Qref, rtol=1e-6, atol=1e-8)
     assert np.allclose(P0, Pl[0], rtol=1e-6, atol=1e-8) and np.allclose(P1, Pl[1], rtol=1e-6, atol=1e-8)
+
+
+# ---- WRMF: row-sharded half-sweeps over NCCL (yue_b200/sharding.py: WrmfShardedTrainer) --------------------------
+def _wrmf_rank_main(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    log = synth.power_law_log(3000, 900, 150000, seed=12)
+    P, Q = synth.init_factors(log.m, log.n, 40, seed=13)
+    eng = Engine(rank)
+    eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    eng.set_factors(P * 10, Q * 10)
+    tr = sharding.WrmfShardedTrainer(eng, dist, torch.device("cuda", rank), log.uq_indptr, eng.wrmf_pair_counts()[1])
+    losses = [tr.iteration(1.0) for _ in range(2)]
+    X, Y = eng.get_factors()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (X, Y, losses))
+    if rank == 0:
+        out["res"] = gathered
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_nccl_wrmf_is_bit_identical_to_one_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_wrmf_rank_main, args=(2, port, out), nprocs=2, join=True)
+    (X0, Y0, l0), (X1, Y1, l1) = out["res"]
+    assert np.array_equal(X0, X1) and np.array_equal(Y0, Y1) and l0 == l1
+    log = synth.power_law_log(3000, 900, 150000, seed=12)
+    P, Q = synth.init_factors(log.m, log.n, 40, seed=13)
+    eng = Engine(0)
+    try:
+        eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+        eng.set_factors(P * 10, Q * 10)
+        ref = []
+        for _ in range(2):
+            ref.append(eng.wrmf_sweep(0, 1.0, 10.0, want_loss=True))
+            eng.wrmf_sweep(1, 1.0, 10.0)
+        X, Y = eng.get_factors()
+    finally:
+        eng.close()
+    assert np.array_equal(X0, X) and np.array_equal(Y0, Y)
+    assert l0 == pytest.approx(ref, rel=1e-12)

@@ -126,3 +126,58 @@ def test_saturation_weights_limits():
     a, G = 0.7, 4
     w = sharding.saturation_weights(np.array([-np.log(a) / 1e-3 * G * 8]), G, 8, 1e-3)[0]
     assert abs(w * G * (1 - a) - (1 - a ** G)) < 1e-6
+
+
+# ---- WRMF: row-sharded half-sweeps (the oracle plays the kernel), rows exchanged over a 2-process gloo group ----
+def _wrmf_half_rows(out, other, indptr, idx, cnt, lo, hi, reg, want_loss=False):
+    """oracle half-sweep restricted to rows [lo, hi): the Gram matrix is of the WHOLE other table, like the kernel's"""
+    from oracle import wrmf_ref
+    sub = out[lo:hi]                                       # view: solved in place
+    return wrmf_ref.half_sweep(sub, other, indptr[lo:hi + 1], idx, cnt, reg, gram="f64", want_loss=want_loss)
+
+
+def _wrmf_worker(rank, world, port, ret):
+    from oracle import wrmf_ref
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    log = synth.power_law_log(300, 150, 9000, seed=21)
+    X, Y = synth.init_factors(log.m, log.n, 12, seed=22)
+    X, Y = X * 10, Y * 10
+    cnt = wrmf_ref.pair_counts(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    itp, itu, itc = wrmf_ref.transpose(log.m, log.n, log.uq_indptr, log.uq_items, cnt)
+    ub, tb = sharding.shard_users_by_events(log.uq_indptr, world), sharding.shard_users_by_events(itp, world)
+    Xt, Yt = torch.from_numpy(X), torch.from_numpy(Y)     # share memory with X, Y
+    losses = []
+    for _ in range(2):
+        loss = _wrmf_half_rows(X, Y, log.uq_indptr, log.uq_items, cnt, ub[rank], ub[rank + 1], 0.5, want_loss=True)
+        sharding.exchange_rows(Xt, ub, dist)
+        _wrmf_half_rows(Y, X, itp, itu, itc, tb[rank], tb[rank + 1], 0.5)
+        sharding.exchange_rows(Yt, tb, dist)
+        lt = torch.tensor([loss], dtype=torch.float64)
+        dist.all_reduce(lt)
+        losses.append(float(lt.item()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (X, Y, losses))
+    if rank == 0:
+        ret["out"] = gathered
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_wrmf_row_exchange_is_exact():
+    from oracle import wrmf_ref
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_wrmf_worker, args=(2, port, ret), nprocs=2, join=True)
+    (Xa, Ya, la), (Xb, Yb, lb) = ret["out"]
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ya, Yb) and la == lb
+    log = synth.power_law_log(300, 150, 9000, seed=21)
+    X, Y = synth.init_factors(log.m, log.n, 12, seed=22)
+    X, Y = X * 10, Y * 10
+    cnt = wrmf_ref.pair_counts(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    itp, itu, itc = wrmf_ref.transpose(log.m, log.n, log.uq_indptr, log.uq_items, cnt)
+    losses = [wrmf_ref.iteration(X, Y, log.uq_indptr, log.uq_items, cnt, itp, itu, itc, 0.5, gram="f64") for _ in range(2)]
+    assert np.array_equal(Xa, X) and np.array_equal(Ya, Y)           # no reduction anywhere: bit-identical to one process
+    assert la == pytest.approx(losses, rel=1e-12)

@@ -157,3 +157,43 @@ def test_wrmf_class_trains_and_ranks(tmp_path):
     assert model.loss == pytest.approx(loss, rel=1e-5)
     assert measure[0] == "Top 5\n" and measure[1].startswith("Precision:") and measure[6] == "Top 10\n"
     assert float(measure[8].split(":")[1]) > 0.02                 # Recall@10 well above chance (10/2000)
+
+
+def test_row_ranges_compose_to_the_sweep_two_handles_emulate_two_ranks():
+    """yue_wrmf_sweep_rows: two handles with the same log and tables each solve a range of rows (balanced by entries, a
+    heavy row on each side of the cut), the solved rows are exchanged through the host in place of the broadcasts of
+    WrmfShardedTrainer: tables bit-identical to the single-handle sweep, losses add up."""
+    from yue_b200 import sharding
+    from yue_b200.engine import Engine
+    m, n, k = 5200, 6100, 40
+    rng = np.random.default_rng(1)
+    base = synth.power_law_log(m, n, 60000, seed=4)
+    bu = np.repeat(np.arange(base.m), np.diff(base.ev_indptr))
+    users = np.concatenate([bu, np.zeros(5000, np.int64), np.full(4800, m - 1), np.arange(4500)])
+    items = np.concatenate([base.ev_items, np.arange(5000), np.arange(1000, 5800), np.full(4500, 7)])
+    ev_indptr, ev_items, uq_indptr, uq_items = csr_from_events(m, n, users.astype(np.int64), items.astype(np.int64))
+    X0, Y0 = synth.init_factors(m, n, k, seed=3)
+    X0, Y0 = X0 * 10, Y0 * 10
+    engs = [Engine(0), Engine(0), Engine(0)]
+    try:
+        for e in engs:
+            e.set_interactions(m, n, ev_indptr, ev_items, uq_indptr, uq_items)
+            e.set_factors(X0, Y0)
+        itp = engs[0].wrmf_pair_counts()[1]
+        ub, tb = sharding.shard_users_by_events(uq_indptr, 2), sharding.shard_users_by_events(itp, 2)
+        assert 0 < ub[1] < m and 0 < tb[1] < n
+        ref_loss = engs[2].wrmf_sweep(0, 0.7, 10.0, want_loss=True)
+        engs[2].wrmf_sweep(1, 0.7, 10.0)
+        Xr, Yr = engs[2].get_factors()
+        parts = [engs[r].wrmf_sweep_rows(0, ub[r], ub[r + 1], 0.7, 10.0, want_loss=True) for r in range(2)]
+        X = np.concatenate([engs[r].get_factors()[0][ub[r]:ub[r + 1]] for r in range(2)])
+        assert np.array_equal(X, Xr) and sum(parts) == pytest.approx(ref_loss, rel=1e-12)
+        for e in engs[:2]:
+            e.set_factors(X, Y0)                                   # the exchange
+        for r in range(2):
+            engs[r].wrmf_sweep_rows(1, tb[r], tb[r + 1], 0.7, 10.0)
+        Y = np.concatenate([engs[r].get_factors()[1][tb[r]:tb[r + 1]] for r in range(2)])
+        assert np.array_equal(Y, Yr)
+    finally:
+        for e in engs:
+            e.close()

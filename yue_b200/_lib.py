@@ -98,6 +98,7 @@ SIGNATURES = {
     "yue_rank_metrics": (C.c_int, [_H, C.c_int, _i32p, _f64p, _i64p]),
     "yue_flush_l2": (C.c_int, [_H]),
     "yue_wrmf_sweep": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, _f64p]),
+    "yue_wrmf_sweep_rows": (C.c_int, [_H, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_double, _f64p]),
     "yue_wrmf_pair_counts": (C.c_int, [_H, _i32p, _i64p, _i32p, _i32p]),
 }
 

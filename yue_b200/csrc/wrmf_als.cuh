@@ -40,7 +40,8 @@ struct WrmfSide {
     const int64_t* indptr;      // [rows + 1]
     const int32_t* idx;         // rows of `other` per entry
     const int32_t* cnt;         // plays per entry (r_ui)
-    int64_t rows;
+    int64_t row_begin, rows;    // this call solves rows [row_begin, rows)
+    int chunk_off;              // first chunk of the heavy rows in that range
     int ld, k;
     double reg, alpha;
     const double* G;            // Gram matrix of `other`, thread layout [TD*TD][kWrmfThreads]
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
     bool active = tid < kWrmfBlocks;
     if (active) wrmf_block_of_thread(tid, ty, tx);
     active = active && ty < (sd.k + TD - 1) / TD;
-    const int ch = blockIdx.x;
+    const int ch = blockIdx.x + sd.chunk_off;
     const int64_t row = sd.chunk_row[ch];
     if (LOSS) for (int c = tid; c < KP; c += kWrmfThreads) xs[c] = c < sd.k ? (double)sd.out[row * sd.ld + c] : 0.0;
     WrmfTile<TD> tl;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
     // Rows blockIdx.x, blockIdx.x + gridDim.x, ...  While a row is being factorised (~64 dependent steps) the first batch
     // of the NEXT row -- entry range, row ids, rows of the other table: three dependent global loads -- is already in
     // flight into registers, so a row starts with its data on chip.
-    int64_t row = blockIdx.x;
+    int64_t row = sd.row_begin + blockIdx.x;
     int64_t e0 = 0, e1 = 0;
     WrmfPre<TD> pre;
     if (row < sd.rows) {

@@ -200,6 +200,7 @@ struct yue_handle {
         DevBuf<int32_t> heavy_rows, heavy_first, chunk_row;
         DevBuf<int64_t> chunk_begin, chunk_end;
         int n_heavy = 0, n_chunks = 0;
+        std::vector<int32_t> h_chunk_row;       // host copy: which chunks belong to a row range
     } wrmf_plan[2];
     DevBuf<double> wrmf_G, wrmf_part, wrmf_partA, wrmf_partb;
 
@@ -1229,6 +1230,7 @@ static int wrmf_plan_side(yue_t* h, int side, const int64_t* indptr, int64_t row
     auto& pl = h->wrmf_plan[side];
     pl.n_heavy = (int)heavy.size();
     pl.n_chunks = (int)crow.size();
+    pl.h_chunk_row = crow;
     CK(pl.heavy_rows.resize(heavy.size())); CK(pl.heavy_first.resize(first.size())); CK(pl.chunk_row.resize(crow.size()));
     CK(pl.chunk_begin.resize(cb.size())); CK(pl.chunk_end.resize(ce.size()));
     cudaStream_t st = h->stream;
@@ -1287,12 +1289,12 @@ static int wrmf_prepare(yue_t* h) {
 }
 
 template <int TD>
-static int wrmf_sweep_impl(yue_t* h, int side, double reg, double alpha, double* loss_out) {
+static int wrmf_sweep_impl(yue_t* h, int side, int64_t row_begin, int64_t row_end, double reg, double alpha, double* loss_out) {
     constexpr int KP = 16 * TD;
     constexpr size_t elems = (size_t)TD * TD * kWrmfThreads;
     cudaStream_t st = h->stream;
     const int64_t rows = side == 0 ? h->m : h->n, other_rows = side == 0 ? h->n : h->m;
-    if (rows == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
+    if (row_end <= row_begin) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     const bool want_loss = loss_out != nullptr;
     auto& pl = h->wrmf_plan[side];
     const int n_part = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 4, other_rows / 64));
@@ -1310,7 +1312,7 @@ static int wrmf_sweep_impl(yue_t* h, int side, double reg, double alpha, double*
     sd.indptr = side == 0 ? h->uq_indptr.p : h->it_indptr.p;
     sd.idx = side == 0 ? h->uq_items.p : h->it_users.p;
     sd.cnt = side == 0 ? h->uq_cnt.p : h->it_cnt.p;
-    sd.rows = rows; sd.ld = h->ld; sd.k = h->k; sd.reg = reg; sd.alpha = alpha; sd.G = h->wrmf_G.p;
+    sd.row_begin = row_begin; sd.rows = row_end; sd.ld = h->ld; sd.k = h->k; sd.reg = reg; sd.alpha = alpha; sd.G = h->wrmf_G.p;
     sd.heavy_rows = pl.heavy_rows.p; sd.heavy_first = pl.heavy_first.p; sd.n_heavy = pl.n_heavy;
     sd.chunk_begin = pl.chunk_begin.p; sd.chunk_end = pl.chunk_end.p; sd.chunk_row = pl.chunk_row.p;
     sd.partA = h->wrmf_partA.p; sd.partb = h->wrmf_partb.p; sd.loss = h->scal.p;
@@ -1322,15 +1324,18 @@ static int wrmf_sweep_impl(yue_t* h, int side, double reg, double alpha, double*
     } else {
         CK(cudaMemsetAsync(h->wrmf_G.p, 0, elems * sizeof(double), st));
     }
-    if (pl.n_chunks) {
-        if (want_loss) wrmf_chunk_kernel<TD, true><<<pl.n_chunks, kWrmfThreads, sm_acc, st>>>(sd);
-        else wrmf_chunk_kernel<TD, false><<<pl.n_chunks, kWrmfThreads, sm_acc, st>>>(sd);
+    const int c0 = (int)(std::lower_bound(pl.h_chunk_row.begin(), pl.h_chunk_row.end(), (int32_t)row_begin) - pl.h_chunk_row.begin());
+    const int c1 = (int)(std::lower_bound(pl.h_chunk_row.begin(), pl.h_chunk_row.end(), (int32_t)std::min<int64_t>(row_end, INT32_MAX)) - pl.h_chunk_row.begin());
+    sd.chunk_off = c0;
+    if (c1 > c0) {
+        if (want_loss) wrmf_chunk_kernel<TD, true><<<c1 - c0, kWrmfThreads, sm_acc, st>>>(sd);
+        else wrmf_chunk_kernel<TD, false><<<c1 - c0, kWrmfThreads, sm_acc, st>>>(sd);
         ++h->launches;
     }
     int per_sm = 1;
     if (want_loss) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, true>, kWrmfThreads, sm_solve));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, false>, kWrmfThreads, sm_solve));
-    const int grid = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * std::max(per_sm, 1));
+    const int grid = (int)std::min<int64_t>(row_end - row_begin, (int64_t)h->sm_count * std::max(per_sm, 1));
     if (want_loss) wrmf_solve_kernel<TD, true><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
     else wrmf_solve_kernel<TD, false><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
     ++h->launches;
@@ -1344,19 +1349,26 @@ static int wrmf_sweep_impl(yue_t* h, int side, double reg, double alpha, double*
     return YUE_OK;
 }
 
-int yue_wrmf_sweep(yue_t* h, int side, double reg, double alpha, double* loss_out) {
+int yue_wrmf_sweep_rows(yue_t* h, int side, int64_t row_begin, int64_t row_end, double reg, double alpha, double* loss_out) {
     REQUIRE(h, YUE_E_ARG, "null handle");
     REQUIRE(h->have_log && h->have_factors, YUE_E_STATE, "interactions or factors not set");
     REQUIRE(side == 0 || side == 1, YUE_E_ARG, "side must be 0 (users) or 1 (tracks)");
     REQUIRE(reg >= 0.0 && alpha >= 0.0, YUE_E_ARG, "reg and alpha must be non-negative");
     REQUIRE(h->k <= 128, YUE_E_UNSUPPORTED, "WRMF: num.factors must be <= 128");
+    const int64_t rows = side == 0 ? h->m : h->n;
+    REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, YUE_E_ARG, "row range outside the table");
     CK(cudaSetDevice(h->device));
     if (int rc = q_rowmajor(h)) return rc;
     if (int rc = wrmf_prepare(h)) return rc;
-    if (h->k <= 16) return wrmf_sweep_impl<1>(h, side, reg, alpha, loss_out);
-    if (h->k <= 32) return wrmf_sweep_impl<2>(h, side, reg, alpha, loss_out);
-    if (h->k <= 64) return wrmf_sweep_impl<4>(h, side, reg, alpha, loss_out);
-    return wrmf_sweep_impl<8>(h, side, reg, alpha, loss_out);
+    if (h->k <= 16) return wrmf_sweep_impl<1>(h, side, row_begin, row_end, reg, alpha, loss_out);
+    if (h->k <= 32) return wrmf_sweep_impl<2>(h, side, row_begin, row_end, reg, alpha, loss_out);
+    if (h->k <= 64) return wrmf_sweep_impl<4>(h, side, row_begin, row_end, reg, alpha, loss_out);
+    return wrmf_sweep_impl<8>(h, side, row_begin, row_end, reg, alpha, loss_out);
+}
+
+int yue_wrmf_sweep(yue_t* h, int side, double reg, double alpha, double* loss_out) {
+    REQUIRE(h && (side == 0 || side == 1), YUE_E_ARG, "null handle or bad side");
+    return yue_wrmf_sweep_rows(h, side, 0, side == 0 ? h->m : h->n, reg, alpha, loss_out);
 }
 
 int yue_wrmf_pair_counts(yue_t* h, int32_t* uq_counts, int64_t* it_indptr, int32_t* it_users, int32_t* it_counts) {

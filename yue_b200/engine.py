@@ -195,6 +195,13 @@ class Engine:
         self._ck(self.lib.yue_wrmf_sweep(self.h, int(side), float(reg), float(alpha), C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
 
+    def wrmf_sweep_rows(self, side, row_begin, row_end, reg, alpha=10.0, want_loss=False):
+        """The half-sweep restricted to rows [row_begin, row_end) (multi-GPU: every rank solves a range)."""
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_wrmf_sweep_rows(self.h, int(side), int(row_begin), int(row_end), float(reg), float(alpha),
+                                              C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
     def wrmf_pair_counts(self):
         """(uq_counts[nnz], it_indptr[n+1], it_users[nnz], it_counts[nnz]): plays per unique pair and the track-major pairs."""
         nnz = self.interaction_sizes()[3]

@@ -132,3 +132,53 @@ class ShardedTrainer:
             loss += l if want_loss else 0.0
             self.exchange()
         return loss if want_loss else None
+
+
+# ---- WRMF: rows of a half-sweep are independent, so the multi-GPU form is exact -------------
+def exchange_rows(table, bounds, dist):
+    """Every rank has solved rows [bounds[r], bounds[r+1]) of `table` ([rows, ld] tensor, same shape on every rank) in
+    place; afterwards every rank holds every solved row.  One broadcast per rank (ranges are balanced by entries, not
+    by rows, so their sizes differ).  Backend-agnostic: gloo on CPU tensors in the tests, NCCL on the library's device
+    buffers on the GPU path."""
+    for r in range(len(bounds) - 1):
+        lo, hi = int(bounds[r]), int(bounds[r + 1])
+        if hi > lo:
+            dist.broadcast(table[lo:hi], src=r)
+
+
+class WrmfShardedTrainer:
+    """One rank of row-sharded WRMF.  Every rank holds the whole log and both tables (Engine.set_interactions /
+    set_factors with the same arrays); per half-sweep a rank solves its range of rows -- ranges balanced by entries
+    (shard_users_by_events on the row pointers) -- and the ranks exchange the solved rows.  No reduction is involved, so
+    the tables are bit-identical to the single-GPU sweep whatever the number of ranks."""
+
+    def __init__(self, engine, dist, device, uq_indptr, it_indptr):
+        import torch
+        from ._lib import BUF_P, BUF_Q
+        self.eng, self.dist, self.torch = engine, dist, torch
+        self.rank, world = dist.get_rank(), dist.get_world_size()
+        self.user_bounds = shard_users_by_events(uq_indptr, world)
+        self.track_bounds = shard_users_by_events(it_indptr, world)
+        ld = (engine.k + 3) & ~3
+        self.tables = []
+        for which, rows in ((BUF_P, engine.m), (BUF_Q, engine.n)):
+            ptr, nbytes = engine.device_buffer(which)
+            self.tables.append(torch.as_tensor(_DevAlias(ptr, nbytes), device=device)[:rows * ld].view(rows, ld))
+        self.stream = torch.cuda.ExternalStream(engine.stream_ptr(), device=device)
+
+    def iteration(self, reg, alpha=10.0, want_loss=True):
+        """WRMF.py:34-83 over all ranks: users, exchange, tracks, exchange.  Returns the loss summed over the ranks."""
+        r = self.rank
+        loss = self.eng.wrmf_sweep_rows(0, self.user_bounds[r], self.user_bounds[r + 1], reg, alpha, want_loss=want_loss)
+        with self.torch.cuda.stream(self.stream):
+            exchange_rows(self.tables[0], self.user_bounds, self.dist)
+        self.eng.sync()
+        self.eng.wrmf_sweep_rows(1, self.track_bounds[r], self.track_bounds[r + 1], reg, alpha)
+        with self.torch.cuda.stream(self.stream):
+            exchange_rows(self.tables[1], self.track_bounds, self.dist)
+            if want_loss:
+                lt = self.torch.tensor([loss], dtype=self.torch.float64, device=self.tables[0].device)
+                self.dist.all_reduce(lt)
+                loss = float(lt.item())
+        self.eng.sync()
+        return loss if want_loss else None
