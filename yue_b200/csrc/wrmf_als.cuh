@@ -42,6 +42,7 @@ struct WrmfSide {
     const int32_t* cnt;         // plays per entry (r_ui)
     int64_t row_begin, rows;    // this call solves rows [row_begin, rows)
     int chunk_off;              // first chunk of the heavy rows in that range
+    int light_max;              // rows with 1..light_max entries are solved by wrmf_light_kernel (0: none)
     int ld, k;
     double reg, alpha;
     const double* G;            // Gram matrix of `other`, thread layout [TD*TD][kWrmfThreads]
@@ -303,17 +304,19 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
     WrmfPre<TD> pre;
     if (row < sd.rows) {
         e0 = sd.indptr[row]; e1 = sd.indptr[row + 1];
-        if (e1 - e0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
+        if (e1 - e0 > sd.light_max && e1 - e0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
     }
     for (; row < sd.rows; ) {
         __syncthreads();                                  // smem of the previous row is free
         const int64_t nrow = row + gridDim.x;
         int64_t ne0 = 0, ne1 = 0;
         if (nrow < sd.rows) { ne0 = sd.indptr[nrow]; ne1 = sd.indptr[nrow + 1]; }
-        if (e1 == e0) {                                   // nobody played it / played nothing: b = 0 -> the row is 0
-            for (int c = tid; c < ld; c += kWrmfThreads) sd.out[row * ld + c] = 0.f;
+        if (e1 - e0 <= sd.light_max) {                    // a light row (wrmf_light_kernel's), or an empty one:
+            if (e1 == e0)                                 // nobody played it / played nothing: b = 0 -> the row is 0
+                for (int c = tid; c < ld; c += kWrmfThreads) sd.out[row * ld + c] = 0.f;
             row = nrow; e0 = ne0; e1 = ne1;
-            if (row < sd.rows && e1 - e0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
+            if (row < sd.rows && e1 - e0 > sd.light_max && e1 - e0 <= kWrmfChunk)
+                wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
             continue;
         }
         if (LOSS) for (int c = tid; c < KP; c += kWrmfThreads) xs[c] = c < k ? (double)sd.out[row * ld + c] : 0.0;
@@ -339,7 +342,8 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
                 }
             }
         }
-        if (nrow < sd.rows && ne1 - ne0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, ne0, ne1);
+        if (nrow < sd.rows && ne1 - ne0 > sd.light_max && ne1 - ne0 <= kWrmfChunk)
+            wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, ne0, ne1);
         // ---- LDL^T, one column per step; the rhs rides along as row KP of the matrix.  The pivot's reciprocal is
         //      computed once, by the thread that owns the pivot, and published with the column (slot KP + 1).
         //      (A variant that works by block columns of TD unknowns -- two barriers per TD columns, TD^3 FMAs per
@@ -428,15 +432,202 @@ constexpr size_t wrmf_accum_smem() {
     return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP);
 }
 
+// ---- light rows: 1..32 entries, k <= 64 ---------------------------------------------------------------------------
+// Most rows of a play log are short (config C2: 77 % of the users have at most 32 tracks).  For them the k x k
+// factorisation above is the wrong shape of work: ~64 dependent steps with a block-wide barrier each, for a matrix that
+// is a rank-d update (d = entries of the row) of one matrix every row shares, B = G + reg I.  With Y_u the d rows of
+// the other table, C = diag(alpha r) and p = 1 + alpha r (Woodbury):
+//     x = (B + Y_u^T C Y_u)^-1 Y_u^T p = B^-1 Y_u^T t,    (C^-1 + Y_u B^-1 Y_u^T) t = C^-1 p
+// i.e. a d x d system instead of a k x k one, and B^-1 is computed once per sweep (wrmf_binv_kernel).  One WARP per
+// row, no block-wide barrier: lane e owns entry e --
+//   Z_e = y_e B^-1 in chunks of 16 columns (B^-1 rows broadcast from shared memory, y_e from the warp's staging
+//   area), M_ef = Z_e . y_f accumulated per chunk in registers, S = M + C^-1 eliminated across the lanes with
+//   shuffles (row e of S lives in lane e), back substitution with shuffles, q = Y_u^T t and x = B^-1 q with lane j
+//   owning columns j and j + 32.
+// All float64, deterministic (no atomics except the loss), the same row gives the same bits in any launch shape.
+constexpr int kWrmfLightMax = 32;        // entries of a light row at most
+constexpr int kWrmfLightWarps = 8;       // warps (rows in flight) per CTA
+
+// B^-1 by in-place Gauss-Jordan (B is symmetric positive definite: no pivoting), one CTA.  G in thread layout.
+template <int TD>
+__global__ void __launch_bounds__(256) wrmf_binv_kernel(const double* __restrict__ G, int k, double reg, double* __restrict__ Binv) {
+    constexpr int KP = 16 * TD;
+    extern __shared__ __align__(16) double wrmf_smem[];
+    double* A = wrmf_smem;                 // [KP][KP + 1]
+    double* colp = A + KP * (KP + 1);      // [KP]
+    double* rowp = colp + KP;              // [KP]
+    const int tid = threadIdx.x;
+    if (tid < kWrmfBlocks) {
+        int ty, tx;
+        wrmf_block_of_thread(tid, ty, tx);
+#pragma unroll
+        for (int i = 0; i < TD; ++i)
+#pragma unroll
+            for (int j = 0; j < TD; ++j) {
+                const int r = ty * TD + i, c = tx * TD + j;
+                double g = (r < k && c < k) ? G[(i * TD + j) * kWrmfThreads + tid] : 0.0;
+                if (r == c) g = r < k ? g + reg : 1.0;
+                A[r * (KP + 1) + c] = g;
+                A[c * (KP + 1) + r] = g;
+            }
+    }
+    for (int p = 0; p < KP; ++p) {
+        __syncthreads();
+        if (tid < KP) { colp[tid] = A[tid * (KP + 1) + p]; rowp[tid] = A[p * (KP + 1) + tid]; }
+        __syncthreads();
+        const double inv = 1.0 / colp[p];
+        for (int e = tid; e < KP * KP; e += 256) {
+            const int r = e / KP, c = e % KP;
+            double* a = A + r * (KP + 1) + c;
+            if (r == p) *a = (c == p) ? inv : rowp[c] * inv;
+            else if (c == p) *a = -colp[r] * inv;
+            else *a = fma(-colp[r] * inv, rowp[c], *a);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < KP * KP; e += 256) Binv[e] = A[(e / KP) * (KP + 1) + e % KP];
+}
+
+template <int KP>
+constexpr size_t wrmf_light_smem() {
+    return sizeof(double) * (size_t)(KP * KP + kWrmfLightWarps * (kWrmfLightMax * (KP + 1) + 2 * KP));
+}
+
+template <int KP, bool LOSS>
+__global__ void __launch_bounds__(kWrmfLightWarps * 32) wrmf_light_kernel(WrmfSide sd, const double* __restrict__ Binv) {
+    constexpr int NCH = KP / 16;                         // chunks of 16 columns
+    constexpr int YS = KP + 1;                           // staging stride: a lane reads its own row without bank conflicts
+    extern __shared__ __align__(16) double wrmf_smem[];
+    double* Bs = wrmf_smem;                              // [KP][KP]  B^-1
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Ys = Bs + KP * KP + warp * (kWrmfLightMax * YS + 2 * KP);   // [32][KP + 1]  rows of the other table, float64
+    double* qs = Ys + kWrmfLightMax * YS;                // [KP]  q = Y_u^T t
+    double* xo = qs + KP;                                // [KP]  the row's solution before the update (loss)
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) Bs[e] = Binv[e];
+    __syncthreads();
+    const unsigned full = 0xffffffffu;
+    const int k = sd.k, ld = sd.ld;
+    double loss = 0.0;
+    const int64_t nw = (int64_t)gridDim.x * kWrmfLightWarps;
+    for (int64_t row = sd.row_begin + (int64_t)blockIdx.x * kWrmfLightWarps + warp; row < sd.rows; row += nw) {
+        const int64_t e0 = sd.indptr[row];
+        const int d = (int)(sd.indptr[row + 1] - e0);
+        if (d < 1 || d > kWrmfLightMax) continue;        // empty and long rows belong to wrmf_solve_kernel
+        __syncwarp();
+        // ---- stage the d rows (float32 -> float64) and the weights ----
+        int32_t my_idx = 0;
+        double cw = 1.0;                                 // alpha r_ui of entry `lane`
+        if (lane < d) { my_idx = sd.idx[e0 + lane]; cw = sd.alpha * (double)sd.cnt[e0 + lane]; }
+        for (int e = 0; e < d; ++e) {
+            const int64_t orow = __shfl_sync(full, my_idx, e);
+            for (int c = lane; c < KP; c += 32) Ys[e * YS + c] = c < ld ? (double)__ldg(sd.other + orow * ld + c) : 0.0;
+        }
+        if (LOSS) for (int c = lane; c < KP; c += 32) xo[c] = c < k ? (double)sd.out[row * ld + c] : 0.0;
+        __syncwarp();
+        // ---- M_ef = y_e B^-1 y_f, row e in lane e ----
+        double m[kWrmfLightMax];
+#pragma unroll
+        for (int f = 0; f < kWrmfLightMax; ++f) m[f] = 0.0;
+        const double* yme = Ys + (lane < d ? lane : 0) * YS;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            double z[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = 0.0;
+#pragma unroll 2
+            for (int c = 0; c < KP; ++c) {
+                const double yc = yme[c];
+                const double* b = Bs + c * KP + ch * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const double2 bv = *reinterpret_cast<const double2*>(b + j);
+                    z[j] = fma(yc, bv.x, z[j]);
+                    z[j + 1] = fma(yc, bv.y, z[j + 1]);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < kWrmfLightMax; ++f) {
+                if (f < d) {
+                    const double* yf = Ys + f * YS + ch * 16;
+                    double s = m[f];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) s = fma(z[j], yf[j], s);
+                    m[f] = s;
+                }
+            }
+        }
+        // ---- S = M + C^-1, rhs C^-1 p; elimination across the lanes (row e in lane e), no pivoting: S is SPD ----
+        double r = (1.0 + cw) / cw;
+#pragma unroll
+        for (int f = 0; f < kWrmfLightMax; ++f) if (f == lane) m[f] += 1.0 / cw;
+#pragma unroll
+        for (int j = 0; j < kWrmfLightMax; ++j) {
+            if (j < d) {
+                const double inv = wrmf_rcp(__shfl_sync(full, m[j], j));
+                const double lj = m[j] * inv;            // multiplier of this lane's row
+                const double rj = __shfl_sync(full, r, j);
+                const bool below = lane > j;
+                if (below) r = fma(-lj, rj, r);
+#pragma unroll
+                for (int f = j + 1; f < kWrmfLightMax; ++f) {
+                    if (f < d) {
+                        const double sjf = __shfl_sync(full, m[f], j);
+                        if (below) m[f] = fma(-lj, sjf, m[f]);
+                    }
+                }
+            }
+        }
+        double t = 0.0;
+#pragma unroll
+        for (int j = kWrmfLightMax - 1; j >= 0; --j) {
+            if (j < d) {
+                const double tj = __shfl_sync(full, r * wrmf_rcp(m[j]), j);
+                if (lane == j) t = tj;
+                if (lane < j) r = fma(-m[j], tj, r);
+            }
+        }
+        // ---- q = Y_u^T t (lane j: columns j, j + 32), x = B^-1 q ----
+        double q[2] = {0.0, 0.0};
+        for (int e = 0; e < d; ++e) {
+            const double te = __shfl_sync(full, t, e);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) q[h] = fma(te, Ys[e * YS + lane + 32 * h], q[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) qs[lane + 32 * h] = q[h];
+        __syncwarp();
+        double x[2] = {0.0, 0.0};
+        for (int c = 0; c < KP; ++c) {
+            const double qc = qs[c];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) x[h] = fma(qc, Bs[c * KP + lane + 32 * h], x[h]);
+        }
+        if (LOSS && lane < d) {                          // (1 - x_old . y_e)^2, WRMF.py:49-50
+            double p = 0.0;
+            for (int c = 0; c < KP; ++c) p = fma(xo[c], yme[c], p);
+            const double err = 1.0 - p;
+            loss = fma(err, err, loss);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) if (lane + 32 * h < k) sd.out[row * ld + lane + 32 * h] = (float)x[h];
+    }
+    if (LOSS) {
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) loss += __shfl_xor_sync(full, loss, s);
+        if (lane == 0 && loss != 0.0) atomicAdd(sd.loss, loss);
+    }
+}
+
 // ---- pair counts and the track-major form of the play sets (WRMF.py:28-33, data/record.py:160-163) ----
 __global__ void wrmf_count_kernel(const int64_t* __restrict__ ev_indptr, const int32_t* __restrict__ ev_items,
                                   const int64_t* __restrict__ uq_indptr, const int32_t* __restrict__ uq_items, int64_t m, int64_t T,
-                                  int32_t* __restrict__ cnt) {
+                                  const int32_t* __restrict__ hot_items, int32_t* __restrict__ cnt) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t lo = 0, hi = m;                           // last u with ev_indptr[u] <= e
         while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (ev_indptr[mid] <= e) lo = mid; else hi = mid; }
         const int64_t u = lo;
-        const int32_t it = ev_items[e];
+        int32_t it = ev_items[e];
+        if (it < 0) it = hot_items[-it - 1];              // hot positives are stored re-labelled -slot-1 (mark_hot_kernel)
         int64_t a = uq_indptr[u], b = uq_indptr[u + 1];
         while (a < b) { const int64_t mid = (a + b) >> 1; if (uq_items[mid] < it) a = mid + 1; else b = mid; }
         atomicAdd(cnt + a, 1);

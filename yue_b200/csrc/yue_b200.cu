@@ -202,7 +202,12 @@ struct yue_handle {
         int n_heavy = 0, n_chunks = 0;
         std::vector<int32_t> h_chunk_row;       // host copy: which chunks belong to a row range
     } wrmf_plan[2];
-    DevBuf<double> wrmf_G, wrmf_part, wrmf_partA, wrmf_partb;
+    DevBuf<double> wrmf_G, wrmf_part, wrmf_partA, wrmf_partb, wrmf_Binv;
+    // YUE_WRMF_LIGHT=1 sends rows with 1..32 entries through the d x d Woodbury kernel (wrmf_light_kernel).  Correct (tests
+    // run both paths) but measured slower than the k x k factorisation at config C2 (83 vs 64 ms per user sweep): 22 K SASS
+    // instructions of unrolled shuffle elimination (31 % of the stall samples are instruction fetch), 8 warps per SM.  Off
+    // by default until that is fixed (profiles/ncu_wrmf_r1.md).
+    int wrmf_light = 0;
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -369,6 +374,7 @@ int yue_create(int device, yue_t** out) {
     if (const char* s = getenv("YUE_SGD_HOT_DIV")) h->hot_div = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_HOT_SHARD_DIV")) h->hot_shard_div = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_GROUP_SEGS")) h->item_group_segs = std::max(1, atoi(s));
+    if (const char* s = getenv("YUE_WRMF_LIGHT")) h->wrmf_light = atoi(s) != 0;
     if (const char* s = getenv("YUE_SGD_KERNEL")) h->sgd_kernel = atoi(s) == 1 ? 1 : 2;
     if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
     if (const char* s = getenv("YUE_SGD_MAX_ITEMS")) h->max_items_per_user = std::max(1, atoi(s));
@@ -395,7 +401,7 @@ int yue_destroy(yue_t* h) {
     h->scal.release();
     h->l2buf.release();
     h->uq_cnt.release(); h->it_users.release(); h->it_cnt.release(); h->it_indptr.release();
-    for (auto* b : {&h->wrmf_G, &h->wrmf_part, &h->wrmf_partA, &h->wrmf_partb}) b->release();
+    for (auto* b : {&h->wrmf_G, &h->wrmf_part, &h->wrmf_partA, &h->wrmf_partb, &h->wrmf_Binv}) b->release();
     for (auto& pl : h->wrmf_plan) { pl.heavy_rows.release(); pl.heavy_first.release(); pl.chunk_row.release(); pl.chunk_begin.release(); pl.chunk_end.release(); }
     h->test_indptr.release(); h->test_items.release(); h->met_terms.release(); h->met_sums.release(); h->met_seen.release(); h->met_distinct.release();
     cudaEventDestroy(h->ev0);
@@ -1262,7 +1268,7 @@ static int wrmf_prepare(yue_t* h) {
     struct Free { std::function<void()> f; ~Free() { f(); } } guard{[&] { k0.release(); k1.release(); tmp.buf.release(); }};
     CK(k0.resize(nz)); CK(k1.resize(nz));
     if (T && m) {
-        wrmf_count_kernel<<<grid, 256, 0, st>>>(h->ev_indptr.p, h->ev_items.p, h->uq_indptr.p, h->uq_items.p, m, T, h->uq_cnt.p);
+        wrmf_count_kernel<<<grid, 256, 0, st>>>(h->ev_indptr.p, h->ev_items.p, h->uq_indptr.p, h->uq_items.p, m, T, h->hot_items.p, h->uq_cnt.p);
         ++h->launches;
     }
     if (nnz) {
@@ -1323,6 +1329,25 @@ static int wrmf_sweep_impl(yue_t* h, int side, int64_t row_begin, int64_t row_en
         h->launches += 2;
     } else {
         CK(cudaMemsetAsync(h->wrmf_G.p, 0, elems * sizeof(double), st));
+    }
+    // rows with 1..32 entries: one warp per row on the d x d Woodbury system (k <= 64, positive weights)
+    const bool light = h->wrmf_light && TD <= 4 && alpha > 0.0 && other_rows > 0;
+    sd.light_max = light ? kWrmfLightMax : 0;
+    if (light) {
+        constexpr int KPL = TD <= 4 ? KP : 64;              // (the kernel is not instantiated for k > 64)
+        CK(h->wrmf_Binv.resize((size_t)KP * KP));
+        const size_t sm_binv = sizeof(double) * (size_t)(KP * (KP + 1) + 2 * KP), sm_light = wrmf_light_smem<KPL>();
+        CK(cudaFuncSetAttribute(wrmf_binv_kernel<(TD <= 4 ? TD : 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_binv));
+        CK(cudaFuncSetAttribute(wrmf_light_kernel<KPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_light));
+        CK(cudaFuncSetAttribute(wrmf_light_kernel<KPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_light));
+        wrmf_binv_kernel<(TD <= 4 ? TD : 4)><<<1, 256, sm_binv, st>>>(h->wrmf_G.p, h->k, reg, h->wrmf_Binv.p);
+        int lp = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lp, wrmf_light_kernel<KPL, false>, kWrmfLightWarps * 32, sm_light));
+        const int64_t want = (row_end - row_begin + kWrmfLightWarps - 1) / kWrmfLightWarps;
+        const int lgrid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)h->sm_count * std::max(lp, 1)));
+        if (want_loss) wrmf_light_kernel<KPL, true><<<lgrid, kWrmfLightWarps * 32, sm_light, st>>>(sd, h->wrmf_Binv.p);
+        else wrmf_light_kernel<KPL, false><<<lgrid, kWrmfLightWarps * 32, sm_light, st>>>(sd, h->wrmf_Binv.p);
+        h->launches += 2;
     }
     const int c0 = (int)(std::lower_bound(pl.h_chunk_row.begin(), pl.h_chunk_row.end(), (int32_t)row_begin) - pl.h_chunk_row.begin());
     const int c1 = (int)(std::lower_bound(pl.h_chunk_row.begin(), pl.h_chunk_row.end(), (int32_t)std::min<int64_t>(row_end, INT32_MAX)) - pl.h_chunk_row.begin());
