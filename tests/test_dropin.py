@@ -216,3 +216,97 @@ def test_cv_folds_and_progress_hook(tmp_path):
         if k == 300:
             break
     assert got == Measure.rankingMeasure(sample, rec, [10], itemcount)
+
+
+def test_wrmf_class_host_logic_reproduces_the_reference_class(golden_dir, tmp_path):
+    """yue_b200.wrmf.WRMF on the log of the golden run, the same seeded init stream, with the oracle standing in for the
+    CUDA sweeps (CPU box): X = P*10 / Y = Q*10, exactly num.max.iter iterations, reg.lambda -u on both sweeps, the loss of
+    the user sweep -- the tables equal the output of the REFERENCE's own WRMF class (tests/golden/wrmf_small.npz) bit for
+    bit, and predict() its scores."""
+    from oracle import wrmf_ref
+    from yue_b200.wrmf import WRMF
+    g, train, test = golden_split(golden_dir)
+    w = np.load(os.path.join(golden_dir, "wrmf_small.npz"))
+    vals = conf_values(tmp_path, extra={"recommender": "WRMF", "num.factors": "20", "num.max.iter": "2",
+                                        "reg.lambda": "-u 1 -i 0.1 -b 0.2 -s 0.2"})
+
+    class OracleSweeps:
+        def __init__(self, model):
+            self.m = model
+            ev_indptr, ev_items, self.up, self.ui = model.data.interaction_arrays(model.recType)
+            self.cnt = wrmf_ref.pair_counts(ev_indptr, ev_items, self.up, self.ui)
+            self.tp, self.tu, self.tc = wrmf_ref.transpose(model.m, model.n, self.up, self.ui, self.cnt)
+            self.calls = []
+
+        def wrmf_sweep(self, side, reg, alpha=10.0, want_loss=False):
+            self.calls.append((side, reg, alpha))
+            if side == 0:
+                return wrmf_ref.half_sweep(self.m.X, self.m.Y, self.up, self.ui, self.cnt, reg, "f32", want_loss, alpha)
+            return wrmf_ref.half_sweep(self.m.Y, self.m.X, self.tp, self.tu, self.tc, reg, "f32", want_loss, alpha)
+
+        def predict(self, u):
+            return self.m.Y.dot(self.m.X[u])
+
+    with redirect_stdout(io.StringIO()):
+        model = WRMF(Config(values=vals), train, test)
+        model.readConfiguration()
+        np.random.seed(4321)
+        model.initModel()
+        assert np.array_equal(model.X, w["X0"]) and np.array_equal(model.Y, w["Y0"])
+        oe = OracleSweeps(model)
+        model._push_factors = lambda: oe
+        model._pull_factors = lambda: None
+        model.buildModel()
+    assert oe.calls == [(0, 1.0, 10.0), (1, 1.0, 10.0)] * 2
+    assert np.array_equal(model.X, w["X"][-1]) and np.array_equal(model.Y, w["Y"][-1])
+    assert model.loss == pytest.approx(float(w["loss"][-1]), rel=1e-7)
+    id2u = {v: k for k, v in model.data.name2id["user"].items()}
+    for u, s in zip(w["score_users"][:5], w["scores"][:5]):
+        assert np.allclose(model.predict(id2u[int(u)]), s, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_wrmf_dropin_shim_on_top_of_the_reference_tree(golden_dir, tmp_path):
+    """dropin/recommender/cf/WRMF.py shadows the reference's module, derives from the REFERENCE's own
+    base.IterativeRecommender, and with the oracle in place of the CUDA sweeps reproduces the tables of the reference's
+    WRMF class (the golden run) bit for bit."""
+    import subprocess
+    code = r'''
+import io, json, os, sys
+import numpy as np
+from contextlib import redirect_stdout
+sys.path[:0] = [%(dropin)r, %(ref)r, %(root)r]
+from tool.config import Config
+from recommender.cf.WRMF import WRMF
+import base.IterativeRecommender as ref_base
+import recommender.cf.WRMF as mod
+assert mod.__file__.startswith(%(dropin)r) and WRMF.__mro__[3] is ref_base.IterativeRecommender, WRMF.__mro__
+from oracle import wrmf_ref
+from yue_b200.host.record import interaction_arrays
+g = json.load(open(%(gold)r + "/record_small.json"))
+train = [e for e, h in zip(g["events"], g["held"]) if not h]
+test = [e for e, h in zip(g["events"], g["held"]) if h]
+open(%(tmp)r + "/c.conf", "w").write("\n".join(k + "=" + v for k, v in %(conf)r.items()))
+w = np.load(%(gold)r + "/wrmf_small.npz")
+with redirect_stdout(io.StringIO()):
+    m = WRMF(Config(%(tmp)r + "/c.conf"), train, test)
+    m.readConfiguration()
+    np.random.seed(4321)
+    m.initModel()
+    ev_indptr, ev_items, up, ui = interaction_arrays(m.data.name2id, m.data.userRecord, m.recType)
+    cnt = wrmf_ref.pair_counts(ev_indptr, ev_items, up, ui)
+    tp, tu, tc = wrmf_ref.transpose(m.m, m.n, up, ui, cnt)
+    class E:
+        def wrmf_sweep(self, side, reg, alpha=10.0, want_loss=False):
+            if side == 0: return wrmf_ref.half_sweep(m.X, m.Y, up, ui, cnt, reg, "f32", want_loss, alpha)
+            return wrmf_ref.half_sweep(m.Y, m.X, tp, tu, tc, reg, "f32", want_loss, alpha)
+    m._push_factors = lambda: E()
+    m._pull_factors = lambda: None
+    m.buildModel()
+assert np.array_equal(m.X, w["X"][-1]) and np.array_equal(m.Y, w["Y"][-1])
+print("OK")
+''' % dict(dropin=os.path.join(ROOT, "dropin"), ref=REF, root=ROOT, gold=golden_dir, tmp=str(tmp_path),
+           conf=conf_values(tmp_path, extra={"recommender": "WRMF", "num.factors": "20", "num.max.iter": "2",
+                                             "reg.lambda": "-u 1 -i 0.1 -b 0.2 -s 0.2"}))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
