@@ -235,3 +235,63 @@ def test_light_rows_woodbury_path_agrees_with_the_direct_factorisation(monkeypat
     for flag in ("1", "0"):
         assert row_rel(res[flag][0], Xo) < 1e-5 and row_rel(res[flag][1], Yo) < 1e-5
         assert res[flag][2] == pytest.approx(lo, rel=1e-6)
+
+
+def test_edge_cases(engine):
+    """Empty log, tiny k (padded leading dimension), alpha = 0, empty row range, and the refusals."""
+    from yue_b200.engine import Engine, YueError
+    from yue_b200 import _lib
+    # a log without events: every row is 0 (b = 0), loss 0
+    m, n = 7, 5
+    z = np.zeros(m + 1, np.int64)
+    engine.set_interactions(m, n, z, np.zeros(0, np.int32), z, np.zeros(0, np.int32))
+    X0, Y0 = synth.init_factors(m, n, 3, seed=1)
+    engine.set_factors(X0, Y0)
+    assert engine.wrmf_sweep(0, 0.5, 10.0, want_loss=True) == 0.0
+    engine.wrmf_sweep(1, 0.5, 10.0)
+    X, Y = engine.get_factors()
+    assert not X.any() and not Y.any()
+    # k = 1 and k = 3 (ld = 4), alpha = 0 (x = (G + reg I)^-1 sum of the played rows), repeat plays
+    log = synth.power_law_log(40, 30, 600, seed=2)
+    cnt = wrmf_ref.pair_counts(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    itp, itu, itc = wrmf_ref.transpose(log.m, log.n, log.uq_indptr, log.uq_items, cnt)
+    for k, alpha in ((1, 10.0), (3, 10.0), (3, 0.0), (17, 2.5)):
+        X0, Y0 = synth.init_factors(log.m, log.n, k, seed=k)
+        X0, Y0 = X0 * 10, Y0 * 10
+        engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+        engine.set_factors(X0, Y0)
+        loss = engine.wrmf_sweep(0, 0.25, alpha, want_loss=True)
+        engine.wrmf_sweep_rows(1, 3, 3, 0.25, alpha)                 # empty range: nothing happens
+        Xh, Yh = engine.get_factors()
+        assert np.array_equal(Yh, Y0)
+        engine.wrmf_sweep(1, 0.25, alpha)
+        X, Y = engine.get_factors()
+        Xo, Yo = X0.copy(), Y0.copy()
+        lo = wrmf_ref.half_sweep(Xo, Yo, log.uq_indptr, log.uq_items, cnt, 0.25, "f64", True, alpha)
+        wrmf_ref.half_sweep(Yo, Xo, itp, itu, itc, 0.25, "f64", False, alpha)
+        assert row_rel(X, Xo) < 1e-5 and row_rel(Y, Yo) < 1e-5, (k, alpha)
+        assert loss == pytest.approx(lo, rel=1e-6)
+    # refusals
+    with pytest.raises(YueError) as ei:
+        engine.wrmf_sweep(2, 1.0)
+    assert ei.value.code == _lib.E_ARG
+    with pytest.raises(YueError) as ei:
+        engine.wrmf_sweep_rows(0, 5, log.m + 1, 1.0)
+    assert ei.value.code == _lib.E_ARG
+    with pytest.raises(YueError) as ei:
+        engine.wrmf_sweep(0, -1.0)
+    assert ei.value.code == _lib.E_ARG
+    X0, Y0 = synth.init_factors(log.m, log.n, 130, seed=1)
+    engine.set_factors(X0, Y0)
+    with pytest.raises(YueError) as ei:
+        engine.wrmf_sweep(0, 1.0)
+    assert ei.value.code == _lib.E_UNSUPPORTED
+    e2 = Engine(0)                                                   # a user shard cannot run the track sweep
+    try:
+        e2.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, user_begin=10, event_base=100)
+        e2.set_factors(*synth.init_factors(log.m, log.n, 8, seed=1))
+        with pytest.raises(YueError) as ei:
+            e2.wrmf_sweep(0, 1.0)
+        assert ei.value.code == _lib.E_UNSUPPORTED
+    finally:
+        e2.close()
