@@ -29,8 +29,16 @@
 
 namespace yue {
 
-constexpr int kWrmfThreads = 160;        // 5 warps; threads 0..135 own a block of A
-constexpr int kWrmfBlocks = 136;         // 16 * 17 / 2 lower-triangular blocks
+// Shape of the tiling: A (k padded to KP = TD * GB) is a GB x GB grid of TD x TD blocks, of which the NB = GB (GB + 1) / 2
+// lower-triangular ones exist, one per thread.  <TD, 16>: 136 blocks on 160 threads (k <= 16 TD); <8, 8>: 36 blocks on 64
+// threads for k <= 64 -- fewer, fatter threads: 64 FMAs per thread and column step instead of 16, a barrier between 2 warps
+// instead of 5, half the shared-memory traffic per step.
+template <int TD, int GB>
+struct WrmfShape {
+    static constexpr int KP = TD * GB;
+    static constexpr int NB = GB * (GB + 1) / 2;
+    static constexpr int NT = (NB + 31) / 32 * 32;
+};
 constexpr int kWrmfBatch = 16;           // rows of the other table staged per step
 constexpr int kWrmfChunk = 4096;         // entries one CTA accumulates for a row at most
 
@@ -78,9 +86,10 @@ __device__ __forceinline__ double wrmf_rcp(double d) {
 // (rows 1..15), ...  A warp then shares (almost) one block column: its reads of the column's entries are broadcasts,
 // its reads of the row entries are contiguous, and once the factorisation has passed a warp's columns the whole warp
 // skips the update -- the shared-memory wavefronts and the float64 issue slots of a step shrink with the trailing matrix.
+template <int GB>
 __device__ __forceinline__ void wrmf_block_of_thread(int t, int& ty, int& tx) {
     int c = 0, start = 0;
-    while (start + (16 - c) <= t) { start += 16 - c; ++c; }
+    while (start + (GB - c) <= t) { start += GB - c; ++c; }
     tx = c; ty = c + (t - start);
 }
 
@@ -99,23 +108,23 @@ __device__ __forceinline__ void wrmf_lds(const double* p, double (&v)[TD]) {
 }
 
 // One staged batch in flight: kWrmfBatch rows of the other table (this thread's float4 slots) and one weight.
-template <int TD>
+template <int TD, int GB>
 struct WrmfPre {
-    static constexpr int Q4 = 16 * TD / 4;                       // float4 per staged row
-    static constexpr int NLOAD = (kWrmfBatch * Q4 + kWrmfThreads - 1) / kWrmfThreads;
+    static constexpr int Q4 = TD * GB / 4;                       // float4 per staged row
+    static constexpr int NLOAD = (kWrmfBatch * Q4 + WrmfShape<TD, GB>::NT - 1) / WrmfShape<TD, GB>::NT;
     float4 v[NLOAD];
     double w;
 };
 
 // issue the loads of entries [eb, min(eb + kWrmfBatch, e1)): rows idx[e] of `other` (rows e themselves when idx ==
 // nullptr) and their weights alpha * cnt[e] (1 when cnt == nullptr)
-template <int TD>
-__device__ __forceinline__ void wrmf_fetch(WrmfPre<TD>& pre, const float* __restrict__ other, int ld, const int32_t* __restrict__ idx,
+template <int TD, int GB>
+__device__ __forceinline__ void wrmf_fetch(WrmfPre<TD, GB>& pre, const float* __restrict__ other, int ld, const int32_t* __restrict__ idx,
                                            const int32_t* __restrict__ cnt, double alpha, int64_t eb, int64_t e1) {
-    constexpr int Q4 = WrmfPre<TD>::Q4;
+    constexpr int Q4 = WrmfPre<TD, GB>::Q4, kWrmfThreads = WrmfShape<TD, GB>::NT;
     const int tid = threadIdx.x;
 #pragma unroll
-    for (int q = 0; q < WrmfPre<TD>::NLOAD; ++q) {
+    for (int q = 0; q < WrmfPre<TD, GB>::NLOAD; ++q) {
         const int s = tid + q * kWrmfThreads;
         const int r = s / Q4, c4 = s % Q4;
         pre.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -131,17 +140,17 @@ __device__ __forceinline__ void wrmf_fetch(WrmfPre<TD>& pre, const float* __rest
 // acc += sum_e w_e y_e y_e^T, bb += sum_e (1 + w_e) y_e over entries [e0, e1) (bb only when cnt != nullptr).  `pre` holds
 // the first batch already (wrmf_fetch(pre, ..., e0, e1) issued by the caller, possibly long ago).  ys: smem
 // [kWrmfBatch][KP] doubles, ws: smem [kWrmfBatch], xs: smem [KP] (the row's current solution, LOSS only).
-template <int TD, bool LOSS>
-__device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, WrmfPre<TD>& pre, const float* __restrict__ other, int ld,
+template <int TD, int GB, bool LOSS>
+__device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, WrmfPre<TD, GB>& pre, const float* __restrict__ other, int ld,
                                                 const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int64_t e0,
                                                 int64_t e1, double alpha, double* ys, double* ws, const double* xs, double& loss,
                                                 int ty, int tx, bool active) {
-    constexpr int KP = 16 * TD;
-    constexpr int Q4 = WrmfPre<TD>::Q4;
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT, kWrmfBlocks = WrmfShape<TD, GB>::NB;
+    constexpr int Q4 = WrmfPre<TD, GB>::Q4;
     const int tid = threadIdx.x;
     for (int64_t eb = e0; eb < e1; eb += kWrmfBatch) {
 #pragma unroll
-        for (int q = 0; q < WrmfPre<TD>::NLOAD; ++q) {
+        for (int q = 0; q < WrmfPre<TD, GB>::NLOAD; ++q) {
             const int s = tid + q * kWrmfThreads;
             const int r = s / Q4, c4 = s % Q4;
             if (r < kWrmfBatch) {
@@ -152,7 +161,7 @@ __device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, WrmfPre<TD>& p
         }
         if (tid < kWrmfBatch) ws[tid] = pre.w;
         __syncthreads();
-        if (eb + kWrmfBatch < e1) wrmf_fetch<TD>(pre, other, ld, idx, cnt, alpha, eb + kWrmfBatch, e1);   // in flight under the FMAs
+        if (eb + kWrmfBatch < e1) wrmf_fetch<TD, GB>(pre, other, ld, idx, cnt, alpha, eb + kWrmfBatch, e1);   // in flight under the FMAs
         const int nb = (int)((e1 - eb) < (int64_t)kWrmfBatch ? (e1 - eb) : (int64_t)kWrmfBatch);
         if (active) {
             for (int e = 0; e < nb; ++e) {
@@ -188,17 +197,17 @@ __device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, WrmfPre<TD>& p
 }
 
 // G partial of rows [row0, row1) of F (unit weights), thread layout
-template <int TD>
-__global__ void __launch_bounds__(kWrmfThreads) wrmf_gram_kernel(const float* __restrict__ F, int64_t n, int ld, int k,
+template <int TD, int GB>
+__global__ void __launch_bounds__(WrmfShape<TD, GB>::NT) wrmf_gram_kernel(const float* __restrict__ F, int64_t n, int ld, int k,
                                                                  double* __restrict__ partial) {
-    constexpr int KP = 16 * TD;
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT, kWrmfBlocks = WrmfShape<TD, GB>::NB;
     extern __shared__ __align__(16) double wrmf_smem[];
     double* ys = wrmf_smem;
     double* ws = ys + kWrmfBatch * KP;
     const int tid = threadIdx.x;
     int ty = 0, tx = 0;
     bool active = tid < kWrmfBlocks;
-    if (active) wrmf_block_of_thread(tid, ty, tx);
+    if (active) wrmf_block_of_thread<GB>(tid, ty, tx);
     active = active && ty < (k + TD - 1) / TD;           // blocks of padded unknowns only: nothing to do
     WrmfTile<TD> tl;
 #pragma unroll
@@ -207,9 +216,9 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_gram_kernel(const float* __
         for (int j = 0; j < TD; ++j) tl.acc[i][j] = 0.0; }
     const int64_t r0 = n * (int64_t)blockIdx.x / gridDim.x, r1 = n * (int64_t)(blockIdx.x + 1) / gridDim.x;
     double dummy = 0.0;
-    WrmfPre<TD> pre;
-    wrmf_fetch<TD>(pre, F, ld, nullptr, nullptr, 1.0, r0, r1);
-    wrmf_accumulate<TD, false>(tl, pre, F, ld, nullptr, nullptr, r0, r1, 1.0, ys, ws, nullptr, dummy, ty, tx, active);
+    WrmfPre<TD, GB> pre;
+    wrmf_fetch<TD, GB>(pre, F, ld, nullptr, nullptr, 1.0, r0, r1);
+    wrmf_accumulate<TD, GB, false>(tl, pre, F, ld, nullptr, nullptr, r0, r1, 1.0, ys, ws, nullptr, dummy, ty, tx, active);
     double* out = partial + (size_t)blockIdx.x * TD * TD * kWrmfThreads;
 #pragma unroll
     for (int i = 0; i < TD; ++i)
@@ -226,9 +235,9 @@ __global__ void wrmf_gram_reduce_kernel(const double* __restrict__ partial, int 
     G[e] = s;
 }
 
-template <int TD, bool LOSS>
-__global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
-    constexpr int KP = 16 * TD;
+template <int TD, int GB, bool LOSS>
+__global__ void __launch_bounds__(WrmfShape<TD, GB>::NT) wrmf_chunk_kernel(WrmfSide sd) {
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT, kWrmfBlocks = WrmfShape<TD, GB>::NB;
     extern __shared__ __align__(16) double wrmf_smem[];
     double* ys = wrmf_smem;
     double* ws = ys + kWrmfBatch * KP;
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
     const int tid = threadIdx.x;
     int ty = 0, tx = 0;
     bool active = tid < kWrmfBlocks;
-    if (active) wrmf_block_of_thread(tid, ty, tx);
+    if (active) wrmf_block_of_thread<GB>(tid, ty, tx);
     active = active && ty < (sd.k + TD - 1) / TD;
     const int ch = blockIdx.x + sd.chunk_off;
     const int64_t row = sd.chunk_row[ch];
@@ -248,9 +257,9 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
         for (int j = 0; j < TD; ++j) tl.acc[i][j] = 0.0; }
     double loss = 0.0;
     const int64_t c0 = sd.chunk_begin[ch], c1 = sd.chunk_end[ch];
-    WrmfPre<TD> pre;
-    wrmf_fetch<TD>(pre, sd.other, sd.ld, sd.idx, sd.cnt, sd.alpha, c0, c1);
-    wrmf_accumulate<TD, LOSS>(tl, pre, sd.other, sd.ld, sd.idx, sd.cnt, c0, c1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
+    WrmfPre<TD, GB> pre;
+    wrmf_fetch<TD, GB>(pre, sd.other, sd.ld, sd.idx, sd.cnt, sd.alpha, c0, c1);
+    wrmf_accumulate<TD, GB, LOSS>(tl, pre, sd.other, sd.ld, sd.idx, sd.cnt, c0, c1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
     double* pa = sd.partA + (size_t)ch * TD * TD * kWrmfThreads;
 #pragma unroll
     for (int i = 0; i < TD; ++i)
@@ -267,9 +276,9 @@ __global__ void __launch_bounds__(kWrmfThreads) wrmf_chunk_kernel(WrmfSide sd) {
     }
 }
 
-template <int TD, bool LOSS>
-__global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_kernel(WrmfSide sd) {
-    constexpr int KP = 16 * TD;
+template <int TD, int GB, bool LOSS>
+__global__ void __launch_bounds__(WrmfShape<TD, GB>::NT, (TD * GB <= 64 ? 4 : 1)) wrmf_solve_kernel(WrmfSide sd) {
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT, kWrmfBlocks = WrmfShape<TD, GB>::NB;
     extern __shared__ __align__(16) double wrmf_smem[];
     double* ys = wrmf_smem;                              // [kWrmfBatch][KP]
     double* ws = ys + kWrmfBatch * KP;                   // [kWrmfBatch]
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
     const int k = sd.k, ld = sd.ld;
     const int nblk = (k + TD - 1) / TD;                  // block rows / columns that hold real unknowns
     bool active = tid < kWrmfBlocks;
-    if (active) wrmf_block_of_thread(tid, ty, tx);
+    if (active) wrmf_block_of_thread<GB>(tid, ty, tx);
     active = active && ty < nblk;                        // blocks of padded unknowns only: nothing to do
     const bool diag = active && ty == tx;
 #pragma unroll
@@ -301,10 +310,10 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
     // flight into registers, so a row starts with its data on chip.
     int64_t row = sd.row_begin + blockIdx.x;
     int64_t e0 = 0, e1 = 0;
-    WrmfPre<TD> pre;
+    WrmfPre<TD, GB> pre;
     if (row < sd.rows) {
         e0 = sd.indptr[row]; e1 = sd.indptr[row + 1];
-        if (e1 - e0 > sd.light_max && e1 - e0 <= kWrmfChunk) wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
+        if (e1 - e0 > sd.light_max && e1 - e0 <= kWrmfChunk) wrmf_fetch<TD, GB>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
     }
     for (; row < sd.rows; ) {
         __syncthreads();                                  // smem of the previous row is free
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
                 for (int c = tid; c < ld; c += kWrmfThreads) sd.out[row * ld + c] = 0.f;
             row = nrow; e0 = ne0; e1 = ne1;
             if (row < sd.rows && e1 - e0 > sd.light_max && e1 - e0 <= kWrmfChunk)
-                wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
+                wrmf_fetch<TD, GB>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, e0, e1);
             continue;
         }
         if (LOSS) for (int c = tid; c < KP; c += kWrmfThreads) xs[c] = c < k ? (double)sd.out[row * ld + c] : 0.0;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
 #pragma unroll
             for (int j = 0; j < TD; ++j) tl.acc[i][j] = gs[(i * TD + j) * kWrmfThreads + tid]; }
         if (e1 - e0 <= kWrmfChunk) {
-            wrmf_accumulate<TD, LOSS>(tl, pre, sd.other, ld, sd.idx, sd.cnt, e0, e1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
+            wrmf_accumulate<TD, GB, LOSS>(tl, pre, sd.other, ld, sd.idx, sd.cnt, e0, e1, sd.alpha, ys, ws, xs, loss, ty, tx, active);
         } else {                                          // chunk partials, in chunk order
             int lo = 0, hi = sd.n_heavy;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (sd.heavy_rows[mid] < row) lo = mid + 1; else hi = mid; }
@@ -343,7 +352,7 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
             }
         }
         if (nrow < sd.rows && ne1 - ne0 > sd.light_max && ne1 - ne0 <= kWrmfChunk)
-            wrmf_fetch<TD>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, ne0, ne1);
+            wrmf_fetch<TD, GB>(pre, sd.other, ld, sd.idx, sd.cnt, sd.alpha, ne0, ne1);
         // ---- LDL^T, one column per step; the rhs rides along as row KP of the matrix.  The pivot's reciprocal is
         //      computed once, by the thread that owns the pivot, and published with the column (slot KP + 1).
         //      (A variant that works by block columns of TD unknowns -- two barriers per TD columns, TD^3 FMAs per
@@ -421,14 +430,14 @@ __global__ void __launch_bounds__(kWrmfThreads, (TD <= 4 ? 4 : 1)) wrmf_solve_ke
     }
 }
 
-template <int TD>
+template <int TD, int GB>
 constexpr size_t wrmf_solve_smem() {
-    constexpr int KP = 16 * TD;
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT;
     return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP + 2 * (KP + 2) + 3 * KP + TD * TD * kWrmfThreads);
 }
-template <int TD>
+template <int TD, int GB>
 constexpr size_t wrmf_accum_smem() {
-    constexpr int KP = 16 * TD;
+    constexpr int KP = TD * GB;
     return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP);
 }
 
@@ -449,9 +458,9 @@ constexpr int kWrmfLightMax = 32;        // entries of a light row at most
 constexpr int kWrmfLightWarps = 8;       // warps (rows in flight) per CTA
 
 // B^-1 by in-place Gauss-Jordan (B is symmetric positive definite: no pivoting), one CTA.  G in thread layout.
-template <int TD>
+template <int TD, int GB>
 __global__ void __launch_bounds__(256) wrmf_binv_kernel(const double* __restrict__ G, int k, double reg, double* __restrict__ Binv) {
-    constexpr int KP = 16 * TD;
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT, kWrmfBlocks = WrmfShape<TD, GB>::NB;
     extern __shared__ __align__(16) double wrmf_smem[];
     double* A = wrmf_smem;                 // [KP][KP + 1]
     double* colp = A + KP * (KP + 1);      // [KP]
@@ -459,7 +468,7 @@ __global__ void __launch_bounds__(256) wrmf_binv_kernel(const double* __restrict
     const int tid = threadIdx.x;
     if (tid < kWrmfBlocks) {
         int ty, tx;
-        wrmf_block_of_thread(tid, ty, tx);
+        wrmf_block_of_thread<GB>(tid, ty, tx);
 #pragma unroll
         for (int i = 0; i < TD; ++i)
 #pragma unroll

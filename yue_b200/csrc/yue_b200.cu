@@ -208,6 +208,9 @@ struct yue_handle {
     // instructions of unrolled shuffle elimination (31 % of the stall samples are instruction fetch), 8 warps per SM.  Off
     // by default until that is fixed (profiles/ncu_wrmf_r1.md).
     int wrmf_light = 0;
+    // 32 < k <= 64: 16 x 16 grid of 4 x 4 blocks on 160 threads (0, default) or 8 x 8 grid of 8 x 8 blocks on 64 threads
+    // (YUE_WRMF_FAT=1; measured slower at config C2: 76 / 34 ms per user / track sweep against 64 / 27)
+    int wrmf_fat = 0;
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -375,6 +378,7 @@ int yue_create(int device, yue_t** out) {
     if (const char* s = getenv("YUE_SGD_HOT_SHARD_DIV")) h->hot_shard_div = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_SGD_GROUP_SEGS")) h->item_group_segs = std::max(1, atoi(s));
     if (const char* s = getenv("YUE_WRMF_LIGHT")) h->wrmf_light = atoi(s) != 0;
+    if (const char* s = getenv("YUE_WRMF_FAT")) h->wrmf_fat = atoi(s) != 0;
     if (const char* s = getenv("YUE_SGD_KERNEL")) h->sgd_kernel = atoi(s) == 1 ? 1 : 2;
     if (const char* s = getenv("YUE_SGD_ITEM_SEGS")) h->item_segs_env = std::max(0, atoi(s));   // 0 = automatic
     if (const char* s = getenv("YUE_SGD_MAX_ITEMS")) h->max_items_per_user = std::max(1, atoi(s));
@@ -1294,9 +1298,9 @@ static int wrmf_prepare(yue_t* h) {
     return YUE_OK;
 }
 
-template <int TD>
+template <int TD, int GB>
 static int wrmf_sweep_impl(yue_t* h, int side, int64_t row_begin, int64_t row_end, double reg, double alpha, double* loss_out) {
-    constexpr int KP = 16 * TD;
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT;
     constexpr size_t elems = (size_t)TD * TD * kWrmfThreads;
     cudaStream_t st = h->stream;
     const int64_t rows = side == 0 ? h->m : h->n, other_rows = side == 0 ? h->n : h->m;
@@ -1306,12 +1310,12 @@ static int wrmf_sweep_impl(yue_t* h, int side, int64_t row_begin, int64_t row_en
     const int n_part = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 4, other_rows / 64));
     CK(h->wrmf_part.resize((size_t)n_part * elems)); CK(h->wrmf_G.resize(elems));
     CK(h->wrmf_partA.resize((size_t)pl.n_chunks * elems)); CK(h->wrmf_partb.resize((size_t)pl.n_chunks * KP));
-    const size_t sm_acc = wrmf_accum_smem<TD>(), sm_solve = wrmf_solve_smem<TD>();
-    CK(cudaFuncSetAttribute(wrmf_gram_kernel<TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
-    CK(cudaFuncSetAttribute(wrmf_chunk_kernel<TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
-    CK(cudaFuncSetAttribute(wrmf_chunk_kernel<TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
-    CK(cudaFuncSetAttribute(wrmf_solve_kernel<TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_solve));
-    CK(cudaFuncSetAttribute(wrmf_solve_kernel<TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_solve));
+    const size_t sm_acc = wrmf_accum_smem<TD, GB>(), sm_solve = wrmf_solve_smem<TD, GB>();
+    CK(cudaFuncSetAttribute(wrmf_gram_kernel<TD, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
+    CK(cudaFuncSetAttribute(wrmf_chunk_kernel<TD, GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
+    CK(cudaFuncSetAttribute(wrmf_chunk_kernel<TD, GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_acc));
+    CK(cudaFuncSetAttribute(wrmf_solve_kernel<TD, GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_solve));
+    CK(cudaFuncSetAttribute(wrmf_solve_kernel<TD, GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_solve));
     WrmfSide sd{};
     sd.out = side == 0 ? h->P.p : h->Q.p;
     sd.other = side == 0 ? h->Q.p : h->P.p;
@@ -1324,23 +1328,23 @@ static int wrmf_sweep_impl(yue_t* h, int side, int64_t row_begin, int64_t row_en
     sd.partA = h->wrmf_partA.p; sd.partb = h->wrmf_partb.p; sd.loss = h->scal.p;
     CK(cudaMemsetAsync(h->scal.p, 0, sizeof(double), st));
     if (other_rows) {
-        wrmf_gram_kernel<TD><<<n_part, kWrmfThreads, sm_acc, st>>>(sd.other, other_rows, h->ld, h->k, h->wrmf_part.p);
+        wrmf_gram_kernel<TD, GB><<<n_part, kWrmfThreads, sm_acc, st>>>(sd.other, other_rows, h->ld, h->k, h->wrmf_part.p);
         wrmf_gram_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(h->wrmf_part.p, n_part, (int)elems, h->wrmf_G.p);
         h->launches += 2;
     } else {
         CK(cudaMemsetAsync(h->wrmf_G.p, 0, elems * sizeof(double), st));
     }
     // rows with 1..32 entries: one warp per row on the d x d Woodbury system (k <= 64, positive weights)
-    const bool light = h->wrmf_light && TD <= 4 && alpha > 0.0 && other_rows > 0;
+    const bool light = h->wrmf_light && KP <= 64 && alpha > 0.0 && other_rows > 0;
     sd.light_max = light ? kWrmfLightMax : 0;
     if (light) {
-        constexpr int KPL = TD <= 4 ? KP : 64;              // (the kernel is not instantiated for k > 64)
+        constexpr int KPL = KP <= 64 ? KP : 64;             // (the kernel is not instantiated for k > 64)
         CK(h->wrmf_Binv.resize((size_t)KP * KP));
         const size_t sm_binv = sizeof(double) * (size_t)(KP * (KP + 1) + 2 * KP), sm_light = wrmf_light_smem<KPL>();
-        CK(cudaFuncSetAttribute(wrmf_binv_kernel<(TD <= 4 ? TD : 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_binv));
+        CK(cudaFuncSetAttribute(wrmf_binv_kernel<TD, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_binv));
         CK(cudaFuncSetAttribute(wrmf_light_kernel<KPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_light));
         CK(cudaFuncSetAttribute(wrmf_light_kernel<KPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_light));
-        wrmf_binv_kernel<(TD <= 4 ? TD : 4)><<<1, 256, sm_binv, st>>>(h->wrmf_G.p, h->k, reg, h->wrmf_Binv.p);
+        wrmf_binv_kernel<TD, GB><<<1, 256, sm_binv, st>>>(h->wrmf_G.p, h->k, reg, h->wrmf_Binv.p);
         int lp = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lp, wrmf_light_kernel<KPL, false>, kWrmfLightWarps * 32, sm_light));
         const int64_t want = (row_end - row_begin + kWrmfLightWarps - 1) / kWrmfLightWarps;
@@ -1353,16 +1357,16 @@ static int wrmf_sweep_impl(yue_t* h, int side, int64_t row_begin, int64_t row_en
     const int c1 = (int)(std::lower_bound(pl.h_chunk_row.begin(), pl.h_chunk_row.end(), (int32_t)std::min<int64_t>(row_end, INT32_MAX)) - pl.h_chunk_row.begin());
     sd.chunk_off = c0;
     if (c1 > c0) {
-        if (want_loss) wrmf_chunk_kernel<TD, true><<<c1 - c0, kWrmfThreads, sm_acc, st>>>(sd);
-        else wrmf_chunk_kernel<TD, false><<<c1 - c0, kWrmfThreads, sm_acc, st>>>(sd);
+        if (want_loss) wrmf_chunk_kernel<TD, GB, true><<<c1 - c0, kWrmfThreads, sm_acc, st>>>(sd);
+        else wrmf_chunk_kernel<TD, GB, false><<<c1 - c0, kWrmfThreads, sm_acc, st>>>(sd);
         ++h->launches;
     }
     int per_sm = 1;
-    if (want_loss) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, true>, kWrmfThreads, sm_solve));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, false>, kWrmfThreads, sm_solve));
+    if (want_loss) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, GB, true>, kWrmfThreads, sm_solve));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wrmf_solve_kernel<TD, GB, false>, kWrmfThreads, sm_solve));
     const int grid = (int)std::min<int64_t>(row_end - row_begin, (int64_t)h->sm_count * std::max(per_sm, 1));
-    if (want_loss) wrmf_solve_kernel<TD, true><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
-    else wrmf_solve_kernel<TD, false><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
+    if (want_loss) wrmf_solve_kernel<TD, GB, true><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
+    else wrmf_solve_kernel<TD, GB, false><<<grid, kWrmfThreads, sm_solve, st>>>(sd);
     ++h->launches;
     CK(cudaGetLastError());
     if (side == 1) { h->tc.q_dirty = true; h->ilv_current = false; }
@@ -1385,10 +1389,11 @@ int yue_wrmf_sweep_rows(yue_t* h, int side, int64_t row_begin, int64_t row_end, 
     CK(cudaSetDevice(h->device));
     if (int rc = q_rowmajor(h)) return rc;
     if (int rc = wrmf_prepare(h)) return rc;
-    if (h->k <= 16) return wrmf_sweep_impl<1>(h, side, row_begin, row_end, reg, alpha, loss_out);
-    if (h->k <= 32) return wrmf_sweep_impl<2>(h, side, row_begin, row_end, reg, alpha, loss_out);
-    if (h->k <= 64) return wrmf_sweep_impl<4>(h, side, row_begin, row_end, reg, alpha, loss_out);
-    return wrmf_sweep_impl<8>(h, side, row_begin, row_end, reg, alpha, loss_out);
+    if (h->k <= 16) return wrmf_sweep_impl<1, 16>(h, side, row_begin, row_end, reg, alpha, loss_out);
+    if (h->k <= 32) return wrmf_sweep_impl<2, 16>(h, side, row_begin, row_end, reg, alpha, loss_out);
+    if (h->k <= 64) return h->wrmf_fat ? wrmf_sweep_impl<8, 8>(h, side, row_begin, row_end, reg, alpha, loss_out)
+                                       : wrmf_sweep_impl<4, 16>(h, side, row_begin, row_end, reg, alpha, loss_out);
+    return wrmf_sweep_impl<8, 16>(h, side, row_begin, row_end, reg, alpha, loss_out);
 }
 
 int yue_wrmf_sweep(yue_t* h, int side, double reg, double alpha, double* loss_out) {
