@@ -441,21 +441,22 @@ constexpr size_t wrmf_accum_smem() {
     return sizeof(double) * (size_t)(kWrmfBatch * KP + kWrmfBatch + KP);
 }
 
-// ---- light rows: 1..32 entries, k <= 64 ---------------------------------------------------------------------------
-// Most rows of a play log are short (config C2: 77 % of the users have at most 32 tracks).  For them the k x k
-// factorisation above is the wrong shape of work: ~64 dependent steps with a block-wide barrier each, for a matrix that
-// is a rank-d update (d = entries of the row) of one matrix every row shares, B = G + reg I.  With Y_u the d rows of
-// the other table, C = diag(alpha r) and p = 1 + alpha r (Woodbury):
+// ---- light rows: 1..16 entries, k <= 64 ---------------------------------------------------------------------------
+// Half the rows of a play log are short (config C2: 48 % of the users have at most 16 tracks, 78 % at most 32).  For them
+// the k x k factorisation above is the wrong shape of work: ~64 dependent steps with a block-wide barrier each, for a
+// matrix that is a rank-d update (d = entries of the row) of one matrix every row shares, B = G + reg I.  With Y_u the d
+// rows of the other table, C = diag(alpha r) and p = 1 + alpha r (Woodbury):
 //     x = (B + Y_u^T C Y_u)^-1 Y_u^T p = B^-1 Y_u^T t,    (C^-1 + Y_u B^-1 Y_u^T) t = C^-1 p
 // i.e. a d x d system instead of a k x k one, and B^-1 is computed once per sweep (wrmf_binv_kernel).  One WARP per
-// row, no block-wide barrier: lane e owns entry e --
-//   Z_e = y_e B^-1 in chunks of 16 columns (B^-1 rows broadcast from shared memory, y_e from the warp's staging
-//   area), M_ef = Z_e . y_f accumulated per chunk in registers, S = M + C^-1 eliminated across the lanes with
-//   shuffles (row e of S lives in lane e), back substitution with shuffles, q = Y_u^T t and x = B^-1 q with lane j
-//   owning columns j and j + 32.
-// All float64, deterministic (no atomics except the loss), the same row gives the same bits in any launch shape.
-constexpr int kWrmfLightMax = 32;        // entries of a light row at most
-constexpr int kWrmfLightWarps = 8;       // warps (rows in flight) per CTA
+// row, no block-wide barrier, everything a row needs in ~13 KB of shared memory (14 rows in flight per SM):
+//   Z = Y_u B^-1 in chunks of 16 columns: lane (h, c) owns column c of the chunk for the entries e = 2i + h -- all 32
+//       lanes busy whatever d is, B^-1 read once per chunk, the y values as half-warp broadcasts;
+//   M += Z_chunk Y_u,chunk^T: lane (e, h) owns row e, columns 8h .. 8h+7 of M, Z_chunk passed through shared memory;
+//   S = M + C^-1 eliminated in shared memory (run-time loops: small code), back substitution, q = Y_u^T t and
+//       x = B^-1 q with lane j owning columns j and j + 32.
+// All float64, no atomics except the loss: a row gives the same bits in any launch shape.
+constexpr int kWrmfLightMax = 16;        // entries of a light row at most
+constexpr int kWrmfLightWarps = 14;      // warps (rows in flight) per CTA, one CTA per SM
 
 // B^-1 by in-place Gauss-Jordan (B is symmetric positive definite: no pivoting), one CTA.  G in thread layout.
 template <int TD, int GB>
@@ -498,30 +499,36 @@ __global__ void __launch_bounds__(256) wrmf_binv_kernel(const double* __restrict
 }
 
 template <int KP>
+__host__ __device__ constexpr int wrmf_light_warp_doubles() { return kWrmfLightMax * KP + 2 * kWrmfLightMax * 17 + kWrmfLightMax + 2 * KP; }
+template <int KP>
 constexpr size_t wrmf_light_smem() {
-    return sizeof(double) * (size_t)(KP * KP + kWrmfLightWarps * (kWrmfLightMax * (KP + 1) + 2 * KP));
+    return sizeof(double) * (size_t)(KP * KP + kWrmfLightWarps * wrmf_light_warp_doubles<KP>());
 }
 
 template <int KP, bool LOSS>
 __global__ void __launch_bounds__(kWrmfLightWarps * 32) wrmf_light_kernel(WrmfSide sd, const double* __restrict__ Binv) {
     constexpr int NCH = KP / 16;                         // chunks of 16 columns
-    constexpr int YS = KP + 1;                           // staging stride: a lane reads its own row without bank conflicts
+    constexpr int DM = kWrmfLightMax;
     extern __shared__ __align__(16) double wrmf_smem[];
     double* Bs = wrmf_smem;                              // [KP][KP]  B^-1
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* Ys = Bs + KP * KP + warp * (kWrmfLightMax * YS + 2 * KP);   // [32][KP + 1]  rows of the other table, float64
-    double* qs = Ys + kWrmfLightMax * YS;                // [KP]  q = Y_u^T t
-    double* xo = qs + KP;                                // [KP]  the row's solution before the update (loss)
+    double* Ys = Bs + KP * KP + warp * wrmf_light_warp_doubles<KP>();   // [16][KP]  rows of the other table, float64
+    double* Zc = Ys + DM * KP;                           // [16][17]  one chunk of Z
+    double* Ss = Zc + DM * 17;                           // [16][17]  S, eliminated in place
+    double* rs = Ss + DM * 17;                           // [16]      rhs, then t
+    double* qs = rs + DM;                                // [KP]      q = Y_u^T t
+    double* xo = qs + KP;                                // [KP]      the row's solution before the update (loss)
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) Bs[e] = Binv[e];
     __syncthreads();
     const unsigned full = 0xffffffffu;
     const int k = sd.k, ld = sd.ld;
+    const int hh = lane >> 4, lc = lane & 15;            // (half, column) in the Z phase; (column half, row) in the M phase
     double loss = 0.0;
     const int64_t nw = (int64_t)gridDim.x * kWrmfLightWarps;
     for (int64_t row = sd.row_begin + (int64_t)blockIdx.x * kWrmfLightWarps + warp; row < sd.rows; row += nw) {
         const int64_t e0 = sd.indptr[row];
         const int d = (int)(sd.indptr[row + 1] - e0);
-        if (d < 1 || d > kWrmfLightMax) continue;        // empty and long rows belong to wrmf_solve_kernel
+        if (d < 1 || d > DM) continue;                   // empty and longer rows belong to wrmf_solve_kernel
         __syncwarp();
         // ---- stage the d rows (float32 -> float64) and the weights ----
         int32_t my_idx = 0;
@@ -529,78 +536,77 @@ __global__ void __launch_bounds__(kWrmfLightWarps * 32) wrmf_light_kernel(WrmfSi
         if (lane < d) { my_idx = sd.idx[e0 + lane]; cw = sd.alpha * (double)sd.cnt[e0 + lane]; }
         for (int e = 0; e < d; ++e) {
             const int64_t orow = __shfl_sync(full, my_idx, e);
-            for (int c = lane; c < KP; c += 32) Ys[e * YS + c] = c < ld ? (double)__ldg(sd.other + orow * ld + c) : 0.0;
+            for (int c = lane; c < KP; c += 32) Ys[e * KP + c] = c < ld ? (double)__ldg(sd.other + orow * ld + c) : 0.0;
         }
         if (LOSS) for (int c = lane; c < KP; c += 32) xo[c] = c < k ? (double)sd.out[row * ld + c] : 0.0;
+        if (lane < DM) rs[lane] = (1.0 + cw) / cw;
         __syncwarp();
-        // ---- M_ef = y_e B^-1 y_f, row e in lane e ----
-        double m[kWrmfLightMax];
+        // ---- M = Y_u B^-1 Y_u^T, 16 columns of Z at a time ----
+        double m[8];
 #pragma unroll
-        for (int f = 0; f < kWrmfLightMax; ++f) m[f] = 0.0;
-        const double* yme = Ys + (lane < d ? lane : 0) * YS;
+        for (int f = 0; f < 8; ++f) m[f] = 0.0;
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
-            double z[16];
+            double z[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = 0.0;
+            for (int i = 0; i < 8; ++i) z[i] = 0.0;
+            const double* bcol = Bs + ch * 16 + lc;
 #pragma unroll 2
-            for (int c = 0; c < KP; ++c) {
-                const double yc = yme[c];
-                const double* b = Bs + c * KP + ch * 16;
+            for (int c = 0; c < KP; c += 2) {
+                const double b0 = bcol[c * KP], b1 = bcol[(c + 1) * KP];
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const double2 bv = *reinterpret_cast<const double2*>(b + j);
-                    z[j] = fma(yc, bv.x, z[j]);
-                    z[j + 1] = fma(yc, bv.y, z[j + 1]);
-                }
-            }
-#pragma unroll
-            for (int f = 0; f < kWrmfLightMax; ++f) {
-                if (f < d) {
-                    const double* yf = Ys + f * YS + ch * 16;
-                    double s = m[f];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) s = fma(z[j], yf[j], s);
-                    m[f] = s;
-                }
-            }
-        }
-        // ---- S = M + C^-1, rhs C^-1 p; elimination across the lanes (row e in lane e), no pivoting: S is SPD ----
-        double r = (1.0 + cw) / cw;
-#pragma unroll
-        for (int f = 0; f < kWrmfLightMax; ++f) if (f == lane) m[f] += 1.0 / cw;
-#pragma unroll
-        for (int j = 0; j < kWrmfLightMax; ++j) {
-            if (j < d) {
-                const double inv = wrmf_rcp(__shfl_sync(full, m[j], j));
-                const double lj = m[j] * inv;            // multiplier of this lane's row
-                const double rj = __shfl_sync(full, r, j);
-                const bool below = lane > j;
-                if (below) r = fma(-lj, rj, r);
-#pragma unroll
-                for (int f = j + 1; f < kWrmfLightMax; ++f) {
-                    if (f < d) {
-                        const double sjf = __shfl_sync(full, m[f], j);
-                        if (below) m[f] = fma(-lj, sjf, m[f]);
+                for (int i = 0; i < 8; ++i) {
+                    if (2 * i + hh < d) {
+                        const double2 y = *reinterpret_cast<const double2*>(Ys + (2 * i + hh) * KP + c);
+                        z[i] = fma(y.x, b0, fma(y.y, b1, z[i]));
                     }
                 }
             }
-        }
-        double t = 0.0;
 #pragma unroll
-        for (int j = kWrmfLightMax - 1; j >= 0; --j) {
-            if (j < d) {
-                const double tj = __shfl_sync(full, r * wrmf_rcp(m[j]), j);
-                if (lane == j) t = tj;
-                if (lane < j) r = fma(-m[j], tj, r);
+            for (int i = 0; i < 8; ++i) Zc[(2 * i + hh) * 17 + lc] = z[i];
+            __syncwarp();
+            // lane (row lc, column half hh): m[ff] += sum_j Z[lc][j] Y[8 hh + ff][16 ch + j]
+            if (lc < d) {
+                for (int j = 0; j < 16; ++j) {
+                    const double zj = Zc[lc * 17 + j];
+#pragma unroll
+                    for (int ff = 0; ff < 8; ++ff)
+                        if (8 * hh + ff < d) m[ff] = fma(zj, Ys[(8 * hh + ff) * KP + ch * 16 + j], m[ff]);
+                }
             }
+            __syncwarp();
+        }
+        // ---- S = M + C^-1 in shared memory ----
+        {
+            const double cinv = 1.0 / __shfl_sync(full, cw, lc);          // 1 / (alpha r) of row lc
+#pragma unroll
+            for (int ff = 0; ff < 8; ++ff) Ss[lc * 17 + 8 * hh + ff] = m[ff] + ((8 * hh + ff == lc) ? cinv : 0.0);
+        }
+        __syncwarp();
+        // ---- elimination (no pivoting: S is symmetric positive definite); lane (row lc, column half hh) ----
+        for (int j = 0; j < d; ++j) {
+            const double inv = wrmf_rcp(Ss[j * 17 + j]);
+            const double l = Ss[lc * 17 + j] * inv;
+            if (lc > j && lc < d) {
+                const int f0 = hh ? (j + 1 > 8 ? j + 1 : 8) : j + 1, f1 = hh ? d : (d < 8 ? d : 8);
+                for (int f = f0; f < f1; ++f) Ss[lc * 17 + f] = fma(-l, Ss[j * 17 + f], Ss[lc * 17 + f]);
+                if (hh == 0) rs[lc] = fma(-l, rs[j], rs[lc]);
+            }
+            __syncwarp();
+        }
+        for (int j = d - 1; j >= 0; --j) {                // back substitution; rs[j] becomes t_j
+            const double tj = rs[j] * wrmf_rcp(Ss[j * 17 + j]);
+            __syncwarp();
+            if (lane == j) rs[j] = tj;
+            if (hh == 0 && lc < j) rs[lc] = fma(-Ss[lc * 17 + j], tj, rs[lc]);
+            __syncwarp();
         }
         // ---- q = Y_u^T t (lane j: columns j, j + 32), x = B^-1 q ----
         double q[2] = {0.0, 0.0};
         for (int e = 0; e < d; ++e) {
-            const double te = __shfl_sync(full, t, e);
+            const double te = rs[e];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) q[h] = fma(te, Ys[e * YS + lane + 32 * h], q[h]);
+            for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) q[h] = fma(te, Ys[e * KP + lane + 32 * h], q[h]);
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) qs[lane + 32 * h] = q[h];
@@ -611,20 +617,20 @@ __global__ void __launch_bounds__(kWrmfLightWarps * 32) wrmf_light_kernel(WrmfSi
 #pragma unroll
             for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) x[h] = fma(qc, Bs[c * KP + lane + 32 * h], x[h]);
         }
-        if (LOSS && lane < d) {                          // (1 - x_old . y_e)^2, WRMF.py:49-50
-            double p = 0.0;
-            for (int c = 0; c < KP; ++c) p = fma(xo[c], yme[c], p);
-            const double err = 1.0 - p;
-            loss = fma(err, err, loss);
+        if (LOSS) {                                       // sum over the entries of (1 - x_old . y_e)^2, WRMF.py:49-50
+            for (int e = 0; e < d; ++e) {
+                double p = 0.0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) if (lane + 32 * h < KP) p = fma(xo[lane + 32 * h], Ys[e * KP + lane + 32 * h], p);
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) p += __shfl_xor_sync(full, p, sft);
+                if (lane == 0) { const double err = 1.0 - p; loss = fma(err, err, loss); }
+            }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) if (lane + 32 * h < k) sd.out[row * ld + lane + 32 * h] = (float)x[h];
     }
-    if (LOSS) {
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) loss += __shfl_xor_sync(full, loss, s);
-        if (lane == 0 && loss != 0.0) atomicAdd(sd.loss, loss);
-    }
+    if (LOSS && lane == 0 && loss != 0.0) atomicAdd(sd.loss, loss);
 }
 
 // ---- pair counts and the track-major form of the play sets (WRMF.py:28-33, data/record.py:160-163) ----

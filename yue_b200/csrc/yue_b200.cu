@@ -203,11 +203,10 @@ struct yue_handle {
         std::vector<int32_t> h_chunk_row;       // host copy: which chunks belong to a row range
     } wrmf_plan[2];
     DevBuf<double> wrmf_G, wrmf_part, wrmf_partA, wrmf_partb, wrmf_Binv;
-    // YUE_WRMF_LIGHT=1 sends rows with 1..32 entries through the d x d Woodbury kernel (wrmf_light_kernel).  Correct (tests
-    // run both paths) but measured slower than the k x k factorisation at config C2 (83 vs 64 ms per user sweep): 22 K SASS
-    // instructions of unrolled shuffle elimination (31 % of the stall samples are instruction fetch), 8 warps per SM.  Off
-    // by default until that is fixed (profiles/ncu_wrmf_r1.md).
-    int wrmf_light = 0;
+    // Rows with 1..16 entries go through the d x d Woodbury kernel (wrmf_light_kernel, one warp per row): 2.9x faster per
+    // row than the k x k factorisation at d = 64 (profiles/ncu_wrmf_r1.md).  YUE_WRMF_LIGHT=0 sends every row through the
+    // factorisation (tests compare the two).
+    int wrmf_light = 1;
     // 32 < k <= 64: 16 x 16 grid of 4 x 4 blocks on 160 threads (0, default) or 8 x 8 grid of 8 x 8 blocks on 64 threads
     // (YUE_WRMF_FAT=1; measured slower at config C2: 76 / 34 ms per user / track sweep against 64 / 27)
     int wrmf_fat = 0;
