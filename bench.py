@@ -289,7 +289,7 @@ def run_native(args):
         wrmf = {"metric": "wrmf_iterations_per_sec", "value": 1e3 / (u_ms + t_ms), "ms_user_sweep": u_ms, "ms_track_sweep": t_ms,
                 "unique_pairs": nnz, "pairs_per_sec": 2 * nnz / ((u_ms + t_ms) * 1e-3), "prepare_seconds": prep_s,
                 "fp64_tflops_user_sweep": flops(m) / (u_ms * 1e-3) / 1e12, "fp64_tflops_track_sweep": flops(n) / (t_ms * 1e-3) / 1e12,
-                "dtype": "f64 arithmetic on f32 tables (as the reference)", "kernel": "wrmf_solve_kernel<4> (+ gram, chunk)",
+                "dtype": "f64 arithmetic on f32 tables (as the reference)", "kernel": "wrmf_solve_kernel<4, 16> + wrmf_light_kernel<64> (rows with <= 16 entries) + gram, chunk",
                 "workload": "WRMF d=64, reg 1, alpha 10 on the C2 log (%d users x %d tracks, %d unique pairs)" % (m, n, nnz)}
         if not args.no_cpu:                         # the reference's per-row solve (oracle port of WRMF.py:36-57), one core
             from oracle import wrmf_ref
