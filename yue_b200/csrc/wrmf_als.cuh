@@ -449,8 +449,8 @@ constexpr size_t wrmf_accum_smem() {
 //     x = (B + Y_u^T C Y_u)^-1 Y_u^T p = B^-1 Y_u^T t,    (C^-1 + Y_u B^-1 Y_u^T) t = C^-1 p
 // i.e. a d x d system instead of a k x k one, and B^-1 is computed once per sweep (wrmf_binv_kernel).  One WARP per
 // row, no block-wide barrier, everything a row needs in ~13 KB of shared memory (14 rows in flight per SM):
-//   Z = Y_u B^-1 in chunks of 16 columns: lane (h, c) owns column c of the chunk for the entries e = 2i + h -- all 32
-//       lanes busy whatever d is, B^-1 read once per chunk, the y values as half-warp broadcasts;
+//   Z = Y_u B^-1: lane (h, c) owns columns c, 16 + c, 32 + c, 48 + c for the entries e = 2i + h -- all 32 lanes busy
+//       whatever d is, every value of B^-1 and of Y_u read once per row (the y values as half-warp broadcasts);
 //   M += Z_chunk Y_u,chunk^T: lane (e, h) owns row e, columns 8h .. 8h+7 of M, Z_chunk passed through shared memory;
 //   S = M + C^-1 eliminated in shared memory (run-time loops: small code), back substitution, q = Y_u^T t and
 //       x = B^-1 q with lane j owning columns j and j + 32.
@@ -545,25 +545,29 @@ __global__ void __launch_bounds__(kWrmfLightWarps * 32) wrmf_light_kernel(WrmfSi
         double m[8];
 #pragma unroll
         for (int f = 0; f < 8; ++f) m[f] = 0.0;
+        double z[NCH][8];                                // Z[e = 2i + hh][16 ch + lc]
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[ch][i] = 0.0;
 #pragma unroll 1
-        for (int ch = 0; ch < NCH; ++ch) {
-            double z[8];
+        for (int c = 0; c < KP; c += 2) {                // every y value is read once, every B^-1 value once per row
+            double b0[NCH], b1[NCH];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = 0.0;
-            const double* bcol = Bs + ch * 16 + lc;
-#pragma unroll 2
-            for (int c = 0; c < KP; c += 2) {
-                const double b0 = bcol[c * KP], b1 = bcol[(c + 1) * KP];
+            for (int ch = 0; ch < NCH; ++ch) { b0[ch] = Bs[c * KP + ch * 16 + lc]; b1[ch] = Bs[(c + 1) * KP + ch * 16 + lc]; }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (2 * i + hh < d) {
-                        const double2 y = *reinterpret_cast<const double2*>(Ys + (2 * i + hh) * KP + c);
-                        z[i] = fma(y.x, b0, fma(y.y, b1, z[i]));
-                    }
+            for (int i = 0; i < 8; ++i) {
+                if (2 * i + hh < d) {
+                    const double2 y = *reinterpret_cast<const double2*>(Ys + (2 * i + hh) * KP + c);
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) z[ch][i] = fma(y.x, b0[ch], fma(y.y, b1[ch], z[ch][i]));
                 }
             }
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) Zc[(2 * i + hh) * 17 + lc] = z[i];
+        for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Zc[(2 * i + hh) * 17 + lc] = z[ch][i];
             __syncwarp();
             // lane (row lc, column half hh): m[ff] += sum_j Z[lc][j] Y[8 hh + ff][16 ch + j]
             if (lc < d) {
