@@ -9,9 +9,12 @@
 //   wrmf_chunk_kernel    rows with more than kWrmfChunk entries (the heaviest users, the most played tracks: one
 //                        track of config C2 has ~6e5 listeners) are cut into chunks whose weighted Gram + rhs partials
 //                        go to scratch, so that no single CTA is a straggler;
-//   wrmf_solve_kernel    one CTA per row (rows strided over the grid, the next row's data prefetched): A = G + reg I + sum of the row's rank-1 terms
-//                        (or of its chunk partials), LDL^T in registers, forward substitution carried as an extra
-//                        row of the factorisation, backward substitution by row blocks, X[row] stored as float32.
+//   wrmf_binv_kernel +   rows with 1..16 entries (half the users of config C2): one warp per row on the d x d Woodbury
+//   wrmf_light_kernel    system with B^-1 = (G + reg I)^-1 computed once per sweep (see "light rows" below);
+//   wrmf_solve_kernel    every other row, one CTA per row (rows strided over the grid, the next row's data prefetched):
+//                        A = G + reg I + sum of the row's rank-1 terms (or of its chunk partials), LDL^T in registers,
+//                        forward substitution carried as an extra row of the factorisation, backward substitution by
+//                        row blocks, X[row] stored as float32.
 //
 // Tile layout.  k is padded to KP = 16 TD (TD = 1, 2, 4, 8 for k <= 16, 32, 64, 128).  A is symmetric: only the 136
 // lower-triangular TD x TD blocks of the 16 x 16 block grid exist, one per thread (160 threads, 24 of them only help
@@ -30,9 +33,9 @@
 namespace yue {
 
 // Shape of the tiling: A (k padded to KP = TD * GB) is a GB x GB grid of TD x TD blocks, of which the NB = GB (GB + 1) / 2
-// lower-triangular ones exist, one per thread.  <TD, 16>: 136 blocks on 160 threads (k <= 16 TD); <8, 8>: 36 blocks on 64
-// threads for k <= 64 -- fewer, fatter threads: 64 FMAs per thread and column step instead of 16, a barrier between 2 warps
-// instead of 5, half the shared-memory traffic per step.
+// lower-triangular ones exist, one per thread.  <TD, 16>: 136 blocks on 160 threads (k <= 16 TD), the default; <8, 8>: 36
+// blocks on 64 threads for k <= 64 -- fewer, fatter threads: 64 FMAs per thread and column step instead of 16, a barrier
+// between 2 warps instead of 5, half the shared-memory traffic per step -- measured slower (YUE_WRMF_FAT=1 selects it).
 template <int TD, int GB>
 struct WrmfShape {
     static constexpr int KP = TD * GB;
