@@ -427,6 +427,22 @@ def bench_ranking(eng, args, bf16_peak, rank=0, world=1, dist=None):
     t0 = time.perf_counter()
     sums, distinct = eng.rank_metrics([5, 10])
     out["metrics_seconds"] = time.perf_counter() - t0
+    # the reference's per-user body of evalRanking (predict + mask + the shipped selection, IterativeRecommender.py:93-145)
+    # as restated by the oracle, on one host core, for a few users of the same problem -- reported beside, not a target
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle import topn
+            hp, hu = np.asarray(indptr), np.asarray(uq)
+            nu = 20 if not args.small else 50
+            t0 = time.perf_counter()
+            for u in range(nu):
+                topn.topn_ref_quirk(Q.dot(P[u]), hu[hp[u]:hp[u + 1]], 10)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": nu / dt, "unit": "users/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                                   "sample": "%d users of the same problem: Q.dot(P[u]) + mask + the reference's selection "
+                                             "(oracle port of IterativeRecommender.py:93-145), serial" % nu}
+        except Exception as exc:                      # a reported baseline must not cost the bench line
+            out["cpu_baseline"] = {"error": repr(exc)}
     out["value"] = out["c4_full"]["users_per_sec"]
     out["workload"] = "C4: top-10 of %d users x %d tracks, d=64, ~50 masked tracks/user, %d GPU(s), users sharded by block" % (m_total, n, world)
     return out
