@@ -18,6 +18,10 @@ What it restates (file:line relative to the reference tree):
 * ``evaluation/measure.py:6-101``      hits / precision / recall / F1 / MAP / coverage
 * ``data/record.py:138-202``           id assignment and test-set semantics
 * ``recommender/advanced/APR.py:25-76,95-137``  adversarial BPR losses and gradients
+* ``recommender/cf/WRMF.py:17-88``      implicit-feedback ALS (``wrmf_ref.py``; pinned by the reference CLASS itself,
+                                        ``make_golden_wrmf.py`` -> ``tests/golden/wrmf_small.npz``)
+* ``recommender/advanced/CUNE.py:118-178``  two-level BPR training loop (``cune_ref.py``; pinned by the reference's loop
+                                        text, ``make_golden_cune.py``; the CUDA kernel for it is not built yet)
 
 Parity pinning.  The reference ships no tests, golden vectors or data, and its
 RNG streams (CPython Mersenne Twister, unseeded) cannot be reproduced by a GPU

@@ -156,3 +156,28 @@ def test_wrmf_oracle_reproduces_the_reference_class(golden_dir):
         for a, b in ((X64, X), (Y64, Y)):
             d = np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-12)
             assert d.max() < 1e-5
+
+
+def test_cune_oracle_reproduces_the_reference_loop(golden_dir):
+    """tests/golden/cune_small.npz is the output of the loop text of recommender/advanced/CUNE.py:119-178 itself, exec'd
+    on the reference's own IterativeRecommender with the Philox draws in place of random.choice
+    (oracle/make_golden_cune.py).  The restatement (oracle/cune_ref.py: groundwork for the next model of SURVEY 8f row 4)
+    gives the same float32 tables bit for bit over two iterations, both branches of the loop included, and the draws
+    are reproducible from the seed."""
+    from oracle import cune_ref
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    ev_user = record_ref.ev_users(g["ev_indptr"])
+    n = g["Q0"].shape[0]
+    deg_ip = np.diff(g["ip_indptr"])
+    assert (deg_ip == 0).any() and (deg_ip > 0).any()
+    P, Q = g["P0"].copy(), g["Q0"].copy()
+    for it in range(len(g["loss"])):
+        for nn in range(3):
+            kp = cune_ref.sample_implicit(int(g["seed"]), it, nn, ev_user, g["ip_indptr"])
+            assert np.array_equal(kp, g["kpos"][it][nn]) and (kp[deg_ip[ev_user] > 0] < deg_ip[ev_user][deg_ip[ev_user] > 0]).all()
+            j = philox.sample_negatives(int(g["seed"]), it, ev_user, n, g["uq_indptr"], g["uq_items"], slot=nn)
+            assert np.array_equal(j, g["neg"][it][nn])
+        loss = cune_ref.epoch(P, Q, g["ev_indptr"], g["ev_items"], g["ip_indptr"], g["ip_items"], g["kpos"][it], g["neg"][it],
+                              float(g["lr"]), float(g["regU"]), float(g["regI"]), float(g["s"]))
+        assert np.array_equal(P, g["P"][it]) and np.array_equal(Q, g["Q"][it])
+        assert loss == pytest.approx(float(g["loss"][it]), rel=1e-9)
