@@ -66,8 +66,11 @@ def metrics(P, Q, log, N=10):
     return rec / len(users), ndcg / len(users)
 
 
-def train(log, P, Q, negs, lr, reg, ranks, hot, exchanges, quantum):
-    """ranks == 1: the serial order.  hot: boolean mask of the tracks whose rows are shared."""
+def train(log, P, Q, negs, lr, reg, ranks, hot, exchanges, quantum, merge=0):
+    """ranks == 1: the serial order.  hot: boolean mask of the tracks whose rows are shared -- as ONE copy every rank reads
+    and writes (merge == 0), or as a local copy per rank that is merged with a master copy every `merge` events of the
+    rank: delta = local - base is added to the master, the master becomes the new local copy and base (what a rank's
+    merger warp would do with remote REDs and one remote load of the hot table, without any barrier)."""
     ev_user = np.repeat(np.arange(log.m), np.diff(log.ev_indptr))
     if ranks == 1:
         for neg in negs:
@@ -77,6 +80,8 @@ def train(log, P, Q, negs, lr, reg, ranks, hot, exchanges, quantum):
     order = [np.concatenate([np.arange(log.ev_indptr[u], log.ev_indptr[u + 1]) for u in range(r, log.m, ranks)]) for r in range(ranks)]
     Qr = [Q.copy() for _ in range(ranks)]          # per-rank copies (tail rows); hot rows live in Q itself
     tail = ~hot
+    base = [Q[hot].copy() for _ in range(ranks)]
+    since = [0] * ranks
     for neg in negs:
         snap = Q.copy()
         pos = [0] * ranks
@@ -89,9 +94,28 @@ def train(log, P, Q, negs, lr, reg, ranks, hot, exchanges, quantum):
                     end = min(pos[r] + quantum, bounds[r][x])
                     for e in order[r][pos[r]:end]:
                         i, j = log.ev_items[e], neg[e]
-                        step(P[ev_user[e]], (Q if hot[i] else Qr[r])[i], (Q if hot[j] else Qr[r])[j], lr, reg)
+                        if merge:
+                            step(P[ev_user[e]], Qr[r][i], Qr[r][j], lr, reg)
+                        else:
+                            step(P[ev_user[e]], (Q if hot[i] else Qr[r])[i], (Q if hot[j] else Qr[r])[j], lr, reg)
+                    if merge:
+                        since[r] += end - pos[r]
+                        if since[r] >= merge:
+                            since[r] = 0
+                            Q[hot] += Qr[r][hot] - base[r]
+                            Qr[r][hot] = Q[hot]
+                            base[r] = Q[hot].copy()
                     live = live or end > pos[r]
                     pos[r] = end
+            if merge:                               # bring every rank's hot rows up to date before the tail exchange
+                for r in range(ranks):
+                    Q[hot] += Qr[r][hot] - base[r]
+                    Qr[r][hot] = Q[hot]
+                    base[r] = Q[hot].copy()
+                    since[r] = 0
+                for r in range(ranks):
+                    Qr[r][hot] = Q[hot]
+                    base[r] = Q[hot].copy()
             new = snap + sum(q - snap for q in Qr)  # the all-reduce of the deltas (tail rows; hot rows are not in Qr)
             Q[tail] = new[tail]
             for q in Qr:
@@ -112,6 +136,7 @@ def main():
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--reg", type=float, default=0.01)
     ap.add_argument("--seeds", type=int, default=2)
+    ap.add_argument("--merge", type=str, default="", help="comma list of merge periods (events per rank) for 64 local hot rows")
     args = ap.parse_args()
     log = synth.power_law_log(args.users, args.tracks, args.plays, seed=77)
     ev_user = np.repeat(np.arange(log.m), np.diff(log.ev_indptr))
@@ -121,21 +146,26 @@ def main():
     by_count = np.argsort(-counts)
     print("log: %d users x %d tracks, %d train events; hottest track %.1f %% of the positives; %d rank(s), %d epochs, d=%d"
           % (log.m, log.n, log.train_size, 100.0 * counts.max() / log.train_size, args.ranks, args.epochs, args.d), flush=True)
-    configs = [("serial", 1, 0, 1)]
-    for H in (0, 64, 512):
-        for X in (4, 32):
-            configs.append(("%d ranks, %4d shared hot rows (%4.1f %% of the positives), %2d exchanges/epoch" %
-                            (args.ranks, H, 100.0 * counts[by_count[:H]].sum() / log.train_size, X), args.ranks, H, X))
+    configs = [("serial", 1, 0, 1, 0)]
+    if args.merge:
+        for K in (int(x) for x in args.merge.split(",")):
+            configs.append(("%d ranks, 64 hot rows local, merged with the master copy every %6d events, 8 exchanges/epoch" %
+                            (args.ranks, K), args.ranks, 64, 8, K))
+    else:
+        for H in (0, 64, 512):
+            for X in (4, 32):
+                configs.append(("%d ranks, %4d shared hot rows (%4.1f %% of the positives), %2d exchanges/epoch" %
+                                (args.ranks, H, 100.0 * counts[by_count[:H]].sum() / log.train_size, X), args.ranks, H, X, 0))
     for seed in range(args.seeds):
         rng = np.random.default_rng(1000 + seed)
         negs = [negatives(rng, ev_user, played, log.n) for _ in range(args.epochs)]
         P0, Q0 = synth.init_factors(log.m, log.n, args.d, seed=5)
         base = None
-        for name, ranks, H, X in configs:
+        for name, ranks, H, X, K in configs:
             hot = np.zeros(log.n, dtype=bool)
             hot[by_count[:H]] = True
             t0 = time.time()
-            P, Q = train(log, P0.copy(), Q0.copy(), negs, args.lr, args.reg, ranks, hot, X, args.quantum)
+            P, Q = train(log, P0.copy(), Q0.copy(), negs, args.lr, args.reg, ranks, hot, X, args.quantum, K)
             rec, nd = metrics(P, Q, log)
             if base is None:
                 base = (rec, nd)
