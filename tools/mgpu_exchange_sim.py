@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--reg", type=float, default=0.01)
     ap.add_argument("--seeds", type=int, default=2)
+    ap.add_argument("--hot", type=str, default="0,64,512", help="comma list: how many of the hottest rows are one shared copy")
+    ap.add_argument("--exchanges", type=str, default="4,32", help="comma list: tail exchanges per epoch")
     ap.add_argument("--merge", type=str, default="", help="comma list of merge periods (events per rank) for 64 local hot rows")
     args = ap.parse_args()
     log = synth.power_law_log(args.users, args.tracks, args.plays, seed=77)
@@ -152,8 +154,8 @@ def main():
             configs.append(("%d ranks, 64 hot rows local, merged with the master copy every %6d events, 8 exchanges/epoch" %
                             (args.ranks, K), args.ranks, 64, 8, K))
     else:
-        for H in (0, 64, 512):
-            for X in (4, 32):
+        for H in (int(x) for x in args.hot.split(",")):
+            for X in (int(x) for x in args.exchanges.split(",")):
                 configs.append(("%d ranks, %4d shared hot rows (%4.1f %% of the positives), %2d exchanges/epoch" %
                                 (args.ranks, H, 100.0 * counts[by_count[:H]].sum() / log.train_size, X), args.ranks, H, X, 0))
     for seed in range(args.seeds):
