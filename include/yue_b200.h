@@ -149,6 +149,22 @@ int yue_apr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
                   double lr, double regU, double regI, double eps, double regA, int mode,
                   double* loss_out);
 
+/* CUNE's two-level BPR (recommender/advanced/CUNE.py:118-178).
+ * yue_cune_set_implicit replaces the `implicit positive` sets CUNE.py:95-113 builds: ip_items[ip_indptr[u] ..
+ * ip_indptr[u+1]) are the tracks of user u's top-K similar users that u has NOT played (a played track is refused,
+ * YUE_E_ARG); m+1 / ip_indptr[m] entries, local user indices, copied to the device.  A new log drops them.
+ * yue_cune_epoch replaces one pass of the training loop (CUNE.py:122-174): for every event (u, i), three repeats, each
+ * drawing an implicit positive k (Philox slot 64 + repeat, attempt 0, position (r * len) >> 32 in the user's list) and
+ * an unplayed track j (slot = repeat, rejection as in yue_bpr_epoch), then the ten row statements of CUNE.py:134-159
+ * with every sigmoid re-evaluated on the current rows; users without implicit positives take the plain BPR step of
+ * CUNE.py:164-171.  `s` is CUNE.conf's -s (> 0).  mode YUE_MODE_SERIAL reproduces the reference's order and rounding
+ * (float32 rows, float64 scalars) and adds regU*|P|^2 + regI*|Q|^2 to the loss after EVERY user like CUNE.py:174;
+ * YUE_MODE_HOGWILD runs one warp per user and adds (users with events) x the end-of-epoch norms instead.
+ * *loss_out is the epoch's loss as CUNE.py:161-174 accumulates it; a non-finite loss is YUE_E_NUMERIC. */
+int yue_cune_set_implicit(yue_t* h, const int64_t* ip_indptr, const int32_t* ip_items);
+int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s,
+                   uint64_t seed, uint32_t epoch, int mode, double* loss_out);
+
 /* (P*P).sum(), (Q*Q).sum() of BPR.py:59, accumulated in float64. */
 int yue_frob2(yue_t* h, double* p2, double* q2);
 

@@ -1,0 +1,221 @@
+"""CUNE's two-level BPR: host logic of yue_b200/cune.py on CPU with the oracle standing in for the
+CUDA epoch, and the kernel (csrc/cune_sgd.cuh through yue_cune_epoch) against the golden run of the reference's own loop
+text (tests/golden/cune_small.npz, oracle/make_golden_cune.py)."""
+import io
+import json
+import os
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from oracle import cune_ref, philox, record_ref
+from yue_b200.host.config import Config
+
+
+def _golden_slice(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    keep = set('u%d' % x for x in range(60))                  # the slice make_golden_cune.py trains on
+    train = [e for e, h in zip(g["events"], g["held"]) if not h and e['user'] in keep]
+    test = [e for e, h in zip(g["events"], g["held"]) if h and e['user'] in keep]
+    return train, test
+
+
+def _conf(out_dir):
+    return {"record": "./dataset/log.txt", "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,",
+            "recommender": "CUNE", "evaluation.setup": "-target track -ap 0.2", "item.ranking": "-topN 5,10",
+            "num.factors": "12", "num.max.iter": "2", "CUNE": "-T 20 -L 10 -l 20 -w 5 -k 50 -s 2 -ep 10",
+            "learnRate": "-init 0.02 -max 0.1", "reg.lambda": "-u 0.01 -i 0.01 -b 0.01 -s 0.2",
+            "output.setup": "on -dir %s/" % out_dir, "yue.sgd": "serial", "yue.seed": "20260105"}
+
+
+def test_implicit_positive_lists_follow_the_reference_statement():
+    """CUNE.py:111-113: per similar user, its tracks minus the user's own; contributions concatenated, duplicates kept."""
+    from yue_b200.cune import implicit_positive_lists
+    rng = np.random.default_rng(5)
+    m, n = 30, 40
+    rows = [np.unique(rng.integers(0, n, rng.integers(1, 12))) for _ in range(m)]
+    uq_indptr = np.zeros(m + 1, np.int64)
+    np.cumsum([len(r) for r in rows], out=uq_indptr[1:])
+    uq_items = np.concatenate(rows).astype(np.int32)
+    top = {u: [int(f) for f in rng.choice([x for x in range(m) if x != u], 3, replace=False)] for u in range(m) if u % 4}
+    indptr, items = implicit_positive_lists(m, uq_indptr, uq_items, top)
+    for u in range(m):
+        want = []
+        for f in top.get(u, ()):
+            want += sorted(set(rows[f].tolist()).difference(rows[u].tolist()))
+        assert items[indptr[u]:indptr[u + 1]].tolist() == want
+        assert not set(want) & set(rows[u].tolist())
+    assert indptr[-1] == len(items) and (np.diff(indptr)[::4] == 0).all()
+
+
+def test_cune_class_host_logic_reproduces_the_reference_loop(golden_dir, tmp_path):
+    """yue_b200.cune.CUNE on the log slice of the golden run, the same seeded init, similar users supplied (the embedding
+    stage needs gensim), the oracle standing in for yue_cune_epoch: the implicit-positive lists equal the golden run's and
+    the tables after two iterations equal the output of the REFERENCE's loop text bit for bit."""
+    from yue_b200.cune import CUNE
+    from yue_b200.engine import MODE_SERIAL
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    train, test = _golden_slice(golden_dir)
+
+    class OracleEpochs:
+        def __init__(self, model):
+            self.m = model
+            self.arr = model.data.interaction_arrays(model.recType)
+            self.calls = []
+
+        def get_interactions(self):
+            return self.arr
+
+        def cune_set_implicit(self, ip_indptr, ip_items):
+            self.ip = (np.asarray(ip_indptr), np.asarray(ip_items))
+
+        def cune_epoch(self, lr, regU, regI, s, seed, epoch, mode):
+            self.calls.append((lr, regU, regI, s, seed, epoch, mode))
+            ev_indptr, ev_items, uq_indptr, uq_items = self.arr
+            ev_user = record_ref.ev_users(ev_indptr)
+            kp = [cune_ref.sample_implicit(seed, epoch, nn, ev_user, self.ip[0]) for nn in range(3)]
+            neg = [philox.sample_negatives(seed, epoch, ev_user, self.m.n, uq_indptr, uq_items, slot=nn) for nn in range(3)]
+            return cune_ref.epoch(self.m.P, self.m.Q, ev_indptr, ev_items, self.ip[0], self.ip[1], kp, neg, lr, regU, regI, s)
+
+    with redirect_stdout(io.StringIO()):
+        model = CUNE(Config(values=_conf(tmp_path)), train, test)
+        model.readConfiguration()
+        np.random.seed(99)
+        model.initModel()
+        assert (model.walkCount, model.walkLength, model.walkDim, model.winSize, model.topK, model.s, model.epoch) == \
+            (20, 10, 20, 5, 50, 2.0, 10)
+        assert np.array_equal(model.P, g["P0"]) and np.array_equal(model.Q, g["Q0"])
+        # the similar users of the golden run (make_golden_cune.py): two fixed others, none for every fifth user
+        u2i = model.data.name2id['user']
+        by_id = {v: k for k, v in u2i.items()}
+        m = len(u2i)
+        model.topKSim = {}
+        for name, uid in u2i.items():
+            if name in model.data.userRecord and uid % 5 != 0:
+                fr = [by_id[f] for f in ((uid * 7 + 3) % m, (uid * 11 + 5) % m)]
+                model.topKSim[name] = [(f, 1.0) for f in fr if f in model.data.userRecord and f != name]
+        oe = OracleEpochs(model)
+        model._push_factors = lambda: oe
+        model._pull_factors = lambda: None
+        model.isConverged = lambda it: False                   # the golden run does exactly num.max.iter iterations
+        model.buildModel()
+    assert np.array_equal(oe.ip[0], g["ip_indptr"]) and np.array_equal(oe.ip[1], g["ip_items"])
+    assert [c[5:] for c in oe.calls] == [(0, MODE_SERIAL), (1, MODE_SERIAL)] and oe.calls[0][:5] == (0.02, 0.01, 0.01, 2.0, 20260105)
+    assert np.array_equal(model.P, g["P"][-1]) and np.array_equal(model.Q, g["Q"][-1])
+    assert float(model.loss) == pytest.approx(float(g["loss"][-1]), rel=1e-9)
+
+
+# ---- GPU: K8 against the golden run ------------------------------------------------------------------------------------
+# First hardware run of this kernel happens at round end (the round's GPU minutes were spent before it was written):
+# non-strict xfail so that an XPASS / XFAIL line records the outcome without gating the rest of the suite.
+_first_run = pytest.mark.xfail(strict=False, reason="K8 (cune_sgd.cuh) not yet run on hardware: round-1 GPU budget was spent")
+
+
+def _load(engine, g):
+    m, n = g["P0"].shape[0], g["Q0"].shape[0]
+    engine.set_interactions(m, n, g["ev_indptr"], g["ev_items"], g["uq_indptr"], g["uq_items"])
+    engine.set_factors(g["P0"].copy(), g["Q0"].copy())
+    engine.cune_set_implicit(g["ip_indptr"], g["ip_items"])
+    return m, n
+
+
+@pytest.mark.gpu
+@_first_run
+def test_cune_serial_epochs_match_the_reference_loop(engine, golden_dir):
+    """Two serial-order iterations from the golden start: tables within 1e-5 relative of the reference loop's float32
+    tables (north_star's serial-order tolerance; the float32 dots sum in a different order), loss within 1e-4 (the
+    reference's loss turns float32 after the first user under numpy 2, the kernel's is float64)."""
+    from yue_b200.engine import MODE_SERIAL
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    _load(engine, g)
+    for it in range(len(g["loss"])):
+        loss = engine.cune_epoch(float(g["lr"]), float(g["regU"]), float(g["regI"]), float(g["s"]), int(g["seed"]), it, MODE_SERIAL)
+        P, Q = engine.get_factors()
+        for a, b in ((P, g["P"][it]), (Q, g["Q"][it])):
+            d = np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)
+            assert d.max() < 1e-5
+        assert loss == pytest.approx(float(g["loss"][it]), rel=1e-4)
+
+
+@pytest.mark.gpu
+@_first_run
+def test_cune_hogwild_epoch_stays_close_to_the_serial_one(engine, golden_dir):
+    """The parallel schedule on the same draws: same events, same k and j per event, so after one iteration the tables are
+    close to the serial ones (small log, few conflicts) and the -log part of the loss agrees to a few percent."""
+    from yue_b200.engine import MODE_HOGWILD
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    _load(engine, g)
+    loss = engine.cune_epoch(float(g["lr"]), 0.0, 0.0, float(g["s"]), int(g["seed"]), 0, MODE_HOGWILD)
+    P, Q = engine.get_factors()
+    assert np.isfinite(P).all() and np.isfinite(Q).all() and np.isfinite(loss) and loss > 0
+    Pr, Qr = g["P0"].copy(), g["Q0"].copy()
+    ref = cune_ref.epoch(Pr, Qr, g["ev_indptr"], g["ev_items"], g["ip_indptr"], g["ip_items"], g["kpos"][0], g["neg"][0],
+                         float(g["lr"]), 0.0, 0.0, float(g["s"]))
+    assert np.abs(P - Pr).max() < 5e-3 and np.abs(Q - Qr).max() < 5e-3
+    assert loss == pytest.approx(float(ref), rel=0.05)
+
+
+@pytest.mark.gpu
+@_first_run
+def test_cune_refusals(engine, golden_dir):
+    from yue_b200.engine import MODE_SERIAL, YueError
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    m, n = g["P0"].shape[0], g["Q0"].shape[0]
+    engine.set_interactions(m, n, g["ev_indptr"], g["ev_items"], g["uq_indptr"], g["uq_items"])
+    engine.set_factors(g["P0"].copy(), g["Q0"].copy())
+    with pytest.raises(YueError):                               # no implicit positives yet
+        engine.cune_epoch(0.02, 0.01, 0.01, 2.0, 1, 0, MODE_SERIAL)
+    bad = g["ip_items"].copy()
+    u = int(np.nonzero(np.diff(g["ip_indptr"]) > 0)[0][0])
+    bad[g["ip_indptr"][u]] = g["uq_items"][g["uq_indptr"][u]]  # a track the user has played
+    with pytest.raises(YueError):
+        engine.cune_set_implicit(g["ip_indptr"], bad)
+    engine.cune_set_implicit(g["ip_indptr"], g["ip_items"])
+    with pytest.raises(YueError):                               # s must be positive
+        engine.cune_epoch(0.02, 0.01, 0.01, 0.0, 1, 0, MODE_SERIAL)
+
+
+# ---- CPU: the kernel's text, compiled for the host ---------------------------------------------------------------------
+def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, tmp_path):
+    """tests/emul/cune_emul.cpp compiles csrc/cune_sgd.cuh itself with g++ as a one-lane warp (shuffles are identities):
+    the kernel's statement order, j == k aliasing, fused Philox draws of k and j, padding columns and loss -- everything
+    but the 32-lane reductions and the launch -- against the golden run of the reference's own loop text, without a GPU."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libcune_emul.so")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(root, "tests", "emul", "stub"),
+                    "-o", so, os.path.join(root, "tests", "emul", "cune_emul.cpp")], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    (m, k), n = g["P0"].shape, g["Q0"].shape[0]
+    csr = [np.ascontiguousarray(g[x], dtype=d) for x, d in (("ev_indptr", np.int64), ("ev_items", np.int32), ("uq_indptr", np.int64),
+                                                           ("uq_items", np.int32), ("ip_indptr", np.int64), ("ip_items", np.int32))]
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    # the golden draws contain repeats whose negative IS the implicit positive (one row updated under two names)
+    ev_user = record_ref.ev_users(g["ev_indptr"])
+    alias = 0
+    for it in range(len(g["loss"])):
+        for nn in range(3):
+            has = g["kpos"][it][nn] >= 0
+            assert has.any() and (~has).any()                  # both branches of the loop
+            alias += int((g["ip_items"][g["ip_indptr"][ev_user[has]] + g["kpos"][it][nn][has]] == g["neg"][it][nn][has]).sum())
+    assert alias > 0
+    err = lambda a, b: float((np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)).max())
+    for ld, serial, tol in ((12, 1, 1e-5), (16, 1, 1e-5), (16, 0, 1e-4)):
+        P, Q = np.zeros((m, ld), np.float32), np.zeros((n, ld), np.float32)
+        P[:, :k], Q[:, :k] = g["P0"], g["Q0"]
+        for it in range(len(g["loss"])):
+            loss, users = C.c_double(), C.c_uint64()
+            rc = lib.cune_emul_epoch(ptr(P), ptr(Q), ld, k, C.c_int64(m), C.c_int64(n), *[ptr(a) for a in csr], C.c_uint64(int(g["seed"])),
+                                     C.c_uint32(it), C.c_double(float(g["lr"])), C.c_double(float(g["regU"])), C.c_double(float(g["regI"])),
+                                     C.c_double(float(g["s"])), serial, C.byref(loss), C.byref(users))
+            assert rc == 0 and users.value == int((np.diff(g["ev_indptr"]) > 0).sum())
+            assert err(P[:, :k], g["P"][it]) < tol and err(Q[:, :k], g["Q"][it]) < tol
+            assert not P[:, k:].any() and not Q[:, k:].any()
+            if serial:
+                assert loss.value == pytest.approx(float(g["loss"][it]), rel=1e-5)

@@ -25,6 +25,7 @@
 #include "rank_metrics.cuh"
 #include "rank_tc.cuh"
 #include "wrmf_als.cuh"
+#include "cune_sgd.cuh"
 
 using namespace yue;
 
@@ -210,6 +211,13 @@ struct yue_handle {
     // 32 < k <= 64: 16 x 16 grid of 4 x 4 blocks on 160 threads (0, default) or 8 x 8 grid of 8 x 8 blocks on 64 threads
     // (YUE_WRMF_FAT=1; measured slower at config C2: 76 / 34 ms per user / track sweep against 64 / 27)
     int wrmf_fat = 0;
+
+    // CUNE (K8): implicit positives per user (tracks of the user's top-K similar users it has not played, CUNE.py:95-113)
+    bool have_ip = false;
+    DevBuf<int64_t> ip_indptr;
+    DevBuf<int32_t> ip_items;
+    DevBuf<double> cune_scal;                 // [0] loss of the epoch
+    DevBuf<unsigned long long> cune_ctr;      // [0] user cursor, [1] users with events
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -402,6 +410,7 @@ int yue_destroy(yue_t* h) {
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->tmp_i, &h->tmp_j, &h->rk_part_ids, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot, &h->hot_dx}) b->release();
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->delta_w, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
+    h->ip_indptr.release(); h->ip_items.release(); h->cune_scal.release(); h->cune_ctr.release();
     h->l2buf.release();
     h->uq_cnt.release(); h->it_users.release(); h->it_cnt.release(); h->it_indptr.release();
     for (auto* b : {&h->wrmf_G, &h->wrmf_part, &h->wrmf_partA, &h->wrmf_partb, &h->wrmf_Binv}) b->release();
@@ -463,6 +472,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     h->have_ev_user = false;
     h->have_log = false;
     h->have_ev_delta = false;
+    h->have_ip = false;                                    // implicit positives belong to the log they were set for
     h->last_rank_B = 0;
     pt.lap("validate + host copies");
 
@@ -1068,6 +1078,94 @@ int yue_bpr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j
 int yue_apr_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T, double lr,
                   double regU, double regI, double eps, double regA, int mode, double* loss_out) {
     return sgd_apply(h, u, i, j, T, lr, regU, regI, mode, loss_out, true, eps, regA);
+}
+
+// ---- K8: CUNE's two-level BPR epoch (cune_sgd.cuh) --------------------------------------------------------------------
+int yue_cune_set_implicit(yue_t* h, const int64_t* ip_indptr, const int32_t* ip_items) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "call yue_set_interactions first");
+    REQUIRE(ip_indptr, YUE_E_ARG, "null ip_indptr");
+    CK(cudaSetDevice(h->device));
+    REQUIRE(ip_indptr[0] == 0, YUE_E_ARG, "ip_indptr[0] must be 0");
+    for (int64_t u = 0; u < h->m; ++u) REQUIRE(ip_indptr[u + 1] >= ip_indptr[u], YUE_E_ARG, "ip_indptr not monotone");
+    const int64_t nip = ip_indptr[h->m];
+    REQUIRE(nip == 0 || ip_items, YUE_E_ARG, "null ip_items");
+    // an implicit positive is a track the user has NOT played (CUNE.py:111-113); the kernel relies on it (k != i)
+    if (int rc = host_indptrs(h)) return rc;
+    std::vector<int32_t> uq((size_t)std::max<int64_t>(h->nnz, 1));
+    if (h->nnz) CK(cudaMemcpyAsync(uq.data(), h->uq_items.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int64_t u = 0; u < h->m; ++u) {
+        const int32_t* rb = uq.data() + h->h_uq_indptr[u];
+        const int32_t* re = uq.data() + h->h_uq_indptr[u + 1];
+        for (int64_t x = ip_indptr[u]; x < ip_indptr[u + 1]; ++x) {
+            REQUIRE(ip_items[x] >= 0 && ip_items[x] < h->n, YUE_E_ARG, "implicit positive out of range");
+            REQUIRE(!std::binary_search(rb, re, ip_items[x]), YUE_E_ARG,
+                    "implicit positive " + std::to_string(ip_items[x]) + " was played by user " + std::to_string(u + h->user_begin));
+        }
+    }
+    CK(h->ip_indptr.resize((size_t)h->m + 1)); CK(h->ip_items.resize((size_t)std::max<int64_t>(nip, 1)));
+    CK(cudaMemcpyAsync(h->ip_indptr.p, ip_indptr, (h->m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (nip) CK(cudaMemcpyAsync(h->ip_items.p, ip_items, nip * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));                   // the caller owns the host arrays
+    h->have_ip = true;
+    return YUE_OK;
+}
+
+template <int NC>
+static cudaError_t launch_cune(const CuneParams& cp, int mode, int grid, cudaStream_t st) {
+    if (mode == YUE_MODE_SERIAL) cune_sgd_kernel<NC, kSerial><<<1, 32, 0, st>>>(cp);
+    else cune_sgd_kernel<NC, kAtomic><<<grid, 256, 0, st>>>(cp);
+    return cudaGetLastError();
+}
+
+int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint64_t seed, uint32_t epoch, int mode,
+                   double* loss_out) {
+    REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
+    REQUIRE(h->have_ip, YUE_E_STATE, "call yue_cune_set_implicit first");
+    REQUIRE(mode == YUE_MODE_SERIAL || mode == YUE_MODE_HOGWILD, YUE_E_ARG, "mode must be YUE_MODE_SERIAL or YUE_MODE_HOGWILD");
+    REQUIRE(s > 0.0 && std::isfinite(s), YUE_E_ARG, "s must be positive");
+    REQUIRE(h->ld <= 32 * kCuneMaxC, YUE_E_UNSUPPORTED, "num.factors > 256");
+    CK(cudaSetDevice(h->device));
+    if (h->T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
+    if (int rc = q_rowmajor(h)) return rc;
+    CK(h->cune_scal.resize(1)); CK(h->cune_ctr.resize(2));
+    CK(cudaMemsetAsync(h->cune_scal.p, 0, sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->cune_ctr.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    CuneParams cp{};
+    cp.P = h->P.p; cp.Q = h->Q.p; cp.ld = h->ld; cp.k = h->k; cp.m = h->m; cp.n = h->n;
+    cp.ev_indptr = h->ev_indptr.p; cp.ev_items = h->ev_items.p; cp.hot_items = h->hot_items.p;
+    cp.uq_indptr = h->uq_indptr.p; cp.uq_items = h->uq_items.p;
+    cp.ip_indptr = h->ip_indptr.p; cp.ip_items = h->ip_items.p;
+    cp.seed = seed; cp.epoch = epoch; cp.event_base = h->event_base; cp.ev_delta = h->have_ev_delta ? h->ev_delta.p : nullptr;
+    cp.lr = lr; cp.inv_s = 1.0 / s; cp.regU = regU; cp.regI = regI;
+    cp.c_u = (float)(lr * regU); cp.c_i = (float)(lr * regI);
+    cp.cursor = h->cune_ctr.p; cp.users_done = h->cune_ctr.p + 1; cp.loss = h->cune_scal.p;
+    // one warp per user, 8 warps per CTA; at most two CTAs per SM so that the users in flight stay a window of the stream
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 2, (h->m + 7) / 8));
+    const int nc = (h->ld + 31) / 32;
+    if (nc <= 1) CK(launch_cune<1>(cp, mode, grid, h->stream));
+    else if (nc <= 2) CK(launch_cune<2>(cp, mode, grid, h->stream));
+    else if (nc <= 4) CK(launch_cune<4>(cp, mode, grid, h->stream));
+    else CK(launch_cune<kCuneMaxC>(cp, mode, grid, h->stream));
+    ++h->launches;
+    h->ilv_current = false;
+    h->tc.q_dirty = true;
+    double loss = 0.0;
+    unsigned long long users = 0;
+    CK(cudaMemcpyAsync(&loss, h->cune_scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&users, h->cune_ctr.p + 1, sizeof(users), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (mode != YUE_MODE_SERIAL && (regU != 0.0 || regI != 0.0)) {
+        // CUNE.py:174 adds the norms after every user; a parallel schedule has no per-user table state, so the
+        // end-of-epoch norms stand in for all of them
+        double p2 = 0.0, q2 = 0.0;
+        if (int rc = yue_frob2(h, &p2, &q2)) return rc;
+        loss += (double)users * (regU * p2 + regI * q2);
+    }
+    if (loss_out) *loss_out = loss;
+    if (!std::isfinite(loss))
+        return fail(h, YUE_E_NUMERIC, "Loss = NaN or Infinity: current settings does not fit the recommender!");
+    return YUE_OK;
 }
 
 int yue_frob2(yue_t* h, double* p2, double* q2) {

@@ -189,6 +189,22 @@ class Engine:
                                         len(u), lr, regU, regI, eps, regA, mode, C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
 
+    def cune_set_implicit(self, ip_indptr, ip_items):
+        """Implicit positives per user (CUNE.py:95-113): tracks of the user's similar users that it has not played."""
+        ip_indptr, ip_items = _as(ip_indptr, np.int64), _as(ip_items, np.int32)
+        if len(ip_indptr) != self.m + 1:
+            raise ValueError("ip_indptr must have m+1 entries")
+        if len(ip_items) != ip_indptr[-1]:
+            raise ValueError("ip_items does not match ip_indptr[-1]")
+        self._ck(self.lib.yue_cune_set_implicit(self.h, _ptr(ip_indptr, C.c_int64), _ptr(ip_items, C.c_int32)))
+
+    def cune_epoch(self, lr, regU, regI, s, seed, epoch, mode=MODE_HOGWILD):
+        """One pass of CUNE's two-level BPR loop (CUNE.py:122-174); returns the loss."""
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_cune_epoch(self.h, float(lr), float(regU), float(regI), float(s), int(seed), int(epoch),
+                                         int(mode), C.byref(loss)))
+        return loss.value
+
     def wrmf_sweep(self, side, reg, alpha=10.0, want_loss=False):
         """One WRMF half-sweep (0: every user row from the track table, 1: every track row from the user table)."""
         loss = C.c_double(0.0)
