@@ -219,3 +219,62 @@ def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, 
             assert not P[:, k:].any() and not Q[:, k:].any()
             if serial:
                 assert loss.value == pytest.approx(float(g["loss"][it]), rel=1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_cune_dropin_shim_on_top_of_the_reference_tree(golden_dir, tmp_path):
+    """dropin/recommender/advanced/CUNE.py shadows the reference's module (which needs gensim at import), derives from the
+    REFERENCE's own base.IterativeRecommender and Record, and with the oracle in place of yue_cune_epoch reproduces the
+    golden tables of the reference's loop text bit for bit."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import io, json, os, sys
+import numpy as np
+from contextlib import redirect_stdout
+sys.path[:0] = [%(dropin)r, "/root/reference", %(root)r]
+from tool.config import Config
+from recommender.advanced.CUNE import CUNE
+import base.IterativeRecommender as ref_base
+import recommender.advanced.CUNE as mod
+assert mod.__file__.startswith(%(dropin)r) and CUNE.__mro__[3] is ref_base.IterativeRecommender, CUNE.__mro__
+from oracle import cune_ref, philox, record_ref
+from yue_b200.host.record import interaction_arrays
+g = json.load(open(%(gold)r + "/record_small.json"))
+keep = set('u%%d' %% x for x in range(60))
+train = [e for e, h in zip(g["events"], g["held"]) if not h and e['user'] in keep]
+test = [e for e, h in zip(g["events"], g["held"]) if h and e['user'] in keep]
+open(%(tmp)r + "/c.conf", "w").write("\n".join(k + "=" + v for k, v in %(conf)r.items()))
+w = np.load(%(gold)r + "/cune_small.npz")
+with redirect_stdout(io.StringIO()):
+    m = CUNE(Config(%(tmp)r + "/c.conf"), train, test)
+    m.readConfiguration()
+    np.random.seed(99)
+    m.initModel()
+    arr = interaction_arrays(m.data.name2id, m.data.userRecord, m.recType)
+    u2i = m.data.name2id['user']; by_id = {v: k for k, v in u2i.items()}; M = len(u2i)
+    m.topKSim = {}
+    for name, uid in u2i.items():
+        if name in m.data.userRecord and uid %% 5 != 0:
+            fr = [by_id[f] for f in ((uid * 7 + 3) %% M, (uid * 11 + 5) %% M)]
+            m.topKSim[name] = [(f, 1.0) for f in fr if f in m.data.userRecord and f != name]
+    class E:
+        def get_interactions(self): return arr
+        def cune_set_implicit(self, a, b): self.ip = (np.asarray(a), np.asarray(b))
+        def cune_epoch(self, lr, regU, regI, s, seed, epoch, mode):
+            evu = record_ref.ev_users(arr[0])
+            kp = [cune_ref.sample_implicit(seed, epoch, nn, evu, self.ip[0]) for nn in range(3)]
+            neg = [philox.sample_negatives(seed, epoch, evu, m.n, arr[2], arr[3], slot=nn) for nn in range(3)]
+            return cune_ref.epoch(m.P, m.Q, arr[0], arr[1], self.ip[0], self.ip[1], kp, neg, lr, regU, regI, s)
+    e = E()
+    m._push_factors = lambda: e
+    m._pull_factors = lambda: None
+    m.isConverged = lambda it: False
+    m.buildModel()
+assert np.array_equal(e.ip[1], w["ip_items"])
+assert np.array_equal(m.P, w["P"][-1]) and np.array_equal(m.Q, w["Q"][-1])
+print("OK")
+''' % dict(dropin=os.path.join(root, "dropin"), root=root, gold=golden_dir, tmp=str(tmp_path), conf=_conf(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
