@@ -34,15 +34,16 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 extern "C" int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int64_t n, const int64_t* ev_indptr,
                                const int32_t* ev_items, const int64_t* uq_indptr, const int32_t* uq_items,
                                const int64_t* ip_indptr, const int32_t* ip_items, uint64_t seed, uint32_t epoch, double lr,
-                               double regU, double regI, double s, int serial, double* loss_out, uint64_t* users_out) {
+                               double regU, double regI, double s, int serial, double* loss_out, uint64_t* users_out,
+                               const int32_t* hot_items, int64_t event_base, const int64_t* ev_delta) {
     if (ld > 16) return 1;
     unsigned long long ctr[2] = {0, 0};
     double loss = 0.0;
     yue::CuneParams cp{};
     cp.P = P; cp.Q = Q; cp.ld = ld; cp.k = k; cp.m = m; cp.n = n;
-    cp.ev_indptr = ev_indptr; cp.ev_items = ev_items; cp.hot_items = nullptr;
+    cp.ev_indptr = ev_indptr; cp.ev_items = ev_items; cp.hot_items = hot_items;
     cp.uq_indptr = uq_indptr; cp.uq_items = uq_items; cp.ip_indptr = ip_indptr; cp.ip_items = ip_items;
-    cp.seed = seed; cp.epoch = epoch; cp.event_base = 0; cp.ev_delta = nullptr;
+    cp.seed = seed; cp.epoch = epoch; cp.event_base = event_base; cp.ev_delta = ev_delta;
     cp.lr = lr; cp.inv_s = 1.0 / s; cp.regU = regU; cp.regI = regI;
     cp.c_u = (float)(lr * regU); cp.c_i = (float)(lr * regI);
     cp.cursor = &ctr[0]; cp.users_done = &ctr[1]; cp.loss = &loss;

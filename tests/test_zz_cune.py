@@ -213,12 +213,39 @@ def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, 
             loss, users = C.c_double(), C.c_uint64()
             rc = lib.cune_emul_epoch(ptr(P), ptr(Q), ld, k, C.c_int64(m), C.c_int64(n), *[ptr(a) for a in csr], C.c_uint64(int(g["seed"])),
                                      C.c_uint32(it), C.c_double(float(g["lr"])), C.c_double(float(g["regU"])), C.c_double(float(g["regI"])),
-                                     C.c_double(float(g["s"])), serial, C.byref(loss), C.byref(users))
+                                     C.c_double(float(g["s"])), serial, C.byref(loss), C.byref(users), None, C.c_int64(0), None)
             assert rc == 0 and users.value == int((np.diff(g["ev_indptr"]) > 0).sum())
             assert err(P[:, :k], g["P"][it]) < tol and err(Q[:, :k], g["Q"][it]) < tol
             assert not P[:, k:].any() and not Q[:, k:].any()
             if serial:
                 assert loss.value == pytest.approx(float(g["loss"][it]), rel=1e-5)
+    # The device-side log conventions the kernel shares with K2: hot positives stored re-labelled as -slot-1, and a log
+    # held as two user shards (local user indices, event_base / per-user offsets giving the global event index the draws
+    # are keyed on).  Shard 0 then shard 1 on the same Q table is the serial epoch.
+    ev_indptr, ev_items = csr[0], csr[1].copy()
+    hot = np.bincount(ev_items).argsort()[::-1][:3].astype(np.int32)
+    for slot, t in enumerate(hot):
+        ev_items[ev_items == t] = -slot - 1
+    assert (ev_items < 0).any()
+    cut = m // 2
+    for use_delta in (False, True):
+        P, Q = np.zeros((m, 16), np.float32), np.zeros((n, 16), np.float32)
+        P[:, :k], Q[:, :k] = g["P0"], g["Q0"]
+        for lo, hi in ((0, cut), (cut, m)):
+            e0 = int(ev_indptr[lo])
+            loc = [np.ascontiguousarray(x) for x in (ev_indptr[lo:hi + 1] - e0, ev_items[e0:int(ev_indptr[hi])],
+                                                     csr[2][lo:hi + 1] - csr[2][lo], csr[3][int(csr[2][lo]):int(csr[2][hi])],
+                                                     csr[4][lo:hi + 1] - csr[4][lo], csr[5][int(csr[4][lo]):int(csr[4][hi])])]
+            Ploc = np.ascontiguousarray(P[lo:hi])
+            delta = np.full(hi - lo, e0, np.int64)
+            loss, users = C.c_double(), C.c_uint64()
+            rc = lib.cune_emul_epoch(ptr(Ploc), ptr(Q), 16, k, C.c_int64(hi - lo), C.c_int64(n), *[ptr(a) for a in loc],
+                                     C.c_uint64(int(g["seed"])), C.c_uint32(0), C.c_double(float(g["lr"])), C.c_double(float(g["regU"])),
+                                     C.c_double(float(g["regI"])), C.c_double(float(g["s"])), 1, C.byref(loss), C.byref(users),
+                                     ptr(hot), C.c_int64(0 if use_delta else e0), ptr(delta) if use_delta else None)
+            assert rc == 0
+            P[lo:hi] = Ploc
+        assert err(P[:, :k], g["P"][0]) < 1e-5 and err(Q[:, :k], g["Q"][0]) < 1e-5
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
