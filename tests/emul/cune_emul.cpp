@@ -24,6 +24,7 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 static inline void __syncwarp() {}
 #define __expf(x) expf(x)
+static inline float __fdividef(float a, float b) { return a / b; }
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }

@@ -111,7 +111,7 @@ template <int MODE>
 __device__ __forceinline__ float cune_gain(double scale, float scale_f, float x) {
     if (MODE == kSerial) return (float)(scale * (1.0 - 1.0 / (1.0 + exp(-(double)x))));
     const float ex = __expf(-fabsf(x));
-    return scale_f * ((x >= 0.f ? ex : 1.f) / (1.f + ex));
+    return scale_f * __fdividef(x >= 0.f ? ex : 1.f, 1.f + ex);    // denominator in [1, 2]: no slow path needed
 }
 template <int MODE>
 __device__ __forceinline__ double cune_nll(float x) {          // -log(sigmoid(x))
@@ -130,7 +130,7 @@ __device__ __forceinline__ double cune_frob2_warp(const float* t, int64_t count,
 }
 
 template <int NC, int MODE, int W = 32>
-__global__ void __launch_bounds__(256) cune_sgd_kernel(const CuneParams p) {
+__global__ void __launch_bounds__(256, 2) cune_sgd_kernel(const CuneParams p) {
     using Row = CuneRow<NC, MODE, W>;
     const int lane = threadIdx.x & (W - 1);
     const float lr_f = (float)p.lr, lr2_f = (float)(p.inv_s * p.lr), inv_s_f = (float)p.inv_s;
@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(256) cune_sgd_kernel(const CuneParams p) {
                 qi0 = qi;
 #pragma unroll
                 for (int nn = 0; nn < 3; ++nn) {
-                    const int32_t j = __shfl_sync(0xffffffffu, my_j[nn], t);
-                    const int32_t k = __shfl_sync(0xffffffffu, my_k[nn], t);
+                    // selects, not my_j[nn]: the arrays stay in registers whether or not the loop is unrolled
+                    const int32_t j = __shfl_sync(0xffffffffu, nn == 0 ? my_j[0] : (nn == 1 ? my_j[1] : my_j[2]), t);
+                    const int32_t k = __shfl_sync(0xffffffffu, nn == 0 ? my_k[0] : (nn == 1 ? my_k[1] : my_k[2]), t);
                     if (j < 0) continue;                         // the user has played the whole catalog: no negative exists
                     float* const qj_ptr = p.Q + (size_t)j * p.ld;
                     Row qj, qj0;
