@@ -36,7 +36,7 @@ extern "C" int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int
                                const int32_t* ev_items, const int64_t* uq_indptr, const int32_t* uq_items,
                                const int64_t* ip_indptr, const int32_t* ip_items, uint64_t seed, uint32_t epoch, double lr,
                                double regU, double regI, double s, int serial, double* loss_out, uint64_t* users_out,
-                               const int32_t* hot_items, int64_t event_base, const int64_t* ev_delta) {
+                               const int32_t* hot_items, int64_t event_base, const int64_t* ev_delta, int64_t chunk) {
     if (ld > 16) return 1;
     unsigned long long ctr[2] = {0, 0};
     double loss = 0.0;
@@ -47,6 +47,9 @@ extern "C" int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int
     cp.seed = seed; cp.epoch = epoch; cp.event_base = event_base; cp.ev_delta = ev_delta;
     cp.lr = lr; cp.inv_s = 1.0 / s; cp.regU = regU; cp.regI = regI;
     cp.c_u = (float)(lr * regU); cp.c_i = (float)(lr * regI);
+    std::vector<int64_t> items;
+    yue::cune_plan_items(m, ev_indptr, serial ? 0 : chunk, items);
+    cp.items = items.data(); cp.n_work = (int64_t)items.size() / yue::kCuneItemWords;
     cp.cursor = &ctr[0]; cp.users_done = &ctr[1]; cp.loss = &loss;
     if (serial) yue::cune_sgd_kernel<16, yue::kSerial, 1>(cp);
     else yue::cune_sgd_kernel<16, yue::kAtomic, 1>(cp);

@@ -206,14 +206,17 @@ def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, 
             alias += int((g["ip_items"][g["ip_indptr"][ev_user[has]] + g["kpos"][it][nn][has]] == g["neg"][it][nn][has]).sum())
     assert alias > 0
     err = lambda a, b: float((np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)).max())
-    for ld, serial, tol in ((12, 1, 1e-5), (16, 1, 1e-5), (16, 0, 1e-4)):
+    # chunk: Hogwild cuts users with more events into work items that publish and re-read P[u] (0 = whole users); run one
+    # after the other they are still the serial order, so the bookkeeping of the shared row is checked here
+    assert int(np.diff(g["ev_indptr"]).max()) > 16
+    for ld, serial, chunk, tol in ((12, 1, 0, 1e-5), (16, 1, 0, 1e-5), (16, 0, 0, 1e-4), (16, 0, 16, 1e-4)):
         P, Q = np.zeros((m, ld), np.float32), np.zeros((n, ld), np.float32)
         P[:, :k], Q[:, :k] = g["P0"], g["Q0"]
         for it in range(len(g["loss"])):
             loss, users = C.c_double(), C.c_uint64()
             rc = lib.cune_emul_epoch(ptr(P), ptr(Q), ld, k, C.c_int64(m), C.c_int64(n), *[ptr(a) for a in csr], C.c_uint64(int(g["seed"])),
                                      C.c_uint32(it), C.c_double(float(g["lr"])), C.c_double(float(g["regU"])), C.c_double(float(g["regI"])),
-                                     C.c_double(float(g["s"])), serial, C.byref(loss), C.byref(users), None, C.c_int64(0), None)
+                                     C.c_double(float(g["s"])), serial, C.byref(loss), C.byref(users), None, C.c_int64(0), None, C.c_int64(chunk))
             assert rc == 0 and users.value == int((np.diff(g["ev_indptr"]) > 0).sum())
             assert err(P[:, :k], g["P"][it]) < tol and err(Q[:, :k], g["Q"][it]) < tol
             assert not P[:, k:].any() and not Q[:, k:].any()
@@ -242,7 +245,7 @@ def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, 
             rc = lib.cune_emul_epoch(ptr(Ploc), ptr(Q), 16, k, C.c_int64(hi - lo), C.c_int64(n), *[ptr(a) for a in loc],
                                      C.c_uint64(int(g["seed"])), C.c_uint32(0), C.c_double(float(g["lr"])), C.c_double(float(g["regU"])),
                                      C.c_double(float(g["regI"])), C.c_double(float(g["s"])), 1, C.byref(loss), C.byref(users),
-                                     ptr(hot), C.c_int64(0 if use_delta else e0), ptr(delta) if use_delta else None)
+                                     ptr(hot), C.c_int64(0 if use_delta else e0), ptr(delta) if use_delta else None, C.c_int64(0))
             assert rc == 0
             P[lo:hi] = Ploc
         assert err(P[:, :k], g["P"][0]) < 1e-5 and err(Q[:, :k], g["Q"][0]) < 1e-5

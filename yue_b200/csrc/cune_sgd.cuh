@@ -18,7 +18,11 @@
 // stay in registers over the three repeats; both draws are fused (Philox streams of oracle/philox.py: negatives with
 // slot n, the implicit positive with slot 64 + n, attempt 0, mapped onto the user's list by (r * len) >> 32).
 //   kSerial: one warp walks the users in order, float64 sigmoid and two roundings per axpy like numpy -- the parity anchor.
-//   kAtomic: warps take users from a cursor in stream order; Q changes leave as float adds (Hogwild), P[u] is private.
+//   kAtomic: warps take WORK ITEMS from a cursor in stream order; Q changes leave as float adds (Hogwild).  An item is a
+//            user, except that a user with more than `chunk` events is cut into items of `chunk` events (on a power-law
+//            log the heaviest user alone would otherwise be seconds of one warp's work).  Warps sharing a user publish
+//            their change of P[u] as adds and re-read the row every kCuneResync events -- the bound on the staleness of
+//            P[u] that K2's quality study found necessary (profiles/quality_study_r1.md) -- everyone else owns P[u].
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -30,7 +34,23 @@ namespace yue { enum : int { kSerial = 0, kAtomic = 1, kStore = 2 }; }
 #endif
 #include "philox.cuh"
 
+#include <vector>
+
 namespace yue {
+
+constexpr int kCuneResync = 8;
+constexpr int64_t kCuneItemWords = 4;      // {user, first event, end event, shared} per work item
+
+// Work items in stream order (host side; the C-ABI and tests/emul use this same text).  chunk <= 0: one item per user.
+inline void cune_plan_items(int64_t m, const int64_t* ev_indptr, int64_t chunk, std::vector<int64_t>& items) {
+    items.clear();
+    for (int64_t u = 0; u < m; ++u) {
+        const int64_t b = ev_indptr[u], e = ev_indptr[u + 1];
+        if (b == e) continue;                                    // PositiveSet has no entry for a user without events
+        if (chunk <= 0 || e - b <= chunk) { items.insert(items.end(), {u, b, e, 0}); continue; }
+        for (int64_t x = b; x < e; x += chunk) items.insert(items.end(), {u, x, x + chunk < e ? x + chunk : e, 1});
+    }
+}
 
 struct CuneParams {
     float* P; float* Q;
@@ -38,6 +58,8 @@ struct CuneParams {
     int k;                           // num.factors (columns >= k are padding and stay zero)
     int64_t m, n;
     const int64_t* ev_indptr;        // [m+1] events per user (user-major, BPR.py:42-45 order)
+    const int64_t* items;            // [n_work * kCuneItemWords] work items (cune_plan_items)
+    int64_t n_work;
     const int32_t* ev_items;         // [T]; v < 0 names hot slot -v-1 (the SGD planner's relabelling)
     const int32_t* hot_items;
     const int64_t* uq_indptr;        // [m+1] sorted-unique play rows (rejection set)
@@ -143,10 +165,10 @@ __global__ void __launch_bounds__(256, 2) cune_sgd_kernel(const CuneParams p) {
         if (lane == 0) it = atomicAdd(p.cursor, 1ull);
         return (int64_t)__shfl_sync(0xffffffffu, it, 0);
     };
-    for (int64_t u = take(); u < p.m; u = take()) {
-        const int64_t eb = p.ev_indptr[u], ee = p.ev_indptr[u + 1];
-        if (eb == ee) continue;                                  // PositiveSet has no entry for a user without events
-        ++done;
+    for (int64_t item = take(); item < p.n_work; item = take()) {
+        const int64_t u = p.items[item * kCuneItemWords], eb = p.items[item * kCuneItemWords + 1], ee = p.items[item * kCuneItemWords + 2];
+        const bool shared = MODE != kSerial && p.items[item * kCuneItemWords + 3] != 0;
+        if (eb == p.ev_indptr[u]) ++done;                        // the user's first item counts the user
         const int64_t r0 = p.uq_indptr[u];
         const int32_t* row = p.uq_items + r0;
         const int row_len = (int)(p.uq_indptr[u + 1] - r0);
@@ -154,8 +176,9 @@ __global__ void __launch_bounds__(256, 2) cune_sgd_kernel(const CuneParams p) {
         const uint32_t ip_len = (uint32_t)(p.ip_indptr[u + 1] - ip0);
         const int64_t gbase = p.ev_delta ? p.ev_delta[u] : p.event_base;
         float* const pu_ptr = p.P + (size_t)u * p.ld;
-        Row pu;
+        Row pu, pu0;
         pu.load(pu_ptr, lane, p.ld);
+        pu0 = pu;
 
         for (int64_t e0 = eb; e0 < ee; e0 += W) {
             const int len = (int)((ee - e0) < W ? (ee - e0) : W);
@@ -179,6 +202,11 @@ __global__ void __launch_bounds__(256, 2) cune_sgd_kernel(const CuneParams p) {
             }
             __syncwarp();
             for (int t = 0; t < len; ++t) {
+                if (shared && (e0 - eb + t) > 0 && (e0 - eb + t) % kCuneResync == 0) {
+                    pu.add_delta(pu_ptr, pu0, lane, p.ld);       // publish, then re-read: same thread, same address -> ordered
+                    pu.load(pu_ptr, lane, p.ld);
+                    pu0 = pu;
+                }
                 const int32_t i = __shfl_sync(0xffffffffu, my_i, t);
                 float* const qi_ptr = p.Q + (size_t)i * p.ld;
                 Row qi, qi0;
@@ -230,7 +258,8 @@ __global__ void __launch_bounds__(256, 2) cune_sgd_kernel(const CuneParams p) {
                 if (MODE == kAtomic) qi.add_delta(qi_ptr, qi0, lane, p.ld); else qi.store(qi_ptr, lane, p.ld);
             }
         }
-        pu.store(pu_ptr, lane, p.ld);                            // P[u] belongs to this warp alone
+        if (shared) pu.add_delta(pu_ptr, pu0, lane, p.ld);
+        else pu.store(pu_ptr, lane, p.ld);                       // P[u] belongs to this warp alone
         if (MODE == kSerial) {                                   // CUNE.py:174, once per user, over the whole tables
             __syncwarp();                                        // the sums read columns other lanes stored (ld % 32 != 0)
             loss += p.regU * cune_frob2_warp<W>(p.P, p.m * p.ld, lane) + p.regI * cune_frob2_warp<W>(p.Q, p.n * p.ld, lane);

@@ -217,6 +217,8 @@ struct yue_handle {
     DevBuf<int64_t> ip_indptr;
     DevBuf<int32_t> ip_items;
     DevBuf<double> cune_scal;                 // [0] loss of the epoch
+    DevBuf<int64_t> cune_items;               // work items of the epoch kernel (cune_plan_items)
+    int64_t cune_n_work = 0, cune_chunk = -1; // -1: no plan for the current log
     DevBuf<unsigned long long> cune_ctr;      // [0] user cursor, [1] users with events
 
     ncclComm_t comm = nullptr;
@@ -410,7 +412,7 @@ int yue_destroy(yue_t* h) {
     for (auto* b : {&h->ev_items, &h->uq_items, &h->ev_user, &h->tmp_i, &h->tmp_j, &h->rk_part_ids, &h->rk_users, &h->rk_ids, &h->hot_items, &h->hot_slot, &h->item_counts, &h->hot_meta, &h->hot_sorted, &h->hot_sorted_slot, &h->hot_dx}) b->release();
     for (auto* b : {&h->P, &h->Q, &h->Qsnap, &h->Qdelta, &h->delta_w, &h->Qilv, &h->rk_scores, &h->pred, &h->rk_part_scores, &h->hot_shards, &h->hotQ}) b->release();
     h->scal.release();
-    h->ip_indptr.release(); h->ip_items.release(); h->cune_scal.release(); h->cune_ctr.release();
+    h->ip_indptr.release(); h->ip_items.release(); h->cune_scal.release(); h->cune_ctr.release(); h->cune_items.release();
     h->l2buf.release();
     h->uq_cnt.release(); h->it_users.release(); h->it_cnt.release(); h->it_indptr.release();
     for (auto* b : {&h->wrmf_G, &h->wrmf_part, &h->wrmf_partA, &h->wrmf_partb, &h->wrmf_Binv}) b->release();
@@ -473,6 +475,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     h->have_log = false;
     h->have_ev_delta = false;
     h->have_ip = false;                                    // implicit positives belong to the log they were set for
+    h->cune_chunk = -1;
     h->last_rank_B = 0;
     pt.lap("validate + host copies");
 
@@ -1129,19 +1132,38 @@ int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint
     if (h->T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     if (int rc = q_rowmajor(h)) return rc;
     CK(h->cune_scal.resize(1)); CK(h->cune_ctr.resize(2));
+    // one warp per work item, 8 warps per CTA; at most two CTAs per SM so that the users in flight stay a window of the stream
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 2, (h->m + 7) / 8));
+    {   // work items: whole users in serial order; Hogwild cuts a user above a quarter of a warp's fair share of the epoch
+        int64_t chunk = 0;
+        if (mode != YUE_MODE_SERIAL) {
+            chunk = std::max<int64_t>(256, std::min<int64_t>(8192, h->T / ((int64_t)grid * 8 * 4)));
+            if (const char* e = getenv("YUE_CUNE_CHUNK")) chunk = std::max<int64_t>(32, atoll(e));
+            chunk = (chunk + 31) / 32 * 32;
+        }
+        if (h->cune_chunk != chunk) {
+            if (int rc = host_indptrs(h)) return rc;
+            std::vector<int64_t> items;
+            cune_plan_items(h->m, h->h_ev_indptr.data(), chunk, items);
+            h->cune_n_work = (int64_t)items.size() / kCuneItemWords;
+            CK(h->cune_items.resize(std::max<size_t>(items.size(), 1)));
+            if (!items.empty()) CK(cudaMemcpyAsync(h->cune_items.p, items.data(), items.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));           // the staging vector dies here
+            h->cune_chunk = chunk;
+        }
+    }
     CK(cudaMemsetAsync(h->cune_scal.p, 0, sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->cune_ctr.p, 0, 2 * sizeof(unsigned long long), h->stream));
     CuneParams cp{};
     cp.P = h->P.p; cp.Q = h->Q.p; cp.ld = h->ld; cp.k = h->k; cp.m = h->m; cp.n = h->n;
     cp.ev_indptr = h->ev_indptr.p; cp.ev_items = h->ev_items.p; cp.hot_items = h->hot_items.p;
+    cp.items = h->cune_items.p; cp.n_work = h->cune_n_work;
     cp.uq_indptr = h->uq_indptr.p; cp.uq_items = h->uq_items.p;
     cp.ip_indptr = h->ip_indptr.p; cp.ip_items = h->ip_items.p;
     cp.seed = seed; cp.epoch = epoch; cp.event_base = h->event_base; cp.ev_delta = h->have_ev_delta ? h->ev_delta.p : nullptr;
     cp.lr = lr; cp.inv_s = 1.0 / s; cp.regU = regU; cp.regI = regI;
     cp.c_u = (float)(lr * regU); cp.c_i = (float)(lr * regI);
     cp.cursor = h->cune_ctr.p; cp.users_done = h->cune_ctr.p + 1; cp.loss = h->cune_scal.p;
-    // one warp per user, 8 warps per CTA; at most two CTAs per SM so that the users in flight stay a window of the stream
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 2, (h->m + 7) / 8));
     const int nc = (h->ld + 31) / 32;
     if (nc <= 1) CK(launch_cune<1>(cp, mode, grid, h->stream));
     else if (nc <= 2) CK(launch_cune<2>(cp, mode, grid, h->stream));
