@@ -1,8 +1,11 @@
 // Test infrastructure: the device code of yue_b200/csrc/cune_sgd.cuh (K8) compiled for the HOST with a one-lane "warp"
 // (W = 1: a lane owns every column, warp shuffles are identities), so that the statement order, the aliasing of j and k,
 // the fused Philox draws and the loss of the kernel can be checked against tests/golden/cune_small.npz on a box without a
-// GPU.  It checks the kernel's TEXT; the 32-lane reductions, the memory system and the launch are what the -m gpu tests
-// check.  Built by tests/test_zz_cune.py with g++ -ffp-contract=off; never loaded by the product.
+// GPU.  With -DEMUL_LANES=8 the warp is eight host threads in lockstep instead (a shuffle is an exchange through a table
+// between two barriers): the butterflies, the lane-per-event draws and their broadcast, the column ownership and the
+// cross-lane visibility rules run as written, for a warp of 8.  It checks the kernel's TEXT; the memory system, the
+// 32-lane width and the launch are what the -m gpu tests check.  Built by tests/test_zz_cune.py with g++
+// -ffp-contract=off; never loaded by the product.
 #define YUE_CUNE_HOST_EMUL 1
 #include <cmath>
 #include <cstdint>
@@ -14,18 +17,47 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#ifndef EMUL_LANES
+#define EMUL_LANES 1
+#endif
 struct EmulIdx { unsigned x = 0, y = 0, z = 0; };
+#if EMUL_LANES == 1
 static EmulIdx threadIdx;
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+static inline void __syncwarp() {}
+template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+#else
+#include <barrier>
+#include <mutex>
+#include <thread>
+static thread_local EmulIdx threadIdx;
+static std::barrier<>* g_bar = nullptr;
+static uint64_t g_xchg[EMUL_LANES];
+static std::mutex g_atomic;
+template <class T> static inline T emul_exchange(T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle operand");
+    uint64_t raw = 0, got;
+    memcpy(&raw, &v, sizeof(T));
+    g_xchg[threadIdx.x] = raw;
+    g_bar->arrive_and_wait();
+    got = g_xchg[src & (EMUL_LANES - 1)];
+    g_bar->arrive_and_wait();
+    T out;
+    memcpy(&out, &got, sizeof(T));
+    return out;
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emul_exchange(v, src); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emul_exchange(v, (int)threadIdx.x ^ m); }
+static inline void __syncwarp() { g_bar->arrive_and_wait(); }
+template <class T> static inline T atomicAdd(T* p, T v) { std::lock_guard<std::mutex> l(g_atomic); T o = *p; *p = o + v; return o; }
+#endif
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
-template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
-static inline void __syncwarp() {}
 #define __expf(x) expf(x)
 static inline float __fdividef(float a, float b) { return a / b; }
-template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
@@ -51,8 +83,23 @@ extern "C" int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int
     yue::cune_plan_items(m, ev_indptr, serial ? 0 : chunk, items);
     cp.items = items.data(); cp.n_work = (int64_t)items.size() / yue::kCuneItemWords;
     cp.cursor = &ctr[0]; cp.users_done = &ctr[1]; cp.loss = &loss;
-    if (serial) yue::cune_sgd_kernel<16, yue::kSerial, 1>(cp);
-    else yue::cune_sgd_kernel<16, yue::kAtomic, 1>(cp);
+    constexpr int kNC = (16 + EMUL_LANES - 1) / EMUL_LANES;
+#if EMUL_LANES == 1
+    if (serial) yue::cune_sgd_kernel<kNC, yue::kSerial, 1>(cp);
+    else yue::cune_sgd_kernel<kNC, yue::kAtomic, 1>(cp);
+#else
+    std::barrier<> bar(EMUL_LANES);
+    g_bar = &bar;
+    std::thread lanes[EMUL_LANES];
+    for (int l = 0; l < EMUL_LANES; ++l)
+        lanes[l] = std::thread([&cp, serial, l]() {
+            threadIdx.x = (unsigned)l;
+            if (serial) yue::cune_sgd_kernel<kNC, yue::kSerial, EMUL_LANES>(cp);
+            else yue::cune_sgd_kernel<kNC, yue::kAtomic, EMUL_LANES>(cp);
+        });
+    for (auto& t : lanes) t.join();
+    g_bar = nullptr;
+#endif
     *loss_out = loss;
     *users_out = ctr[1];
     return 0;

@@ -251,6 +251,42 @@ def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, 
         assert err(P[:, :k], g["P"][0]) < 1e-5 and err(Q[:, :k], g["Q"][0]) < 1e-5
 
 
+def test_cune_kernel_text_as_an_eight_lane_warp_in_lockstep(golden_dir, tmp_path):
+    """The same header with -DEMUL_LANES=8: eight host threads in lockstep, a shuffle = an exchange between two barriers.
+    Runs the warp-level text as written -- xor butterflies, one lane per event drawing k and j and the broadcast of its
+    draws, lane-owned columns (12 columns on 8 lanes: a partial second chunk), the barrier before the per-user norms that
+    read other lanes' columns, lane 0's cursor and loss -- against the golden run, serial and Hogwild with shared items."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libcune_emul8.so")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-DEMUL_LANES=8", "-shared", "-fPIC",
+                    "-I" + os.path.join(root, "tests", "emul", "stub"), "-o", so, os.path.join(root, "tests", "emul", "cune_emul.cpp")],
+                   check=True, capture_output=True)
+    lib = C.CDLL(so)
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    (m, k), n = g["P0"].shape, g["Q0"].shape[0]
+    csr = [np.ascontiguousarray(g[x], dtype=d) for x, d in (("ev_indptr", np.int64), ("ev_items", np.int32), ("uq_indptr", np.int64),
+                                                           ("uq_items", np.int32), ("ip_indptr", np.int64), ("ip_items", np.int32))]
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    err = lambda a, b: float((np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)).max())
+    for ld, serial, chunk, tol in ((12, 1, 0, 1e-5), (16, 0, 16, 1e-4)):
+        P, Q = np.zeros((m, ld), np.float32), np.zeros((n, ld), np.float32)
+        P[:, :k], Q[:, :k] = g["P0"], g["Q0"]
+        loss, users = C.c_double(), C.c_uint64()
+        rc = lib.cune_emul_epoch(ptr(P), ptr(Q), ld, k, C.c_int64(m), C.c_int64(n), *[ptr(a) for a in csr], C.c_uint64(int(g["seed"])),
+                                 C.c_uint32(0), C.c_double(float(g["lr"])), C.c_double(float(g["regU"])), C.c_double(float(g["regI"])),
+                                 C.c_double(float(g["s"])), serial, C.byref(loss), C.byref(users), None, C.c_int64(0), None, C.c_int64(chunk))
+        assert rc == 0 and users.value == int((np.diff(g["ev_indptr"]) > 0).sum())
+        assert err(P[:, :k], g["P"][0]) < tol and err(Q[:, :k], g["Q"][0]) < tol
+        assert not P[:, k:].any() and not Q[:, k:].any()
+        if serial:
+            assert loss.value == pytest.approx(float(g["loss"][0]), rel=1e-5)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 def test_cune_dropin_shim_on_top_of_the_reference_tree(golden_dir, tmp_path):
     """dropin/recommender/advanced/CUNE.py shadows the reference's module (which needs gensim at import), derives from the
