@@ -62,6 +62,14 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+namespace yue {                      // the three row accessors of bpr_sgd.cuh (PTX there)
+static inline float4 ld_row(const float* p) { return float4{p[0], p[1], p[2], p[3]}; }
+static inline void st_row(float* p, float4 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+static inline void red_row(float* p, float4 v) { atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w); }
+}  // namespace yue
+
 #include "../../yue_b200/csrc/cune_sgd.cuh"
 
 extern "C" int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int64_t n, const int64_t* ev_indptr,
@@ -83,7 +91,7 @@ extern "C" int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int
     yue::cune_plan_items(m, ev_indptr, serial ? 0 : chunk, items);
     cp.items = items.data(); cp.n_work = (int64_t)items.size() / yue::kCuneItemWords;
     cp.cursor = &ctr[0]; cp.users_done = &ctr[1]; cp.loss = &loss;
-    constexpr int kNC = (16 + EMUL_LANES - 1) / EMUL_LANES;
+    constexpr int kNC = (4 + EMUL_LANES - 1) / EMUL_LANES;      // 16-byte chunks per lane for ld <= 16
 #if EMUL_LANES == 1
     if (serial) yue::cune_sgd_kernel<kNC, yue::kSerial, 1>(cp);
     else yue::cune_sgd_kernel<kNC, yue::kAtomic, 1>(cp);

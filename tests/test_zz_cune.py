@@ -254,7 +254,7 @@ def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, 
 def test_cune_kernel_text_as_an_eight_lane_warp_in_lockstep(golden_dir, tmp_path):
     """The same header with -DEMUL_LANES=8: eight host threads in lockstep, a shuffle = an exchange between two barriers.
     Runs the warp-level text as written -- xor butterflies, one lane per event drawing k and j and the broadcast of its
-    draws, lane-owned columns (12 columns on 8 lanes: a partial second chunk), the barrier before the per-user norms that
+    draws, lane-owned 16-byte chunks (three of them at 12 columns: most lanes hold none), the barrier before the per-user norms that
     read other lanes' columns, lane 0's cursor and loss -- against the golden run, serial and Hogwild with shared items."""
     import ctypes as C
     import shutil

@@ -13,8 +13,9 @@
 // shipped); the serial mode does exactly that, the parallel mode adds (users with events) x the end-of-epoch norms on
 // the host side of the C-ABI (documented deviation: the mid-epoch state of a parallel schedule is not defined).
 //
-// One warp per user; a lane owns floats lane, lane+32, ... of every row it touches (coalesced 128-byte accesses, and no
-// lane ever reads a column another lane wrote, so a warp needs no fences between its own statements).  P[u] and Q[i]
+// One warp per work item; a lane owns the 16-byte chunks lane, lane+32, ... of every row it touches (128-bit accesses, at
+// d = 64 one per row on half the lanes; no lane ever reads a column another lane wrote, so a warp needs no fences between
+// its own statements).  P[u] and Q[i]
 // stay in registers over the three repeats; both draws are fused (Philox streams of oracle/philox.py: negatives with
 // slot n, the implicit positive with slot 64 + n, attempt 0, mapped onto the user's list by (r * len) >> 32).
 //   kSerial: one warp walks the users in order, float64 sigmoid and two roundings per axpy like numpy -- the parity anchor.
@@ -75,42 +76,58 @@ struct CuneParams {
     unsigned long long* users_done;  // users with at least one event (parallel mode: the host scales the norms by it)
 };
 
-constexpr int kCuneMaxC = 8;         // ld <= 256
+constexpr int kCuneMaxC = 2;         // 16-byte chunks per lane: ld <= 256
 
-// W = lanes per warp: 32 on the device; 1 in the host emulation of tests/emul (same statements, shuffles are identities)
+// W = lanes per warp: 32 on the device; 1 or 8 in the host emulation of tests/emul (same statements).
+// A lane owns the 16-byte chunks lane, lane + W, ... of a row (ld % 4 == 0): one 128-bit load per chunk, and the change of
+// a shared row leaves as ONE vector add per chunk (red.global.add.v4.f32, like K2) instead of four scalar atomics.
 template <int NC, int MODE, int W = 32>
 struct CuneRow {
-    float v[NC];
+    float4 v[NC];
+    static __device__ __forceinline__ bool has(int lane, int c, int ld) { return 4 * (lane + W * c) < ld; }
     __device__ __forceinline__ void load(const float* p, int lane, int ld) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] = (lane + W * c < ld) ? __ldcg(p + lane + W * c) : 0.f;
+        for (int c = 0; c < NC; ++c) v[c] = has(lane, c, ld) ? ld_row(p + 4 * (lane + W * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __device__ __forceinline__ void store(float* p, int lane, int ld) const {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) if (lane + W * c < ld) __stcg(p + lane + W * c, v[c]);
+        for (int c = 0; c < NC; ++c) if (has(lane, c, ld)) st_row(p + 4 * (lane + W * c), v[c]);
     }
     // p += (v - old): the change of a shared row leaves as adds
     __device__ __forceinline__ void add_delta(float* p, const CuneRow& old, int lane, int ld) const {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) if (lane + W * c < ld) atomicAdd(p + lane + W * c, v[c] - old.v[c]);
+        for (int c = 0; c < NC; ++c)
+            if (has(lane, c, ld))
+                red_row(p + 4 * (lane + W * c), make_float4(v[c].x - old.v[c].x, v[c].y - old.v[c].y, v[c].z - old.v[c].z, v[c].w - old.v[c].w));
+    }
+    static __device__ __forceinline__ float axpy1(float g, float a, float y) {         // y + g a; serial: two roundings like numpy
+        return MODE == kSerial ? __fadd_rn(y, __fmul_rn(g, a)) : fmaf(g, a, y);
     }
     // this += g * (a - b)
     __device__ __forceinline__ void axpy_diff(float g, const CuneRow& a, const CuneRow& b) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            const float d = __fsub_rn(a.v[c], b.v[c]);
-            v[c] = MODE == kSerial ? __fadd_rn(v[c], __fmul_rn(g, d)) : fmaf(g, d, v[c]);
+            v[c].x = axpy1(g, __fsub_rn(a.v[c].x, b.v[c].x), v[c].x);
+            v[c].y = axpy1(g, __fsub_rn(a.v[c].y, b.v[c].y), v[c].y);
+            v[c].z = axpy1(g, __fsub_rn(a.v[c].z, b.v[c].z), v[c].z);
+            v[c].w = axpy1(g, __fsub_rn(a.v[c].w, b.v[c].w), v[c].w);
         }
     }
     // this += g * a
     __device__ __forceinline__ void axpy(float g, const CuneRow& a) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] = MODE == kSerial ? __fadd_rn(v[c], __fmul_rn(g, a.v[c])) : fmaf(g, a.v[c], v[c]);
+        for (int c = 0; c < NC; ++c) {
+            v[c].x = axpy1(g, a.v[c].x, v[c].x); v[c].y = axpy1(g, a.v[c].y, v[c].y);
+            v[c].z = axpy1(g, a.v[c].z, v[c].z); v[c].w = axpy1(g, a.v[c].w, v[c].w);
+        }
     }
     // this -= c * this
     __device__ __forceinline__ void shrink(float cc) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] = MODE == kSerial ? __fsub_rn(v[c], __fmul_rn(cc, v[c])) : fmaf(-cc, v[c], v[c]);
+        for (int c = 0; c < NC; ++c) {
+            v[c].x = axpy1(-cc, v[c].x, v[c].x); v[c].y = axpy1(-cc, v[c].y, v[c].y);
+            v[c].z = axpy1(-cc, v[c].z, v[c].z); v[c].w = axpy1(-cc, v[c].w, v[c].w);
+        }
     }
 };
 
@@ -119,7 +136,12 @@ template <int NC, int MODE, int W>
 __device__ __forceinline__ float cune_dot_diff(const CuneRow<NC, MODE, W>& p, const CuneRow<NC, MODE, W>& a, const CuneRow<NC, MODE, W>& b) {
     float da = 0.f, db = 0.f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { da = fmaf(p.v[c], a.v[c], da); db = fmaf(p.v[c], b.v[c], db); }
+    for (int c = 0; c < NC; ++c) {
+        da = fmaf(p.v[c].x, a.v[c].x, da); db = fmaf(p.v[c].x, b.v[c].x, db);
+        da = fmaf(p.v[c].y, a.v[c].y, da); db = fmaf(p.v[c].y, b.v[c].y, db);
+        da = fmaf(p.v[c].z, a.v[c].z, da); db = fmaf(p.v[c].z, b.v[c].z, db);
+        da = fmaf(p.v[c].w, a.v[c].w, da); db = fmaf(p.v[c].w, b.v[c].w, db);
+    }
 #pragma unroll
     for (int mk = W / 2; mk >= 1; mk >>= 1) {
         da += __shfl_xor_sync(0xffffffffu, da, mk);

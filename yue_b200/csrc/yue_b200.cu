@@ -1127,7 +1127,7 @@ int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint
     REQUIRE(h->have_ip, YUE_E_STATE, "call yue_cune_set_implicit first");
     REQUIRE(mode == YUE_MODE_SERIAL || mode == YUE_MODE_HOGWILD, YUE_E_ARG, "mode must be YUE_MODE_SERIAL or YUE_MODE_HOGWILD");
     REQUIRE(s > 0.0 && std::isfinite(s), YUE_E_ARG, "s must be positive");
-    REQUIRE(h->ld <= 32 * kCuneMaxC, YUE_E_UNSUPPORTED, "num.factors > 256");
+    REQUIRE(h->ld <= 128 * kCuneMaxC && h->ld % 4 == 0, YUE_E_UNSUPPORTED, "num.factors > 256");
     CK(cudaSetDevice(h->device));
     if (h->T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     if (int rc = q_rowmajor(h)) return rc;
@@ -1164,10 +1164,7 @@ int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint
     cp.lr = lr; cp.inv_s = 1.0 / s; cp.regU = regU; cp.regI = regI;
     cp.c_u = (float)(lr * regU); cp.c_i = (float)(lr * regI);
     cp.cursor = h->cune_ctr.p; cp.users_done = h->cune_ctr.p + 1; cp.loss = h->cune_scal.p;
-    const int nc = (h->ld + 31) / 32;
-    if (nc <= 1) CK(launch_cune<1>(cp, mode, grid, h->stream));
-    else if (nc <= 2) CK(launch_cune<2>(cp, mode, grid, h->stream));
-    else if (nc <= 4) CK(launch_cune<4>(cp, mode, grid, h->stream));
+    if (h->ld <= 128) CK(launch_cune<1>(cp, mode, grid, h->stream));       // one 16-byte chunk per lane
     else CK(launch_cune<kCuneMaxC>(cp, mode, grid, h->stream));
     ++h->launches;
     h->ilv_current = false;
