@@ -344,3 +344,48 @@ print("OK")
 ''' % dict(dropin=os.path.join(root, "dropin"), root=root, gold=golden_dir, tmp=str(tmp_path), conf=_conf(tmp_path))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@_first_run
+@pytest.mark.parametrize("d", [64, 128, 200])
+def test_cune_serial_epoch_matches_oracle_at_bench_widths(engine, d):
+    """Row widths the golden run does not have (one 16-byte chunk per lane on 16 / 32 lanes, two chunks at d = 200) on a
+    synthetic power-law log with synthetic similar users: serial kernel (fused draws) against the oracle loop fed the
+    oracle's draws; then the Hogwild kernel with heavy users cut into 32-event items stays close to it."""
+    from yue_b200 import synth
+    from yue_b200.cune import implicit_positive_lists
+    from yue_b200.engine import MODE_HOGWILD, MODE_SERIAL
+    log = synth.power_law_log(80, 150, 1500, seed=11, test_ratio=0.0)
+    m, n = log.m, log.n
+    top = {u: [f for f in ((u * 7 + 3) % m, (u * 11 + 5) % m) if f != u] for u in range(m) if u % 5}
+    ip_indptr, ip_items = implicit_positive_lists(m, log.uq_indptr, log.uq_items, top)
+    rng = np.random.default_rng(d)
+    P0 = rng.uniform(0, 0.1, (m, d)).astype(np.float32)
+    Q0 = rng.uniform(0, 0.1, (n, d)).astype(np.float32)
+    engine.set_interactions(m, n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    engine.set_factors(P0.copy(), Q0.copy())
+    engine.cune_set_implicit(ip_indptr, ip_items)
+    loss = engine.cune_epoch(0.02, 0.01, 0.01, 2.0, 5, 0, MODE_SERIAL)
+    P, Q = engine.get_factors()
+    ev_user = record_ref.ev_users(log.ev_indptr)
+    kp = [cune_ref.sample_implicit(5, 0, nn, ev_user, ip_indptr) for nn in range(3)]
+    neg = [philox.sample_negatives(5, 0, ev_user, n, log.uq_indptr, log.uq_items, slot=nn) for nn in range(3)]
+    Pr, Qr = P0.copy(), Q0.copy()
+    ref = cune_ref.epoch(Pr, Qr, log.ev_indptr, log.ev_items, ip_indptr, ip_items, kp, neg, 0.02, 0.01, 0.01, 2.0)
+    err = lambda a, b: float((np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)).max())
+    assert err(P, Pr) < 1e-5 and err(Q, Qr) < 1e-5
+    assert loss == pytest.approx(float(ref), rel=1e-4)
+    os.environ["YUE_CUNE_CHUNK"] = "32"
+    try:
+        engine.set_factors(P0.copy(), Q0.copy())
+        lh = engine.cune_epoch(0.02, 0.0, 0.0, 2.0, 5, 0, MODE_HOGWILD)
+    finally:
+        del os.environ["YUE_CUNE_CHUNK"]
+    Ph, Qh = engine.get_factors()
+    Pr, Qr = P0.copy(), Q0.copy()
+    ref0 = cune_ref.epoch(Pr, Qr, log.ev_indptr, log.ev_items, ip_indptr, ip_items, kp, neg, 0.02, 0.0, 0.0, 2.0)
+    # seven warps share the heaviest user (198 events): a different schedule than the serial one, second-order differences
+    assert np.isfinite(Ph).all() and np.isfinite(Qh).all()
+    assert np.abs(Ph - Pr).max() < 5e-2 and np.abs(Qh - Qr).max() < 5e-2
+    assert lh == pytest.approx(float(ref0), rel=0.1)
