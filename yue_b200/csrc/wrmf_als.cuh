@@ -148,7 +148,7 @@ __device__ __forceinline__ void wrmf_accumulate(WrmfTile<TD>& tl, WrmfPre<TD, GB
                                                 const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt, int64_t e0,
                                                 int64_t e1, double alpha, double* ys, double* ws, const double* xs, double& loss,
                                                 int ty, int tx, bool active) {
-    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT, kWrmfBlocks = WrmfShape<TD, GB>::NB;
+    constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT;
     constexpr int Q4 = WrmfPre<TD, GB>::Q4;
     const int tid = threadIdx.x;
     for (int64_t eb = e0; eb < e1; eb += kWrmfBatch) {

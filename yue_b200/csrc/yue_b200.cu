@@ -1419,7 +1419,7 @@ static int wrmf_sweep_impl(yue_t* h, int side, int64_t row_begin, int64_t row_en
     constexpr int KP = TD * GB, kWrmfThreads = WrmfShape<TD, GB>::NT;
     constexpr size_t elems = (size_t)TD * TD * kWrmfThreads;
     cudaStream_t st = h->stream;
-    const int64_t rows = side == 0 ? h->m : h->n, other_rows = side == 0 ? h->n : h->m;
+    const int64_t other_rows = side == 0 ? h->n : h->m;
     if (row_end <= row_begin) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     const bool want_loss = loss_out != nullptr;
     auto& pl = h->wrmf_plan[side];
