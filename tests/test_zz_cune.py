@@ -287,6 +287,45 @@ def test_cune_kernel_text_as_an_eight_lane_warp_in_lockstep(golden_dir, tmp_path
             assert loss.value == pytest.approx(float(g["loss"][0]), rel=1e-5)
 
 
+def test_cune_kernel_text_at_the_device_warp_width(golden_dir, tmp_path):
+    """-DEMUL_LANES=32: the instantiation the C-ABI launches for num.factors <= 128 (one 16-byte chunk per lane, 32-event
+    batches of draws), as 32 host threads in lockstep, on the first users of the golden log (one of them has 203 events:
+    seven batches) against the oracle loop fed the golden draws; serial, and Hogwild with 32-event shared items."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libcune_emul32.so")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-DEMUL_LANES=32", "-shared", "-fPIC",
+                    "-I" + os.path.join(root, "tests", "emul", "stub"), "-o", so, os.path.join(root, "tests", "emul", "cune_emul.cpp")],
+                   check=True, capture_output=True)
+    lib = C.CDLL(so)
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    mm, k, n = 6, g["P0"].shape[1], g["Q0"].shape[0]
+    E = int(g["ev_indptr"][mm])
+    csr = [np.ascontiguousarray(x) for x in (g["ev_indptr"][:mm + 1], g["ev_items"][:E], g["uq_indptr"][:mm + 1],
+                                             g["uq_items"][:int(g["uq_indptr"][mm])], g["ip_indptr"][:mm + 1],
+                                             g["ip_items"][:int(g["ip_indptr"][mm])])]
+    assert int(np.diff(csr[0]).max()) > 64 and (np.diff(csr[4]) == 0).any() and (np.diff(csr[4]) > 0).any()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    err = lambda a, b: float((np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)).max())
+    for serial, chunk, reg, tol in ((1, 0, float(g["regU"]), 1e-5), (0, 32, 0.0, 1e-4)):
+        P, Q = np.zeros((mm, 16), np.float32), np.zeros((n, 16), np.float32)
+        P[:, :k], Q[:, :k] = g["P0"][:mm], g["Q0"]
+        loss, users = C.c_double(), C.c_uint64()
+        rc = lib.cune_emul_epoch(ptr(P), ptr(Q), 16, k, C.c_int64(mm), C.c_int64(n), *[ptr(a) for a in csr], C.c_uint64(int(g["seed"])),
+                                 C.c_uint32(0), C.c_double(float(g["lr"])), C.c_double(reg), C.c_double(reg), C.c_double(float(g["s"])),
+                                 serial, C.byref(loss), C.byref(users), None, C.c_int64(0), None, C.c_int64(chunk))
+        Pr, Qr = g["P0"][:mm].copy(), g["Q0"].copy()
+        ref = cune_ref.epoch(Pr, Qr, csr[0], csr[1], csr[4], csr[5], [x[:E] for x in g["kpos"][0]], [x[:E] for x in g["neg"][0]],
+                             float(g["lr"]), reg, reg, float(g["s"]))
+        assert rc == 0 and users.value == mm
+        assert err(P[:, :k], Pr) < tol and err(Q[:, :k], Qr) < tol
+        assert loss.value == pytest.approx(float(ref), rel=1e-5 if serial else 1e-3)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 def test_cune_dropin_shim_on_top_of_the_reference_tree(golden_dir, tmp_path):
     """dropin/recommender/advanced/CUNE.py shadows the reference's module (which needs gensim at import), derives from the
