@@ -5,7 +5,7 @@
 // between two barriers): the butterflies, the lane-per-event draws and their broadcast, the column ownership and the
 // cross-lane visibility rules run as written, for a warp of 8.  It checks the kernel's TEXT; the memory system, the
 // 32-lane width and the launch are what the -m gpu tests check.  Built by tests/test_zz_cune.py with g++
-// -ffp-contract=off; never loaded by the product.
+// -ffp-contract=off -fvisibility=hidden -Wl,-Bsymbolic; never loaded by the product.
 #define YUE_CUNE_HOST_EMUL 1
 #include <cmath>
 #include <cstdint>
@@ -72,7 +72,9 @@ static inline void red_row(float* p, float4 v) { atomicAdd(p, v.x); atomicAdd(p 
 
 #include "../../yue_b200/csrc/cune_sgd.cuh"
 
-extern "C" int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int64_t n, const int64_t* ev_indptr,
+// Built with -fvisibility=hidden -Wl,-Bsymbolic: libyue_b200.so, when it is loaded in the same process, exports host stubs
+// with the very names of the instantiations used here (yue::cune_sgd_kernel<1, MODE, 32>), and they must not be bound to.
+extern "C" __attribute__((visibility("default"))) int cune_emul_epoch(float* P, float* Q, int ld, int k, int64_t m, int64_t n, const int64_t* ev_indptr,
                                const int32_t* ev_items, const int64_t* uq_indptr, const int32_t* uq_items,
                                const int64_t* ip_indptr, const int32_t* ip_items, uint64_t seed, uint32_t epoch, double lr,
                                double regU, double regI, double s, int serial, double* loss_out, uint64_t* users_out,

@@ -188,7 +188,7 @@ def test_cune_kernel_text_on_the_host_reproduces_the_reference_loop(golden_dir, 
         pytest.skip("no g++")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = str(tmp_path / "libcune_emul.so")
-    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(root, "tests", "emul", "stub"),
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I" + os.path.join(root, "tests", "emul", "stub"),
                     "-o", so, os.path.join(root, "tests", "emul", "cune_emul.cpp")], check=True, capture_output=True)
     lib = C.CDLL(so)
     g = np.load(os.path.join(golden_dir, "cune_small.npz"))
@@ -263,7 +263,7 @@ def test_cune_kernel_text_as_an_eight_lane_warp_in_lockstep(golden_dir, tmp_path
         pytest.skip("no g++")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = str(tmp_path / "libcune_emul8.so")
-    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-DEMUL_LANES=8", "-shared", "-fPIC",
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-DEMUL_LANES=8", "-shared", "-fPIC", "-fvisibility=hidden", "-Wl,-Bsymbolic",
                     "-I" + os.path.join(root, "tests", "emul", "stub"), "-o", so, os.path.join(root, "tests", "emul", "cune_emul.cpp")],
                    check=True, capture_output=True)
     lib = C.CDLL(so)
@@ -298,7 +298,7 @@ def test_cune_kernel_text_at_the_device_warp_width(golden_dir, tmp_path):
         pytest.skip("no g++")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = str(tmp_path / "libcune_emul32.so")
-    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-DEMUL_LANES=32", "-shared", "-fPIC",
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++20", "-pthread", "-DEMUL_LANES=32", "-shared", "-fPIC", "-fvisibility=hidden", "-Wl,-Bsymbolic",
                     "-I" + os.path.join(root, "tests", "emul", "stub"), "-o", so, os.path.join(root, "tests", "emul", "cune_emul.cpp")],
                    check=True, capture_output=True)
     lib = C.CDLL(so)
