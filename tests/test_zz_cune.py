@@ -107,9 +107,35 @@ def test_cune_class_host_logic_reproduces_the_reference_loop(golden_dir, tmp_pat
 
 
 # ---- GPU: K8 against the golden run ------------------------------------------------------------------------------------
-# First hardware run of this kernel happens at round end (the round's GPU minutes were spent before it was written):
-# non-strict xfail so that an XPASS / XFAIL line records the outcome without gating the rest of the suite.
-_first_run = pytest.mark.xfail(strict=False, reason="K8 (cune_sgd.cuh) not yet run on hardware: round-1 GPU budget was spent")
+# Round 2, first hardware run (profiles/cune_r2.md): the serial kernel reproduced the reference loop at every width on the
+# first try; the Hogwild kernel with EVERY user of these tiny logs in flight at once (64 warps, 60 users) landed a whole
+# P[u] norm away from the serial tables -- not a fault of the kernel (one warp taking the same work items in order gives
+# the serial tables to 1e-6) but a schedule that is not a window sliding over the reference's user stream.  The C-ABI
+# now gives a small log few warps, like K2; the tests pin the Hogwild text with ONE warp (deterministic: the serial order
+# through the atomic / fast-math path, shared users published and re-read) and check many warps for sanity only.
+import contextlib
+
+
+@contextlib.contextmanager
+def _env(**kv):
+    old = {k: os.environ.get(k) for k in kv}
+    try:
+        for k, v in kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _row_err(a, b):
+    return float((np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)).max())
 
 
 def _load(engine, g):
@@ -121,7 +147,6 @@ def _load(engine, g):
 
 
 @pytest.mark.gpu
-@_first_run
 def test_cune_serial_epochs_match_the_reference_loop(engine, golden_dir):
     """Two serial-order iterations from the golden start: tables within 1e-5 relative of the reference loop's float32
     tables (north_star's serial-order tolerance; the float32 dots sum in a different order), loss within 1e-4 (the
@@ -139,25 +164,49 @@ def test_cune_serial_epochs_match_the_reference_loop(engine, golden_dir):
 
 
 @pytest.mark.gpu
-@_first_run
-def test_cune_hogwild_epoch_stays_close_to_the_serial_one(engine, golden_dir):
-    """The parallel schedule on the same draws: same events, same k and j per event, so after one iteration the tables are
-    close to the serial ones (small log, few conflicts) and the -log part of the loss agrees to a few percent."""
+@pytest.mark.parametrize("chunk", [None, 32])
+def test_cune_hogwild_kernel_in_stream_order_reproduces_the_serial_tables(engine, golden_dir, chunk):
+    """The Hogwild kernel on the golden log.  3 347 events are far below one warp's minimum share, so the C-ABI launches
+    ONE warp: the work items in stream order through the atomic path (float adds, fast sigmoid, fused multiply-adds).
+    Same draws, same order -> the serial tables to 1e-4 and the -log part of the loss to 1e-3.  With 32-event items the
+    heavy users (up to 494 events) are SHARED items: P[u] published as adds and re-read every 8 events."""
     from yue_b200.engine import MODE_HOGWILD
     g = np.load(os.path.join(golden_dir, "cune_small.npz"))
-    _load(engine, g)
-    loss = engine.cune_epoch(float(g["lr"]), 0.0, 0.0, float(g["s"]), int(g["seed"]), 0, MODE_HOGWILD)
-    P, Q = engine.get_factors()
-    assert np.isfinite(P).all() and np.isfinite(Q).all() and np.isfinite(loss) and loss > 0
-    Pr, Qr = g["P0"].copy(), g["Q0"].copy()
-    ref = cune_ref.epoch(Pr, Qr, g["ev_indptr"], g["ev_items"], g["ip_indptr"], g["ip_items"], g["kpos"][0], g["neg"][0],
-                         float(g["lr"]), 0.0, 0.0, float(g["s"]))
-    assert np.abs(P - Pr).max() < 5e-3 and np.abs(Q - Qr).max() < 5e-3
-    assert loss == pytest.approx(float(ref), rel=0.05)
+    lr, s_, seed = float(g["lr"]), float(g["s"]), int(g["seed"])
+    for regU, regI in ((0.0, 0.0), (float(g["regU"]), float(g["regI"]))):
+        _load(engine, g)
+        with _env(YUE_CUNE_CHUNK=chunk, YUE_CUNE_WARPS=None):
+            loss = engine.cune_epoch(lr, regU, regI, s_, seed, 0, MODE_HOGWILD)
+        P, Q = engine.get_factors()
+        Pr, Qr = g["P0"].copy(), g["Q0"].copy()
+        ref = cune_ref.epoch(Pr, Qr, g["ev_indptr"], g["ev_items"], g["ip_indptr"], g["ip_items"], g["kpos"][0], g["neg"][0],
+                             lr, regU, regI, s_)
+        assert _row_err(P, Pr) < 1e-4 and _row_err(Q, Qr) < 1e-4
+        if regU == 0.0:                                         # with a regulariser the two modes define the loss differently
+            assert loss == pytest.approx(float(ref), rel=1e-3)
 
 
 @pytest.mark.gpu
-@_first_run
+def test_cune_hogwild_with_every_user_in_flight_stays_sane(engine, golden_dir):
+    """64 warps forced onto the 60 users of the golden log: NOT the serial order (every user trains against tables that
+    all the others are changing), so only sanity is asserted -- finite tables, no lost padding, the epoch loss within 15 %
+    of the serial one (measured on a B200: +2.9 % whole users, +5.4 % with 32-event shared items)."""
+    from yue_b200.engine import MODE_HOGWILD
+    g = np.load(os.path.join(golden_dir, "cune_small.npz"))
+    Pr, Qr = g["P0"].copy(), g["Q0"].copy()
+    ref = cune_ref.epoch(Pr, Qr, g["ev_indptr"], g["ev_items"], g["ip_indptr"], g["ip_items"], g["kpos"][0], g["neg"][0],
+                         float(g["lr"]), 0.0, 0.0, float(g["s"]))
+    for chunk in (None, 32):
+        _load(engine, g)
+        with _env(YUE_CUNE_CHUNK=chunk, YUE_CUNE_WARPS=64):
+            loss = engine.cune_epoch(float(g["lr"]), 0.0, 0.0, float(g["s"]), int(g["seed"]), 0, MODE_HOGWILD)
+        P, Q = engine.get_factors()
+        assert np.isfinite(P).all() and np.isfinite(Q).all()
+        assert np.abs(P).max() < 2.0 and np.abs(Q).max() < 2.0
+        assert loss == pytest.approx(float(ref), rel=0.15)
+
+
+@pytest.mark.gpu
 def test_cune_refusals(engine, golden_dir):
     from yue_b200.engine import MODE_SERIAL, YueError
     g = np.load(os.path.join(golden_dir, "cune_small.npz"))
@@ -386,7 +435,6 @@ print("OK")
 
 
 @pytest.mark.gpu
-@_first_run
 @pytest.mark.parametrize("d", [64, 128, 200])
 def test_cune_serial_epoch_matches_oracle_at_bench_widths(engine, d):
     """Row widths the golden run does not have (one 16-byte chunk per lane on 16 / 32 lanes, two chunks at d = 200) on a
@@ -415,16 +463,19 @@ def test_cune_serial_epoch_matches_oracle_at_bench_widths(engine, d):
     err = lambda a, b: float((np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-12)).max())
     assert err(P, Pr) < 1e-5 and err(Q, Qr) < 1e-5
     assert loss == pytest.approx(float(ref), rel=1e-4)
-    os.environ["YUE_CUNE_CHUNK"] = "32"
-    try:
+    # the Hogwild kernel, one warp (what the C-ABI gives a log this small), heavy users cut into 32-event shared items
+    with _env(YUE_CUNE_CHUNK=32, YUE_CUNE_WARPS=None):
         engine.set_factors(P0.copy(), Q0.copy())
         lh = engine.cune_epoch(0.02, 0.0, 0.0, 2.0, 5, 0, MODE_HOGWILD)
-    finally:
-        del os.environ["YUE_CUNE_CHUNK"]
     Ph, Qh = engine.get_factors()
     Pr, Qr = P0.copy(), Q0.copy()
     ref0 = cune_ref.epoch(Pr, Qr, log.ev_indptr, log.ev_items, ip_indptr, ip_items, kp, neg, 0.02, 0.0, 0.0, 2.0)
-    # seven warps share the heaviest user (198 events): a different schedule than the serial one, second-order differences
-    assert np.isfinite(Ph).all() and np.isfinite(Qh).all()
-    assert np.abs(Ph - Pr).max() < 5e-2 and np.abs(Qh - Qr).max() < 5e-2
-    assert lh == pytest.approx(float(ref0), rel=0.1)
+    assert err(Ph, Pr) < 1e-4 and err(Qh, Qr) < 1e-4
+    assert lh == pytest.approx(float(ref0), rel=1e-3)
+    # and with all 80 users in flight on 64 warps: a different schedule, sanity only (measured: loss within 2 %)
+    with _env(YUE_CUNE_CHUNK=32, YUE_CUNE_WARPS=64):
+        engine.set_factors(P0.copy(), Q0.copy())
+        lw = engine.cune_epoch(0.02, 0.0, 0.0, 2.0, 5, 0, MODE_HOGWILD)
+    Pw, Qw = engine.get_factors()
+    assert np.isfinite(Pw).all() and np.isfinite(Qw).all()
+    assert lw == pytest.approx(float(ref0), rel=0.1)

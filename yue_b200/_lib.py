@@ -15,21 +15,53 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _sources():
+    return sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))) + [HEADER]
+
+
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for s in _sources():
+        h.update(os.path.basename(s).encode() + b"\0")
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def is_stale():
+    """True when the library was not built from the sources as they are now (compared by content -- a copy of the tree
+    to the GPU box does not keep file times in order)."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [HEADER]
-    if not force and os.path.exists(LIB_PATH) and \
-            os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
+    import fcntl
+    if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, SRC, "-ldl"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:       # ranks of one job may all find it stale at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():
+            return LIB_PATH
+        nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+        tmp = LIB_PATH + ".tmp%d" % os.getpid()
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, SRC, "-ldl"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+        os.replace(tmp, LIB_PATH)
+        with open(HASH_PATH, "w") as f:
+            f.write(_source_hash() + "\n")
     return LIB_PATH
 
 
@@ -109,10 +141,17 @@ _lib = None
 
 
 def load():
-    """Load the shared library (building it first when sources are newer and nvcc exists)."""
+    """Load the shared library.  A library that was not built from the current sources is rebuilt first when nvcc is
+    here; without a compiler it is an error -- tests and benchmarks never run against a stale library."""
     global _lib
     if _lib is not None:
         return _lib
+    nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+    if os.path.exists(LIB_PATH) and is_stale():
+        if os.path.exists(nvcc):
+            build()
+        else:
+            raise ImportError("yue_b200: %s is older than its sources and there is no nvcc to rebuild it" % LIB_PATH)
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             "yue_b200: %s is missing.  Build it with `python -c 'import __graft_entry__ as g; "

@@ -74,6 +74,9 @@ struct CuneParams {
     unsigned long long* cursor;
     double* loss;                    // [0] sum of the -log terms (+ the per-user norms in serial mode)
     unsigned long long* users_done;  // users with at least one event (parallel mode: the host scales the norms by it)
+    int skip_user_norms;             // serial mode: 1 = leave CUNE.py:174's per-user pass over both tables out of the loss
+                                     // (both regs are 0, or a schedule comparison at a size where m passes over the tables
+                                     // by one warp would take minutes: YUE_CUNE_EVENT_LOSS=1)
 };
 
 constexpr int kCuneMaxC = 2;         // 16-byte chunks per lane: ld <= 256
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(256, 2) cune_sgd_kernel(const CuneParams p) {
         }
         if (shared) pu.add_delta(pu_ptr, pu0, lane, p.ld);
         else pu.store(pu_ptr, lane, p.ld);                       // P[u] belongs to this warp alone
-        if (MODE == kSerial) {                                   // CUNE.py:174, once per user, over the whole tables
+        if (MODE == kSerial && !p.skip_user_norms) {             // CUNE.py:174, once per user, over the whole tables
             __syncwarp();                                        // the sums read columns other lanes stored (ld % 32 != 0)
             loss += p.regU * cune_frob2_warp<W>(p.P, p.m * p.ld, lane) + p.regI * cune_frob2_warp<W>(p.Q, p.n * p.ld, lane);
         }

@@ -68,4 +68,24 @@ __global__ void ingest_range_check_kernel(const int32_t* __restrict__ u, const i
         if (u[e] < 0 || u[e] >= m || it[e] < 0 || it[e] >= n) *bad = 1;
 }
 
+// Arrays handed to yue_set_interactions: every track id in [0, n) and every play row strictly increasing (the rejection
+// sampler and the ranking mask search the rows; an id outside the catalog would index Q and the counters out of bounds).
+// bad[0] |= 1: event id out of range, 2: play-row id out of range, 4: play row not sorted-unique.
+__global__ void interaction_check_kernel(const int32_t* __restrict__ ev_items, int64_t T, const int64_t* __restrict__ uq_indptr,
+                                         const int32_t* __restrict__ uq_items, int64_t nnz, int64_t m, int64_t n, int* __restrict__ bad) {
+    int flags = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t e = t0; e < T; e += stride) if (ev_items[e] < 0 || ev_items[e] >= n) flags |= 1;
+    for (int64_t x = t0; x < nnz; x += stride) if (uq_items[x] < 0 || uq_items[x] >= n) flags |= 2;
+    // row starts are the only places where uq_items[x - 1] >= uq_items[x] is allowed: clear those, then every other descent is an error
+    for (int64_t x = t0 + 1; x < nnz; x += stride) {
+        if (uq_items[x - 1] >= uq_items[x]) {
+            int64_t lo = 0, hi = m;                                  // is x the first entry of a row?  (rare path: binary search)
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (uq_indptr[mid] < x) lo = mid + 1; else hi = mid; }
+            if (!(lo <= m && uq_indptr[lo] == x)) flags |= 4;
+        }
+    }
+    if (flags) atomicOr(bad, flags);
+}
+
 }  // namespace yue

@@ -364,18 +364,24 @@ int yue_create(int device, yue_t** out) {
     yue_t* h = new yue_handle();
     h->device = device;
     cudaDeviceProp prop;
+    auto release = [&]() {                       // error paths: nothing created so far may outlive the handle
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        h->scal.release();
+        if (h->stream) cudaStreamDestroy(h->stream);
+        delete h;
+    };
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = h->scal.resize(4)) != cudaSuccess) {
         g_create_error = std::string("device setup failed: ") + cudaGetErrorString(e);
-        delete h;
+        release();
         return YUE_E_CUDA;
     }
     if (prop.major < 10) {
         g_create_error = "yue_b200 needs an sm_100a device (B200); found sm_" + std::to_string(prop.major * 10 + prop.minor);
-        cudaStreamDestroy(h->stream);
-        delete h;
+        release();
         return YUE_E_UNSUPPORTED;
     }
     h->sm_count = prop.multiProcessorCount;
@@ -448,7 +454,7 @@ int yue_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? YUE_OK : YU
 
 // second half of yue_set_interactions / yue_ingest_events: the four arrays are on the device (h->m, n, T, nnz set),
 // ev_indptr / uq_indptr are their host copies.  Validates, plans segments and work items, selects the hot tracks.
-static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t* uq_indptr) {
+static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t* uq_indptr, bool check_items) {
     const int64_t m_local = h->m, n = h->n, T = h->T;
     PhaseTimer pt;
     {   // validation on the host cores: monotone indptr; a user who played the whole catalog has no negative
@@ -492,6 +498,23 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     CK(h->seg_rec.resize(h->nseg)); CK(h->item_ptr.resize(2 * h->n_items)); CK(h->cursor.resize(1));
     if (h->nseg) CK(cudaMemcpyAsync(h->seg_rec.p, h->pin_rec.p, h->nseg * sizeof(SegRec), cudaMemcpyHostToDevice, h->stream));
     if (h->n_items) CK(cudaMemcpyAsync(h->item_ptr.p, h->pin_items.p, 2 * h->n_items * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (check_items && (T > 0 || h->nnz > 0)) {
+        // the caller's arrays (the ingest path has checked and sorted its own): ids inside the catalog, play rows sorted-unique
+        int* bad = (int*)(h->scal.p + 3);
+        CK(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
+        const int64_t work = std::max(T, h->nnz);
+        interaction_check_kernel<<<(int)std::min<int64_t>((work + 255) / 256, (int64_t)h->sm_count * 16), 256, 0, h->stream>>>(
+            h->ev_items.p, T, h->uq_indptr.p, h->uq_items.p, h->nnz, m_local, n, bad);
+        ++h->launches;
+        CK(cudaGetLastError());
+        int hbad = 0;
+        CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        REQUIRE(!(hbad & 1), YUE_E_ARG, "ev_items names a track outside [0, n)");
+        REQUIRE(!(hbad & 2), YUE_E_ARG, "uq_items names a track outside [0, n)");
+        REQUIRE(!(hbad & 4), YUE_E_ARG, "uq_items rows must be strictly increasing (sorted, unique)");
+        pt.lap("wait: uploads + id check");
+    }
     // hot tracks: device histogram of the positives, top hot_max by count on the host, then the hot
     // positives of the device copy of ev_items are re-labelled -slot-1 (see SgdParams::hot_items)
     h->n_hot = 0;
@@ -564,6 +587,10 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     REQUIRE((T == 0 || ev_items) && (nnz == 0 || uq_items), YUE_E_ARG, "null item array");
     REQUIRE(T >= 0 && nnz >= 0, YUE_E_ARG, "indptr not monotone");
     CK(cudaSetDevice(h->device));
+    // from here on the old log is gone: a failure below must not leave its plan behind for the new arrays, and tables
+    // sized for another m or n must not be indexed by the new log
+    h->have_log = false;
+    if (m_local != h->m || n != h->n) h->have_factors = false;
     if (n != h->n) h->have_delta_w = false;   // per-track weights belong to a catalog
     h->m = m_local; h->n = n; h->T = T; h->nnz = nnz; h->user_begin = user_begin; h->event_base = event_base;
     h->have_test = false;              // a new log: the held-out set of the old one no longer applies
@@ -573,7 +600,7 @@ int yue_set_interactions_shard(yue_t* h, int64_t m_local, int64_t n, int64_t use
     CK(cudaMemcpyAsync(h->uq_indptr.p, uq_indptr, (m_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     if (T) CK(cudaMemcpyAsync(h->ev_items.p, ev_items, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     if (nnz) CK(cudaMemcpyAsync(h->uq_items.p, uq_items, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    return finish_interactions(h, ev_indptr, uq_indptr);
+    return finish_interactions(h, ev_indptr, uq_indptr, true);
 }
 
 int yue_set_interactions(yue_t* h, int64_t m, int64_t n, const int64_t* ev_indptr, const int32_t* ev_items,
@@ -639,6 +666,8 @@ int yue_ingest_events(yue_t* h, int64_t m, int64_t n, int64_t E, const int32_t* 
         REQUIRE(hc[5] == 0, YUE_E_ARG, "an event names a user or track outside [0, m) x [0, n)");
     }
     const int64_t T = hc[0], Et = hc[2];
+    h->have_log = false;                       // see yue_set_interactions_shard
+    if (m != h->m || n != h->n) h->have_factors = false;
     if (n != h->n) h->have_delta_w = false;
     h->m = m; h->n = n; h->T = T; h->user_begin = 0; h->event_base = 0;
     CK(h->ev_indptr.resize(m + 1)); CK(h->uq_indptr.resize(m + 1)); CK(h->test_indptr.resize(m + 1));
@@ -690,7 +719,7 @@ int yue_ingest_events(yue_t* h, int64_t m, int64_t n, int64_t E, const int32_t* 
     CK(cudaMemcpyAsync(hev.data(), h->ev_indptr.p, (m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(huq.data(), h->uq_indptr.p, (m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    return finish_interactions(h, hev.data(), huq.data());
+    return finish_interactions(h, hev.data(), huq.data(), false);
 }
 
 int yue_interaction_sizes(yue_t* h, int64_t* m, int64_t* n, int64_t* T, int64_t* nnz, int64_t* n_test) {
@@ -1115,9 +1144,9 @@ int yue_cune_set_implicit(yue_t* h, const int64_t* ip_indptr, const int32_t* ip_
 }
 
 template <int NC>
-static cudaError_t launch_cune(const CuneParams& cp, int mode, int grid, cudaStream_t st) {
+static cudaError_t launch_cune(const CuneParams& cp, int mode, int grid, int wpc, cudaStream_t st) {
     if (mode == YUE_MODE_SERIAL) cune_sgd_kernel<NC, kSerial><<<1, 32, 0, st>>>(cp);
-    else cune_sgd_kernel<NC, kAtomic><<<grid, 256, 0, st>>>(cp);
+    else cune_sgd_kernel<NC, kAtomic><<<grid, wpc * 32, 0, st>>>(cp);
     return cudaGetLastError();
 }
 
@@ -1132,12 +1161,20 @@ int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint
     if (h->T == 0) { if (loss_out) *loss_out = 0.0; return YUE_OK; }
     if (int rc = q_rowmajor(h)) return rc;
     CK(h->cune_scal.resize(1)); CK(h->cune_ctr.resize(2));
-    // one warp per work item, 8 warps per CTA; at most two CTAs per SM so that the users in flight stay a window of the stream
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 2, (h->m + 7) / 8));
+    // One warp per work item.  Like K2 (yue_handle::min_events_per_warp) a small log gets few warps: with every user of a
+    // tiny log in flight at once the schedule is no longer a window sliding over the reference's user stream (first
+    // hardware run, profiles/cune_r2.md: 60 users on 64 warps moved P[u] of the heaviest user by 2x its norm; one warp
+    // reproduces the serial tables to 1e-6; 400 K events: 73 warps +1.1 points of Recall@10 against the serial order,
+    // 293 warps +2.4).
+    int n_warps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 16, h->T / h->min_events_per_warp));
+    if (const char* e = getenv("YUE_CUNE_WARPS")) n_warps = std::max(1, std::min(h->sm_count * 16, atoi(e)));   // tests, experiments
+    if (mode == YUE_MODE_SERIAL) n_warps = 1;
+    const int wpc = std::min(8, n_warps);
+    const int grid = (n_warps + wpc - 1) / wpc;
     {   // work items: whole users in serial order; Hogwild cuts a user above a quarter of a warp's fair share of the epoch
         int64_t chunk = 0;
         if (mode != YUE_MODE_SERIAL) {
-            chunk = std::max<int64_t>(256, std::min<int64_t>(8192, h->T / ((int64_t)grid * 8 * 4)));
+            chunk = std::max<int64_t>(256, std::min<int64_t>(8192, h->T / ((int64_t)n_warps * 4)));
             if (const char* e = getenv("YUE_CUNE_CHUNK")) chunk = std::max<int64_t>(32, atoll(e));
             chunk = (chunk + 31) / 32 * 32;
         }
@@ -1164,8 +1201,10 @@ int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint
     cp.lr = lr; cp.inv_s = 1.0 / s; cp.regU = regU; cp.regI = regI;
     cp.c_u = (float)(lr * regU); cp.c_i = (float)(lr * regI);
     cp.cursor = h->cune_ctr.p; cp.users_done = h->cune_ctr.p + 1; cp.loss = h->cune_scal.p;
-    if (h->ld <= 128) CK(launch_cune<1>(cp, mode, grid, h->stream));       // one 16-byte chunk per lane
-    else CK(launch_cune<kCuneMaxC>(cp, mode, grid, h->stream));
+    const bool event_loss = getenv("YUE_CUNE_EVENT_LOSS") != nullptr;      // the -log terms alone, in both modes (schedule comparisons)
+    cp.skip_user_norms = (regU == 0.0 && regI == 0.0) || event_loss;
+    if (h->ld <= 128) CK(launch_cune<1>(cp, mode, grid, wpc, h->stream));       // one 16-byte chunk per lane
+    else CK(launch_cune<kCuneMaxC>(cp, mode, grid, wpc, h->stream));
     ++h->launches;
     h->ilv_current = false;
     h->tc.q_dirty = true;
@@ -1174,7 +1213,7 @@ int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint
     CK(cudaMemcpyAsync(&loss, h->cune_scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&users, h->cune_ctr.p + 1, sizeof(users), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (mode != YUE_MODE_SERIAL && (regU != 0.0 || regI != 0.0)) {
+    if (mode != YUE_MODE_SERIAL && (regU != 0.0 || regI != 0.0) && !event_loss) {
         // CUNE.py:174 adds the norms after every user; a parallel schedule has no per-user table state, so the
         // end-of-epoch norms stand in for all of them
         double p2 = 0.0, q2 = 0.0;
