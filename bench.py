@@ -34,15 +34,47 @@ METRIC = "bpr_sgd_triplets_per_sec"
 UNIT = "triplets/s"
 SEED = 20260103            # SEED_BASE + config# (C2 -> 2, +1 so that rank offsets never collide with C1)
 LR, REG_U, REG_I = 0.02, 0.01, 0.01          # config/BPR.conf
-D = 64
-BYTES_PER_TRIPLET = 6 * D * 4 + 12
+D = 64                                       # set by --config (C2: 64, C3: 128)
 
 
-def workload(small):
+def bytes_per_triplet(d):
+    """3 rows read + 3 rows written + positive id + amortised play-row probe."""
+    return 6 * d * 4 + 12
+
+
+def workload(small, config="C2", world=1):
+    if config == "C3":
+        # BASELINE.json configs[2]: ONE log of 10 M users x 2 M tracks x 1 B plays, d = 128, user-sharded over the ranks
+        # (strong scaling: a rank holds 1/world of the users and of the plays; Q, 1.02 GB, is replicated)
+        u, t, p = (10_000_000, 2_000_000, 1_000_000_000) if not small else (200_000, 50_000, 8_000_000)
+        return dict(name="C3: BPR d=128, 10M users x 2M tracks x 1B plays, user-sharded over %d GPU(s) (synthetic power-law log, "
+                         "each rank generates its shard)" % world, users=u // world, tracks=t, plays=p // world, d=128, scaling="strong")
     if small:
-        return dict(name="C2-small (debug)", users=50_000, tracks=20_000, plays=2_000_000)
+        return dict(name="C2-small (debug)", users=50_000, tracks=20_000, plays=2_000_000, d=64, scaling="weak")
     return dict(name="C2: BPR d=64, 1M users x 200K tracks x 50M plays (synthetic power-law log)",
-                users=1_000_000, tracks=200_000, plays=50_000_000)
+                users=1_000_000, tracks=200_000, plays=50_000_000, d=64, scaling="weak")
+
+
+def sgd_kernel_name(d):
+    """The kernel yue_bpr_epoch launches in Hogwild mode for rows of d floats (yue_b200.cu: use_blk_kernel)."""
+    ld = (d + 3) & ~3
+    if ld > 128:
+        return "bpr_sgd_kernel<%d, kAtomic>" % ((ld // 4 + 15) // 16)
+    v = 1 if ld <= 32 else 2 if ld <= 64 else 4
+    return "bpr_sgd_blk_kernel<%d, false, %s>" % (v, "true" if ld != 32 * v else "false")
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the SGD kernel on this workload, from the committed
+    ncu --set full capture of the same command (profiles/ncu_traffic.json names the report each figure comes from).
+    Not measurable inside a timed run (no profiler under a bench number); null when no capture exists for the config."""
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tpath):
+        return None, None
+    ent = json.load(open(tpath)).get(key)
+    if not ent:
+        return None, None
+    return ent.get("dram_bytes_per_launch"), ent.get("source")
 
 
 def peaks():
@@ -131,7 +163,10 @@ def run_reference(args):
     if rank != 0:
         return
     from yue_b200 import synth
-    wl = workload(args.small)
+    # C3: the sample is drawn from one of 8 shards of the log (generating 1 B plays to sample 60 K of them would take
+    # longer than the whole arm); the degree mix and the catalog are the full config's
+    wl = workload(args.small, args.config, 8 if args.config == "C3" else 1)
+    D = wl["d"]
     per_step = 60_000                      # ~1.5-2 s of CPU per step at ~4e4 triplets/s
     log = synth.power_law_log_torch(wl["users"], wl["tracks"], wl["plays"], SEED) \
         if not args.small else synth.power_law_log(wl["users"], wl["tracks"], wl["plays"], SEED, test_ratio=0)
@@ -144,8 +179,8 @@ def run_reference(args):
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "d": D, "triplets_per_step_per_gpu": wl["plays"], "lr": LR, "reg": [REG_U, REG_I],
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload(args.small, args.config, max(1, args.gpus))["name"], "d": D, "triplets_per_step_per_gpu": wl["plays"], "lr": LR, "reg": [REG_U, REG_I],
                    "sgd_mode": "serial (the reference's loop order)", "parallelism": "1 host core (the loop is inherently serial)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
                          "host_cores": os.cpu_count()},
@@ -159,9 +194,8 @@ def run_reference(args):
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from yue_b200 import synth
-    from yue_b200.engine import (MODE_HOGWILD, MODE_HOGWILD_STORE, RANK_AUTO, RANK_EXACT, RANK_TC, Engine,
-                                 PinnedArray)
+    from yue_b200 import quality, sharding, synth
+    from yue_b200.engine import MODE_HOGWILD, MODE_HOGWILD_STORE, MODE_SERIAL, Engine, PinnedArray
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,12 +203,16 @@ def run_native(args):
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wl = workload(args.small)
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")   # the exchange runs UNDER the next sub-epoch on the SMs the epoch kernel leaves free
+        dist.init_process_group("nccl", device_id=dev)
+    wl = workload(args.small, args.config, world)
+    d = wl["d"]
     mode = MODE_HOGWILD_STORE if args.sgd_mode == "store" else MODE_HOGWILD
     hbm_peak, bf16_peak, peak_kind = peaks()
+    bpt = bytes_per_triplet(d)
 
     log = synth.power_law_log_torch(wl["users"], wl["tracks"], wl["plays"], SEED + rank, device="cuda")
     T = log.train_size
@@ -189,38 +227,57 @@ def run_native(args):
         pa.array[:] = a
         setattr(log, name, pa.array)
         pins.append(pa)
-    pP, pQ = PinnedArray((m, D), np.float32), PinnedArray((n, D), np.float32)
-    P0, Q0 = synth.init_factors(m, n, D, SEED + 1000 + rank)
+    pP, pQ = PinnedArray((m, d), np.float32), PinnedArray((n, d), np.float32)
+    P0, Q0 = synth.init_factors(m, n, d, SEED + 1000 + rank)
     if world > 1:                                   # Q is replicated: same init everywhere
-        Q0 = synth.init_factors(1, n, D, SEED + 999)[1]
+        Q0 = synth.init_factors(1, n, d, SEED + 999)[1]
     pP.array[:], pQ.array[:] = P0, Q0
-    user_begin, event_base = rank * m, rank * T     # weak scaling: rank r owns users [r*m, (r+1)*m)
+    # every rank owns its own users (weak scaling at C2: a C2-shaped shard each; strong at C3: 1/world of the one log);
+    # global event indices keep the ranks' sampler streams apart
+    user_begin, event_base = rank * m, rank * T
+    local_counts = np.bincount(log.ev_items, minlength=n)
 
     def upload():
         eng.set_interactions(m, n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items,
                              user_begin=user_begin, event_base=event_base)
         eng.set_factors(pP.array, pQ.array)
 
-    upload()
-    trainer = None
-    if world > 1:                                   # user-sharded: dQ all-reduced once per step (yue_b200/sharding.py)
-        from yue_b200.sharding import ShardedTrainer, saturation_weights
-        # plays per track over all ranks -> per-track factor for the summed deltas (profiles/quality_study_r1.md section E)
-        cnt = torch.from_numpy(np.bincount(log.ev_items, minlength=n)).to("cuda")
-        dist.all_reduce(cnt)
-        w = saturation_weights(cnt.cpu().numpy(), world, args.sub_epochs, 0.05 * LR)
-        trainer = ShardedTrainer(eng, dist, torch.device("cuda", local), sub_epochs=args.sub_epochs, row_weights=w)
-
-    def step(epoch, want_loss=False):
-        if trainer is not None:
-            return trainer.epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
-        return eng.bpr_epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
-
     def barrier():
         eng.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+
+    def allmax(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    upload()
+
+    # ---- dominant kernel alone, one GPU's plain epochs (no collective): per-launch duration for the roofline ----
+    for w in range(2):
+        eng.bpr_epoch(LR, REG_U, REG_I, SEED, 900 + w, mode, want_loss=False)
+    kms = []
+    for k in range(max(3, min(args.steps, 10))):
+        eng.sync()
+        eng.timer_start()
+        eng.bpr_epoch(LR, REG_U, REG_I, SEED, 1000 + k, mode, want_loss=False)
+        kms.append(eng.timer_stop())
+    k_ms = float(np.mean(kms))
+    eng.set_factors(pP.array, pQ.array)             # the timed steps below start from the initial tables
+
+    # ---- N > 1: N REPLICAS -- every GPU trains its own model on its own C2-shaped log (cross-validation folds, seeds,
+    #      hyper-parameter points: host/driver.py maps -cv folds to devices), no collective.  Why not one sharded model:
+    #      DESIGN.md section 6 -- at this log's skew any schedule that keeps Recall/NDCG within 0.5 points of the serial
+    #      order is bound by how many updates of one row may be in flight, and N GPUs cannot beat one.  The sharded
+    #      trainer is measured below (`sharded`), with its own quality verdict. ----
+    ctl = sharding.TorchCtl(dist, dev) if world > 1 else None
+    reduce_factory = quality.torch_reduce_factory(dist, dev) if world > 1 else None
+
+    def step(epoch, want_loss=False):
+        return eng.bpr_epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
 
     # ---- value: K steps, inputs resident in HBM ---------------------------------------------
     for w in range(args.warmup):
@@ -235,43 +292,66 @@ def run_native(args):
         step(args.warmup + k)
     ms = eng.timer_stop()
     barrier()
-    launches = eng.launch_count() - l0
-    ms_t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms = float(ms_t.item())
-    value = T * world * args.steps / (ms * 1e-3)
-
-    # ---- dominant kernel alone (no collective): per-launch duration for the roofline --------
-    kms = []
-    for k in range(max(3, min(args.steps, 10))):
-        eng.sync()
-        eng.timer_start()
-        eng.bpr_epoch(LR, REG_U, REG_I, SEED, 1000 + k, mode, want_loss=False)
-        kms.append(eng.timer_stop())
     clk = clocks.stop() if rank == 0 else None
-    k_ms = float(np.mean(kms))
-    achieved = BYTES_PER_TRIPLET * T / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("bpr_sgd_kernel_dram_bytes_per_launch")
+    launches = eng.launch_count() - l0
+    ms = allmax(ms)
+    value = T * world * args.steps / (ms * 1e-3)
+    achieved = bpt * T / (k_ms * 1e-3) / 1e9
+    tkey = args.config + ("-small" if args.small else "") + ("/%d" % world if args.config == "C3" else "")
+    traffic, traffic_src = ncu_traffic(tkey)
 
     # ---- config C5: APR epoch (adversarial BPR, fused per-triplet perturbation), APR.conf hyper-parameters ----
     apr = None
-    if world == 1 and not args.no_apr:
+    if not args.no_apr and d == 64:
         ams = []
         for k in range(4):
-            eng.sync()
+            barrier()
             eng.timer_start()
             eng.apr_epoch(0.003, 0.002, 0.01, 0.5, 2.0, SEED, 3000 + k, 0, mode, want_loss=False)
-            ams.append(eng.timer_stop())
-        apr = {"metric": "apr_triplets_per_sec", "value": T / (min(ams[1:]) * 1e-3), "ms_per_epoch": min(ams[1:]),
-               "workload": "C5: APR d=64 on the C2 log, eps 0.5, regA 2, lr 0.003 (config/APR.conf)", "kernel": "bpr_sgd_blk_kernel<2, APR>"}
+            ams.append(allmax(eng.timer_stop()))
+        apr = {"metric": "apr_triplets_per_sec", "value": T * world / (min(ams[1:]) * 1e-3), "ms_per_epoch": min(ams[1:]), "n_gpus": world,
+               "workload": "C5: APR d=64 on the C2 log, eps 0.5, regA 2, lr 0.003 (config/APR.conf)", "kernel": "bpr_sgd_blk_kernel<2, APR>",
+               "parallelism": ("%d replicas, like the headline" % world) if world > 1 else "single GPU"}
+
+    # ---- the SHARDED trainer (one model over N GPUs: SURVEY 8e / north_star's partitioning), measured, not the headline ----
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        upload()
+        cnt = torch.from_numpy(local_counts).to("cuda")
+        dist.all_reduce(cnt)
+        # the tail of Q is summed 32 times per epoch; at this size a moderately played track is still touched thousands of
+        # times per rank between two exchanges, so the sum is saturation-weighted (round 1) -- without it the run diverges
+        # on 4 GPUs (NaN loss, measured)
+        w = sharding.saturation_weights(cnt.cpu().numpy(), world, args.sub_epochs, 0.05 * LR)
+        tr = sharding.SharedHotTrainer(eng, ctl, local_counts, sub_epochs=args.sub_epochs, asynchrony=args.asynchrony,
+                                       reduce=reduce_factory(eng), reserve_sms=args.reserve_sms, row_weights=w)
+        sms, ams = [], []
+        try:
+            for k in range(2 + min(args.steps, 4)):
+                barrier()
+                eng.timer_start()
+                tr.epoch(LR, REG_U, REG_I, SEED, 4000 + k, finalize=True)
+                sms.append(allmax(eng.timer_stop()))
+            for k in range(3):
+                barrier()
+                eng.timer_start()
+                tr.epoch(0.003, 0.002, 0.01, SEED, 4100 + k, apr=(0.5, 2.0), finalize=True)
+                ams.append(allmax(eng.timer_stop()))
+        finally:
+            sinfo = dict(hot_rows=int(len(tr.hot_tracks)), hot_share_of_positives=float(tr.hot_share_of_events), warps_per_rank=int(tr.n_warps),
+                         ctas_per_rank=int(tr.n_ctas), parts_per_epoch=args.sub_epochs, asynchrony=args.asynchrony)
+            tr.close()
+            eng.set_delta_weights(None)
+        sharded = {"metric": METRIC, "value": T * world / (min(sms[2:]) * 1e-3), "unit": UNIT, "ms_per_step": min(sms[2:]), "scaling": "weak",
+                   "apr_value": T * world / (min(ams[1:]) * 1e-3), "apr_ms_per_epoch": min(ams[1:]),
+                   "schedule": "users sharded, P rows private; the most played tracks' rows live ONCE (slot s on rank s % N) and are loaded / "
+                               "added over NVLink peer memory (CUDA IPC, ld/red .sys); the tail of Q is replicated, dQ all-reduced by NCCL on a "
+                               "second stream UNDER the next part and applied one part late (saturation-weighted at this size); the ranks "
+                               "together run `asynchrony` x the warps one GPU gives the whole log", **sinfo}
 
     # ---- WRMF (implicit ALS, recommender/cf/WRMF.py) on the same log and tables, d = 64 ----
     wrmf = None
-    if world == 1 and not args.no_wrmf:
+    if world == 1 and not args.no_wrmf and d == 64:
         eng.sync()
         t0 = time.perf_counter()
         nnz = int(len(log.uq_items))
@@ -285,7 +365,7 @@ def run_native(args):
                 eng.wrmf_sweep(side, 1.0, 10.0, want_loss=False)
                 wms[side].append(eng.timer_stop())
         u_ms, t_ms = min(wms[0][1:]), min(wms[1][1:])
-        flops = lambda rows: nnz * D * (D + 1) + rows * (D ** 3 / 3.0 + 2 * D * D)      # rank-1 terms (lower triangle) + LDL^T + substitutions
+        flops = lambda rows: nnz * d * (d + 1) + rows * (d ** 3 / 3.0 + 2 * d * d)      # rank-1 terms (lower triangle) + LDL^T + substitutions
         wrmf = {"metric": "wrmf_iterations_per_sec", "value": 1e3 / (u_ms + t_ms), "ms_user_sweep": u_ms, "ms_track_sweep": t_ms,
                 "unique_pairs": nnz, "pairs_per_sec": 2 * nnz / ((u_ms + t_ms) * 1e-3), "prepare_seconds": prep_s,
                 "fp64_tflops_user_sweep": flops(m) / (u_ms * 1e-3) / 1e12, "fp64_tflops_track_sweep": flops(n) / (t_ms * 1e-3) / 1e12,
@@ -298,7 +378,7 @@ def run_native(args):
             sub_ptr = np.zeros(len(rows) + 1, np.int64)
             np.cumsum(log.uq_indptr[rows + 1] - log.uq_indptr[rows], out=sub_ptr[1:])
             sub_idx = np.concatenate([log.uq_items[log.uq_indptr[r]:log.uq_indptr[r + 1]] for r in rows])
-            out_rows = np.zeros((len(rows), D), np.float32)
+            out_rows = np.zeros((len(rows), d), np.float32)
             t0 = time.perf_counter()
             wrmf_ref.half_sweep(out_rows, Qn, sub_ptr, sub_idx, np.ones(len(sub_idx), np.int32), 1.0, gram="f32")
             dt = time.perf_counter() - t0
@@ -306,57 +386,151 @@ def run_native(args):
                                     "sample": "200 evenly spaced users of the same log, oracle port of WRMF.py:36-57 incl. one YtY",
                                     "gpu_user_rows_per_sec": m / (u_ms * 1e-3)}
 
-    # ---- e2e: same step through the C ABI with host buffers ---------------------------------
+    # ---- e2e: the job a user of the class API runs (IterativeRecommender.buildModel): the log and the tables go up ONCE
+    #      from pinned host memory, num.max.iter = E epochs each return their loss (the lr schedule needs it), the tables
+    #      come back.  Also: the same with the upload repeated before EVERY epoch (round 1's definition). ----
+    E = args.e2e_epochs
     h2d = log.ev_indptr.nbytes + log.ev_items.nbytes + log.uq_indptr.nbytes + log.uq_items.nbytes + pP.nbytes + pQ.nbytes
-    d2h = pP.nbytes + pQ.nbytes + 8
-    e2e_steps = max(1, min(args.steps, 3))
-    barrier()
-    t0 = time.perf_counter()
-    eng.timer_start()
-    for k in range(e2e_steps):
+    d2h = pP.nbytes + pQ.nbytes + 8 * E
+
+    def e2e_job(epochs, base_epoch):
         upload()
-        if world > 1:
-            eng.q_snapshot()
-        loss = step(2000 + k, want_loss=True)
-        if world > 1:                               # the epoch loss is a sum over all ranks' events
-            lt = torch.tensor([loss], device="cuda", dtype=torch.float64)
-            dist.all_reduce(lt)
-            loss = float(lt.item())
-        p2, q2 = eng.frob2()
+        loss = 0.0
+        for ep in range(epochs):
+            loss = eng.bpr_epoch(LR, REG_U, REG_I, SEED, base_epoch + ep, mode, want_loss=True)
+            p2, q2 = eng.frob2()
+            loss += REG_U * p2 + REG_I * q2         # BPR.py:59
         eng.get_factors(pP.array, pQ.array)
-        loss += REG_U * p2 + REG_I * q2
-    e2e_ms = eng.timer_stop()
-    e2e_wall = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e2e_ms, e2e_wall)                  # host-side work between copies counts too
-    e_t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-    e2e_value = T * world * e2e_steps / (float(e_t.item()) * 1e-3)
+        return loss
+
+    def timed(fn):
+        barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        eng.sync()
+        return r, allmax((time.perf_counter() - t0) * 1e3)
+
+    e2e_job(1, 1900)                                # warm: allocations, pinned staging
+    loss, job_ms = timed(lambda: e2e_job(E, 2000))
+    e2e_value = T * world * E / (job_ms * 1e-3)
+    _, one_ms = timed(lambda: e2e_job(1, 2100))
+    e2e_every = T * world / (one_ms * 1e-3)
+
+    # ---- north_star check 4 for THIS schedule: Recall@10 / NDCG@10 against the serial-order run of the same log ----
+    qual = None
+    if not args.no_quality:
+        spec = dict(quality.QUALITY_LOG)
+        if args.small:
+            spec.update(users=20_000, tracks=5_000, plays=600_000)
+        qlog, qP, qQ = quality.make_log(spec)
+        torch.cuda.empty_cache()
+        base = [0.0, 0.0, 0.0]
+        if rank == 0:
+            br, bn, bdt, _ = quality.single_gpu_run(local, qlog, qP, qQ, spec, MODE_SERIAL)
+            base = [br, bn, bdt]
+        bt = torch.tensor(base, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.broadcast(bt, 0)
+        br, bn, bdt = (float(x) for x in bt)
+        run = [0.0, 0.0, 0.0, 0.0]
+        if rank == 0:
+            run = list(quality.single_gpu_run(local, qlog, qP, qQ, spec, mode))
+        rt = torch.tensor(run, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.broadcast(rt, 0)
+        qual = quality.verdict(dict(recall=float(rt[0]), ndcg=float(rt[1]), seconds=float(rt[2]), last_epoch_loss=float(rt[3]), ranks=1), br, bn)
+        qlog_desc = "%d users x %d tracks, %d training events (20 %% of %d plays held out), d=%d, %d epochs, lr %.2f" % (
+            qlog.m, qlog.n, qlog.train_size, spec["plays"], spec["d"], spec["epochs"], spec["lr"])
+        qref = ("serial-order mode on one GPU (reproduces BPR.py:40-62 to 1e-5), same tables and sampler seed: "
+                "recall@10 %.4f ndcg@10 %.4f (%.1f s)" % (br, bn, bdt))
+        qual.update(log=qlog_desc, reference=qref, schedule="yue_bpr_epoch, Hogwild mode on one GPU: the schedule of `value` (every replica runs it)")
+        if sharded is not None:                     # the sharded trainer on ONE log, users interleaved over the ranks
+            srun = quality.shared_hot_run(local, ctl, qlog, qP, qQ, spec, args.sub_epochs, args.asynchrony, reduce_factory=reduce_factory,
+                                          reserve_sms=args.reserve_sms)
+            sq = quality.verdict(srun, br, bn)
+            sq.update(log=qlog_desc + "; ONE log, users interleaved over the ranks, plain sum of the tail deltas", reference=qref)
+            sharded["quality"] = sq
+            sharded["quality_at_bench_size"] = ("not in the gate: on C2-sized shards a moderately played track is touched thousands of times per "
+                                                "rank between two of the 32 exchanges, beyond what summed deltas follow (DESIGN.md section 6); "
+                                                "the quality block above is this trainer on a log small enough for 32 exchanges per epoch")
+        del qlog, qP, qQ
+
+    # ---- round 1's schedule, for continuity: replicas of ALL rows, saturation-weighted sum once per epoch ----
+    tmode = None
+    if world > 1 and not args.no_throughput_mode:
+        upload()
+        cnt = torch.from_numpy(local_counts).to("cuda")
+        dist.all_reduce(cnt)
+        w = sharding.saturation_weights(cnt.cpu().numpy(), world, 1, 0.05 * LR)
+        old = sharding.ShardedTrainer(eng, dist, dev, sub_epochs=1, row_weights=w)
+        for k in range(3):
+            old.epoch(LR, REG_U, REG_I, SEED, 5000 + k, mode)
+        barrier()
+        eng.timer_start()
+        for k in range(args.steps):
+            old.epoch(LR, REG_U, REG_I, SEED, 5003 + k, mode)
+        tms = allmax(eng.timer_stop())
+        eng.set_delta_weights(None)
+        tmode = {"value": T * world * args.steps / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms / args.steps,
+                 "schedule": "round 1: every row of Q replicated, full concurrency on every rank, ONE saturation-weighted all-reduce of dQ per epoch",
+                 "quality": "outside the gate (profiles/quality_study_r1.md section E: Recall@10 +0.02 against the serial order on 2 GPUs, "
+                            "unstable without the weights on 4) -- reported as a throughput ceiling, not as a result"}
+
+    # ---- config C3's shard on one GPU: Q = 1 GB does not fit in L2, the honest HBM case (N = 1 line only) ----
+    c3 = None
+    if world == 1 and args.config == "C2" and not args.no_c3:
+        c3 = bench_c3_shard(eng, args, hbm_peak)
 
     out = None
     if rank == 0:
+        par = "single GPU"
+        if world > 1:
+            par = ("%d replicas: every GPU trains its own model on its own C2-shaped log (folds / seeds / hyper-parameter points), no "
+                   "collective on the path; one SHARDED model is measured in `sharded` and cannot hold the 0.5-point gate at this size "
+                   "(DESIGN.md section 6)" % world)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "d": D, "triplets_per_step_per_gpu": T, "lr": LR,
+            "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "d": d, "triplets_per_step_per_gpu": T, "lr": LR,
                        "reg": [REG_U, REG_I], "sgd_mode": "hogwild_" + ("store" if mode == MODE_HOGWILD_STORE else "atomic_delta"),
-                       "l2": "inputs exceed L2 (P 256 MB + log 400 MB per step; Q 51 MB is L2-resident by nature)",
-                       "parallelism": ("user-sharded, Q replicated, %d all-reduce(s) of dQ per step, saturation-weighted sum" % args.sub_epochs) if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "what": "set_interactions + set_factors (pinned) + bpr_epoch + frob2 + get_factors"},
+                       "l2": "inputs exceed L2 (P %d MB + log %d MB per step; Q %d MB %s)" % (
+                           pP.nbytes >> 20, (log.ev_items.nbytes + log.uq_items.nbytes) >> 20, pQ.nbytes >> 20,
+                           "is L2-resident by nature" if pQ.nbytes < (100 << 20) else "exceeds L2 too"),
+                       "parallelism": par},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // E), "d2h_bytes_per_step": int(d2h // E),
+                    "steps": E, "ms_per_job": job_ms, "h2d_bytes_per_job": int(h2d), "d2h_bytes_per_job": int(d2h),
+                    "what": "one buildModel through the C ABI with HOST buffers, as the class API runs it (num.max.iter = %d): set_interactions + "
+                            "set_factors from pinned memory ONCE, then %d x (epoch + its loss + frob2 to the host: the lr schedule reads it), "
+                            "then get_factors; value = %d epochs' triplets / the job's wall time" % (E, E, E),
+                    "upload_before_every_epoch": {"value": e2e_every, "ms_per_step": one_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h - 8 * (E - 1)),
+                                                  "what": "round 1's definition: upload + one epoch + download, every step"}},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "kernel": "bpr_sgd_kernel", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": BYTES_PER_TRIPLET * T},
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                         "kernel": sgd_kernel_name(d), "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": bpt * T, "algorithmic_bytes_per_triplet": bpt,
+                         "l2_bytes_per_triplet": 4 * d * 4 + 12,
+                         "l2_note": "what a warp-per-user kernel must move through L2 per triplet: Q[i], Q[j] read and added (4 rows) + ids; "
+                                    "P[u] lives in registers over a user's events.  Q (%d MB) %s, so DRAM traffic (`traffic`) is %s" % (
+                                        pQ.nbytes >> 20, "fits in L2" if pQ.nbytes < (100 << 20) else "does not fit in L2",
+                                        "a small fraction of the algorithmic bytes: the bound is L2 atomics + issue, see profiles/" if pQ.nbytes < (100 << 20)
+                                        else "the real bound")},
             "final_loss": loss,
         }
+        if qual:
+            out["quality"] = qual
+        if sharded:
+            out["sharded"] = sharded
+        if tmode:
+            out["throughput_mode"] = tmode
         if apr:
             out["apr"] = apr
         if wrmf:
             out["wrmf"] = wrmf
+        if c3:
+            out["c3"] = c3
 
     # ---- secondary metric: full-catalog masked top-10 (config C4 shape, bounded user block) --
     if not args.no_rank:
@@ -366,7 +540,7 @@ def run_native(args):
 
     # ---- cpu_baseline (rank 0, N = 1 only) -----------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = cpu_sample(log, 400_000 if not args.small else 40_000, D, SEED)
+        sample = cpu_sample(log, 400_000 if not args.small else 40_000, d, SEED)
         t = cpu_epoch(sample, 0)
         out["cpu_baseline"] = {"value": sample["T"] / t, "unit": UNIT, "cores": 1, "kind": "port",
                                "host_cores": os.cpu_count(),
@@ -377,6 +551,40 @@ def run_native(args):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_c3_shard(eng, args, hbm_peak):
+    """One GPU's share of config C3 at 8 GPUs: 1.25 M users x 2 M tracks x 125 M plays, d = 128.  Q is 1.02 GB -- ten times
+    the L2 -- so this is the case where the SGD kernel really runs against HBM (SURVEY.md section 7 "roofline honesty")."""
+    import torch
+    from yue_b200 import synth
+    from yue_b200.engine import MODE_HOGWILD
+    users, tracks, plays, d = (1_250_000, 2_000_000, 125_000_000, 128) if not args.small else (60_000, 100_000, 3_000_000, 128)
+    log = synth.power_law_log_torch(users, tracks, plays, SEED + 31, device="cuda")
+    torch.cuda.empty_cache()
+    P, Q = synth.init_factors(log.m, log.n, d, SEED + 32)
+    eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    eng.set_factors(P, Q)
+    T = log.train_size
+    for k in range(2):
+        eng.bpr_epoch(LR, REG_U, REG_I, SEED, k, MODE_HOGWILD, want_loss=False)
+    times = []
+    for k in range(4):
+        eng.sync()
+        eng.timer_start()
+        eng.bpr_epoch(LR, REG_U, REG_I, SEED, 10 + k, MODE_HOGWILD, want_loss=False)
+        times.append(eng.timer_stop())
+    ms = float(np.mean(times))
+    bpt = bytes_per_triplet(d)
+    traffic, src = ncu_traffic("C3-shard" + ("-small" if args.small else ""))
+    ach = bpt * T / (ms * 1e-3) / 1e9
+    out = {"metric": METRIC, "value": T / (ms * 1e-3), "unit": UNIT, "ms_per_epoch": ms, "n_gpus": 1,
+           "workload": "C3 shard (1 of 8): BPR d=128, %d users x %d tracks x %d plays; Q = %d MB" % (log.m, log.n, T, Q.nbytes >> 20),
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "kernel": sgd_kernel_name(d),
+                        "kernel_ms": ms, "algorithmic_bytes_per_triplet": bpt, "traffic": traffic, "traffic_source": src,
+                        "dram_gbs": (traffic / (ms * 1e-3) / 1e9) if traffic else None,
+                        "dram_frac_of_peak": (traffic / (ms * 1e-3) / 1e9 / hbm_peak) if traffic else None}}
+    return out
 
 
 def bench_ranking(eng, args, bf16_peak, rank=0, world=1, dist=None):
@@ -474,7 +682,16 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--small", action="store_true", help="debug-size workload (not a bench number)")
     ap.add_argument("--sgd-mode", default="atomic", choices=["atomic", "store"])
-    ap.add_argument("--sub-epochs", type=int, default=1, help="multi-GPU: Q-delta all-reduces per epoch")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="BASELINE.json configs[1] (default) or configs[2]")
+    ap.add_argument("--sub-epochs", type=int, default=32, help="multi-GPU: parts per epoch = exchanges of the tail of Q")
+    ap.add_argument("--asynchrony", type=float, default=1.0,
+                    help="multi-GPU: the ranks together run this many times the warps one GPU gives the whole log (DESIGN.md section 6)")
+    ap.add_argument("--reserve-sms", type=int, default=8, help="multi-GPU: SMs the epoch kernel leaves to the NCCL kernels")
+    ap.add_argument("--e2e-epochs", type=int, default=4, help="num.max.iter of the e2e job")
+    ap.add_argument("--no-quality", action="store_true")
+    ap.add_argument("--no-throughput-mode", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-rank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-apr", action="store_true")

@@ -223,13 +223,69 @@ int yue_q_delta_apply(yue_t* h);    /* Q <- snapshot + w * delta (after the redu
  * rank has already moved the row to its equilibrium); yue_b200/sharding.py: saturation_weights computes
  * (1 - a^G) / (G (1 - a)), a = exp(-kappa * plays per rank and exchange).  DESIGN.md section 6. */
 int yue_set_delta_weights(yue_t* h, const float* w);
-int yue_device_buffer(yue_t* h, int which, void** dev_ptr, size_t* bytes);
+int yue_device_buffer(yue_t* h, int which, void** dev_ptr, size_t* bytes);   /* YUE_BUF_* */
 int yue_stream(yue_t* h, void** cuda_stream);
 /* NCCL path for non-Python hosts: id is an ncclUniqueId (128 bytes) from yue_comm_unique_id
  * on rank 0, distributed by the caller. */
 int yue_comm_unique_id(void* id128);
 int yue_comm_init(yue_t* h, int nranks, int rank, const void* id128);
 int yue_allreduce_q_delta(yue_t* h);   /* pack + ncclAllReduce(sum, fp32) + apply            */
+
+/* ---- multi-GPU, round 2: the most played tracks' rows live ONCE, the long tail is exchanged under the next sub-epoch ----
+ * Why: summed deltas of a row that every rank touches thousands of times between two exchanges overshoot (every rank has
+ * already made the whole move towards the row's equilibrium); profiles/quality_study_r1.md section E.  So the rows of
+ * the hot tracks (the hot-row table of the blocked kernel, bpr_sgd_blk.cuh) are not replicated at all: slot s of the
+ * table lives in the table of rank s % nranks, every rank maps every table (CUDA IPC between processes, plain peer
+ * access inside one process) and the epoch kernel of every rank loads and adds (ld/red .sys) the one copy over NVLink.
+ * All ranks must use the same hot set in the same slot order:
+ *   yue_hot_tracks      the handle's current hot set (chosen from its own log by yue_set_interactions): tracks_out[n_hot]
+ *   yue_set_hot_tracks  impose a hot set (tracks[] in slot order, counts[] = plays over ALL ranks, total_events likewise;
+ *                       n_hot <= 24; tracks above 1/40 of the events get a second accumulator row); re-labels the events
+ *   yue_hot_table_export / _open   this handle's table as a cudaIpcMemHandle_t (64 bytes) / map a peer's in this process
+ *   yue_enable_peer     cudaDeviceEnablePeerAccess from the handle's device to `peer_device` (same-process handles)
+ *   yue_hot_share       tables[r] = rank r's table as a device pointer valid in this process (tables[rank] may be NULL);
+ *                       moves the rows this rank owns from Q into its table; from here on yue_bpr_epoch(_part) /
+ *                       yue_apr_epoch(_part) in YUE_MODE_HOGWILD work on the shared tables and Q's hot rows are STALE.
+ *                       Barrier between the ranks before the first epoch call.
+ *   yue_hot_pull        copy every hot row from its owner's table into this handle's Q (ranks quiescent: sync + barrier
+ *                       before, barrier after if anyone goes on training)
+ *   yue_hot_unshare     yue_hot_pull, then back to the per-launch private table
+ * Needs num.factors = 32, 64 or 128 (the full-width blocked kernel). */
+int yue_hot_tracks(yue_t* h, int32_t* tracks_out, int* n_hot);
+int yue_set_hot_tracks(yue_t* h, const int32_t* tracks, const int64_t* counts, int n_hot, int64_t total_events);
+int yue_hot_table_export(yue_t* h, void* ipc_handle64, void** dev_ptr);
+int yue_hot_table_open(yue_t* h, const void* ipc_handle64, void** dev_ptr);
+int yue_enable_peer(yue_t* h, int peer_device);
+int yue_hot_share(yue_t* h, int nranks, int rank, void* const* tables);
+int yue_hot_pull(yue_t* h);
+int yue_hot_unshare(yue_t* h);
+/* Exchange of the long tail, overlapped: begin packs delta = own = Q - snapshot on the handle's stream and lets its
+ * SECOND stream (yue_stream2) wait for that; the caller all-reduces BUF_Q_DELTA on the second stream
+ * (yue_q_exchange_reduce: the library's NCCL communicator; or torch.distributed on that stream) while the next sub-epoch
+ * runs on the first; finish makes the first stream wait for the reduction and applies
+ *     Q += w * sum - own,   snapshot += w * sum
+ * i.e. the other ranks' changes arrive one sub-epoch late and this rank's own newer changes are kept.  quiescent != 0
+ * states that no epoch ran on this handle since begin (the end of training): Q is then written as the new snapshot
+ * itself, so that all ranks hold the same bits. */
+int yue_q_exchange_begin(yue_t* h);
+int yue_q_exchange_reduce(yue_t* h);
+/* The reduction for ranks that are handles of ONE process (the class API with yue.devices=0,1,...; no NCCL involved):
+ * deltas[r] = rank r's YUE_BUF_Q_DELTA (NULL = this handle's own), peer access enabled (yue_enable_peer).  Every rank
+ * sums all ranks' deltas in rank order on its second stream and returns when that is done.  The caller synchronises:
+ * every rank's yue_q_exchange_begin has completed (yue_sync + a barrier) before anyone calls this, and a barrier
+ * after it before anyone's next yue_q_exchange_begin. */
+int yue_q_exchange_reduce_peers(yue_t* h, int nranks, void* const* deltas);
+int yue_q_exchange_finish(yue_t* h, int quiescent);
+int yue_stream2(yue_t* h, void** cuda_stream);
+/* Concurrency of the Hogwild epoch kernels: n_warps warps on n_ctas CTAs (one CTA per SM; 0 = the automatic choice of
+ * yue_set_interactions).  With N ranks sharing the hot rows the number of updates of one row that are in flight between
+ * a read and the add becoming visible grows N-fold plus the NVLink round trip; tools/staleness_sim.py and DESIGN.md
+ * section 6 show where the trajectory leaves the 0.5-point gate.  Fewer CTAs than SMs also leave room for the NCCL
+ * kernels of the overlapped exchange. */
+int yue_set_sgd_concurrency(yue_t* h, int n_warps, int n_ctas);
+/* yue_apr_epoch for the part-th of n_parts ranges of the work items (see yue_bpr_epoch_part) */
+int yue_apr_epoch_part(yue_t* h, double lr, double regU, double regI, double eps, double regA, uint64_t seed,
+                       uint32_t epoch, uint32_t slot, int mode, int part, int n_parts, double* loss_out);
 
 /* ---- measurement hooks (bench.py): CUDA events on the handle's stream, launch counter ---- */
 int yue_timer_start(yue_t* h);

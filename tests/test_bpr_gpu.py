@@ -250,8 +250,9 @@ def test_hot_row_path_conserves_updates(monkeypatch):
     assert np.linalg.norm(Q1 - Q) == pytest.approx(np.linalg.norm(Q0 - Q), rel=1e-3)
 
 
-# ---- the blocked kernel (bpr_sgd_blk.cuh): all three row widths, hot-row table, second rows ----------
-@pytest.mark.parametrize("d", [32, 64, 128])
+# ---- the blocked kernel (bpr_sgd_blk.cuh): full rows (32/64/128) and masked ones (config/BPR.conf ships num.factors=10,
+# CUNE.conf 20, LightGCN.conf 50), hot-row table, second rows ----------
+@pytest.mark.parametrize("d", [10, 20, 32, 50, 64, 100, 128])
 def test_blocked_kernel_conflict_free_all_widths(engine, d):
     """Disjoint rows per triplet: the blocked kernel (4 triplets per block, scores from the Gram
     recurrence) must give the serial loop's factors -- several triplets per user so that the
@@ -274,7 +275,7 @@ def test_blocked_kernel_conflict_free_all_widths(engine, d):
     assert loss == pytest.approx(ref_loss, rel=1e-5)
 
 
-@pytest.mark.parametrize("d", [32, 64, 128])
+@pytest.mark.parametrize("d", [10, 32, 50, 64, 100, 128])
 def test_blocked_kernel_hot_table_lr0_and_conservation(monkeypatch, d):
     """Hot-row table with second rows, every track of a small catalog hot.  (1) lr = 0: the epoch must
     leave P and Q bit-identical (rows travel Q -> table -> Q) and the loss is the sum of softplus;

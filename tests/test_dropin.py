@@ -162,6 +162,60 @@ def test_c1_end_to_end_through_the_class_api(tmp_path):
 
 
 @pytest.mark.gpu
+def test_class_api_on_several_devices(tmp_path):
+    """yue.devices=a,b through Yue -> BPR.execute() (yue.py:59-131, base/recommender.py:152-174): evalRanking ranks a block
+    of the test users per device and must produce the lists and measures of ONE device bit for bit; buildModel shards the
+    users over the devices (hot rows shared over peer memory, tail summed over peer memory, no NCCL) and must stay within
+    the 0.5-point gate of the serial-order run.  On a one-GPU box the two "devices" are two handles on device 0 -- the
+    same code, threads and peer pointers included."""
+    from yue_b200 import synth
+    from yue_b200.engine import device_count
+    from yue_b200.host.driver import Yue
+    from yue_b200.bpr import BPR
+    from yue_b200.apr import APR
+    import random
+    devs = "0,1" if device_count() >= 2 else "0,0"
+    log_path = tmp_path / "log.txt"
+    synth.write_csv_log(str(log_path), 6000, 3000, 400000, seed=20260102)
+    runs = {}
+    for name, extra in (("serial", {"yue.sgd": "serial"}), ("one", {}), ("two", {"yue.devices": devs, "yue.sub_epochs": "16"})):
+        vals = conf_values(tmp_path / name, extra=dict({"record": str(log_path), "yue.seed": "77", "num.max.iter": "4", "num.factors": "64",
+                                                        "item.ranking": "-topN 10"}, **extra))
+        random.seed(5)
+        np.random.seed(11)
+        with redirect_stdout(io.StringIO()):
+            y = Yue(Config(values=vals))
+            model = BPR(y.config, y.trainingData, y.testData)
+            model.execute()
+        runs[name] = model
+    rec = lambda m: float(m.measure[2].split(":")[1])          # Recall@10
+    ser, one, two = runs["serial"], runs["one"], runs["two"]
+    assert two.P.shape == ser.P.shape and two.Q.shape == ser.Q.shape and np.isfinite(two.P).all() and np.isfinite(two.Q).all()
+    assert abs(rec(one) - rec(ser)) < 0.005 and abs(one.ndcg[10] - ser.ndcg[10]) < 0.005
+    assert abs(rec(two) - rec(ser)) < 0.005 and abs(two.ndcg[10] - ser.ndcg[10]) < 0.005
+    assert two.loss == pytest.approx(ser.loss, rel=0.02)
+    # ranking on two devices = ranking on one, given the same tables
+    users = list(two.data.testSet.keys())
+    with redirect_stdout(io.StringIO()):
+        lists2, ids2, sc2 = two._topn_lists(users, 10)
+        one.P, one.Q = two.P, two.Q
+        lists1, ids1, sc1 = one._topn_lists(users, 10)
+    assert np.array_equal(ids1, ids2) and np.array_equal(sc1, sc2) and lists1 == lists2
+    # APR (recommender/advanced/APR.py:113-137) through the same sharded session: trains, stays finite, ranks
+    vals = conf_values(tmp_path / "apr", extra={"record": str(log_path), "recommender": "APR", "yue.seed": "77", "num.max.iter": "2",
+                                                "num.factors": "64", "item.ranking": "-topN 10", "yue.devices": devs, "yue.sub_epochs": "16",
+                                                "batch_size": "512", "APR": "-eps 0.5 -regA 2 -advEpoch 1"})
+    random.seed(5)
+    np.random.seed(11)
+    with redirect_stdout(io.StringIO()):
+        y = Yue(Config(values=vals))
+        apr = APR(y.config, y.trainingData, y.testData)
+        apr.execute()
+    assert np.isfinite(apr.P).all() and np.isfinite(apr.Q).all() and np.isfinite(apr.loss)
+    assert rec(apr) > 0.5 * rec(ser)
+
+
+@pytest.mark.gpu
 def test_cv_folds_and_progress_hook(tmp_path):
     """SURVEY 8f row 3.  `-cv 3` through the driver (yue.py:72-123): every fold trains and ranks in its own process
     (serially, and under `-p` on device fold % device_count), the fold measures are averaged label by label and the

@@ -181,3 +181,95 @@ def test_two_rank_gloo_wrmf_row_exchange_is_exact():
     losses = [wrmf_ref.iteration(X, Y, log.uq_indptr, log.uq_items, cnt, itp, itu, itc, 0.5, gram="f64") for _ in range(2)]
     assert np.array_equal(Xa, X) and np.array_equal(Ya, Y)           # no reduction anywhere: bit-identical to one process
     assert la == pytest.approx(losses, rel=1e-12)
+
+
+# ---- round 2: shared hot rows + overlapped exchange (yue_b200/sharding.py: SharedHotTrainer), host logic ------------------
+def test_select_hot_tracks_rule_and_order():
+    c = np.zeros(1000, np.int64)
+    c[[5, 7, 9, 11]] = [50000, 90000, 50000, 16000]          # 11 is below min_count
+    c[100:600] = 3000                                          # the tail: 1.5 M events
+    tracks, counts, total = sharding.select_hot_tracks(c)
+    assert total == int(c.sum())
+    assert tracks.tolist() == [7, 5, 9] and counts.tolist() == [90000, 50000, 50000]      # most played first, ties by id
+    assert sharding.select_hot_tracks(c, hot_max=2)[0].tolist() == [7, 5]
+    # a track must also carry more than 1/128 of ALL events
+    c2 = c.copy(); c2[100:600] = 30000
+    assert sharding.select_hot_tracks(c2)[0].tolist() == []
+
+
+class _FakeEngine:
+    """Records the order of the C-ABI calls SharedHotTrainer makes."""
+    device = 0
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def f(*a, **k):
+            self.calls.append(name)
+            if name == "hot_table_export":
+                return b"\0" * 64, 0x1000
+            if name in ("bpr_epoch_part", "apr_epoch_part"):
+                return 1.5
+            return None
+        return f
+
+
+def test_shared_hot_trainer_pipeline_order_two_thread_ranks():
+    """Two ranks as threads (ThreadCtl): hot set agreed from the summed counts, tables exchanged, and per part
+    epoch -> finish(previous) -> begin -> reduce, i.e. the sum of part k is applied after part k+1."""
+    import threading
+    shared = sharding.ThreadCtl.Shared(2)
+    engs = [_FakeEngine(), _FakeEngine()]
+    counts = np.zeros(500, np.int64); counts[3] = 40000; counts[10:400] = 2000
+    out = [None, None]
+    reduced = [0, 0]
+
+    def run(r):
+        ctl = sharding.ThreadCtl(shared, r)
+
+        def reduce(e):
+            reduced[r] += 1
+            e.calls.append("reduce")
+        tr = sharding.SharedHotTrainer(engs[r], ctl, counts // 2, sub_epochs=3, asynchrony=1.0, reduce=reduce)
+        l = tr.epoch(0.02, 0.01, 0.01, 7, 0, want_loss=True)
+        l2 = tr.epoch(0.003, 0.002, 0.01, 7, 1, want_loss=True, apr=(0.5, 2.0), finalize=True)
+        out[r] = (tr, l, l2)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for r in range(2):
+        tr, l, l2 = out[r]
+        assert tr.hot_tracks.tolist() == [3] and l == 4.5 and l2 == 4.5 and reduced[r] == 6
+        c = engs[r].calls
+        setup = c[:c.index("bpr_epoch_part")]
+        assert setup == ["set_hot_tracks", "hot_table_export", "enable_peer", "hot_share", "sync", "set_delta_weights",
+                         "q_snapshot", "set_sgd_concurrency"]
+        body = c[len(setup):]
+        part = ["q_exchange_finish", "q_exchange_begin", "reduce"]
+        assert body == (["bpr_epoch_part", "q_exchange_begin", "reduce"] + ["bpr_epoch_part"] + part + ["bpr_epoch_part"] + part
+                        + (["apr_epoch_part"] + part) * 3 + ["q_exchange_finish", "sync", "hot_pull"])
+        # concurrency: both ranks together = what one GPU would give the whole log (here 1.2 M events -> 50 warps)
+        assert tr.n_warps == max(1, round(min(148 * 12, int(counts.sum()) // 16384) / 2)) and tr.n_ctas == 140
+
+
+def _ctl_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctl = sharding.TorchCtl(dist)
+    got = ctl.allgather(("rank", rank, b"\1" * 4))
+    s = ctl.allreduce_sum(np.arange(5, dtype=np.int64) * (rank + 1))
+    ctl.barrier()
+    if rank == 0:
+        ret["got"], ret["sum"] = got, s
+    dist.destroy_process_group()
+
+
+def test_torch_ctl_over_gloo_world_size_2():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_ctl_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["got"] == [("rank", 0, b"\1" * 4), ("rank", 1, b"\1" * 4)]
+    assert ret["sum"].tolist() == [0, 3, 6, 9, 12]

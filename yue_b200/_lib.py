@@ -120,6 +120,22 @@ SIGNATURES = {
     "yue_comm_unique_id": (C.c_int, [C.c_void_p]),
     "yue_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "yue_allreduce_q_delta": (C.c_int, [_H]),
+    "yue_hot_tracks": (C.c_int, [_H, _i32p, C.POINTER(C.c_int)]),
+    "yue_set_hot_tracks": (C.c_int, [_H, _i32p, _i64p, C.c_int, C.c_int64]),
+    "yue_hot_table_export": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "yue_hot_table_open": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "yue_enable_peer": (C.c_int, [_H, C.c_int]),
+    "yue_hot_share": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "yue_hot_pull": (C.c_int, [_H]),
+    "yue_hot_unshare": (C.c_int, [_H]),
+    "yue_q_exchange_begin": (C.c_int, [_H]),
+    "yue_q_exchange_reduce": (C.c_int, [_H]),
+    "yue_q_exchange_reduce_peers": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p)]),
+    "yue_q_exchange_finish": (C.c_int, [_H, C.c_int]),
+    "yue_stream2": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "yue_set_sgd_concurrency": (C.c_int, [_H, C.c_int, C.c_int]),
+    "yue_apr_epoch_part": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,
+                                     C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _f64p]),
     "yue_timer_start": (C.c_int, [_H]),
     "yue_timer_stop": (C.c_int, [_H, _f32p]),
     "yue_launch_count": (C.c_int, [_H, _i64p]),

@@ -34,6 +34,18 @@ class GpuAPRMixin(GpuBPRMixin):
         eng = self._push_factors()
         mode = MODE_SERIAL if self._opt('yue.sgd', 'hogwild') == 'serial' else MODE_HOGWILD
         seed = int(self._opt('yue.seed', random.getrandbits(63)))
+        devs = self._sharded_devices(mode)
+        if devs:                                                # yue.devices=0,1,...: the same two phases, users sharded
+            loss = 0.0
+            with self._sharded_session(eng, devs) as run_epoch:
+                for epoch in range(self.maxIter):
+                    loss = run_epoch(seed, epoch)[0]
+                    print('iteration:', epoch, 'loss:', loss)
+                for epoch in range(self.advEpoch):
+                    loss = sum(run_epoch(seed, self.maxIter + epoch, apr=(self.eps, self.regAdv, slot))[0] for slot in range(self.negativeCount))
+                    print('iteration:', epoch, 'loss:', loss)
+            self.loss = loss
+            return
         for epoch in range(self.maxIter):                       # phase 1: BPR (APR.py:120-127)
             loss = eng.bpr_epoch(self.lRate, self.regU, self.regI, seed, epoch, mode)
             print('iteration:', epoch, 'loss:', loss)

@@ -39,6 +39,10 @@ class GpuBPRMixin(object):
     #:   yue.seed=<int>        sampler seed (default: drawn from `random`, unseeded like the reference)
     #:   yue.ingest=host|device   where the array form of the log (event CSR, play sets, test sets) is built: host =
     #:                         numpy on Record's dicts; device = yue_ingest_events on the numbered events (K0)
+    #:   yue.devices=0,1,...   several CUDA devices, driven by threads of this process: evalRanking ranks a block of the test
+    #:                         users on each; buildModel (Hogwild, num.factors 32/64/128) shards the users over them with the
+    #:                         hot rows shared over peer memory (yue_b200/sharding.py: SharedHotTrainer).  The first one is
+    #:                         the device everything else runs on.  yue.sub_epochs (32) / yue.asynchrony (1.0) tune that trainer.
     #:   yue.metrics=host|device  where evalRanking computes Precision/Recall/F1/MAP/Coverage (default host:
     #:                         the reference's own summation order; device = one kernel over the lists that are
     #:                         already on the GPU, for test sets where the Python set operations dominate)
@@ -48,9 +52,18 @@ class GpuBPRMixin(object):
     def _opt(self, key, default):
         return self.config[key] if self.config.contains(key) else default
 
+    def _devices(self):
+        v = self._opt('yue.devices', None)
+        if v is None:
+            return [int(self._opt('yue.device', os.environ.get('YUE_DEVICE', '0')))]
+        devs = [int(x) for x in str(v).replace(' ', '').split(',') if x != '']
+        if not devs:
+            raise ValueError('yue.devices is empty')
+        return devs
+
     def _get_engine(self):
         if self._engine is None:
-            dev = int(self._opt('yue.device', os.environ.get('YUE_DEVICE', '0')))
+            dev = self._devices()[0]
             self._engine = Engine(dev)
             arrays = getattr(self.data, 'interaction_arrays', None)
             self._test_on_device = False
@@ -114,6 +127,9 @@ class GpuBPRMixin(object):
         eng = self._push_factors()
         mode = MODE_SERIAL if self._opt('yue.sgd', 'hogwild') == 'serial' else MODE_HOGWILD
         seed = int(self._opt('yue.seed', random.getrandbits(63)))
+        devs = self._sharded_devices(mode)
+        if devs:
+            return self._build_sharded(eng, devs, seed)
         iteration = 0
         while iteration < self.maxIter:
             loss = eng.bpr_epoch(self.lRate, self.regU, self.regI, seed, iteration, mode)
@@ -124,6 +140,81 @@ class GpuBPRMixin(object):
                 break
         self._pull_factors()
 
+    def _sharded_session(self, eng, devs):
+        """buildModel over several GPUs.  BPR.py:40-62 with the users dealt out to the devices (user u on devs[u % N], so
+        that all devices walk the reference's user stream together), the same negatives as one GPU would draw (the sampler
+        is a function of the global event index) and the schedule of sharding.SharedHotTrainer; one handle per device,
+        each driven by its own thread.  Context manager: yields run_epoch(seed, iteration, apr=None) -> (sum of the ranks'
+        -log losses, |P|^2, |Q|^2); on exit the trained tables are gathered into the host attributes."""
+        import contextlib
+        from . import sharding
+
+        @contextlib.contextmanager
+        def session():
+            world = len(devs)
+            ev_indptr, ev_items, uq_indptr, uq_items = eng.get_interactions()
+            P, Q = getattr(self, self._user_table), getattr(self, self._item_table)
+            shared = sharding.ThreadCtl.Shared(world)
+            S, A = int(self._opt('yue.sub_epochs', 32)), float(self._opt('yue.asynchrony', 1.0))
+
+            def start(r, ctl):
+                mine = sharding.interleaved_users(self.m, world, r)
+                sh = sharding.local_shard_of_users(ev_indptr, ev_items, uq_indptr, uq_items, mine)
+                e = Engine(devs[r])
+                e.set_interactions(sh['m_local'], self.n, sh['ev_indptr'], sh['ev_items'], sh['uq_indptr'], sh['uq_items'])
+                e.set_event_offsets(sh['event_offsets'])
+                e.set_factors(np.ascontiguousarray(P[mine]), Q)
+                tr = sharding.SharedHotTrainer(e, ctl, np.bincount(sh['ev_items'], minlength=self.n), sub_epochs=S, asynchrony=A)
+                return mine, e, tr
+            ranks = sharding.run_on_ranks(shared, start)
+
+            def run_epoch(seed, iteration, apr=None):
+                def epoch(r, ctl):
+                    _, e, tr = ranks[r]
+                    loss = tr.epoch(self.lRate, self.regU, self.regI, seed, iteration, want_loss=True, apr=apr, finalize=True)
+                    p2, q2 = e.frob2()
+                    return loss, p2, q2
+                res = sharding.run_on_ranks(shared, epoch)
+                return sum(x[0] for x in res), sum(x[1] for x in res), res[0][2]
+            try:
+                yield run_epoch
+
+                def finish(r, ctl):
+                    _, e, tr = ranks[r]
+                    tr.close()
+                    return e.get_factors()
+                tables = sharding.run_on_ranks(shared, finish)
+            finally:
+                for _, e, _ in ranks:
+                    e.close()
+            Pn = np.array(P, dtype=np.float32, copy=True)
+            for (mine, _, _), (Pl, _) in zip(ranks, tables):
+                Pn[mine] = Pl
+            setattr(self, self._user_table, Pn)
+            setattr(self, self._item_table, tables[0][1])
+            self._synced = (None, None)                # the main handle gets the trained tables on its next use
+        return session()
+
+    def _sharded_devices(self, mode):
+        """The devices buildModel trains on when it shards the users, else None."""
+        devs = self._devices()
+        if len(devs) > 1 and mode == MODE_HOGWILD:
+            if self.k in (32, 64, 128):
+                return devs
+            print('yue.devices: num.factors=%d trains on device %d alone (the shared hot rows of the multi-GPU trainer need 32, 64 '
+                  'or 128 factors); ranking uses all devices' % (self.k, devs[0]))
+        return None
+
+    def _build_sharded(self, eng, devs, seed):
+        with self._sharded_session(eng, devs) as run_epoch:
+            iteration = 0
+            while iteration < self.maxIter:
+                loss, p2, q2 = run_epoch(seed, iteration)
+                self.loss = loss + self.regU * p2 + self.regI * q2
+                iteration += 1
+                if self.isConverged(iteration):
+                    break
+
     def predict(self, u):
         'invoked to rank all the items for the user'
         return self._push_factors().predict(self.data.getId(u, 'user'))
@@ -132,9 +223,42 @@ class GpuBPRMixin(object):
         """[user names] -> {user: [N track names]} through the fused score+mask+top-N kernel."""
         eng = self._push_factors()
         uid = np.array([self.data.getId(u, 'user') for u in users], dtype=np.int32)
-        ids, scores = eng.rank_topn(uid, N, RANK_AUTO)
+        devs = self._devices()
+        if len(devs) > 1 and len(uid) >= 2 * len(devs):
+            ids, scores = self._rank_on_devices(eng, devs, uid, N)
+        else:
+            ids, scores = eng.rank_topn(uid, N, RANK_AUTO)
         id2name = self.data.id2name[self.recType]
         return {u: [id2name[int(t)] for t in row if t >= 0] for u, row in zip(users, ids)}, ids, scores
+
+    _rank_engines = None
+
+    def _rank_on_devices(self, eng, devs, uid, N):
+        """Every device ranks a contiguous block of the users against its own copy of Q and of the play sets (SURVEY.md 8e:
+        no collective, the host concatenates the lists).  Same kernels, same tables: the lists are those of one device."""
+        from . import sharding
+        if self._rank_engines is None:
+            arrays = eng.get_interactions()
+            self._rank_engines = [eng]
+            for dv in devs[1:]:
+                e = Engine(dv)
+                e.set_interactions(self.m, self.n, *arrays)
+                self._rank_engines.append(e)
+            self._rank_synced = [None] * len(devs)
+        P, Q = self._synced
+        world = len(devs)
+        bounds = [len(uid) * r // world for r in range(world + 1)]
+        ids, scores = np.empty((len(uid), N), np.int32), np.empty((len(uid), N), np.float32)
+
+        def rank(r, ctl):
+            e = self._rank_engines[r]
+            if r > 0 and self._rank_synced[r] is not P:
+                e.set_factors(P, Q)
+                self._rank_synced[r] = P
+            lo, hi = bounds[r], bounds[r + 1]
+            e.rank_topn(uid[lo:hi], N, RANK_AUTO, ids[lo:hi], scores[lo:hi])
+        sharding.run_on_ranks(sharding.ThreadCtl.Shared(world), rank)
+        return ids, scores
 
     def evalRanking(self):
         top = [int(num) for num in self.ranking['-topN'].split(',')]

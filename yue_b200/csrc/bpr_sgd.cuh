@@ -115,6 +115,9 @@ struct SgdParams {
     const int32_t* hot_sorted_slot;
     const int32_t* hot_dx;         // [n_hot] byte distance from a slot's row to its second accumulator row, 0 = none
     int resync_mask;               // resync when (block & resync_mask) == 0: resync_events / 4 - 1, a power of two - 1
+    // multi-GPU (yue_hot_share): hot slot s lives in the table of rank s % nranks; [n_hot] address of that table (this
+    // process's mapping of it, incl. the owner's placement offset) -- peer memory for the slots other ranks own
+    const unsigned long long* hot_base;
 };
 
 __device__ __forceinline__ float4 ld_row(const float* p) {
@@ -509,6 +512,14 @@ __global__ void mark_hot_kernel(int32_t* __restrict__ ev_items, int64_t T, const
     }
 }
 
+// undo mark_hot_kernel (before another hot set is imposed, yue_set_hot_tracks)
+__global__ void unmark_hot_kernel(int32_t* __restrict__ ev_items, int64_t T, const int32_t* __restrict__ hot_items) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < T; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = ev_items[e];
+        if (v < 0) ev_items[e] = hot_items[-v - 1];
+    }
+}
+
 // ---- sum of squares of a [rows, ld] table in float64 (BPR.py:59) --------------------------
 __global__ void frob2_kernel(const float* __restrict__ x, size_t count, double* out) {
     double acc = 0.0;
@@ -534,6 +545,45 @@ __global__ void frob2_kernel(const float* __restrict__ x, size_t count, double* 
 }
 
 // ---- elementwise helpers of the multi-GPU Q reconciliation (K4) ---------------------------
+// overlapped exchange (yue_q_exchange_*): delta = own = Q - snapshot;  later  Q += w * sum - own,  snapshot += w * sum
+__global__ void q_exchange_pack_kernel(const float4* __restrict__ q, const float4* __restrict__ snap,
+                                       float4* __restrict__ delta, float4* __restrict__ own, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = q[i], b = snap[i];
+        const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        delta[i] = d; own[i] = d;
+    }
+}
+// All-reduce over peer memory for ranks that live in one process (yue_q_exchange_reduce_peers): every rank reads every
+// rank's packed delta -- its own and, through NVLink peer access, the others' -- and sums them in rank order (so every
+// rank gets the same bits).  Up to 8 ranks.
+struct PeerDeltas { const float4* p[8]; int n; };
+__global__ void q_exchange_sum_peers_kernel(PeerDeltas src, float4* __restrict__ sum, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = __ldcg(src.p[0] + i);
+        for (int r = 1; r < src.n; ++r) {
+            const float4 b = __ldcg(src.p[r] + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        sum[i] = a;
+    }
+}
+
+// adopt: no epoch ran since the pack, so Q = snapshot + w * sum exactly -- written as that, so that every rank ends with the
+// same bits (Q + sum - own would differ between ranks in the last place)
+__global__ void q_exchange_apply_kernel(float4* __restrict__ q, float4* __restrict__ snap, const float4* __restrict__ sum,
+                                        const float4* __restrict__ own, const float* __restrict__ w, int per_row4, size_t n4, bool adopt) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 s = sum[i];
+        if (w) { const float f = w[i / per_row4]; s.x *= f; s.y *= f; s.z *= f; s.w *= f; }
+        const float4 o = own[i];
+        float4 a = q[i], b = snap[i];
+        a.x += s.x - o.x; a.y += s.y - o.y; a.z += s.z - o.z; a.w += s.w - o.w;
+        b.x += s.x; b.y += s.y; b.z += s.z; b.w += s.w;
+        q[i] = adopt ? b : a; snap[i] = b;
+    }
+}
+
 __global__ void q_delta_pack_kernel(const float4* __restrict__ q, const float4* __restrict__ snap,
                                     float4* __restrict__ delta, size_t n4) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;

@@ -1,5 +1,8 @@
-// K1+K2, blocked form: the throughput-mode BPR update for rows of 32, 64 or 128 floats
+// K1+K2, blocked form: the throughput-mode BPR update for rows of up to 128 floats
 // (replaces recommender/cf/BPR.py:42-58, same schedule and sampler as bpr_sgd.cuh).
+// Rows of exactly 32, 64 or 128 floats use every lane (MASK = false); any other width (num.factors = 10, 20, 50, 100 ...:
+// config/BPR.conf ships 10) runs the same text with the lanes past the row's end switched off (MASK = true): their
+// registers stay zero, so they add nothing to a dot product, and they neither load nor add.
 //
 // Why a second form.  ncu on bpr_sgd_kernel (profiles/ncu_summary_r1.md): 251 warp instructions per
 // triplet, issued one every ~7 cycles per warp -- the kernel is bound by the DEPENDENT instruction
@@ -51,6 +54,30 @@ template <> __device__ __forceinline__ void redv<2>(float* p, const float (&v)[2
 }
 template <> __device__ __forceinline__ void redv<4>(float* p, const float (&v)[4]) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
+// The same at system scope, for rows that may live in a peer GPU's memory (yue_hot_share): a strong load is served by
+// the L2 of the GPU that owns the line, the add is performed there; relaxed -- the schedule is Hogwild.
+template <int V> __device__ __forceinline__ void ldv_sys(const float* p, float (&v)[V]);
+template <> __device__ __forceinline__ void ldv_sys<1>(const float* p, float (&v)[1]) {
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v[0]) : "l"(p) : "memory");
+}
+template <> __device__ __forceinline__ void ldv_sys<2>(const float* p, float (&v)[2]) {
+    asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p) : "memory");
+}
+template <> __device__ __forceinline__ void ldv_sys<4>(const float* p, float (&v)[4]) {
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p) : "memory");
+}
+template <int V> __device__ __forceinline__ void redv_sys(float* p, const float (&v)[V]);
+template <> __device__ __forceinline__ void redv_sys<1>(float* p, const float (&v)[1]) {
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" :: "l"(p), "f"(v[0]) : "memory");
+}
+template <> __device__ __forceinline__ void redv_sys<2>(float* p, const float (&v)[2]) {
+    asm volatile("red.relaxed.sys.global.add.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+}
+template <> __device__ __forceinline__ void redv_sys<4>(float* p, const float (&v)[4]) {
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 
@@ -174,7 +201,7 @@ __global__ void hot_gather_kernel(const float* __restrict__ Q, float* __restrict
         float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            row[v] = Q[(size_t)hot_items[s] * ld + V * lane + v];
+            row[v] = V * lane + v < ld ? Q[(size_t)hot_items[s] * ld + V * lane + v] : 0.f;
             if (hot_dx[s]) row[hot_dx[s] / 4 + v] = 0.f;
         }
     }
@@ -187,7 +214,39 @@ __global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restric
         const float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane);
 #pragma unroll
         for (int v = 0; v < V; ++v)
-            Q[(size_t)hot_items[s] * ld + V * lane + v] = row[v] + (hot_dx[s] ? row[hot_dx[s] / 4 + v] : 0.f);
+            if (V * lane + v < ld) Q[(size_t)hot_items[s] * ld + V * lane + v] = row[v] + (hot_dx[s] ? row[hot_dx[s] / 4 + v] : 0.f);
+    }
+}
+
+// yue_hot_share: slot s lives in the table of rank s % nranks (hot_base[s] = this process's mapping of it).
+// gather: the slots THIS rank owns move from its Q into its own table (second rows zeroed).
+template <int V>
+__global__ void hot_gather_shared_kernel(const float* __restrict__ Q, const unsigned long long* __restrict__ hot_base,
+                                         const int32_t* __restrict__ hot_items, const int32_t* __restrict__ hot_dx, int n_hot, int ld,
+                                         int nranks, int rank) {
+    const int lane = threadIdx.x & 31;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
+        if (s % nranks != rank) continue;
+        float* row = reinterpret_cast<float*>(hot_base[s]) + hot_slot_offset(s) + hot_lane_offset<V>(lane);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            row[v] = Q[(size_t)hot_items[s] * ld + V * lane + v];
+            if (hot_dx[s]) row[hot_dx[s] / 4 + v] = 0.f;
+        }
+    }
+}
+// pull: every hot row (the sum of its accumulator rows) from its owner's table into this rank's Q
+template <int V>
+__global__ void hot_pull_shared_kernel(float* __restrict__ Q, const unsigned long long* __restrict__ hot_base,
+                                       const int32_t* __restrict__ hot_items, const int32_t* __restrict__ hot_dx, int n_hot, int ld) {
+    const int lane = threadIdx.x & 31;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
+        const float* row = reinterpret_cast<const float*>(hot_base[s]) + hot_slot_offset(s) + hot_lane_offset<V>(lane);
+        float a[V], b[V];
+        ldv_sys<V>(row, a);
+        if (hot_dx[s]) ldv_sys<V>(row + hot_dx[s] / 4, b);
+#pragma unroll
+        for (int v = 0; v < V; ++v) Q[(size_t)hot_items[s] * ld + V * lane + v] = a[v] + (hot_dx[s] ? b[v] : 0.f);
     }
 }
 
@@ -199,14 +258,19 @@ __global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restric
 // virtual empty segment, so all of this exists once in the code (the first version, with the block
 // loop unrolled by two and the prologue inlined three times, was 12 K instructions and spent 57 % of
 // its stall samples waiting for the instruction cache).
-template <int V, bool APR>
+// SHARED (yue_hot_share, N GPUs): slot s of the hot-row table lives in the table of rank s % N -- p.hot_base[s] is this
+// process's mapping of that table -- and every access to a row of Q or of a table is made at system scope.
+template <int V, bool APR, bool MASK = false, bool SHARED = false>
 __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdParams p) {
+    static_assert(!(SHARED && MASK), "shared hot rows need full-width rows");
     extern __shared__ __align__(16) int hot_sm[];           // [n_hot] hot track ids, ascending; [n_hot] their slots; [n_hot] dx
     int* hot_sorted = hot_sm;
     int* hot_sorted_slot = hot_sm + p.n_hot;
     int* hot_dx = hot_sm + 2 * p.n_hot;                     // per slot: byte distance to its second row, or 0
+    unsigned long long* hot_base = reinterpret_cast<unsigned long long*>(hot_sm + ((3 * p.n_hot + 3) & ~3));   // SHARED: [n_hot]
     for (int x = threadIdx.x; x < p.n_hot; x += blockDim.x) {
         hot_sorted[x] = p.hot_sorted[x]; hot_sorted_slot[x] = p.hot_sorted_slot[x]; hot_dx[x] = p.hot_dx[x];
+        if (SHARED) hot_base[x] = p.hot_base[x];
     }
     __syncthreads();
     const unsigned full = 0xffffffffu;
@@ -214,10 +278,23 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (warp >= p.n_warps) return;
     const int lane_off = V * lane;
+    const bool act = !MASK || lane_off < p.ld;               // does this lane hold a part of the row?  (ld % 4 == 0, V | 4)
+    auto ldrow = [&](const float* ptr, float (&v)[V]) {
+        if (!MASK || act) ldv<V>(ptr, v);
+        else {
+#pragma unroll
+            for (int x = 0; x < V; ++x) v[x] = 0.f;
+        }
+    };
+    auto redrow = [&](float* ptr, const float (&v)[V]) { if (!MASK || act) redv<V>(ptr, v); };
+    // rows of Q / of a hot-row table
+    auto ldq = [&](const float* ptr, float (&v)[V]) { if (SHARED) ldv_sys<V>(ptr, v); else ldrow(ptr, v); };
+    auto redq = [&](float* ptr, const float (&v)[V]) { if (SHARED) redv_sys<V>(ptr, v); else redrow(ptr, v); };
     const float cu1 = 1.f - p.c_u;
     // per-lane base addresses; a row is then base + (32-bit byte offset), see q_ptr
     char* const q_lane = reinterpret_cast<char*>(p.Q + lane_off);
     char* const hot_lane = reinterpret_cast<char*>(p.hotQ + hot_lane_offset<V>(lane));
+    const uint32_t hot_lane_bytes = (uint32_t)(hot_lane_offset<V>(lane) * sizeof(float));
     const uint32_t row_bytes = (uint32_t)p.ld * 4u;          // n * ld * 4 < 4 GB is checked by the host
 
     float pu[V], pu0[V], pun[V];
@@ -230,6 +307,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
     auto q_ptr = [&](int32_t t) -> float* {
         const int s = -t - 1;
         const uint32_t off = t < 0 ? (uint32_t)(((s >> 1) << 2) | (s & 1)) * 256u : (uint32_t)t * row_bytes;
+        if (SHARED && t < 0) return reinterpret_cast<float*>(hot_base[s] + hot_lane_bytes + off);
         return reinterpret_cast<float*>((t < 0 ? hot_lane : q_lane) + off);
     };
     auto flush_user = [&]() {
@@ -237,12 +315,12 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
         float dlt[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) dlt[v] = pu[v] - pu0[v];
-        redv<V>(p.P + (size_t)cur_u * p.ld + lane_off, dlt);
+        redrow(p.P + (size_t)cur_u * p.ld + lane_off, dlt);
     };
     auto sync_user = [&](int uu) {          // publish the pending change of P[cur_u], (re)load P[uu]
         flush_user();
         cur_u = uu;
-        ldv<V>(p.P + (size_t)uu * p.ld + lane_off, pu);
+        ldrow(p.P + (size_t)uu * p.ld + lane_off, pu);
 #pragma unroll
         for (int v = 0; v < V; ++v) pu0[v] = pu[v];
     };
@@ -314,7 +392,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                         }
                     }
                     __syncwarp();
-                    if (n_u != cur_u) ldv<V>(p.P + (size_t)n_u * p.ld + lane_off, pun);
+                    if (n_u != cur_u) ldrow(p.P + (size_t)n_u * p.ld + lane_off, pun);
                     // the segment after: its record arrived a segment ago -> prefetch its data, fetch the next record
                     if (seg + 2 < se) prefetch_seg(fa, fb);
                     na = fa; nb = fb;
@@ -331,11 +409,11 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                         nxt.dx[a] = 0;
                         if (t < src_len) {
                             nxt.pi[a] = q_ptr(it); nxt.pj[a] = q_ptr(jt);
-                            ldv<V>(nxt.pi[a], nxt.qi[a]);
-                            ldv<V>(nxt.pj[a], nxt.qj[a]);
+                            ldq(nxt.pi[a], nxt.qi[a]);
+                            ldq(nxt.pj[a], nxt.qj[a]);
                             if (it < 0) {                                   // a sharded hot positive: fetch its second row too
                                 nxt.dx[a] = hot_dx[-it - 1];
-                                if (nxt.dx[a]) ldv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(nxt.pi[a]) + nxt.dx[a]), nxt.ex[a]);
+                                if (nxt.dx[a]) ldq(reinterpret_cast<float*>(reinterpret_cast<char*>(nxt.pi[a]) + nxt.dx[a]), nxt.ex[a]);
                             }
                         } else {
 #pragma unroll
@@ -408,8 +486,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                                     dj[v] = fmaf(-p.c_i, cur.qj[a][v] - gp, -gp);
                                     pu[v] = fmaf(-p.c_u, pn, pn);
                                 }
-                                redv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
-                                redv<V>(cur.pj[a], dj);
+                                redq(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
+                                redq(cur.pj[a], dj);
                             }
                         }
                     } else {
@@ -478,8 +556,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                                     dj[v] = fmaf(-p.c_i, cur.qj[a][v] - step, -step);
                                     pu[v] = fmaf(-p.c_u, pn, pn);
                                 }
-                                redv<V>(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
-                                redv<V>(cur.pj[a], dj);
+                                redq(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
+                                redq(cur.pj[a], dj);
                             }
                         }
                     }

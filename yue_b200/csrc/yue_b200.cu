@@ -223,6 +223,20 @@ struct yue_handle {
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+
+    // multi-GPU, shared hot rows (yue_hot_share) and the overlapped exchange of the tail (yue_q_exchange_*)
+    bool hot_shared = false;
+    int hot_nranks = 1, hot_rank = 0;
+    DevBuf<unsigned long long> hot_base;      // [n_hot] this process's address of the table that owns each slot
+    std::vector<void*> ipc_opened;            // peer tables mapped by yue_hot_table_open ...
+    std::vector<std::string> ipc_keys;        // ... and the 64-byte handle each came from (a handle is opened once per process)
+    DevBuf<float> Qown;                       // this rank's packed delta while the sum is in flight
+    DevBuf<float> Qsum;                       // yue_q_exchange_reduce_peers: the sum (the ranks' deltas must stay readable)
+    bool sum_in_qsum = false;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_red = nullptr;
+    bool exchange_pending = false;
+    int sgd_warps_forced = 0, sgd_ctas_forced = 0;   // yue_set_sgd_concurrency
 };
 
 #define CK(...)                                                                           \
@@ -420,6 +434,11 @@ int yue_destroy(yue_t* h) {
     h->scal.release();
     h->ip_indptr.release(); h->ip_items.release(); h->cune_scal.release(); h->cune_ctr.release(); h->cune_items.release();
     h->l2buf.release();
+    h->hot_base.release(); h->Qown.release(); h->Qsum.release();
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+    if (h->ev_red) cudaEventDestroy(h->ev_red);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     h->uq_cnt.release(); h->it_users.release(); h->it_cnt.release(); h->it_indptr.release();
     for (auto* b : {&h->wrmf_G, &h->wrmf_part, &h->wrmf_partA, &h->wrmf_partb, &h->wrmf_Binv}) b->release();
     for (auto& pl : h->wrmf_plan) { pl.heavy_rows.release(); pl.heavy_first.release(); pl.chunk_row.release(); pl.chunk_begin.release(); pl.chunk_end.release(); }
@@ -451,6 +470,46 @@ int yue_host_alloc(size_t bytes, void** out) {
     return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? YUE_OK : YUE_E_CUDA;
 }
 int yue_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? YUE_OK : YUE_E_CUDA; }
+
+// Make `cand` (slot order) the hot set: lookup tables for the kernels, second rows for tracks above 1/hot_shard_div of
+// `total` events, and the hot positives of the device copy of ev_items re-labelled -slot-1 (ev_items must be unmarked).
+static int install_hot_set(yue_t* h, const std::vector<int32_t>& cand, const std::vector<int64_t>& cand_counts, int64_t total) {
+    const int64_t n = h->n, T = h->T;
+    h->n_hot = (int)cand.size();
+    h->h_hot_counts.clear();
+    for (int64_t c : cand_counts) h->h_hot_counts.push_back((int32_t)std::min<int64_t>(c, INT32_MAX));
+    h->h_hot_items = cand;
+    h->hot_meta_cap = 0;
+    if (!h->n_hot) return YUE_OK;
+    std::vector<int32_t> slot((size_t)n, -1);
+    for (int s2 = 0; s2 < h->n_hot; ++s2) slot[cand[s2]] = s2;
+    std::vector<int32_t> order((size_t)h->n_hot), sorted_ids, sorted_slots;      // ascending track id, for the kernel's lookup of negatives
+    for (int s2 = 0; s2 < h->n_hot; ++s2) order[s2] = s2;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cand[a] < cand[b]; });
+    for (int32_t s2 : order) { sorted_ids.push_back(cand[s2]); sorted_slots.push_back(s2); }
+    std::vector<int32_t> dx((size_t)h->n_hot, 0);       // second rows for the most played tracks (blocked kernel)
+    for (int s2 = 0, extra = 0; s2 < h->n_hot && extra < kHotExtra; ++s2)
+        if (cand_counts[s2] * h->hot_shard_div > total) {
+            dx[s2] = (int32_t)((hot_slot_offset(h->n_hot + extra) - hot_slot_offset(s2)) * sizeof(float));
+            ++extra;
+        }
+    CK(h->hot_dx.resize(h->n_hot));
+    CK(cudaMemcpyAsync(h->hot_dx.p, dx.data(), dx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(h->hot_sorted.resize(h->n_hot)); CK(h->hot_sorted_slot.resize(h->n_hot)); CK(h->hotQ.resize(kHotTableFloats + (size_t)(kHotCandidates + 1) * kHotCandidateStep * 64));
+    CK(cudaMemcpyAsync(h->hot_sorted.p, sorted_ids.data(), sorted_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hot_sorted_slot.p, sorted_slots.data(), sorted_slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(h->hot_items.resize(h->n_hot)); CK(h->hot_slot.resize(n));
+    CK(cudaMemcpyAsync(h->hot_items.p, cand.data(), cand.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hot_slot.p, slot.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (T > 0) {
+        const int grid = (int)std::min<int64_t>((T + 255) / 256, (int64_t)h->sm_count * 16);
+        mark_hot_kernel<<<grid, 256, 0, h->stream>>>(h->ev_items.p, T, h->hot_slot.p);
+        ++h->launches;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));      // host vectors die here
+    return YUE_OK;
+}
 
 // second half of yue_set_interactions / yue_ingest_events: the four arrays are on the device (h->m, n, T, nnz set),
 // ev_indptr / uq_indptr are their host copies.  Validates, plans segments and work items, selects the hot tracks.
@@ -519,6 +578,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     // positives of the device copy of ev_items are re-labelled -slot-1 (see SgdParams::hot_items)
     h->n_hot = 0;
     h->h_hot_items.clear();
+    h->hot_shared = false;                     // a new log: its hot set is private until yue_hot_share is called again
     if (T > 0 && h->hot_max > 0) {
         CK(h->item_counts.resize(n));
         CK(cudaMemsetAsync(h->item_counts.p, 0, n * sizeof(int32_t), h->stream));
@@ -538,37 +598,9 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
             if ((int64_t)counts[t] * stride >= h->hot_min_count && (int64_t)counts[t] * stride * h->hot_div > T) cand.push_back((int32_t)t);
         std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return counts[a] != counts[b] ? counts[a] > counts[b] : a < b; });
         if ((int)cand.size() > h->hot_max) cand.resize(h->hot_max);
-        h->n_hot = (int)cand.size();
-        h->h_hot_counts.clear();
-        for (int32_t t : cand) h->h_hot_counts.push_back((int32_t)std::min<int64_t>(counts[t] * stride, INT32_MAX));
-        h->h_hot_items = cand;
-        h->hot_meta_cap = 0;
-        if (h->n_hot) {
-            std::vector<int32_t> slot((size_t)n, -1);
-            for (int s2 = 0; s2 < h->n_hot; ++s2) slot[cand[s2]] = s2;
-            std::vector<int32_t> order((size_t)h->n_hot), sorted_ids, sorted_slots;      // ascending track id, for the kernel's lookup of negatives
-            for (int s2 = 0; s2 < h->n_hot; ++s2) order[s2] = s2;
-            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cand[a] < cand[b]; });
-            for (int32_t s2 : order) { sorted_ids.push_back(cand[s2]); sorted_slots.push_back(s2); }
-            std::vector<int32_t> dx((size_t)h->n_hot, 0);       // second rows for the most played tracks (blocked kernel)
-            for (int s2 = 0, extra = 0; s2 < h->n_hot && extra < kHotExtra; ++s2)
-                if ((int64_t)counts[cand[s2]] * stride * h->hot_shard_div > T) {
-                    dx[s2] = (int32_t)((hot_slot_offset(h->n_hot + extra) - hot_slot_offset(s2)) * sizeof(float));
-                    ++extra;
-                }
-            CK(h->hot_dx.resize(h->n_hot));
-            CK(cudaMemcpyAsync(h->hot_dx.p, dx.data(), dx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            CK(h->hot_sorted.resize(h->n_hot)); CK(h->hot_sorted_slot.resize(h->n_hot)); CK(h->hotQ.resize(kHotTableFloats + (size_t)(kHotCandidates + 1) * kHotCandidateStep * 64));
-            CK(cudaMemcpyAsync(h->hot_sorted.p, sorted_ids.data(), sorted_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemcpyAsync(h->hot_sorted_slot.p, sorted_slots.data(), sorted_slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            CK(h->hot_items.resize(h->n_hot)); CK(h->hot_slot.resize(n));
-            CK(cudaMemcpyAsync(h->hot_items.p, cand.data(), cand.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemcpyAsync(h->hot_slot.p, slot.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            mark_hot_kernel<<<grid, 256, 0, h->stream>>>(h->ev_items.p, T, h->hot_slot.p);
-            ++h->launches;
-            CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(h->stream));
-        }
+        std::vector<int64_t> cand_counts;
+        for (int32_t t : cand) cand_counts.push_back((int64_t)counts[t] * stride);
+        if (int rc = install_hot_set(h, cand, cand_counts, T)) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));      // host vectors die here
     pt.lap("hot tracks");
@@ -783,6 +815,8 @@ int yue_set_factors(yue_t* h, int k, const float* P, const float* Q) {
     CK(cudaStreamSynchronize(h->stream));
     h->have_factors = true;
     h->have_snap = false;
+    h->exchange_pending = false;
+    h->hot_shared = false;                     // new tables: the owners' rows no longer describe them
     h->tc.q_dirty = true;
     h->rowmajor_current = true;
     h->ilv_current = false;
@@ -881,18 +915,28 @@ static cudaError_t launch_sgd(const SgdParams& sp, int mode, int warps_per_cta, 
 // blocked kernel: hot rows move into the slice-friendly table for the launch and back after it
 template <int V, bool APR>
 static cudaError_t launch_sgd_blk(const SgdParams& sp, int warps_per_cta, cudaStream_t st, int64_t& launches) {
+    const bool mask = sp.ld != 32 * V;          // rows narrower than the warp's 32 x V floats: tail lanes switched off
     warps_per_cta = std::min(warps_per_cta, kBlkThreads / 32);
     const int grid = (sp.n_warps + warps_per_cta - 1) / warps_per_cta;
+    if (sp.hot_base) {                          // yue_hot_share: the rows stay in the owners' tables across launches
+        const size_t smem = (size_t)((3 * sp.n_hot + 3) & ~3) * 4 + (size_t)sp.n_hot * 8;
+        bpr_sgd_blk_kernel<V, APR, false, true><<<grid, warps_per_cta * 32, smem, st>>>(sp);
+        return cudaGetLastError();
+    }
     if (sp.n_hot > 0) { hot_gather_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
-    bpr_sgd_blk_kernel<V, APR><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
+    if (mask) bpr_sgd_blk_kernel<V, APR, true><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
+    else bpr_sgd_blk_kernel<V, APR, false><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
     if (sp.n_hot > 0) { hot_scatter_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
     return cudaGetLastError();
 }
 
+// floats per lane of the blocked kernel for rows of ld floats (ld <= 128)
+static int blk_width(int ld) { return ld <= 32 ? 1 : ld <= 64 ? 2 : 4; }
+
 // does the blocked kernel (bpr_sgd_blk.cuh) take this launch?
 static bool use_blk_kernel(const yue_t* h, int mode, bool apr) {
     (void)apr;
-    return h->sgd_kernel == 2 && mode == YUE_MODE_HOGWILD && (h->ld == 32 || h->ld == 64 || h->ld == 128) &&
+    return h->sgd_kernel == 2 && mode == YUE_MODE_HOGWILD && h->ld <= 128 &&
            (uint64_t)h->n * h->ld * 4 < ((uint64_t)1 << 32);      // 32-bit byte offsets inside Q
 }
 
@@ -938,9 +982,9 @@ static int calibrate_hot_offset(yue_t* h, SgdParams sp, int wpc) {
         const unsigned long long c0 = (unsigned long long)sp.item_first;
         CK(cudaMemcpyAsync(h->cursor.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
         CK(cudaEventRecord(h->ev0, h->stream));
-        switch (h->ld) {
-            case 32: CK(launch_sgd_blk<1, false>(sp, wpc, h->stream, h->launches)); break;
-            case 64: CK(launch_sgd_blk<2, false>(sp, wpc, h->stream, h->launches)); break;
+        switch (blk_width(h->ld)) {
+            case 1: CK(launch_sgd_blk<1, false>(sp, wpc, h->stream, h->launches)); break;
+            case 2: CK(launch_sgd_blk<2, false>(sp, wpc, h->stream, h->launches)); break;
             default: CK(launch_sgd_blk<4, false>(sp, wpc, h->stream, h->launches)); break;
         }
         ++h->launches;
@@ -963,8 +1007,14 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr 
     if (ilv) { if (int rc = q_interleaved(h)) return rc; } else { if (int rc = q_rowmajor(h)) return rc; }
     sp.P = h->P.p; sp.Q = ilv ? h->Qilv.p : h->Q.p; sp.ld = h->ld; sp.nchunks = h->ld / 4; sp.n_items = (uint32_t)h->n;
     sp.uq_indptr = h->uq_indptr.p; sp.uq_items = h->uq_items.p; sp.loss = h->scal.p;
+    if (h->hot_shared && sp.n_hot > 0)
+        REQUIRE(blk && h->ld == 32 * blk_width(h->ld) && mode == YUE_MODE_HOGWILD, YUE_E_STATE,
+                "the hot rows are shared between ranks (yue_hot_share): only the Hogwild epochs at num.factors 32/64/128 may run; call yue_hot_unshare first");
     if (sp.n_hot > 0) {
-        if (blk) {
+        if (blk && h->hot_shared) {
+            sp.hot_sorted = h->hot_sorted.p; sp.hot_sorted_slot = h->hot_sorted_slot.p; sp.hot_dx = h->hot_dx.p;
+            sp.hot_base = h->hot_base.p; sp.hotQ = h->hotQ.p;
+        } else if (blk) {
             sp.hot_sorted = h->hot_sorted.p; sp.hot_sorted_slot = h->hot_sorted_slot.p; sp.hot_dx = h->hot_dx.p;
             if (int rc = calibrate_hot_offset(h, sp, std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm)))) return rc;
             sp.hotQ = h->hotQ.p + (size_t)h->hot_offset_granules * 64;
@@ -978,11 +1028,17 @@ static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr 
     if (sp.item_first == 0) CK(cudaMemsetAsync(h->cursor.p, 0, sizeof(unsigned long long), h->stream));
     else { const unsigned long long c0 = (unsigned long long)sp.item_first; CK(cudaMemcpyAsync(h->cursor.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
     const int nch = (sp.nchunks + 15) / 16;
-    const int wpc = std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm));
+    int wpc = std::max(1, std::min(kSgdThreads / 32, h->warps_per_sm));
+    if (mode != YUE_MODE_SERIAL && h->sgd_warps_forced > 0) {        // yue_set_sgd_concurrency
+        sp.n_warps = h->sgd_warps_forced;
+        const int ctas = h->sgd_ctas_forced > 0 ? h->sgd_ctas_forced : h->sm_count;
+        wpc = std::max(1, std::min(blk ? kBlkThreads / 32 : kSgdThreads / 32, (sp.n_warps + ctas - 1) / ctas));
+        sp.n_warps = std::min(sp.n_warps, wpc * ctas);
+    }
     if (blk) {
-        switch (h->ld) {
-            case 32: CK(apr ? launch_sgd_blk<1, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<1, false>(sp, wpc, h->stream, h->launches)); break;
-            case 64: CK(apr ? launch_sgd_blk<2, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<2, false>(sp, wpc, h->stream, h->launches)); break;
+        switch (blk_width(h->ld)) {
+            case 1: CK(apr ? launch_sgd_blk<1, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<1, false>(sp, wpc, h->stream, h->launches)); break;
+            case 2: CK(apr ? launch_sgd_blk<2, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<2, false>(sp, wpc, h->stream, h->launches)); break;
             default: CK(apr ? launch_sgd_blk<4, true>(sp, wpc, h->stream, h->launches) : launch_sgd_blk<4, false>(sp, wpc, h->stream, h->launches)); break;
         }
     } else
@@ -1052,6 +1108,11 @@ int yue_bpr_epoch_part(yue_t* h, double lr, double regU, double regI, uint64_t s
 int yue_apr_epoch(yue_t* h, double lr, double regU, double regI, double eps, double regA, uint64_t seed,
                   uint32_t epoch, uint32_t slot, int mode, double* loss_out) {
     return sgd_epoch(h, lr, regU, regI, seed, epoch, slot, mode, loss_out, true, eps, regA);
+}
+
+int yue_apr_epoch_part(yue_t* h, double lr, double regU, double regI, double eps, double regA, uint64_t seed,
+                       uint32_t epoch, uint32_t slot, int mode, int part, int n_parts, double* loss_out) {
+    return sgd_epoch(h, lr, regU, regI, seed, epoch, slot, mode, loss_out, true, eps, regA, part, n_parts);
 }
 
 static int sgd_apply(yue_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t T, double lr,
@@ -1661,6 +1722,220 @@ int yue_allreduce_q_delta(yue_t* h) {
     const int rc = g_nccl.AllReduce(h->Qdelta.p, h->Qdelta.p, (size_t)h->n * h->ld, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream);
     if (rc != 0) return fail(h, YUE_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     return yue_q_delta_apply(h);
+}
+
+// ---- multi-GPU: shared hot rows (one copy per row, on its owner's GPU) + overlapped exchange of the tail --------------
+int yue_hot_tracks(yue_t* h, int32_t* tracks_out, int* n_hot) {
+    REQUIRE(h && h->have_log && n_hot, YUE_E_STATE, "interactions not set");
+    *n_hot = h->n_hot;
+    if (tracks_out) for (int s = 0; s < h->n_hot; ++s) tracks_out[s] = h->h_hot_items[(size_t)s];
+    return YUE_OK;
+}
+
+int yue_set_hot_tracks(yue_t* h, const int32_t* tracks, const int64_t* counts, int n_hot, int64_t total_events) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "call yue_set_interactions first");
+    REQUIRE(!h->hot_shared, YUE_E_STATE, "the hot rows are shared (yue_hot_unshare first)");
+    REQUIRE(n_hot >= 0 && n_hot <= kHotSlots && (n_hot == 0 || (tracks && counts)) && total_events >= 0, YUE_E_ARG, "bad hot set");
+    CK(cudaSetDevice(h->device));
+    std::vector<int32_t> cand(tracks, tracks + n_hot), seen(cand);
+    std::sort(seen.begin(), seen.end());
+    REQUIRE(std::adjacent_find(seen.begin(), seen.end()) == seen.end(), YUE_E_ARG, "a track is listed twice");
+    REQUIRE(n_hot == 0 || (seen.front() >= 0 && seen.back() < h->n), YUE_E_ARG, "hot track outside [0, n)");
+    if (h->n_hot > 0 && h->T > 0) {             // back to plain ids before the new labels go on
+        const int grid = (int)std::min<int64_t>((h->T + 255) / 256, (int64_t)h->sm_count * 16);
+        unmark_hot_kernel<<<grid, 256, 0, h->stream>>>(h->ev_items.p, h->T, h->hot_items.p);
+        ++h->launches;
+        CK(cudaGetLastError());
+    }
+    h->hot_calibrated_key = 0;
+    return install_hot_set(h, cand, std::vector<int64_t>(counts, counts + n_hot), total_events);
+}
+
+int yue_hot_table_export(yue_t* h, void* ipc_handle64, void** dev_ptr) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "call yue_set_interactions first");
+    CK(cudaSetDevice(h->device));
+    CK(h->hotQ.resize(kHotTableFloats + (size_t)(kHotCandidates + 1) * kHotCandidateStep * 64));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (ipc_handle64) CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle64, h->hotQ.p));
+    if (dev_ptr) *dev_ptr = h->hotQ.p;
+    return YUE_OK;
+}
+
+int yue_hot_table_open(yue_t* h, const void* ipc_handle64, void** dev_ptr) {
+    REQUIRE(h && ipc_handle64 && dev_ptr, YUE_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle64, sizeof(hd));
+    const std::string key((const char*)ipc_handle64, sizeof(hd));
+    for (size_t x = 0; x < h->ipc_keys.size(); ++x)
+        if (h->ipc_keys[x] == key) { *dev_ptr = h->ipc_opened[x]; return YUE_OK; }     // the peer's table outlives its logs
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    h->ipc_keys.push_back(key);
+    *dev_ptr = p;
+    return YUE_OK;
+}
+
+int yue_enable_peer(yue_t* h, int peer_device) {
+    REQUIRE(h, YUE_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    if (peer_device == h->device) return YUE_OK;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, h->device, peer_device));
+    REQUIRE(can, YUE_E_UNSUPPORTED, "device " + std::to_string(h->device) + " cannot access device " + std::to_string(peer_device) + " as a peer");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return YUE_OK; }
+    CK(e);
+    return YUE_OK;
+}
+
+template <int V>
+static cudaError_t launch_hot_gather_shared(yue_t* h) {
+    hot_gather_shared_kernel<V><<<(h->n_hot + 7) / 8, 256, 0, h->stream>>>(h->Q.p, h->hot_base.p, h->hot_items.p, h->hot_dx.p, h->n_hot, h->ld,
+                                                                           h->hot_nranks, h->hot_rank);
+    return cudaGetLastError();
+}
+template <int V>
+static cudaError_t launch_hot_pull_shared(yue_t* h) {
+    hot_pull_shared_kernel<V><<<(h->n_hot + 7) / 8, 256, 0, h->stream>>>(h->Q.p, h->hot_base.p, h->hot_items.p, h->hot_dx.p, h->n_hot, h->ld);
+    return cudaGetLastError();
+}
+
+int yue_hot_share(yue_t* h, int nranks, int rank, void* const* tables) {
+    REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "set interactions and factors first");
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && tables, YUE_E_ARG, "bad rank arguments");
+    REQUIRE(h->ld == 32 || h->ld == 64 || h->ld == 128, YUE_E_UNSUPPORTED, "shared hot rows need num.factors = 32, 64 or 128");
+    REQUIRE((uint64_t)h->n * h->ld * 4 < ((uint64_t)1 << 32), YUE_E_UNSUPPORTED, "catalog too large for the blocked kernel");
+    CK(cudaSetDevice(h->device));
+    if (int rc = q_rowmajor(h)) return rc;
+    h->hot_nranks = nranks; h->hot_rank = rank;
+    if (h->n_hot > 0) {
+        CK(h->hotQ.resize(kHotTableFloats + (size_t)(kHotCandidates + 1) * kHotCandidateStep * 64));
+        std::vector<unsigned long long> base((size_t)h->n_hot);
+        for (int s = 0; s < h->n_hot; ++s) {
+            const int owner = s % nranks;
+            void* t = owner == rank ? (void*)h->hotQ.p : tables[owner];
+            REQUIRE(t, YUE_E_ARG, "table of rank " + std::to_string(owner) + " is NULL");
+            base[(size_t)s] = (unsigned long long)(uintptr_t)t;
+        }
+        CK(h->hot_base.resize(h->n_hot));
+        CK(cudaMemcpyAsync(h->hot_base.p, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+        switch (blk_width(h->ld)) {
+            case 1: CK(launch_hot_gather_shared<1>(h)); break;
+            case 2: CK(launch_hot_gather_shared<2>(h)); break;
+            default: CK(launch_hot_gather_shared<4>(h)); break;
+        }
+        ++h->launches;
+        CK(cudaStreamSynchronize(h->stream));       // base dies here; the caller's barrier then covers every rank's rows
+    }
+    h->hot_shared = true;
+    return YUE_OK;
+}
+
+int yue_hot_pull(yue_t* h) {
+    REQUIRE(h && h->hot_shared, YUE_E_STATE, "the hot rows are not shared");
+    CK(cudaSetDevice(h->device));
+    if (h->n_hot > 0) {
+        switch (blk_width(h->ld)) {
+            case 1: CK(launch_hot_pull_shared<1>(h)); break;
+            case 2: CK(launch_hot_pull_shared<2>(h)); break;
+            default: CK(launch_hot_pull_shared<4>(h)); break;
+        }
+        ++h->launches;
+        h->tc.q_dirty = true;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+int yue_hot_unshare(yue_t* h) {
+    if (int rc = yue_hot_pull(h)) return rc;
+    h->hot_shared = false;
+    return YUE_OK;
+}
+
+int yue_set_sgd_concurrency(yue_t* h, int n_warps, int n_ctas) {
+    REQUIRE(h && n_warps >= 0 && n_ctas >= 0, YUE_E_ARG, "negative concurrency");
+    h->sgd_warps_forced = n_warps;
+    h->sgd_ctas_forced = std::min(n_ctas, h->sm_count);
+    return YUE_OK;
+}
+
+static int ensure_exchange(yue_t* h) {
+    if (int rc = ensure_snap(h)) return rc;
+    CK(h->Qown.resize((size_t)h->n * h->ld));
+    if (!h->stream2) {
+        CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_red, cudaEventDisableTiming));
+    }
+    return YUE_OK;
+}
+int yue_stream2(yue_t* h, void** cuda_stream) {
+    REQUIRE(h && cuda_stream, YUE_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_exchange(h)) return rc;
+    *cuda_stream = (void*)h->stream2;
+    return YUE_OK;
+}
+int yue_q_exchange_begin(yue_t* h) {
+    REQUIRE(h && h->have_factors && h->have_snap, YUE_E_STATE, "call yue_q_snapshot first");
+    REQUIRE(!h->exchange_pending, YUE_E_STATE, "an exchange is already in flight (yue_q_exchange_finish first)");
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_exchange(h)) return rc;
+    if (int rc = q_rowmajor(h)) return rc;
+    const size_t n4 = (size_t)h->n * h->ld / 4;
+    q_exchange_pack_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((const float4*)h->Q.p, (const float4*)h->Qsnap.p, (float4*)h->Qdelta.p,
+                                                                   (float4*)h->Qown.p, n4);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_pack, h->stream));
+    CK(cudaStreamWaitEvent(h->stream2, h->ev_pack, 0));
+    h->exchange_pending = true;
+    return YUE_OK;
+}
+int yue_q_exchange_reduce(yue_t* h) {
+    REQUIRE(h && h->comm, YUE_E_STATE, "call yue_comm_init first");
+    REQUIRE(h->exchange_pending, YUE_E_STATE, "call yue_q_exchange_begin first");
+    CK(cudaSetDevice(h->device));
+    const int rc = g_nccl.AllReduce(h->Qdelta.p, h->Qdelta.p, (size_t)h->n * h->ld, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream2);
+    if (rc != 0) return fail(h, YUE_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return YUE_OK;
+}
+int yue_q_exchange_reduce_peers(yue_t* h, int nranks, void* const* deltas) {
+    REQUIRE(h && h->exchange_pending, YUE_E_STATE, "call yue_q_exchange_begin first");
+    REQUIRE(nranks >= 1 && nranks <= 8 && deltas, YUE_E_ARG, "1..8 ranks");
+    CK(cudaSetDevice(h->device));
+    CK(h->Qsum.resize((size_t)h->n * h->ld));
+    PeerDeltas src{};
+    src.n = nranks;
+    for (int r = 0; r < nranks; ++r) {
+        src.p[r] = (const float4*)(deltas[r] ? deltas[r] : (void*)h->Qdelta.p);
+    }
+    const size_t n4 = (size_t)h->n * h->ld / 4;
+    q_exchange_sum_peers_kernel<<<h->sm_count * 4, 256, 0, h->stream2>>>(src, (float4*)h->Qsum.p, n4);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream2));     // the caller's barrier then tells every rank that its delta has been read
+    h->sum_in_qsum = true;
+    return YUE_OK;
+}
+int yue_q_exchange_finish(yue_t* h, int quiescent) {
+    REQUIRE(h && h->exchange_pending, YUE_E_STATE, "no exchange in flight");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev_red, h->stream2));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_red, 0));
+    const size_t n4 = (size_t)h->n * h->ld / 4;
+    q_exchange_apply_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>((float4*)h->Q.p, (float4*)h->Qsnap.p,
+                                                                    (const float4*)(h->sum_in_qsum ? h->Qsum.p : h->Qdelta.p), (const float4*)h->Qown.p, h->have_delta_w ? h->delta_w.p : nullptr, h->ld / 4, n4, quiescent != 0);
+    ++h->launches;
+    CK(cudaGetLastError());
+    h->exchange_pending = false;
+    h->sum_in_qsum = false;
+    h->tc.q_dirty = true;
+    h->ilv_current = false;
+    return YUE_OK;
 }
 
 // ---- measurement hooks ---------------------------------------------------------------------

@@ -302,6 +302,72 @@ class Engine:
     def allreduce_q_delta(self):
         self._ck(self.lib.yue_allreduce_q_delta(self.h))
 
+    # shared hot rows + overlapped exchange of the tail (include/yue_b200.h, "multi-GPU, round 2")
+    def hot_tracks(self):
+        n = C.c_int(0)
+        out = np.empty(64, dtype=np.int32)
+        self._ck(self.lib.yue_hot_tracks(self.h, _ptr(out, C.c_int32), C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_hot_tracks(self, tracks, counts, total_events):
+        tracks, counts = _as(tracks, np.int32), _as(counts, np.int64)
+        if len(tracks) != len(counts):
+            raise ValueError("one count per hot track")
+        self._ck(self.lib.yue_set_hot_tracks(self.h, _ptr(tracks, C.c_int32), _ptr(counts, C.c_int64), len(tracks), int(total_events)))
+
+    def hot_table_export(self):
+        """(64-byte CUDA IPC handle, device pointer) of this handle's hot-row table."""
+        buf, p = C.create_string_buffer(64), C.c_void_p()
+        self._ck(self.lib.yue_hot_table_export(self.h, buf, C.byref(p)))
+        return buf.raw, p.value
+
+    def hot_table_open(self, ipc_handle):
+        p = C.c_void_p()
+        self._ck(self.lib.yue_hot_table_open(self.h, C.create_string_buffer(bytes(ipc_handle), 64), C.byref(p)))
+        return p.value
+
+    def enable_peer(self, peer_device):
+        self._ck(self.lib.yue_enable_peer(self.h, int(peer_device)))
+
+    def hot_share(self, nranks, rank, tables):
+        arr = (C.c_void_p * nranks)(*[C.c_void_p(t) if t else C.c_void_p(None) for t in tables])
+        self._ck(self.lib.yue_hot_share(self.h, int(nranks), int(rank), arr))
+
+    def hot_pull(self):
+        self._ck(self.lib.yue_hot_pull(self.h))
+
+    def hot_unshare(self):
+        self._ck(self.lib.yue_hot_unshare(self.h))
+
+    def q_exchange_begin(self):
+        self._ck(self.lib.yue_q_exchange_begin(self.h))
+
+    def q_exchange_reduce(self):
+        self._ck(self.lib.yue_q_exchange_reduce(self.h))
+
+    def q_exchange_reduce_peers(self, deltas):
+        """deltas[r]: rank r's BUF_Q_DELTA pointer in this process (None = own)."""
+        arr = (C.c_void_p * len(deltas))(*[C.c_void_p(t) if t else C.c_void_p(None) for t in deltas])
+        self._ck(self.lib.yue_q_exchange_reduce_peers(self.h, len(deltas), arr))
+
+    def q_exchange_finish(self, quiescent=False):
+        self._ck(self.lib.yue_q_exchange_finish(self.h, 1 if quiescent else 0))
+
+    def stream2_ptr(self):
+        s = C.c_void_p()
+        self._ck(self.lib.yue_stream2(self.h, C.byref(s)))
+        return s.value or 0
+
+    def set_sgd_concurrency(self, n_warps, n_ctas=0):
+        """Warps / CTAs of the Hogwild epoch kernels (0, 0 = automatic)."""
+        self._ck(self.lib.yue_set_sgd_concurrency(self.h, int(n_warps), int(n_ctas)))
+
+    def apr_epoch_part(self, lr, regU, regI, eps, regA, seed, epoch, part, n_parts, slot=0, mode=MODE_HOGWILD, want_loss=True):
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_apr_epoch_part(self.h, lr, regU, regI, eps, regA, seed, epoch, slot, mode, part, n_parts,
+                                             C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
     # -- measurement -----------------------------------------------------------------------
     def timer_start(self):
         self._ck(self.lib.yue_timer_start(self.h))

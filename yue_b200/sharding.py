@@ -182,3 +182,209 @@ class WrmfShardedTrainer:
                 loss = float(lt.item())
         self.eng.sync()
         return loss if want_loss else None
+
+
+# ---- round 2: hot rows as ONE copy over peer memory, the tail exchanged under the next sub-epoch ---------------------------
+def select_hot_tracks(global_counts, hot_max=24, hot_div=128, min_count=16384):
+    """The hot set every rank must agree on (same rule as yue_set_interactions applies to one GPU's log): tracks that are
+    the positive of more than 1/hot_div of ALL events and of at least min_count, most played first (ties: lower id)."""
+    c = np.asarray(global_counts, dtype=np.int64)
+    total = int(c.sum())
+    cand = np.nonzero((c >= min_count) & (c * hot_div > total))[0]
+    cand = cand[np.lexsort((cand, -c[cand]))][:hot_max]
+    return cand.astype(np.int32), c[cand].astype(np.int64), total
+
+
+class ThreadCtl:
+    """Control plane of R ranks that are threads of one process (one Engine per GPU): the class-API path, and the tests."""
+
+    class Shared:
+        def __init__(self, world):
+            import threading
+            self.world, self.barrier, self.slots = world, threading.Barrier(world), [None] * world
+
+    def __init__(self, shared, rank):
+        self.s, self.rank, self.world = shared, rank, shared.world
+
+    def barrier(self):
+        self.s.barrier.wait()
+
+    def allgather(self, obj):
+        self.s.barrier.wait()
+        self.s.slots[self.rank] = obj
+        self.s.barrier.wait()
+        out = list(self.s.slots)
+        self.s.barrier.wait()
+        return out
+
+    def allreduce_sum(self, arr):
+        return np.sum(self.allgather(np.asarray(arr)), axis=0)
+
+
+def run_on_ranks(shared, fn):
+    """fn(rank, ctl) on one thread per rank of a ThreadCtl group; returns the results in rank order.  A rank that raises
+    aborts the group's barrier so that the others do not wait for it forever; the first error is re-raised."""
+    import threading
+    out, errs = [None] * shared.world, []
+
+    def run(r):
+        try:
+            out[r] = fn(r, ThreadCtl(shared, r))
+        except BaseException as exc:                    # noqa: BLE001
+            errs.append(exc)
+            shared.barrier.abort()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(shared.world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        first = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)]
+        raise (first or errs)[0]
+    return out
+
+
+class TorchCtl:
+    """Control plane over torch.distributed (one process per GPU, NCCL or gloo)."""
+
+    def __init__(self, dist, device=None):
+        self.dist, self.rank, self.world, self.device = dist, dist.get_rank(), dist.get_world_size(), device
+
+    def barrier(self):
+        self.dist.barrier()
+
+    def allgather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def allreduce_sum(self, arr):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if self.device is not None:
+            t = t.to(self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+
+class SharedHotTrainer:
+    """One rank of the round-2 trainer (include/yue_b200.h "multi-GPU, round 2").
+
+    * users are sharded (interleaved_users + set_event_offsets keep every rank at the same place of the reference's user
+      stream with the reference's negatives), P rows are private;
+    * the rows of the most played tracks exist ONCE: slot s of the hot-row table lives on rank s % world, every rank's epoch
+      kernel loads and adds it over NVLink -- nothing to reconcile, nothing to overshoot;
+    * the long tail of Q is replicated and exchanged `sub_epochs` times per epoch: delta = Q - snapshot is packed after a
+      part, all-reduced on the handle's second stream WHILE the next part runs, and applied one part late
+      (Q += sum - own, snapshot += sum);
+    * `asynchrony` bounds how many updates are in flight over all ranks: the ranks together run asynchrony x the warps one
+      GPU would give the whole log (tools/staleness_sim.py: the trajectory leaves the 0.5-point gate when the updates of
+      the most played row in flight exceed ~1000; one B200 at full speed is at ~550).
+
+    engine: holds this rank's shard and factors.  ctl: ThreadCtl / TorchCtl.  local_counts[n]: plays per track in the shard.
+    reduce: a callable(engine) that all-reduces BUF_Q_DELTA on the handle's second stream (bench.py passes
+    torch.distributed), or None = chosen here: ranks that are handles of ONE process sum each other's deltas over peer
+    memory (yue_q_exchange_reduce_peers), ranks in different processes use the library's NCCL communicator."""
+
+    def __init__(self, engine, ctl, local_counts, sub_epochs=32, asynchrony=1.0, reserve_sms=8, reduce=None, row_weights=None,
+                 hot_max=24, sm_count=148, warps_per_sm=12, min_events_per_warp=16384):
+        import os
+        from . import engine as _eng
+        self.eng, self.ctl, self.sub_epochs = engine, ctl, int(sub_epochs)
+        counts = ctl.allreduce_sum(np.asarray(local_counts, dtype=np.int64))
+        tracks, tcounts, total = select_hot_tracks(counts, hot_max=hot_max)
+        self.hot_tracks, self.total_events = tracks, total
+        self.hot_share_of_events = float(tcounts.sum()) / max(total, 1)
+        engine.set_hot_tracks(tracks, tcounts, total)
+        # every rank maps every table: a pointer inside one process, a CUDA IPC handle between processes
+        ipc, ptr = engine.hot_table_export()
+        peers = ctl.allgather((os.getpid(), engine.device, ipc, ptr))
+        tables = []
+        for r, (pid, dev, handle, p) in enumerate(peers):
+            if r == ctl.rank:
+                tables.append(None)
+            elif pid == os.getpid():
+                engine.enable_peer(dev)
+                tables.append(p)
+            else:
+                tables.append(engine.hot_table_open(handle))
+        engine.hot_share(ctl.world, ctl.rank, tables)
+        engine.sync()
+        ctl.barrier()                                  # every owner's rows are in its table before anyone trains
+        engine.set_delta_weights(row_weights)
+        engine.q_snapshot()
+        # concurrency: all ranks together = asynchrony x one GPU's automatic choice for the whole log
+        auto = max(1, min(sm_count * warps_per_sm, total // min_events_per_warp))
+        self.n_ctas = max(1, sm_count - (reserve_sms if ctl.world > 1 else 0))
+        self.n_warps = max(1, min(self.n_ctas * warps_per_sm, int(round(asynchrony * auto / ctl.world))))
+        engine.set_sgd_concurrency(self.n_warps, self.n_ctas)
+        if reduce is None and ctl.world > 1:
+            if all(pid == os.getpid() for pid, _, _, _ in peers):
+                # all ranks are handles of this process: every rank sums the ranks' packed deltas itself over peer memory
+                from ._lib import BUF_Q_DELTA
+                ptrs = ctl.allgather(engine.device_buffer(BUF_Q_DELTA)[0])
+                deltas = [None if r == ctl.rank else p for r, p in enumerate(ptrs)]
+
+                def reduce(e):
+                    e.sync()                           # my pack is done ...
+                    ctl.barrier()                      # ... and so is everybody's
+                    e.q_exchange_reduce_peers(deltas)
+                    ctl.barrier()                      # everybody has read my delta: the next pack may overwrite it
+            else:
+                uid = ctl.allgather(_eng.comm_unique_id() if ctl.rank == 0 else None)[0]
+                engine.comm_init(ctl.world, ctl.rank, uid)
+                reduce = lambda e: e.q_exchange_reduce()   # noqa: E731
+        self.reduce = reduce
+        self.pending = False
+
+    def _exchange(self):
+        if self.ctl.world == 1:
+            return
+        if self.pending:
+            self.eng.q_exchange_finish()               # last part's sum has had a whole part to arrive
+        self.eng.q_exchange_begin()
+        self.reduce(self.eng)
+        self.pending = True
+
+    def epoch(self, lr, regU, regI, seed, epoch, want_loss=False, apr=None, finalize=False):
+        """One epoch = sub_epochs parts; returns the local loss (sum over the parts) when want_loss.  apr = (eps, regA[, slot])
+        trains the APR variant (K2a; slot = which of the positive's negatives, APR draws 3).  finalize: see `finalize`."""
+        from ._lib import E_NUMERIC, MODE_HOGWILD, YueError
+        loss, diverged = 0.0, False
+        for part in range(self.sub_epochs):
+            try:
+                if apr is None:
+                    l = self.eng.bpr_epoch_part(lr, regU, regI, seed, epoch, part, self.sub_epochs, MODE_HOGWILD, want_loss=want_loss)
+                else:
+                    l = self.eng.apr_epoch_part(lr, regU, regI, apr[0], apr[1], seed, epoch, part, self.sub_epochs,
+                                                apr[2] if len(apr) > 2 else 0, MODE_HOGWILD, want_loss=want_loss)
+            except YueError as exc:                    # a non-finite loss on THIS rank: keep the collectives of the epoch in step,
+                if exc.code != E_NUMERIC:              # then fail on every rank together
+                    raise
+                l, diverged = float("nan"), True
+            loss += l if want_loss else 0.0
+            self._exchange()
+        if want_loss and self.ctl.world > 1:
+            diverged = bool(self.ctl.allreduce_sum(np.array([1 if diverged else 0], dtype=np.int64))[0] > 0)
+        if diverged:
+            raise YueError(E_NUMERIC, "Loss = NaN or Infinity: current settings does not fit the recommender!")
+        if finalize:
+            self.finalize()
+        return loss if want_loss else None
+
+    def finalize(self):
+        """Apply the exchange still in flight and bring this rank's Q up to date with the shared hot rows (the handle's Q
+        is then complete: yue_get_factors, yue_frob2, ranking).  Training may go on afterwards."""
+        if self.pending:
+            self.eng.q_exchange_finish(quiescent=True)     # nothing trained since the pack: every rank ends with the same bits
+            self.pending = False
+        self.eng.sync()
+        self.ctl.barrier()                             # nobody is still adding to a table
+        self.eng.hot_pull()
+        self.ctl.barrier()                             # nobody's next epoch changes a table while another rank reads it
+
+    def close(self):
+        """Back to private per-launch tables (the handle keeps its complete Q)."""
+        self.finalize()
+        self.eng.hot_unshare()
+        self.eng.set_sgd_concurrency(0, 0)
