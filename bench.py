@@ -476,6 +476,10 @@ def run_native(args):
                  "quality": "outside the gate (profiles/quality_study_r1.md section E: Recall@10 +0.02 against the serial order on 2 GPUs, "
                             "unstable without the weights on 4) -- reported as a throughput ceiling, not as a result"}
 
+    cune = None
+    if world == 1 and args.config == "C2" and not args.no_cune:
+        cune = bench_cune(eng, args)
+
     # ---- config C3's shard on one GPU: Q = 1 GB does not fit in L2, the honest HBM case (N = 1 line only) ----
     c3 = None
     if world == 1 and args.config == "C2" and not args.no_c3:
@@ -529,6 +533,8 @@ def run_native(args):
             out["apr"] = apr
         if wrmf:
             out["wrmf"] = wrmf
+        if cune:
+            out["cune"] = cune
         if c3:
             out["c3"] = c3
 
@@ -551,6 +557,37 @@ def run_native(args):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_cune(eng, args):
+    """one epoch of CUNE's two-level BPR (recommender/advanced/CUNE.py:118-178, K8) on a tenth of config C2's
+    shape -- the similar-user lists CUNE derives from its DeepWalk embedding are synthetic here (two other users per user,
+    none for every fifth), the per-user implicit-positive sets are built from them as CUNE.py:95-113 does."""
+    from yue_b200 import synth
+    from yue_b200.cune import implicit_positive_lists
+    from yue_b200.engine import MODE_HOGWILD
+    users, tracks, plays, d = (100_000, 20_000, 5_000_000, 64) if not args.small else (10_000, 4_000, 300_000, 64)
+    log = synth.power_law_log(users, tracks, plays, SEED + 8, test_ratio=0.0)
+    m = log.m
+    top = {u: [f for f in ((u * 7 + 3) % m, (u * 11 + 5) % m) if f != u] for u in range(m) if u % 5}
+    ip_indptr, ip_items = implicit_positive_lists(m, log.uq_indptr, log.uq_items, top)
+    P, Q = synth.init_factors(log.m, log.n, d, SEED + 9)
+    eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    eng.set_factors(P, Q)
+    eng.cune_set_implicit(ip_indptr, ip_items)
+    T = log.train_size
+    ms = []
+    for ep in range(3):
+        eng.sync()
+        eng.timer_start()
+        eng.cune_epoch(0.02, 0.01, 0.01, 2.0, SEED, ep, MODE_HOGWILD)
+        ms.append(eng.timer_stop())
+    t = min(ms[1:])
+    return {"metric": "cune_events_per_sec", "value": T / (t * 1e-3), "unit": "events/s (3 repeats each)", "ms_per_epoch": t,
+            "kernel": "cune_sgd_kernel<1, kAtomic>", "warps": int(max(1, min(148 * 16, T // 16384))),
+            "workload": "CUNE d=64, s=2, lr 0.02, reg 0.01: %d users x %d tracks x %d events, %d implicit positives" % (m, log.n, T, len(ip_items)),
+            "note": "the number of warps is bounded by the log (one per 16 384 events, like K2: profiles/cune_r2.md); the kernel is a chain of "
+                    "7 dependent dot products + sigmoids per repeat (CUNE.py:134-159 re-evaluates every sigmoid), issue-latency bound"}
 
 
 def bench_c3_shard(eng, args, hbm_peak):
@@ -692,6 +729,7 @@ def main():
     ap.add_argument("--no-throughput-mode", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-c3", action="store_true")
+    ap.add_argument("--no-cune", action="store_true")
     ap.add_argument("--no-rank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-apr", action="store_true")

@@ -1,0 +1,173 @@
+"""yue_b200/ingest.py: the log as numbered events without a Python object per event, and the result
+lines / measures without a Python loop per item -- against the goldens of the reference's own Record (tests/golden/
+record_small.json, produced by oracle/make_golden.py from data/record.py) and against the reference-pinned host classes."""
+import io
+import json
+import os
+import random
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from oracle import record_ref
+from yue_b200 import ingest
+from yue_b200.host.config import Config, LineConfig
+from yue_b200.host.fileio import DataSplit
+from yue_b200.host.measure import Measure
+
+COLUMNS = {"user": 1, "track": 2, "artist": 3, "time": 0}          # record.setup of config/BPR.conf: -columns user:1,track:2,artist:3,time:0
+
+
+def _write_csv(path, events):
+    with open(path, "w") as f:
+        for e in events:
+            f.write("%s,%s,%s,%s\n" % (e["time"], e["user"], e["track"], e["artist"]))
+
+
+def _csr_from_numbered(log):
+    """What K0 builds on the device, in numpy: events grouped by user (stable), sorted-unique play rows."""
+    tr = log.is_test == 0
+    u, it = log.ev_user[tr].astype(np.int64), log.ev_item[tr]
+    order = np.argsort(u, kind="stable")
+    ev_indptr = np.zeros(log.m + 1, np.int64)
+    np.cumsum(np.bincount(u, minlength=log.m), out=ev_indptr[1:])
+    key = np.unique(u * log.n + it)
+    uq_indptr = np.zeros(log.m + 1, np.int64)
+    np.cumsum(np.bincount(key // log.n, minlength=log.m), out=uq_indptr[1:])
+    return ev_indptr, it[order].astype(np.int32), uq_indptr, (key % log.n).astype(np.int32)
+
+
+def test_numbered_events_reproduce_the_reference_records_ids_and_arrays(golden_dir, tmp_path):
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    path = str(tmp_path / "log.txt")
+    _write_csv(path, g["events"])
+    cols = ingest.read_columns(path, COLUMNS, ",")
+    assert list(cols.keys()) == ["user", "track", "artist", "time"] and len(cols["user"]) == len(g["events"])
+    assert cols["track"][0] == g["events"][0]["track"] and cols["time"][1] == g["events"][1]["time"]
+    held = np.array(g["held"], dtype=bool)
+    log = ingest.number_events({k: v[~held] for k, v in cols.items()}, {k: v[held] for k, v in cols.items()}, "track", list(COLUMNS))
+    # ids: the reference's Record, key by key (data/record.py:138-146, 182-188)
+    for kind in ("user", "track", "artist"):
+        assert {name: i for i, name in enumerate(log.names[kind])} == g["name2id"][kind]
+    assert log.train_size == g["recordCount"]
+    # arrays: the oracle's restatement of BPR.py:32-45 on the reference-shaped dicts
+    train = [e for e, h in zip(g["events"], g["held"]) if not h]
+    test = [e for e, h in zip(g["events"], g["held"]) if h]
+    name2id, user_record, test_set = record_ref.preprocess(train, test)
+    want = record_ref.interaction_arrays(name2id, user_record)
+    for a, b in zip(_csr_from_numbered(log), want):
+        assert np.array_equal(a, b)
+    # the Record facade
+    rec = ingest.ArrayRecord(log)
+    assert rec.getSize("user") == len(g["name2id"]["user"]) and rec.getId("u15", "user") == g["name2id"]["user"]["u15"]
+    assert rec.id2name["track"][g["name2id"]["track"]["t5"]] == "t5" and len(rec.trainingData) == g["recordCount"]
+    # test set: held-out pairs minus training pairs, as a CSR (what K0 returns) -> the dict view equals the reference's
+    te = log.is_test == 1
+    tr_key = np.unique(log.ev_user[~te].astype(np.int64) * log.n + log.ev_item[~te])
+    te_key = np.unique(log.ev_user[te].astype(np.int64) * log.n + log.ev_item[te])
+    te_key = te_key[~np.isin(te_key, tr_key)]
+    rec.test_indptr = np.zeros(log.m + 1, np.int64)
+    np.cumsum(np.bincount(te_key // log.n, minlength=log.m), out=rec.test_indptr[1:])
+    rec.test_items = (te_key % log.n).astype(np.int32)
+    assert {u: set(d) for u, d in rec.testSet.items()} == {u: set(d) for u, d in g["testSet"].items()}
+
+
+def test_splits_follow_the_reference(golden_dir, tmp_path):
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    # -ap: one random() per event in file order (tool/dataSplit.py:9-23)
+    random.seed(5)
+    held = ingest.split_ap(len(g["events"]), 0.2)
+    random.seed(5)
+    train, test = DataSplit.dataSplit(g["events"], test_ratio=0.2)
+    assert [e for e, h in zip(g["events"], held) if not h] == train and int(held.sum()) == len(test)
+    # -byTime: the reference's own Record on the first events (golden), ids and per-user training rows
+    bt = g["byTime"]
+    events = g["events"][:bt["n_events"]]
+    path = str(tmp_path / "log.txt")
+    _write_csv(path, events)
+    ev = LineConfig("-target track -byTime 0.2")
+    log = ingest.load_numbered(path, COLUMNS, ",", ev, "track")
+    for kind in ("user", "track"):
+        assert {name: i for i, name in enumerate(log.names[kind])} == bt["name2id"][kind]
+    assert log.train_size == bt["recordCount"]
+    ev_indptr, ev_items, _, _ = _csr_from_numbered(log)
+    for user, tracks in bt["userRecord"].items():
+        u = bt["name2id"]["user"][user]
+        assert [log.names["track"][t] for t in ev_items[ev_indptr[u]:ev_indptr[u + 1]]] == tracks
+
+
+def test_result_lines_and_measures_match_the_loops():
+    rng = np.random.default_rng(3)
+    m, n, N = 300, 500, 10
+    users = np.sort(rng.choice(m, 200, replace=False)).astype(np.int32)
+    ids = np.stack([rng.choice(n, N, replace=False) for _ in users]).astype(np.int32)
+    ids[5, 7:] = -1                                           # a short list (fewer than N unmasked tracks)
+    deg = np.zeros(m, np.int64)
+    deg[users] = rng.integers(1, 8, len(users))
+    test_indptr = np.zeros(m + 1, np.int64)
+    np.cumsum(deg, out=test_indptr[1:])
+    test_items = np.concatenate([np.sort(rng.choice(n, d, replace=False)) for d in deg]).astype(np.int32)
+    for b, u in enumerate(users[:50]):                        # plant hits (exact top-N lists never repeat a track)
+        t = test_items[test_indptr[u]]
+        if t not in ids[b]:
+            ids[b, rng.integers(0, 5)] = t
+    un = np.array(["u%d" % i for i in range(m)], dtype=object)
+    tn = np.array(["t%d" % i for i in range(n)], dtype=object)
+    hits = ingest.hit_mask(users, ids, n, test_indptr, test_items)
+    origin = {un[u]: {tn[t]: 1 for t in test_items[test_indptr[u]:test_indptr[u + 1]]} for u in users}
+    rec = {un[u]: [tn[t] for t in row if t >= 0] for u, row in zip(users, ids)}
+    want_hits = np.array([[t >= 0 and tn[t] in origin[un[u]] for t in row] for u, row in zip(users, ids)])
+    assert np.array_equal(hits, want_hits) and hits.sum() >= 40
+    # IterativeRecommender.py:145-155
+    want_lines = [un[u] + ":" + "".join(item + ("*" if item in origin[un[u]] else "") for item in rec[un[u]]) + "\n" for u in users]
+    assert ingest.result_lines(un[users], tn, ids, hits) == want_lines
+    # evaluation/measure.py:16-41 (+ NDCG)
+    with redirect_stdout(io.StringIO()):
+        want = Measure.rankingMeasure(origin, rec, [5, 10], n)
+        got, ndcg = ingest.ranking_measure(ids, hits, np.diff(test_indptr)[users], [5, 10], n)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.split(":")[0] == b.split(":")[0]
+        if ":" in a:
+            assert float(a.split(":")[1]) == pytest.approx(float(b.split(":")[1]), rel=1e-12, abs=1e-15)
+    for k in (5, 10):
+        assert ndcg[k] == pytest.approx(Measure.NDCG(origin, rec, k), rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_class_api_with_array_ingest_equals_the_dict_path(tmp_path):
+    """Yue -> BPR.execute() with yue.ingest=arrays (C parser, column-wise ids, K0 on the device, array result lines) against
+    the default path (lists of dicts, Record, Python loops): same split (same `random` seed), same initial tables, same
+    sampler seed, serial order -> the same tables bit for bit, the same measures and the same result lines."""
+    from yue_b200 import synth
+    from yue_b200.bpr import BPR
+    from yue_b200.host.driver import Yue
+    log_path = tmp_path / "log.txt"
+    synth.write_csv_log(str(log_path), 1500, 4000, 60000, seed=20260101)
+    out = {}
+    for name in ("dicts", "arrays"):
+        vals = {"record": str(log_path), "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,", "recommender": "BPR",
+                "evaluation.setup": "-target track -ap 0.2", "item.ranking": "-topN 5,10", "num.factors": "10", "num.max.iter": "2",
+                "learnRate": "-init 0.02 -max 1", "reg.lambda": "-u 0.01 -i 0.01 -b 0.2 -s 0.2", "output.setup": "on -dir %s/" % (tmp_path / name),
+                "yue.sgd": "serial", "yue.seed": "77"}
+        if name == "arrays":
+            vals["yue.ingest"] = "arrays"
+        random.seed(5)
+        np.random.seed(11)
+        with redirect_stdout(io.StringIO()):
+            y = Yue(Config(values=vals))
+            model = BPR(y.config, y.trainingData, y.testData)
+            measure = model.execute()
+        files = sorted(os.listdir(tmp_path / name))
+        top = [f for f in files if "-top-" in f][0]
+        out[name] = (model, measure, open(tmp_path / name / top).read().splitlines())
+    (md, meas_d, lines_d), (ma, meas_a, lines_a) = out["dicts"], out["arrays"]
+    assert ma.m == md.m and ma.n == md.n and np.array_equal(ma.P, md.P) and np.array_equal(ma.Q, md.Q)
+    assert len(meas_a) == len(meas_d)
+    for a, b in zip(meas_a, meas_d):
+        assert a.split(":")[0] == b.split(":")[0]
+        if ":" in a:
+            assert float(a.split(":")[1]) == pytest.approx(float(b.split(":")[1]), rel=1e-12, abs=1e-15)
+    # the dict path lists the test users in the order of the test events, the array path in id order: same set of lines
+    assert lines_a[0] == lines_d[0] and sorted(lines_a[1:]) == sorted(lines_d[1:])

@@ -3,7 +3,7 @@
 serial-order run of the same log, on 1..8 GPUs, sweeping sub-epochs and the asynchrony bound.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/quality_mgpu.py \
-        [--log users,tracks,plays] [--epochs E] [--sub-epochs 8,32] [--asynchrony 1,2,4] [--no-serial r,n] [--time-c2]
+        [--size users,tracks,plays] [--epochs E] [--sub-epochs 8,32] [--asynchrony 1,2,4] [--no-serial r,n] [--time-c2]
 
 Every rank generates the same log (same seed) and keeps the users rank, rank+N, ...; rank 0 also trains the serial order
 (the reference's loop order) unless --no-serial gives its numbers.  One line per configuration; see yue_b200/quality.py."""
@@ -22,7 +22,7 @@ from yue_b200.engine import MODE_HOGWILD, MODE_SERIAL  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--log", default="")
+    ap.add_argument("--size", default="")
     ap.add_argument("--epochs", type=int, default=0)
     ap.add_argument("--sub-epochs", default="32")
     ap.add_argument("--asynchrony", default="1")
@@ -39,8 +39,8 @@ def main():
                             init_method=None if "MASTER_ADDR" in os.environ else "tcp://127.0.0.1:29511",
                             rank=rank, world_size=world)
     spec = dict(quality.QUALITY_LOG)
-    if args.log:
-        spec["users"], spec["tracks"], spec["plays"] = (int(x) for x in args.log.split(","))
+    if args.size:
+        spec["users"], spec["tracks"], spec["plays"] = (int(x) for x in args.size.split(","))
     if args.epochs:
         spec["epochs"] = args.epochs
     log, P, Q = quality.make_log(spec)

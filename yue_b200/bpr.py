@@ -67,6 +67,12 @@ class GpuBPRMixin(object):
             self._engine = Engine(dev)
             arrays = getattr(self.data, 'interaction_arrays', None)
             self._test_on_device = False
+            if hasattr(self.data, 'log'):                       # yue.ingest=arrays (ingest.ArrayRecord): numbered events -> K0
+                self.data.log.upload(self._engine)
+                self.data.test_indptr, self.data.test_items = self._engine.get_test_set()
+                self._test_on_device = True
+                self._synced = (None, None)
+                return self._engine
             if self._opt('yue.ingest', 'host') == 'device':
                 # Record's containers as numbered events: every training event per user in file order
                 # (userRecord, data/record.py:147-150), then the held-out pairs (testSet, 182-192)
@@ -260,12 +266,45 @@ class GpuBPRMixin(object):
         sharding.run_on_ranks(sharding.ThreadCtl.Shared(world), rank)
         return ids, scores
 
+    def _eval_ranking_arrays(self, top, N):
+        """evalRanking over ingest.ArrayRecord: every step on arrays -- ranking (K3/K5), the measures (K6) and the hit marks
+        of the result lines (one sorted search); the only per-user Python left is joining a line's cells."""
+        from .ingest import hit_mask, ranking_measure, result_lines
+        eng = self._push_factors()
+        data = self.data
+        uid = np.flatnonzero(np.diff(data.test_indptr) > 0).astype(np.int32)
+        devs = self._devices()
+        if len(devs) > 1 and len(uid) >= 2 * len(devs):
+            ids, _ = self._rank_on_devices(eng, devs, uid, N)
+        else:
+            ids, _ = eng.rank_topn(uid, N, RANK_AUTO)
+        un, tn = data.log.names['user'], data.log.names[self.recType]
+        hits = hit_mask(uid, ids, self.n, data.test_indptr, data.test_items)
+        res = ['userId: recommendations in (itemId, ranking score) pairs, * means the item matches.\n'] + result_lines(un[uid], tn, ids, hits)
+        self.rec_ids, self.rec_users = ids, uid
+        if self._opt('yue.metrics', 'host') == 'device' and len(devs) == 1:
+            measure, ndcg = self._format_device_measure(uid, top)      # K6 over the lists the call left on the device
+        else:
+            measure, ndcg = ranking_measure(ids, hits, np.diff(data.test_indptr)[uid], top, self.n)
+        return res, measure, ndcg
+
     def evalRanking(self):
         top = [int(num) for num in self.ranking['-topN'].split(',')]
         N = max(top)
         if N > 100 or N < 0:
             print('N can not be larger than 100! It has been reassigned with 10')
             N = 10
+        if hasattr(self.data, 'log'):
+            res, self.measure, self.ndcg = self._eval_ranking_arrays(top, N)
+            currentTime = strftime("%Y-%m-%d %H-%M-%S", localtime(time()))
+            outDir = self.output['-dir']
+            if self.isOutput:
+                FileIO.writeFile(outDir, self.config['recommender'] + '@' + currentTime + '-top-' + self.ranking['-topN'] + 'items'
+                                 + self.foldInfo + '.txt', res)
+                print('The result has been output to ', abspath(outDir), '.')
+            FileIO.writeFile(outDir, self.config['recommender'] + '@' + currentTime + '-measure' + self.foldInfo + '.txt', self.measure)
+            print('The result of %s %s:\n%s' % (self.algorName, self.foldInfo, ''.join(self.measure)))
+            return
         users = list(self.data.testSet.keys())
         recList, _, _ = self._topn_lists(users, N)
         res = ['userId: recommendations in (itemId, ranking score) pairs, * means the item matches.\n']

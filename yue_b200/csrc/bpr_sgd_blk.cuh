@@ -359,13 +359,17 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
         int u = cur_u, len = 0;
         bool resync = false;
         int32_t my_i = 0, my_j = 0;
-        BlkRows<V> cur, nxt;
+        // two row buffers that swap roles every block (the block being computed / the block whose loads are in flight):
+        // the body below exists twice, once per assignment, selected by a warp-uniform bit -- a copy `cur = nxt` per
+        // block was 44 MOVs, 9.4 of the 158 instructions per triplet (profiles/ncu_summary_r1.md)
+        BlkRows<V> rowsA, rowsB;
+        bool flip = false;                                   // false: cur = rowsA, nxt = rowsB
 #pragma unroll
         for (int a = 0; a < kBlkK; ++a) {
-            cur.pi[a] = cur.pj[a] = nullptr;
-            cur.dx[a] = 0;
+            rowsA.pi[a] = rowsA.pj[a] = nullptr;
+            rowsA.dx[a] = 0;
 #pragma unroll
-            for (int v = 0; v < V; ++v) cur.qi[a][v] = cur.qj[a][v] = cur.ex[a][v] = 0.f;
+            for (int v = 0; v < V; ++v) rowsA.qi[a][v] = rowsA.qj[a][v] = rowsA.ex[a][v] = 0.f;
         }
         for (int64_t seg = sb - 1; seg < se; ++seg) {
             const int nblk = (len + kBlkK - 1) / kBlkK;
@@ -398,171 +402,179 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                     na = fa; nb = fb;
                     if (seg + 3 < se) load_rec(seg + 3, fa, fb);
                 }
-                // ---- loads of the next block: block b+1 of this segment, or block 0 of the next one ----
-                if (!last || has_next) {
-                    const int32_t src_i = last ? n_i : my_i, src_j = last ? n_j : my_j;
-                    const int src_len = last ? n_len : len, t0 = last ? 0 : kBlkK * (b + 1);
+                auto half = [&](BlkRows<V>& cur, BlkRows<V>& nxt) {
+                    // ---- loads of the next block: block b+1 of this segment, or block 0 of the next one ----
+                    if (!last || has_next) {
+                        const int32_t src_i = last ? n_i : my_i, src_j = last ? n_j : my_j;
+                        const int src_len = last ? n_len : len, t0 = last ? 0 : kBlkK * (b + 1);
 #pragma unroll
-                    for (int a = 0; a < kBlkK; ++a) {
-                        const int t = t0 + a;                               // <= 31
-                        const int32_t it = __shfl_sync(full, src_i, t), jt = __shfl_sync(full, src_j, t);
-                        nxt.dx[a] = 0;
-                        if (t < src_len) {
-                            nxt.pi[a] = q_ptr(it); nxt.pj[a] = q_ptr(jt);
-                            ldq(nxt.pi[a], nxt.qi[a]);
-                            ldq(nxt.pj[a], nxt.qj[a]);
-                            if (it < 0) {                                   // a sharded hot positive: fetch its second row too
-                                nxt.dx[a] = hot_dx[-it - 1];
-                                if (nxt.dx[a]) ldq(reinterpret_cast<float*>(reinterpret_cast<char*>(nxt.pi[a]) + nxt.dx[a]), nxt.ex[a]);
+                        for (int a = 0; a < kBlkK; ++a) {
+                            const int t = t0 + a;                               // <= 31
+                            const int32_t it = __shfl_sync(full, src_i, t), jt = __shfl_sync(full, src_j, t);
+                            nxt.dx[a] = 0;
+                            if (t < src_len) {
+                                nxt.pi[a] = q_ptr(it); nxt.pj[a] = q_ptr(jt);
+                                ldq(nxt.pi[a], nxt.qi[a]);
+                                ldq(nxt.pj[a], nxt.qj[a]);
+                                if (it < 0) {                                   // a sharded hot positive: fetch its second row too
+                                    nxt.dx[a] = hot_dx[-it - 1];
+                                    if (nxt.dx[a]) ldq(reinterpret_cast<float*>(reinterpret_cast<char*>(nxt.pi[a]) + nxt.dx[a]), nxt.ex[a]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < V; ++v) nxt.qi[a][v] = nxt.qj[a][v] = 0.f;
+                            }
+                        }
+                    }
+                    if (b < nblk) {
+                        // ---- K2: block b of the current segment ----------------------------------------
+                        const int nbk = len - kBlkK * b;                        // >= 1 triplets in this block
+                        if (resync && b > 0 && (b & p.resync_mask) == 0) sync_user(u);
+                        float d[kBlkK][V];
+#pragma unroll
+                        for (int a = 0; a < kBlkK; ++a) {
+                            if (cur.dx[a]) {                                    // logical row of a sharded positive = sum of its rows
+#pragma unroll
+                                for (int v = 0; v < V; ++v) cur.qi[a][v] += cur.ex[a][v];
+                            }
+#pragma unroll
+                            for (int v = 0; v < V; ++v) d[a][v] = cur.qi[a][v] - cur.qj[a][v];   // Q[i] - Q[j], old rows (BPR.py:51)
+                        }
+                        if constexpr (!APR) {
+                            float x[10];
+#pragma unroll
+                            for (int a = 0; a < kBlkK; ++a) {
+                                float s = 0.f;
+#pragma unroll
+                                for (int v = 0; v < V; ++v) s = fmaf(pu[v], d[a][v], s);
+                                x[a] = s;
+                            }
+                            {
+                                int g = 4;
+#pragma unroll
+                                for (int a = 0; a < kBlkK; ++a)
+#pragma unroll
+                                    for (int c = a + 1; c < kBlkK; ++c) {
+                                        float s = 0.f;
+#pragma unroll
+                                        for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
+                                        x[g++] = s;                              // order: 01 02 03 12 13 23
+                                    }
+                            }
+                            warp_allreduce10(x, lane);
+                            // scalar recurrence: w_c = P_a . d_c for the current a
+                            float g[kBlkK];
+                            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                            g[0] = bpr_grad(x[0], p.lr, l0);
+                            float w1 = cu1 * fmaf(g[0], x[4], x[1]);
+                            float w2 = cu1 * fmaf(g[0], x[5], x[2]);
+                            float w3 = cu1 * fmaf(g[0], x[6], x[3]);
+                            g[1] = bpr_grad(w1, p.lr, l1);
+                            w2 = cu1 * fmaf(g[1], x[7], w2);
+                            w3 = cu1 * fmaf(g[1], x[8], w3);
+                            g[2] = bpr_grad(w2, p.lr, l2);
+                            w3 = cu1 * fmaf(g[2], x[9], w3);
+                            g[3] = bpr_grad(w3, p.lr, l3);
+                            loss += (double)(l0 + (nbk > 1 ? l1 : 0.f) + (nbk > 2 ? l2 : 0.f) + (nbk > 3 ? l3 : 0.f));
+                            // row updates in the reference's order (BPR.py:51-57): P first, Q with the updated P,
+                            // then the three multiplicative shrinks; Q changes leave as deltas (vector atomics)
+#pragma unroll
+                            for (int a = 0; a < kBlkK; ++a) {
+                                if (a < nbk) {
+                                    const float ga = g[a];
+                                    float di[V], dj[V];
+#pragma unroll
+                                    for (int v = 0; v < V; ++v) {
+                                        const float pn = fmaf(ga, d[a][v], pu[v]);
+                                        const float gp = ga * pn;
+                                        di[v] = fmaf(-p.c_i, cur.qi[a][v] + gp, gp);    // (q + g p)(1 - c) - q
+                                        dj[v] = fmaf(-p.c_i, cur.qj[a][v] - gp, -gp);
+                                        pu[v] = fmaf(-p.c_u, pn, pn);
+                                    }
+                                    redq(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
+                                    redq(cur.pj[a], dj);
+                                }
                             }
                         } else {
+                            // K2a, APR (recommender/advanced/APR.py:25-76, oracle/apr_ref.py): per triplet, from the OLD rows,
+                            //   y_adv = y - 2 eps |P| - eps |d| + 2 eps^2 y / (|P||d|),  a = lr (s0 + regA s1),  b = lr regA s1 eps,
+                            //   P <- c (alpha P + a d),  alpha = 1 - 2 b / |P|;   Q[i] += a P - (b/|d|) d,  Q[j] -= the same
+                            // The block needs |d_a|^2 and |P_0|^2 besides the 10 dots of BPR (16 reduced values); then
+                            //   P_{a+1}.d_c = c (alpha w_c + a G_ac),   |P_{a+1}|^2 = c^2 (alpha^2 |P_a|^2 + 2 alpha a w_a + a^2 G_aa).
+                            float x[16];
+                            float pp = 0.f;
 #pragma unroll
-                            for (int v = 0; v < V; ++v) nxt.qi[a][v] = nxt.qj[a][v] = 0.f;
-                        }
-                    }
-                }
-                if (b < nblk) {
-                    // ---- K2: block b of the current segment ----------------------------------------
-                    const int nbk = len - kBlkK * b;                        // >= 1 triplets in this block
-                    if (resync && b > 0 && (b & p.resync_mask) == 0) sync_user(u);
-                    float d[kBlkK][V];
+                            for (int v = 0; v < V; ++v) pp = fmaf(pu[v], pu[v], pp);
 #pragma unroll
-                    for (int a = 0; a < kBlkK; ++a) {
-                        if (cur.dx[a]) {                                    // logical row of a sharded positive = sum of its rows
+                            for (int a = 0; a < kBlkK; ++a) {
+                                float s = 0.f, q = 0.f;
 #pragma unroll
-                            for (int v = 0; v < V; ++v) cur.qi[a][v] += cur.ex[a][v];
-                        }
-#pragma unroll
-                        for (int v = 0; v < V; ++v) d[a][v] = cur.qi[a][v] - cur.qj[a][v];   // Q[i] - Q[j], old rows (BPR.py:51)
-                    }
-                    if constexpr (!APR) {
-                        float x[10];
-#pragma unroll
-                        for (int a = 0; a < kBlkK; ++a) {
-                            float s = 0.f;
-#pragma unroll
-                            for (int v = 0; v < V; ++v) s = fmaf(pu[v], d[a][v], s);
-                            x[a] = s;
-                        }
-                        {
-                            int g = 4;
-#pragma unroll
-                            for (int a = 0; a < kBlkK; ++a)
-#pragma unroll
-                                for (int c = a + 1; c < kBlkK; ++c) {
-                                    float s = 0.f;
-#pragma unroll
-                                    for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
-                                    x[g++] = s;                              // order: 01 02 03 12 13 23
-                                }
-                        }
-                        warp_allreduce10(x, lane);
-                        // scalar recurrence: w_c = P_a . d_c for the current a
-                        float g[kBlkK];
-                        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                        g[0] = bpr_grad(x[0], p.lr, l0);
-                        float w1 = cu1 * fmaf(g[0], x[4], x[1]);
-                        float w2 = cu1 * fmaf(g[0], x[5], x[2]);
-                        float w3 = cu1 * fmaf(g[0], x[6], x[3]);
-                        g[1] = bpr_grad(w1, p.lr, l1);
-                        w2 = cu1 * fmaf(g[1], x[7], w2);
-                        w3 = cu1 * fmaf(g[1], x[8], w3);
-                        g[2] = bpr_grad(w2, p.lr, l2);
-                        w3 = cu1 * fmaf(g[2], x[9], w3);
-                        g[3] = bpr_grad(w3, p.lr, l3);
-                        loss += (double)(l0 + (nbk > 1 ? l1 : 0.f) + (nbk > 2 ? l2 : 0.f) + (nbk > 3 ? l3 : 0.f));
-                        // row updates in the reference's order (BPR.py:51-57): P first, Q with the updated P,
-                        // then the three multiplicative shrinks; Q changes leave as deltas (vector atomics)
-#pragma unroll
-                        for (int a = 0; a < kBlkK; ++a) {
-                            if (a < nbk) {
-                                const float ga = g[a];
-                                float di[V], dj[V];
-#pragma unroll
-                                for (int v = 0; v < V; ++v) {
-                                    const float pn = fmaf(ga, d[a][v], pu[v]);
-                                    const float gp = ga * pn;
-                                    di[v] = fmaf(-p.c_i, cur.qi[a][v] + gp, gp);    // (q + g p)(1 - c) - q
-                                    dj[v] = fmaf(-p.c_i, cur.qj[a][v] - gp, -gp);
-                                    pu[v] = fmaf(-p.c_u, pn, pn);
-                                }
-                                redq(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
-                                redq(cur.pj[a], dj);
+                                for (int v = 0; v < V; ++v) { s = fmaf(pu[v], d[a][v], s); q = fmaf(d[a][v], d[a][v], q); }
+                                x[a] = s; x[10 + a] = q;
                             }
-                        }
-                    } else {
-                        // K2a, APR (recommender/advanced/APR.py:25-76, oracle/apr_ref.py): per triplet, from the OLD rows,
-                        //   y_adv = y - 2 eps |P| - eps |d| + 2 eps^2 y / (|P||d|),  a = lr (s0 + regA s1),  b = lr regA s1 eps,
-                        //   P <- c (alpha P + a d),  alpha = 1 - 2 b / |P|;   Q[i] += a P - (b/|d|) d,  Q[j] -= the same
-                        // The block needs |d_a|^2 and |P_0|^2 besides the 10 dots of BPR (16 reduced values); then
-                        //   P_{a+1}.d_c = c (alpha w_c + a G_ac),   |P_{a+1}|^2 = c^2 (alpha^2 |P_a|^2 + 2 alpha a w_a + a^2 G_aa).
-                        float x[16];
-                        float pp = 0.f;
+                            {
+                                int g = 4;
 #pragma unroll
-                        for (int v = 0; v < V; ++v) pp = fmaf(pu[v], pu[v], pp);
+                                for (int a = 0; a < kBlkK; ++a)
 #pragma unroll
-                        for (int a = 0; a < kBlkK; ++a) {
-                            float s = 0.f, q = 0.f;
+                                    for (int c = a + 1; c < kBlkK; ++c) {
+                                        float s = 0.f;
 #pragma unroll
-                            for (int v = 0; v < V; ++v) { s = fmaf(pu[v], d[a][v], s); q = fmaf(d[a][v], d[a][v], q); }
-                            x[a] = s; x[10 + a] = q;
-                        }
-                        {
-                            int g = 4;
+                                        for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
+                                        x[g++] = s;
+                                    }
+                            }
+                            x[14] = pp; x[15] = 0.f;
+                            warp_allreduce16(x, lane);
+                            float w[kBlkK] = {x[0], x[1], x[2], x[3]};
+                            const float G[kBlkK][kBlkK] = {{x[10], x[4], x[5], x[6]}, {x[4], x[11], x[7], x[8]},
+                                                           {x[5], x[7], x[12], x[9]}, {x[6], x[8], x[9], x[13]}};
+                            float np2 = x[14], lsum = 0.f;
+                            float ca[kBlkK], calpha[kBlkK], cbd[kBlkK];           // a, alpha, b/|d| of each triplet
 #pragma unroll
-                            for (int a = 0; a < kBlkK; ++a)
+                            for (int a = 0; a < kBlkK; ++a) {
+                                const float y = w[a];
+                                const float inp = np2 > 0.f ? rsqrtf(np2) : 0.f, ind = G[a][a] > 0.f ? rsqrtf(G[a][a]) : 0.f;
+                                const float n_p = np2 * inp, n_d = G[a][a] * ind;
+                                const float ya = y - 2.f * p.eps * n_p - p.eps * n_d + 2.f * p.eps * p.eps * y * inp * ind;
+                                const float e0 = __expf(-fabsf(y)), e1 = __expf(-fabsf(ya));
+                                const float s0 = __fdividef(y >= 0.f ? e0 : 1.f, 1.f + e0);      // sigmoid(-y)
+                                const float s1 = __fdividef(ya >= 0.f ? e1 : 1.f, 1.f + e1);
+                                if (a < nbk) lsum += fmaxf(-y, 0.f) + __logf(1.f + e0) + p.regA * (fmaxf(-ya, 0.f) + __logf(1.f + e1));
+                                const float aa = p.lr * (s0 + p.regA * s1), bb = p.lr * p.regA * s1 * p.eps;
+                                const float alpha = 1.f - 2.f * bb * inp;
+                                ca[a] = aa; calpha[a] = alpha; cbd[a] = bb * ind;
+                                np2 = cu1 * cu1 * (alpha * alpha * np2 + 2.f * alpha * aa * w[a] + aa * aa * G[a][a]);
 #pragma unroll
-                                for (int c = a + 1; c < kBlkK; ++c) {
-                                    float s = 0.f;
+                                for (int c = a + 1; c < kBlkK; ++c) w[c] = cu1 * (alpha * w[c] + aa * G[a][c]);
+                            }
+                            loss += (double)lsum;
 #pragma unroll
-                                    for (int v = 0; v < V; ++v) s = fmaf(d[a][v], d[c][v], s);
-                                    x[g++] = s;
+                            for (int a = 0; a < kBlkK; ++a) {
+                                if (a < nbk) {
+                                    float di[V], dj[V];
+#pragma unroll
+                                    for (int v = 0; v < V; ++v) {
+                                        const float step = fmaf(ca[a], pu[v], -cbd[a] * d[a][v]);      // a P - (b/|d|) d, old P
+                                        const float pn = fmaf(calpha[a], pu[v], ca[a] * d[a][v]);
+                                        di[v] = fmaf(-p.c_i, cur.qi[a][v] + step, step);
+                                        dj[v] = fmaf(-p.c_i, cur.qj[a][v] - step, -step);
+                                        pu[v] = fmaf(-p.c_u, pn, pn);
+                                    }
+                                    redq(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
+                                    redq(cur.pj[a], dj);
                                 }
-                        }
-                        x[14] = pp; x[15] = 0.f;
-                        warp_allreduce16(x, lane);
-                        float w[kBlkK] = {x[0], x[1], x[2], x[3]};
-                        const float G[kBlkK][kBlkK] = {{x[10], x[4], x[5], x[6]}, {x[4], x[11], x[7], x[8]},
-                                                       {x[5], x[7], x[12], x[9]}, {x[6], x[8], x[9], x[13]}};
-                        float np2 = x[14], lsum = 0.f;
-                        float ca[kBlkK], calpha[kBlkK], cbd[kBlkK];           // a, alpha, b/|d| of each triplet
-#pragma unroll
-                        for (int a = 0; a < kBlkK; ++a) {
-                            const float y = w[a];
-                            const float inp = np2 > 0.f ? rsqrtf(np2) : 0.f, ind = G[a][a] > 0.f ? rsqrtf(G[a][a]) : 0.f;
-                            const float n_p = np2 * inp, n_d = G[a][a] * ind;
-                            const float ya = y - 2.f * p.eps * n_p - p.eps * n_d + 2.f * p.eps * p.eps * y * inp * ind;
-                            const float e0 = __expf(-fabsf(y)), e1 = __expf(-fabsf(ya));
-                            const float s0 = __fdividef(y >= 0.f ? e0 : 1.f, 1.f + e0);      // sigmoid(-y)
-                            const float s1 = __fdividef(ya >= 0.f ? e1 : 1.f, 1.f + e1);
-                            if (a < nbk) lsum += fmaxf(-y, 0.f) + __logf(1.f + e0) + p.regA * (fmaxf(-ya, 0.f) + __logf(1.f + e1));
-                            const float aa = p.lr * (s0 + p.regA * s1), bb = p.lr * p.regA * s1 * p.eps;
-                            const float alpha = 1.f - 2.f * bb * inp;
-                            ca[a] = aa; calpha[a] = alpha; cbd[a] = bb * ind;
-                            np2 = cu1 * cu1 * (alpha * alpha * np2 + 2.f * alpha * aa * w[a] + aa * aa * G[a][a]);
-#pragma unroll
-                            for (int c = a + 1; c < kBlkK; ++c) w[c] = cu1 * (alpha * w[c] + aa * G[a][c]);
-                        }
-                        loss += (double)lsum;
-#pragma unroll
-                        for (int a = 0; a < kBlkK; ++a) {
-                            if (a < nbk) {
-                                float di[V], dj[V];
-#pragma unroll
-                                for (int v = 0; v < V; ++v) {
-                                    const float step = fmaf(ca[a], pu[v], -cbd[a] * d[a][v]);      // a P - (b/|d|) d, old P
-                                    const float pn = fmaf(calpha[a], pu[v], ca[a] * d[a][v]);
-                                    di[v] = fmaf(-p.c_i, cur.qi[a][v] + step, step);
-                                    dj[v] = fmaf(-p.c_i, cur.qj[a][v] - step, -step);
-                                    pu[v] = fmaf(-p.c_u, pn, pn);
-                                }
-                                redq(reinterpret_cast<float*>(reinterpret_cast<char*>(cur.pi[a]) + ((warp & 1) ? cur.dx[a] : 0)), di);
-                                redq(cur.pj[a], dj);
                             }
                         }
                     }
+                };
+                if constexpr (V <= 2) {
+                    if (flip) half(rowsB, rowsA); else half(rowsA, rowsB);
+                    flip = !flip;
+                } else {                                     // 128 floats per row: two bodies do not fit the register file (spills)
+                    half(rowsA, rowsB);
+                    rowsA = rowsB;
                 }
-                cur = nxt;
             }
             if (!has_next) break;
             // ---- switch to segment seg+1: its first block is already in flight ------------------

@@ -55,6 +55,14 @@ class Yue(object):
 
         def load(path):
             return FileIO.loadDataSet(path, columns=columns, binarized=binarized, threshold=bottom, delim=delim)
+        if self.config.contains('yue.ingest') and self.config['yue.ingest'] == 'arrays' and not self.evaluation.contains('-cv') \
+                and not binarized:
+            # the log as numbered events, without a Python object per event (yue_b200/ingest.py)
+            from ..ingest import load_numbered
+            target = self.evaluation['-target'] if self.evaluation.contains('-target') else 'track'
+            self.trainingData = load_numbered(config['record'], columns, delim, self.evaluation, target)
+            print('preprocessing...')
+            return
         if self.evaluation.contains('-testSet'):
             self.trainingData = load(config['record'])
             self.testData = load(self.evaluation['-testSet'])

@@ -18,11 +18,15 @@ class Recommender(object):
         self.isSaveModel = False
         self.isLoadModel = False
         self.isOutput = True
-        self.data = Record(self.config, trainingSet, testSet)
+        from ..ingest import ArrayLog, ArrayRecord
+        arrays = isinstance(trainingSet, ArrayLog)             # yue.ingest=arrays: numbered events instead of lists of dicts
+        self.data = ArrayRecord(trainingSet) if arrays else Record(self.config, trainingSet, testSet)
         self.foldInfo = fold
         self.evalConfig = LineConfig(self.config['evaluation.setup'])
         self.recType = self.evalConfig['-target'] if self.evalConfig.contains('-target') else 'track'
         self.measure = []
+        if arrays and (self.evalConfig.contains('-cold') or self.evalConfig.contains('-sample')):
+            raise NotImplementedError('-cold / -sample edit the dict form of the test set: not available with yue.ingest=arrays')
         if self.evalConfig.contains('-cold'):
             # keep only held-out tracks with at most `threshold` training plays (recommender.py:22-42)
             threshold = int(self.evalConfig['-cold'])

@@ -1,0 +1,233 @@
+"""The steps either side of the hot path without per-event Python.
+
+Before: log file -> numbered events.  The reference reads the log line by line into a list of dicts
+(tool/file.py:23-52), splits it with one `random()` per event (tool/dataSplit.py:9-23) and hands out ids by first appearance
+while walking those dicts (data/record.py:138-146, 182-188) -- microseconds of interpreter per event, minutes at config
+C2's 50 M events.  Here the file goes through a C parser into columns, ids are first-appearance codes of whole columns
+(`pandas.factorize`: the same order, training events first, test events extending the maps), and the numbered events go to
+the device, where K0 (yue_ingest_events) builds the event CSR, the play sets and the test sets.
+
+After: ranked ids -> result lines.  IterativeRecommender.py:145-155 builds `user:` + track names, `*` after a hit, one
+Python loop per user and per item; here the hits are one sorted search over (user, track) keys and the lines are built
+column-wise.
+
+`ArrayRecord` gives the recommender classes the part of the reference's Record interface they use (name2id / id2name /
+getId / getSize / testSet) on top of the arrays; the dict views are built only when somebody asks for them.
+"""
+import re
+
+import numpy as np
+
+
+class ArrayLog(object):
+    """Numbered events of one log: ids by first appearance (training events first), file order kept."""
+
+    def __init__(self, ev_user, ev_item, is_test, names, rec_type):
+        self.ev_user, self.ev_item, self.is_test = ev_user, ev_item, is_test
+        self.names, self.rec_type = names, rec_type            # names[kind] = array of names, index = id
+        self.m, self.n = len(names['user']), len(names[rec_type])
+
+    @property
+    def train_size(self):
+        return int(len(self.is_test) - int(self.is_test.sum()))
+
+    def upload(self, engine):
+        engine.ingest_events(self.m, self.n, self.ev_user, self.ev_item, self.is_test)
+
+
+def read_columns(path, columns, delim=''):
+    """The named columns of a log file as arrays of strings, in file order (tool/file.py:23-40: fields split on `delim`,
+    default comma / blank / tab; `columns` = {name: field index} in record.setup's -columns order)."""
+    import pandas as pd
+    names = list(columns.keys())
+    where = [int(columns[k]) for k in names]
+    if len(names) < 2:
+        print('The dataset needs more information or the record.setup setting has some problems...')
+        exit(-1)
+    sep = delim if delim != '' else ',| |\t'
+    single = len(sep) == 1 and not re.escape(sep) != sep
+    try:
+        df = pd.read_csv(path, sep=sep, header=None, usecols=sorted(set(where)), dtype=str, engine='c' if single else 'python',
+                         keep_default_na=False, skipinitialspace=False, quoting=3)
+    except (ValueError, IndexError):
+        print('The record file is not in a correct format.')
+        exit(-1)
+    return {name: df[ind].to_numpy(dtype=object) for name, ind in zip(names, where)}
+
+
+def split_ap(count, test_ratio):
+    """tool/dataSplit.py:9-23: event e goes to the test set when random() < ratio -- the same global `random` stream, one
+    draw per event in file order, so a seeded run splits exactly like the reference's."""
+    from random import random
+    if test_ratio >= 1 or test_ratio <= 0:
+        test_ratio = 0.3
+    return np.fromiter((random() < test_ratio for _ in range(count)), dtype=bool, count=count)
+
+
+def number_events(train, test, rec_type='track', key_order=None):
+    """train / test: {column name: array of strings} (test may be None).  Ids per column by first appearance over the
+    training events, then the test events (data/record.py:138-146, 182-188).  Returns an ArrayLog whose events are the
+    training events in order followed by the test events."""
+    import pandas as pd
+    names = {}
+    codes = {}
+    nt = len(train['user'])
+    for kind in (key_order or train.keys()):
+        if kind == 'time':
+            continue
+        col = train[kind] if test is None else np.concatenate([train[kind], test[kind]])
+        c, uniq = pd.factorize(col, sort=False)
+        codes[kind], names[kind] = c.astype(np.int32), np.asarray(uniq, dtype=object)
+    is_test = np.zeros(len(codes['user']), dtype=np.uint8)
+    is_test[nt:] = 1
+    return ArrayLog(codes['user'], codes[rec_type], is_test, names, rec_type)
+
+
+def by_time(cols, ratio):
+    """data/record.py:108-123: per user (in order of first appearance) the events sorted by their `time` field AS STRINGS
+    (the loader keeps fields as text), the first int(len * (1 - ratio)) for training, the rest for test.  Returns the two
+    index arrays into the file's events, each in the reference's order (user by user)."""
+    import pandas as pd
+    ucode, _ = pd.factorize(cols['user'], sort=False)
+    order = np.lexsort((np.arange(len(ucode)), cols['time'].astype(str), ucode))       # user, then time string, then file order
+    u_sorted = ucode[order]
+    start = np.flatnonzero(np.r_[True, u_sorted[1:] != u_sorted[:-1]])
+    length = np.diff(np.r_[start, len(order)])
+    rank_in_user = np.arange(len(order)) - np.repeat(start, length)
+    cut = (length * (1 - ratio)).astype(np.int64)
+    is_train = rank_in_user < np.repeat(cut, length)
+    return order[is_train], order[~is_train]
+
+
+def load_numbered(path, columns, delim, evaluation, rec_type='track'):
+    """File -> ArrayLog under the reference's evaluation.setup options -ap r / -testSet file / -byTime r (yue.py:38-46)."""
+    cols = read_columns(path, columns, delim)
+    order = [k for k in columns.keys()]
+    if evaluation.contains('-testSet'):
+        return number_events(cols, read_columns(evaluation['-testSet'], columns, delim), rec_type, order)
+    if evaluation.contains('-ap'):
+        held = split_ap(len(cols['user']), float(evaluation['-ap']))
+        return number_events({k: v[~held] for k, v in cols.items()}, {k: v[held] for k, v in cols.items()}, rec_type, order)
+    if evaluation.contains('-byTime'):
+        tr, te = by_time(cols, float(evaluation['-byTime']))
+        return number_events({k: v[tr] for k, v in cols.items()}, {k: v[te] for k, v in cols.items()}, rec_type, order)
+    return number_events(cols, None, rec_type, order)
+
+
+class _IdToName(object):
+    """id2name[kind][id] over an array."""
+
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __getitem__(self, i):
+        return self.arr[int(i)]
+
+    def __len__(self):
+        return len(self.arr)
+
+
+class ArrayRecord(object):
+    """The slice of data/record.py's interface the GPU recommenders use, over an ArrayLog."""
+
+    def __init__(self, log):
+        self.log = log
+        self.trainingData = range(log.train_size)              # len() is all anybody asks of it (BPR.py:28)
+        self.recordCount = log.train_size
+        self.id2name = {k: _IdToName(v) for k, v in log.names.items()}
+        self._name2id, self._test = {}, None
+        self.test_indptr = self.test_items = None              # set by the recommender from the device (K0)
+
+    class _Lazy(dict):
+        def __init__(self, rec):
+            dict.__init__(self)
+            self.rec = rec
+
+        def __missing__(self, kind):
+            self[kind] = {name: i for i, name in enumerate(self.rec.log.names[kind])}
+            return self[kind]
+
+    @property
+    def name2id(self):
+        if not isinstance(self._name2id, ArrayRecord._Lazy):
+            self._name2id = ArrayRecord._Lazy(self)
+        return self._name2id
+
+    def getSize(self, t):
+        return len(self.log.names[t])
+
+    def getId(self, obj, t):
+        ids = self.name2id[t]
+        if obj in ids:
+            return ids[obj]
+        print('No ' + t + ' ' + obj + ' exists!')
+        exit(-1)
+
+    def contains(self, obj, t):
+        return obj in self.name2id[t]
+
+    def printTrainingSize(self):
+        for kind in ('user', 'artist', 'album', 'track'):
+            if kind in self.log.names:
+                print(kind + ' count:', len(self.log.names[kind]))
+        print('Training set size:', self.recordCount)
+
+    @property
+    def testSet(self):
+        """{user: {track: 1}} built from the device's test CSR the first time someone wants the dict form."""
+        if self._test is None:
+            un, tn = self.log.names['user'], self.log.names[self.log.rec_type]
+            self._test = {}
+            for u in np.flatnonzero(np.diff(self.test_indptr) > 0):
+                self._test[un[u]] = {tn[t]: 1 for t in self.test_items[self.test_indptr[u]:self.test_indptr[u + 1]]}
+        return self._test
+
+
+def hit_mask(users, ids, n, test_indptr, test_items):
+    """[B, N] bool: is ids[b, r] a held-out track of users[b]?  One sorted search over (user, track) keys."""
+    users = np.asarray(users, dtype=np.int64)
+    owner = np.repeat(np.arange(len(test_indptr) - 1, dtype=np.int64), np.diff(test_indptr))
+    keys = owner * n + np.asarray(test_items, dtype=np.int64)              # sorted: the CSR is user-major, rows ascending
+    q = users[:, None] * n + np.where(ids >= 0, ids, 0).astype(np.int64)
+    pos = np.searchsorted(keys, q.ravel()).reshape(q.shape)
+    pos = np.minimum(pos, max(len(keys) - 1, 0))
+    return (keys[pos] == q) & (ids >= 0) if len(keys) else np.zeros(ids.shape, dtype=bool)
+
+
+def result_lines(user_names, track_names, ids, hits):
+    """IterativeRecommender.py:145-155: 'user:' + the names of the ranked tracks, '*' after a hit, newline -- column-wise."""
+    ids = np.asarray(ids)
+    cells = np.where(ids >= 0, np.asarray(track_names, dtype=object)[np.where(ids >= 0, ids, 0)], '')
+    cells = cells + np.where(hits, '*', '').astype(object)
+    lines = np.asarray(user_names, dtype=object) + ':'
+    for r in range(ids.shape[1]):
+        lines = lines + cells[:, r]
+    return list(lines + '\n')
+
+
+def ranking_measure(ids, hits, n_test, tops, item_count):
+    """Measure.rankingMeasure's list of strings (evaluation/measure.py:16-41: hits 7-13, precision 51-53, recall 91-94, F1
+    97-101, MAP 56-66, coverage 43-48) and {n: NDCG@n} from the ranked ids [B, N], their hit flags and the users' numbers
+    of held-out tracks -- whole-array arithmetic (the lists may come from several devices).  Same sums as the reference's
+    loops up to the order of float64 additions."""
+    ids, hits = np.asarray(ids), np.asarray(hits, dtype=bool)
+    B = ids.shape[0]
+    n_test = np.asarray(n_test, dtype=np.float64)
+    cum = np.cumsum(hits, axis=1)
+    ranks = np.arange(1, ids.shape[1] + 1, dtype=np.float64)
+    disc = 1.0 / np.log2(ranks + 1.0)
+    print('rank measure...')
+    measure, ndcg = [], {}
+    for n in tops:
+        h = cum[:, n - 1] if n <= ids.shape[1] else cum[:, -1]
+        prec = float(h.sum()) / (B * n)
+        recall = float((h / n_test).sum()) / float(B)
+        ap = ((cum[:, :n] / ranks[:n]) * hits[:, :n]).sum(axis=1) / np.minimum(n_test, n)
+        f1 = 2 * prec * recall / (prec + recall) if (prec + recall) != 0 else 0
+        shown = ids[:, :n]
+        distinct = np.unique(shown[shown >= 0]).size
+        measure += ['Top ' + str(n) + '\n', 'Precision:' + str(prec) + '\n', 'Recall:' + str(recall) + '\n', 'F1:' + str(f1) + '\n',
+                    'MAP:' + str(float(ap.sum()) / B) + '\n', 'Coverage:' + str(distinct / float(item_count)) + '\n']
+        ideal = np.cumsum(disc)[np.minimum(n_test, n).astype(np.int64) - 1]
+        ndcg[n] = float(((hits[:, :n] * disc[:n]).sum(axis=1) / ideal).sum()) / B
+    return measure, ndcg
