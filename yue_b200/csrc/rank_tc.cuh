@@ -50,7 +50,7 @@ constexpr int kTcBoxBytes = 128 * 128;   // one TMA box: 128 rows x 128 B
 constexpr float kTf32ErrCoef = 2.1e-3f;  // 2^-9 (two operands truncated to 10 mantissa bits) + slack
 
 struct RankTcParams {
-    int kblocks;                // 128-byte k-blocks per row: ceil(ld / 32), 1..2
+    int kblocks;                // 128-byte k-blocks per row: ceil(ld / 32), 1..4
     int ntiles;
     int n_items;
     int64_t B;
@@ -111,6 +111,32 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// true on exactly one lane of a converged warp (the MMA warp runs converged so that ptxas keeps the MMA's operands in
+// uniform registers; issuing from `if (lane == 0)` costs a uniform-register waterfall loop per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.b32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+// One 128-byte k-block = 4 MMAs (K = 8 tf32 each), issued from ONE asm block with descriptors the caller precomputed: the
+// issuing thread is a single warp executing dependent scalar code at ~6 cycles per instruction, and round 1's loop
+// (descriptor built per MMA, tile counters by division, one uniform-register waterfall per MMA: ~170 instructions per tile)
+// took ~1000 cycles per tile against 536 of tensor-pipe work (profiles/ncu_rank_r2.md).  Along the swizzle row the k-th
+// MMA's operands start 32 bytes further: +2 in the descriptor's 16-byte address field.
+__device__ __forceinline__ void tc_mma_tf32_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "add.u64 a1, %1, 2;\n add.u64 a2, %1, 4;\n add.u64 a3, %1, 6;\n"
+        "add.u64 b1, %2, 2;\n add.u64 b2, %2, 4;\n add.u64 b3, %2, 6;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], a1, b1, %3, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, b2, %3, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, b3, %3, 1;\n"
+        "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc_first) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (base lane + t)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
@@ -233,7 +259,10 @@ __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int 
     return thr;
 }
 
-template <int CAP, int BN, int kTcStages>
+// EXP: timing experiments only (YUE_RANK_EXP; results are NOT valid for EXP = 1): 1 = the epilogue reads TMEM and frees the
+// stage but looks at nothing (what the TMA -> MMA -> TMEM-read pipeline does on its own); 2 = both halves of a tile are
+// requested before the first wait.
+template <int CAP, int BN, int kTcStages, int EXP = 0>
 __global__ void __launch_bounds__(kTcThreads, 1)
 rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const RankTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
@@ -289,26 +318,35 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the warp stays converged, one elected lane issues =====
+        {
+            const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
             mbar_wait(bar_a, 0);
+            // everything that does not depend on the tile is computed once: operand descriptors (A per k-block, B of stage 0;
+            // a stage / k-block further is a constant in the 16-byte address field); stage and accumulator indices, phases
+            // and the stage offset advance by increments
+            const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
+            const uint64_t bdesc_base = umma_desc_sw128(smem_u32(sB));
+            const uint32_t stage16 = stage_bytes >> 4, kb16 = kBBox >> 4, ka16 = kTcBoxBytes >> 4;
+            int s = 0, t = 0;
+            uint32_t ph = 0, tph = 0, boff = 0;
             for (int j = 0; j < p.ntiles; ++j) {
-                const int s = j % kTcStages, t = j % kTcAcc;
-                const uint32_t ph = (uint32_t)(j / kTcStages) & 1u, tph = (uint32_t)(j / kTcAcc) & 1u;
                 mbar_wait(bar_tempty(t), tph ^ 1u);
                 mbar_wait(bar_full(s), ph);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * stage_bytes);
-                for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {       // UMMA K = 8 tf32 = 32 bytes along the swizzle row
-                        const uint64_t ad = umma_desc_sw128(a0 + kb * kTcBoxBytes + k * 32);
-                        const uint64_t bd = umma_desc_sw128(b0 + kb * kBBox + k * 32);
-                        tc_mma_tf32(tmem_base + (uint32_t)t * BN, ad, bd, idesc_tf32<BN>(), (kb | k) ? 1u : 0u);
-                    }
+                if (elect_one()) {
+                    const uint32_t dcol = tbase + (uint32_t)t * BN;
+                    const uint64_t bd = bdesc_base + boff;      // stays inside the 14-bit address field (smem < 256 KB)
+                    tc_mma_tf32_x4(dcol, adesc0, bd, idesc_tf32<BN>(), 0u);
+                    for (int kb = 1; kb < KB; ++kb)             // up to 4 k-blocks of 32 floats (num.factors <= 128)
+                        tc_mma_tf32_x4(dcol, adesc0 + (uint32_t)kb * ka16, bd + (uint32_t)kb * kb16, idesc_tf32<BN>(), 1u);
+                    tc_commit(bar_empty(s));            // smem stage free once these MMAs retire
+                    tc_commit(bar_tfull(t));            // accumulator ready for the epilogue
                 }
-                tc_commit(bar_empty(s));                // smem stage free once these MMAs retire
-                tc_commit(bar_tfull(t));                // accumulator ready for the epilogue
+                __syncwarp();
+                boff += stage16;
+                if (++s == kTcStages) { s = 0; ph ^= 1u; boff = 0; }
+                if (++t == kTcAcc) { t = 0; tph ^= 1u; }
             }
         }
     } else {
@@ -327,19 +365,32 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint64_t* keys_quarter = keys + (size_t)(quarter * 32) * CAP;
 
-        // examine 32 scores of columns [col0, col0+32): push survivors, then compact crowded rows
+        // examine 32 scores of columns [col0, col0+32): push survivors, then compact crowded rows.  Entered by the whole warp
+        // when ANY of its 32 rows has a chunk maximum above its threshold (~3 % of the chunks once the thresholds have
+        // settled), and a warp that is late with a tile holds up the MMA of that TMEM stage for all four quarters -- so the
+        // path is kept short: a row first looks at the maxima of its four groups of 8 scores and scans only a group that can
+        // hold a survivor (usually one row, one group), and the compaction is called only when some row's buffer is crowded.
 #define TC_RARE(v, col0, m)                                                                          \
         do {                                                                                         \
             if ((m) >= thr) {                                                                        \
                 _Pragma("unroll")                                                                    \
-                for (int x = 0; x < 32; ++x) {                                                       \
-                    const float sc = __uint_as_float((v)[x]);                                        \
-                    if (sc >= thr && (col0) + x < p.n_items)                                         \
-                        if (tc_push(&st, K, p.uq_items, p.ovf_pool, sc, (col0) + x)) thr = INFINITY; \
+                for (int g = 0; g < 4; ++g) {                                                        \
+                    float mg = __uint_as_float((v)[8 * g]);                                          \
+                    _Pragma("unroll")                                                                \
+                    for (int x = 1; x < 8; ++x) mg = fmaxf(mg, __uint_as_float((v)[8 * g + x]));     \
+                    if (mg >= thr) {                                                                 \
+                        _Pragma("unroll")                                                            \
+                        for (int x = 8 * g; x < 8 * g + 8; ++x) {                                    \
+                            const float sc = __uint_as_float((v)[x]);                                \
+                            if (sc >= thr && (col0) + x < p.n_items)                                 \
+                                if (tc_push(&st, K, p.uq_items, p.ovf_pool, sc, (col0) + x)) thr = INFINITY; \
+                        }                                                                            \
+                    }                                                                                \
                 }                                                                                    \
             }                                                                                        \
             __syncwarp();                                                                            \
-            thr = tc_compact<CAP>(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next, p.ovf_rows);       \
+            if (__any_sync(0xffffffffu, st.cnt > CAP - 32))                                          \
+                thr = tc_compact<CAP>(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next, p.ovf_rows); \
         } while (0)
 
         for (int j = 0; j < p.ntiles; ++j) {
@@ -350,8 +401,16 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             tc_fence_after();
             uint32_t va[64], vb[64];
             tc_ld64_issue(trow + (uint32_t)(t * BN), va);
-            tc_ld_wait();
+            if (EXP != 2) tc_ld_wait();
             if (BN == 128) tc_ld64_issue(trow + (uint32_t)(t * BN + 64), vb);   // in flight while the first half is reduced
+            if (EXP == 2) tc_ld_wait();
+            if (EXP == 1) {
+                tc_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar_tempty(t));
+                if (va[lane] == 0x7fc00001u && vb[lane] == 0x7fc00002u) thr = 0.f;      // keep the loads alive
+                continue;
+            }
             float m0 = __uint_as_float(va[0]), m1 = __uint_as_float(va[32]);
 #pragma unroll
             for (int x = 1; x < 32; ++x) { m0 = fmaxf(m0, __uint_as_float(va[x])); m1 = fmaxf(m1, __uint_as_float(va[32 + x])); }
@@ -599,9 +658,20 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
         TC_CK(cudaFuncSetAttribute(rank_tc_kernel<CAP_, BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         rank_tc_kernel<CAP_, BN_, ST_><<<grid, kTcThreads, smem, stream>>>(tmP, tmQ, p);                                   \
     } while (0)
+    const char* exp_s = getenv("YUE_RANK_EXP");
+    const int exp_mode = exp_s ? atoi(exp_s) : 0;
+#define TC_LAUNCH_EXP(E_)                                                                                                   \
+    do {                                                                                                                   \
+        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<64, 128, 3, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rank_tc_kernel<64, 128, 3, E_><<<grid, kTcThreads, smem, stream>>>(tmP, tmQ, p);                                   \
+    } while (0)
+    if (bn == 128 && cap == 64 && exp_mode == 1) TC_LAUNCH_EXP(1);
+    else if (bn == 128 && cap == 64 && exp_mode == 2) TC_LAUNCH_EXP(2);
+    else
     if (bn == 128) { if (cap == 64) TC_LAUNCH(64, 128, 3); else TC_LAUNCH(96, 128, 3); }
     else { if (cap == 64) TC_LAUNCH(64, 64, 2); else TC_LAUNCH(96, 64, 2); }
 #undef TC_LAUNCH
+#undef TC_LAUNCH_EXP
     ++launches;
     TC_CK(cudaGetLastError());
 
