@@ -276,7 +276,24 @@ def run_native(args):
     ctl = sharding.TorchCtl(dist, dev) if world > 1 else None
     reduce_factory = quality.torch_reduce_factory(dist, dev) if world > 1 else None
 
+    # config C3 IS the sharded one ("user-sharded SGD with Q-delta allreduce at 2/4/8 B200"): there the trainer is the headline,
+    # with the quality caveat spelled out in the line
+    headline_sharded = args.config == "C3" and world > 1
+
+    def make_trainer():
+        cnt = torch.from_numpy(local_counts).to("cuda")
+        dist.all_reduce(cnt)
+        # at this size a moderately played track is touched thousands of times per rank between two exchanges: the summed
+        # tail deltas are saturation-weighted (round 1) -- the plain sum diverges on 4 GPUs (NaN loss, measured)
+        w = sharding.saturation_weights(cnt.cpu().numpy(), world, args.sub_epochs, 0.05 * LR)
+        return sharding.SharedHotTrainer(eng, ctl, local_counts, sub_epochs=args.sub_epochs, asynchrony=args.asynchrony,
+                                         reduce=reduce_factory(eng), reserve_sms=args.reserve_sms, row_weights=w)
+
+    trainer = make_trainer() if headline_sharded else None
+
     def step(epoch, want_loss=False):
+        if trainer is not None:
+            return trainer.epoch(LR, REG_U, REG_I, SEED, epoch, want_loss=want_loss)
         return eng.bpr_epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
 
     # ---- value: K steps, inputs resident in HBM ---------------------------------------------
@@ -290,6 +307,8 @@ def run_native(args):
     eng.timer_start()
     for k in range(args.steps):
         step(args.warmup + k)
+    if trainer is not None:
+        trainer.finalize()                          # the exchange still in flight + the hot rows back into every rank's Q
     ms = eng.timer_stop()
     barrier()
     clk = clocks.stop() if rank == 0 else None
@@ -299,6 +318,14 @@ def run_native(args):
     achieved = bpt * T / (k_ms * 1e-3) / 1e9
     tkey = args.config + ("-small" if args.small else "") + ("/%d" % world if args.config == "C3" else "")
     traffic, traffic_src = ncu_traffic(tkey)
+
+    sched = None
+    if trainer is not None:
+        sched = dict(hot_rows=int(len(trainer.hot_tracks)), hot_share=float(trainer.hot_share_of_events), warps=int(trainer.n_warps),
+                     ctas=int(trainer.n_ctas))
+        trainer.close()
+        eng.set_delta_weights(None)
+        trainer = None
 
     # ---- config C5: APR epoch (adversarial BPR, fused per-triplet perturbation), APR.conf hyper-parameters ----
     apr = None
@@ -315,16 +342,9 @@ def run_native(args):
 
     # ---- the SHARDED trainer (one model over N GPUs: SURVEY 8e / north_star's partitioning), measured, not the headline ----
     sharded = None
-    if world > 1 and not args.no_sharded:
+    if world > 1 and not args.no_sharded and not headline_sharded:
         upload()
-        cnt = torch.from_numpy(local_counts).to("cuda")
-        dist.all_reduce(cnt)
-        # the tail of Q is summed 32 times per epoch; at this size a moderately played track is still touched thousands of
-        # times per rank between two exchanges, so the sum is saturation-weighted (round 1) -- without it the run diverges
-        # on 4 GPUs (NaN loss, measured)
-        w = sharding.saturation_weights(cnt.cpu().numpy(), world, args.sub_epochs, 0.05 * LR)
-        tr = sharding.SharedHotTrainer(eng, ctl, local_counts, sub_epochs=args.sub_epochs, asynchrony=args.asynchrony,
-                                       reduce=reduce_factory(eng), reserve_sms=args.reserve_sms, row_weights=w)
+        tr = make_trainer()
         sms, ams = [], []
         try:
             for k in range(2 + min(args.steps, 4)):
@@ -395,11 +415,18 @@ def run_native(args):
 
     def e2e_job(epochs, base_epoch):
         upload()
+        tr = make_trainer() if headline_sharded else None
         loss = 0.0
         for ep in range(epochs):
-            loss = eng.bpr_epoch(LR, REG_U, REG_I, SEED, base_epoch + ep, mode, want_loss=True)
+            if tr is not None:
+                loss = tr.epoch(LR, REG_U, REG_I, SEED, base_epoch + ep, want_loss=True, finalize=True)
+            else:
+                loss = eng.bpr_epoch(LR, REG_U, REG_I, SEED, base_epoch + ep, mode, want_loss=True)
             p2, q2 = eng.frob2()
-            loss += REG_U * p2 + REG_I * q2         # BPR.py:59
+            loss += REG_U * p2 + REG_I * q2         # BPR.py:59 (per rank: its events, its P rows)
+        if tr is not None:
+            tr.close()
+            eng.set_delta_weights(None)
         eng.get_factors(pP.array, pQ.array)
         return loss
 
@@ -488,7 +515,13 @@ def run_native(args):
     out = None
     if rank == 0:
         par = "single GPU"
-        if world > 1:
+        if headline_sharded:
+            par = ("ONE model over %d GPUs: users sharded, P rows private; the %d most played tracks' rows (%.0f %% of the positives) live once "
+                   "(slot s on rank s %% %d) and are loaded / added over NVLink peer memory; the tail of Q replicated, dQ all-reduced %d times "
+                   "per epoch under the next part (saturation-weighted sum), %d warps on %d CTAs per rank.  QUALITY: at this size no sharded "
+                   "schedule stays within the 0.5-point gate of the serial order (DESIGN.md section 6); the `quality` block is the one-GPU "
+                   "schedule" % (world, sched["hot_rows"], 100 * sched["hot_share"], world, args.sub_epochs, sched["warps"], sched["ctas"]))
+        elif world > 1:
             par = ("%d replicas: every GPU trains its own model on its own C2-shaped log (folds / seeds / hyper-parameter points), no "
                    "collective on the path; one SHARDED model is measured in `sharded` and cannot hold the 0.5-point gate at this size "
                    "(DESIGN.md section 6)" % world)

@@ -117,6 +117,25 @@ def test_tc_topn_matches_oracle(engine, d, N, n, B):
     check(engine, P, Q, users, N, log.uq_indptr, log.uq_items, RANK_TC)
 
 
+@pytest.mark.parametrize("d,N", [(64, 10), (64, 20), (128, 10)])
+def test_tc_equals_exact_kernel_at_the_catalog_of_config_c4(engine, d, N):
+    """Config C4's catalog (2 M tracks, ~50 masked tracks per user; BASELINE.json configs[3]) on a block of users: the
+    tensor-core flavour (15 625 tiles per row, spill pool and exact-kernel fallback included) returns the exact kernel's
+    ids and scores bit for bit; uniform U[0, 0.1) tables like bench.py's -- the near-tie-heavy case."""
+    m, n = 640, 2_000_000
+    indptr, uq = synth.mask_csr(m, n, 50, seed=8)
+    P, Q = synth.init_factors(m, n, d, seed=9)
+    engine.set_interactions(m, n, np.zeros(m + 1, np.int64), np.zeros(0, np.int32), indptr, uq)
+    engine.set_factors(P, Q)
+    users = np.arange(m, dtype=np.int32)
+    ie, se = engine.rank_topn(users, N, RANK_EXACT)
+    it, st = engine.rank_topn(users, N, RANK_TC)
+    assert np.array_equal(ie, it) and np.array_equal(se, st)
+    assert (ie >= 0).all() and (np.diff(se, axis=1) <= 0).all()
+    for b in (0, 77, m - 1):
+        assert not np.isin(it[b], uq[indptr[b]:indptr[b + 1]]).any()
+
+
 def test_tc_equals_exact_kernel_at_scale(engine):
     """Bigger than the oracle likes: the tensor-core flavour against the exact kernel, trained-like
     factors (heavy-tailed norms), 100 K tracks."""
