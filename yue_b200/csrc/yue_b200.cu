@@ -288,11 +288,15 @@ struct ItemPlanArgs {
     bool allow_shared; int64_t item_segs, max_items, group_segs; int seg_events; const int64_t* uq_indptr;
 };
 // host threads a handle may use for planning: the cores divided by the processes that share the box
-// (LOCAL_WORLD_SIZE is set by torchrun: one process per GPU), at most 16
+// (LOCAL_WORLD_SIZE is set by torchrun: one process per GPU), at most 4 -- the planner writes pinned staging while the
+// DMA of the log reads pinned memory, and more writers slow that DMA down by more than they shorten the plan (config C2,
+// 16 cores: 16 threads plan in 4.5 ms and yue_set_interactions takes 12.7 ms; 4 threads plan in 6.7 ms and it takes 10.5)
 static size_t host_threads() {
     size_t hw = std::max(1u, std::thread::hardware_concurrency());
     if (const char* s = getenv("LOCAL_WORLD_SIZE")) hw = std::max<size_t>(1, hw / (size_t)std::max(1, atoi(s)));
-    return std::min<size_t>(16, hw);
+    size_t cap = 4;
+    if (const char* s = getenv("YUE_HOST_THREADS")) cap = (size_t)std::max(1, atoi(s));
+    return std::min<size_t>(cap, hw);
 }
 
 // one pass over runs [r0, r1): WRITE = false only counts segments and items, WRITE = true fills
