@@ -406,6 +406,30 @@ def run_native(args):
                                     "sample": "200 evenly spaced users of the same log, oracle port of WRMF.py:36-57 incl. one YtY",
                                     "gpu_user_rows_per_sec": m / (u_ms * 1e-3)}
 
+    # ---- WRMF over N GPUs: rows of a half-sweep are independent, every rank solves a range and broadcasts it -- exact,
+    #      bit-identical to one GPU (tests/test_multigpu.py).  ONE log (rank 0's shape) held by every rank. ----
+    if world > 1 and not args.no_wrmf and d == 64 and not headline_sharded:
+        wlog = synth.power_law_log_torch(wl["users"], wl["tracks"], wl["plays"], SEED, device="cuda")      # the same log on every rank
+        torch.cuda.empty_cache()
+        wP, wQ = synth.init_factors(wlog.m, wlog.n, d, SEED + 1000)
+        eng.set_interactions(wlog.m, wlog.n, wlog.ev_indptr, wlog.ev_items, wlog.uq_indptr, wlog.uq_items)
+        eng.set_factors(wP * 10, wQ * 10)
+        it_indptr = eng.wrmf_pair_counts()[1]
+        wt = sharding.WrmfShardedTrainer(eng, dist, dev, wlog.uq_indptr, it_indptr)
+        wts = []
+        for k in range(4):
+            barrier()
+            eng.timer_start()
+            wt.iteration(1.0, want_loss=False)
+            wts.append(allmax(eng.timer_stop()))
+        nnz = int(len(wlog.uq_items))
+        wrmf = {"metric": "wrmf_iterations_per_sec", "value": 1e3 / min(wts[1:]), "ms_per_iteration": min(wts[1:]), "n_gpus": world, "scaling": "strong",
+                "unique_pairs": nnz, "pairs_per_sec": 2 * nnz / (min(wts[1:]) * 1e-3),
+                "parallelism": "every rank holds the log and both tables, solves a range of rows balanced by entries and broadcasts it (NCCL); "
+                               "no reduction: bit-identical to one GPU",
+                "workload": "WRMF d=64, reg 1, alpha 10 on ONE C2 log (%d users x %d tracks, %d unique pairs)" % (wlog.m, wlog.n, nnz)}
+        del wlog, wP, wQ
+
     # ---- e2e: the job a user of the class API runs (IterativeRecommender.buildModel): the log and the tables go up ONCE
     #      from pinned host memory, num.max.iter = E epochs each return their loss (the lr schedule needs it), the tables
     #      come back.  Also: the same with the upload repeated before EVERY epoch (round 1's definition). ----

@@ -99,10 +99,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// the same box delivered to the same shared-memory offset of every CTA in `mask` (and its bytes signalled on the barrier at
+// the same offset in each of them): one read of L2 serves the whole cluster
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" :: "r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -137,6 +153,36 @@ __device__ __forceinline__ void tc_mma_tf32_x4(uint32_t tmem_d, uint64_t adesc, 
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, b2, %3, 1;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, b3, %3, 1;\n"
         "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc_first) : "memory");
+}
+// The same with A read from TENSOR MEMORY (lane = row of A, one 32-bit column per tf32 element): the user block is the same
+// for every tile, and with both operands in shared memory the K = 8 tf32 MMA reads 8 KB per 65 cycles -- all of the SM's
+// shared-memory bandwidth, on top of which the TMA writes the next Q tile (32 KB): the bare pipeline ran at 750 cycles per
+// tile = (8 x 8 KB + 32 KB) / 128 B/clk.  A in TMEM halves the operand traffic.
+__device__ __forceinline__ void tc_mma_tf32_ts_x4(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 b1, b2, b3;\n"
+        ".reg .b32 a1, a2, a3;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "add.u32 a1, %1, 8;\n add.u32 a2, %1, 16;\n add.u32 a3, %1, 24;\n"
+        "add.u64 b1, %2, 2;\n add.u64 b2, %2, 4;\n add.u64 b3, %2, 6;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], b1, %3, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], b2, %3, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], b3, %3, 1;\n"
+        "}" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc_first) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns written from registers: thread t of the warp writes TMEM lane (base lane + t)
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (base lane + t)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
@@ -262,14 +308,22 @@ __device__ __noinline__ float tc_compact(TcRow* st, uint64_t* keys_quarter, int 
 // EXP: timing experiments only (YUE_RANK_EXP; results are NOT valid for EXP = 1): 1 = the epilogue reads TMEM and frees the
 // stage but looks at nothing (what the TMA -> MMA -> TMEM-read pipeline does on its own); 2 = both halves of a tile are
 // requested before the first wait.
-template <int CAP, int BN, int kTcStages, int EXP = 0>
+// CL: CTAs per cluster (1, 2 or 4).  The CTAs of a cluster walk the catalog together: each loads 1/CL of every Q tile and
+// TMA multicasts it to all of them, so a tile is read from L2 once per cluster instead of once per CTA (every CTA streams
+// all of Q: 11.8 TB/s over a wave with CL = 1, the bound of the bare pipeline -- profiles/ncu_rank_r2.md).  A stage may be
+// refilled only when the MMAs of ALL the cluster's CTAs have read it: their commits arrive on every CTA's `empty` barrier.
+// ATM: the user block (A) lives in tensor memory instead of shared memory (d <= 64: 3 accumulator stages of 128 columns + 64
+// columns of A; see tc_mma_tf32_ts_x4).
+template <int CAP, int BN, int kTcStages, int EXP = 0, int CL = 1, bool ATM = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const RankTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_tc_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_tc_raw) + 1023) & ~(uintptr_t)1023);
     const int KB = p.kblocks;
+    constexpr int NACC = ATM ? 3 : kTcAcc;                   // TMEM accumulator stages
+    constexpr uint32_t kAtmCol = NACC * BN;                  // first TMEM column of A (ATM)
     constexpr uint32_t kBBox = BN * 128;                     // one TMA box of Q: BN rows x 128 B
-    const uint32_t a_bytes = (uint32_t)KB * kTcBoxBytes, stage_bytes = (uint32_t)KB * kBBox;
+    const uint32_t a_bytes = ATM ? 0u : (uint32_t)KB * kTcBoxBytes, stage_bytes = (uint32_t)KB * kBBox;
     uint8_t* sA = smem;
     uint8_t* sB = sA + a_bytes;
     constexpr int kTcPer = CAP / 32;
@@ -284,10 +338,12 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kTcStages + 2 * kTcAcc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
     if (threadIdx.x == 0) {
-        mbar_init(bar_a, 1);
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int t = 0; t < kTcAcc; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_tempty(t), 128); }
+        mbar_init(bar_a, ATM ? 128 : 1);
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), CL); }
+        for (int t = 0; t < NACC; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_tempty(t), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmP) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmQ) : "memory");
@@ -300,21 +356,27 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL > 1) cluster_sync_all();                     // every CTA's barriers exist before a peer signals them
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(bar_a, a_bytes);
-            for (int kb = 0; kb < KB; ++kb)
-                tma_load_2d(smem_u32(sA + kb * kTcBoxBytes), &tmP, bar_a, kb * 32, blockIdx.x * kTcBM);
+            if (!ATM) {
+                mbar_expect_tx(bar_a, a_bytes);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(smem_u32(sA + kb * kTcBoxBytes), &tmP, bar_a, kb * 32, blockIdx.x * kTcBM);
+            }
             for (int j = 0; j < p.ntiles; ++j) {
                 const int s = j % kTcStages;
                 const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
                 mbar_wait(bar_empty(s), ph ^ 1u);
-                mbar_expect_tx(bar_full(s), stage_bytes);
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(smem_u32(sB + s * stage_bytes + kb * kBBox), &tmQ, bar_full(s), kb * 32, j * BN);
+                mbar_expect_tx(bar_full(s), stage_bytes);       // the whole stage: this CTA's part and its peers'
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (CL == 1) tma_load_2d(smem_u32(sB + s * stage_bytes + kb * kBBox), &tmQ, bar_full(s), kb * 32, j * BN);
+                    else tma_load_2d_mc(smem_u32(sB + s * stage_bytes + kb * kBBox) + crank * (uint32_t)(BN / CL * 128), &tmQ, bar_full(s),
+                                        kb * 32, j * BN + (int)crank * (BN / CL), kClusterMask);
+                }
             }
         }
     } else if (warp == 1) {
@@ -337,16 +399,23 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                 if (elect_one()) {
                     const uint32_t dcol = tbase + (uint32_t)t * BN;
                     const uint64_t bd = bdesc_base + boff;      // stays inside the 14-bit address field (smem < 256 KB)
-                    tc_mma_tf32_x4(dcol, adesc0, bd, idesc_tf32<BN>(), 0u);
-                    for (int kb = 1; kb < KB; ++kb)             // up to 4 k-blocks of 32 floats (num.factors <= 128)
-                        tc_mma_tf32_x4(dcol, adesc0 + (uint32_t)kb * ka16, bd + (uint32_t)kb * kb16, idesc_tf32<BN>(), 1u);
-                    tc_commit(bar_empty(s));            // smem stage free once these MMAs retire
+                    if (ATM) {
+                        tc_mma_tf32_ts_x4(dcol, tbase + kAtmCol, bd, idesc_tf32<BN>(), 0u);
+                        for (int kb = 1; kb < KB; ++kb)
+                            tc_mma_tf32_ts_x4(dcol, tbase + kAtmCol + (uint32_t)kb * 32u, bd + (uint32_t)kb * kb16, idesc_tf32<BN>(), 1u);
+                    } else {
+                        tc_mma_tf32_x4(dcol, adesc0, bd, idesc_tf32<BN>(), 0u);
+                        for (int kb = 1; kb < KB; ++kb)         // up to 4 k-blocks of 32 floats (num.factors <= 128)
+                            tc_mma_tf32_x4(dcol, adesc0 + (uint32_t)kb * ka16, bd + (uint32_t)kb * kb16, idesc_tf32<BN>(), 1u);
+                    }
+                    if (CL == 1) tc_commit(bar_empty(s));   // smem stage free once these MMAs retire
+                    else tc_commit_mc(bar_empty(s), kClusterMask);
                     tc_commit(bar_tfull(t));            // accumulator ready for the epilogue
                 }
                 __syncwarp();
                 boff += stage16;
                 if (++s == kTcStages) { s = 0; ph ^= 1u; boff = 0; }
-                if (++t == kTcAcc) { t = 0; tph ^= 1u; }
+                if (++t == NACC) { t = 0; tph ^= 1u; }
             }
         }
     } else {
@@ -393,9 +462,26 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
                 thr = tc_compact<CAP>(&st, keys_quarter, lane, p.N, eps2, thr, p.ovf_pool, p.ovf_next, p.ovf_rows); \
         } while (0)
 
-        for (int j = 0; j < p.ntiles; ++j) {
-            const int t = j % kTcAcc;
-            const uint32_t tph = (uint32_t)(j / kTcAcc) & 1u;
+        if (ATM) {
+            // this thread's row of the user block -> TMEM lane r, columns kAtmCol ... (fp32 bits; the MMA reads them as tf32)
+            const float* prow = p.Psel + (size_t)((int64_t)blockIdx.x * kTcBM + r) * p.ld;        // rows past B are zero rows
+            for (int kb = 0; kb < KB; ++kb) {
+                uint32_t a[32];
+#pragma unroll
+                for (int x = 0; x < 32; x += 4) {
+                    const bool in = kb * 32 + x < p.ld;
+                    const float4 v = in ? __ldg(reinterpret_cast<const float4*>(prow + kb * 32 + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    a[x] = __float_as_uint(v.x); a[x + 1] = __float_as_uint(v.y); a[x + 2] = __float_as_uint(v.z); a[x + 3] = __float_as_uint(v.w);
+                }
+                tc_st32(trow + kAtmCol + (uint32_t)kb * 32u, a);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(bar_a);
+        }
+        int t = 0;
+        uint32_t tph = 0;
+        for (int j = 0; j < p.ntiles; ++j, t = (t + 1 == NACC ? 0 : t + 1), tph ^= (t == 0 ? 1u : 0u)) {
             const int i0 = j * BN;
             mbar_wait(bar_tfull(t), tph);
             tc_fence_after();
@@ -497,6 +583,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                     // no CTA leaves while a peer may still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
@@ -617,7 +704,12 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
         TC_CK(cudaMalloc((void**)&st.fail_count, sizeof(int)));
         TC_CK(cudaMalloc((void**)&st.ovf_next, sizeof(int)));
     }
-    const int64_t Bpad = (B + kTcBM - 1) / kTcBM * kTcBM;
+    // CTAs per cluster sharing each Q tile by TMA multicast (YUE_RANK_CLUSTER = 1, 2, 4; see rank_tc_kernel)
+    int cl = 1;                                           // measured on B200: 2 = no gain (L2 is not the bound), 4 = half the clusters fit
+    if (const char* e = getenv("YUE_RANK_CLUSTER")) cl = atoi(e);
+    if (cl != 2 && cl != 4) cl = 1;
+    if (B <= kTcBM) cl = 1;                               // a single user block: nobody to share with
+    const int64_t Bpad = (B + kTcBM * cl - 1) / (kTcBM * cl) * (kTcBM * cl);   // whole clusters; rows past B are zero rows
     TC_CK(tc_grow(st.ovf_pool, st.ovf_rows, (size_t)std::max<int64_t>(kTcOvfRowsMin, B / 16) * kTcOvfCap));
     size_t cap_tmp = st.psel_cap;
     TC_CK(tc_grow(st.psel, st.psel_cap, (size_t)Bpad * ld));
@@ -637,8 +729,12 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
     TC_CK(cudaGetLastError());
 
     CUtensorMap tmP, tmQ;
-    const int bn = ld <= 64 ? 128 : 64, stages = ld <= 64 ? 3 : 2;
-    if (!tc_make_map(st.encode, &tmP, st.psel, (uint64_t)Bpad, ld) || !tc_make_map(st.encode, &tmQ, Q, (uint64_t)n_items, ld, (unsigned)bn)) {
+    // A in tensor memory (default): the user block costs no shared memory, so every width takes 128-track tiles (3 stages of
+    // 32 KB for d <= 64, 2 stages of up to 64 KB above); YUE_RANK_ATM=0 / clusters: round 1's layout (A in shared memory)
+    const bool atm = cl == 1 && !(getenv("YUE_RANK_ATM") && atoi(getenv("YUE_RANK_ATM")) == 0);
+    const int bn = (ld <= 64 || atm) ? 128 : 64;
+    int stages = ld <= 64 ? 3 : 2;
+    if (!tc_make_map(st.encode, &tmP, st.psel, (uint64_t)Bpad, ld) || !tc_make_map(st.encode, &tmQ, Q, (uint64_t)n_items, ld, (unsigned)(bn / cl))) {
         err = "cuTensorMapEncodeTiled failed";
         return 2;
     }
@@ -651,27 +747,40 @@ inline int rank_tc_run(RankTcState& st, cudaStream_t stream, int sm_count, const
     p.fail_count = st.fail_count; p.fail_rows = st.fail_rows;
     p.ovf_pool = st.ovf_pool; p.ovf_next = st.ovf_next; p.ovf_rows = (int)(st.ovf_rows / kTcOvfCap);
     const int cap = N <= 12 ? 64 : 96;
-    const size_t smem = 1024 + (size_t)p.kblocks * (kTcBoxBytes + (size_t)stages * bn * 128) + (size_t)kTcBM * cap * 8 + 256;
+    if (bn == 128 && cap == 64 && getenv("YUE_RANK_STAGES4")) stages = 4;       // experiment: a fourth Q stage (measured: no gain)
+    const size_t smem = 1024 + (size_t)p.kblocks * ((atm ? 0 : kTcBoxBytes) + (size_t)stages * bn * 128) + (size_t)kTcBM * cap * 8 + 256;
     const unsigned grid = (unsigned)(Bpad / kTcBM);
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid, 1, 1); lc.blockDim = dim3(kTcThreads, 1, 1); lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeClusterDimension;
+    lattr[0].val.clusterDim.x = (unsigned)cl; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
+    lc.attrs = lattr; lc.numAttrs = 1;
+#define TC_LAUNCH_K(K_)                                                                                                    \
+    do {                                                                                                                   \
+        TC_CK(cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                           \
+        TC_CK(cudaLaunchKernelEx(&lc, K_, tmP, tmQ, p));                                                                   \
+    } while (0)
 #define TC_LAUNCH(CAP_, BN_, ST_)                                                                                          \
     do {                                                                                                                   \
-        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<CAP_, BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rank_tc_kernel<CAP_, BN_, ST_><<<grid, kTcThreads, smem, stream>>>(tmP, tmQ, p);                                   \
+        if (cl == 2) TC_LAUNCH_K((rank_tc_kernel<CAP_, BN_, ST_, 0, 2>));                                                  \
+        else if (cl == 4) TC_LAUNCH_K((rank_tc_kernel<CAP_, BN_, ST_, 0, 4>));                                             \
+        else TC_LAUNCH_K((rank_tc_kernel<CAP_, BN_, ST_, 0, 1>));                                                          \
     } while (0)
     const char* exp_s = getenv("YUE_RANK_EXP");
     const int exp_mode = exp_s ? atoi(exp_s) : 0;
-#define TC_LAUNCH_EXP(E_)                                                                                                   \
-    do {                                                                                                                   \
-        TC_CK(cudaFuncSetAttribute(rank_tc_kernel<64, 128, 3, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rank_tc_kernel<64, 128, 3, E_><<<grid, kTcThreads, smem, stream>>>(tmP, tmQ, p);                                   \
-    } while (0)
-    if (bn == 128 && cap == 64 && exp_mode == 1) TC_LAUNCH_EXP(1);
-    else if (bn == 128 && cap == 64 && exp_mode == 2) TC_LAUNCH_EXP(2);
+    if (!atm && bn == 128 && cap == 64 && exp_mode == 1 && cl == 1) TC_LAUNCH_K((rank_tc_kernel<64, 128, 3, 1, 1>));
+    else if (bn == 128 && cap == 64 && exp_mode == 1 && cl == 2) TC_LAUNCH_K((rank_tc_kernel<64, 128, 3, 1, 2>));
+    else if (atm && exp_mode == 1 && cap == 64) TC_LAUNCH_K((rank_tc_kernel<64, 128, 3, 1, 1, true>));
+    else if (atm && cap == 64 && stages == 3) TC_LAUNCH_K((rank_tc_kernel<64, 128, 3, 0, 1, true>));
+    else if (atm && stages == 3) TC_LAUNCH_K((rank_tc_kernel<96, 128, 3, 0, 1, true>));
+    else if (atm && cap == 64) TC_LAUNCH_K((rank_tc_kernel<64, 128, 2, 0, 1, true>));
+    else if (atm) TC_LAUNCH_K((rank_tc_kernel<96, 128, 2, 0, 1, true>));
     else
-    if (bn == 128) { if (cap == 64) TC_LAUNCH(64, 128, 3); else TC_LAUNCH(96, 128, 3); }
+    if (bn == 128) { if (cap == 64 && stages == 4) TC_LAUNCH(64, 128, 4); else if (cap == 64) TC_LAUNCH(64, 128, 3); else TC_LAUNCH(96, 128, 3); }
     else { if (cap == 64) TC_LAUNCH(64, 64, 2); else TC_LAUNCH(96, 64, 2); }
 #undef TC_LAUNCH
-#undef TC_LAUNCH_EXP
+#undef TC_LAUNCH_K
     ++launches;
     TC_CK(cudaGetLastError());
 
