@@ -275,6 +275,40 @@ def test_blocked_kernel_conflict_free_all_widths(engine, d):
     assert loss == pytest.approx(ref_loss, rel=1e-5)
 
 
+@pytest.mark.parametrize("d,n", [(64, 40), (64, 7), (32, 12), (128, 25), (20, 9)])
+def test_blocked_kernel_read_schedule_is_pinned_when_tracks_repeat(engine, d, n):
+    """What the throughput kernel does when a track REPEATS inside a block of 4 triplets or in the next block -- the case
+    the conflict-free test avoids and the quality checks only see statistically.  One warp (the log is far below a second
+    warp's share), tiny catalogs (7-40 tracks: repeats in nearly every block), users with 1..70 triplets: the tables must
+    equal oracle/bpr_blk_ref.py -- the reference's arithmetic per triplet, rows of block k read before block k-1's changes
+    are added, every change added -- to 1e-4 (a row of a 7-track catalog takes ~600 float32 adds whose rounding depends
+    on the order the atomics land in; measured 4e-6 on P, 2e-5 on Q), the loss to 1e-5; the serial order is 100x further."""
+    from oracle import bpr_blk_ref
+    m = 60
+    rng = np.random.default_rng(d * 100 + n)
+    per = 1 + rng.integers(0, 70, m)
+    u = np.repeat(np.arange(m, dtype=np.int32), per)
+    T = len(u)
+    i = rng.integers(0, n, T).astype(np.int32)
+    j = ((i + 1 + rng.integers(0, n - 1, T)) % n).astype(np.int32)            # any track but the positive
+    assert (i != j).all()
+    log = synth.power_law_log(m, max(n, 300), 3000, seed=3)                   # only fixes m for the handle; triplets are explicit
+    P, Q = synth.init_factors(m, max(n, 300), d, seed=2)
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    engine.set_factors(P, Q)
+    loss = engine.bpr_apply(u, i, j, 0.05, 0.01, 0.02, MODE_HOGWILD)
+    Pg, Qg = engine.get_factors()
+    Pr, Qr = P.copy(), Q.copy()
+    ref_loss = bpr_blk_ref.sgd_apply_blocked(Pr, Qr, u, i, j, 0.05, 0.01, 0.02)
+    eP, eQ = rel_err(Pg, Pr), rel_err(Qg, Qr)
+    assert eP < 1e-4 and eQ < 1e-4
+    assert loss == pytest.approx(ref_loss, rel=1e-5)
+    # and it is NOT the serial order: the schedule is a real, pinned deviation
+    Ps, Qs = P.copy(), Q.copy()
+    bpr_ref.sgd_epoch(Ps, Qs, u, i, j, 0.05, 0.01, 0.02)
+    assert rel_err(Qg, Qs) > 20 * max(eQ, REL)
+
+
 @pytest.mark.parametrize("d", [10, 32, 50, 64, 100, 128])
 def test_blocked_kernel_hot_table_lr0_and_conservation(monkeypatch, d):
     """Hot-row table with second rows, every track of a small catalog hot.  (1) lr = 0: the epoch must

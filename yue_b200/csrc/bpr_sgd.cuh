@@ -100,8 +100,10 @@ struct SgdParams {
     // 5 %).  Per-CTA copies of the hot rows in shared memory removed the chain but cost 1.5-2.4 points
     // of Recall@10 (stale replicas; profiles/quality_study_r1.md), so the hot rows are instead kept
     // as SHARDED ACCUMULATORS: the logical row is  Q[t] + sum_r shard[r][t];  a warp adds its change
-    // to shard (warp % R) and every reader sums all R rows.  One logical copy, nothing goes stale,
-    // the chain per address is R times shorter.  hot_fold_kernel folds the shards back into Q.
+    // to shard (warp % R) and every reader OF A POSITIVE sums all R rows.  One logical copy, nothing goes
+    // stale, the chain per address is R times shorter.  hot_fold_kernel folds the shards back into Q.
+    // (A hot track drawn as the NEGATIVE -- a uniform draw: n_hot / n of the triplets -- is read through
+    // Q[t] alone, i.e. without the shards' share of the launch's changes; what is added is unaffected.)
     uint32_t slot;                 // which negative of the positive (0 for BPR; APR draws 3, slots 0..2)
     float eps, regA;               // APR only: perturbation size and adversarial weight (APR.conf -eps -regA)
     int resync_events;             // a shared (multi-item) user publishes + re-reads P[u] every this many events

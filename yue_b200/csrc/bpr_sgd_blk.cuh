@@ -416,6 +416,11 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                                 nxt.pi[a] = q_ptr(it); nxt.pj[a] = q_ptr(jt);
                                 ldq(nxt.pi[a], nxt.qi[a]);
                                 ldq(nxt.pj[a], nxt.qj[a]);
+                                // A sharded hot track drawn as the NEGATIVE is read through its first accumulator row only (its
+                                // second row would need V more registers per triplet in a kernel that has none to spare): the
+                                // score then misses the other row's share of the launch's changes.  A negative is a uniform draw
+                                // over the catalog, so at most kHotExtra / n of the triplets (config C2: 8 / 200 000) are
+                                // affected, and only in the value read, never in what is added.
                                 if (it < 0) {                                   // a sharded hot positive: fetch its second row too
                                     nxt.dx[a] = hot_dx[-it - 1];
                                     if (nxt.dx[a]) ldq(reinterpret_cast<float*>(reinterpret_cast<char*>(nxt.pi[a]) + nxt.dx[a]), nxt.ex[a]);
