@@ -806,7 +806,11 @@ int yue_set_factors(yue_t* h, int k, const float* P, const float* Q) {
     REQUIRE(h->have_log, YUE_E_STATE, "call yue_set_interactions first (it fixes m and n)");
     REQUIRE(k >= 1 && k <= 256, YUE_E_UNSUPPORTED, "num.factors must be in 1..256");
     CK(cudaSetDevice(h->device));
-    const int ld = (k + 3) & ~3;
+    // Row stride: k rounded up to 4 floats (128-bit accesses).  Between 65 and 127 factors the blocked SGD kernel would run
+    // its 4-floats-per-lane form with masked lanes, which does not fit the register file (1.3 KB of spills): those widths
+    // are padded to 128 floats instead (the full-width instantiation; pad columns stay zero under every update).
+    int ld = (k + 3) & ~3;
+    if (ld > 64 && ld < 128 && !(getenv("YUE_LD_PAD128") && atoi(getenv("YUE_LD_PAD128")) == 0)) ld = 128;
     h->k = k; h->ld = ld;
     CK(h->P.resize((size_t)std::max<int64_t>(h->m, 1) * ld));
     CK(h->Q.resize((size_t)h->n * ld));
