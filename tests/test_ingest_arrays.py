@@ -97,6 +97,29 @@ def test_splits_follow_the_reference(golden_dir, tmp_path):
         assert [log.names["track"][t] for t in ev_items[ev_indptr[u]:ev_indptr[u + 1]]] == tracks
 
 
+def test_arrow_coded_path_equals_the_object_path(golden_dir, tmp_path):
+    """load_numbered's fast path (Arrow CSV reader + dictionary codes, ids re-assigned by integer work only) gives exactly
+    the numbered events and name tables of the object path (which the tests above pin to the reference's Record)."""
+    pytest.importorskip("pyarrow")
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    path = str(tmp_path / "log.txt")
+    _write_csv(path, g["events"])
+    assert ingest.read_coded(path, COLUMNS, ",") is not None and ingest.read_coded(path, COLUMNS, "") is None
+    for ev in ("-target track -ap 0.2", "-target track"):
+        random.seed(5)
+        a = ingest.load_numbered(path, COLUMNS, ",", LineConfig(ev), "track")
+        random.seed(5)
+        cols = ingest.read_columns(path, COLUMNS, ",")
+        if "-ap" in ev:
+            held = ingest.split_ap(len(cols["user"]), 0.2)
+            b = ingest.number_events({k: v[~held] for k, v in cols.items()}, {k: v[held] for k, v in cols.items()}, "track", list(COLUMNS))
+        else:
+            b = ingest.number_events(cols, None, "track", list(COLUMNS))
+        assert np.array_equal(a.ev_user, b.ev_user) and np.array_equal(a.ev_item, b.ev_item) and np.array_equal(a.is_test, b.is_test)
+        for kind in ("user", "track", "artist"):
+            assert list(a.names[kind]) == list(b.names[kind])
+
+
 def test_result_lines_and_measures_match_the_loops():
     rng = np.random.default_rng(3)
     m, n, N = 300, 500, 10
@@ -122,6 +145,17 @@ def test_result_lines_and_measures_match_the_loops():
     # IterativeRecommender.py:145-155
     want_lines = [un[u] + ":" + "".join(item + ("*" if item in origin[un[u]] else "") for item in rec[un[u]]) + "\n" for u in users]
     assert ingest.result_lines(un[users], tn, ids, hits) == want_lines
+    # the same lines from the library's host code (yue_result_lines, what the class API uses): one string, all cores
+    ub, uo = ingest.name_blob(un[users])
+    tb, to = ingest.name_blob(tn)
+    assert ingest.result_text(ub, uo, tb, to, ids, hits) == "".join(want_lines)
+    big = np.tile(ids, (30, 1))                               # > 4096 rows: the multi-threaded path
+    bh = np.tile(hits, (30, 1))
+    bub, buo = ingest.name_blob(np.tile(un[users], 30))
+    assert ingest.result_text(bub, buo, tb, to, big, bh) == "".join(want_lines * 30)
+    bad = ids.copy(); bad[3, 2] = n                           # an id outside the catalog is refused, not read
+    with pytest.raises(Exception):
+        ingest.result_text(ub, uo, tb, to, bad, hits)
     # evaluation/measure.py:16-41 (+ NDCG)
     with redirect_stdout(io.StringIO()):
         want = Measure.rankingMeasure(origin, rec, [5, 10], n)

@@ -136,6 +136,8 @@ SIGNATURES = {
     "yue_set_sgd_concurrency": (C.c_int, [_H, C.c_int, C.c_int]),
     "yue_apr_epoch_part": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,
                                      C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _f64p]),
+    "yue_result_lines": (C.c_int, [C.c_char_p, _i64p, C.c_char_p, _i64p, C.c_int64, _i32p, C.POINTER(C.c_uint8), C.c_int64, C.c_int,
+                                   C.c_void_p, C.c_int64, _i64p]),
     "yue_timer_start": (C.c_int, [_H]),
     "yue_timer_stop": (C.c_int, [_H, _f32p]),
     "yue_launch_count": (C.c_int, [_H, _i64p]),

@@ -269,7 +269,7 @@ class GpuBPRMixin(object):
     def _eval_ranking_arrays(self, top, N):
         """evalRanking over ingest.ArrayRecord: every step on arrays -- ranking (K3/K5), the measures (K6) and the hit marks
         of the result lines (one sorted search); the only per-user Python left is joining a line's cells."""
-        from .ingest import hit_mask, ranking_measure, result_lines
+        from .ingest import hit_mask, name_blob, ranking_measure, result_text
         eng = self._push_factors()
         data = self.data
         uid = np.flatnonzero(np.diff(data.test_indptr) > 0).astype(np.int32)
@@ -280,9 +280,13 @@ class GpuBPRMixin(object):
             ids, _ = eng.rank_topn(uid, N, RANK_AUTO)
         un, tn = data.log.names['user'], data.log.names[self.recType]
         hits = hit_mask(uid, ids, self.n, data.test_indptr, data.test_items)
-        res = ['userId: recommendations in (itemId, ranking score) pairs, * means the item matches.\n'] + result_lines(un[uid], tn, ids, hits)
+        if getattr(data, '_track_blob', None) is None:
+            data._track_blob = name_blob(tn)                        # the catalog's names as one blob, once per Record
+        ub, uo = name_blob(un[uid])
+        res = ['userId: recommendations in (itemId, ranking score) pairs, * means the item matches.\n',
+               result_text(ub, uo, data._track_blob[0], data._track_blob[1], ids, hits)]
         self.rec_ids, self.rec_users = ids, uid
-        if self._opt('yue.metrics', 'host') == 'device' and len(devs) == 1:
+        if self._opt('yue.metrics', 'device') == 'device' and len(devs) == 1:
             measure, ndcg = self._format_device_measure(uid, top)      # K6 over the lists the call left on the device
         else:
             measure, ndcg = ranking_measure(ids, hits, np.diff(data.test_indptr)[uid], top, self.n)

@@ -1946,6 +1946,62 @@ int yue_q_exchange_finish(yue_t* h, int quiescent) {
     return YUE_OK;
 }
 
+// ---- result lines of evalRanking (host code) --------------------------------------------------------------------------
+int yue_result_lines(const char* user_blob, const int64_t* user_off, const char* track_blob, const int64_t* track_off,
+                     int64_t n_tracks, const int32_t* ids, const uint8_t* hits, int64_t B, int N,
+                     char* out, int64_t out_cap, int64_t* out_len) {
+    if (!user_blob || !user_off || !track_blob || !track_off || !ids || !hits || !out_len || B < 0 || N < 0 || n_tracks < 0) {
+        g_create_error = "yue_result_lines: null or negative argument";
+        return YUE_E_ARG;
+    }
+    const size_t nth = B < 4096 ? 1 : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<int64_t> first(nth + 1, 0);
+    std::vector<int> bad(nth, 0);
+    auto share = [&](size_t t) { return B * (int64_t)t / (int64_t)nth; };
+    auto line_len = [&](int64_t b) {
+        int64_t len = user_off[b + 1] - user_off[b] + 2;                   // name ':' ... '\n'
+        for (int r = 0; r < N; ++r) {
+            const int32_t id = ids[b * N + r];
+            if (id < 0) continue;
+            if (id >= n_tracks) return (int64_t)-1;
+            len += track_off[id + 1] - track_off[id] + (hits[b * N + r] ? 1 : 0);
+        }
+        return len;
+    };
+    auto run = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nth; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto& x : th) x.join();
+    };
+    run([&](size_t t) {                                                     // pass 1: bytes per thread's share
+        int64_t sum = 0;
+        for (int64_t b = share(t); b < share(t + 1); ++b) { const int64_t l = line_len(b); if (l < 0) { bad[t] = 1; return; } sum += l; }
+        first[t + 1] = sum;
+    });
+    for (size_t t = 0; t < nth; ++t) if (bad[t]) { g_create_error = "yue_result_lines: a ranked id is outside the catalog"; return YUE_E_ARG; }
+    for (size_t t = 0; t < nth; ++t) first[t + 1] += first[t];
+    *out_len = first[nth];
+    if (!out || out_cap < first[nth]) { g_create_error = "yue_result_lines: output buffer too small"; return YUE_E_ARG; }
+    run([&](size_t t) {                                                     // pass 2: the bytes
+        char* w = out + first[t];
+        for (int64_t b = share(t); b < share(t + 1); ++b) {
+            const int64_t ul = user_off[b + 1] - user_off[b];
+            memcpy(w, user_blob + user_off[b], (size_t)ul); w += ul;
+            *w++ = ':';
+            for (int r = 0; r < N; ++r) {
+                const int32_t id = ids[b * N + r];
+                if (id < 0) continue;
+                const int64_t tl = track_off[id + 1] - track_off[id];
+                memcpy(w, track_blob + track_off[id], (size_t)tl); w += tl;
+                if (hits[b * N + r]) *w++ = '*';
+            }
+            *w++ = '\n';
+        }
+    });
+    return YUE_OK;
+}
+
 // ---- measurement hooks ---------------------------------------------------------------------
 int yue_timer_start(yue_t* h) { CK(cudaSetDevice(h->device)); CK(cudaEventRecord(h->ev0, h->stream)); return YUE_OK; }
 int yue_timer_stop(yue_t* h, float* ms) {

@@ -99,10 +99,70 @@ def by_time(cols, ratio):
     return order[is_train], order[~is_train]
 
 
+def read_coded(path, columns, delim):
+    """The non-time columns of a log file as (codes int32[events], names[array of str]) per column WITHOUT creating a Python
+    string per field: Arrow's multi-threaded CSV reader + dictionary encoding (codes in order of first appearance in the
+    file).  None when that reader cannot take the file (a regex delimiter, pyarrow missing): the caller falls back to
+    read_columns."""
+    if len(delim) != 1:
+        return None
+    try:
+        import pyarrow as pa
+        import pyarrow.csv as pc
+    except ImportError:
+        return None
+    used = sorted(set(int(v) for k, v in columns.items() if k != 'time'))
+    tbl = pc.read_csv(path, read_options=pc.ReadOptions(autogenerate_column_names=True),
+                      parse_options=pc.ParseOptions(delimiter=delim, quote_char=False),
+                      convert_options=pc.ConvertOptions(include_columns=['f%d' % i for i in used], column_types={'f%d' % i: pa.string() for i in used},
+                                                        strings_can_be_null=False))
+    out = {}
+    for name, ind in columns.items():
+        if name == 'time':
+            continue
+        d = tbl['f%d' % int(ind)].combine_chunks().dictionary_encode()
+        idx = d.indices                                            # int32, no nulls: read the buffer directly (to_numpy() pulls in pandas)
+        codes = np.frombuffer(idx.buffers()[1], dtype=np.int32, count=len(idx), offset=idx.offset * 4).copy()
+        out[name] = (codes, np.asarray(d.dictionary.to_pylist(), dtype=object))
+    return out
+
+
+def number_coded(train, test, rec_type='track', key_order=None):
+    """number_events on coded columns: train / test = {column: (codes, names)} with the SAME names table per column (codes of
+    one dictionary).  Ids are re-assigned by first appearance over the training events, then the test events
+    (data/record.py:138-146, 182-188) -- integer work only."""
+    codes, names = {}, {}
+    nt = len(train['user'][0])
+    for kind in (key_order or train.keys()):
+        if kind == 'time':
+            continue
+        c = train[kind][0] if test is None else np.concatenate([train[kind][0], test[kind][0]])
+        table = train[kind][1]
+        # where each code occurs first: written back to front, so that for a repeated code the LAST write -- its first
+        # occurrence -- stays (numpy assigns repeated indices in order); no sort over the events
+        first = np.full(len(table), len(c), dtype=np.int64)
+        first[c[::-1]] = np.arange(len(c) - 1, -1, -1, dtype=np.int64)
+        seen = np.flatnonzero(first < len(c))
+        order = seen[np.argsort(first[seen], kind='stable')]        # the codes that occur, in order of first appearance
+        remap = np.full(len(table), -1, dtype=np.int32)
+        remap[order] = np.arange(len(order), dtype=np.int32)
+        codes[kind], names[kind] = remap[c], table[order]
+    is_test = np.zeros(len(codes['user']), dtype=np.uint8)
+    is_test[nt:] = 1
+    return ArrayLog(codes['user'], codes[rec_type], is_test, names, rec_type)
+
+
 def load_numbered(path, columns, delim, evaluation, rec_type='track'):
     """File -> ArrayLog under the reference's evaluation.setup options -ap r / -testSet file / -byTime r (yue.py:38-46)."""
-    cols = read_columns(path, columns, delim)
     order = [k for k in columns.keys()]
+    if not evaluation.contains('-byTime'):                          # -byTime compares the time fields as strings: object path
+        coded = read_coded(path, columns, delim)
+        if coded is not None and evaluation.contains('-ap'):
+            held = split_ap(len(coded['user'][0]), float(evaluation['-ap']))
+            return number_coded({k: (c[~held], t) for k, (c, t) in coded.items()}, {k: (c[held], t) for k, (c, t) in coded.items()}, rec_type, order)
+        if coded is not None and not evaluation.contains('-testSet'):
+            return number_coded(coded, None, rec_type, order)
+    cols = read_columns(path, columns, delim)
     if evaluation.contains('-testSet'):
         return number_events(cols, read_columns(evaluation['-testSet'], columns, delim), rec_type, order)
     if evaluation.contains('-ap'):
@@ -192,6 +252,34 @@ def hit_mask(users, ids, n, test_indptr, test_items):
     pos = np.searchsorted(keys, q.ravel()).reshape(q.shape)
     pos = np.minimum(pos, max(len(keys) - 1, 0))
     return (keys[pos] == q) & (ids >= 0) if len(keys) else np.zeros(ids.shape, dtype=bool)
+
+
+def name_blob(names):
+    """(bytes, int64 offsets[len + 1]) of an array of names: the form yue_result_lines reads."""
+    enc = [x.encode('utf-8') for x in names]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum(np.fromiter((len(x) for x in enc), dtype=np.int64, count=len(enc)), out=off[1:])
+    return b''.join(enc), off
+
+
+def result_text(user_blob, user_off, track_blob, track_off, ids, hits):
+    """IterativeRecommender.py:145-155 for all ranked users at once, as ONE string of lines, built by the library's host
+    code on all cores (yue_result_lines); user_blob / user_off describe the ranked users in order."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    hits = np.ascontiguousarray(hits, dtype=np.uint8)
+    B, N = ids.shape
+    need = C.c_int64(0)
+    args = (user_blob, user_off.ctypes.data_as(C.POINTER(C.c_int64)), track_blob, track_off.ctypes.data_as(C.POINTER(C.c_int64)),
+            C.c_int64(len(track_off) - 1), ids.ctypes.data_as(C.POINTER(C.c_int32)), hits.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(B), C.c_int(N))
+    lib.yue_result_lines(*args, None, C.c_int64(0), C.byref(need))
+    buf = C.create_string_buffer(max(need.value, 1))
+    rc = lib.yue_result_lines(*args, C.cast(buf, C.c_void_p), C.c_int64(need.value), C.byref(need))
+    if rc:
+        raise _lib.YueError(rc, lib.yue_last_error(None).decode())
+    return buf.raw[:need.value].decode('utf-8')
 
 
 def result_lines(user_names, track_names, ids, hits):
