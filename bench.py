@@ -502,8 +502,8 @@ def run_native(args):
             sq.update(log=qlog_desc + "; ONE log, users interleaved over the ranks, plain sum of the tail deltas", reference=qref)
             sharded["quality"] = sq
             sharded["quality_at_bench_size"] = ("not in the gate: on C2-sized shards a moderately played track is touched thousands of times per "
-                                                "rank between two of the 32 exchanges, beyond what summed deltas follow (DESIGN.md section 6); "
-                                                "the quality block above is this trainer on a log small enough for 32 exchanges per epoch")
+                                                "rank between two exchanges, beyond what summed deltas follow (DESIGN.md section 6); "
+                                                "the quality block above is this trainer on a log small enough for %d exchanges per epoch" % args.sub_epochs)
         del qlog, qP, qQ
 
     # ---- round 1's schedule, for continuity: replicas of ALL rows, saturation-weighted sum once per epoch ----
@@ -777,7 +777,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug-size workload (not a bench number)")
     ap.add_argument("--sgd-mode", default="atomic", choices=["atomic", "store"])
     ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="BASELINE.json configs[1] (default) or configs[2]")
-    ap.add_argument("--sub-epochs", type=int, default=32, help="multi-GPU: parts per epoch = exchanges of the tail of Q")
+    ap.add_argument("--sub-epochs", type=int, default=0, help="multi-GPU: parts per epoch = exchanges of the tail of Q (0 = sharding.default_sub_epochs: 32 up to 2 GPUs, 4 N^2 above)")
     ap.add_argument("--asynchrony", type=float, default=1.0,
                     help="multi-GPU: the ranks together run this many times the warps one GPU gives the whole log (DESIGN.md section 6)")
     ap.add_argument("--reserve-sms", type=int, default=8, help="multi-GPU: SMs the epoch kernel leaves to the NCCL kernels")
@@ -796,6 +796,9 @@ def main():
     if args.warmup < 3 and not args.small:
         args.warmup = 3
     quiet_stdout()
+    if args.sub_epochs <= 0:
+        from yue_b200.sharding import default_sub_epochs
+        args.sub_epochs = default_sub_epochs(int(os.environ.get("WORLD_SIZE", args.gpus)))
     if args.impl == "reference":
         run_reference(args)
     else:

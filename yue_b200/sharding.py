@@ -267,6 +267,15 @@ class TorchCtl:
         return t.cpu().numpy()
 
 
+def default_sub_epochs(world):
+    """Parts per epoch (= exchanges of the tail of Q) that kept SharedHotTrainer inside the 0.5-point gate on the fixed
+    5 M-play quality log (profiles/r2/quality_n*.log, asynchrony 1 and 2): 32 on 2 GPUs, 32 / 64 on 4, 64 / 128 / 256 on 8
+    (32 parts on 8 GPUs: Recall@10 -0.022).  Every rank adds its tail deltas blind to the other N - 1 ranks' for two parts
+    (the sum arrives one part late), so the parts have to shrink as the ranks grow: 32 up to 2 ranks, 4 N^2 above."""
+    world = int(world)
+    return 32 if world <= 2 else 4 * world * world
+
+
 class SharedHotTrainer:
     """One rank of the round-2 trainer (include/yue_b200.h "multi-GPU, round 2").
 
@@ -286,11 +295,12 @@ class SharedHotTrainer:
     torch.distributed), or None = chosen here: ranks that are handles of ONE process sum each other's deltas over peer
     memory (yue_q_exchange_reduce_peers), ranks in different processes use the library's NCCL communicator."""
 
-    def __init__(self, engine, ctl, local_counts, sub_epochs=32, asynchrony=1.0, reserve_sms=8, reduce=None, row_weights=None,
+    def __init__(self, engine, ctl, local_counts, sub_epochs=None, asynchrony=1.0, reserve_sms=8, reduce=None, row_weights=None,
                  hot_max=24, sm_count=148, warps_per_sm=12, min_events_per_warp=16384):
         import os
         from . import engine as _eng
-        self.eng, self.ctl, self.sub_epochs = engine, ctl, int(sub_epochs)
+        self.eng, self.ctl = engine, ctl
+        self.sub_epochs = int(sub_epochs) if sub_epochs else default_sub_epochs(ctl.world)
         counts = ctl.allreduce_sum(np.asarray(local_counts, dtype=np.int64))
         tracks, tcounts, total = select_hot_tracks(counts, hot_max=hot_max)
         self.hot_tracks, self.total_events = tracks, total
