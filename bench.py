@@ -530,6 +530,9 @@ def run_native(args):
     cune = None
     if world == 1 and args.config == "C2" and not args.no_cune:
         cune = bench_cune(eng, args)
+    gcn = None
+    if world == 1 and args.config == "C2" and not args.no_gcn:
+        gcn = bench_lightgcn(eng, args)
 
     # ---- config C3's shard on one GPU: Q = 1 GB does not fit in L2, the honest HBM case (N = 1 line only) ----
     c3 = None
@@ -592,6 +595,8 @@ def run_native(args):
             out["wrmf"] = wrmf
         if cune:
             out["cune"] = cune
+        if gcn:
+            out["lightgcn"] = gcn
         if c3:
             out["c3"] = c3
 
@@ -645,6 +650,47 @@ def bench_cune(eng, args):
             "workload": "CUNE d=64, s=2, lr 0.02, reg 0.01: %d users x %d tracks x %d events, %d implicit positives" % (m, log.n, T, len(ip_items)),
             "note": "the number of warps is bounded by the log (one per 16 384 events, like K2: profiles/cune_r2.md); the kernel is a chain of "
                     "7 dependent dot products + sigmoids per repeat (CUNE.py:134-159 re-evaluates every sigmoid), issue-latency bound"}
+
+
+def bench_lightgcn(eng, args):
+    """LightGCN (recommender/advanced/LightGCN.py:27-98, K9) at config/LightGCN.conf's settings (50 factors,
+    batches of 128, lr 0.002, reg 0.001, 3 layers) on config C1's shape (the reference's own scale: every step propagates
+    over the WHOLE graph), and on a log ten times larger.  A pass over the batches is one cooperative launch; a step is
+    2 L + 2 = 8 graph-wide phases."""
+    from yue_b200 import synth
+    from yue_b200.lightgcn import truncated_normal
+    out = {"metric": "lightgcn_steps_per_sec", "unit": "Adam steps/s (128 triplets, 3-layer propagation forward and backward over the whole graph)",
+           "kernel": "gcn_steps_kernel<16, 1>: one cooperative launch per pass"}
+    for name, (users, tracks, plays, steps) in (("c1_shape", (4_000, 50_000, 100_000, 0)), ("x10", (40_000, 100_000, 1_000_000, 600))):
+        if args.small and name == "x10":
+            continue
+        log = synth.power_law_log(users, tracks, plays, SEED + 41, test_ratio=0.2)
+        ev_user = np.repeat(np.arange(log.m, dtype=np.int32), np.diff(log.ev_indptr))
+        perm = np.random.default_rng(SEED + 42).permutation(len(ev_user))
+        rng = np.random.default_rng(SEED + 43)
+        U, V = truncated_normal((log.m, 50), 0.005, rng), truncated_normal((log.n, 50), 0.005, rng)
+        eng.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+        eng.set_factors(U, V)
+        eng.gcn_set_events(ev_user[perm], log.ev_items[perm])
+        n_steps = (log.train_size + 127) // 128
+        end = min(n_steps, steps) if steps else n_steps
+        eng.gcn_epoch(128, 0.002, 0.001, SEED, 0, step_end=min(end, 50))          # warm-up (also builds the row lists)
+        ms, losses = [], None
+        for ep in range(1, 4):
+            eng.sync()
+            eng.timer_start()
+            losses = eng.gcn_epoch(128, 0.002, 0.001, SEED, ep, step_end=end)
+            ms.append(eng.timer_stop())
+        t = min(ms)
+        nnz = int(log.uq_indptr[-1])
+        out[name] = {"users": log.m, "tracks": log.n, "train_events": log.train_size, "graph_edges": 2 * nnz, "steps": end,
+                     "ms_per_pass": t, "us_per_step": 1e3 * t / end, "steps_per_sec": end / (t * 1e-3),
+                     "gathered_GBps": 5 * 2 * nnz * 52 * 4 * end / (t * 1e-3) / 1e9,
+                     "first_loss": float(losses[0]), "last_loss": float(losses[-1])}
+    out["value"] = out["c1_shape"]["steps_per_sec"]
+    out["note"] = ("gathered_GBps = 5 dense products per step x edges x 208-byte rows (the sixth product reads only the <= 384 rows the "
+                   "batch touched); at C1's shape a step is bound by its 8 grid barriers, not by bandwidth")
+    return out
 
 
 def bench_c3_shard(eng, args, hbm_peak):
@@ -787,6 +833,7 @@ def main():
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-cune", action="store_true")
+    ap.add_argument("--no-gcn", action="store_true")
     ap.add_argument("--no-rank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-apr", action="store_true")

@@ -165,6 +165,31 @@ int yue_cune_set_implicit(yue_t* h, const int64_t* ip_indptr, const int32_t* ip_
 int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s,
                    uint64_t seed, uint32_t epoch, int mode, double* loss_out);
 
+/* LightGCN (recommender/advanced/LightGCN.py:15-105 on base/DeepRecommender:22-35).  The TF-1 graph:
+ * e_0 = [U; V], e_k = A e_{k-1}, F = e_0 + sum_k l2_normalize(e_k) (37-45), A = one SparseTensor entry of value count(u, t)
+ * per training EVENT and direction, duplicates summed, i.e. weight count^2 per pair (29-33: built here from the resident
+ * log's play counts); loss = -sum log sigmoid(F_u.(F_i - F_j)) + reg/2 (|F_u|^2 + |F_i|^2 + |F_j|^2) over a batch (83-87);
+ * AdamOptimizer(lr) on every row of U and V (88-90).  U, V are the handle's factor tables (yue_set_factors: the
+ * truncated-normal init of DeepRecommender:30-31 is the caller's); a new yue_set_factors restarts Adam.
+ * yue_gcn_set_events: the training events in FILE order -- next_batch_pairwise (56-79) walks `trainingData` in slices of
+ *   batch_size; they must be the resident log's events (YUE_E_ARG otherwise).
+ * yue_gcn_epoch: steps [step_begin, step_end) of one pass (step_end < 0: to the end; ceil(T / batch_size) steps per pass);
+ *   step s trains on events [s * batch_size, ...), one negative per event: the FIFTH draw (Philox slot 4, event = file
+ *   index, rejection against the user's plays) -- the reference draws five and keeps the last (68-78).
+ *   loss_out[s - step_begin] = that step's loss (what line 97 prints).  All steps run in one cooperative launch.
+ * yue_gcn_apply: one step on the caller's triplets (parity hook, no sampler).
+ * yue_gcn_finalize: P, Q <- the propagated tables F (what predict() ranks with, 45-47 and 101-105), so that yue_predict /
+ *   yue_rank_topn / yue_get_factors see them; the variables are kept and come back on the next yue_gcn_epoch / _apply. */
+int yue_gcn_set_events(yue_t* h, int64_t T, const int32_t* ev_user, const int32_t* ev_item);
+int yue_gcn_epoch(yue_t* h, int n_layers, int batch_size, double lr, double reg, uint64_t seed, uint32_t epoch,
+                  int64_t step_begin, int64_t step_end, double* loss_out);
+int yue_gcn_apply(yue_t* h, int n_layers, int64_t B, const int32_t* u, const int32_t* i, const int32_t* j,
+                  double lr, double reg, double* loss_out);
+int yue_gcn_finalize(yue_t* h, int n_layers);
+/* Adam's state (checkpointing; tests read the first step's gradient from it: m_1 = 0.1 g): first / second moments of U and
+ * V, [m, k] and [n, k] each (NULL = skip), and the number of steps taken since yue_set_factors. */
+int yue_gcn_moments(yue_t* h, float* m_users, float* m_tracks, float* v_users, float* v_tracks, int64_t* steps);
+
 /* (P*P).sum(), (Q*Q).sum() of BPR.py:59, accumulated in float64. */
 int yue_frob2(yue_t* h, double* p2, double* q2);
 

@@ -1,0 +1,180 @@
+"""K9 (LightGCN): oracle/lightgcn_ref.py restates recommender/advanced/LightGCN.py:27-98 (PARITY UNPINNED by
+the reference -- its module cannot be imported, see the oracle's header); the CPU tests pin the restatement's own gradient
+numerically, the GPU tests compare csrc/lightgcn.cuh (yue_gcn_apply / yue_gcn_epoch / yue_gcn_finalize) with it.
+
+Tolerances (float32 kernel against the float64 restatement): the loss of a step 2e-5 relative; the gradient of the first
+step (read back from Adam's first moment, m_1 = 0.1 g) 2e-4 of the largest row gradient, per row; the propagated tables
+1e-5 per row.  After several Adam steps a table entry whose gradient is rounding noise may differ by a full step (Adam
+divides by |g|), so the tables after a run are compared entry-wise: at least 99.5 % within 2 % of the distance moved."""
+import numpy as np
+import pytest
+
+from oracle import lightgcn_ref as lg
+from oracle import philox
+from yue_b200 import synth
+
+
+def file_order(log, seed):
+    """The log's training events in a shuffled 'file' order (any order with the same events per user is a valid file)."""
+    users = np.repeat(np.arange(log.m, dtype=np.int32), np.diff(log.ev_indptr))
+    perm = np.random.default_rng(seed).permutation(len(users))
+    return users[perm], log.ev_items[perm].astype(np.int32)
+
+
+def test_oracle_gradient_is_the_numerical_gradient():
+    rng = np.random.default_rng(0)
+    m, n, T, k = 30, 40, 300, 6
+    eu, ei = rng.integers(0, m, T), rng.zipf(1.5, T) % n
+    A = lg.adjacency(m, n, eu, ei)
+    U, V = lg.init_tables(m, n, k, 1)
+    E0 = np.concatenate([U, V]).astype(np.float64) * 20
+    u, i, j = eu[:16], ei[:16], rng.integers(0, n, 16)
+    _, g = lg.loss_and_grad(A, E0, m, u, i, j, 0.01)
+    for r, c in zip(rng.integers(0, m + n, 30), rng.integers(0, k, 30)):
+        Ep, Em = E0.copy(), E0.copy()
+        Ep[r, c] += 1e-6
+        Em[r, c] -= 1e-6
+        num = (lg.loss_of(A, Ep, m, u, i, j, 0.01) - lg.loss_of(A, Em, m, u, i, j, 0.01)) / 2e-6
+        assert abs(num - g[r, c]) <= 1e-6 * max(1.0, abs(num))
+
+
+def test_oracle_adjacency_weighs_a_pair_by_its_squared_count():
+    """LightGCN.py:29-33: one entry of value count per EVENT; duplicate entries add up in the sparse product."""
+    eu, ei = np.array([0, 0, 0, 1, 1]), np.array([2, 2, 1, 2, 0])
+    A = lg.adjacency(2, 3, eu, ei).toarray()
+    assert A[0, 2 + 2] == 4 and A[0, 2 + 1] == 1 and A[1, 2 + 2] == 1 and A[1, 2 + 0] == 1
+    assert np.array_equal(A, A.T) and A[:2, :2].sum() == 0 and A[2:, 2:].sum() == 0
+
+
+def test_truncated_normal_init_and_class_config(tmp_path):
+    from yue_b200.lightgcn import truncated_normal
+    x = truncated_normal((2000, 8), 0.005, np.random.default_rng(3))
+    assert x.dtype == np.float32 and np.abs(x).max() <= 0.01 + 1e-9 and 0.004 < x.std() < 0.0048
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [8, 50, 100, 130])
+def test_one_step_gradient_loss_and_update_match_the_oracle(engine, d):
+    log = synth.power_law_log(300, 200, 9000, seed=41)
+    eu, ei = file_order(log, 1)
+    assert np.bincount(ei, minlength=log.n).max() > 64                  # a row a whole CTA works on
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    U, V = lg.init_tables(log.m, log.n, d, 7)
+    U, V = U * 20, V * 20                                                # larger rows: sigmoid away from 1/2
+    engine.set_factors(U, V)
+    rng = np.random.default_rng(d)
+    B = 96
+    u, i = eu[:B].copy(), ei[:B].copy()
+    j = rng.integers(0, log.n, B).astype(np.int32)
+    u[5], i[5], j[6] = u[4], i[4], i[4]                                  # repeated rows inside the batch, on both sides
+    A = lg.adjacency(log.m, log.n, eu, ei)
+    E0 = np.concatenate([U, V]).astype(np.float64)
+    ref_loss, g = lg.loss_and_grad(A, E0, log.m, u, i, j, 0.001)
+    loss = engine.gcn_apply(u, i, j, 0.002, 0.001)
+    assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss)
+    mu, mt, vu, vt, steps = engine.gcn_moments()
+    assert steps == 1
+    got = np.concatenate([mu, mt]).astype(np.float64) / 0.1
+    scale = np.linalg.norm(g, axis=1).max()
+    assert np.linalg.norm(got - g, axis=1).max() <= 2e-4 * scale
+    assert np.allclose(np.concatenate([vu, vt]), 0.001 * g * g, rtol=2e-3, atol=1e-7 * scale * scale)
+    # the first Adam step moves every entry with a gradient by lr * g / (|g| + 1e-8 / sqrt(0.001)) ...
+    P1, Q1 = engine.get_factors()
+    moved = np.concatenate([P1, Q1]).astype(np.float64) - E0
+    want = -0.002 * g / (np.abs(g) + 1e-8 / np.sqrt(0.001))
+    sure = np.abs(g) > 1e-3 * scale
+    assert np.allclose(moved[sure], want[sure], rtol=1e-3, atol=1e-7)
+    assert np.array_equal(moved[g == 0], np.zeros(int((g == 0).sum())))  # ... and leaves the others where they were
+
+
+@pytest.mark.gpu
+def test_steps_with_the_fused_sampler_follow_the_oracle_and_finalize_gives_the_ranking_tables(engine):
+    log = synth.power_law_log(400, 300, 6000, seed=43)
+    eu, ei = file_order(log, 2)
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    d, batch, lr, reg, seed, steps = 50, 128, 0.002, 0.001, 20260107, 12
+    U, V = lg.init_tables(log.m, log.n, d, 9)
+    engine.set_factors(U, V)
+    engine.gcn_set_events(eu, ei)
+    neg = philox.sample_negatives(seed, 0, eu, log.n, log.uq_indptr, log.uq_items, slot=lg.NEG_SLOT)
+    assert not any(neg[e] in log.uq_items[log.uq_indptr[eu[e]]:log.uq_indptr[eu[e] + 1]] for e in range(0, len(eu), 37))
+    A = lg.adjacency(log.m, log.n, eu, ei)
+    rU, rV, rloss, _ = lg.train(A, U, V, eu, ei, log.uq_indptr, log.uq_items, batch, lr, reg, seed, epochs=1, max_steps=steps)
+    # two launches (5 + 7 steps): Adam's state and the step counter carry over
+    loss = np.concatenate([engine.gcn_epoch(batch, lr, reg, seed, 0, step_begin=0, step_end=5),
+                           engine.gcn_epoch(batch, lr, reg, seed, 0, step_begin=5, step_end=steps)])
+    assert np.allclose(loss, rloss, rtol=5e-4)
+    P, Q = engine.get_factors()
+    got, ref, start = np.concatenate([P, Q]).astype(np.float64), np.concatenate([rU, rV]), np.concatenate([U, V]).astype(np.float64)
+    moved = np.abs(ref - start)
+    ok = np.abs(got - ref) <= 0.02 * moved + 1e-9
+    assert ok.mean() >= 0.995
+    assert np.abs(got - ref).max() <= 2.5 * lr * steps
+    # the tables predict() ranks with: F of the kernel's own variables against the oracle's propagation of the same variables
+    engine.gcn_finalize()
+    FU, FV = engine.get_factors()
+    wU, wV = lg.embeddings(A, P, Q)
+    rel = np.linalg.norm(np.concatenate([FU, FV]) - np.concatenate([wU, wV]), axis=1) / np.linalg.norm(np.concatenate([wU, wV]), axis=1)
+    assert rel.max() <= 1e-5
+    scores = engine.predict(3)
+    assert np.allclose(scores, FV @ FU[3], rtol=1e-5, atol=1e-6)
+    # training goes on from the variables, not from F
+    more = engine.gcn_epoch(batch, lr, reg, seed, 0, step_begin=steps, step_end=steps + 1)
+    P2, _ = engine.get_factors()
+    assert np.isfinite(more).all() and np.abs(P2 - P).max() <= 3 * lr
+
+
+@pytest.mark.gpu
+def test_refusals(engine):
+    from yue_b200.engine import YueError
+    log = synth.power_law_log(50, 60, 600, seed=3)
+    eu, ei = file_order(log, 3)
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    U, V = lg.init_tables(log.m, log.n, 16, 1)
+    engine.set_factors(U, V)
+    with pytest.raises(YueError):
+        engine.gcn_epoch(128, 0.002, 0.001, 1, 0)                        # events not set
+    with pytest.raises(YueError):
+        engine.gcn_set_events(eu[:-1], ei[:-1])                          # not the resident log
+    bad = eu.copy()
+    bad[0] = (bad[0] + 1) % log.m
+    with pytest.raises(YueError):
+        engine.gcn_set_events(bad, ei)                                   # another user's event
+    engine.gcn_set_events(eu, ei)
+    with pytest.raises(YueError):
+        engine.gcn_epoch(5000, 0.002, 0.001, 1, 0)                       # batch beyond the scratch
+    with pytest.raises(YueError):
+        engine.gcn_apply(np.array([0]), np.array([0]), np.array([log.n]), 0.002, 0.001)
+    assert len(engine.gcn_epoch(128, 0.002, 0.001, 1, 0)) == (len(eu) + 127) // 128
+
+
+@pytest.mark.gpu
+def test_class_api_trains_and_ranks_with_the_propagated_tables(tmp_path, golden_dir):
+    """Yue -> LightGCN.execute() on the golden log: the losses of a pass fall, predict() is F_items . F_user, the measure
+    list has the reference's layout."""
+    import io
+    import json
+    import os
+    from contextlib import redirect_stdout
+    from yue_b200.host.config import Config
+    from yue_b200.lightgcn import LightGCN
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    train = [e for e, h in zip(g["events"], g["held"]) if not h]
+    test = [e for e, h in zip(g["events"], g["held"]) if h]
+    conf = Config(values={"record": "./dataset/log.txt", "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,",
+                          "recommender": "LightGCN", "evaluation.setup": "-target track -byTime 0.2", "item.ranking": "-topN 5,10",
+                          "num.factors": "50", "num.max.iter": "3", "batch_size": "128", "learnRate": "-init 0.002 -max 1",
+                          "reg.lambda": "-u 0.001 -i 0.001 -b 0.2 -s 0.2", "output.setup": "on -dir %s/" % tmp_path,
+                          "yue.seed": "5"})
+    out = io.StringIO()
+    with redirect_stdout(out):
+        rec = LightGCN(conf, train, test)
+        measure = rec.execute()
+    text = out.getvalue()
+    first = [float(l.split('loss:')[1]) for l in text.splitlines() if l.startswith('training:') and ' batch 0 ' in l]
+    assert len(first) == 3 and first[2] < first[0]
+    assert measure[0] == 'Top 5\n' and measure[1].startswith('Precision:')
+    u = next(iter(rec.data.testSet))
+    uid = rec.data.getId(u, 'user')
+    assert np.allclose(rec.predict(u), rec.multi_item_embeddings @ rec.multi_user_embeddings[uid], rtol=1e-5, atol=1e-6)
+    assert rec.U.shape == (rec.m, 50) and not np.array_equal(rec.U, rec.multi_user_embeddings)

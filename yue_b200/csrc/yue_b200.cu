@@ -26,6 +26,7 @@
 #include "rank_tc.cuh"
 #include "wrmf_als.cuh"
 #include "cune_sgd.cuh"
+#include "lightgcn.cuh"
 
 using namespace yue;
 
@@ -220,6 +221,18 @@ struct yue_handle {
     DevBuf<int64_t> cune_items;               // work items of the epoch kernel (cune_plan_items)
     int64_t cune_n_work = 0, cune_chunk = -1; // -1: no plan for the current log
     DevBuf<unsigned long long> cune_ctr;      // [0] user cursor, [1] users with events
+
+
+    // LightGCN (K9): the training events in FILE order (batches are slices of it), row lists of the product phases, the
+    // layers, the backward buffers, Adam's moments and the batch scratch
+    bool gcn_events = false, gcn_planned = false, gcn_final = false;
+    DevBuf<int32_t> gcn_ev_user, gcn_ev_item, gcn_neg, gcn_heavy, gcn_light, gcn_slot_row, gcn_slot_of;
+    DevBuf<uint32_t> gcn_stamp;
+    DevBuf<float> gcn_E[kGcnMaxLayers], gcn_rinv, gcn_D[2], gcn_am, gcn_av, gcn_slot_grad, gcn_NB, gcn_trip_loss, gcn_varP, gcn_varQ;
+    DevBuf<double> gcn_loss;
+    std::vector<int64_t> h_it_indptr;
+    int gcn_n_heavy = 0; int64_t gcn_n_light = 0, gcn_t = 0;
+    uint32_t gcn_stamp_base = 0;
 
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -438,6 +451,9 @@ int yue_destroy(yue_t* h) {
     h->scal.release();
     h->ip_indptr.release(); h->ip_items.release(); h->cune_scal.release(); h->cune_ctr.release(); h->cune_items.release();
     h->l2buf.release();
+    for (auto* b : {&h->gcn_ev_user, &h->gcn_ev_item, &h->gcn_neg, &h->gcn_heavy, &h->gcn_light, &h->gcn_slot_row, &h->gcn_slot_of}) b->release();
+    for (auto* b : {&h->gcn_E[0], &h->gcn_E[1], &h->gcn_E[2], &h->gcn_E[3], &h->gcn_rinv, &h->gcn_D[0], &h->gcn_D[1], &h->gcn_am, &h->gcn_av, &h->gcn_slot_grad, &h->gcn_NB, &h->gcn_trip_loss, &h->gcn_varP, &h->gcn_varQ}) b->release();
+    h->gcn_stamp.release(); h->gcn_loss.release();
     h->hot_base.release(); h->Qown.release(); h->Qsum.release();
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
@@ -545,6 +561,7 @@ static int finish_interactions(yue_t* h, const int64_t* ev_indptr, const int64_t
     h->have_ev_delta = false;
     h->have_ip = false;                                    // implicit positives belong to the log they were set for
     h->cune_chunk = -1;
+    h->gcn_events = false; h->gcn_planned = false; h->gcn_final = false;
     h->last_rank_B = 0;
     pt.lap("validate + host copies");
 
@@ -822,6 +839,7 @@ int yue_set_factors(yue_t* h, int k, const float* P, const float* Q) {
     CK(cudaMemcpy2DAsync(h->Q.p, ld * sizeof(float), Q, k * sizeof(float), k * sizeof(float), h->n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->have_factors = true;
+    h->gcn_t = 0; h->gcn_final = false;         // new variables: Adam starts over
     h->have_snap = false;
     h->exchange_pending = false;
     h->hot_shared = false;                     // new tables: the owners' rows no longer describe them
@@ -1295,6 +1313,210 @@ int yue_cune_epoch(yue_t* h, double lr, double regU, double regI, double s, uint
     return YUE_OK;
 }
 
+// ---- K9: LightGCN (lightgcn.cuh) --------------------------------------------------------------------------------------
+static int wrmf_prepare(yue_t* h);
+
+// the row lists of the product phases: a row with more than kGcnHeavy neighbours is worked on by a whole CTA
+static int gcn_plan(yue_t* h) {
+    if (h->gcn_planned) return YUE_OK;
+    if (int rc = wrmf_prepare(h)) return rc;           // play counts per pair and the track-major copy of the pairs
+    const int64_t m = h->m, n = h->n;
+    REQUIRE(m + n < ((int64_t)1 << 31), YUE_E_UNSUPPORTED, "more than 2^31 graph rows");
+    std::vector<int32_t> heavy, light;
+    for (int64_t r = 0; r < m + n; ++r) {
+        const int64_t deg = r < m ? h->h_uq_indptr[r + 1] - h->h_uq_indptr[r] : h->h_it_indptr[r - m + 1] - h->h_it_indptr[r - m];
+        if (deg > kGcnHeavy) heavy.push_back((int32_t)r); else light.push_back((int32_t)r);
+    }
+    // heaviest first: the CTAs that get two heavy rows get the smallest ones
+    std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t a, int32_t b) {
+        auto deg = [&](int64_t r) { return r < m ? h->h_uq_indptr[r + 1] - h->h_uq_indptr[r] : h->h_it_indptr[r - m + 1] - h->h_it_indptr[r - m]; };
+        return deg(a) > deg(b);
+    });
+    CK(h->gcn_heavy.resize(std::max<size_t>(heavy.size(), 1))); CK(h->gcn_light.resize(std::max<size_t>(light.size(), 1)));
+    if (!heavy.empty()) CK(cudaMemcpyAsync(h->gcn_heavy.p, heavy.data(), heavy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (!light.empty()) CK(cudaMemcpyAsync(h->gcn_light.p, light.data(), light.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->gcn_n_heavy = (int)heavy.size(); h->gcn_n_light = (int64_t)light.size();
+    h->gcn_planned = true;
+    return YUE_OK;
+}
+
+int yue_gcn_set_events(yue_t* h, int64_t T, const int32_t* ev_user, const int32_t* ev_item) {
+    REQUIRE(h && h->have_log, YUE_E_STATE, "call yue_set_interactions first");
+    REQUIRE(T == h->T && (T == 0 || (ev_user && ev_item)), YUE_E_ARG, "the events must be the resident log's training events (same number), in file order");
+    REQUIRE(h->user_begin == 0 && h->event_base == 0 && !h->have_ev_delta, YUE_E_UNSUPPORTED, "LightGCN needs the whole log on one handle");
+    CK(cudaSetDevice(h->device));
+    if (int rc = host_indptrs(h)) return rc;
+    std::vector<int64_t> per_user((size_t)h->m, 0);
+    for (int64_t e = 0; e < T; ++e) {
+        REQUIRE(ev_user[e] >= 0 && ev_user[e] < h->m && ev_item[e] >= 0 && ev_item[e] < h->n, YUE_E_ARG, "event " + std::to_string(e) + ": id out of range");
+        ++per_user[ev_user[e]];
+    }
+    for (int64_t u = 0; u < h->m; ++u)
+        REQUIRE(per_user[u] == h->h_ev_indptr[u + 1] - h->h_ev_indptr[u], YUE_E_ARG, "user " + std::to_string(u) + ": not the resident log's events");
+    CK(h->gcn_ev_user.resize((size_t)std::max<int64_t>(T, 1))); CK(h->gcn_ev_item.resize((size_t)std::max<int64_t>(T, 1)));
+    if (T) {
+        CK(cudaMemcpyAsync(h->gcn_ev_user.p, ev_user, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->gcn_ev_item.p, ev_item, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->gcn_events = true;
+    return YUE_OK;
+}
+
+// buffers for L layers and batches of up to `batch` triplets; the variables come back if yue_gcn_finalize replaced them
+static int gcn_buffers(yue_t* h, int L, int batch) {
+    const size_t M = (size_t)(h->m + h->n), ld = (size_t)h->ld, rows = std::max<size_t>(M * ld, 1);
+    cudaStream_t st = h->stream;
+    for (int k = 0; k < L; ++k) CK(h->gcn_E[k].resize(rows));
+    CK(h->gcn_rinv.resize(std::max<size_t>((size_t)L * M, 1)));
+    CK(h->gcn_D[0].resize(rows)); CK(h->gcn_D[1].resize(rows));
+    const bool fresh_adam = h->gcn_am.n < rows || h->gcn_av.n < rows || h->gcn_t == 0;
+    CK(h->gcn_am.resize(rows)); CK(h->gcn_av.resize(rows));
+    if (fresh_adam) {
+        CK(cudaMemsetAsync(h->gcn_am.p, 0, rows * sizeof(float), st)); CK(cudaMemsetAsync(h->gcn_av.p, 0, rows * sizeof(float), st));
+        h->gcn_t = 0;
+    }
+    if (h->gcn_stamp.n < M || h->gcn_stamp_base > 0xF0000000u) {
+        CK(h->gcn_stamp.resize(std::max<size_t>(M, 1))); CK(h->gcn_slot_of.resize(std::max<size_t>(M, 1)));
+        CK(cudaMemsetAsync(h->gcn_stamp.p, 0, std::max<size_t>(M, 1) * sizeof(uint32_t), st));
+        h->gcn_stamp_base = 0;
+    }
+    CK(h->gcn_slot_of.resize(std::max<size_t>(M, 1)));
+    const size_t slots = 3 * (size_t)batch;
+    CK(h->gcn_slot_row.resize(slots)); CK(h->gcn_slot_grad.resize(slots * ld)); CK(h->gcn_NB.resize((size_t)(L + 1) * slots * ld));
+    CK(h->gcn_trip_loss.resize((size_t)batch));
+    if (h->gcn_final) {                       // P, Q hold the propagated tables: the variables come back
+        CK(cudaMemcpyAsync(h->P.p, h->gcn_varP.p, (size_t)h->m * ld * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(h->Q.p, h->gcn_varQ.p, (size_t)h->n * ld * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        h->gcn_final = false;
+    }
+    return YUE_OK;
+}
+
+template <int G, int NC>
+static cudaError_t gcn_launch_as(yue_t* h, GcnParams& gp) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gcn_steps_kernel<G, NC>, kGcnThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    int ctas = std::min(per_sm, 2) * h->sm_count;
+    if (const char* s = getenv("YUE_GCN_CTAS")) ctas = std::max(1, std::min(per_sm * h->sm_count, atoi(s)));
+    void* args[] = {&gp};
+    return cudaLaunchCooperativeKernel((void*)gcn_steps_kernel<G, NC>, dim3((unsigned)ctas), dim3(kGcnThreads), args, 0, h->stream);
+}
+
+static int gcn_launch(yue_t* h, GcnParams& gp) {
+    gp.m = h->m; gp.n = h->n; gp.ld = h->ld;
+    gp.u_indptr = h->uq_indptr.p; gp.u_items = h->uq_items.p; gp.u_cnt = h->uq_cnt.p;
+    gp.t_indptr = h->it_indptr.p; gp.t_users = h->it_users.p; gp.t_cnt = h->it_cnt.p;
+    gp.P = h->P.p; gp.Q = h->Q.p;
+    for (int k = 0; k < gp.L; ++k) gp.E[k] = h->gcn_E[k].p;
+    gp.rinv = h->gcn_rinv.p; gp.D[0] = h->gcn_D[0].p; gp.D[1] = h->gcn_D[1].p; gp.am = h->gcn_am.p; gp.av = h->gcn_av.p;
+    gp.stamp = h->gcn_stamp.p; gp.slot_of = h->gcn_slot_of.p; gp.slot_row = h->gcn_slot_row.p; gp.slot_grad = h->gcn_slot_grad.p;
+    gp.NB = h->gcn_NB.p; gp.trip_loss = h->gcn_trip_loss.p; gp.loss_out = h->gcn_loss.p;
+    gp.heavy_rows = h->gcn_heavy.p; gp.n_heavy = h->gcn_n_heavy; gp.light_rows = h->gcn_light.p; gp.n_light = h->gcn_n_light;
+    gp.stamp_base = h->gcn_stamp_base; gp.adam_t = h->gcn_t;
+    if (h->ld <= 32) CK(gcn_launch_as<8, 1>(h, gp));
+    else if (h->ld <= 64) CK(gcn_launch_as<16, 1>(h, gp));
+    else if (h->ld <= 128) CK(gcn_launch_as<32, 1>(h, gp));
+    else CK(gcn_launch_as<32, 2>(h, gp));
+    ++h->launches;
+    return YUE_OK;
+}
+
+static int gcn_run_steps(yue_t* h, GcnParams& gp, double* loss_out) {
+    const int64_t steps = gp.step_end - gp.step_begin;
+    CK(h->gcn_loss.resize((size_t)std::max<int64_t>(steps, 1)));
+    if (int rc = gcn_launch(h, gp)) return rc;
+    h->gcn_stamp_base += (uint32_t)steps; h->gcn_t += steps;
+    h->ilv_current = false; h->tc.q_dirty = true;
+    std::vector<double> loss((size_t)steps);
+    CK(cudaMemcpyAsync(loss.data(), h->gcn_loss.p, steps * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    bool finite = true;
+    for (int64_t s = 0; s < steps; ++s) { if (loss_out) loss_out[s] = loss[s]; finite = finite && std::isfinite(loss[s]); }
+    if (!finite) return fail(h, YUE_E_NUMERIC, "Loss = NaN or Infinity: current settings does not fit the recommender!");
+    return YUE_OK;
+}
+
+static int gcn_check(yue_t* h, int n_layers, int64_t batch) {
+    REQUIRE(h && h->have_log && h->have_factors, YUE_E_STATE, "log and factors must be set");
+    REQUIRE(n_layers >= 1 && n_layers <= kGcnMaxLayers, YUE_E_UNSUPPORTED, "1..4 propagation layers");
+    REQUIRE(batch >= 1 && batch <= kGcnMaxBatch, YUE_E_UNSUPPORTED, "batch_size must be in 1..4096");
+    CK(cudaSetDevice(h->device));
+    if (int rc = q_rowmajor(h)) return rc;
+    if (int rc = gcn_plan(h)) return rc;
+    return YUE_OK;
+}
+
+int yue_gcn_epoch(yue_t* h, int n_layers, int batch_size, double lr, double reg, uint64_t seed, uint32_t epoch,
+                  int64_t step_begin, int64_t step_end, double* loss_out) {
+    if (int rc = gcn_check(h, n_layers, batch_size)) return rc;
+    REQUIRE(h->gcn_events, YUE_E_STATE, "call yue_gcn_set_events first (batches are slices of the log in file order)");
+    const int64_t n_steps = (h->T + batch_size - 1) / batch_size;
+    if (step_end < 0) step_end = n_steps;
+    REQUIRE(step_begin >= 0 && step_begin <= step_end && step_end <= n_steps, YUE_E_ARG, "step range outside the epoch");
+    if (step_begin == step_end) return YUE_OK;
+    if (int rc = gcn_buffers(h, n_layers, batch_size)) return rc;
+    GcnParams gp{};
+    gp.L = n_layers; gp.ev_user = h->gcn_ev_user.p; gp.ev_item = h->gcn_ev_item.p; gp.ev_neg = nullptr; gp.T = h->T; gp.batch = batch_size;
+    gp.step_begin = step_begin; gp.step_end = step_end; gp.seed = seed; gp.epoch = epoch; gp.lr = (float)lr; gp.reg = (float)reg;
+    return gcn_run_steps(h, gp, loss_out);
+}
+
+int yue_gcn_apply(yue_t* h, int n_layers, int64_t B, const int32_t* u, const int32_t* i, const int32_t* j,
+                  double lr, double reg, double* loss_out) {
+    if (int rc = gcn_check(h, n_layers, B)) return rc;
+    REQUIRE(u && i && j, YUE_E_ARG, "null argument");
+    for (int64_t b = 0; b < B; ++b)
+        REQUIRE(u[b] >= 0 && u[b] < h->m && i[b] >= 0 && i[b] < h->n && j[b] >= 0 && j[b] < h->n, YUE_E_ARG, "triplet " + std::to_string(b) + ": id out of range");
+    if (int rc = gcn_buffers(h, n_layers, (int)B)) return rc;
+    CK(h->tmp_i.resize((size_t)B)); CK(h->tmp_j.resize((size_t)B)); CK(h->gcn_neg.resize((size_t)B));
+    CK(cudaMemcpyAsync(h->tmp_i.p, u, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_j.p, i, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->gcn_neg.p, j, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    GcnParams gp{};
+    gp.L = n_layers; gp.ev_user = h->tmp_i.p; gp.ev_item = h->tmp_j.p; gp.ev_neg = h->gcn_neg.p; gp.T = B; gp.batch = (int)B;
+    gp.step_begin = 0; gp.step_end = 1; gp.lr = (float)lr; gp.reg = (float)reg;
+    return gcn_run_steps(h, gp, loss_out);
+}
+
+int yue_gcn_finalize(yue_t* h, int n_layers) {
+    if (int rc = gcn_check(h, n_layers, 1)) return rc;
+    if (h->gcn_final) return YUE_OK;
+    if (int rc = gcn_buffers(h, n_layers, 1)) return rc;
+    const size_t ld = (size_t)h->ld;
+    CK(h->gcn_varP.resize(std::max<size_t>((size_t)h->m * ld, 1))); CK(h->gcn_varQ.resize(std::max<size_t>((size_t)h->n * ld, 1)));
+    GcnParams gp{};
+    gp.L = n_layers; gp.forward_only = 1; gp.batch = 1;
+    gp.FP = h->gcn_varP.p; gp.FQ = h->gcn_varQ.p;
+    if (int rc = gcn_launch(h, gp)) return rc;
+    std::swap(h->P, h->gcn_varP); std::swap(h->Q, h->gcn_varQ);      // P, Q <- F; the variables wait in gcn_var*
+    h->gcn_final = true;
+    h->ilv_current = false; h->tc.q_dirty = true;
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
+int yue_gcn_moments(yue_t* h, float* m_users, float* m_tracks, float* v_users, float* v_tracks, int64_t* steps) {
+    REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
+    CK(cudaSetDevice(h->device));
+    const size_t k = (size_t)h->k, ld = (size_t)h->ld, M = (size_t)(h->m + h->n);
+    if (steps) *steps = h->gcn_t;
+    const bool have = h->gcn_t > 0 && h->gcn_am.n >= M * ld;
+    struct { float* dst; const float* src; int64_t rows; } parts[4] = {
+        {m_users, h->gcn_am.p, h->m}, {m_tracks, have ? h->gcn_am.p + (size_t)h->m * ld : nullptr, h->n},
+        {v_users, h->gcn_av.p, h->m}, {v_tracks, have ? h->gcn_av.p + (size_t)h->m * ld : nullptr, h->n}};
+    for (auto& x : parts) {
+        if (!x.dst || x.rows == 0) continue;
+        if (!have) { std::memset(x.dst, 0, (size_t)x.rows * k * sizeof(float)); continue; }
+        CK(cudaMemcpy2DAsync(x.dst, k * sizeof(float), x.src, ld * sizeof(float), k * sizeof(float), (size_t)x.rows, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return YUE_OK;
+}
+
 int yue_frob2(yue_t* h, double* p2, double* q2) {
     REQUIRE(h && h->have_factors, YUE_E_STATE, "factors not set");
     CK(cudaSetDevice(h->device));
@@ -1512,7 +1734,8 @@ static int wrmf_prepare(yue_t* h) {
     ingest_indptr_from_keys_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(k1.p, nnz, n, h->it_indptr.p);
     ++h->launches;
     CK(cudaGetLastError());
-    std::vector<int64_t> hit((size_t)n + 1);
+    std::vector<int64_t>& hit = h->h_it_indptr;
+    hit.assign((size_t)n + 1, 0);
     CK(cudaMemcpyAsync(hit.data(), h->it_indptr.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (int rc = host_indptrs(h)) return rc;

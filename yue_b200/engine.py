@@ -205,6 +205,45 @@ class Engine:
                                          int(mode), C.byref(loss)))
         return loss.value
 
+    # ---- LightGCN (K9, csrc/lightgcn.cuh) ----
+    def gcn_set_events(self, ev_user, ev_item):
+        """The training events in FILE order: LightGCN's batches are consecutive slices of them (LightGCN.py:56-66)."""
+        ev_user, ev_item = _as(ev_user, np.int32), _as(ev_item, np.int32)
+        if ev_user.shape != ev_item.shape or ev_user.ndim != 1:
+            raise ValueError("ev_user / ev_item must be equally long vectors")
+        self._ck(self.lib.yue_gcn_set_events(self.h, len(ev_user), _ptr(ev_user, C.c_int32), _ptr(ev_item, C.c_int32)))
+        self._gcn_T = len(ev_user)
+
+    def gcn_epoch(self, batch_size, lr, reg, seed, epoch, n_layers=3, step_begin=0, step_end=-1):
+        """Steps [step_begin, step_end) of one pass over the batches, in one launch; returns the per-step losses."""
+        n_steps = (self._gcn_T + int(batch_size) - 1) // int(batch_size)
+        end = n_steps if step_end < 0 else int(step_end)
+        loss = np.zeros(max(end - int(step_begin), 0), dtype=np.float64)
+        self._ck(self.lib.yue_gcn_epoch(self.h, int(n_layers), int(batch_size), float(lr), float(reg), int(seed), int(epoch),
+                                        int(step_begin), end, _ptr(loss, C.c_double)))
+        return loss
+
+    def gcn_apply(self, u, i, j, lr, reg, n_layers=3):
+        """One Adam step on the caller's triplets (parity hook); returns the batch loss."""
+        u, i, j = _as(u, np.int32), _as(i, np.int32), _as(j, np.int32)
+        loss = C.c_double(0.0)
+        self._ck(self.lib.yue_gcn_apply(self.h, int(n_layers), len(u), _ptr(u, C.c_int32), _ptr(i, C.c_int32), _ptr(j, C.c_int32),
+                                        float(lr), float(reg), C.byref(loss)))
+        return loss.value
+
+    def gcn_finalize(self, n_layers=3):
+        """P, Q <- the propagated tables predict() ranks with (LightGCN.py:45-47); the variables return on the next step."""
+        self._ck(self.lib.yue_gcn_finalize(self.h, int(n_layers)))
+
+    def gcn_moments(self):
+        """Adam's state: (m_users, m_tracks, v_users, v_tracks, steps taken since set_factors)."""
+        mu, vu = np.empty((self.m, self.k), np.float32), np.empty((self.m, self.k), np.float32)
+        mt, vt = np.empty((self.n, self.k), np.float32), np.empty((self.n, self.k), np.float32)
+        steps = C.c_int64(0)
+        self._ck(self.lib.yue_gcn_moments(self.h, _ptr(mu, C.c_float), _ptr(mt, C.c_float), _ptr(vu, C.c_float), _ptr(vt, C.c_float),
+                                          C.byref(steps)))
+        return mu, mt, vu, vt, steps.value
+
     def wrmf_sweep(self, side, reg, alpha=10.0, want_loss=False):
         """One WRMF half-sweep (0: every user row from the track table, 1: every track row from the user table)."""
         loss = C.c_double(0.0)
