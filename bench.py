@@ -683,11 +683,27 @@ def bench_lightgcn(eng, args):
             ms.append(eng.timer_stop())
         t = min(ms)
         nnz = int(log.uq_indptr[-1])
+        if name == "c1_shape":
+            c1 = (log, ev_user, perm, U, V)
         out[name] = {"users": log.m, "tracks": log.n, "train_events": log.train_size, "graph_edges": 2 * nnz, "steps": end,
                      "ms_per_pass": t, "us_per_step": 1e3 * t / end, "steps_per_sec": end / (t * 1e-3),
                      "gathered_GBps": 5 * 2 * nnz * 52 * 4 * end / (t * 1e-3) / 1e9,
                      "first_loss": float(losses[0]), "last_loss": float(losses[-1])}
     out["value"] = out["c1_shape"]["steps_per_sec"]
+    # the CPU restatement of the same step (float64 scipy CSR products + numpy Adam), on the last log built, a few steps
+    from oracle import lightgcn_ref as lg
+    log, ev_user, perm, U, V = c1
+    A = lg.adjacency(log.m, log.n, ev_user, log.ev_items)
+    E0 = np.concatenate([U, V]).astype(np.float64)
+    adam, neg = lg.Adam(E0.shape), rng.integers(0, log.n, 128)
+    t0, n_cpu = time.perf_counter(), 0
+    while n_cpu < 3 or time.perf_counter() - t0 < 5.0:
+        sl = slice(128 * n_cpu, 128 * n_cpu + 128)
+        _, g = lg.loss_and_grad(A, E0, log.m, ev_user[perm][sl], log.ev_items[perm][sl], neg, 0.001)
+        adam.step(E0, g, 0.002)
+        n_cpu += 1
+    out["cpu_baseline"] = {"value": n_cpu / (time.perf_counter() - t0), "unit": "steps/s", "cores": 1, "kind": "port",
+                           "sample": "%d steps on the c1_shape log (oracle/lightgcn_ref.py: scipy CSR products in float64, numpy Adam)" % n_cpu}
     out["note"] = ("gathered_GBps = 5 dense products per step x edges x 208-byte rows (the sixth product reads only the <= 384 rows the "
                    "batch touched); at C1's shape a step is bound by its 8 grid barriers, not by bandwidth")
     return out

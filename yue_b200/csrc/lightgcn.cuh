@@ -38,9 +38,17 @@ namespace cg = cooperative_groups;
 constexpr int kGcnMaxLayers = 4;
 constexpr int kGcnThreads = 512;
 constexpr int kGcnHeavy = 64;          // neighbours beyond which a CTA shares the row
+constexpr int kGcnSegRows = 8;         // light rows per segment (<= the smallest group), at most kGcnSegEdges neighbours together
+constexpr int kGcnSegEdges = 128;
+constexpr int kGcnHashSize = 8192;     // the stamped rows' hash table: >= 2 x kGcnSmemSlots, a power of two
+constexpr int kGcnSmemSlots = 3072;    // slot ids kept in shared memory by the combine phase (batches of up to 1024)
 constexpr int kGcnMaxBatch = 4096;
 constexpr uint32_t kGcnNegSlot = 4;    // the fifth draw is the one LightGCN.py:76-78 keeps
 constexpr float kGcnNormEps = 1e-12f;
+
+// a chunk of a heavy row's neighbours: [off, off + len) of row `row`; its partial sum goes to partial[slot]; the row's chunks
+// are partial[first_slot .. first_slot + n_chunks) and count themselves in at arrived[hidx]
+struct GcnChunk { int32_t row, off, len, slot, first_slot, n_chunks, hidx, pad; };
 
 struct GcnParams {
     int64_t m, n;                      // users, tracks; graph rows: users first, then tracks (M = m + n)
@@ -62,8 +70,11 @@ struct GcnParams {
     uint64_t seed; uint32_t epoch; uint32_t stamp_base;
     int64_t adam_t;                    // Adam steps taken before this launch
     float lr, reg;
-    const int32_t* heavy_rows; int n_heavy; const int32_t* light_rows; int64_t n_light;
+    const GcnChunk* chunks; int64_t n_chunk;   // heavy rows cut into chunks of neighbours
+    float* partial; unsigned* arrived;         // [n_chunk, ld] partial sums, [heavy rows] chunks that have arrived
+    const int2* segs; int64_t n_seg;           // light rows: (first row, rows) of up to kGcnSegRows consecutive rows of one side
     float* FP; float* FQ;              // forward_only: where F goes
+    unsigned long long* phase_ns;      // diagnostics (YUE_GCN_TIMING): [16] nanoseconds per phase, summed over the steps, by CTA 0
     int forward_only;
 };
 
@@ -142,10 +153,22 @@ template <int G, int NC> struct GcnDenseSrc {
     GcnTable t;
     __device__ __forceinline__ void fetch(int side, int32_t id, int gl, GcnVec<G, NC>& v) const { v.load(t.nbr_row(side, id), t.ld, gl); }
 };
+// NB_L on the rows the batch stamped.  The stamped rows (<= 3 B of up to a million) sit in a hash table in shared memory
+// that every CTA builds from the slot list at the start of the phase (row -> leading slot + 1, the row itself is slot_ids[slot]): a neighbour that is not in it
+// costs a shared-memory probe instead of a load from L2.  Batches beyond kGcnSmemSlots slots use the stamps in global memory.
+__device__ __forceinline__ uint32_t gcn_hash(int32_t r) { return ((uint32_t)r * 2654435761u) >> 19; }   // 13 bits
 template <int G, int NC> struct GcnStampedSrc {
     const uint32_t* stamp; const int32_t* slot_of; const float* nb; uint32_t cur; int ld; int64_t m;
+    const int* table; const int32_t* slot_ids;                      // shared memory; table == nullptr: use the stamps
     __device__ __forceinline__ void fetch(int side, int32_t id, int gl, GcnVec<G, NC>& v) const {
         const int64_t r = side == 0 ? m + id : id;
+        if (table) {
+            uint32_t hsh = gcn_hash((int32_t)r);
+            int e = table[hsh];
+            while (e != 0 && slot_ids[e - 1] != (int32_t)r) { hsh = (hsh + 1) & (kGcnHashSize - 1); e = table[hsh]; }
+            if (e != 0) v.load(nb + (int64_t)(e - 1) * ld, ld, gl); else v.zero();
+            return;
+        }
         if (__ldcg(stamp + r) == cur) v.load(nb + (int64_t)__ldcg(slot_of + r) * ld, ld, gl);
         else v.zero();
     }
@@ -154,95 +177,162 @@ template <int G, int NC> struct GcnStampedSrc {
 // neighbour rows in flight per group (registers: 4 NC floats each)
 template <int NC> struct GcnFlight { static constexpr int value = NC == 1 ? 8 : 4; };
 
-// acc += sum over neighbours [b, e) of w * src(neighbour),  w = count^2
-template <int G, int NC, class Src>
-__device__ __forceinline__ void gcn_gather(const GcnRowRange& rr, int64_t b, int64_t e, int gl, unsigned mask, const Src& src, GcnVec<G, NC>& acc) {
-    constexpr int kGcnFlight = GcnFlight<NC>::value;
-    for (int64_t p0 = b; p0 < e; p0 += G) {
-        int32_t id = 0; float w = 0.f;
-        if (p0 + gl < e) { id = __ldg(rr.nbr + p0 + gl); const float c = (float)__ldg(rr.cnt + p0 + gl); w = c * c; }
-        const int cnt = (int)((e - p0) < (int64_t)G ? (e - p0) : (int64_t)G);
-        for (int t = 0; t < cnt; t += kGcnFlight) {
-            GcnVec<G, NC> v[kGcnFlight]; float ww[kGcnFlight];
+// Walk the neighbours [eb, eb + n_edges) of `nr` consecutive rows (lane x holds where row x ends, relative to eb) with
+// GcnFlight rows in flight ACROSS row boundaries; the ids of the next G neighbours are fetched while the current ones are
+// worked on.  fin.begin(row) when a row starts, fin.finish(row, acc) when it is complete (rows without neighbours too).
+template <int G, int NC, class Src, class Fin>
+__device__ __forceinline__ void gcn_walk(const GcnRowRange& rr, int64_t eb, int n_edges, int nr, int my_end, int gl, unsigned mask,
+                                         const Src& src, Fin& fin) {
+    constexpr int FL = GcnFlight<NC>::value;
+    int row = 0, row_end = __shfl_sync(mask, my_end, 0, G);
+    GcnVec<G, NC> acc; acc.zero();
+    fin.begin(0);
+    auto finish_row = [&]() {
+        fin.finish(row, acc);
+        acc.zero(); ++row;
+        if (row < nr) { row_end = __shfl_sync(mask, my_end, row, G); fin.begin(row); }
+        else row_end = 0x7fffffff;
+    };
+    int32_t id_n = 0, cn_n = 0;
+    if (gl < n_edges) { id_n = __ldg(rr.nbr + eb + gl); cn_n = __ldg(rr.cnt + eb + gl); }
+    for (int p0 = 0; p0 < n_edges; p0 += G) {
+        const int32_t id = id_n; const float w = (float)cn_n * (float)cn_n;
+        id_n = 0; cn_n = 0;
+        if (p0 + G + gl < n_edges) { id_n = __ldg(rr.nbr + eb + p0 + G + gl); cn_n = __ldg(rr.cnt + eb + p0 + G + gl); }
+        const int cnt = n_edges - p0 < G ? n_edges - p0 : G;
+        for (int t = 0; t < cnt; t += FL) {
+            GcnVec<G, NC> v[FL]; float ww[FL];
 #pragma unroll
-            for (int x = 0; x < kGcnFlight; ++x) {
-                const int lane = (t + x) & (G - 1);                       // past the end: a lane whose weight is 0 (or id 0)
+            for (int x = 0; x < FL; ++x) {
+                const int lane = (t + x) & (G - 1);
                 const int32_t nid = __shfl_sync(mask, id, lane, G);
-                const float wv = __shfl_sync(mask, w, lane, G);
-                ww[x] = (t + x) < cnt ? wv : 0.f;
+                ww[x] = __shfl_sync(mask, w, lane, G);
                 if ((t + x) < cnt) src.fetch(rr.side, nid, gl, v[x]); else v[x].zero();
             }
 #pragma unroll
-            for (int x = 0; x < kGcnFlight; ++x) acc.axpy(ww[x], v[x]);
-        }
-    }
-}
-
-// one product phase: epi(row, acc) for every row of the graph
-template <int G, int NC, class Src, class Epi>
-__device__ __forceinline__ void gcn_product(const GcnParams& p, const Src& src, const Epi& epi, float* part) {
-    constexpr int NGRP = kGcnThreads / G, W = 4 * G * NC;
-    const int gl = threadIdx.x % G, grp = threadIdx.x / G;
-    const unsigned mask = gcn_group_mask<G>();
-    for (int hi = blockIdx.x; hi < p.n_heavy; hi += gridDim.x) {
-        const int64_t r = __ldg(p.heavy_rows + hi);
-        const GcnRowRange rr = gcn_row_range(p, r);
-        const int64_t per = ((rr.e - rr.b + NGRP - 1) / NGRP + 7) / 8 * 8;
-        const int64_t gb = rr.b + grp * per, ge = gb + per < rr.e ? gb + per : rr.e;
-        GcnVec<G, NC> acc; acc.zero();
-        if (gb < ge) gcn_gather<G, NC>(rr, gb, ge, gl, mask, src, acc);
-#pragma unroll
-        for (int q = 0; q < NC; ++q) *reinterpret_cast<float4*>(part + grp * W + 4 * (gl + G * q)) = acc.c[q];
-        __syncthreads();
-        if (grp == 0) {
-            for (int g2 = 1; g2 < NGRP; ++g2) {
-#pragma unroll
-                for (int q = 0; q < NC; ++q) {
-                    const float4 x = *reinterpret_cast<const float4*>(part + g2 * W + 4 * (gl + G * q));
-                    acc.c[q].x += x.x; acc.c[q].y += x.y; acc.c[q].z += x.z; acc.c[q].w += x.w;
+            for (int x = 0; x < FL; ++x) {
+                if ((t + x) < cnt) {
+                    while (p0 + t + x >= row_end) finish_row();
+                    acc.axpy(ww[x], v[x]);
                 }
             }
-            epi(r, acc, gl, mask);
         }
-        __syncthreads();
     }
-    const int64_t tot = (int64_t)gridDim.x * NGRP;
-    for (int64_t li = (int64_t)blockIdx.x * NGRP + grp; li < p.n_light; li += tot) {
-        const int64_t r = __ldg(p.light_rows + li);
-        const GcnRowRange rr = gcn_row_range(p, r);
-        GcnVec<G, NC> acc; acc.zero();
-        gcn_gather<G, NC>(rr, rr.b, rr.e, gl, mask, src, acc);
-        epi(r, acc, gl, mask);
+    while (row < nr) finish_row();
+}
+
+// One product phase: epi(row, acc) for every row of the graph.  Work items, dealt to the groups of the whole grid in turn:
+//  * CHUNKS of heavy rows (more than kGcnHeavy neighbours; a chunk is ~sqrt(degree), at least kGcnHeavy, neighbours): the
+//    group leaves its partial sum in scratch and counts itself in; the group that arrives LAST adds the row's partials up
+//    in chunk order (same bits on every run, whoever is last) and runs the row's epilogue.  No CTA waits for another.
+//  * SEGMENTS of up to kGcnSegRows consecutive light rows: their neighbour lists are one contiguous range of the CSR; a light
+//    row has ~2 neighbours, row by row each would cost its own chain of dependent latencies.
+template <int G, int NC, class Src, class Epi>
+__device__ __forceinline__ void gcn_product(const GcnParams& p, const Src& src, const Epi& epi, uint32_t cur) {
+    constexpr int NGRP = kGcnThreads / G, FL = GcnFlight<NC>::value;
+    const int gl = threadIdx.x % G, grp = threadIdx.x / G;
+    const unsigned mask = gcn_group_mask<G>();
+    const int64_t tot = (int64_t)gridDim.x * NGRP, n_items = p.n_chunk + p.n_seg;
+    for (int64_t it = (int64_t)blockIdx.x * NGRP + grp; it < n_items; it += tot) {
+        if (it < p.n_chunk) {
+            const GcnChunk ck = p.chunks[it];
+            const GcnRowRange rr = gcn_row_range(p, ck.row);
+            struct {
+                const GcnParams& p; const Epi& epi; const GcnChunk& ck; uint32_t cur; int gl; unsigned mask;
+                __device__ __forceinline__ void begin(int) {}
+                __device__ __forceinline__ void finish(int, GcnVec<G, NC>& acc) {
+                    const int ld = p.ld;
+                    acc.store(p.partial + (int64_t)ck.slot * ld, ld, gl);
+                    __threadfence();
+                    __syncwarp(mask);
+                    unsigned old = 0;
+                    if (gl == 0) old = atomicAdd(p.arrived + ck.hidx, 1u);
+                    old = __shfl_sync(mask, old, 0, G);
+                    if (old != (unsigned)ck.n_chunks - 1u) return;
+                    __threadfence();                                     // last to arrive: every partial of the row is visible
+                    typename Epi::Pre pre; epi.prefetch(ck.row, gl, pre);
+                    const bool stamped = Epi::kStamp && __ldcg(p.stamp + ck.row) == cur;
+                    acc.zero();
+                    for (int c0 = 0; c0 < ck.n_chunks; c0 += FL) {
+                        GcnVec<G, NC> v[FL];
+#pragma unroll
+                        for (int x = 0; x < FL; ++x) { if (c0 + x < ck.n_chunks) v[x].load(p.partial + (int64_t)(ck.first_slot + c0 + x) * ld, ld, gl); else v[x].zero(); }
+#pragma unroll
+                        for (int x = 0; x < FL; ++x) acc.add(v[x]);
+                    }
+                    epi(ck.row, acc, pre, stamped, gl, mask);
+                    if (gl == 0) p.arrived[ck.hidx] = 0u;                // the next phase counts from zero
+                }
+            } fin{p, epi, ck, cur, gl, mask};
+            gcn_walk<G, NC>(rr, rr.b + ck.off, ck.len, 1, ck.len, gl, mask, src, fin);
+        } else {
+            const int2 sg = __ldg(p.segs + (it - p.n_chunk));            // first row, rows (consecutive, one side)
+            const int64_t r0 = sg.x; const int nr = sg.y;
+            GcnRowRange rr;
+            const int64_t* ip;
+            if (r0 < p.m) { rr.nbr = p.u_items; rr.cnt = p.u_cnt; rr.side = 0; ip = p.u_indptr + r0; }
+            else { rr.nbr = p.t_users; rr.cnt = p.t_cnt; rr.side = 1; ip = p.t_indptr + (r0 - p.m); }
+            const int64_t eb = __ldg(ip);
+            const int my_end = gl < nr ? (int)(__ldg(ip + 1 + gl) - eb) : 0; // lane x: where row r0 + x ends, from eb
+            const uint32_t my_stamp = Epi::kStamp && gl < nr ? __ldcg(p.stamp + r0 + gl) : 0u;
+            const int n_edges = __shfl_sync(mask, my_end, nr - 1, G);
+            struct {
+                const Epi& epi; int64_t r0; uint32_t my_stamp, cur; int gl; unsigned mask; typename Epi::Pre pre;
+                __device__ __forceinline__ void begin(int row) { epi.prefetch(r0 + row, gl, pre); }
+                __device__ __forceinline__ void finish(int row, GcnVec<G, NC>& acc) {
+                    const bool stamped = Epi::kStamp && __shfl_sync(mask, my_stamp, row, G) == cur;
+                    epi(r0 + row, acc, pre, stamped, gl, mask);
+                }
+            } fin{epi, r0, my_stamp, cur, gl, mask, {}};
+            gcn_walk<G, NC>(rr, eb, n_edges, nr, my_end, gl, mask, src, fin);
+        }
     }
 }
 
 template <int G, int NC> struct GcnForwardEpi {
+    static constexpr bool kStamp = false;
+    struct Pre {};
     float* out; float* rinv; int ld;
-    __device__ __forceinline__ void operator()(int64_t r, GcnVec<G, NC>& acc, int gl, unsigned mask) const {
+    __device__ __forceinline__ void prefetch(int64_t, int, Pre&) const {}
+    __device__ __forceinline__ void operator()(int64_t r, GcnVec<G, NC>& acc, const Pre&, bool, int gl, unsigned mask) const {
         acc.store(out + r * ld, ld, gl);
         const float ss = gcn_group_sum<G>(acc.dot_part(acc), mask);
         if (gl == 0) rinv[r] = rsqrtf(fmaxf(ss, kGcnNormEps));
     }
 };
 
+// D_k = (product) + NB_k on stamped rows, k >= 1
 template <int G, int NC> struct GcnBackwardEpi {
-    const uint32_t* stamp; const int32_t* slot_of; const float* nb_k;    // NB_k (k = 0: the summed gradient itself)
-    uint32_t cur; int ld;
-    float* out;                                                           // D_k, or nullptr at k = 0
-    GcnTable var; float* am; float* av; float lr_t;                       // k = 0: Adam on the row of e_0
-    __device__ __forceinline__ void operator()(int64_t r, GcnVec<G, NC>& acc, int gl, unsigned) const {
-        if (__ldcg(stamp + r) == cur) {
+    static constexpr bool kStamp = true;
+    struct Pre {};
+    const int32_t* slot_of; const float* nb_k; int ld; float* out;
+    __device__ __forceinline__ void prefetch(int64_t, int, Pre&) const {}
+    __device__ __forceinline__ void operator()(int64_t r, GcnVec<G, NC>& acc, const Pre&, bool stamped, int gl, unsigned) const {
+        if (stamped) {
             GcnVec<G, NC> x; x.load(nb_k + (int64_t)__ldcg(slot_of + r) * ld, ld, gl);
             acc.add(x);
         }
-        if (out) { acc.store(out + r * ld, ld, gl); return; }
-        GcnVec<G, NC> mo, ve, va;
-        mo.load(am + r * ld, ld, gl); ve.load(av + r * ld, ld, gl);
-        float* vr = var.row(r);
-        va.load(vr, ld, gl);
+        acc.store(out + r * ld, ld, gl);
+    }
+};
+
+// k = 0: the gradient of the row of e_0 is complete in registers -- Adam's step on the row, D_0 is never stored
+template <int G, int NC> struct GcnAdamEpi {
+    static constexpr bool kStamp = true;
+    struct Pre { GcnVec<G, NC> mo, ve, va; };
+    const int32_t* slot_of; const float* nb_0; int ld;
+    GcnTable var; float* am; float* av; float lr_t;
+    __device__ __forceinline__ void prefetch(int64_t r, int gl, Pre& pre) const {
+        pre.mo.load(am + r * ld, ld, gl); pre.ve.load(av + r * ld, ld, gl); pre.va.load(var.row(r), ld, gl);
+    }
+    __device__ __forceinline__ void operator()(int64_t r, GcnVec<G, NC>& acc, Pre& pre, bool stamped, int gl, unsigned) const {
+        if (stamped) {
+            GcnVec<G, NC> x; x.load(nb_0 + (int64_t)__ldcg(slot_of + r) * ld, ld, gl);
+            acc.add(x);
+        }
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
-            float* g = &acc.c[q].x; float* mm = &mo.c[q].x; float* vv = &ve.c[q].x; float* xx = &va.c[q].x;
+            float* g = &acc.c[q].x; float* mm = &pre.mo.c[q].x; float* vv = &pre.ve.c[q].x; float* xx = &pre.va.c[q].x;
 #pragma unroll
             for (int z = 0; z < 4; ++z) {
                 mm[z] = 0.9f * mm[z] + 0.1f * g[z];
@@ -250,7 +340,7 @@ template <int G, int NC> struct GcnBackwardEpi {
                 xx[z] -= lr_t * mm[z] / (sqrtf(vv[z]) + 1e-8f);
             }
         }
-        mo.store(am + r * ld, ld, gl); ve.store(av + r * ld, ld, gl); va.store(vr, ld, gl);
+        pre.mo.store(am + r * ld, ld, gl); pre.ve.store(av + r * ld, ld, gl); pre.va.store(var.row(r), ld, gl);
     }
 };
 
@@ -265,10 +355,17 @@ __device__ __forceinline__ void gcn_final_row(const GcnParams& p, int64_t r, int
     }
 }
 
+__device__ __forceinline__ unsigned long long gcn_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// phase slots of GcnParams::phase_ns: 0..3 forward k, 4 batch, 5 combine, 6..9 backward k, then the same + 16 for the barrier after it
+#define GCN_TICK(slot)                                                                          \
+    if (p.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long t1_ = gcn_now(); p.phase_ns[slot] += t1_ - t_last; t_last = t1_; }
+
 template <int G, int NC>
 __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnParams p) {
+    unsigned long long t_last = p.phase_ns ? gcn_now() : 0ull;
     constexpr int NGRP = kGcnThreads / G;
-    __shared__ __align__(16) float part[NGRP * 4 * G * NC];
+    __shared__ int32_t slot_ids[kGcnSmemSlots];        // the batch's slot -> graph row
+    __shared__ int hash_tab[kGcnHashSize];             // stamped row -> its leading slot + 1 (0: empty), open addressing
     cg::grid_group grid = cg::this_grid();
     const int gl = threadIdx.x % G, grp = threadIdx.x / G;
     const unsigned mask = gcn_group_mask<G>();
@@ -281,8 +378,10 @@ __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnPara
         for (int k = 1; k <= p.L; ++k) {
             const GcnDenseSrc<G, NC> src{k == 1 ? gcn_table0(p) : gcn_table(p, p.E[k - 2])};
             const GcnForwardEpi<G, NC> epi{p.E[k - 1], p.rinv + (int64_t)(k - 1) * M, ld};
-            gcn_product<G, NC>(p, src, epi, part);
+            gcn_product<G, NC>(p, src, epi, 0u);
+            GCN_TICK(k - 1)
             grid.sync();
+            GCN_TICK(16 + k - 1)
         }
         if (p.forward_only) {
             for (int64_t r = ggrp; r < M; r += tot) {
@@ -325,18 +424,26 @@ __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnPara
                 p.trip_loss[b] = nll + 0.5f * p.reg * n2;
             }
         }
+        GCN_TICK(4)
         grid.sync();
+        GCN_TICK(20)
 
         // ---- combine: the first slot of a row sums the row's slots in slot order, norm-backward per layer, stamp ----
         const int ns = 3 * nb;
+        const bool ids_in_smem = ns <= kGcnSmemSlots;                 // the slots' rows: every leader test scans them
+        if (ids_in_smem) {
+            for (int x = threadIdx.x; x < ns; x += kGcnThreads) slot_ids[x] = __ldcg(p.slot_row + x);
+            __syncthreads();
+        }
+        auto slot_id = [&](int64_t x) { return ids_in_smem ? slot_ids[x] : __ldcg(p.slot_row + x); };
         for (int64_t sl = ggrp; sl < ns; sl += tot) {
-            const int32_t r = __ldcg(p.slot_row + sl);
+            const int32_t r = slot_id(sl);
             bool dup = false;
-            for (int64_t x = gl; x < sl; x += G) dup |= __ldcg(p.slot_row + x) == r;
+            for (int64_t x = gl; x < sl; x += G) dup |= slot_id(x) == r;
             if (!__any_sync(mask, dup)) {
                 GcnVec<G, NC> g; g.load(p.slot_grad + sl * ld, ld, gl);
                 for (int64_t x0 = sl + 1; x0 < ns; x0 += G) {
-                    const bool hit = x0 + gl < ns && __ldcg(p.slot_row + x0 + gl) == r;
+                    const bool hit = x0 + gl < ns && slot_id(x0 + gl) == r;
                     unsigned bal = (__ballot_sync(mask, hit) & mask) >> ((threadIdx.x & 31) & ~(G - 1));
                     while (bal) {
                         const int t = __ffs(bal) - 1; bal &= bal - 1;
@@ -365,22 +472,40 @@ __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnPara
                 if (gl == 0) p.loss_out[s] = a;
             }
         }
+        GCN_TICK(5)
         grid.sync();
+        GCN_TICK(21)
 
         // ---- backward: D_k = A D_{k+1} + NB_k, k = L-1 .. 0; k = 0 is the Adam step ----
         const double t_adam = (double)(p.adam_t + s + 1);
         const float lr_t = (float)((double)p.lr * sqrt(1.0 - pow(0.999, t_adam)) / (1.0 - pow(0.9, t_adam)));
         for (int k = p.L - 1; k >= 0; --k) {
-            GcnBackwardEpi<G, NC> epi{p.stamp, p.slot_of, p.NB + (int64_t)k * 3 * p.batch * ld, cur, ld,
-                                      k > 0 ? p.D[k & 1] : nullptr, gcn_table0(p), p.am, p.av, lr_t};
+            const float* nb_k = p.NB + (int64_t)k * 3 * p.batch * ld;
+            const GcnBackwardEpi<G, NC> epi{p.slot_of, nb_k, ld, p.D[k & 1]};
+            const GcnAdamEpi<G, NC> adam{p.slot_of, nb_k, ld, gcn_table0(p), p.am, p.av, lr_t};
             if (k == p.L - 1) {
-                const GcnStampedSrc<G, NC> src{p.stamp, p.slot_of, p.NB + (int64_t)p.L * 3 * p.batch * ld, cur, ld, p.m};
-                gcn_product<G, NC>(p, src, epi, part);
+                if (ids_in_smem) {                                   // stamped row -> leading slot, built by every CTA for itself
+                    for (int x = threadIdx.x; x < kGcnHashSize; x += kGcnThreads) hash_tab[x] = 0;
+                    __syncthreads();
+                    for (int x = threadIdx.x; x < ns; x += kGcnThreads) {
+                        const int32_t r = slot_ids[x];
+                        if (__ldcg(p.slot_of + r) == x) {
+                            uint32_t hsh = gcn_hash(r);
+                            while (atomicCAS(&hash_tab[hsh], 0, x + 1) != 0) hsh = (hsh + 1) & (kGcnHashSize - 1);
+                        }
+                    }
+                    __syncthreads();
+                }
+                const GcnStampedSrc<G, NC> src{p.stamp, p.slot_of, p.NB + (int64_t)p.L * 3 * p.batch * ld, cur, ld, p.m,
+                                               ids_in_smem ? hash_tab : nullptr, slot_ids};
+                if (k > 0) gcn_product<G, NC>(p, src, epi, cur); else gcn_product<G, NC>(p, src, adam, cur);
             } else {
                 const GcnDenseSrc<G, NC> src{gcn_table(p, p.D[(k + 1) & 1])};
-                gcn_product<G, NC>(p, src, epi, part);
+                if (k > 0) gcn_product<G, NC>(p, src, epi, cur); else gcn_product<G, NC>(p, src, adam, cur);
             }
+            GCN_TICK(6 + k)
             grid.sync();
+            GCN_TICK(22 + k)
         }
     }
 }

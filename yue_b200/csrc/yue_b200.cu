@@ -226,12 +226,16 @@ struct yue_handle {
     // LightGCN (K9): the training events in FILE order (batches are slices of it), row lists of the product phases, the
     // layers, the backward buffers, Adam's moments and the batch scratch
     bool gcn_events = false, gcn_planned = false, gcn_final = false;
-    DevBuf<int32_t> gcn_ev_user, gcn_ev_item, gcn_neg, gcn_heavy, gcn_light, gcn_slot_row, gcn_slot_of;
+    DevBuf<int32_t> gcn_ev_user, gcn_ev_item, gcn_neg, gcn_slot_row, gcn_slot_of;
+    DevBuf<int2> gcn_segs;
+    DevBuf<GcnChunk> gcn_chunks;
+    DevBuf<unsigned> gcn_arrived;
+    DevBuf<unsigned long long> gcn_phase_ns;
     DevBuf<uint32_t> gcn_stamp;
-    DevBuf<float> gcn_E[kGcnMaxLayers], gcn_rinv, gcn_D[2], gcn_am, gcn_av, gcn_slot_grad, gcn_NB, gcn_trip_loss, gcn_varP, gcn_varQ;
+    DevBuf<float> gcn_E[kGcnMaxLayers], gcn_rinv, gcn_D[2], gcn_am, gcn_av, gcn_slot_grad, gcn_NB, gcn_trip_loss, gcn_varP, gcn_varQ, gcn_partial;
     DevBuf<double> gcn_loss;
     std::vector<int64_t> h_it_indptr;
-    int gcn_n_heavy = 0; int64_t gcn_n_light = 0, gcn_t = 0;
+    int64_t gcn_n_chunk = 0, gcn_n_seg = 0, gcn_t = 0;
     uint32_t gcn_stamp_base = 0;
 
     ncclComm_t comm = nullptr;
@@ -451,8 +455,9 @@ int yue_destroy(yue_t* h) {
     h->scal.release();
     h->ip_indptr.release(); h->ip_items.release(); h->cune_scal.release(); h->cune_ctr.release(); h->cune_items.release();
     h->l2buf.release();
-    for (auto* b : {&h->gcn_ev_user, &h->gcn_ev_item, &h->gcn_neg, &h->gcn_heavy, &h->gcn_light, &h->gcn_slot_row, &h->gcn_slot_of}) b->release();
-    for (auto* b : {&h->gcn_E[0], &h->gcn_E[1], &h->gcn_E[2], &h->gcn_E[3], &h->gcn_rinv, &h->gcn_D[0], &h->gcn_D[1], &h->gcn_am, &h->gcn_av, &h->gcn_slot_grad, &h->gcn_NB, &h->gcn_trip_loss, &h->gcn_varP, &h->gcn_varQ}) b->release();
+    for (auto* b : {&h->gcn_ev_user, &h->gcn_ev_item, &h->gcn_neg, &h->gcn_slot_row, &h->gcn_slot_of}) b->release();
+    h->gcn_segs.release(); h->gcn_chunks.release(); h->gcn_arrived.release(); h->gcn_phase_ns.release();
+    for (auto* b : {&h->gcn_E[0], &h->gcn_E[1], &h->gcn_E[2], &h->gcn_E[3], &h->gcn_rinv, &h->gcn_D[0], &h->gcn_D[1], &h->gcn_am, &h->gcn_av, &h->gcn_slot_grad, &h->gcn_NB, &h->gcn_trip_loss, &h->gcn_varP, &h->gcn_varQ, &h->gcn_partial}) b->release();
     h->gcn_stamp.release(); h->gcn_loss.release();
     h->hot_base.release(); h->Qown.release(); h->Qsum.release();
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -1322,21 +1327,39 @@ static int gcn_plan(yue_t* h) {
     if (int rc = wrmf_prepare(h)) return rc;           // play counts per pair and the track-major copy of the pairs
     const int64_t m = h->m, n = h->n;
     REQUIRE(m + n < ((int64_t)1 << 31), YUE_E_UNSUPPORTED, "more than 2^31 graph rows");
-    std::vector<int32_t> heavy, light;
+    std::vector<int32_t> heavy;
+    std::vector<int2> segs;
+    auto deg = [&](int64_t r) { return r < m ? h->h_uq_indptr[r + 1] - h->h_uq_indptr[r] : h->h_it_indptr[r - m + 1] - h->h_it_indptr[r - m]; };
+    int64_t open_row = -1, open_edges = 0;                // the segment being filled: rows [open_row, r)
+    auto close = [&](int64_t r) { if (open_row >= 0) segs.push_back(make_int2((int)open_row, (int)(r - open_row))); open_row = -1; open_edges = 0; };
     for (int64_t r = 0; r < m + n; ++r) {
-        const int64_t deg = r < m ? h->h_uq_indptr[r + 1] - h->h_uq_indptr[r] : h->h_it_indptr[r - m + 1] - h->h_it_indptr[r - m];
-        if (deg > kGcnHeavy) heavy.push_back((int32_t)r); else light.push_back((int32_t)r);
+        const int64_t d = deg(r);
+        if (r == m) close(r);                              // a segment stays on one side of the graph
+        if (d > kGcnHeavy) { close(r); heavy.push_back((int32_t)r); continue; }
+        if (open_row >= 0 && (r - open_row >= kGcnSegRows || open_edges + d > kGcnSegEdges)) close(r);
+        if (open_row < 0) open_row = r;
+        open_edges += d;
     }
-    // heaviest first: the CTAs that get two heavy rows get the smallest ones
-    std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t a, int32_t b) {
-        auto deg = [&](int64_t r) { return r < m ? h->h_uq_indptr[r + 1] - h->h_uq_indptr[r] : h->h_it_indptr[r - m + 1] - h->h_it_indptr[r - m]; };
-        return deg(a) > deg(b);
-    });
-    CK(h->gcn_heavy.resize(std::max<size_t>(heavy.size(), 1))); CK(h->gcn_light.resize(std::max<size_t>(light.size(), 1)));
-    if (!heavy.empty()) CK(cudaMemcpyAsync(h->gcn_heavy.p, heavy.data(), heavy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    if (!light.empty()) CK(cudaMemcpyAsync(h->gcn_light.p, light.data(), light.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    close(m + n);
+    // heavy rows, heaviest first, cut into chunks of ~sqrt(degree) (>= kGcnHeavy) neighbours: the gather of a chunk and the
+    // sum of the row's partials by the last group to arrive then take about the same number of load rounds
+    std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
+    std::vector<GcnChunk> chunks;
+    for (size_t hi = 0; hi < heavy.size(); ++hi) {
+        const int64_t d = deg(heavy[hi]);
+        int64_t c = (int64_t)std::ceil(std::sqrt((double)d) / 8.0) * 8;
+        c = std::max<int64_t>(c, kGcnHeavy);
+        const int nck = (int)((d + c - 1) / c), first = (int)chunks.size();
+        for (int q = 0; q < nck; ++q)
+            chunks.push_back(GcnChunk{heavy[hi], (int32_t)(q * c), (int32_t)std::min<int64_t>(c, d - q * c), first + q, first, nck, (int32_t)hi, 0});
+    }
+    CK(h->gcn_chunks.resize(std::max<size_t>(chunks.size(), 1))); CK(h->gcn_segs.resize(std::max<size_t>(segs.size(), 1)));
+    CK(h->gcn_arrived.resize(std::max<size_t>(heavy.size(), 1)));
+    CK(cudaMemsetAsync(h->gcn_arrived.p, 0, std::max<size_t>(heavy.size(), 1) * sizeof(unsigned), h->stream));
+    if (!chunks.empty()) CK(cudaMemcpyAsync(h->gcn_chunks.p, chunks.data(), chunks.size() * sizeof(GcnChunk), cudaMemcpyHostToDevice, h->stream));
+    if (!segs.empty()) CK(cudaMemcpyAsync(h->gcn_segs.p, segs.data(), segs.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->gcn_n_heavy = (int)heavy.size(); h->gcn_n_light = (int64_t)light.size();
+    h->gcn_n_chunk = (int64_t)chunks.size(); h->gcn_n_seg = (int64_t)segs.size();
     h->gcn_planned = true;
     return YUE_OK;
 }
@@ -1371,6 +1394,7 @@ static int gcn_buffers(yue_t* h, int L, int batch) {
     for (int k = 0; k < L; ++k) CK(h->gcn_E[k].resize(rows));
     CK(h->gcn_rinv.resize(std::max<size_t>((size_t)L * M, 1)));
     CK(h->gcn_D[0].resize(rows)); CK(h->gcn_D[1].resize(rows));
+    CK(h->gcn_partial.resize(std::max<size_t>((size_t)h->gcn_n_chunk * ld, 1)));
     const bool fresh_adam = h->gcn_am.n < rows || h->gcn_av.n < rows || h->gcn_t == 0;
     CK(h->gcn_am.resize(rows)); CK(h->gcn_av.resize(rows));
     if (fresh_adam) {
@@ -1415,13 +1439,26 @@ static int gcn_launch(yue_t* h, GcnParams& gp) {
     gp.rinv = h->gcn_rinv.p; gp.D[0] = h->gcn_D[0].p; gp.D[1] = h->gcn_D[1].p; gp.am = h->gcn_am.p; gp.av = h->gcn_av.p;
     gp.stamp = h->gcn_stamp.p; gp.slot_of = h->gcn_slot_of.p; gp.slot_row = h->gcn_slot_row.p; gp.slot_grad = h->gcn_slot_grad.p;
     gp.NB = h->gcn_NB.p; gp.trip_loss = h->gcn_trip_loss.p; gp.loss_out = h->gcn_loss.p;
-    gp.heavy_rows = h->gcn_heavy.p; gp.n_heavy = h->gcn_n_heavy; gp.light_rows = h->gcn_light.p; gp.n_light = h->gcn_n_light;
+    gp.chunks = h->gcn_chunks.p; gp.n_chunk = h->gcn_n_chunk; gp.partial = h->gcn_partial.p; gp.arrived = h->gcn_arrived.p;
+    gp.segs = h->gcn_segs.p; gp.n_seg = h->gcn_n_seg;
     gp.stamp_base = h->gcn_stamp_base; gp.adam_t = h->gcn_t;
+    const bool timing = getenv("YUE_GCN_TIMING") != nullptr;
+    if (timing) { CK(h->gcn_phase_ns.resize(32)); CK(cudaMemsetAsync(h->gcn_phase_ns.p, 0, 32 * sizeof(unsigned long long), h->stream)); gp.phase_ns = h->gcn_phase_ns.p; }
     if (h->ld <= 32) CK(gcn_launch_as<8, 1>(h, gp));
     else if (h->ld <= 64) CK(gcn_launch_as<16, 1>(h, gp));
     else if (h->ld <= 128) CK(gcn_launch_as<32, 1>(h, gp));
     else CK(gcn_launch_as<32, 2>(h, gp));
     ++h->launches;
+    if (timing) {
+        unsigned long long ns[32];
+        CK(cudaMemcpyAsync(ns, h->gcn_phase_ns.p, sizeof(ns), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const double steps = (double)std::max<int64_t>(1, gp.step_end - gp.step_begin);
+        fprintf(stderr, "[yue gcn timing] us per step, work / barrier after it (CTA 0):");
+        const char* names[10] = {"fwd1", "fwd2", "fwd3", "fwd4", "batch", "combine", "bwd0+adam", "bwd1", "bwd2", "bwd3"};
+        for (int i = 0; i < 10; ++i) if (ns[i] || ns[16 + i]) fprintf(stderr, "  %s %.1f/%.1f", names[i], ns[i] / steps * 1e-3, ns[16 + i] / steps * 1e-3);
+        fprintf(stderr, "\n");
+    }
     return YUE_OK;
 }
 
