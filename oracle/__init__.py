@@ -21,7 +21,11 @@ What it restates (file:line relative to the reference tree):
 * ``recommender/cf/WRMF.py:17-88``      implicit-feedback ALS (``wrmf_ref.py``; pinned by the reference CLASS itself,
                                         ``make_golden_wrmf.py`` -> ``tests/golden/wrmf_small.npz``)
 * ``recommender/advanced/CUNE.py:118-178``  two-level BPR training loop (``cune_ref.py``; pinned by the reference's loop
-                                        text, ``make_golden_cune.py``; the CUDA kernel for it is not built yet)
+                                        text, ``make_golden_cune.py``)
+
+* ``recommender/advanced/LightGCN.py:15-105``  LightGCN's graph, loss, Adam loop (``lightgcn_ref.py``; PARITY UNPINNED: the module
+                                        cannot be imported -- TF-1 and ``base/DeepRecommender`` without ``.py`` -- so the restatement is
+                                        checked against its own numerical gradient only)
 
 Parity pinning.  The reference ships no tests, golden vectors or data, and its
 RNG streams (CPython Mersenne Twister, unseeded) cannot be reproduced by a GPU

@@ -39,7 +39,7 @@ constexpr int kGcnMaxLayers = 4;
 constexpr int kGcnThreads = 512;
 constexpr int kGcnHeavy = 64;          // neighbours beyond which a CTA shares the row
 constexpr int kGcnSegRows = 8;         // light rows per segment (<= the smallest group), at most kGcnSegEdges neighbours together
-constexpr int kGcnSegEdges = 128;
+constexpr int kGcnSegEdges = 64;
 constexpr int kGcnHashSize = 8192;     // the stamped rows' hash table: >= 2 x kGcnSmemSlots, a power of two
 constexpr int kGcnSmemSlots = 3072;    // slot ids kept in shared memory by the combine phase (batches of up to 1024)
 constexpr int kGcnMaxBatch = 4096;

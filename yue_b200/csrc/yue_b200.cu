@@ -1341,6 +1341,12 @@ static int gcn_plan(yue_t* h) {
         open_edges += d;
     }
     close(m + n);
+    // largest first: the groups take items in turn, so every group's share ends with the small ones
+    auto seg_edges = [&](const int2& sg) {
+        const int64_t r0 = sg.x, r1 = sg.x + sg.y;
+        return r0 < m ? h->h_uq_indptr[r1] - h->h_uq_indptr[r0] : h->h_it_indptr[r1 - m] - h->h_it_indptr[r0 - m];
+    };
+    std::stable_sort(segs.begin(), segs.end(), [&](const int2& a, const int2& b) { return seg_edges(a) > seg_edges(b); });
     // heavy rows, heaviest first, cut into chunks of ~sqrt(degree) (>= kGcnHeavy) neighbours: the gather of a chunk and the
     // sum of the row's partials by the last group to arrive then take about the same number of load rounds
     std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t a, int32_t b) { return deg(a) > deg(b); });
