@@ -52,6 +52,97 @@ def test_truncated_normal_init_and_class_config(tmp_path):
     assert x.dtype == np.float32 and np.abs(x).max() <= 0.01 + 1e-9 and 0.004 < x.std() < 0.0048
 
 
+def test_class_trains_on_the_training_split_in_file_order(golden_dir, tmp_path):
+    """Under -byTime (config/LightGCN.conf) Record keeps the UNSPLIT log in trainingData (data/record.py:37 before 47-48):
+    the class takes the entries of the training split, in the file's order, and reads batch_size like DeepRecommender."""
+    import io
+    import json
+    import os
+    from contextlib import redirect_stdout
+    from yue_b200.host.config import Config
+    from yue_b200.lightgcn import LightGCN
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    train = [e for e, h in zip(g["events"], g["held"]) if not h]
+    test = [e for e, h in zip(g["events"], g["held"]) if h]
+    vals = {"record": "./dataset/log.txt", "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,",
+            "recommender": "LightGCN", "evaluation.setup": "-target track -byTime 0.2", "item.ranking": "-topN 5,10",
+            "num.factors": "50", "num.max.iter": "3", "batch_size": "128", "learnRate": "-init 0.002 -max 1",
+            "reg.lambda": "-u 0.001 -i 0.001 -b 0.2 -s 0.2", "output.setup": "on -dir %s/" % tmp_path}
+    with redirect_stdout(io.StringIO()):
+        rec = LightGCN(Config(values=vals), train, test)
+        rec.readConfiguration()
+        rec.initModel()
+    assert rec.batch_size == 128 and rec.U.shape == (rec.m, 50) and np.abs(rec.U).max() <= 0.01
+    eu, ei = rec._file_order_events()
+    n_train = sum(len(v) for v in rec.data.userRecord.values())
+    assert len(rec.data.trainingData) > n_train == len(eu) == len(ei)
+    uid, tid = rec.data.name2id['user'], rec.data.name2id['track']
+    kept = set(id(e) for evs in rec.data.userRecord.values() for e in evs)
+    want = [(uid[e['user']], tid[e['track']]) for e in rec.data.trainingData if id(e) in kept]
+    assert list(zip(eu.tolist(), ei.tolist())) == want
+    with redirect_stdout(io.StringIO()):
+        vals["evaluation.setup"] = "-target track -ap 0.2"
+        rec2 = LightGCN(Config(values=vals), train, test)
+        rec2.readConfiguration()
+        rec2.initModel()
+    eu2, _ = rec2._file_order_events()
+    assert len(eu2) == len(train) and eu2.tolist() == [rec2.data.name2id['user'][e['user']] for e in train]
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_dropin_shim_on_top_of_the_reference_tree(golden_dir, tmp_path):
+    """dropin/recommender/advanced/LightGCN.py shadows the reference's module (TF-1, unimportable base), derives from the
+    REFERENCE's own base.IterativeRecommender and Record (under -byTime: the reference's own time split), and drives the
+    engine with the calls INTEGRATION.md lists -- checked with a recording engine in place of the CUDA one."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    conf = {"record": "./dataset/log.txt", "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,",
+            "recommender": "LightGCN", "evaluation.setup": "-target track -byTime 0.2", "item.ranking": "-topN 5,10",
+            "num.factors": "50", "num.max.iter": "2", "batch_size": "128", "learnRate": "-init 0.002 -max 1",
+            "reg.lambda": "-u 0.001 -i 0.001 -b 0.2 -s 0.2", "output.setup": "on -dir %s/" % tmp_path, "yue.seed": "11"}
+    code = r'''
+import io, json, sys
+import numpy as np
+from contextlib import redirect_stdout
+sys.path[:0] = [%(dropin)r, "/root/reference", %(root)r]
+from tool.config import Config
+from recommender.advanced.LightGCN import LightGCN
+import base.IterativeRecommender as ref_base
+import recommender.advanced.LightGCN as mod
+assert mod.__file__.startswith(%(dropin)r) and LightGCN.__mro__[3] is ref_base.IterativeRecommender, LightGCN.__mro__
+g = json.load(open(%(gold)r + "/record_small.json"))
+events = g["events"]
+open(%(tmp)r + "/c.conf", "w").write("\n".join(k + "=" + v for k, v in %(conf)r.items()))
+calls = []
+class Rec(object):
+    def set_factors(self, U, V): calls.append(("set_factors", U.shape, V.shape, float(np.abs(U).max())))
+    def gcn_set_events(self, eu, ei): calls.append(("events", len(eu))); self.T = len(eu)
+    def gcn_epoch(self, batch, lr, reg, seed, it, L): calls.append(("epoch", batch, lr, reg, seed, it, L)); return np.arange(3.0) + it
+    def get_factors(self): return np.zeros((2, 50), np.float32), np.ones((3, 50), np.float32)
+    def gcn_finalize(self, L): calls.append(("finalize", L))
+with redirect_stdout(io.StringIO()) as out:
+    m = LightGCN(Config(%(tmp)r + "/c.conf"), events, [])
+    m.readConfiguration()
+    m.initModel()
+    eng = Rec()
+    m._get_engine = lambda: eng
+    m._engine = eng
+    m.buildModel()
+n_train = sum(len(v) for v in m.data.userRecord.values())
+assert 0 < n_train < len(events) and m.data.testSet                      # the reference's own -byTime split
+assert calls[0][0] == "set_factors" and calls[0][1] == (m.m, 50) and calls[0][3] <= 0.01
+assert calls[1] == ("events", n_train)
+assert calls[2] == ("epoch", 128, 0.002, 0.001, 11, 0, 3) and calls[3] == ("epoch", 128, 0.002, 0.001, 11, 1, 3)
+assert calls[4] == ("finalize", 3) and m.loss == 3.0
+assert m.multi_item_embeddings.shape == (3, 50) and "training: 2 batch 2 loss: 3.0" in out.getvalue()
+print("shim ok")
+''' % dict(dropin=os.path.join(root, "dropin"), root=root, gold=golden_dir, tmp=str(tmp_path), conf=conf)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "shim ok" in res.stdout, res.stdout + res.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("d", [8, 50, 100, 130])
 def test_one_step_gradient_loss_and_update_match_the_oracle(engine, d):
