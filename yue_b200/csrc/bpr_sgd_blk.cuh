@@ -395,6 +395,16 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
                             if (lo < p.n_hot && hot_sorted[lo] == n_j) n_j = -hot_sorted_slot[lo] - 1;
                         }
                     }
+                    if (p.pf_stride > 0 && lane < n_len) {
+                        // Q beyond the L2 (config C3: 1 GB): the segment's 64 rows start their way from DRAM now, 1..8 blocks
+                        // before the register loads that use them (those are issued one block ahead only)
+                        const char* ri = reinterpret_cast<const char*>(p.Q) + (size_t)(n_i < 0 ? 0 : n_i) * row_bytes;
+                        const char* rj = reinterpret_cast<const char*>(p.Q) + (size_t)(n_j < 0 ? 0 : n_j) * row_bytes;
+                        for (uint32_t o = 0; o < row_bytes; o += (uint32_t)p.pf_stride) {
+                            if (n_i >= 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(ri + o));
+                            if (n_j >= 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(rj + o));
+                        }
+                    }
                     __syncwarp();
                     if (n_u != cur_u) ldrow(p.P + (size_t)n_u * p.ld + lane_off, pun);
                     // the segment after: its record arrived a segment ago -> prefetch its data, fetch the next record
