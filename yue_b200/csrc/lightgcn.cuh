@@ -228,12 +228,24 @@ __device__ __forceinline__ void gcn_walk(const GcnRowRange& rr, int64_t eb, int 
 //  * SEGMENTS of up to kGcnSegRows consecutive light rows: their neighbour lists are one contiguous range of the CSR; a light
 //    row has ~2 neighbours, row by row each would cost its own chain of dependent latencies.
 template <int G, int NC, class Src, class Epi>
-__device__ __forceinline__ void gcn_product(const GcnParams& p, const Src& src, const Epi& epi, uint32_t cur) {
+__device__ __forceinline__ void gcn_product(const GcnParams& p, const Src& src, const Epi& epi, uint32_t cur, int* cta_next) {
     constexpr int NGRP = kGcnThreads / G, FL = GcnFlight<NC>::value;
     const int gl = threadIdx.x % G, grp = threadIdx.x / G;
     const unsigned mask = gcn_group_mask<G>();
-    const int64_t tot = (int64_t)gridDim.x * NGRP, n_items = p.n_chunk + p.n_seg;
-    for (int64_t it = (int64_t)blockIdx.x * NGRP + grp; it < n_items; it += tot) {
+    // Items (largest first) are dealt to the CTAs in runs of NGRP consecutive items -- neighbouring groups work on neighbouring
+    // rows, and every CTA gets about the same work -- and inside a CTA a group that is done takes the CTA's next one (a counter
+    // in shared memory; a single global ticket counter was tried: 12 K same-address atomics per phase cost more than the
+    // imbalance they removed).
+    const int64_t n_items = p.n_chunk + p.n_seg, tot = (int64_t)gridDim.x * NGRP;
+    if (threadIdx.x == 0) *cta_next = NGRP;
+    __syncthreads();
+    auto item_of = [&](int k) { return (int64_t)(k / NGRP) * tot + (int64_t)blockIdx.x * NGRP + (k % NGRP); };
+    auto take = [&]() -> int64_t {
+        int t = 0;
+        if (gl == 0) t = atomicAdd(cta_next, 1);
+        return item_of(__shfl_sync(mask, t, 0, G));
+    };
+    for (int64_t it = item_of(grp); it < n_items; it = take()) {
         if (it < p.n_chunk) {
             const GcnChunk ck = p.chunks[it];
             const GcnRowRange rr = gcn_row_range(p, ck.row);
@@ -365,6 +377,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnPara
     unsigned long long t_last = p.phase_ns ? gcn_now() : 0ull;
     constexpr int NGRP = kGcnThreads / G;
     __shared__ int32_t slot_ids[kGcnSmemSlots];        // the batch's slot -> graph row
+    __shared__ int cta_next;                           // product phases: the CTA's next unclaimed item
     __shared__ int hash_tab[kGcnHashSize];             // stamped row -> its leading slot + 1 (0: empty), open addressing
     cg::grid_group grid = cg::this_grid();
     const int gl = threadIdx.x % G, grp = threadIdx.x / G;
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnPara
         for (int k = 1; k <= p.L; ++k) {
             const GcnDenseSrc<G, NC> src{k == 1 ? gcn_table0(p) : gcn_table(p, p.E[k - 2])};
             const GcnForwardEpi<G, NC> epi{p.E[k - 1], p.rinv + (int64_t)(k - 1) * M, ld};
-            gcn_product<G, NC>(p, src, epi, 0u);
+            gcn_product<G, NC>(p, src, epi, 0u, &cta_next);
             GCN_TICK(k - 1)
             grid.sync();
             GCN_TICK(16 + k - 1)
@@ -480,6 +493,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnPara
         const double t_adam = (double)(p.adam_t + s + 1);
         const float lr_t = (float)((double)p.lr * sqrt(1.0 - pow(0.999, t_adam)) / (1.0 - pow(0.9, t_adam)));
         for (int k = p.L - 1; k >= 0; --k) {
+            const unsigned long long t_adam0 = p.phase_ns && k == 0 ? gcn_now() : 0ull;
             const float* nb_k = p.NB + (int64_t)k * 3 * p.batch * ld;
             const GcnBackwardEpi<G, NC> epi{p.slot_of, nb_k, ld, p.D[k & 1]};
             const GcnAdamEpi<G, NC> adam{p.slot_of, nb_k, ld, gcn_table0(p), p.am, p.av, lr_t};
@@ -498,12 +512,13 @@ __global__ void __launch_bounds__(kGcnThreads, 1) gcn_steps_kernel(const GcnPara
                 }
                 const GcnStampedSrc<G, NC> src{p.stamp, p.slot_of, p.NB + (int64_t)p.L * 3 * p.batch * ld, cur, ld, p.m,
                                                ids_in_smem ? hash_tab : nullptr, slot_ids};
-                if (k > 0) gcn_product<G, NC>(p, src, epi, cur); else gcn_product<G, NC>(p, src, adam, cur);
+                if (k > 0) gcn_product<G, NC>(p, src, epi, cur, &cta_next); else gcn_product<G, NC>(p, src, adam, cur, &cta_next);
             } else {
                 const GcnDenseSrc<G, NC> src{gcn_table(p, p.D[(k + 1) & 1])};
-                if (k > 0) gcn_product<G, NC>(p, src, epi, cur); else gcn_product<G, NC>(p, src, adam, cur);
+                if (k > 0) gcn_product<G, NC>(p, src, epi, cur, &cta_next); else gcn_product<G, NC>(p, src, adam, cur, &cta_next);
             }
             GCN_TICK(6 + k)
+            if (p.phase_ns && k == 0 && threadIdx.x == 0) p.phase_ns[32 + blockIdx.x] += gcn_now() - t_adam0;   // per CTA: its Adam phase
             grid.sync();
             GCN_TICK(22 + k)
         }

@@ -1454,7 +1454,7 @@ static int gcn_launch(yue_t* h, GcnParams& gp) {
     gp.segs = h->gcn_segs.p; gp.n_seg = h->gcn_n_seg;
     gp.stamp_base = h->gcn_stamp_base; gp.adam_t = h->gcn_t;
     const bool timing = getenv("YUE_GCN_TIMING") != nullptr;
-    if (timing) { CK(h->gcn_phase_ns.resize(32)); CK(cudaMemsetAsync(h->gcn_phase_ns.p, 0, 32 * sizeof(unsigned long long), h->stream)); gp.phase_ns = h->gcn_phase_ns.p; }
+    if (timing) { CK(h->gcn_phase_ns.resize(32 + 1024)); CK(cudaMemsetAsync(h->gcn_phase_ns.p, 0, (32 + 1024) * sizeof(unsigned long long), h->stream)); gp.phase_ns = h->gcn_phase_ns.p; }
     if (h->ld <= 32) CK(gcn_launch_as<8, 1>(h, gp));
     else if (h->ld <= 64) CK(gcn_launch_as<16, 1>(h, gp));
     else if (h->ld <= 128) CK(gcn_launch_as<32, 1>(h, gp));
@@ -1468,6 +1468,11 @@ static int gcn_launch(yue_t* h, GcnParams& gp) {
         fprintf(stderr, "[yue gcn timing] us per step, work / barrier after it (CTA 0):");
         const char* names[10] = {"fwd1", "fwd2", "fwd3", "fwd4", "batch", "combine", "bwd0+adam", "bwd1", "bwd2", "bwd3"};
         for (int i = 0; i < 10; ++i) if (ns[i] || ns[16 + i]) fprintf(stderr, "  %s %.1f/%.1f", names[i], ns[i] / steps * 1e-3, ns[16 + i] / steps * 1e-3);
+        fprintf(stderr, "\n");
+        std::vector<unsigned long long> per((size_t)1024);
+        CK(cudaMemcpy(per.data(), h->gcn_phase_ns.p + 32, 1024 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[yue gcn timing] Adam phase, us per step by CTA:");
+        for (int c = 0; c < h->sm_count; ++c) fprintf(stderr, " %.0f", per[c] / steps * 1e-3);
         fprintf(stderr, "\n");
     }
     return YUE_OK;
