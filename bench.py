@@ -92,14 +92,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, None
 
     def start(self):
+        """Started BEFORE the warm-up steps: nvidia-smi needs a few hundred ms to deliver its first line, more than a short
+        timed region lasts (10 epochs of config C2 are 130 ms); mark() is called where the timed region begins."""
         if os.environ.get("YUE_BENCH_NO_CLOCKS"):
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("YUE_BENCH_CLOCKS_MS", "100")],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("YUE_BENCH_CLOCKS_MS", "50")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -108,16 +110,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def wait_ready(self, timeout=2.0):
+        """Block until nvidia-smi has delivered its first line (call BEFORE the barrier that precedes the timed region)."""
+        t0 = time.monotonic()
+        while self.proc and not self.rows and time.monotonic() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        self.t_mark = time.monotonic()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.monotonic()
         time.sleep(0.15)
         self.proc.terminate()
         self.thread.join(timeout=2)
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        timed = [r for t, r in self.rows if t0 <= t <= t_end + 0.06]      # a line describes the ~50 ms before it arrived
+        window = "timed region"
+        if not timed:                                                     # region shorter than a sampling period
+            timed, window = [r for _, r in self.rows], "warm-up + timed region (the timed region is shorter than a sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in timed:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -126,7 +143,7 @@ class ClockSampler:
             except (ValueError, IndexError):
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -297,12 +314,14 @@ def run_native(args):
         return eng.bpr_epoch(LR, REG_U, REG_I, SEED, epoch, mode, want_loss=want_loss)
 
     # ---- value: K steps, inputs resident in HBM ---------------------------------------------
-    for w in range(args.warmup):
-        step(w)
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    clocks.wait_ready()
+    for w in range(args.warmup):
+        step(w)
+    barrier()
+    clocks.mark()
     l0 = eng.launch_count()
     eng.timer_start()
     for k in range(args.steps):
