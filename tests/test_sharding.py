@@ -192,9 +192,11 @@ def test_select_hot_tracks_rule_and_order():
     assert total == int(c.sum())
     assert tracks.tolist() == [7, 5, 9] and counts.tolist() == [90000, 50000, 50000]      # most played first, ties by id
     assert sharding.select_hot_tracks(c, hot_max=2)[0].tolist() == [7, 5]
-    # a track must also carry more than 1/128 of ALL events
+    # a track must also carry more than 1/hot_div of ALL events: 1/128 is the one-GPU rule, 1/4096 the sharded trainer's default
     c2 = c.copy(); c2[100:600] = 30000
-    assert sharding.select_hot_tracks(c2)[0].tolist() == []
+    assert sharding.select_hot_tracks(c2, hot_div=128)[0].tolist() == []
+    wide = sharding.select_hot_tracks(c2)[0]
+    assert len(wide) == 248 and wide[:3].tolist() == [7, 5, 9] and set(wide[3:].tolist()) <= set(range(100, 600))
 
 
 class _FakeEngine:

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--no-serial", default="")
     ap.add_argument("--reserve-sms", type=int, default=8)
     ap.add_argument("--kappa", default="none", help="comma list: none = plain sum of the tail deltas, else the per-touch contraction of saturation_weights")
+    ap.add_argument("--hot", default="248:4096", help="comma list of hot_max:hot_div -- the shared table holds up to hot_max tracks that are the positive of more than 1/hot_div of the events")
     ap.add_argument("--hogwild-1gpu", action="store_true", help="rank 0 also trains the plain one-GPU Hogwild epochs")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -66,8 +67,10 @@ def main():
     ctl = sharding.TorchCtl(dist, dev if world > 1 else None)
     rf = quality.torch_reduce_factory(dist, dev) if world > 1 else None
     for S in (int(x) for x in args.sub_epochs.split(",")):
-        for A, K in [(float(x), None if k == "none" else float(k)) for x in args.asynchrony.split(",") for k in args.kappa.split(",")]:
-            run = quality.verdict(quality.shared_hot_run(local, ctl, log, P, Q, spec, S, A, reduce_factory=rf, reserve_sms=args.reserve_sms, kappa=K), br, bn)
+        for A, K, HM, HD in [(float(x), None if k == "none" else float(k), int(hh.split(":")[0]), int(hh.split(":")[1]))
+                             for x in args.asynchrony.split(",") for k in args.kappa.split(",") for hh in args.hot.split(",")]:
+            run = quality.verdict(quality.shared_hot_run(local, ctl, log, P, Q, spec, S, A, reduce_factory=rf, reserve_sms=args.reserve_sms, kappa=K,
+                                                         hot_max=HM, hot_div=HD), br, bn)
             say("kappa %s: " % K + "%d rank(s), %2d parts/epoch, asynchrony %.2f (%d warps on %d CTAs per rank, %d hot rows = %.0f %% of the events): "
                 "recall@10 %.4f (%+.4f) ndcg@10 %.4f (%+.4f) %s  loss %.1f  %.2f s = %.3e triplets/s"
                 % (world, S, A, run["warps_per_rank"], run["ctas_per_rank"], run["hot_tracks"], 100 * run["hot_share_of_events"],

@@ -42,7 +42,7 @@ class GpuBPRMixin(object):
     #:   yue.devices=0,1,...   several CUDA devices, driven by threads of this process: evalRanking ranks a block of the test
     #:                         users on each; buildModel (Hogwild, num.factors 32/64/128) shards the users over them with the
     #:                         hot rows shared over peer memory (yue_b200/sharding.py: SharedHotTrainer).  The first one is
-    #:                         the device everything else runs on.  yue.sub_epochs (32 up to 2 devices, 4 N^2 above) / yue.asynchrony (1.0) tune it.
+    #:                         the device everything else runs on.  yue.sub_epochs (32 up to 2 devices, 4 N^2 above) / yue.asynchrony (0.25) tune it.
     #:   yue.metrics=host|device  where evalRanking computes Precision/Recall/F1/MAP/Coverage (default host:
     #:                         the reference's own summation order; device = one kernel over the lists that are
     #:                         already on the GPU, for test sets where the Python set operations dominate)
@@ -161,7 +161,7 @@ class GpuBPRMixin(object):
             ev_indptr, ev_items, uq_indptr, uq_items = eng.get_interactions()
             P, Q = getattr(self, self._user_table), getattr(self, self._item_table)
             shared = sharding.ThreadCtl.Shared(world)
-            S, A = int(self._opt('yue.sub_epochs', 0)), float(self._opt('yue.asynchrony', 1.0))   # 0: sharding.default_sub_epochs
+            S, A = int(self._opt('yue.sub_epochs', 0)), float(self._opt('yue.asynchrony', 0))   # 0: sharding.default_sub_epochs / default_asynchrony
 
             def start(r, ctl):
                 mine = sharding.interleaved_users(self.m, world, r)

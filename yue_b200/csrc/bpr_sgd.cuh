@@ -117,6 +117,7 @@ struct SgdParams {
     const int32_t* hot_sorted_slot;
     const int32_t* hot_dx;         // [n_hot] byte distance from a slot's row to its second accumulator row, 0 = none
     int resync_mask;               // resync when (block & resync_mask) == 0: resync_events / 4 - 1, a power of two - 1
+    int hot_plane;                 // blocked kernel: floats between two sectors of a hot row (hot_plane_floats(rows of the table))
     int pf_stride;                 // blocked kernel: > 0 = the rows of a segment's triplets are prefetched into L2 when its negatives are
                                    // drawn (one prefetch per pf_stride bytes of a row); for tables that do not fit in L2 (config C3)
     // multi-GPU (yue_hot_share): hot slot s lives in the table of rank s % nranks; [n_hot] address of that table (this

@@ -178,27 +178,31 @@ struct BlkRows {
 // The most played tracks of all additionally get a SECOND accumulator row in the table (the logical
 // row is the sum of both; a warp adds to row warp % 2, readers fetch both): one 32-byte address takes
 // a dependent load + atomic every ~2.2 ns, which for the top track of C2 is still 8.6 ms per epoch.
-constexpr int kHotSlots = 24;                                 // hot tracks
+constexpr int kHotSlots = 248;                                // hot tracks: one GPU uses ~10 (tracks above 1/128 of the events); the sharded
+                                                              // trainer shares up to all of them between the ranks (tracks above 1/4096)
 constexpr int kHotExtra = 8;                                  // of which so many may have a second row
 constexpr int kHotRows = kHotSlots + kHotExtra;
-constexpr int kHotPlaneFloats = (2 * kHotRows + 1) * 64;      // 65 granules of 256 B (measured: tools/red_probe3.cu)
+// floats between two sectors of a row ("plane"): 2 x rows + 1 granules of 256 B.  65 granules for tables of up to 32 rows (the
+// stride measured in tools/red_probe3.cu, on which the one-GPU numbers rest), 513 for larger ones.
+constexpr int kHotPlaneSmall = (2 * 32 + 1) * 64, kHotPlaneBig = (2 * kHotRows + 1) * 64;
+__host__ __device__ __forceinline__ int hot_plane_floats(int rows) { return rows <= 32 ? kHotPlaneSmall : kHotPlaneBig; }
 __host__ __device__ __forceinline__ size_t hot_slot_offset(int row) {       // floats; row = slot, or n_hot + k for an extra row
     return (size_t)(((row >> 1) << 2) | (row & 1)) * 64;
 }
 // float offset, inside a slot's row, of the V floats lane `lane` owns
-template <int V> __host__ __device__ __forceinline__ size_t hot_lane_offset(int lane) {
-    return (size_t)((V * lane) >> 3) * kHotPlaneFloats + ((V * lane) & 7);
+template <int V> __host__ __device__ __forceinline__ size_t hot_lane_offset(int lane, int plane) {
+    return (size_t)((V * lane) >> 3) * plane + ((V * lane) & 7);
 }
-constexpr size_t kHotTableFloats = (size_t)16 * kHotPlaneFloats;           // up to 16 sectors (ld = 128)
+constexpr size_t kHotTableFloats = (size_t)16 * kHotPlaneBig;              // up to 16 sectors (ld = 128)
 constexpr int kHotCandidates = 8;        // placements of the table the first launch on a log times (yue_b200.cu)
 constexpr int kHotCandidateStep = 11;    // granules between them
 
 template <int V>
 __global__ void hot_gather_kernel(const float* __restrict__ Q, float* __restrict__ hotQ, const int32_t* __restrict__ hot_items,
-                                  const int32_t* __restrict__ hot_dx, int n_hot, int ld) {
+                                  const int32_t* __restrict__ hot_dx, int n_hot, int ld, int plane) {
     const int lane = threadIdx.x & 31;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
-        float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane);
+        float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane, plane);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             row[v] = V * lane + v < ld ? Q[(size_t)hot_items[s] * ld + V * lane + v] : 0.f;
@@ -208,10 +212,10 @@ __global__ void hot_gather_kernel(const float* __restrict__ Q, float* __restrict
 }
 template <int V>
 __global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restrict__ hotQ, const int32_t* __restrict__ hot_items,
-                                   const int32_t* __restrict__ hot_dx, int n_hot, int ld) {
+                                   const int32_t* __restrict__ hot_dx, int n_hot, int ld, int plane) {
     const int lane = threadIdx.x & 31;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
-        const float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane);
+        const float* row = hotQ + hot_slot_offset(s) + hot_lane_offset<V>(lane, plane);
 #pragma unroll
         for (int v = 0; v < V; ++v)
             if (V * lane + v < ld) Q[(size_t)hot_items[s] * ld + V * lane + v] = row[v] + (hot_dx[s] ? row[hot_dx[s] / 4 + v] : 0.f);
@@ -223,11 +227,11 @@ __global__ void hot_scatter_kernel(float* __restrict__ Q, const float* __restric
 template <int V>
 __global__ void hot_gather_shared_kernel(const float* __restrict__ Q, const unsigned long long* __restrict__ hot_base,
                                          const int32_t* __restrict__ hot_items, const int32_t* __restrict__ hot_dx, int n_hot, int ld,
-                                         int nranks, int rank) {
+                                         int nranks, int rank, int plane) {
     const int lane = threadIdx.x & 31;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
         if (s % nranks != rank) continue;
-        float* row = reinterpret_cast<float*>(hot_base[s]) + hot_slot_offset(s) + hot_lane_offset<V>(lane);
+        float* row = reinterpret_cast<float*>(hot_base[s]) + hot_slot_offset(s) + hot_lane_offset<V>(lane, plane);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             row[v] = Q[(size_t)hot_items[s] * ld + V * lane + v];
@@ -238,10 +242,10 @@ __global__ void hot_gather_shared_kernel(const float* __restrict__ Q, const unsi
 // pull: every hot row (the sum of its accumulator rows) from its owner's table into this rank's Q
 template <int V>
 __global__ void hot_pull_shared_kernel(float* __restrict__ Q, const unsigned long long* __restrict__ hot_base,
-                                       const int32_t* __restrict__ hot_items, const int32_t* __restrict__ hot_dx, int n_hot, int ld) {
+                                       const int32_t* __restrict__ hot_items, const int32_t* __restrict__ hot_dx, int n_hot, int ld, int plane) {
     const int lane = threadIdx.x & 31;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_hot; s += (gridDim.x * blockDim.x) >> 5) {
-        const float* row = reinterpret_cast<const float*>(hot_base[s]) + hot_slot_offset(s) + hot_lane_offset<V>(lane);
+        const float* row = reinterpret_cast<const float*>(hot_base[s]) + hot_slot_offset(s) + hot_lane_offset<V>(lane, plane);
         float a[V], b[V];
         ldv_sys<V>(row, a);
         if (hot_dx[s]) ldv_sys<V>(row + hot_dx[s] / 4, b);
@@ -293,8 +297,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) bpr_sgd_blk_kernel(const SgdPa
     const float cu1 = 1.f - p.c_u;
     // per-lane base addresses; a row is then base + (32-bit byte offset), see q_ptr
     char* const q_lane = reinterpret_cast<char*>(p.Q + lane_off);
-    char* const hot_lane = reinterpret_cast<char*>(p.hotQ + hot_lane_offset<V>(lane));
-    const uint32_t hot_lane_bytes = (uint32_t)(hot_lane_offset<V>(lane) * sizeof(float));
+    char* const hot_lane = reinterpret_cast<char*>(p.hotQ + hot_lane_offset<V>(lane, p.hot_plane));
+    const uint32_t hot_lane_bytes = (uint32_t)(hot_lane_offset<V>(lane, p.hot_plane) * sizeof(float));
     const uint32_t row_bytes = (uint32_t)p.ld * 4u;          // n * ld * 4 < 4 GB is checked by the host
 
     float pu[V], pu0[V], pun[V];

@@ -117,7 +117,7 @@ struct yue_handle {
     // Hot tracks (see SgdParams): a track is hot when it is the positive of >= hot_min_count events AND of
     // more than 1/hot_div of all events; it gets min(cap, pow2ceil(share * hot_div)) accumulator shards, so
     // the chain of dependent atomics on one address stays below ~T/hot_div updates (~11 ns each).
-    int hot_max = kHotSlots;
+    int hot_max = 24;                 // one GPU: the table relieves L2 slices, a few rows do (YUE_SGD_HOT_MAX, up to kHotSlots)
     int hot_min_count = 16384;
     // Where the hot-row table starts inside its allocation, in 256-byte granules.  Which L2 slices the table's
     // sectors share with each other and with the rest of the working set depends on physical addresses the
@@ -954,10 +954,10 @@ static cudaError_t launch_sgd_blk(const SgdParams& sp, int warps_per_cta, cudaSt
         bpr_sgd_blk_kernel<V, APR, false, true><<<grid, warps_per_cta * 32, smem, st>>>(sp);
         return cudaGetLastError();
     }
-    if (sp.n_hot > 0) { hot_gather_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
+    if (sp.n_hot > 0) { hot_gather_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld, sp.hot_plane); ++launches; }
     if (mask) bpr_sgd_blk_kernel<V, APR, true><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
     else bpr_sgd_blk_kernel<V, APR, false><<<grid, warps_per_cta * 32, (size_t)sp.n_hot * 12, st>>>(sp);
-    if (sp.n_hot > 0) { hot_scatter_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld); ++launches; }
+    if (sp.n_hot > 0) { hot_scatter_kernel<V><<<(sp.n_hot + 7) / 8, 256, 0, st>>>(sp.Q, sp.hotQ, sp.hot_items, sp.hot_dx, sp.n_hot, sp.ld, sp.hot_plane); ++launches; }
     return cudaGetLastError();
 }
 
@@ -1032,6 +1032,7 @@ static int calibrate_hot_offset(yue_t* h, SgdParams sp, int wpc) {
 static int run_sgd(yue_t* h, SgdParams sp, int mode, double* loss_out, bool apr = false) {
     REQUIRE(mode >= YUE_MODE_SERIAL && mode <= YUE_MODE_HOGWILD_STORE, YUE_E_ARG, "unknown mode");
     sp.cursor = h->cursor.p;
+    sp.hot_plane = hot_plane_floats(sp.n_hot + kHotExtra);       // every rank of a shared table has the same n_hot
     const bool blk = use_blk_kernel(h, mode, apr);
     { int rb = 1; while (rb * 2 * kBlkK <= sp.resync_events) rb *= 2; sp.resync_mask = rb - 1; }
     // YUE_SGD_L2_PREFETCH = stride in bytes (experiments): prefetch a segment's rows into L2 when its negatives are drawn.  Off:
@@ -2077,12 +2078,13 @@ int yue_enable_peer(yue_t* h, int peer_device) {
 template <int V>
 static cudaError_t launch_hot_gather_shared(yue_t* h) {
     hot_gather_shared_kernel<V><<<(h->n_hot + 7) / 8, 256, 0, h->stream>>>(h->Q.p, h->hot_base.p, h->hot_items.p, h->hot_dx.p, h->n_hot, h->ld,
-                                                                           h->hot_nranks, h->hot_rank);
+                                                                           h->hot_nranks, h->hot_rank, hot_plane_floats(h->n_hot + kHotExtra));
     return cudaGetLastError();
 }
 template <int V>
 static cudaError_t launch_hot_pull_shared(yue_t* h) {
-    hot_pull_shared_kernel<V><<<(h->n_hot + 7) / 8, 256, 0, h->stream>>>(h->Q.p, h->hot_base.p, h->hot_items.p, h->hot_dx.p, h->n_hot, h->ld);
+    hot_pull_shared_kernel<V><<<(h->n_hot + 7) / 8, 256, 0, h->stream>>>(h->Q.p, h->hot_base.p, h->hot_items.p, h->hot_dx.p, h->n_hot, h->ld,
+                                                                         hot_plane_floats(h->n_hot + kHotExtra));
     return cudaGetLastError();
 }
 

@@ -344,7 +344,7 @@ class Engine:
     # shared hot rows + overlapped exchange of the tail (include/yue_b200.h, "multi-GPU, round 2")
     def hot_tracks(self):
         n = C.c_int(0)
-        out = np.empty(64, dtype=np.int32)
+        out = np.empty(1024, dtype=np.int32)                   # kHotSlots = 248
         self._ck(self.lib.yue_hot_tracks(self.h, _ptr(out, C.c_int32), C.byref(n)))
         return out[:n.value].copy()
 

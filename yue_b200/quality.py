@@ -50,11 +50,14 @@ def single_gpu_run(device, log, P, Q, spec, mode):
     return r / max(cnt, 1), n / max(cnt, 1), dt, loss
 
 
-def shared_hot_run(device, ctl, log, P, Q, spec, sub_epochs, asynchrony, reduce_factory=None, reserve_sms=8, apr=None, kappa=None):
+def shared_hot_run(device, ctl, log, P, Q, spec, sub_epochs, asynchrony, reduce_factory=None, reserve_sms=8, apr=None, kappa=None,
+                   hot_max=248, hot_div=4096):
     """This rank's part of one run of SharedHotTrainer on `log` (every rank holds the same log and initial tables and keeps
     the users rank, rank + world, ...).  kappa: None = plain sum of the tail deltas, else sharding.saturation_weights with
     that per-touch contraction.  Returns a dict on every rank (metric sums are all-reduced through ctl)."""
     rank, world = ctl.rank, ctl.world
+    sub_epochs = int(sub_epochs) if sub_epochs else sharding.default_sub_epochs(world)       # 0 / None: the trainer's defaults
+    asynchrony = float(asynchrony) if asynchrony else sharding.default_asynchrony(world)
     mine = sharding.interleaved_users(log.m, world, rank)
     sh = sharding.local_shard_of_users(log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items, mine)
     te = sharding.local_shard_of_users(log.test_indptr, log.test_items, log.test_indptr, log.test_items, mine)
@@ -69,7 +72,7 @@ def shared_hot_run(device, ctl, log, P, Q, spec, sub_epochs, asynchrony, reduce_
         if kappa is not None and world > 1:
             w = sharding.saturation_weights(np.bincount(log.ev_items, minlength=log.n), world, sub_epochs, kappa)
         tr = sharding.SharedHotTrainer(eng, ctl, local_counts, sub_epochs=sub_epochs, asynchrony=asynchrony, reduce=reduce,
-                                       reserve_sms=reserve_sms, row_weights=w)
+                                       reserve_sms=reserve_sms, row_weights=w, hot_max=hot_max, hot_div=hot_div)
         eng.sync()
         ctl.barrier()
         t0 = time.perf_counter()

@@ -185,9 +185,12 @@ class WrmfShardedTrainer:
 
 
 # ---- round 2: hot rows as ONE copy over peer memory, the tail exchanged under the next sub-epoch ---------------------------
-def select_hot_tracks(global_counts, hot_max=24, hot_div=128, min_count=16384):
-    """The hot set every rank must agree on (same rule as yue_set_interactions applies to one GPU's log): tracks that are
-    the positive of more than 1/hot_div of ALL events and of at least min_count, most played first (ties: lower id)."""
+def select_hot_tracks(global_counts, hot_max=248, hot_div=4096, min_count=16384):
+    """The hot set every rank must agree on: tracks that are the positive of more than 1/hot_div of ALL events and of at least
+    min_count, most played first (ties: lower id).  One GPU keeps ~10 rows in its table (hot_max 24, hot_div 128: the rows whose
+    L2 slice would saturate); the ranks of a sharded model share MANY more -- every row in the table exists once and is exact,
+    every other row is a replica that is reconciled only at the exchanges: at config C2's size 239 shared rows (47 % of the
+    positives) are what brings Recall@10 from -0.026 to inside the gate (profiles/r2/quality_c2_n2_hot.log)."""
     c = np.asarray(global_counts, dtype=np.int64)
     total = int(c.sum())
     cand = np.nonzero((c >= min_count) & (c * hot_div > total))[0]
@@ -276,6 +279,14 @@ def default_sub_epochs(world):
     return 32 if world <= 2 else 4 * world * world
 
 
+def default_asynchrony(world):
+    """All ranks together run `asynchrony` x the warps one GPU would give the whole log.  A row shared over NVLink has its
+    updates in flight ~4x longer than a local one, so the same bound on updates in flight allows a
+    quarter of the warps: at config C2's size 2 GPUs leave the gate at 1.0 and 0.5 (Recall@10 -0.011 / -0.010) and are inside
+    at 0.25 and 0.125 (-0.0012 / -0.0005; profiles/r2/quality_c2_n2_async.log)."""
+    return 1.0 if int(world) <= 1 else 0.25
+
+
 class SharedHotTrainer:
     """One rank of the round-2 trainer (include/yue_b200.h "multi-GPU, round 2").
 
@@ -295,14 +306,16 @@ class SharedHotTrainer:
     torch.distributed), or None = chosen here: ranks that are handles of ONE process sum each other's deltas over peer
     memory (yue_q_exchange_reduce_peers), ranks in different processes use the library's NCCL communicator."""
 
-    def __init__(self, engine, ctl, local_counts, sub_epochs=None, asynchrony=1.0, reserve_sms=8, reduce=None, row_weights=None,
-                 hot_max=24, sm_count=148, warps_per_sm=12, min_events_per_warp=16384):
+    def __init__(self, engine, ctl, local_counts, sub_epochs=None, asynchrony=None, reserve_sms=8, reduce=None, row_weights=None,
+                 hot_max=248, hot_div=4096, sm_count=148, warps_per_sm=12, min_events_per_warp=16384):
         import os
         from . import engine as _eng
         self.eng, self.ctl = engine, ctl
         self.sub_epochs = int(sub_epochs) if sub_epochs else default_sub_epochs(ctl.world)
+        asynchrony = float(asynchrony) if asynchrony else default_asynchrony(ctl.world)
+        self.asynchrony = asynchrony
         counts = ctl.allreduce_sum(np.asarray(local_counts, dtype=np.int64))
-        tracks, tcounts, total = select_hot_tracks(counts, hot_max=hot_max)
+        tracks, tcounts, total = select_hot_tracks(counts, hot_max=hot_max, hot_div=hot_div)
         self.hot_tracks, self.total_events = tracks, total
         self.hot_share_of_events = float(tcounts.sum()) / max(total, 1)
         engine.set_hot_tracks(tracks, tcounts, total)
