@@ -216,6 +216,31 @@ def test_steps_with_the_fused_sampler_follow_the_oracle_and_finalize_gives_the_r
 
 
 @pytest.mark.gpu
+def test_whole_pass_with_a_partial_last_batch_and_two_layers(engine):
+    """ceil(T / batch) steps, the last one shorter; n_layers = 2; rows without any neighbour (tracks nobody played) in the graph."""
+    log = synth.power_law_log(120, 400, 1500, seed=47)
+    eu, ei = file_order(log, 5)
+    assert len(eu) % 128 != 0 and (np.bincount(ei, minlength=log.n) == 0).sum() > 50
+    engine.set_interactions(log.m, log.n, log.ev_indptr, log.ev_items, log.uq_indptr, log.uq_items)
+    U, V = lg.init_tables(log.m, log.n, 20, 13)
+    U, V = U * 10, V * 10
+    engine.set_factors(U, V)
+    engine.gcn_set_events(eu, ei)
+    A = lg.adjacency(log.m, log.n, eu, ei)
+    rU, rV, rloss, _ = lg.train(A, U, V, eu, ei, log.uq_indptr, log.uq_items, 128, 0.002, 0.001, 77, epochs=1, n_layers=2)
+    loss = engine.gcn_epoch(128, 0.002, 0.001, 77, 0, n_layers=2)
+    assert len(loss) == len(rloss) == (len(eu) + 127) // 128
+    assert np.allclose(loss, rloss, rtol=5e-4)
+    P, Q = engine.get_factors()
+    got, ref, start = np.concatenate([P, Q]).astype(np.float64), np.concatenate([rU, rV]), np.concatenate([U, V]).astype(np.float64)
+    assert (np.abs(got - ref) <= 0.02 * np.abs(ref - start) + 1e-9).mean() >= 0.995
+    engine.gcn_finalize(2)
+    FU, FV = engine.get_factors()
+    wU, wV = lg.embeddings(A, P, Q, n_layers=2)
+    assert np.abs(np.concatenate([FU, FV]) - np.concatenate([wU, wV])).max() <= 1e-5 * np.abs(np.concatenate([wU, wV])).max()
+
+
+@pytest.mark.gpu
 def test_refusals(engine):
     from yue_b200.engine import YueError
     log = synth.power_law_log(50, 60, 600, seed=3)
