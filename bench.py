@@ -441,7 +441,7 @@ def run_native(args):
         nnz = int(len(wlog.uq_items))
         wrmf = {"metric": "wrmf_iterations_per_sec", "value": 1e3 / min(wts[1:]), "ms_per_iteration": min(wts[1:]), "n_gpus": world, "scaling": "strong",
                 "unique_pairs": nnz, "pairs_per_sec": 2 * nnz / (min(wts[1:]) * 1e-3),
-                "parallelism": "every rank holds the log and both tables, solves a range of rows balanced by entries and broadcasts it (NCCL); "
+                "parallelism": "every rank holds the log and both tables, solves a range of rows balanced by cost (sharding.shard_rows_by_cost: entries plus the factorisation every row pays) and broadcasts it (NCCL); "
                                "no reduction: bit-identical to one GPU",
                 "workload": "WRMF d=64, reg 1, alpha 10 on ONE C2 log (%d users x %d tracks, %d unique pairs)" % (wlog.m, wlog.n, nnz)}
         del wlog, wP, wQ

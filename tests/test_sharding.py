@@ -199,6 +199,23 @@ def test_select_hot_tracks_rule_and_order():
     assert len(wide) == 248 and wide[:3].tolist() == [7, 5, 9] and set(wide[3:].tolist()) <= set(range(100, 600))
 
 
+def test_wrmf_row_ranges_are_balanced_by_cost_and_default_rules():
+    """shard_rows_by_cost: every row pays a factorisation besides its entries, so the ranges hold about the same COST; by
+    entries alone the last rank of a power-law log gets several times the rows.  And the sharded SGD trainer's defaults."""
+    log = synth.power_law_log(20000, 3000, 600000, seed=8)
+    e = np.diff(log.uq_indptr).astype(np.float64)
+    cost = np.where(e == 0, 0.0, np.where(e <= 16, 39.0 + 0.5 * e, 59.0 + e))
+    for world in (2, 4, 8):
+        b = sharding.shard_rows_by_cost(log.uq_indptr, world)
+        assert b[0] == 0 and b[-1] == log.m and (np.diff(b) > 0).all()
+        per = np.array([cost[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert per.max() <= 1.02 * per.mean() + cost.max()
+        by_entries = np.diff(sharding.shard_users_by_events(log.uq_indptr, world))
+        assert np.diff(b).max() < by_entries.max()
+    assert [sharding.default_sub_epochs(w) for w in (1, 2, 4, 8)] == [32, 32, 64, 256]
+    assert [sharding.default_asynchrony(w) for w in (1, 2, 8)] == [1.0, 0.25, 0.25]
+
+
 class _FakeEngine:
     """Records the order of the C-ABI calls SharedHotTrainer makes."""
     device = 0

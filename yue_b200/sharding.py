@@ -24,6 +24,25 @@ def shard_users_by_events(ev_indptr, world):
     return np.asarray(bounds, dtype=np.int64)
 
 
+def shard_rows_by_cost(indptr, world, fixed=59.0, light_max=16, light_fixed=39.0, light_per_entry=0.5):
+    """Contiguous row ranges of (nearly) equal WRMF cost: world+1 boundaries.  Fitted to the two sweeps of config C2 on one
+    B200 (user sweep 47.0 ms: 480 K Woodbury rows at 22 ns, 520 K factorised rows; track sweep 27.1 ms: 200 K rows, 36.7 M
+    entries): a factorised row costs 30.5 ns + 0.52 ns per entry -- the k x k factorisation is a latency chain that does not
+    depend on the entries and weighs as much as 59 of them -- a row of 1..light_max entries (Woodbury kernel) 22 ns, an empty
+    row nothing.  Balancing by entries alone hands the rank with the lightest rows several times the rows of the others: on
+    8 GPUs the iteration took 23.4 ms against 74 / 8 = 9.3 (profiles/r2/bench_r2_n8_session2.json)."""
+    e = np.diff(np.asarray(indptr, dtype=np.int64)).astype(np.float64)
+    cost = np.where(e == 0, 0.0, np.where(e <= light_max, light_fixed + light_per_entry * e, fixed + e))
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    m = len(e)
+    bounds = [0]
+    for r in range(1, world):
+        u = int(np.searchsorted(cum, cum[-1] * r / world, side="left"))
+        bounds.append(min(max(u, bounds[-1]), m))
+    bounds.append(m)
+    return np.asarray(bounds, dtype=np.int64)
+
+
 def local_shard(ev_indptr, ev_items, uq_indptr, uq_items, bounds, rank):
     """Rebased CSR slices of rank's users + (user_begin, event_base) for yue_set_interactions_shard."""
     u0, u1 = int(bounds[rank]), int(bounds[rank + 1])
@@ -148,8 +167,8 @@ def exchange_rows(table, bounds, dist):
 
 class WrmfShardedTrainer:
     """One rank of row-sharded WRMF.  Every rank holds the whole log and both tables (Engine.set_interactions /
-    set_factors with the same arrays); per half-sweep a rank solves its range of rows -- ranges balanced by entries
-    (shard_users_by_events on the row pointers) -- and the ranks exchange the solved rows.  No reduction is involved, so
+    set_factors with the same arrays); per half-sweep a rank solves its range of rows -- ranges balanced by cost
+    (shard_rows_by_cost: entries plus the factorisation every row pays) -- and the ranks exchange the solved rows.  No reduction is involved, so
     the tables are bit-identical to the single-GPU sweep whatever the number of ranks."""
 
     def __init__(self, engine, dist, device, uq_indptr, it_indptr):
@@ -157,8 +176,8 @@ class WrmfShardedTrainer:
         from ._lib import BUF_P, BUF_Q
         self.eng, self.dist, self.torch = engine, dist, torch
         self.rank, world = dist.get_rank(), dist.get_world_size()
-        self.user_bounds = shard_users_by_events(uq_indptr, world)
-        self.track_bounds = shard_users_by_events(it_indptr, world)
+        self.user_bounds = shard_rows_by_cost(uq_indptr, world)
+        self.track_bounds = shard_rows_by_cost(it_indptr, world)
         ld = (engine.k + 3) & ~3
         self.tables = []
         for which, rows in ((BUF_P, engine.m), (BUF_Q, engine.n)):
