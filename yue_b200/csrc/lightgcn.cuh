@@ -183,10 +183,20 @@ template <int NC> struct GcnFlight { static constexpr int value = NC == 1 ? 8 : 
 template <int G, int NC, class Src, class Fin>
 __device__ __forceinline__ void gcn_walk(const GcnRowRange& rr, int64_t eb, int n_edges, int nr, int my_end, int gl, unsigned mask,
                                          const Src& src, Fin& fin) {
+    // The groups of a warp walk their items IN LOCKSTEP: the trip counts below are the warp's maximum, a group that is
+    // through its own neighbours runs empty iterations.  Two groups that drift apart are issued one after the other (the
+    // warp's instruction stream doubles) and every 16-lane shuffle becomes a MATCH / VOTE sequence (profiles/ncu_gcn_r2.md);
+    // in lockstep the shuffles of the walk are plain full-warp SHFLs with a width.  Only the end of a row (finish_row) is
+    // group-uniform code: its shuffles name the group's lanes, and the warp reconverges behind it.
     constexpr int FL = GcnFlight<NC>::value;
-    int row = 0, row_end = __shfl_sync(mask, my_end, 0, G);
+    constexpr unsigned full = 0xffffffffu;
+    int n_iter = (n_edges + G - 1) / G;
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) n_iter = max(n_iter, __shfl_xor_sync(full, n_iter, o));
+    const int first_end = __shfl_sync(full, my_end, 0, G);            // every lane of the warp executes it: an empty item too
+    int row = 0, row_end = nr > 0 ? first_end : 0x7fffffff;
     GcnVec<G, NC> acc; acc.zero();
-    fin.begin(0);
+    if (nr > 0) fin.begin(0);
     auto finish_row = [&]() {
         fin.finish(row, acc);
         acc.zero(); ++row;
@@ -195,18 +205,19 @@ __device__ __forceinline__ void gcn_walk(const GcnRowRange& rr, int64_t eb, int 
     };
     int32_t id_n = 0, cn_n = 0;
     if (gl < n_edges) { id_n = __ldg(rr.nbr + eb + gl); cn_n = __ldg(rr.cnt + eb + gl); }
-    for (int p0 = 0; p0 < n_edges; p0 += G) {
+    for (int c = 0; c < n_iter; ++c) {
+        const int p0 = c * G;
         const int32_t id = id_n; const float w = (float)cn_n * (float)cn_n;
         id_n = 0; cn_n = 0;
         if (p0 + G + gl < n_edges) { id_n = __ldg(rr.nbr + eb + p0 + G + gl); cn_n = __ldg(rr.cnt + eb + p0 + G + gl); }
-        const int cnt = n_edges - p0 < G ? n_edges - p0 : G;
-        for (int t = 0; t < cnt; t += FL) {
+        const int cnt = n_edges - p0 < G ? n_edges - p0 : G;           // <= 0: this group is through
+#pragma unroll 1
+        for (int t = 0; t < G; t += FL) {
             GcnVec<G, NC> v[FL]; float ww[FL];
 #pragma unroll
             for (int x = 0; x < FL; ++x) {
-                const int lane = (t + x) & (G - 1);
-                const int32_t nid = __shfl_sync(mask, id, lane, G);
-                ww[x] = __shfl_sync(mask, w, lane, G);
+                const int32_t nid = __shfl_sync(full, id, t + x, G);
+                ww[x] = __shfl_sync(full, w, t + x, G);
                 if ((t + x) < cnt) src.fetch(rr.side, nid, gl, v[x]); else v[x].zero();
             }
 #pragma unroll
@@ -230,22 +241,26 @@ __device__ __forceinline__ void gcn_walk(const GcnRowRange& rr, int64_t eb, int 
 template <int G, int NC, class Src, class Epi>
 __device__ __forceinline__ void gcn_product(const GcnParams& p, const Src& src, const Epi& epi, uint32_t cur, int* cta_next) {
     constexpr int NGRP = kGcnThreads / G, FL = GcnFlight<NC>::value;
-    const int gl = threadIdx.x % G, grp = threadIdx.x / G;
+    const int gl = threadIdx.x % G;
     const unsigned mask = gcn_group_mask<G>();
     // Items (largest first) are dealt to the CTAs in runs of NGRP consecutive items -- neighbouring groups work on neighbouring
-    // rows, and every CTA gets about the same work -- and inside a CTA a group that is done takes the CTA's next one (a counter
-    // in shared memory; a single global ticket counter was tried: 12 K same-address atomics per phase cost more than the
-    // imbalance they removed).
+    // rows, and every CTA gets about the same work -- and inside a CTA a WARP that is done takes the CTA's next 32 / G items, one
+    // per group (a counter in shared memory; a single global ticket counter was tried: 12 K same-address atomics per phase cost
+    // more than the imbalance they removed).  The chunk list is padded to a multiple of 32 / G, so the groups of a warp always
+    // work on items of one kind, side by side (gcn_walk).
+    constexpr int GPW = 32 / G, NWARP = kGcnThreads / 32;
+    const int sub = (threadIdx.x & 31) / G, warp = threadIdx.x >> 5;
     const int64_t n_items = p.n_chunk + p.n_seg, tot = (int64_t)gridDim.x * NGRP;
-    if (threadIdx.x == 0) *cta_next = NGRP;
+    if (threadIdx.x == 0) *cta_next = NWARP;
     __syncthreads();
-    auto item_of = [&](int k) { return (int64_t)(k / NGRP) * tot + (int64_t)blockIdx.x * NGRP + (k % NGRP); };
+    auto first_item = [&](int k) { return (int64_t)(k / NWARP) * tot + (int64_t)blockIdx.x * NGRP + (int64_t)(k % NWARP) * GPW; };
     auto take = [&]() -> int64_t {
         int t = 0;
-        if (gl == 0) t = atomicAdd(cta_next, 1);
-        return item_of(__shfl_sync(mask, t, 0, G));
+        if ((threadIdx.x & 31) == 0) t = atomicAdd(cta_next, 1);
+        return first_item(__shfl_sync(0xffffffffu, t, 0));
     };
-    for (int64_t it = item_of(grp); it < n_items; it = take()) {
+    for (int64_t it0 = first_item(warp); it0 < n_items; it0 = take()) {
+        const int64_t it = it0 + sub;
         if (it < p.n_chunk) {
             const GcnChunk ck = p.chunks[it];
             const GcnRowRange rr = gcn_row_range(p, ck.row);
@@ -278,7 +293,8 @@ __device__ __forceinline__ void gcn_product(const GcnParams& p, const Src& src, 
             } fin{p, epi, ck, cur, gl, mask};
             gcn_walk<G, NC>(rr, rr.b + ck.off, ck.len, 1, ck.len, gl, mask, src, fin);
         } else {
-            const int2 sg = __ldg(p.segs + (it - p.n_chunk));            // first row, rows (consecutive, one side)
+            // first row, rows (consecutive, one side); the last run of a phase may be short: an empty item, through the same code
+            const int2 sg = it < n_items ? __ldg(p.segs + (it - p.n_chunk)) : make_int2(0, 0);
             const int64_t r0 = sg.x; const int nr = sg.y;
             GcnRowRange rr;
             const int64_t* ip;

@@ -1365,9 +1365,12 @@ static int gcn_plan(yue_t* h) {
         for (int q = 0; q < nck; ++q)
             chunks.push_back(GcnChunk{heavy[hi], (int32_t)(q * c), (int32_t)std::min<int64_t>(c, d - q * c), first + q, first, nck, (int32_t)hi, 0});
     }
+    // the groups of a warp (up to 4 of 8 lanes) take consecutive items and walk them in lockstep: they must be of one kind, so
+    // the chunk list is padded to a multiple of 4 with empty chunks that never complete a row (their own counter, slot, row 0)
+    while (chunks.size() % 4) chunks.push_back(GcnChunk{0, 0, 0, (int32_t)chunks.size(), (int32_t)chunks.size(), 0x7fffffff, (int32_t)heavy.size(), 0});
     CK(h->gcn_chunks.resize(std::max<size_t>(chunks.size(), 1))); CK(h->gcn_segs.resize(std::max<size_t>(segs.size(), 1)));
-    CK(h->gcn_arrived.resize(std::max<size_t>(heavy.size(), 1)));
-    CK(cudaMemsetAsync(h->gcn_arrived.p, 0, std::max<size_t>(heavy.size(), 1) * sizeof(unsigned), h->stream));
+    CK(h->gcn_arrived.resize(heavy.size() + 1));
+    CK(cudaMemsetAsync(h->gcn_arrived.p, 0, (heavy.size() + 1) * sizeof(unsigned), h->stream));
     if (!chunks.empty()) CK(cudaMemcpyAsync(h->gcn_chunks.p, chunks.data(), chunks.size() * sizeof(GcnChunk), cudaMemcpyHostToDevice, h->stream));
     if (!segs.empty()) CK(cudaMemcpyAsync(h->gcn_segs.p, segs.data(), segs.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
