@@ -21,8 +21,10 @@
 //                      update of the row in the same pass (D_0 is never stored)
 // A row of the graph is worked on by a group of G lanes (G = 8 / 16 / 32 for rows of up to 32 / 64 / 128 floats, 16-byte
 // chunks per lane, two chunks per lane up to 256), neighbour ids are read G at a time and broadcast, eight neighbour rows
-// are in flight per group.  Rows with more than kGcnHeavy neighbours (the most played tracks, the heaviest users) are
-// worked on by a whole CTA: every group takes a slice, partial sums meet in shared memory in a fixed order.
+// are in flight per group, the groups of a warp walk consecutive items in lockstep.  Rows with more than kGcnHeavy
+// neighbours (the most played tracks, the heaviest users) are cut into chunks dealt to groups all over the grid; the group
+// that arrives last adds the row's partial sums up in chunk order.  Light rows come in segments of consecutive rows whose
+// neighbour lists are one range of the CSR (gcn_product, gcn_walk).  What was measured on the way: profiles/ncu_gcn_r2.md.
 // Everything a later phase reads was written in an earlier one by other SMs: those loads are ld.global.cg (L2, never a
 // stale L1 line); only the graph structure and the events go through the read-only path.
 #pragma once
