@@ -375,7 +375,11 @@ def run_native(args):
                 ams.append(allmax(eng.timer_stop()))
         finally:
             sinfo = dict(hot_rows=int(len(tr.hot_tracks)), hot_share_of_positives=float(tr.hot_share_of_events), warps_per_rank=int(tr.n_warps),
-                         ctas_per_rank=int(tr.n_ctas), parts_per_epoch=args.sub_epochs, asynchrony=float(tr.asynchrony))
+                         ctas_per_rank=int(tr.n_ctas), parts_per_epoch=args.sub_epochs, asynchrony=float(tr.asynchrony),
+                         # what the shared rows put on NVLink, from the schedule (a model, not a counter: ncu is one process per
+                         # call here): a positive in the shared table is on another rank for (N - 1) / N of the slots, and a touch
+                         # is one row loaded and one row added
+                         nvlink_bytes_per_triplet_model=float(tr.hot_share_of_events) * (world - 1) / world * 2 * d * 4)
             tr.close()
             eng.set_delta_weights(None)
         sharded = {"metric": METRIC, "value": T * world / (min(sms[2:]) * 1e-3), "unit": UNIT, "ms_per_step": min(sms[2:]), "scaling": "weak",
