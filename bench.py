@@ -524,8 +524,8 @@ def run_native(args):
             sharded["quality_at_bench_size"] = ("measured with tools/quality_mgpu.py at config C2's own size (1 M users x 200 K tracks, 50 M training events, 4 epochs; "
                                                 "serial order 0.0978 / 0.0791) with this trainer's defaults -- up to 248 shared rows (239 = 47 % of the positives), "
                                                 "asynchrony 0.25, plain sum: 2 GPUs, 32 parts: Recall@10 -0.0012 / NDCG@10 +0.0005; 4 GPUs, 64 parts: -0.0005 / +0.0049 -- "
-                                                "inside the 0.5-point gate (profiles/r2/quality_c2_n2_async.log, quality_c2_n4_hot.log); with round 2's earlier 9 shared rows "
-                                                "-0.026 / -0.016 at any asynchrony; 8 GPUs at this size: not measured")
+                                                "8 GPUs, 256 parts: -0.0014 / +0.0030 -- inside the 0.5-point gate (profiles/r2/quality_c2_n2_async.log, quality_c2_n4_hot.log, "
+                                                "quality_c2_n8_hot.log); with round 2's earlier 9 shared rows -0.026 / -0.016 at any asynchrony")
         del qlog, qP, qQ
 
     # ---- round 1's schedule, for continuity: replicas of ALL rows, saturation-weighted sum once per epoch ----
@@ -568,7 +568,7 @@ def run_native(args):
             par = ("ONE model over %d GPUs: users sharded, P rows private; the %d most played tracks' rows (%.0f %% of the positives) live once "
                    "(slot s on rank s %% %d) and are loaded / added over NVLink peer memory; the tail of Q replicated, dQ all-reduced %d times "
                    "per epoch under the next part (plain sum), %d warps on %d CTAs per rank.  QUALITY: the same schedule is inside the 0.5-point "
-                   "gate of the serial order at config C2's size on 2 and 4 GPUs (`sharded.quality_at_bench_size`); not measured at C3's size; "
+                   "gate of the serial order at config C2's size on 2, 4 and 8 GPUs (`sharded.quality_at_bench_size`); not measured at C3's size; "
                    "the `quality` block is the one-GPU schedule" % (world, sched["hot_rows"], 100 * sched["hot_share"], world, args.sub_epochs,
                                                                     sched["warps"], sched["ctas"]))
         elif world > 1:
