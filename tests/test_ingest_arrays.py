@@ -205,3 +205,48 @@ def test_class_api_with_array_ingest_equals_the_dict_path(tmp_path):
             assert float(a.split(":")[1]) == pytest.approx(float(b.split(":")[1]), rel=1e-12, abs=1e-15)
     # the dict path lists the test users in the order of the test events, the array path in id order: same set of lines
     assert lines_a[0] == lines_d[0] and sorted(lines_a[1:]) == sorted(lines_d[1:])
+
+
+def test_global_randoms_is_the_random_module_stream_bit_for_bit():
+    """ingest.global_randoms(n) == [random.random() for _ in range(n)] on the SAME global generator, and the generator
+    continues where the loop would have left it (tool/dataSplit.py:15 draws from it, and so does whatever runs next)."""
+    import random
+    from yue_b200 import ingest
+    for seed in (1, 20260101):
+        for n in (0, 1, 311, 312, 313, 50001):                  # around the 624-word refill of the twister
+            random.seed(seed)
+            ref = [random.random() for _ in range(n)]
+            after = (random.random(), random.randint(0, 10 ** 9), random.getrandbits(63))
+            random.seed(seed)
+            got = ingest.global_randoms(n)
+            assert got.dtype == np.float64 and np.array_equal(got, np.array(ref, dtype=np.float64))
+            assert (random.random(), random.randint(0, 10 ** 9), random.getrandbits(63)) == after
+    random.seed(7)
+    held = ingest.split_ap(1000, 0.2)
+    random.seed(7)
+    assert held.tolist() == [random.random() < 0.2 for _ in range(1000)]
+
+
+def test_read_coded_blocks_merge_to_the_same_numbering(tmp_path):
+    """A file larger than the reader's block: the per-block dictionaries are merged and number_coded assigns the ids of
+    the one-pass dict reader (first appearance over the training events, then the test events)."""
+    from yue_b200 import ingest
+    rng = np.random.default_rng(4)
+    n = 700_000                                                  # ~ 20 MB of text: three 8 MB blocks
+    users = rng.zipf(1.3, n) % 50_000
+    tracks = rng.zipf(1.2, n) % 30_000
+    path = os.path.join(str(tmp_path), "log.csv")
+    with open(path, "w") as f:
+        f.write("".join("%d,user_%d,track_%d,a%d\n" % (1500000000 + k, u, t, t % 97) for k, (u, t) in enumerate(zip(users, tracks))))
+    assert os.path.getsize(path) > (16 << 20)
+    cols = dict([('user', 1), ('track', 2), ('artist', 3), ('time', 0)])
+    coded = ingest.read_coded(path, cols, ',')
+    log = ingest.number_coded(coded, None, 'track', list(cols))
+    first_u, first_t = {}, {}
+    for u, t in zip(users.tolist(), tracks.tolist()):
+        first_u.setdefault(u, len(first_u))
+        first_t.setdefault(t, len(first_t))
+    assert log.m == len(first_u) and log.n == len(first_t)
+    assert np.array_equal(log.ev_user, np.array([first_u[u] for u in users.tolist()], dtype=np.int32))
+    assert np.array_equal(log.ev_item, np.array([first_t[t] for t in tracks.tolist()], dtype=np.int32))
+    assert log.names['user'][log.ev_user[12345]] == "user_%d" % users[12345]

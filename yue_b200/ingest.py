@@ -55,13 +55,29 @@ def read_columns(path, columns, delim=''):
     return {name: df[ind].to_numpy(dtype=object) for name, ind in zip(names, where)}
 
 
+def global_randoms(n):
+    """n values of `random.random()` drawn from -- and advancing -- CPython's global Mersenne Twister, as one array: the
+    generator's state is handed to numpy's MT19937 (the same recurrence and tempering), 2 n words are drawn and combined the
+    way `random.random()` does ((a >> 5) * 2^26 + (b >> 6)) / 2^53, and the advanced state is written back, so whatever draws
+    from `random` next continues the same stream.  Bit-identical to the loop (tests/test_ingest_arrays.py)."""
+    import random
+    ver, st, gauss = random.getstate()
+    bg = np.random.MT19937()
+    bg.state = {'bit_generator': 'MT19937', 'state': {'key': np.array(st[:624], dtype=np.uint32), 'pos': int(st[624])}}
+    raw = bg.random_raw(2 * int(n))
+    a = (raw[0::2] >> np.uint64(5)).astype(np.float64)
+    b = (raw[1::2] >> np.uint64(6)).astype(np.float64)
+    ns = bg.state['state']
+    random.setstate((ver, tuple(int(x) for x in ns['key']) + (int(ns['pos']),), gauss))
+    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0)
+
+
 def split_ap(count, test_ratio):
     """tool/dataSplit.py:9-23: event e goes to the test set when random() < ratio -- the same global `random` stream, one
     draw per event in file order, so a seeded run splits exactly like the reference's."""
-    from random import random
     if test_ratio >= 1 or test_ratio <= 0:
         test_ratio = 0.3
-    return np.fromiter((random() < test_ratio for _ in range(count)), dtype=bool, count=count)
+    return global_randoms(count) < test_ratio
 
 
 def number_events(train, test, rec_type='track', key_order=None):
@@ -112,15 +128,20 @@ def read_coded(path, columns, delim):
     except ImportError:
         return None
     used = sorted(set(int(v) for k, v in columns.items() if k != 'time'))
-    tbl = pc.read_csv(path, read_options=pc.ReadOptions(autogenerate_column_names=True),
+    # The columns are converted to dictionary type BY THE READER: every 8 MB block is parsed and encoded on its own thread
+    # (encoding the finished columns afterwards is one thread per column: 1.0 s of the 2.4 s a 5 M-event file took), the
+    # blocks' dictionaries are merged once per column.  Whatever order the merged dictionary has, number_coded re-assigns
+    # the ids by first appearance.
+    tbl = pc.read_csv(path, read_options=pc.ReadOptions(autogenerate_column_names=True, block_size=8 << 20),
                       parse_options=pc.ParseOptions(delimiter=delim, quote_char=False),
-                      convert_options=pc.ConvertOptions(include_columns=['f%d' % i for i in used], column_types={'f%d' % i: pa.string() for i in used},
+                      convert_options=pc.ConvertOptions(include_columns=['f%d' % i for i in used],
+                                                        column_types={'f%d' % i: pa.dictionary(pa.int32(), pa.string()) for i in used},
                                                         strings_can_be_null=False))
     out = {}
     for name, ind in columns.items():
         if name == 'time':
             continue
-        d = tbl['f%d' % int(ind)].combine_chunks().dictionary_encode()
+        d = tbl['f%d' % int(ind)].unify_dictionaries().combine_chunks()
         idx = d.indices                                            # int32, no nulls: read the buffer directly (to_numpy() pulls in pandas)
         codes = np.frombuffer(idx.buffers()[1], dtype=np.int32, count=len(idx), offset=idx.offset * 4).copy()
         out[name] = (codes, np.asarray(d.dictionary.to_pylist(), dtype=object))
@@ -131,11 +152,11 @@ def number_coded(train, test, rec_type='track', key_order=None):
     """number_events on coded columns: train / test = {column: (codes, names)} with the SAME names table per column (codes of
     one dictionary).  Ids are re-assigned by first appearance over the training events, then the test events
     (data/record.py:138-146, 182-188) -- integer work only."""
-    codes, names = {}, {}
+    from concurrent.futures import ThreadPoolExecutor
     nt = len(train['user'][0])
-    for kind in (key_order or train.keys()):
-        if kind == 'time':
-            continue
+    kinds = [k for k in (key_order or train.keys()) if k != 'time']
+
+    def one(kind):
         c = train[kind][0] if test is None else np.concatenate([train[kind][0], test[kind][0]])
         table = train[kind][1]
         # where each code occurs first: written back to front, so that for a repeated code the LAST write -- its first
@@ -146,7 +167,11 @@ def number_coded(train, test, rec_type='track', key_order=None):
         order = seen[np.argsort(first[seen], kind='stable')]        # the codes that occur, in order of first appearance
         remap = np.full(len(table), -1, dtype=np.int32)
         remap[order] = np.arange(len(order), dtype=np.int32)
-        codes[kind], names[kind] = remap[c], table[order]
+        return remap[c], table[order]
+    with ThreadPoolExecutor(max(1, len(kinds))) as pool:            # the columns are independent; numpy's indexing drops the GIL
+        done = list(pool.map(one, kinds))
+    codes = {k: d[0] for k, d in zip(kinds, done)}
+    names = {k: d[1] for k, d in zip(kinds, done)}
     is_test = np.zeros(len(codes['user']), dtype=np.uint8)
     is_test[nt:] = 1
     return ArrayLog(codes['user'], codes[rec_type], is_test, names, rec_type)
