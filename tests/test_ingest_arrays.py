@@ -120,6 +120,39 @@ def test_arrow_coded_path_equals_the_object_path(golden_dir, tmp_path):
             assert list(a.names[kind]) == list(b.names[kind])
 
 
+@pytest.mark.parametrize("times", ["golden", "epoch", "ragged"])
+def test_coded_by_time_split_equals_the_object_path(golden_dir, tmp_path, times):
+    """-byTime (config/BPR.conf's own evaluation.setup): the coded path -- user codes + the time column as one Arrow array,
+    numeric sort when every time field is a run of digits of one length, Arrow's string sort otherwise -- gives the training
+    and test events of the object path (data/record.py:108-123 restated on Python strings, pinned to the reference above):
+    users by first appearance, inside a user by the time STRING, ties in file order."""
+    pytest.importorskip("pyarrow")
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    events = [dict(e) for e in g["events"]]
+    rng = np.random.default_rng(11)
+    if times == "epoch":                                         # ten digits, many ties
+        for e in events:
+            e["time"] = str(1500000000 + int(rng.integers(0, 400)))
+    elif times == "ragged":                                      # strings of different lengths and non-digits: "10" < "9", "2a" > "2"
+        pool = ["9", "10", "2", "2a", "100", "x1", "", "07", "7", "1e3"]
+        for e in events:
+            e["time"] = pool[int(rng.integers(0, len(pool)))]
+    path = str(tmp_path / "log.txt")
+    _write_csv(path, events)
+    ev = LineConfig("-target track -byTime 0.2")
+    coded = ingest.read_coded(path, COLUMNS, ",", want_time=True)
+    assert coded is not None and len(coded["time"]) == len(events)
+    a = ingest.load_numbered(path, COLUMNS, ",", ev, "track")
+    cols = ingest.read_columns(path, COLUMNS, ",")
+    tr, te = ingest.by_time(cols, 0.2)
+    tr2, te2 = ingest.by_time_coded(coded["user"][0], coded["time"], 0.2)
+    assert np.array_equal(tr, tr2) and np.array_equal(te, te2)
+    b = ingest.number_events({k: v[tr] for k, v in cols.items()}, {k: v[te] for k, v in cols.items()}, "track", list(COLUMNS))
+    assert np.array_equal(a.ev_user, b.ev_user) and np.array_equal(a.ev_item, b.ev_item) and np.array_equal(a.is_test, b.is_test)
+    for kind in ("user", "track", "artist"):
+        assert list(a.names[kind]) == list(b.names[kind])
+
+
 def test_result_lines_and_measures_match_the_loops():
     rng = np.random.default_rng(3)
     m, n, N = 300, 500, 10

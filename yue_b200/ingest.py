@@ -115,12 +115,41 @@ def by_time(cols, ratio):
     return order[is_train], order[~is_train]
 
 
-def read_coded(path, columns, delim):
+def by_time_coded(ucodes, times, ratio):
+    """by_time on a coded user column and the time column as an Arrow string array: the same two index arrays, without a
+    Python string per event.  Users in order of first appearance in the file, inside a user by the time field AS A STRING,
+    ties in file order (`sorted` is stable).  When every time field is a run of digits of one length (epoch seconds) the
+    string order is the numeric order and the sort is a numpy lexsort; otherwise Arrow sorts the strings (byte order of
+    UTF-8 = code-point order = Python's str order)."""
+    import pyarrow as pa
+    import pyarrow.compute as pcc
+    n = len(ucodes)
+    first = np.full(int(ucodes.max()) + 1 if n else 0, n, dtype=np.int64)
+    first[ucodes[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)
+    rank = np.empty(len(first), dtype=np.int64)
+    rank[np.argsort(first, kind='stable')] = np.arange(len(first))
+    u = rank[ucodes]                                               # user codes numbered by first appearance
+    lens = pcc.min_max(pcc.utf8_length(times)).as_py() if n else {'min': 0, 'max': 0}
+    if n and lens['min'] == lens['max'] and 0 < lens['max'] <= 18 and pcc.all(pcc.utf8_is_digit(times)).as_py():
+        order = np.lexsort((pcc.cast(times, pa.int64()).to_numpy(zero_copy_only=False), u))      # stable: ties keep file order
+    else:
+        tbl = pa.table({'u': pa.array(u), 't': times, 'i': pa.array(np.arange(n, dtype=np.int64))})
+        order = pcc.sort_indices(tbl, sort_keys=[('u', 'ascending'), ('t', 'ascending'), ('i', 'ascending')]).to_numpy(zero_copy_only=False)
+    u_sorted = u[order]
+    start = np.flatnonzero(np.r_[True, u_sorted[1:] != u_sorted[:-1]])
+    length = np.diff(np.r_[start, len(order)])
+    rank_in_user = np.arange(len(order)) - np.repeat(start, length)
+    cut = (length * (1 - ratio)).astype(np.int64)
+    is_train = rank_in_user < np.repeat(cut, length)
+    return order[is_train], order[~is_train]
+
+
+def read_coded(path, columns, delim, want_time=False):
     """The non-time columns of a log file as (codes int32[events], names[array of str]) per column WITHOUT creating a Python
     string per field: Arrow's multi-threaded CSV reader + dictionary encoding (codes in order of first appearance in the
     file).  None when that reader cannot take the file (a regex delimiter, pyarrow missing): the caller falls back to
-    read_columns."""
-    if len(delim) != 1:
+    read_columns.  want_time: out['time'] is the time column as ONE Arrow string array (by_time_coded sorts it)."""
+    if len(delim) != 1 or (want_time and 'time' not in columns):
         return None
     try:
         import pyarrow as pa
@@ -132,12 +161,17 @@ def read_coded(path, columns, delim):
     # (encoding the finished columns afterwards is one thread per column: 1.0 s of the 2.4 s a 5 M-event file took), the
     # blocks' dictionaries are merged once per column.  Whatever order the merged dictionary has, number_coded re-assigns
     # the ids by first appearance.
+    types = {'f%d' % i: pa.dictionary(pa.int32(), pa.string()) for i in used}
+    if want_time:
+        if int(columns['time']) in used:                           # the time field doubles as another column: object path
+            return None
+        types['f%d' % int(columns['time'])] = pa.string()
     tbl = pc.read_csv(path, read_options=pc.ReadOptions(autogenerate_column_names=True, block_size=8 << 20),
                       parse_options=pc.ParseOptions(delimiter=delim, quote_char=False),
-                      convert_options=pc.ConvertOptions(include_columns=['f%d' % i for i in used],
-                                                        column_types={'f%d' % i: pa.dictionary(pa.int32(), pa.string()) for i in used},
-                                                        strings_can_be_null=False))
+                      convert_options=pc.ConvertOptions(include_columns=sorted(types), column_types=types, strings_can_be_null=False))
     out = {}
+    if want_time:
+        out['time'] = tbl['f%d' % int(columns['time'])].combine_chunks()
     for name, ind in columns.items():
         if name == 'time':
             continue
@@ -180,13 +214,19 @@ def number_coded(train, test, rec_type='track', key_order=None):
 def load_numbered(path, columns, delim, evaluation, rec_type='track'):
     """File -> ArrayLog under the reference's evaluation.setup options -ap r / -testSet file / -byTime r (yue.py:38-46)."""
     order = [k for k in columns.keys()]
-    if not evaluation.contains('-byTime'):                          # -byTime compares the time fields as strings: object path
+    if not evaluation.contains('-byTime'):
         coded = read_coded(path, columns, delim)
         if coded is not None and evaluation.contains('-ap'):
             held = split_ap(len(coded['user'][0]), float(evaluation['-ap']))
             return number_coded({k: (c[~held], t) for k, (c, t) in coded.items()}, {k: (c[held], t) for k, (c, t) in coded.items()}, rec_type, order)
         if coded is not None and not evaluation.contains('-testSet'):
             return number_coded(coded, None, rec_type, order)
+    elif not evaluation.contains('-testSet') and not evaluation.contains('-ap'):
+        coded = read_coded(path, columns, delim, want_time=True)   # config/BPR.conf's own split
+        if coded is not None:
+            times = coded.pop('time')
+            tr, te = by_time_coded(coded['user'][0], times, float(evaluation['-byTime']))
+            return number_coded({k: (c[tr], t) for k, (c, t) in coded.items()}, {k: (c[te], t) for k, (c, t) in coded.items()}, rec_type, order)
     cols = read_columns(path, columns, delim)
     if evaluation.contains('-testSet'):
         return number_events(cols, read_columns(evaluation['-testSet'], columns, delim), rec_type, order)
