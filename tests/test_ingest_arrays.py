@@ -151,6 +151,10 @@ def test_coded_by_time_split_equals_the_object_path(golden_dir, tmp_path, times)
     assert np.array_equal(a.ev_user, b.ev_user) and np.array_equal(a.ev_item, b.ev_item) and np.array_equal(a.is_test, b.is_test)
     for kind in ("user", "track", "artist"):
         assert list(a.names[kind]) == list(b.names[kind])
+    # the position of every numbered event in the file (LightGCN's batches walk the training events in file order)
+    assert np.array_equal(a.file_pos, np.concatenate([tr, te])) and sorted(a.file_pos.tolist()) == list(range(len(events)))
+    names = np.asarray(a.names["user"], dtype=object)
+    assert [events[p]["user"] for p in a.file_pos[:50].tolist()] == names[a.ev_user[:50]].tolist()
 
 
 def test_result_lines_and_measures_match_the_loops():

@@ -25,6 +25,7 @@ class ArrayLog(object):
     def __init__(self, ev_user, ev_item, is_test, names, rec_type):
         self.ev_user, self.ev_item, self.is_test = ev_user, ev_item, is_test
         self.names, self.rec_type = names, rec_type            # names[kind] = array of names, index = id
+        self.file_pos = None                                   # -byTime: position of every event in the file (the split reorders them)
         self.m, self.n = len(names['user']), len(names[rec_type])
 
     @property
@@ -226,7 +227,9 @@ def load_numbered(path, columns, delim, evaluation, rec_type='track'):
         if coded is not None:
             times = coded.pop('time')
             tr, te = by_time_coded(coded['user'][0], times, float(evaluation['-byTime']))
-            return number_coded({k: (c[tr], t) for k, (c, t) in coded.items()}, {k: (c[te], t) for k, (c, t) in coded.items()}, rec_type, order)
+            log = number_coded({k: (c[tr], t) for k, (c, t) in coded.items()}, {k: (c[te], t) for k, (c, t) in coded.items()}, rec_type, order)
+            log.file_pos = np.concatenate([tr, te])
+            return log
     cols = read_columns(path, columns, delim)
     if evaluation.contains('-testSet'):
         return number_events(cols, read_columns(evaluation['-testSet'], columns, delim), rec_type, order)
@@ -235,7 +238,9 @@ def load_numbered(path, columns, delim, evaluation, rec_type='track'):
         return number_events({k: v[~held] for k, v in cols.items()}, {k: v[held] for k, v in cols.items()}, rec_type, order)
     if evaluation.contains('-byTime'):
         tr, te = by_time(cols, float(evaluation['-byTime']))
-        return number_events({k: v[tr] for k, v in cols.items()}, {k: v[te] for k, v in cols.items()}, rec_type, order)
+        log = number_events({k: v[tr] for k, v in cols.items()}, {k: v[te] for k, v in cols.items()}, rec_type, order)
+        log.file_pos = np.concatenate([tr, te])
+        return log
     return number_events(cols, None, rec_type, order)
 
 

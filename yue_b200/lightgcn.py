@@ -52,7 +52,9 @@ class GpuLightGCNMixin(GpuBPRMixin):
         """(user ids, track ids) of trainingData in file order (LightGCN.py:59-60)."""
         if hasattr(self.data, 'log'):                          # yue.ingest=arrays: the numbered events are already arrays
             log = self.data.log
-            keep = log.is_test == 0
+            keep = np.flatnonzero(log.is_test == 0)
+            if log.file_pos is not None:                       # -byTime grouped the events by user: back to the file's order
+                keep = keep[np.argsort(log.file_pos[keep], kind='stable')]
             return log.ev_user[keep], log.ev_item[keep]
         uid, tid = self.data.name2id['user'], self.data.name2id[self.recType]
         events = self.data.trainingData
