@@ -23,9 +23,10 @@ What it restates (file:line relative to the reference tree):
 * ``recommender/advanced/CUNE.py:118-178``  two-level BPR training loop (``cune_ref.py``; pinned by the reference's loop
                                         text, ``make_golden_cune.py``)
 
-* ``recommender/advanced/LightGCN.py:15-105``  LightGCN's graph, loss, Adam loop (``lightgcn_ref.py``; PARITY UNPINNED: the module
-                                        cannot be imported -- TF-1 and ``base/DeepRecommender`` without ``.py`` -- so the restatement is
-                                        checked against its own numerical gradient only)
+* ``recommender/advanced/LightGCN.py:15-105``  LightGCN's graph, loss, Adam loop (``lightgcn_ref.py``; pinned by the reference's own
+                                        two files run unmodified over ``tf1_shim.py`` -- a stand-in for their TensorFlow-1 calls on
+                                        torch autograd -- ``make_golden_lightgcn.py`` -> ``tests/golden/lightgcn_small.npz``; the
+                                        meaning of the TF ops themselves is restated from TF's documentation)
 
 Parity pinning.  The reference ships no tests, golden vectors or data, and its
 RNG streams (CPython Mersenne Twister, unseeded) cannot be reproduced by a GPU

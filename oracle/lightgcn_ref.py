@@ -1,10 +1,15 @@
 """Oracle (test infrastructure) for LightGCN as the reference ships it: recommender/advanced/LightGCN.py:15-100 on
 base/DeepRecommender:22-35.
 
-PARITY UNPINNED by the reference: the module imports TensorFlow 1.x and `base.DeepRecommender`, a file without the `.py`
-extension, so it cannot be imported or executed here and it ships no golden outputs.  This file restates its
-graph in float64 numpy / scipy from the text, and checks its own hand-derived gradient against a numerical one
-(tests/test_oracle_golden.py); the CUDA path (csrc/lightgcn.cuh) is compared with it.
+PINNED BY THE REFERENCE'S OWN TEXT, up to the meaning of the TensorFlow ops: the module imports TensorFlow 1.x and
+`base.DeepRecommender`, a file without the `.py` extension, so it cannot be imported as it stands -- but
+oracle/make_golden_lightgcn.py executes both files UNMODIFIED in the build container over oracle/tf1_shim.py (a stand-in for
+the TF calls they make, on torch autograd in float64) with `random.randint` fed the Philox attempt stream, and commits the
+run as tests/golden/lightgcn_small.npz: 60 Adam steps, their losses, U and V, the propagated tables.  This file reproduces
+that run to 1e-12 (tests/test_lightgcn.py) -- the graph wiring, the loss, the optimiser's scope, the batch loop and the
+sampler are therefore the reference's; what each TF op MEANS (duplicate entries of a SparseTensor add up, l2_normalize's
+epsilon, Adam's formula) is restated from TensorFlow's documentation in the shim's header and has no pin in the reference
+tree.  Its hand-derived gradient is also checked against a numerical one and, through the shim, against torch's autograd.
 
 What the text says, line by line:
 

@@ -1,6 +1,10 @@
-"""K9 (LightGCN): oracle/lightgcn_ref.py restates recommender/advanced/LightGCN.py:27-98 (PARITY UNPINNED by
-the reference -- its module cannot be imported, see the oracle's header); the CPU tests pin the restatement's own gradient
-numerically, the GPU tests compare csrc/lightgcn.cuh (yue_gcn_apply / yue_gcn_epoch / yue_gcn_finalize) with it.
+"""K9 (LightGCN): oracle/lightgcn_ref.py restates recommender/advanced/LightGCN.py:27-98.  The reference's
+module needs TensorFlow 1 and a base file without `.py`, so it is pinned the way the SGD loop and CUNE are: its OWN text, both
+files unmodified, was executed in the build container over a stand-in for the TF calls it makes (oracle/tf1_shim.py on torch
+autograd, oracle/make_golden_lightgcn.py) and its losses, variables and propagated tables after 60 Adam steps are the golden
+run tests/golden/lightgcn_small.npz -- the oracle reproduces them to 1e-12, the kernel to float32 accuracy.  (What the shim
+cannot pin is the meaning of each TF op, restated from TF's documentation in its header.)  The CPU tests also check the
+restatement's gradient numerically; the GPU tests compare csrc/lightgcn.cuh (yue_gcn_apply / _epoch / _finalize) with it.
 
 Tolerances (float32 kernel against the float64 restatement): the loss of a step 2e-5 relative; the gradient of the first
 step (read back from Adam's first moment, m_1 = 0.1 g) 2e-4 of the largest row gradient, per row; the propagated tables
@@ -36,6 +40,26 @@ def test_oracle_gradient_is_the_numerical_gradient():
         Em[r, c] -= 1e-6
         num = (lg.loss_of(A, Ep, m, u, i, j, 0.01) - lg.loss_of(A, Em, m, u, i, j, 0.01)) / 2e-6
         assert abs(num - g[r, c]) <= 1e-6 * max(1.0, abs(num))
+
+
+def test_oracle_reproduces_the_reference_graph_run_over_the_tf_shim(golden_dir):
+    """tests/golden/lightgcn_small.npz is the output of the reference's own LightGCN.py + base/DeepRecommender (unmodified) over
+    oracle/tf1_shim.py, its sampler fed the Philox attempt stream (consumed exactly: asserted by the generator).  The
+    restatement gives the same 60 losses, the same U and V after two passes and the same propagated tables."""
+    import os
+    g = np.load(os.path.join(golden_dir, "lightgcn_small.npz"))
+    m, n = int(g["m"]), int(g["n"])
+    A = lg.adjacency(m, n, g["ev_user"], g["ev_item"])
+    for ep in range(int(g["iters"])):                               # the kept negative = the fifth draw, Philox slot 4
+        assert np.array_equal(lg.batch_negatives(int(g["seed"]), ep, g["ev_user"], n, g["uq_indptr"], g["uq_items"]), g["neg"][ep])
+    U, V, losses, _ = lg.train(A, g["U0"], g["V0"], g["ev_user"], g["ev_item"], g["uq_indptr"], g["uq_items"], int(g["batch"]),
+                               float(g["lr"]), float(g["reg"]), int(g["seed"]), epochs=int(g["iters"]))
+    assert len(losses) == len(g["losses"]) == 60 and np.allclose(losses, g["losses"], rtol=1e-12)
+    assert np.abs(g["U"] - g["U0"]).max() > 0.01                    # the variables moved ...
+    assert np.abs(U - g["U"]).max() < 1e-12 and np.abs(V - g["V"]).max() < 1e-12      # ... to the same place
+    FU, FV = lg.embeddings(A, U, V)
+    assert np.abs(FU - g["FU"]).max() < 1e-11 and np.abs(FV - g["FV"]).max() < 1e-11
+    assert np.allclose(FU[g["pred_users"]] @ FV.T, g["preds"], rtol=1e-10)
 
 
 def test_oracle_adjacency_weighs_a_pair_by_its_squared_count():
@@ -238,6 +262,29 @@ def test_whole_pass_with_a_partial_last_batch_and_two_layers(engine):
     FU, FV = engine.get_factors()
     wU, wV = lg.embeddings(A, P, Q, n_layers=2)
     assert np.abs(np.concatenate([FU, FV]) - np.concatenate([wU, wV])).max() <= 1e-5 * np.abs(np.concatenate([wU, wV])).max()
+
+
+@pytest.mark.gpu
+def test_kernel_follows_the_reference_graph_golden_run(engine, golden_dir):
+    """The CUDA path against the golden run of the reference's own LightGCN text (tests/golden/lightgcn_small.npz): the same
+    log, initial variables and sampler seed, two passes of 30 steps through yue_gcn_epoch: every step's loss within 5e-4,
+    >= 99.5 % of the table entries within 2 % of the distance they moved, the propagated tables the golden ones."""
+    import os
+    g = np.load(os.path.join(golden_dir, "lightgcn_small.npz"))
+    m, n = int(g["m"]), int(g["n"])
+    engine.set_interactions(m, n, g["ev_indptr"], g["ev_items"], g["uq_indptr"], g["uq_items"])
+    engine.set_factors(g["U0"].astype(np.float32), g["V0"].astype(np.float32))
+    engine.gcn_set_events(g["ev_user"], g["ev_item"])
+    loss = np.concatenate([engine.gcn_epoch(int(g["batch"]), float(g["lr"]), float(g["reg"]), int(g["seed"]), ep) for ep in range(int(g["iters"]))])
+    assert np.allclose(loss, g["losses"], rtol=5e-4)
+    P, Q = engine.get_factors()
+    got, ref = np.concatenate([P, Q]).astype(np.float64), np.concatenate([g["U"], g["V"]])
+    moved = np.abs(ref - np.concatenate([g["U0"], g["V0"]]))
+    assert (np.abs(got - ref) <= 0.02 * moved + 1e-9).mean() >= 0.995
+    engine.gcn_finalize()
+    FU, FV = engine.get_factors()
+    ref_f = np.concatenate([g["FU"], g["FV"]])
+    assert np.abs(np.concatenate([FU, FV]) - ref_f).max() <= 2e-3 * np.abs(ref_f).max()
 
 
 @pytest.mark.gpu
