@@ -17,7 +17,8 @@ What it restates (file:line relative to the reference tree):
                                            selection actually shipped (``ref_quirk``)
 * ``evaluation/measure.py:6-101``      hits / precision / recall / F1 / MAP / coverage
 * ``data/record.py:138-202``           id assignment and test-set semantics
-* ``recommender/advanced/APR.py:25-76,95-137``  adversarial BPR losses and gradients
+* ``recommender/advanced/APR.py:25-76,95-137``  adversarial BPR losses and gradients (``apr_ref.py``; its closed forms pinned by the
+                                        reference's own graph evaluated over ``tf1_shim.py`` on single triplets: ``make_golden_apr.py``)
 * ``recommender/cf/WRMF.py:17-88``      implicit-feedback ALS (``wrmf_ref.py``; pinned by the reference CLASS itself,
                                         ``make_golden_wrmf.py`` -> ``tests/golden/wrmf_small.npz``)
 * ``recommender/advanced/CUNE.py:118-178``  two-level BPR training loop (``cune_ref.py``; pinned by the reference's loop

@@ -18,8 +18,11 @@ and the SGD step on the loss above with D constant (all gradients from the OLD r
     s0 = sigmoid(-y), s1 = sigmoid(-y_adv), a = lr (s0 + regA s1), b = lr regA s1 eps
     P  += a d - 2 b P^      V_i += a P - b d^      V_j -= a P - b d^
 followed by the multiplicative L2 shrink of BPR.py:55-57.  The optimiser (SGD instead of Adam), the
-epoch structure and the per-triplet perturbation are this build's; PARITY UNPINNED by the
-reference.  Pinned here by a numerical-gradient check (tests/test_apr.py).
+epoch structure and the per-triplet perturbation are this build's (north_star's).  The FORMULAS are pinned by the
+reference's own graph: APR.py and base/DeepRecommender, unmodified, are evaluated over oracle/tf1_shim.py (their
+TensorFlow-1 calls on torch autograd) on single triplets -- where the batch form and the per-triplet form coincide --
+and the perturbation, y_adv, loss_adv and its gradients with the perturbation held constant agree with this file to
+1e-14 (oracle/make_golden_apr.py -> tests/golden/apr_graph.npz, tests/test_apr.py); a numerical-gradient check besides.
 """
 import math
 

@@ -1,5 +1,5 @@
-"""Test infrastructure: a minimal stand-in for the TensorFlow 1.x API that recommender/advanced/LightGCN.py and
-base/DeepRecommender use, built on torch (CPU, float64, autograd) -- so that the REFERENCE'S OWN graph-building and training
+"""Test infrastructure: a minimal stand-in for the TensorFlow 1.x API that recommender/advanced/LightGCN.py,
+recommender/advanced/APR.py and base/DeepRecommender use, built on torch (CPU, float64, autograd) -- so that the REFERENCE'S OWN graph-building and training
 text can be executed unmodified in the build container (oracle/make_golden_lightgcn.py), where TensorFlow 1 does not exist.
 
 What this pins and what it does not.  Executing the reference's text pins everything the reference WROTE: which tensors feed
@@ -11,7 +11,9 @@ from TensorFlow's documentation and is not pinned by anything in the reference t
   * `train.AdamOptimizer(lr)`: beta1 0.9, beta2 0.999, epsilon 1e-8; lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);
     m, v moving averages of g and g^2; var -= lr_t m / (sqrt(v) + epsilon); every variable the loss depends on, every step;
   * `truncated_normal(stddev)`: normal draws beyond two standard deviations are redrawn (numpy's global generator here);
-  * `reduce_sum` of a Python list of tensors stacks them first.
+  * `reduce_sum` of a Python list of tensors stacks them first;
+  * `gradients(y, [variables])`: dense d y / d variable (zero rows where the batch does not touch the variable);
+    `nn.softplus(x)` = log(1 + e^x); `Variable.assign` takes effect when the returned node is run.
 A graph is a tree of lazy nodes; `Session.run(fetches, feed_dict)` evaluates them with torch (one cache per run), the
 `minimize` node runs autograd on the loss and applies Adam.  Only what those two files touch exists.
 """
@@ -61,14 +63,24 @@ class Placeholder(Node):
 
 
 class Variable(Node):
-    def __init__(self, initial_value, name=None):
+    def __init__(self, initial_value, name=None, dtype=None, trainable=True):
         Node.__init__(self, None)
-        self.name = name
-        self.tensor = torch.tensor(np.asarray(initial_value), dtype=DT, requires_grad=True)
-        _VARIABLES.append(self)
+        self.name, self.trainable = name, trainable
+        self.tensor = torch.tensor(np.asarray(initial_value), dtype=DT, requires_grad=True)     # tf.gradients may ask for any variable
+        if trainable:
+            _VARIABLES.append(self)
 
     def value(self, feeds, cache):
         return self.tensor
+
+    def assign(self, value):
+        var = self
+
+        def fn(v):
+            with torch.no_grad():
+                var.tensor.copy_(v)
+            return var.tensor
+        return Node(fn, value)
 
 
 def placeholder(dtype, shape=None, name=None):
@@ -125,6 +137,36 @@ def split(value, num_or_size_splits, axis=0):
     return [Node(lambda parts, k=k: parts[k], whole) for k in range(len(sizes))]
 
 
+def zeros(shape, dtype=None):
+    return np.zeros(tuple(shape), dtype=np.float32)
+
+
+def constant(value, dtype=None):
+    return float(value)
+
+
+def add(a, b):
+    return Node(lambda x, y: x + y, a, b)
+
+
+def subtract(a, b):
+    return Node(lambda x, y: x - y, a, b)
+
+
+def stop_gradient(x):
+    return Node(lambda v: v.detach(), x)
+
+
+def gradients(ys, xs):
+    """d ys / d x for every x in xs, dense (TF returns IndexedSlices for gathered variables; APR.py densifies them)."""
+    def one(x):
+        def fn(y):
+            g = torch.autograd.grad(y, x.tensor, retain_graph=True, allow_unused=True)[0]
+            return torch.zeros_like(x.tensor) if g is None else g
+        return Node(fn, ys)
+    return [one(x) for x in xs]
+
+
 def multiply(a, b):
     return Node(lambda x, y: x * y, a, b)
 
@@ -149,6 +191,10 @@ class _NN(object):
     @staticmethod
     def l2_loss(x):
         return Node(lambda v: (v * v).sum() / 2, x)
+
+    @staticmethod
+    def softplus(x):
+        return Node(torch.nn.functional.softplus, x)
 
 
 nn = _NN()
@@ -194,6 +240,12 @@ def global_variables_initializer():
 
 
 class Session(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
     def run(self, fetches, feed_dict=None):
         feeds, cache = feed_dict or {}, {}
         many = isinstance(fetches, (list, tuple))

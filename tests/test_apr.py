@@ -1,5 +1,8 @@
-"""APR (adversarial BPR): the oracle's closed forms against first principles (CPU), and the fused
-GPU kernel against the oracle."""
+"""APR (adversarial BPR): the oracle's closed forms against the REFERENCE'S OWN GRAPH (recommender/advanced/APR.py and
+base/DeepRecommender, unmodified, evaluated over oracle/tf1_shim.py on single triplets: tests/golden/apr_graph.npz, written
+by oracle/make_golden_apr.py) and against first principles (CPU), and the fused GPU kernel against the oracle.  The
+optimiser (per-triplet SGD where the reference runs Adam on mini-batches) and the per-triplet perturbation (the reference
+aggregates its gradient per row over the batch) are north_star's and stay this build's."""
 import numpy as np
 import pytest
 
@@ -34,6 +37,31 @@ def test_closed_form_adversarial_score_and_step_match_first_principles():
         gj = np.array([(L(p, qi, qj + h * np.eye(d)[k]) - L(p, qi, qj - h * np.eye(d)[k])) / (2 * h) for k in range(d)])
         assert np.allclose(P[0] - p, -lr * gp, atol=1e-8)
         assert np.allclose(Q[0] - qi, -lr * gi, atol=1e-8) and np.allclose(Q[1] - qj, -lr * gj, atol=1e-8)
+
+
+def test_oracle_step_is_the_reference_graph_on_a_single_triplet(golden_dir):
+    """For a batch that is ONE triplet the reference's graph and the per-triplet form coincide.  From the reference's own
+    text: the perturbation `assign(l2_normalize(grad) * eps)` (APR.py:51-60) is the closed form -eps d^ / -eps P^ / +eps P^;
+    `loss_adv` (62-72) is softplus(-y) + regA softplus(-y_adv) with adv_score()'s y_adv; and the gradients of `loss_adv`
+    with respect to U and V with the perturbation held constant (what `minimize(self.loss_adv)` differentiates) are the
+    step of apr_epoch(): one call with lr and no shrink moves the rows by -lr times them."""
+    import os
+    g = np.load(os.path.join(golden_dir, "apr_graph.npz"))
+    eps, regA, lr = float(g["eps"]), float(g["regA"]), 0.01
+    assert len(g["u"]) == 24
+    for t in range(len(g["u"])):
+        p, qi, qj = g["p"][t], g["qi"][t], g["qj"][t]
+        d = qi - qj
+        n_p, n_d = np.linalg.norm(p), np.linalg.norm(d)
+        assert np.allclose(g["du"][t], -eps * d / n_d, atol=1e-13)
+        assert np.allclose(g["di"][t], -eps * p / n_p, atol=1e-13) and np.allclose(g["dj"][t], eps * p / n_p, atol=1e-13)
+        assert g["y"][t] == pytest.approx(p.dot(d), rel=1e-12)
+        assert apr_ref.adv_score(float(p.dot(d)), n_p, n_d, eps) == pytest.approx(g["ya"][t], rel=1e-12, abs=1e-13)
+        P, Q = p[None, :].copy(), np.stack([qi, qj])
+        loss = apr_ref.apr_epoch(P, Q, [0], [0], [1], lr, 0.0, 0.0, eps, regA)
+        assert loss == pytest.approx(g["loss_adv"][t], rel=1e-12)
+        assert np.allclose(P[0] - p, -lr * g["gp"][t], atol=1e-14)
+        assert np.allclose(Q[0] - qi, -lr * g["gi"][t], atol=1e-14) and np.allclose(Q[1] - qj, -lr * g["gj"][t], atol=1e-14)
 
 
 def test_apr_reduces_to_simultaneous_bpr_when_adversary_is_off():
