@@ -228,9 +228,11 @@ def test_cv_folds_and_progress_hook(tmp_path):
     log_path = tmp_path / "log.txt"
     synth.write_csv_log(str(log_path), 800, 3000, 20000, seed=3)
     out = {}
-    for flag in ("", " -p"):
-        vals = conf_values(tmp_path / ("cv" + flag.strip()), eval_setup="-target track -cv 3" + flag,
-                           extra={"record": str(log_path), "yue.sgd": "serial", "yue.seed": "5", "num.max.iter": "2"})
+    for flag in ("", " -p", "arrays"):                   # "arrays": the folds numbered from ONE coded read of the file (ingest.cv_folds)
+        extra = {"record": str(log_path), "yue.sgd": "serial", "yue.seed": "5", "num.max.iter": "2"}
+        if flag == "arrays":
+            extra["yue.ingest"] = "arrays"
+        vals = conf_values(tmp_path / ("cv" + flag.strip()), eval_setup="-target track -cv 3" + (flag if flag != "arrays" else ""), extra=extra)
         random.seed(9)
         with redirect_stdout(io.StringIO()):
             res = Yue(Config(values=vals)).execute()
@@ -241,10 +243,10 @@ def test_cv_folds_and_progress_hook(tmp_path):
         out[flag] = res
     # same folds (same `random` seed), same sampler seed, serial order: the two schedules give the same averages up to
     # the unseeded factor init in the child processes -- so only the structure and the ranges are compared
-    for a, b in zip(out[""], out[" -p"]):
-        assert a.split(":")[0] == b.split(":")[0]
+    for a, b, c in zip(out[""], out[" -p"], out["arrays"]):
+        assert a.split(":")[0] == b.split(":")[0] == c.split(":")[0]
         if ":" in a:
-            assert 0.0 <= float(a.split(":")[1]) <= 1.0 and 0.0 <= float(b.split(":")[1]) <= 1.0
+            assert all(0.0 <= float(x.split(":")[1]) <= 1.0 for x in (a, b, c))
 
     # the progress hook
     vals = conf_values(tmp_path / "hook", extra={"record": str(log_path), "yue.seed": "5", "num.max.iter": "1"})

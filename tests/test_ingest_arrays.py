@@ -157,6 +157,28 @@ def test_coded_by_time_split_equals_the_object_path(golden_dir, tmp_path, times)
     assert [events[p]["user"] for p in a.file_pos[:50].tolist()] == names[a.ev_user[:50]].tolist()
 
 
+def test_cv_folds_equal_the_reference_split_numbered_fold_by_fold(golden_dir, tmp_path):
+    """-cv k: tool/dataSplit.py:26-38 holds out the events at positions i modulo k; every fold is numbered like the Record the
+    reference builds from the two lists.  cv_folds (one read of the file, coded columns) against crossValidation + the object
+    path; k outside 2..10 means 3 (dataSplit.py:27-28)."""
+    pytest.importorskip("pyarrow")
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    events = g["events"][:1500]
+    path = str(tmp_path / "log.txt")
+    _write_csv(path, events)
+    cols = ingest.read_columns(path, COLUMNS, ",")
+    for k in (4, 1):
+        kk = 3 if k <= 1 else k
+        folds = list(ingest.cv_folds(path, COLUMNS, ",", k, "track"))
+        assert len(folds) == kk
+        for i, a in enumerate(folds):
+            held = np.arange(len(events)) % kk == i
+            b = ingest.number_events({c: v[~held] for c, v in cols.items()}, {c: v[held] for c, v in cols.items()}, "track", list(COLUMNS))
+            assert np.array_equal(a.ev_user, b.ev_user) and np.array_equal(a.ev_item, b.ev_item) and np.array_equal(a.is_test, b.is_test)
+            assert list(a.names["user"]) == list(b.names["user"]) and list(a.names["track"]) == list(b.names["track"])
+            assert int(a.is_test.sum()) == int(held.sum())
+
+
 def test_result_lines_and_measures_match_the_loops():
     rng = np.random.default_rng(3)
     m, n, N = 300, 500, 10

@@ -55,14 +55,20 @@ class Yue(object):
 
         def load(path):
             return FileIO.loadDataSet(path, columns=columns, binarized=binarized, threshold=bottom, delim=delim)
-        if self.config.contains('yue.ingest') and self.config['yue.ingest'] == 'arrays' and not self.evaluation.contains('-cv') \
-                and not binarized:
+        self._array_folds = None
+        if self.config.contains('yue.ingest') and self.config['yue.ingest'] == 'arrays' and not binarized:
             # the log as numbered events, without a Python object per event (yue_b200/ingest.py)
-            from ..ingest import load_numbered
+            from ..ingest import cv_folds, load_numbered
             target = self.evaluation['-target'] if self.evaluation.contains('-target') else 'track'
-            self.trainingData = load_numbered(config['record'], columns, delim, self.evaluation, target)
-            print('preprocessing...')
-            return
+            pure_cv = self.evaluation.contains('-cv') and not any(self.evaluation.contains(o) for o in ('-testSet', '-ap', '-byTime'))
+            if pure_cv:                                 # every fold numbered from the coded columns of ONE read of the file
+                self._array_folds = lambda k: ((log, []) for log in cv_folds(config['record'], columns, delim, k, target))
+            if pure_cv or not self.evaluation.contains('-cv'):
+                if not pure_cv:
+                    self.trainingData = load_numbered(config['record'], columns, delim, self.evaluation, target)
+                print('preprocessing...')
+                return
+            # -cv on top of another split: the dict form below (execute() folds whatever list the split left)
         if self.evaluation.contains('-testSet'):
             self.trainingData = load(config['record'])
             self.testData = load(self.evaluation['-testSet'])
@@ -89,7 +95,8 @@ class Yue(object):
         from ..engine import device_count
         ndev = max(1, device_count())
         procs = []
-        for i, (train, test) in enumerate(DataSplit.crossValidation(self.trainingData, k), 1):
+        folds = self._array_folds(k) if getattr(self, '_array_folds', None) else DataSplit.crossValidation(self.trainingData, k)
+        for i, (train, test) in enumerate(folds, 1):
             p = ctx.Process(target=_run_fold, args=(queue, name, self.config, train, test, '[' + str(i) + ']', i,
                                                     (i - 1) % ndev if parallel else 0))
             p.start()

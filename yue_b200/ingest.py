@@ -244,6 +244,25 @@ def load_numbered(path, columns, delim, evaluation, rec_type='track'):
     return number_events(cols, None, rec_type, order)
 
 
+def cv_folds(path, columns, delim, k, rec_type='track'):
+    """-cv k (tool/dataSplit.py:26-38, yue.py:72-96): fold i holds out the events whose position in the file is i modulo k.
+    Yields one ArrayLog per fold; the file is read once, every fold is numbered on its own (ids by first appearance over
+    ITS training events, then its test events -- what Record does with the two lists the reference hands it)."""
+    if k <= 1 or k > 10:
+        k = 3
+    order = [c for c in columns.keys()]
+    coded = read_coded(path, columns, delim)
+    cols = read_columns(path, columns, delim) if coded is None else None
+    n = len(coded['user'][0]) if coded is not None else len(cols['user'])
+    pos = np.arange(n)
+    for i in range(k):
+        held = pos % k == i
+        if coded is not None:
+            yield number_coded({c: (v[~held], t) for c, (v, t) in coded.items()}, {c: (v[held], t) for c, (v, t) in coded.items()}, rec_type, order)
+        else:
+            yield number_events({c: v[~held] for c, v in cols.items()}, {c: v[held] for c, v in cols.items()}, rec_type, order)
+
+
 class _IdToName(object):
     """id2name[kind][id] over an array."""
 
