@@ -115,3 +115,39 @@ def test_loader_and_splitters(tmp_path):
     assert len(folds) == 5 and folds[1][1] == [1, 6] and len(folds[0][0]) == 8
     tr, te = DataSplit.dataSplit(list(range(1000)), 0.2)
     assert len(tr) + len(te) == 1000 and 120 < len(te) < 280
+
+
+def test_bench_clock_sampler_windows_on_the_timed_region():
+    """bench.py's clock sampler: lines that arrive inside the timed region are the ones reported; a region shorter than a
+    sampling period falls back to everything since the start and says so; throttle reasons are collected by name."""
+    import importlib.util
+    import os
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc(object):
+        def terminate(self):
+            pass
+
+    class FakeThread(object):
+        def join(self, timeout=None):
+            pass
+
+    def sampler(rows, mark_at):
+        c = bench.ClockSampler(0)
+        c.proc, c.thread = FakeProc(), FakeThread()
+        now = time.monotonic()
+        c.rows = [(now + dt, r) for dt, r in rows]
+        c.t_mark = now + mark_at
+        return c
+
+    idle = ["0", "210", "1965", "140", "0x0", "Not Active", "Not Active", "Not Active", "Not Active"]
+    busy = ["0", "1965", "1965", "900", "0x4", "Not Active", "Not Active", "Not Active", "Active"]
+    out = sampler([(-1.0, idle), (-0.5, idle), (-0.02, busy), (-0.01, busy)], mark_at=-0.05).stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+    out = sampler([(-1.0, idle), (-0.5, busy)], mark_at=-0.05).stop()
+    assert out["samples"] == 2 and out["window"].startswith("warm-up + timed region")
+    assert bench.ClockSampler(0).stop()["reasons"] == ["nvidia-smi unavailable"]
