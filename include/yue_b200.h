@@ -276,7 +276,8 @@ int yue_allreduce_q_delta(yue_t* h);   /* pack + ncclAllReduce(sum, fp32) + appl
  * All ranks must use the same hot set in the same slot order:
  *   yue_hot_tracks      the handle's current hot set (chosen from its own log by yue_set_interactions): tracks_out[n_hot]
  *   yue_set_hot_tracks  impose a hot set (tracks[] in slot order, counts[] = plays over ALL ranks, total_events likewise;
- *                       n_hot <= 24; tracks above 1/40 of the events get a second accumulator row); re-labels the events
+ *                       n_hot <= 248 -- the sharded trainer shares every track above 1/4096 of the events, one GPU's own
+ *                       rule keeps the ~10 above 1/128; tracks above 1/40 get a second accumulator row); re-labels the events
  *   yue_hot_table_export / _open   this handle's table as a cudaIpcMemHandle_t (64 bytes) / map a peer's in this process
  *   yue_enable_peer     cudaDeviceEnablePeerAccess from the handle's device to `peer_device` (same-process handles)
  *   yue_hot_share       tables[r] = rank r's table as a device pointer valid in this process (tables[rank] may be NULL);
