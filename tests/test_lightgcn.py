@@ -113,6 +113,42 @@ def test_class_trains_on_the_training_split_in_file_order(golden_dir, tmp_path):
     assert len(eu2) == len(train) and eu2.tolist() == [rec2.data.name2id['user'][e['user']] for e in train]
 
 
+def test_both_ingest_modes_give_the_class_the_same_batches(golden_dir, tmp_path):
+    """-byTime (config/LightGCN.conf): the dict Record and the array ingest (yue.ingest=arrays, ArrayLog with the events' file
+    positions) number users and tracks alike and hand LightGCN the SAME training events in the SAME (file) order."""
+    pytest.importorskip("pyarrow")
+    import io
+    import json
+    import os
+    from contextlib import redirect_stdout
+    from yue_b200 import ingest
+    from yue_b200.host.config import Config, LineConfig
+    from yue_b200.lightgcn import LightGCN
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    events = g["events"][:2500]
+    path = os.path.join(str(tmp_path), "log.txt")
+    with open(path, "w") as f:
+        f.write("".join("%s,%s,%s,%s\n" % (e["time"], e["user"], e["track"], e["artist"]) for e in events))
+    vals = {"record": path, "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,", "recommender": "LightGCN",
+            "evaluation.setup": "-target track -byTime 0.2", "item.ranking": "-topN 5,10", "num.factors": "8", "num.max.iter": "1",
+            "batch_size": "128", "learnRate": "-init 0.002 -max 1", "reg.lambda": "-u 0.001 -i 0.001 -b 0.2 -s 0.2",
+            "output.setup": "on -dir %s/" % tmp_path}
+    columns = dict([("user", 1), ("track", 2), ("artist", 3), ("time", 0)])
+    log = ingest.load_numbered(path, columns, ",", LineConfig(vals["evaluation.setup"]), "track")
+    with redirect_stdout(io.StringIO()):
+        a = LightGCN(Config(values=vals), log, [])
+        b = LightGCN(Config(values=vals), [dict(e) for e in events], [])
+        for mdl in (a, b):
+            mdl.readConfiguration()
+            mdl.initModel()
+    assert (a.m, a.n, a.train_size) == (b.m, b.n, sum(len(v) for v in b.data.userRecord.values()))
+    ua, ia = a._file_order_events()
+    ub, ib = b._file_order_events()
+    assert np.array_equal(ua, ub) and np.array_equal(ia, ib)
+    names = np.asarray(log.names["user"], dtype=object)
+    assert names[ua[:20]].tolist() == [b.data.id2name["user"][int(x)] for x in ub[:20]]
+
+
 @pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 def test_dropin_shim_on_top_of_the_reference_tree(golden_dir, tmp_path):
     """dropin/recommender/advanced/LightGCN.py shadows the reference's module (TF-1, unimportable base), derives from the
