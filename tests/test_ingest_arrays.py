@@ -179,6 +179,52 @@ def test_cv_folds_equal_the_reference_split_numbered_fold_by_fold(golden_dir, tm
             assert int(a.is_test.sum()) == int(held.sum())
 
 
+@pytest.mark.parametrize("ev", ["-target track -ap 0.2 -cold 3", "-target track -ap 0.2 -sample", "-target track -ap 0.2 -cold 5 -sample"])
+def test_cold_and_sample_edit_the_test_csr_like_the_dict_form(golden_dir, ev):
+    """base/recommender.py:22-49 (-cold t, -sample) on the CSR form of the test set (ingest.filter_test_rows) against the
+    dict form the Recommender base class edits -- and, in the build container, against the REFERENCE's own base class."""
+    from yue_b200.host.recommender import Recommender
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    train = [e for e, h in zip(g["events"], g["held"]) if not h]
+    test = [e for e, h in zip(g["events"], g["held"]) if h]
+    vals = {"record": "./dataset/log.txt", "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,", "recommender": "BPR",
+            "evaluation.setup": ev, "item.ranking": "-topN 5,10", "num.factors": "8", "num.max.iter": "1",
+            "learnRate": "-init 0.02 -max 0.1", "reg.lambda": "-u 0.01 -i 0.01 -b 0.01 -s 0.2", "output.setup": "off"}
+    with redirect_stdout(io.StringIO()):
+        ref = Recommender(Config(values=vals), train, test)
+    want = {u: sorted(t) for u, t in ref.data.testSet.items()}
+    if os.path.isdir("/root/reference"):                         # the reference's own base class says the same
+        import subprocess
+        import sys
+        code = ("import sys, json, io\nfrom contextlib import redirect_stdout\nsys.path.insert(0, '/root/reference')\n"
+                "from tool.config import Config\nfrom base.recommender import Recommender\n"
+                "g = json.load(open(%r))\ntrain = [e for e, h in zip(g['events'], g['held']) if not h]\n"
+                "test = [e for e, h in zip(g['events'], g['held']) if h]\nopen(%r, 'w').write(%r)\n"
+                "with redirect_stdout(io.StringIO()):\n    r = Recommender(Config(%r), train, test)\n"
+                "print(json.dumps({u: sorted(t) for u, t in r.data.testSet.items()}))\n"
+                % (os.path.join(golden_dir, "record_small.json"), "/tmp/_yue_cold.conf",
+                   "\n".join(k + "=" + v for k, v in vals.items()), "/tmp/_yue_cold.conf"))
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr
+        assert json.loads(res.stdout.strip().splitlines()[-1]) == want
+    # the array form: numbered events -> the test CSR K0 would build (unique held-out pairs minus training pairs) -> the edits
+    cols = {k: np.array([e[k] for e in train + test], dtype=object) for k in ("user", "track", "artist")}
+    nt = len(train)
+    log = ingest.number_events({k: v[:nt] for k, v in cols.items()}, {k: v[nt:] for k, v in cols.items()}, "track", ["user", "track", "artist"])
+    tr = log.is_test == 0
+    tr_key = np.unique(log.ev_user[tr].astype(np.int64) * log.n + log.ev_item[tr])
+    te_key = np.unique(log.ev_user[~tr].astype(np.int64) * log.n + log.ev_item[~tr])
+    te_key = te_key[~np.isin(te_key, tr_key)]
+    indptr = np.zeros(log.m + 1, np.int64)
+    np.cumsum(np.bincount(te_key // log.n, minlength=log.m), out=indptr[1:])
+    items = (te_key % log.n).astype(np.int32)
+    line = LineConfig(ev)
+    ip, it = ingest.filter_test_rows(log, indptr, items, cold=int(line["-cold"]) if line.contains("-cold") else None, sample=line.contains("-sample"))
+    un, tn = log.names["user"], log.names["track"]
+    got = {un[u]: sorted(tn[t] for t in it[ip[u]:ip[u + 1]]) for u in np.flatnonzero(np.diff(ip) > 0)}
+    assert got == want and 0 < len(got) < len(np.flatnonzero(np.diff(indptr) > 0)) + (0 if "-sample" in ev else 1)
+
+
 def test_result_lines_and_measures_match_the_loops():
     rng = np.random.default_rng(3)
     m, n, N = 300, 500, 10

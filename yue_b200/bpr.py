@@ -70,6 +70,13 @@ class GpuBPRMixin(object):
             if hasattr(self.data, 'log'):                       # yue.ingest=arrays (ingest.ArrayRecord): numbered events -> K0
                 self.data.log.upload(self._engine)
                 self.data.test_indptr, self.data.test_items = self._engine.get_test_set()
+                ev = LineConfig(self.config['evaluation.setup'])
+                if ev.contains('-cold') or ev.contains('-sample'):         # base/recommender.py:22-49 on the CSR form
+                    from .ingest import filter_test_rows
+                    self.data.test_indptr, self.data.test_items = filter_test_rows(
+                        self.data.log, self.data.test_indptr, self.data.test_items,
+                        cold=int(ev['-cold']) if ev.contains('-cold') else None, sample=ev.contains('-sample'))
+                    self._engine.set_test_set(self.data.test_indptr, self.data.test_items)
                 self._test_on_device = True
                 self._synced = (None, None)
                 return self._engine

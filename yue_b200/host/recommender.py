@@ -25,8 +25,8 @@ class Recommender(object):
         self.evalConfig = LineConfig(self.config['evaluation.setup'])
         self.recType = self.evalConfig['-target'] if self.evalConfig.contains('-target') else 'track'
         self.measure = []
-        if arrays and (self.evalConfig.contains('-cold') or self.evalConfig.contains('-sample')):
-            raise NotImplementedError('-cold / -sample edit the dict form of the test set: not available with yue.ingest=arrays')
+        if arrays:
+            return                                             # -cold / -sample: ingest.filter_test_rows, when the test CSR exists
         if self.evalConfig.contains('-cold'):
             # keep only held-out tracks with at most `threshold` training plays (recommender.py:22-42)
             threshold = int(self.evalConfig['-cold'])

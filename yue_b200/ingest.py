@@ -263,6 +263,39 @@ def cv_folds(path, columns, delim, k, rec_type='track'):
             yield number_events({c: v[~held] for c, v in cols.items()}, {c: v[held] for c, v in cols.items()}, rec_type, order)
 
 
+def filter_test_rows(log, test_indptr, test_items, cold=None, sample=False):
+    """The two edits base/recommender.py:22-49 makes to the test set, on the CSR form (rows = users, sorted unique held-out
+    tracks that are not training plays of the user -- what K0 / Record leave):
+      -cold t   a held-out track with more than t TRAINING events is dropped, for users that have training events
+                (recommender.py:22-42: len(trackRecord[item]) > threshold, user in userRecord); users left empty go;
+      -sample   of the remaining test users, in the order in which they first appear among the test EVENTS (the key order of
+                Record's testSet), the first int(0.9 * count) are dropped (45-49).
+    Returns the new (test_indptr, test_items)."""
+    test_indptr = np.asarray(test_indptr, dtype=np.int64)
+    test_items = np.asarray(test_items, dtype=np.int32)
+    m = len(test_indptr) - 1
+    owner = np.repeat(np.arange(m, dtype=np.int64), np.diff(test_indptr))
+    keep = np.ones(len(test_items), dtype=bool)
+    train = log.is_test == 0
+    if cold is not None and log.rec_type == 'track':               # trackRecord is keyed by TRACK names whatever the target
+        plays = np.bincount(log.ev_item[train], minlength=log.n)
+        has_train = np.bincount(log.ev_user[train], minlength=m) > 0
+        keep &= ~(has_train[owner] & (plays[test_items] > int(cold)))
+    if sample:
+        left = np.bincount(owner[keep], minlength=m) > 0                 # users that still have a test row
+        tu = log.ev_user[~train]
+        first = np.full(m, len(tu), dtype=np.int64)
+        first[tu[::-1]] = np.arange(len(tu) - 1, -1, -1, dtype=np.int64)
+        users = np.flatnonzero(left)
+        users = users[np.argsort(first[users], kind='stable')]          # Record's testSet key order
+        dropped = np.zeros(m, dtype=bool)
+        dropped[users[:int(len(users) * 0.9)]] = True
+        keep &= ~dropped[owner]
+    out_indptr = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(np.bincount(owner[keep], minlength=m), out=out_indptr[1:])
+    return out_indptr, np.ascontiguousarray(test_items[keep])
+
+
 class _IdToName(object):
     """id2name[kind][id] over an array."""
 
