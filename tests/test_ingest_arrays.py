@@ -275,10 +275,12 @@ def test_result_lines_and_measures_match_the_loops():
 
 
 @pytest.mark.gpu
-def test_class_api_with_array_ingest_equals_the_dict_path(tmp_path):
+@pytest.mark.parametrize("ev", ["-target track -ap 0.2", "-target track -byTime 0.2 -sample"])
+def test_class_api_with_array_ingest_equals_the_dict_path(tmp_path, ev):
     """Yue -> BPR.execute() with yue.ingest=arrays (C parser, column-wise ids, K0 on the device, array result lines) against
-    the default path (lists of dicts, Record, Python loops): same split (same `random` seed), same initial tables, same
-    sampler seed, serial order -> the same tables bit for bit, the same measures and the same result lines."""
+    the default path (lists of dicts, Record, Python loops): same split (same `random` seed; or config/WRMF.conf's -byTime
+    with -sample), same initial tables, same sampler seed, serial order -> the same tables bit for bit, the same measures
+    and the same result lines."""
     from yue_b200 import synth
     from yue_b200.bpr import BPR
     from yue_b200.host.driver import Yue
@@ -287,7 +289,7 @@ def test_class_api_with_array_ingest_equals_the_dict_path(tmp_path):
     out = {}
     for name in ("dicts", "arrays"):
         vals = {"record": str(log_path), "record.setup": "-columns user:1,track:2,artist:3,time:0 -delim ,", "recommender": "BPR",
-                "evaluation.setup": "-target track -ap 0.2", "item.ranking": "-topN 5,10", "num.factors": "10", "num.max.iter": "2",
+                "evaluation.setup": ev, "item.ranking": "-topN 5,10", "num.factors": "10", "num.max.iter": "2",
                 "learnRate": "-init 0.02 -max 1", "reg.lambda": "-u 0.01 -i 0.01 -b 0.2 -s 0.2", "output.setup": "on -dir %s/" % (tmp_path / name),
                 "yue.sgd": "serial", "yue.seed": "77"}
         if name == "arrays":
