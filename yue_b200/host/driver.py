@@ -56,7 +56,8 @@ class Yue(object):
         def load(path):
             return FileIO.loadDataSet(path, columns=columns, binarized=binarized, threshold=bottom, delim=delim)
         self._array_folds = None
-        if self.config.contains('yue.ingest') and self.config['yue.ingest'] == 'arrays' and not binarized:
+        if self.config.contains('yue.ingest') and self.config['yue.ingest'] == 'arrays':
+            # (-b only rewrites the value of a `play` field, tool/file.py:40-44; no model on this path reads that field)
             # the log as numbered events, without a Python object per event (yue_b200/ingest.py)
             from ..ingest import cv_folds, load_numbered
             target = self.evaluation['-target'] if self.evaluation.contains('-target') else 'track'
