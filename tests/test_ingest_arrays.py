@@ -225,6 +225,26 @@ def test_cold_and_sample_edit_the_test_csr_like_the_dict_form(golden_dir, ev):
     assert got == want and 0 < len(got) < len(np.flatnonzero(np.diff(indptr) > 0)) + (0 if "-sample" in ev else 1)
 
 
+def test_coded_test_set_file_equals_the_object_path(golden_dir, tmp_path):
+    """-testSet file: the log and the test file are read by the coded reader into ONE names table per column, then numbered
+    like the object path (training events first, the test file's events extend the maps: data/record.py:138-146, 182-188)."""
+    pytest.importorskip("pyarrow")
+    g = json.load(open(os.path.join(golden_dir, "record_small.json")))
+    train = [e for e, h in zip(g["events"], g["held"]) if not h]
+    test = [e for e, h in zip(g["events"], g["held"]) if h]
+    p_train, p_test = str(tmp_path / "train.txt"), str(tmp_path / "test.txt")
+    _write_csv(p_train, train)
+    _write_csv(p_test, test)
+    ev = LineConfig("-target track -testSet " + p_test)
+    a = ingest.load_numbered(p_train, COLUMNS, ",", ev, "track")
+    b = ingest.number_events(ingest.read_columns(p_train, COLUMNS, ","), ingest.read_columns(p_test, COLUMNS, ","), "track", list(COLUMNS))
+    both = ingest.read_coded([p_train, p_test], COLUMNS, ",")
+    assert len(both) == 2 and both[0]["user"][1] is both[1]["user"][1] and len(both[1]["user"][0]) == len(test)
+    assert np.array_equal(a.ev_user, b.ev_user) and np.array_equal(a.ev_item, b.ev_item) and np.array_equal(a.is_test, b.is_test)
+    for kind in ("user", "track", "artist"):
+        assert list(a.names[kind]) == list(b.names[kind])
+
+
 def test_result_lines_and_measures_match_the_loops():
     rng = np.random.default_rng(3)
     m, n, N = 300, 500, 10

@@ -149,7 +149,8 @@ def read_coded(path, columns, delim, want_time=False):
     """The non-time columns of a log file as (codes int32[events], names[array of str]) per column WITHOUT creating a Python
     string per field: Arrow's multi-threaded CSV reader + dictionary encoding (codes in order of first appearance in the
     file).  None when that reader cannot take the file (a regex delimiter, pyarrow missing): the caller falls back to
-    read_columns.  want_time: out['time'] is the time column as ONE Arrow string array (by_time_coded sorts it)."""
+    read_columns.  want_time: out['time'] is the time column as ONE Arrow string array (by_time_coded sorts it).
+    `path` may be a list of files (-testSet: the log and the test file): one result per file, the names tables shared."""
     if len(delim) != 1 or (want_time and 'time' not in columns):
         return None
     try:
@@ -157,6 +158,7 @@ def read_coded(path, columns, delim, want_time=False):
         import pyarrow.csv as pc
     except ImportError:
         return None
+    paths = [path] if isinstance(path, str) else list(path)
     used = sorted(set(int(v) for k, v in columns.items() if k != 'time'))
     # The columns are converted to dictionary type BY THE READER: every 8 MB block is parsed and encoded on its own thread
     # (encoding the finished columns afterwards is one thread per column: 1.0 s of the 2.4 s a 5 M-event file took), the
@@ -167,20 +169,27 @@ def read_coded(path, columns, delim, want_time=False):
         if int(columns['time']) in used:                           # the time field doubles as another column: object path
             return None
         types['f%d' % int(columns['time'])] = pa.string()
-    tbl = pc.read_csv(path, read_options=pc.ReadOptions(autogenerate_column_names=True, block_size=8 << 20),
-                      parse_options=pc.ParseOptions(delimiter=delim, quote_char=False),
-                      convert_options=pc.ConvertOptions(include_columns=sorted(types), column_types=types, strings_can_be_null=False))
-    out = {}
+    tables = [pc.read_csv(p, read_options=pc.ReadOptions(autogenerate_column_names=True, block_size=8 << 20),
+                          parse_options=pc.ParseOptions(delimiter=delim, quote_char=False),
+                          convert_options=pc.ConvertOptions(include_columns=sorted(types), column_types=types, strings_can_be_null=False))
+              for p in paths]
+    tbl = tables[0] if len(tables) == 1 else pa.concat_tables(tables)
+    bounds = np.cumsum([0] + [t.num_rows for t in tables])
+    outs = [{} for _ in paths]
     if want_time:
-        out['time'] = tbl['f%d' % int(columns['time'])].combine_chunks()
+        tm = tbl['f%d' % int(columns['time'])].combine_chunks()
+        for k, o in enumerate(outs):
+            o['time'] = tm.slice(int(bounds[k]), int(bounds[k + 1] - bounds[k]))
     for name, ind in columns.items():
         if name == 'time':
             continue
         d = tbl['f%d' % int(ind)].unify_dictionaries().combine_chunks()
         idx = d.indices                                            # int32, no nulls: read the buffer directly (to_numpy() pulls in pandas)
         codes = np.frombuffer(idx.buffers()[1], dtype=np.int32, count=len(idx), offset=idx.offset * 4).copy()
-        out[name] = (codes, np.asarray(d.dictionary.to_pylist(), dtype=object))
-    return out
+        names = np.asarray(d.dictionary.to_pylist(), dtype=object)
+        for k, o in enumerate(outs):
+            o[name] = (codes[bounds[k]:bounds[k + 1]], names)
+    return outs[0] if isinstance(path, str) else outs
 
 
 def number_coded(train, test, rec_type='track', key_order=None):
@@ -222,6 +231,10 @@ def load_numbered(path, columns, delim, evaluation, rec_type='track'):
             return number_coded({k: (c[~held], t) for k, (c, t) in coded.items()}, {k: (c[held], t) for k, (c, t) in coded.items()}, rec_type, order)
         if coded is not None and not evaluation.contains('-testSet'):
             return number_coded(coded, None, rec_type, order)
+        if coded is not None:                                       # -testSet file: one names table per column over both files
+            both = read_coded([path, evaluation['-testSet']], columns, delim)
+            if both is not None:
+                return number_coded(both[0], both[1], rec_type, order)
     elif not evaluation.contains('-testSet') and not evaluation.contains('-ap'):
         coded = read_coded(path, columns, delim, want_time=True)   # config/BPR.conf's own split
         if coded is not None:
